@@ -1,0 +1,201 @@
+"""Oracle: per-road class vote, tags, confusion counts and class-balanced F1.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Restates
+  scripts/road_segmentation/determine_class.py:122-190   determine_detected_class
+  scripts/road_segmentation/final_metrics.py:22-89       get_metrics
+  scripts/road_segmentation/final_metrics.py:91-105      get_tag
+  scripts/road_segmentation/final_metrics.py:277-316     threshold sweep
+Pinned: the table functions are checked against the reference's own code executed
+with geopandas/plotly stubbed (tests/golden/vote_*.json, tests/golden/metrics.json).
+
+The raster restatement (below table a14) is this project's
+definition, not reference code: detections arrive as a class plane (0 none,
+1 artificial, 2 natural) and a uint8 score plane; each road accumulates the joint
+histogram h[k][s] of (class, score) over its pixels.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+CLASSES = ["artificial", "natural"]
+COVER = ["artificial", "natural", "undetermined", "undetected"]   # codes 0..3
+THRESHOLDS = np.arange(0, 1.0, 0.05)                               # final_metrics.py:277
+
+
+# ----------------------------------------------------------------------------
+# vector form -- reference-shaped
+# ----------------------------------------------------------------------------
+def determine_detected_class(predictions: pd.DataFrame, roads: pd.DataFrame, threshold=0) -> pd.DataFrame:
+    """predictions: OBJECTID, score, det_class_name, weighted_score, area_pred_in_label."""
+    valid = predictions[predictions["score"] >= threshold]
+    seen = set(valid["OBJECTID"].unique().tolist())
+    rec = {"road_id": [], "cover_type": [], "nat_score": [], "art_score": [], "diff_score": []}
+    for rid in roads["OBJECTID"].unique().tolist():
+        rec["road_id"].append(rid)
+        if rid not in seen:
+            rec["cover_type"].append("undetected")
+            rec["nat_score"].append(0)
+            rec["art_score"].append(0)
+            rec["diff_score"].append(0)
+            continue
+        sums = valid[valid["OBJECTID"] == rid].groupby("det_class_name")[["weighted_score", "area_pred_in_label"]].sum()
+        idx = {}
+        for k in ("natural", "artificial"):
+            if k in sums.index and sums.loc[k, "weighted_score"] != 0:
+                idx[k] = sums.loc[k, "weighted_score"] / sums.loc[k, "area_pred_in_label"]
+            else:
+                idx[k] = 0
+        a, n = idx["artificial"], idx["natural"]
+        if a == n:
+            rec["cover_type"].append("undetermined")
+            rec["diff_score"].append(0)
+        else:
+            rec["cover_type"].append("artificial" if a > n else "natural")
+            rec["diff_score"].append(abs(a - n))
+        rec["art_score"].append(round(a, 3))
+        rec["nat_score"].append(round(n, 3))
+    keep = ["OBJECTID"] + [c for c in ("CATEGORY", "gt_type") if c in roads.columns and "gt_type" in roads.columns]
+    return pd.DataFrame(rec).merge(roads[keep], how="inner", left_on="road_id", right_on="OBJECTID")
+
+
+def get_tag(cover_type: str, category: str) -> str:
+    if cover_type in ("undetermined", "undetected"):
+        return "FN"
+    return "TP" if cover_type == category else "wrong class"
+
+
+def get_metrics(comparison_df: pd.DataFrame, classes: Sequence[str] = CLASSES):
+    rows = []
+    for k in classes:
+        is_k = comparison_df["CATEGORY"] == k
+        tp = int(((comparison_df["tag"] == "TP") & is_k).sum())
+        fp = int(((comparison_df["tag"] == "wrong class") & (comparison_df["cover_type"] == k)).sum())
+        fn = int(((comparison_df["tag"] == "FN") & is_k).sum()) + int(((comparison_df["tag"] == "wrong class") & is_k).sum())
+        if tp == 0:
+            pk = rk = f1k = 0
+        else:
+            pk = tp / (tp + fp)
+            rk = tp / (tp + fn)
+            f1k = 2 * pk * rk / (pk + rk)
+        rows.append({"cover_class": k, "TP": tp, "FP": fp, "FN": fn, "Pk": pk, "Rk": rk, "f1k": f1k, "count": int(is_k.sum())})
+    by_class = pd.DataFrame(rows)
+    return by_class, global_from_by_class(by_class)
+
+
+def global_from_by_class(by_class: pd.DataFrame) -> pd.DataFrame:
+    total = by_class["count"].sum()
+    pw = (by_class["Pk"] * by_class["count"]).sum() / total
+    rw = (by_class["Rk"] * by_class["count"]).sum() / total
+    f1w = 0 if (pw == 0 and rw == 0) else 2 * pw * rw / (pw + rw)
+    pb = by_class["Pk"].sum() / 2          # literal 2 (final_metrics.py:78-79)
+    rb = by_class["Rk"].sum() / 2
+    f1b = 0 if (pb == 0 and rb == 0) else 2 * pb * rb / (pb + rb)
+    return pd.DataFrame({"Pw": [pw], "Rw": [rw], "f1w": [f1w], "Pb": [pb], "Rb": [rb], "f1b": [f1b]})
+
+
+# ----------------------------------------------------------------------------
+# raster form
+# ----------------------------------------------------------------------------
+def score_cutoffs(thresholds: Sequence[float] = THRESHOLDS) -> np.ndarray:
+    """Smallest uint8 score s with s/255.0 >= thr, per threshold (256 if none)."""
+    s = np.arange(256) / 255.0
+    return np.array([int(np.argmax(s >= t)) if (s >= t).any() else 256 for t in thresholds], np.int32)
+
+
+def raster_vote(joint_hist: np.ndarray, cutoff: int, rule: str = "count", min_area_frac: float = 0.0):
+    """joint_hist (R, 3, 256) = h[k][s]; returns (cover_code (R,), art_score, nat_score, diff_score).
+
+    rule 'count'  (north star): argmax of pixel counts n_k = sum_{s>=cutoff} h_k[s]
+    rule 'score'  (reference-shaped, determine_class.py:149-176): compare the mean scores
+                  S_k/(255 n_k), S_k = sum s*h_k[s]; exact through S_a*n_n vs S_n*n_a.
+    Classes whose area fraction round(n_k/n_inside, 2) <= min_area_frac are ignored
+    (per-class stand-in for determine_class.py:118, which filters per detection).
+    """
+    h = np.asarray(joint_hist, np.int64)
+    R = h.shape[0]
+    s = np.arange(256, dtype=np.int64)
+    sel = s >= cutoff
+    n = (h[:, :, sel]).sum(axis=2)                      # (R, 3)
+    S = (h[:, :, sel] * s[sel]).sum(axis=2)
+    n_inside = h.sum(axis=(1, 2))
+    if min_area_frac > 0:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            frac = np.round(n / np.maximum(n_inside, 1)[:, None], 2)
+        drop = frac <= min_area_frac
+        n = np.where(drop, 0, n)
+        S = np.where(drop, 0, S)
+    na, nn = n[:, 1], n[:, 2]
+    Sa, Sn = S[:, 1], S[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ia = np.where((na > 0) & (Sa > 0), Sa / (255.0 * np.maximum(na, 1)), 0.0)
+        inn = np.where((nn > 0) & (Sn > 0), Sn / (255.0 * np.maximum(nn, 1)), 0.0)
+    if rule == "count":
+        left, right = na, nn
+    elif rule == "score":
+        left, right = Sa * np.maximum(nn, 1) * (na > 0), Sn * np.maximum(na, 1) * (nn > 0)
+    else:
+        raise ValueError(rule)
+    cover = np.full(R, 2, np.int32)
+    cover[left > right] = 0
+    cover[left < right] = 1
+    cover[(na + nn) == 0] = 3
+    diff = np.abs(ia - inn)
+    return cover, ia, inn, diff
+
+
+def confusion(cover: np.ndarray, gt: np.ndarray) -> np.ndarray:
+    """(2, 4) counts: rows gt class (0 artificial, 1 natural), columns COVER codes."""
+    m = np.zeros((2, 4), np.int64)
+    np.add.at(m, (np.asarray(gt), np.asarray(cover)), 1)
+    return m
+
+
+def metrics_from_confusion(m: np.ndarray) -> Dict[str, float]:
+    """final_metrics.get_metrics from the confusion counts."""
+    out: Dict[str, float] = {}
+    P, Rr, cnt = [], [], []
+    for k in (0, 1):
+        tp = int(m[k, k])
+        fp = int(m[1 - k, k])
+        fn = int(m[k, 2] + m[k, 3] + m[k, 1 - k])
+        if tp == 0:
+            pk = rk = f1k = 0.0
+        else:
+            pk = tp / (tp + fp)
+            rk = tp / (tp + fn)
+            f1k = 2 * pk * rk / (pk + rk)
+        out.update({f"TP_{k}": tp, f"FP_{k}": fp, f"FN_{k}": fn, f"P_{k}": pk, f"R_{k}": rk, f"f1_{k}": f1k})
+        P.append(pk)
+        Rr.append(rk)
+        cnt.append(int(m[k].sum()))
+    total = sum(cnt)
+    pw = (P[0] * cnt[0] + P[1] * cnt[1]) / total if total else float("nan")
+    rw = (Rr[0] * cnt[0] + Rr[1] * cnt[1]) / total if total else float("nan")
+    out["Pw"], out["Rw"] = pw, rw
+    out["f1w"] = 0.0 if (pw == 0 and rw == 0) else 2 * pw * rw / (pw + rw)
+    pb, rb = (P[0] + P[1]) / 2, (Rr[0] + Rr[1]) / 2
+    out["Pb"], out["Rb"] = pb, rb
+    out["f1b"] = 0.0 if (pb == 0 and rb == 0) else 2 * pb * rb / (pb + rb)
+    return out
+
+
+def sweep(joint_hist: np.ndarray, gt: np.ndarray, thresholds: Sequence[float] = THRESHOLDS, rule: str = "count",
+          min_area_frac: float = 0.0):
+    """final_metrics.py:277-316 on raster accumulators: per threshold the confusion counts
+    and metrics; best = max f1b, ties broken by larger Pb, first threshold wins otherwise."""
+    cuts = score_cutoffs(thresholds)
+    rows = []
+    best = None
+    for i, (t, c) in enumerate(zip(thresholds, cuts)):
+        cover, *_ = raster_vote(joint_hist, int(c), rule, min_area_frac)
+        m = confusion(cover, gt)
+        met = metrics_from_confusion(m)
+        met["threshold"] = float(t)
+        met["confusion"] = m
+        rows.append(met)
+        if i == 0 or met["f1b"] > best[1] or (met["f1b"] == best[1] and met["Pb"] > best[2]):
+            best = (i, met["f1b"], met["Pb"])
+    return rows, best[0]

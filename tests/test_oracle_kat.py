@@ -1,0 +1,142 @@
+"""Hand-derived known-answer tests for the oracle rasterizer (the reference ships none).
+
+Each expected mask below was worked out by hand from the GDAL 3.0.x fill rule
+(SURVEY.md A.1): scanline through pixel centres, an edge is active for
+y_low <= cy < y_high, crossings are rounded floor(x+0.5) BEFORE sorting, pixels
+xs..xe-1 between paired crossings are burnt, horizontal edges lying exactly on a
+scanline are burnt separately only when they run towards -x.
+"""
+import numpy as np
+import pytest
+
+from oracle import cport, gdal_fill
+
+IMPLS = [("py", gdal_fill.rasterize), ("c", cport.rasterize)]
+
+
+def ring(*pts):
+    pts = list(pts)
+    if pts[0] != pts[-1]:
+        pts.append(pts[0])
+    return np.array(pts, np.float64)
+
+
+def pix(mask):
+    ys, xs = np.nonzero(mask)
+    return sorted(zip(ys.tolist(), xs.tolist()))
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_integer_rectangle(name, rast):
+    m = rast([ring((2, 1), (6, 1), (6, 4), (2, 4))], (8, 8))
+    assert pix(m) == [(y, x) for y in (1, 2, 3) for x in (2, 3, 4, 5)]
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_rectangle_on_pixel_centres_orientation_matters(name, rast):
+    # edges exactly through pixel centres: xa < cx <= xb keeps columns 2..4;
+    # y_low <= cy < y_high keeps rows 1,2; the far horizontal edge (y = 3.5) lies on
+    # scanline 3 and is burnt only if it runs towards -x.
+    a = rast([ring((1.5, 1.5), (4.5, 1.5), (4.5, 3.5), (1.5, 3.5))], (6, 8))
+    assert pix(a) == [(y, x) for y in (1, 2, 3) for x in (2, 3, 4)]
+    b = rast([ring((1.5, 1.5), (1.5, 3.5), (4.5, 3.5), (4.5, 1.5))], (6, 8))
+    assert pix(b) == [(y, x) for y in (1, 2) for x in (2, 3, 4)]
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_triangle_vertex_on_scanline_counted_once(name, rast):
+    m = rast([ring((1, 0), (7, 0), (4, 2.5))], (4, 8))
+    assert pix(m) == [(0, 2), (0, 3), (0, 4), (0, 5), (1, 3), (1, 4)]
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_hole(name, rast):
+    m = rast([ring((0, 0), (10, 0), (10, 10), (0, 10)), ring((3, 3), (3, 7), (7, 7), (7, 3))], (10, 10))
+    exp = np.ones((10, 10), np.uint8)
+    exp[3:7, 3:7] = 0
+    assert np.array_equal(m, exp)
+    assert m.sum() == 84
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_overlapping_parts_cancel_even_odd(name, rast):
+    m = rast([ring((0, 0), (6, 0), (6, 4), (0, 4)), ring((4, 0), (10, 0), (10, 4), (4, 4))], (4, 10))
+    exp = np.ones((4, 10), np.uint8)
+    exp[:, 4:6] = 0
+    assert np.array_equal(m, exp)
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_partly_and_fully_outside(name, rast):
+    m = rast([ring((-5, -5), (3, -5), (3, 2), (-5, 2))], (8, 8))
+    assert pix(m) == [(y, x) for y in (0, 1) for x in (0, 1, 2)]
+    assert rast([ring((20, 20), (30, 20), (30, 30), (20, 30))], (8, 8)).sum() == 0
+    assert rast([ring((-20, 1), (-10, 1), (-10, 5), (-20, 5))], (8, 8)).sum() == 0
+    m = rast([ring((-100, -100), (100, -100), (100, 100), (-100, 100))], (8, 8))
+    assert m.sum() == 64
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_slivers(name, rast):
+    # both crossings round to 3 -> empty span
+    assert rast([ring((2.6, 0), (2.9, 0), (2.9, 5), (2.6, 5))], (5, 8)).sum() == 0
+    # crossings round to 2 and 3 -> exactly column 2 (centre 2.5 in (2.4, 2.6])
+    m = rast([ring((2.4, 0), (2.6, 0), (2.6, 5), (2.4, 5))], (5, 8))
+    assert pix(m) == [(y, 2) for y in range(5)]
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_transform_north_up(name, rast):
+    # 2 m pixels, origin (100, 200), north-up: world rect x 104..112, y 190..196
+    # -> pixel cols 2..6, rows 2..5
+    t = (2.0, 0.0, 100.0, 0.0, -2.0, 200.0)
+    m = rast([ring((104, 190), (112, 190), (112, 196), (104, 196))], (8, 8), t)
+    assert pix(m) == [(y, x) for y in (2, 3, 4) for x in (2, 3, 4, 5)]
+
+
+def test_unclosed_ring_is_closed_by_wraparound_edge():
+    closed = ring((1, 1), (6, 1), (6, 5), (1, 5))
+    for _, rast in IMPLS:
+        assert np.array_equal(rast([closed], (8, 8)), rast([closed[:-1]], (8, 8)))
+
+
+def test_geometry_window_and_crop_equivalence():
+    t = (0.5, 0.0, 1000.0, 0.0, -0.5, 5000.0)      # 16x16 px raster covers x 1000..1008, y 4992..5000
+    rings = [ring((1001.2, 4995.1), (1005.7, 4995.1), (1005.7, 4998.9), (1001.2, 4998.9))]
+    # pixel space: cols 2.4..11.4 -> 2..12 ; rows 2.2..9.8 -> 2..10
+    assert gdal_fill.geometry_window(t, rings, 16, 16) == (2, 2, 10, 8)
+    assert cport.geometry_window(t, rings, 16, 16) == (2, 2, 10, 8)
+    # partly outside: clipped to the raster
+    rings2 = [ring((990.0, 4990.0), (1002.0, 4990.0), (1002.0, 4997.0), (990.0, 4997.0))]
+    assert gdal_fill.geometry_window(t, rings2, 16, 16) == (0, 6, 4, 10)
+    assert cport.geometry_window(t, rings2, 16, 16) == (0, 6, 4, 10)
+    # touching only: WindowError in rasterio
+    rings3 = [ring((1008.0, 4990.0), (1010.0, 4990.0), (1010.0, 4997.0), (1008.0, 4997.0))]
+    assert gdal_fill.geometry_window(t, rings3, 16, 16) is None
+    assert cport.geometry_window(t, rings3, 16, 16) is None
+    inside, win = gdal_fill.raster_geometry_mask(t, rings, 16, 16)
+    full = gdal_fill.rasterize(rings, (16, 16), t)
+    c0, r0, w, h = win
+    assert np.array_equal(full[r0:r0 + h, c0:c0 + w], inside)
+    assert full.sum() == inside.sum()
+    assert np.array_equal(cport.pair_mask_full(t, rings, 16, 16), full)
+
+
+def _random_polygon(rng, W, H, n):
+    ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+    rad = rng.uniform(0.2, 1.0, n) * min(W, H) * 0.6
+    cx, cy = rng.uniform(-0.2 * W, 1.2 * W), rng.uniform(-0.2 * H, 1.2 * H)
+    pts = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], 1)
+    if rng.random() < 0.3:   # snap to the half-pixel lattice: exercises ties and horizontal edges
+        pts = np.round(pts * 2) / 2
+    return np.concatenate([pts, pts[:1]])
+
+
+def test_python_and_c_oracles_agree_on_random_polygons():
+    rng = np.random.default_rng(20261018)
+    for i in range(300):
+        W, H = int(rng.integers(4, 48)), int(rng.integers(4, 48))
+        rings = [_random_polygon(rng, W, H, int(rng.integers(3, 12))) for _ in range(int(rng.integers(1, 4)))]
+        a = gdal_fill.rasterize(rings, (H, W))
+        b = cport.rasterize(rings, (H, W))
+        assert np.array_equal(a, b), i
