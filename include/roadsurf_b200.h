@@ -1,0 +1,201 @@
+/*
+ * roadsurf_b200 -- C ABI of the B200-native raster-vector overlay hot path of proj-roadsurf.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  The
+ * reference has no FFI (it is Python calling rasterio/GDAL, rasterstats, pandas and
+ * geopandas); each entry point below names the reference call it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - every function returns an int status (RS_OK == 0, negative = error); nothing throws;
+ *  - "_dev" entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t passed as
+ *    void*, NULL = default stream) and return without synchronising; kernel-side failures
+ *    (capacity overflow ...) are latched in the context and read with rs_ctx_sync_status();
+ *  - "_host" entry points take HOST pointers, do their own host<->device copies and return
+ *    after the results are in the host buffers;
+ *  - the caller owns every input and output buffer; the library only owns its context.
+ *
+ * Geometry layout (all entry points): a "road" is a (Multi)Polygon flattened to rings,
+ *   xy            double[n_verts][2]   ring vertices in tile CRS, rings stored as given
+ *                                      (GeoJSON rings are closed: last == first)
+ *   ring_off      int32[n_rings+1]     vertex offset of each ring
+ *   road_ring_off int32[n_roads+1]     ring offset of each road (exterior + holes of every part)
+ *   road_bbox     double[n_roads][4]   xmin, ymin, xmax, ymax over the road's vertices
+ * Tiles: pixels [n_tiles][height][width][channels], pixel-interleaved; gt double[n_tiles][6]
+ * = affine (a, b, c, d, e, f) with x = a*col + b*row + c, y = d*col + e*row + f (rasterio
+ * order); only north-up transforms (b == d == 0) are on the hot path.
+ * Pairs: road-major CSR -- road_pair_off int32[n_roads+1], pair_tile int32[n_pairs]: the
+ * tiles each road is masked against (reference: gpd.sjoin result consumed by the double loop
+ * scripts/statistical_analysis/statistical_analysis.py:170-171,180-193).
+ */
+#ifndef ROADSURF_B200_H
+#define ROADSURF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_VERSION 100
+
+enum rs_status {
+    RS_OK = 0,
+    RS_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, misaligned xy, bad enum            */
+    RS_ERR_CUDA = -2,          /* a CUDA runtime call failed (rs_ctx_last_cuda_error for details)  */
+    RS_ERR_CAPACITY = -3,      /* a scanline produced more crossings than the on-chip pool holds  */
+    RS_ERR_ROTATED = -4,       /* a tile transform has b != 0 or d != 0                           */
+    RS_ERR_NO_DEVICE = -5,     /* no CUDA device / device is not sm_100                           */
+    RS_ERR_UNSUPPORTED = -6    /* width > 32766, channels not in 1..4, dtype/channels combination */
+};
+
+enum rs_dtype { RS_U8 = 0, RS_U16 = 1 };
+
+enum rs_hist_mode {
+    RS_HIST_BANDS = 0,         /* hist[slot][band][256]: one histogram per band                   */
+    RS_HIST_CLASS_SCORE = 1    /* channels == 2 (class, score): hist[slot][3][256], class 0/1/2   */
+};
+
+enum rs_window_mode {
+    RS_WINDOW_CROP = 0,        /* rasterio.mask.mask(crop=True): per-pair integer window and its   */
+                               /* window transform (fct_misc.py:77)                                */
+    RS_WINDOW_FULL = 1         /* rasterio.features.rasterize(shapes, out_shape, transform): the   */
+                               /* tile transform itself (add_tile_mask.py:112-113)                 */
+};
+
+enum rs_nodata_mode {
+    RS_NODATA_RAW = 0,         /* statistics over every in-mask pixel                              */
+    RS_NODATA_NONE = 1,        /* tile nodata is None: pixels with all bands 0 dropped (fct_misc.py:117-119) */
+    RS_NODATA_ZERO = 2,        /* tile nodata == 0: per band zeros dropped, short bands zero-padded (fct_misc.py:95-111) */
+    RS_NODATA_ZERO_MASKED = 3  /* rasterstats nodata=0: per band zeros masked (statistical_analysis.py:221) */
+};
+
+typedef struct rs_ctx rs_ctx;
+
+typedef struct rs_roads {
+    const double  *xy;
+    const int32_t *ring_off;
+    const int32_t *road_ring_off;
+    const double  *road_bbox;
+    int32_t n_roads, n_rings, n_verts;
+} rs_roads;
+
+typedef struct rs_tiles {
+    const void   *pixels;
+    const double *gt;
+    int32_t n_tiles, height, width, channels;
+    int32_t dtype;              /* enum rs_dtype */
+} rs_tiles;
+
+typedef struct rs_pairs {
+    const int32_t *road_pair_off;
+    const int32_t *pair_tile;
+    int32_t n_pairs;
+} rs_pairs;
+
+typedef struct rs_zonal_params {
+    int32_t hist_mode;          /* enum rs_hist_mode */
+    int32_t window_mode;        /* enum rs_window_mode */
+    int32_t rescale;            /* RS_U16 only: 0 = none (illegal), 1 = float64, 2 = float32 working precision */
+    int32_t reserved;
+    double  scale_k[4];         /* dst = clamp(src*k + off, 0, 255) + 0.5 truncated -- gdal.Translate    */
+    double  scale_off[4];       /* scaleParams (scripts/preprocessing/tif2cog.py:260-270)                */
+    const int32_t *road_slot;   /* optional int32[n_roads]: output row of each road (NULL = identity)    */
+} rs_zonal_params;
+
+/* statistics row produced by rs_finalize_stats_*: doubles, RS_NSTAT fixed columns then the
+ * requested percentiles */
+enum rs_stat_col { RS_STAT_COUNT = 0, RS_STAT_MIN, RS_STAT_MAX, RS_STAT_SUM, RS_STAT_SUMSQ,
+                   RS_STAT_MEAN, RS_STAT_STD, RS_STAT_MEDIAN, RS_STAT_MARGIN, RS_NSTAT };
+
+/* per-threshold metrics row produced by rs_vote_metrics_*: doubles */
+enum rs_metric_col { RS_MET_P0 = 0, RS_MET_R0, RS_MET_F0, RS_MET_P1, RS_MET_R1, RS_MET_F1,
+                     RS_MET_PW, RS_MET_RW, RS_MET_F1W, RS_MET_PB, RS_MET_RB, RS_MET_F1B, RS_NMETRIC };
+
+enum rs_vote_rule { RS_VOTE_COUNT = 0, RS_VOTE_SCORE = 1 };
+enum rs_cover { RS_COVER_ARTIFICIAL = 0, RS_COVER_NATURAL = 1, RS_COVER_UNDETERMINED = 2, RS_COVER_UNDETECTED = 3 };
+
+int         rs_version(void);
+const char *rs_status_string(int status);
+
+/* one context per device: owns the work counters, the status word and the staging buffers
+ * of the _host entry points */
+int rs_ctx_create(int device, rs_ctx **out);
+int rs_ctx_destroy(rs_ctx *ctx);
+/* synchronise `stream`, return and clear the latched kernel-side status */
+int rs_ctx_sync_status(rs_ctx *ctx, void *stream);
+int rs_ctx_last_cuda_error(rs_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py: gpu_launches) */
+int64_t rs_ctx_launch_count(rs_ctx *ctx);
+
+/* road_bbox from xy (device pointers).  Host code normally has it from geometry.bounds. */
+int rs_road_bbox_dev(rs_ctx *ctx, const rs_roads *roads, double *road_bbox_out, void *stream);
+
+/*
+ * Fused rasterize + zonal accumulation.  Replaces, for the whole pair list at once,
+ *   scripts/functions/fct_misc.py:57-123 get_pixel_values  (rasterio.mask.mask :77 + np.extract :95)
+ *   scripts/statistical_analysis/statistical_analysis.py:180-193 (the road x tile loop)
+ *   rasterstats.zonal_stats rasterize+mask (statistical_analysis.py:221, fct_rasters.py:162)
+ * hist      uint32[n_slots][HC][256], HC = channels (RS_HIST_BANDS) or 3 (RS_HIST_CLASS_SCORE)
+ * n_allzero uint32[n_slots]: in-mask pixels whose bands are all 0
+ * Every road's slot is written exactly once (zeros if the road has no pixels): outputs need
+ * no clearing.  Integer outputs are bit-exact and independent of scheduling.
+ */
+int rs_zonal_hist_dev(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                      const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, void *stream);
+int rs_zonal_hist_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                       const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero);
+
+/*
+ * Pixel masks.  Replaces rasterio.features.rasterize (scripts/sandbox/add_tile_mask.py:112-113,
+ * window_mode FULL) and the shape mask of rasterio.mask.mask (fct_misc.py:77, window_mode CROP).
+ * masks uint8[n_pairs][height][width] (pair order = pair_tile order), 1 = selected; the
+ * buffer must be zeroed by the caller.  `tiles->pixels` is not read.
+ */
+int rs_rasterize_pairs_dev(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                           int window_mode, uint8_t *masks, void *stream);
+int rs_rasterize_pairs_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                            int window_mode, uint8_t *masks);
+
+/*
+ * Statistics from merged histograms.  Replaces pandas groupby.agg(['min','max','median','mean',
+ * 'count','std']) + margin (scripts/functions/fct_statistics.py:55-63; ddof = 1) and the
+ * rasterstats reductions (ddof = 0).  stats double[n_roads][channels][RS_NSTAT + n_pct];
+ * rows without pixels get count 0 and NaN elsewhere.  percentiles in [0,100], numpy 'linear'.
+ */
+int rs_finalize_stats_dev(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int32_t n_roads,
+                          int32_t channels, int32_t nodata_mode, int32_t ddof, const double *percentiles_host,
+                          int32_t n_pct, double *stats, void *stream);
+int rs_finalize_stats_host(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int32_t n_roads,
+                           int32_t channels, int32_t nodata_mode, int32_t ddof, const double *percentiles,
+                           int32_t n_pct, double *stats);
+
+/*
+ * Per-road vote, tags, confusion counts and F1 for a list of score cut-offs in one launch.
+ * Replaces determine_class.determine_detected_class (scripts/road_segmentation/determine_class.py:122-190),
+ * final_metrics.get_tag / get_metrics (scripts/road_segmentation/final_metrics.py:91-105, :22-89)
+ * and the threshold sweep (:277-316) on raster accumulators.
+ * joint_hist uint32[n_roads][3][256] (RS_HIST_CLASS_SCORE); gt_class int8[n_roads] (0 artificial,
+ * 1 natural, anything else = road not in the ground truth, skipped); cutoffs int32[n_thr] = smallest
+ * uint8 score kept.  Outputs: cover int8[n_thr][n_roads] (enum rs_cover), scores double[n_thr][n_roads][3]
+ * (art_score, nat_score, diff_score), confusion int64[n_thr][2][4], metrics double[n_thr][RS_NMETRIC].
+ */
+int rs_vote_metrics_dev(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int32_t n_roads,
+                        const int32_t *cutoffs_host, int32_t n_thr, int32_t rule, double min_area_frac,
+                        int8_t *cover, double *scores, int64_t *confusion, double *metrics, void *stream);
+int rs_vote_metrics_host(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int32_t n_roads,
+                         const int32_t *cutoffs, int32_t n_thr, int32_t rule, double min_area_frac,
+                         int8_t *cover, double *scores, int64_t *confusion, double *metrics);
+
+/*
+ * Deterministic synthetic tiles (bench / tests only; the reference ships no imagery,
+ * data/readme.md:20-21).  value = f(seed, tile_key[t], pixel, band), see DESIGN.md.
+ * kind 0: iid uniform; 1: low-entropy "asphalt"; 2: class/score planes (channels == 2).
+ */
+int rs_synth_tiles_dev(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int32_t n_tiles, int32_t height,
+                       int32_t width, int32_t channels, int32_t dtype, int32_t kind, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROADSURF_B200_H */

@@ -1,0 +1,339 @@
+// C ABI of libroadsurf_b200.so (include/roadsurf_b200.h): context, argument checks, and the
+// _host entry points (host buffers in, host buffers out, copies inside).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "rs_internal.h"
+
+namespace rs {
+
+int ensure(rs_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return RS_OK;
+    if (b.p) RS_CUDA_OK(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    RS_CUDA_OK(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return RS_OK;
+}
+
+static int bind(rs_ctx *ctx)
+{
+    if (!ctx) return RS_ERR_INVALID_ARG;
+    RS_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return RS_OK;
+}
+
+static int up(rs_ctx *ctx, DevBuf &b, const void *src, size_t bytes)
+{
+    int rc = ensure(ctx, b, bytes);
+    if (rc) return rc;
+    if (bytes) RS_CUDA_OK(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->host_stream));
+    return RS_OK;
+}
+
+static size_t elem_bytes(int dtype) { return dtype == RS_U16 ? 2 : 1; }
+
+// Copies roads / tiles / pairs to the device staging buffers and returns device-side descriptors.
+static int stage_inputs(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, bool need_pixels,
+                        rs_roads &dr, rs_tiles &dt, rs_pairs &dp)
+{
+    if (!roads || !tiles || !pairs) return RS_ERR_INVALID_ARG;
+    if (roads->n_roads < 0 || roads->n_rings < 0 || roads->n_verts < 0 || tiles->n_tiles < 0 || pairs->n_pairs < 0)
+        return RS_ERR_INVALID_ARG;
+    if (tiles->channels < 1 || tiles->channels > 4) return RS_ERR_UNSUPPORTED;
+    if (tiles->dtype != RS_U8 && tiles->dtype != RS_U16) return RS_ERR_INVALID_ARG;
+    if (roads->n_roads > 0 && (!roads->xy || !roads->ring_off || !roads->road_ring_off || !pairs->road_pair_off))
+        return RS_ERR_INVALID_ARG;
+    int rc;
+    dr = *roads;
+    dt = *tiles;
+    dp = *pairs;
+    if ((rc = up(ctx, ctx->stage[0], roads->xy, sizeof(double) * 2 * (size_t)roads->n_verts))) return rc;
+    if ((rc = up(ctx, ctx->stage[1], roads->ring_off, sizeof(int32_t) * ((size_t)roads->n_rings + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[2], roads->road_ring_off, sizeof(int32_t) * ((size_t)roads->n_roads + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[3], pairs->road_pair_off, sizeof(int32_t) * ((size_t)roads->n_roads + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[4], pairs->pair_tile, sizeof(int32_t) * (size_t)pairs->n_pairs))) return rc;
+    if ((rc = up(ctx, ctx->stage[5], tiles->gt, sizeof(double) * 6 * (size_t)tiles->n_tiles))) return rc;
+    dr.xy = (const double *)ctx->stage[0].p;
+    dr.ring_off = (const int32_t *)ctx->stage[1].p;
+    dr.road_ring_off = (const int32_t *)ctx->stage[2].p;
+    dp.road_pair_off = (const int32_t *)ctx->stage[3].p;
+    dp.pair_tile = (const int32_t *)ctx->stage[4].p;
+    dt.gt = (const double *)ctx->stage[5].p;
+    if ((rc = ensure(ctx, ctx->stage[6], sizeof(double) * 4 * (size_t)roads->n_roads))) return rc;
+    if (roads->road_bbox) {
+        if ((rc = up(ctx, ctx->stage[6], roads->road_bbox, sizeof(double) * 4 * (size_t)roads->n_roads))) return rc;
+    } else if ((rc = launch_road_bbox(ctx, &dr, (double *)ctx->stage[6].p, ctx->host_stream)))
+        return rc;
+    dr.road_bbox = (const double *)ctx->stage[6].p;
+    if (need_pixels) {
+        if (tiles->n_tiles > 0 && !tiles->pixels) return RS_ERR_INVALID_ARG;
+        const size_t nb = (size_t)tiles->n_tiles * tiles->height * tiles->width * tiles->channels * elem_bytes(tiles->dtype);
+        if ((rc = up(ctx, ctx->stage[7], tiles->pixels, nb))) return rc;
+        dt.pixels = ctx->stage[7].p;
+    } else
+        dt.pixels = nullptr;
+    return RS_OK;
+}
+
+static int finish(rs_ctx *ctx)
+{
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_status_pinned, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->host_stream));
+    RS_CUDA_OK(ctx, cudaStreamSynchronize(ctx->host_stream));
+    const int st = *ctx->h_status_pinned;
+    if (st != 0) RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->host_stream));
+    return st;
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+extern "C" {
+
+int rs_version(void) { return RS_VERSION; }
+
+const char *rs_status_string(int status)
+{
+    switch (status) {
+        case RS_OK: return "ok";
+        case RS_ERR_INVALID_ARG: return "invalid argument";
+        case RS_ERR_CUDA: return "CUDA runtime error";
+        case RS_ERR_CAPACITY: return "scanline crossing capacity exceeded";
+        case RS_ERR_ROTATED: return "rotated tile transform is not supported on this path";
+        case RS_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        case RS_ERR_UNSUPPORTED: return "unsupported tile shape or dtype";
+        default: return "unknown status";
+    }
+}
+
+int rs_ctx_create(int device, rs_ctx **out)
+{
+    if (!out) return RS_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RS_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RS_ERR_NO_DEVICE;
+    if (prop.major != 10) return RS_ERR_NO_DEVICE;       // the kernels are built for sm_100a only
+    rs_ctx *ctx = new (std::nothrow) rs_ctx();
+    if (!ctx) return RS_ERR_INVALID_ARG;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_status, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, sizeof(int) * RS_NCOUNTERS);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_status, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, sizeof(int) * RS_NCOUNTERS);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_status_pinned, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        rs_ctx_destroy(ctx);
+        return RS_ERR_CUDA;
+    }
+    *out = ctx;
+    return RS_OK;
+}
+
+int rs_ctx_destroy(rs_ctx *ctx)
+{
+    if (!ctx) return RS_OK;
+    cudaSetDevice(ctx->device);
+    for (auto &b : ctx->stage)
+        if (b.p) cudaFree(b.p);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_status_pinned) cudaFreeHost(ctx->h_status_pinned);
+    if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    delete ctx;
+    return RS_OK;
+}
+
+int rs_ctx_sync_status(rs_ctx *ctx, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_status_pinned, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    const int s = *ctx->h_status_pinned;
+    if (s != 0) {
+        RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), st));
+        RS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    }
+    return s;
+}
+
+int rs_ctx_last_cuda_error(rs_ctx *ctx) { return ctx ? ctx->last_cuda_error : 0; }
+int64_t rs_ctx_launch_count(rs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rs_road_bbox_dev(rs_ctx *ctx, const rs_roads *roads, double *road_bbox_out, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!roads || roads->n_roads < 0) return RS_ERR_INVALID_ARG;
+    if (roads->n_roads > 0 && (!roads->xy || !roads->ring_off || !roads->road_ring_off || !road_bbox_out))
+        return RS_ERR_INVALID_ARG;
+    return launch_road_bbox(ctx, roads, road_bbox_out, (cudaStream_t)stream);
+}
+
+int rs_zonal_hist_dev(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                      const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!prm) return RS_ERR_INVALID_ARG;
+    return launch_zonal(ctx, roads, tiles, pairs, prm, hist, n_allzero, nullptr, prm->window_mode, (cudaStream_t)stream);
+}
+
+int rs_rasterize_pairs_dev(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                           int window_mode, uint8_t *masks, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!masks && pairs && pairs->n_pairs > 0) return RS_ERR_INVALID_ARG;
+    if (pairs && pairs->n_pairs == 0) return RS_OK;
+    return launch_zonal(ctx, roads, tiles, pairs, nullptr, nullptr, nullptr, masks, window_mode, (cudaStream_t)stream);
+}
+
+int rs_zonal_hist_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                       const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!prm || !hist || !n_allzero) return RS_ERR_INVALID_ARG;
+    rs_roads dr;
+    rs_tiles dt;
+    rs_pairs dp;
+    if ((rc = stage_inputs(ctx, roads, tiles, pairs, true, dr, dt, dp))) return rc;
+    rs_zonal_params p = *prm;
+    int n_slots = prm->road_slot ? 0 : roads->n_roads;      /* rows of the output buffers */
+    if (prm->road_slot) {
+        for (int i = 0; i < roads->n_roads; i++) {
+            if (prm->road_slot[i] < 0) return RS_ERR_INVALID_ARG;
+            n_slots = prm->road_slot[i] + 1 > n_slots ? prm->road_slot[i] + 1 : n_slots;
+        }
+        if ((rc = up(ctx, ctx->stage[8], prm->road_slot, sizeof(int32_t) * (size_t)roads->n_roads))) return rc;
+        p.road_slot = (const int32_t *)ctx->stage[8].p;
+    }
+    const int HC = prm->hist_mode == RS_HIST_CLASS_SCORE ? 3 : tiles->channels;
+    const size_t hb = sizeof(uint32_t) * 256 * (size_t)HC * n_slots, zb = sizeof(uint32_t) * (size_t)n_slots;
+    if ((rc = ensure(ctx, ctx->stage[9], hb))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
+    if (prm->road_slot) {      // slots no road maps to stay zero
+        RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[9].p, 0, hb, ctx->host_stream));
+        RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[10].p, 0, zb, ctx->host_stream));
+    }
+    rc = launch_zonal(ctx, &dr, &dt, &dp, &p, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
+                      prm->window_mode, ctx->host_stream);
+    if (rc) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(hist, ctx->stage[9].p, hb, cudaMemcpyDeviceToHost, ctx->host_stream));
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(n_allzero, ctx->stage[10].p, zb, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
+int rs_rasterize_pairs_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                            int window_mode, uint8_t *masks)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!pairs || !tiles) return RS_ERR_INVALID_ARG;
+    if (pairs->n_pairs == 0) return RS_OK;
+    if (!masks) return RS_ERR_INVALID_ARG;
+    rs_roads dr;
+    rs_tiles dt;
+    rs_pairs dp;
+    if ((rc = stage_inputs(ctx, roads, tiles, pairs, false, dr, dt, dp))) return rc;
+    const size_t mb = (size_t)pairs->n_pairs * tiles->height * tiles->width;
+    if ((rc = ensure(ctx, ctx->stage[9], mb))) return rc;
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[9].p, 0, mb, ctx->host_stream));
+    rc = launch_zonal(ctx, &dr, &dt, &dp, nullptr, nullptr, nullptr, (uint8_t *)ctx->stage[9].p, window_mode, ctx->host_stream);
+    if (rc) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(masks, ctx->stage[9].p, mb, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
+int rs_finalize_stats_dev(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int32_t n_roads, int32_t channels,
+                          int32_t nodata_mode, int32_t ddof, const double *percentiles_host, int32_t n_pct, double *stats,
+                          void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    return launch_finalize(ctx, hist, n_allzero, n_roads, channels, nodata_mode, ddof, percentiles_host, n_pct, stats,
+                           (cudaStream_t)stream);
+}
+
+int rs_finalize_stats_host(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int32_t n_roads, int32_t channels,
+                           int32_t nodata_mode, int32_t ddof, const double *percentiles, int32_t n_pct, double *stats)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_roads < 0 || channels < 1 || channels > 4 || n_pct < 0 || n_pct > 16) return RS_ERR_INVALID_ARG;
+    if (n_roads == 0) return RS_OK;
+    if (!hist || !stats) return RS_ERR_INVALID_ARG;
+    const size_t hb = sizeof(uint32_t) * 256 * (size_t)channels * n_roads;
+    const size_t sb = sizeof(double) * (size_t)(RS_NSTAT + n_pct) * channels * n_roads;
+    if ((rc = up(ctx, ctx->stage[9], hist, hb))) return rc;
+    if (n_allzero && (rc = up(ctx, ctx->stage[10], n_allzero, sizeof(uint32_t) * (size_t)n_roads))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], sb))) return rc;
+    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, n_allzero ? (const uint32_t *)ctx->stage[10].p : nullptr,
+                         n_roads, channels, nodata_mode, ddof, percentiles, n_pct, (double *)ctx->stage[11].p, ctx->host_stream);
+    if (rc) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[11].p, sb, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
+int rs_vote_metrics_dev(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int32_t n_roads,
+                        const int32_t *cutoffs_host, int32_t n_thr, int32_t rule, double min_area_frac, int8_t *cover,
+                        double *scores, int64_t *confusion, double *metrics, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    return launch_vote(ctx, joint_hist, gt_class, n_roads, cutoffs_host, n_thr, rule, min_area_frac, cover, scores, confusion,
+                       metrics, (cudaStream_t)stream);
+}
+
+int rs_vote_metrics_host(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int32_t n_roads,
+                         const int32_t *cutoffs, int32_t n_thr, int32_t rule, double min_area_frac, int8_t *cover,
+                         double *scores, int64_t *confusion, double *metrics)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_roads < 0 || n_thr < 1 || n_thr > 32 || !cutoffs || !confusion) return RS_ERR_INVALID_ARG;
+    const size_t R = (size_t)n_roads, T = (size_t)n_thr;
+    if ((rc = up(ctx, ctx->stage[9], joint_hist, sizeof(uint32_t) * 768 * R))) return rc;
+    if (gt_class && (rc = up(ctx, ctx->stage[10], gt_class, R))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], T * R))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[12], sizeof(double) * 3 * T * R))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[13], sizeof(int64_t) * 8 * T))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[14], sizeof(double) * RS_NMETRIC * T))) return rc;
+    rc = launch_vote(ctx, (const uint32_t *)ctx->stage[9].p, gt_class ? (const int8_t *)ctx->stage[10].p : nullptr, n_roads,
+                     cutoffs, n_thr, rule, min_area_frac, cover ? (int8_t *)ctx->stage[11].p : nullptr,
+                     scores ? (double *)ctx->stage[12].p : nullptr, (int64_t *)ctx->stage[13].p,
+                     metrics ? (double *)ctx->stage[14].p : nullptr, ctx->host_stream);
+    if (rc) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if (cover && R) RS_CUDA_OK(ctx, cudaMemcpyAsync(cover, ctx->stage[11].p, T * R, cudaMemcpyDeviceToHost, st));
+    if (scores && R) RS_CUDA_OK(ctx, cudaMemcpyAsync(scores, ctx->stage[12].p, sizeof(double) * 3 * T * R, cudaMemcpyDeviceToHost, st));
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(confusion, ctx->stage[13].p, sizeof(int64_t) * 8 * T, cudaMemcpyDeviceToHost, st));
+    if (metrics) RS_CUDA_OK(ctx, cudaMemcpyAsync(metrics, ctx->stage[14].p, sizeof(double) * RS_NMETRIC * T, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
+int rs_synth_tiles_dev(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int32_t n_tiles, int32_t height, int32_t width,
+                       int32_t channels, int32_t dtype, int32_t kind, uint64_t seed, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    return launch_synth(ctx, pixels, tile_key, n_tiles, height, width, channels, dtype, kind, seed, (cudaStream_t)stream);
+}
+
+}  // extern "C"

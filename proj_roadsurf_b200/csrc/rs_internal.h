@@ -1,0 +1,62 @@
+// Internal declarations shared by the translation units of libroadsurf_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "roadsurf_b200.h"
+
+namespace rs {
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace rs
+
+struct rs_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int last_cuda_error = 0;
+    int64_t launches = 0;
+    int *d_status = nullptr;      // latched kernel-side status (min over failures)
+    int *d_counters = nullptr;    // work counters / list sizes, RS_NCOUNTERS ints
+    int *h_status_pinned = nullptr;
+    cudaStream_t host_stream = nullptr;   // stream of the _host entry points
+    rs::DevBuf stage[16];                 // grow-only device staging of the _host entry points
+};
+
+namespace rs {
+
+enum { RS_NCOUNTERS = 16 };
+
+// Make `b` hold at least `bytes` bytes of device memory.
+int ensure(rs_ctx *ctx, DevBuf &b, size_t bytes);
+
+#define RS_CUDA_OK(ctx, call)                                  \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) {                              \
+            (ctx)->last_cuda_error = (int)e__;                 \
+            return RS_ERR_CUDA;                                \
+        }                                                      \
+    } while (0)
+
+// launches (defined in the .cu files)
+int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                 const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks,
+                 int window_mode, cudaStream_t st);
+int launch_road_bbox(rs_ctx *ctx, const rs_roads *roads, double *out, cudaStream_t st);
+int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int n_roads, int channels,
+                    int nodata_mode, int ddof, const double *pct_host, int n_pct, double *stats, cudaStream_t st);
+int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int n_roads,
+                const int32_t *cutoffs_host, int n_thr, int rule, double min_area_frac, int8_t *cover,
+                double *scores, int64_t *confusion, double *metrics, cudaStream_t st);
+int launch_synth(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int n_tiles, int H, int W, int C, int dtype,
+                 int kind, uint64_t seed, cudaStream_t st);
+
+}  // namespace rs

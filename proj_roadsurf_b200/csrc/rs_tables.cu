@@ -1,0 +1,393 @@
+// K3 statistics from merged histograms, K4 vote + confusion + F1, synthetic tile generator (sm_100a).
+//
+// K3 replaces pandas groupby.agg(['min','max','median','mean','count','std']) + margin
+//    (scripts/functions/fct_statistics.py:55-63, ddof 1) and the rasterstats reductions (ddof 0),
+//    including the two nodata conventions of fct_misc.get_pixel_values (fct_misc.py:95-119).
+// K4 replaces determine_class.determine_detected_class (scripts/road_segmentation/determine_class.py:122-190),
+//    final_metrics.get_tag / get_metrics (scripts/road_segmentation/final_metrics.py:91-105, :22-89)
+//    for every cut-off of the sweep (:277-316) in one launch, on raster accumulators.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "rs_internal.h"
+
+namespace rs {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 warp_sum_u64(u64 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: one warp per road; lane l owns bins [8l, 8l+8)
+// ---------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+    const uint32_t *hist;
+    const uint32_t *nzero;
+    int n_roads, C, mode, ddof, n_pct;
+    double pct[16];
+    double *stats;
+};
+
+// value of the k-th (0-based) smallest element of the multiset described by the lane-distributed bins
+__device__ __forceinline__ int order_stat(const u64 c[8], u64 excl, u64 nl, u64 k, int lane)
+{
+    const bool owner = (k >= excl) && (k < excl + nl);
+    int v = 0;
+    if (owner) {
+        u64 run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (k < run + c[j]) { v = 8 * lane + j; break; }
+            run += c[j];
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, owner);
+    return __shfl_sync(0xffffffffu, v, m ? __ffs(m) - 1 : 0);
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a)
+{
+    const int road = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (road >= a.n_roads) return;
+    const int C = a.C, NS = RS_NSTAT + a.n_pct;
+    const uint32_t *hr = a.hist + (size_t)road * C * 256;
+
+    u64 longest = 0;
+    if (a.mode == RS_NODATA_ZERO) {
+        for (int b = 0; b < C; b++) {
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane);
+            const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane + 4);
+            u64 nzv = (u64)q0.y + q0.z + q0.w + q1.x + q1.y + q1.z + q1.w + (lane ? (u64)q0.x : 0ull);
+            nzv = warp_sum_u64(nzv);
+            longest = nzv > longest ? nzv : longest;
+        }
+    }
+    const u64 allzero = a.nzero ? (u64)a.nzero[road] : 0ull;
+
+    for (int b = 0; b < C; b++) {
+        const uint4 q0 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane);
+        const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane + 4);
+        u64 c[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        if (a.mode != RS_NODATA_RAW) {
+            u64 nzv = c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7] + (lane ? c[0] : 0ull);
+            if (a.mode == RS_NODATA_ZERO) nzv = warp_sum_u64(nzv);
+            if (lane == 0) {
+                if (a.mode == RS_NODATA_NONE) c[0] = c[0] >= allzero ? c[0] - allzero : 0ull;
+                else if (a.mode == RS_NODATA_ZERO) c[0] = longest - nzv;
+                else c[0] = 0ull;                       // RS_NODATA_ZERO_MASKED
+            }
+        }
+        u64 nl = 0, s1 = 0, s2 = 0;
+        int vmin = 256, vmax = -1;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const u64 v = (u64)(8 * lane + j);
+            nl += c[j];
+            s1 += v * c[j];
+            s2 += v * v * c[j];
+            if (c[j]) { vmin = min(vmin, (int)v); vmax = max(vmax, (int)v); }
+        }
+        // exclusive prefix of nl over lanes
+        u64 incl = nl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const u64 excl = incl - nl;
+        const u64 n = __shfl_sync(0xffffffffu, incl, 31);
+        s1 = warp_sum_u64(s1);
+        s2 = warp_sum_u64(s2);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        }
+        double *out = a.stats + ((size_t)road * C + b) * NS;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        if (n == 0) {
+            if (lane == 0) {
+                out[RS_STAT_COUNT] = 0.0;
+                for (int i = 1; i < NS; i++) out[i] = nan;
+            }
+            continue;
+        }
+        const int med_lo = order_stat(c, excl, nl, (n - 1) >> 1, lane);
+        const int med_hi = order_stat(c, excl, nl, n >> 1, lane);
+        double pv[16];
+        for (int i = 0; i < a.n_pct; i++) {
+            // numpy.percentile, method 'linear': virtual index (n-1)*q/100, _lerp between neighbours
+            const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(a.pct[i], 100.0));
+            double fl = floor(vi);
+            if (fl < 0.0) fl = 0.0;
+            u64 k0 = (u64)fl;
+            if (k0 > n - 1) k0 = n - 1;
+            const u64 k1 = k0 + 1 > n - 1 ? n - 1 : k0 + 1;
+            const double t = __dsub_rn(vi, fl);
+            const double va = (double)order_stat(c, excl, nl, k0, lane), vb = (double)order_stat(c, excl, nl, k1, lane);
+            const double d = __dsub_rn(vb, va);
+            pv[i] = t >= 0.5 ? __dsub_rn(vb, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(va, __dmul_rn(d, t));
+        }
+        if (lane == 0) {
+            const double dn = (double)n;
+            const double mean = (double)s1 / dn;
+            double sd = nan;
+            if (n > (u64)a.ddof) {
+                const unsigned __int128 num = (unsigned __int128)n * s2 - (unsigned __int128)s1 * s1;
+                const double var = (double)num / (dn * (double)(n - (u64)a.ddof));
+                sd = sqrt(var);
+            }
+            out[RS_STAT_COUNT] = dn;
+            out[RS_STAT_MIN] = (double)vmin;
+            out[RS_STAT_MAX] = (double)vmax;
+            out[RS_STAT_SUM] = (double)s1;
+            out[RS_STAT_SUMSQ] = (double)s2;
+            out[RS_STAT_MEAN] = mean;
+            out[RS_STAT_STD] = sd;
+            out[RS_STAT_MEDIAN] = ((double)med_lo + (double)med_hi) * 0.5;
+            out[RS_STAT_MARGIN] = 2.0 * sd / sqrt(dn);        // Z = 2, fct_statistics.py:58-59
+            for (int i = 0; i < a.n_pct; i++) out[RS_NSTAT + i] = pv[i];
+        }
+    }
+}
+
+int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int n_roads, int channels,
+                    int nodata_mode, int ddof, const double *pct_host, int n_pct, double *stats, cudaStream_t st)
+{
+    if (n_roads < 0 || channels < 1 || channels > 4 || n_pct < 0 || n_pct > 16 || ddof < 0) return RS_ERR_INVALID_ARG;
+    if (nodata_mode < RS_NODATA_RAW || nodata_mode > RS_NODATA_ZERO_MASKED) return RS_ERR_INVALID_ARG;
+    if (n_roads == 0) return RS_OK;
+    if (!hist || !stats || (n_pct > 0 && !pct_host)) return RS_ERR_INVALID_ARG;
+    if (nodata_mode == RS_NODATA_NONE && !n_allzero) return RS_ERR_INVALID_ARG;
+    FinalizeArgs a{};
+    a.hist = hist; a.nzero = n_allzero; a.n_roads = n_roads; a.C = channels; a.mode = nodata_mode; a.ddof = ddof;
+    a.n_pct = n_pct;
+    for (int i = 0; i < n_pct; i++) a.pct[i] = pct_host[i];
+    a.stats = stats;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)(((size_t)n_roads * 32 + threads - 1) / threads);
+    finalize_kernel<<<blocks, threads, 0, st>>>(a);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: vote (one warp per road, all cut-offs) + confusion counts, then metrics (one thread per cut-off)
+// ---------------------------------------------------------------------------------------------
+enum { RS_MAX_THR = 32 };
+
+struct VoteArgs {
+    const uint32_t *jh;
+    const int8_t *gt;
+    int n_roads, n_thr, rule;
+    double min_area_frac;
+    int cut[RS_MAX_THR];
+    int8_t *cover;
+    double *scores;
+    u64 *confusion;     // [n_thr][2][4]
+};
+
+__global__ void __launch_bounds__(256) vote_kernel(const VoteArgs a)
+{
+    __shared__ unsigned int conf[RS_MAX_THR * 8];
+    for (int i = threadIdx.x; i < RS_MAX_THR * 8; i += blockDim.x) conf[i] = 0;
+    __syncthreads();
+    const int road = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (road < a.n_roads) {
+        const uint32_t *hr = a.jh + (size_t)road * 768;
+        u64 c[3][8];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(hr + k * 256 + 8 * lane);
+            const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + k * 256 + 8 * lane + 4);
+            c[k][0] = q0.x; c[k][1] = q0.y; c[k][2] = q0.z; c[k][3] = q0.w;
+            c[k][4] = q1.x; c[k][5] = q1.y; c[k][6] = q1.z; c[k][7] = q1.w;
+        }
+        u64 ninside = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) ninside += c[k][j];
+        ninside = warp_sum_u64(ninside);
+
+        u64 my_n[2] = {0, 0}, my_s[2] = {0, 0};     // lane i keeps the sums of cut-off i
+        for (int i = 0; i < a.n_thr; i++) {
+            const int cut = a.cut[i];
+            u64 n1 = 0, n2 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int sc = 8 * lane + j;
+                if (sc >= cut) {
+                    n1 += c[1][j]; s1 += (u64)sc * c[1][j];
+                    n2 += c[2][j]; s2 += (u64)sc * c[2][j];
+                }
+            }
+            n1 = warp_sum_u64(n1); n2 = warp_sum_u64(n2);
+            s1 = warp_sum_u64(s1); s2 = warp_sum_u64(s2);
+            if (lane == i) { my_n[0] = n1; my_n[1] = n2; my_s[0] = s1; my_s[1] = s2; }
+        }
+        if (lane < a.n_thr) {
+            u64 na = my_n[0], nn = my_n[1], sa = my_s[0], sn = my_s[1];
+            if (a.min_area_frac > 0.0) {
+                const double den = (double)(ninside ? ninside : 1ull);
+                const double fa = rint(__dmul_rn(__ddiv_rn((double)na, den), 100.0)) / 100.0;   // np.round(x, 2)
+                const double fn = rint(__dmul_rn(__ddiv_rn((double)nn, den), 100.0)) / 100.0;
+                if (fa <= a.min_area_frac) { na = 0; sa = 0; }
+                if (fn <= a.min_area_frac) { nn = 0; sn = 0; }
+            }
+            const double ia = (na > 0 && sa > 0) ? (double)sa / (255.0 * (double)na) : 0.0;
+            const double in_ = (nn > 0 && sn > 0) ? (double)sn / (255.0 * (double)nn) : 0.0;
+            unsigned __int128 left, right;
+            if (a.rule == RS_VOTE_COUNT) { left = na; right = nn; }
+            else {
+                left = na > 0 ? (unsigned __int128)sa * (nn ? nn : 1ull) : 0;
+                right = nn > 0 ? (unsigned __int128)sn * (na ? na : 1ull) : 0;
+            }
+            int cov = RS_COVER_UNDETERMINED;
+            if (left > right) cov = RS_COVER_ARTIFICIAL;
+            else if (left < right) cov = RS_COVER_NATURAL;
+            if (na + nn == 0) cov = RS_COVER_UNDETECTED;
+            const size_t o = (size_t)lane * a.n_roads + road;
+            if (a.cover) a.cover[o] = (int8_t)cov;
+            if (a.scores) {
+                a.scores[3 * o + 0] = ia;
+                a.scores[3 * o + 1] = in_;
+                a.scores[3 * o + 2] = fabs(ia - in_);
+            }
+            const int g = a.gt ? (int)a.gt[road] : -1;
+            if (g == 0 || g == 1) atomicAdd(&conf[lane * 8 + g * 4 + cov], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.n_thr * 8; i += blockDim.x)
+        if (conf[i]) atomicAdd(&a.confusion[i], (u64)conf[i]);
+}
+
+__global__ void metrics_kernel(const u64 *confusion, int n_thr, double *metrics)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_thr) return;
+    const u64 *m = confusion + (size_t)i * 8;      // m[g*4 + cov]
+    double P[2], R[2], F[2], cnt[2];
+    for (int k = 0; k < 2; k++) {
+        const double tp = (double)m[k * 4 + k];
+        const double fp = (double)m[(1 - k) * 4 + k];
+        const double fn = (double)(m[k * 4 + 2] + m[k * 4 + 3] + m[k * 4 + (1 - k)]);
+        if (tp == 0.0) { P[k] = 0.0; R[k] = 0.0; F[k] = 0.0; }
+        else {
+            P[k] = tp / (tp + fp);
+            R[k] = tp / (tp + fn);
+            F[k] = 2.0 * P[k] * R[k] / (P[k] + R[k]);
+        }
+        cnt[k] = (double)(m[k * 4] + m[k * 4 + 1] + m[k * 4 + 2] + m[k * 4 + 3]);
+    }
+    const double total = cnt[0] + cnt[1];
+    const double pw = (P[0] * cnt[0] + P[1] * cnt[1]) / total;
+    const double rw = (R[0] * cnt[0] + R[1] * cnt[1]) / total;
+    const double f1w = (pw == 0.0 && rw == 0.0) ? 0.0 : 2.0 * pw * rw / (pw + rw);
+    const double pb = (P[0] + P[1]) / 2.0, rb = (R[0] + R[1]) / 2.0;      // literal 2, final_metrics.py:78-79
+    const double f1b = (pb == 0.0 && rb == 0.0) ? 0.0 : 2.0 * pb * rb / (pb + rb);
+    double *o = metrics + (size_t)i * RS_NMETRIC;
+    o[RS_MET_P0] = P[0]; o[RS_MET_R0] = R[0]; o[RS_MET_F0] = F[0];
+    o[RS_MET_P1] = P[1]; o[RS_MET_R1] = R[1]; o[RS_MET_F1] = F[1];
+    o[RS_MET_PW] = pw; o[RS_MET_RW] = rw; o[RS_MET_F1W] = f1w;
+    o[RS_MET_PB] = pb; o[RS_MET_RB] = rb; o[RS_MET_F1B] = f1b;
+}
+
+int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int n_roads,
+                const int32_t *cutoffs_host, int n_thr, int rule, double min_area_frac, int8_t *cover, double *scores,
+                int64_t *confusion, double *metrics, cudaStream_t st)
+{
+    if (n_roads < 0 || n_thr < 1 || n_thr > RS_MAX_THR || !cutoffs_host) return RS_ERR_INVALID_ARG;
+    if (rule != RS_VOTE_COUNT && rule != RS_VOTE_SCORE) return RS_ERR_INVALID_ARG;
+    if (!confusion || (n_roads > 0 && !joint_hist)) return RS_ERR_INVALID_ARG;
+    RS_CUDA_OK(ctx, cudaMemsetAsync(confusion, 0, sizeof(int64_t) * 8 * (size_t)n_thr, st));
+    if (n_roads > 0) {
+        VoteArgs a{};
+        a.jh = joint_hist; a.gt = gt_class; a.n_roads = n_roads; a.n_thr = n_thr; a.rule = rule;
+        a.min_area_frac = min_area_frac;
+        for (int i = 0; i < n_thr; i++) a.cut[i] = cutoffs_host[i];
+        a.cover = cover; a.scores = scores; a.confusion = (u64 *)confusion;
+        const int threads = 256;
+        const unsigned blocks = (unsigned)(((size_t)n_roads * 32 + threads - 1) / threads);
+        vote_kernel<<<blocks, threads, 0, st>>>(a);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+    }
+    if (metrics) {
+        metrics_kernel<<<1, RS_MAX_THR, 0, st>>>((const u64 *)confusion, n_thr, metrics);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+    }
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic tiles: counter-based, any shard regenerates its own tiles from (seed, tile_key)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 mix64(u64 z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) synth_kernel(T *__restrict__ px, const int64_t *__restrict__ key, int n_tiles, int H, int W,
+                                                    int C, int kind, u64 seed)
+{
+    const size_t per_tile = (size_t)H * W;
+    const size_t total = per_tile * n_tiles;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = i / per_tile, p = i - t * per_tile;
+        const u64 tk = mix64(seed ^ ((u64)key[t] * 0xD6E8FEB86659FD93ull));
+        const u64 hp = mix64(tk ^ (u64)p);
+        const bool hole = (hp >> 40) % 100ull == 0ull;          // 1 % of pixels: every band 0
+        T *o = px + i * C;
+        if (kind == 2) {
+            const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+            const u64 cell = mix64(tk ^ (0xC0FFEEull + (u64)(y >> 4) * 65537ull + (u64)(x >> 4)));
+            const unsigned cls = (unsigned)(cell & 3ull);
+            o[0] = (T)(cls == 3u ? 0u : cls);
+            o[1] = (T)((hp >> 8) & 255ull);
+            continue;
+        }
+        for (int c = 0; c < C; c++) {
+            const u64 h = mix64(hp + 0x632BE59BD9B4E019ull * (u64)(c + 1));
+            unsigned v;
+            if (sizeof(T) == 2) v = (unsigned)(h >> 48);
+            else if (kind == 1) {
+                const int sum = (int)(h & 255) + (int)((h >> 8) & 255) + (int)((h >> 16) & 255) + (int)((h >> 24) & 255);
+                int g = 110 + ((sum - 510) * 6) / 148;
+                v = (unsigned)(g < 0 ? 0 : (g > 255 ? 255 : g));
+            } else v = (unsigned)(h >> 56);
+            o[c] = hole ? (T)0 : (T)v;
+        }
+    }
+}
+
+int launch_synth(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int n_tiles, int H, int W, int C, int dtype,
+                 int kind, uint64_t seed, cudaStream_t st)
+{
+    if (n_tiles < 0 || H < 1 || W < 1 || C < 1 || C > 4 || kind < 0 || kind > 2) return RS_ERR_INVALID_ARG;
+    if (kind == 2 && (C != 2 || dtype != RS_U8)) return RS_ERR_INVALID_ARG;
+    if (n_tiles == 0) return RS_OK;
+    if (!pixels || !tile_key) return RS_ERR_INVALID_ARG;
+    const int grid = ctx->sm_count * 16;
+    if (dtype == RS_U8) synth_kernel<uint8_t><<<grid, 256, 0, st>>>((uint8_t *)pixels, tile_key, n_tiles, H, W, C, kind, seed);
+    else if (dtype == RS_U16) synth_kernel<uint16_t><<<grid, 256, 0, st>>>((uint16_t *)pixels, tile_key, n_tiles, H, W, C, kind, seed);
+    else return RS_ERR_INVALID_ARG;
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+}  // namespace rs

@@ -1,0 +1,318 @@
+"""Batched overlay engine: the Python face of the C ABI (include/roadsurf_b200.h).
+
+Two families of calls:
+  * ``*_host``  numpy arrays in, numpy arrays out; host<->device copies happen inside the C call
+                (what the reference-shaped helpers in functions/ and road_segmentation/ use);
+  * ``*_dev``   torch CUDA tensors in, torch CUDA tensors out, asynchronous on the current torch
+                stream (inputs resident in HBM; what bench.py times as ``value``).
+torch is plumbing here (device memory, streams); every computation is a hand-written kernel in
+libroadsurf_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .geometry import PairList, RoadSet, TileBatch
+
+_HIST_MODES = {"bands": N.RS_HIST_BANDS, "class_score": N.RS_HIST_CLASS_SCORE}
+_WINDOW_MODES = {"crop": N.RS_WINDOW_CROP, "full": N.RS_WINDOW_FULL}
+_NODATA_MODES = {"raw": N.RS_NODATA_RAW, "none": N.RS_NODATA_NONE, "zero": N.RS_NODATA_ZERO,
+                 "zero_masked": N.RS_NODATA_ZERO_MASKED}
+_RULES = {"count": N.RS_VOTE_COUNT, "score": N.RS_VOTE_SCORE}
+
+
+def scale_params(smin: Sequence[float], smax: Sequence[float], f32: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """k, off of gdal.Translate scaleParams [smin, smax, 0, 255] (tif2cog.py:260-270), evaluated in
+    the working precision GDAL is assumed to use (float64 by default)."""
+    ft = np.float32 if f32 else np.float64
+    lo, hi = np.asarray(smin, ft), np.asarray(smax, ft)
+    k = ft(255.0) / (hi - lo)
+    off = ft(0.0) - lo * k
+    return k.astype(np.float64), off.astype(np.float64)
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+@dataclass
+class DeviceRoads:
+    xy: "object"
+    ring_off: "object"
+    road_ring_off: "object"
+    bbox: "object"
+    n_roads: int
+    n_rings: int
+    n_verts: int
+
+
+@dataclass
+class DevicePairs:
+    road_pair_off: "object"
+    pair_tile: "object"
+    n_pairs: int
+
+
+@dataclass
+class DeviceTiles:
+    pixels: "object"       # (T, H, W, C) uint8 | int16-viewed uint16
+    gt: "object"
+    n_tiles: int
+    height: int
+    width: int
+    channels: int
+    dtype: int
+
+
+class Engine:
+    """One context per device (rs_ctx_create)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = N.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        N.check(self.lib.rs_ctx_create(self.device, C.byref(h)), "rs_ctx_create")
+        self._ctx = h
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.rs_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rs_ctx_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ descriptors
+    @staticmethod
+    def _roads_desc(xy, ring_off, road_ring_off, bbox, n_roads, n_rings, n_verts) -> N.RsRoads:
+        return N.RsRoads(xy, ring_off, road_ring_off, bbox, n_roads, n_rings, n_verts)
+
+    @staticmethod
+    def _params(hist_mode, window, rescale, road_slot_ptr) -> N.RsZonalParams:
+        p = N.RsZonalParams()
+        p.hist_mode = _HIST_MODES[hist_mode]
+        p.window_mode = _WINDOW_MODES[window]
+        p.rescale = 0
+        if rescale is not None:
+            k, off, f32 = rescale
+            p.rescale = 2 if f32 else 1
+            for i in range(4):
+                p.scale_k[i] = float(k[i]) if i < len(k) else 1.0
+                p.scale_off[i] = float(off[i]) if i < len(off) else 0.0
+        p.road_slot = road_slot_ptr
+        return p
+
+    # ------------------------------------------------------------------ host family
+    def zonal_hist_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, hist_mode: str = "bands",
+                        window: str = "crop", rescale=None, road_slot: Optional[np.ndarray] = None,
+                        n_slots: Optional[int] = None):
+        """Per-road histograms (n_slots, HC, 256) uint32 and all-zero-pixel counts (n_slots,) uint32."""
+        px = np.ascontiguousarray(tiles.pixels)
+        dtype = N.RS_U16 if px.dtype == np.uint16 else N.RS_U8
+        R = roads.n_roads
+        HC = 3 if hist_mode == "class_score" else tiles.channels
+        slot = None if road_slot is None else np.ascontiguousarray(road_slot, np.int32)
+        S = R if slot is None else (int(slot.max()) + 1 if R else 0)     # rows the C call writes back
+        if n_slots is not None and slot is not None:
+            assert n_slots >= S, "n_slots smaller than the largest slot"
+        S_out = S if (n_slots is None or slot is None) else int(n_slots)
+        hist = np.zeros((S_out, HC, 256), np.uint32)
+        nzero = np.zeros(S_out, np.uint32)
+        xy = np.ascontiguousarray(roads.xy, np.float64)
+        ro, rro = np.ascontiguousarray(roads.ring_off, np.int32), np.ascontiguousarray(roads.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        rpo, pt = np.ascontiguousarray(pairs.road_pair_off, np.int32), np.ascontiguousarray(pairs.pair_tile, np.int32)
+        gt = np.ascontiguousarray(tiles.gt, np.float64)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), R, roads.n_rings, roads.n_verts)
+        td = N.RsTiles(_np_ptr(px), _np_ptr(gt), tiles.n_tiles, tiles.height, tiles.width, tiles.channels, dtype)
+        pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
+        prm = self._params(hist_mode, window, rescale, _np_ptr(slot))
+        st = self.lib.rs_zonal_hist_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
+                                         _np_ptr(hist), _np_ptr(nzero))
+        N.check(st, "rs_zonal_hist_host", self._ctx)
+        return hist, nzero
+
+    def rasterize_pairs_host(self, roads: RoadSet, gt: np.ndarray, height: int, width: int, pairs: PairList,
+                             window: str = "crop") -> np.ndarray:
+        """uint8 masks (n_pairs, H, W), 1 = pixel selected for that (road, tile) pair."""
+        masks = np.zeros((pairs.n_pairs, height, width), np.uint8)
+        if pairs.n_pairs == 0:
+            return masks
+        xy = np.ascontiguousarray(roads.xy, np.float64)
+        ro, rro = np.ascontiguousarray(roads.ring_off, np.int32), np.ascontiguousarray(roads.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        rpo, pt = np.ascontiguousarray(pairs.road_pair_off, np.int32), np.ascontiguousarray(pairs.pair_tile, np.int32)
+        gt = np.ascontiguousarray(gt, np.float64).reshape(-1, 6)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), roads.n_roads, roads.n_rings, roads.n_verts)
+        td = N.RsTiles(None, _np_ptr(gt), gt.shape[0], height, width, 1, N.RS_U8)
+        pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
+        st = self.lib.rs_rasterize_pairs_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), _WINDOW_MODES[window],
+                                              _np_ptr(masks))
+        N.check(st, "rs_rasterize_pairs_host", self._ctx)
+        return masks
+
+    def finalize_stats_host(self, hist: np.ndarray, n_allzero: Optional[np.ndarray], nodata_mode: str = "none",
+                            ddof: int = 1, percentiles: Sequence[float] = ()) -> np.ndarray:
+        """(R, C, RS_NSTAT + len(percentiles)) float64; columns _native.STAT_COLS then the percentiles."""
+        hist = np.ascontiguousarray(hist, np.uint32)
+        R, Cc = hist.shape[0], hist.shape[1]
+        nz = None if n_allzero is None else np.ascontiguousarray(n_allzero, np.uint32)
+        pct = np.ascontiguousarray(percentiles, np.float64)
+        out = np.zeros((R, Cc, N.RS_NSTAT + len(pct)), np.float64)
+        st = self.lib.rs_finalize_stats_host(self._ctx, _np_ptr(hist), _np_ptr(nz), R, Cc, _NODATA_MODES[nodata_mode],
+                                             int(ddof), _np_ptr(pct) if len(pct) else None, len(pct), _np_ptr(out))
+        N.check(st, "rs_finalize_stats_host", self._ctx)
+        return out
+
+    def vote_metrics_host(self, joint_hist: np.ndarray, gt_class: Optional[np.ndarray], cutoffs: Sequence[int],
+                          rule: str = "count", min_area_frac: float = 0.0):
+        """cover (n_thr, R) int8, scores (n_thr, R, 3), confusion (n_thr, 2, 4) int64, metrics (n_thr, 12)."""
+        jh = np.ascontiguousarray(joint_hist, np.uint32)
+        R = jh.shape[0]
+        gtc = None if gt_class is None else np.ascontiguousarray(gt_class, np.int8)
+        cut = np.ascontiguousarray(cutoffs, np.int32)
+        T = len(cut)
+        cover = np.zeros((T, R), np.int8)
+        scores = np.zeros((T, R, 3), np.float64)
+        conf = np.zeros((T, 2, 4), np.int64)
+        met = np.zeros((T, N.RS_NMETRIC), np.float64)
+        st = self.lib.rs_vote_metrics_host(self._ctx, _np_ptr(jh), _np_ptr(gtc), R, _np_ptr(cut), T, _RULES[rule],
+                                           float(min_area_frac), _np_ptr(cover), _np_ptr(scores), _np_ptr(conf), _np_ptr(met))
+        N.check(st, "rs_vote_metrics_host", self._ctx)
+        return cover, scores, conf, met
+
+    # ------------------------------------------------------------------ device family (torch tensors)
+    def _torch(self):
+        import torch
+        return torch
+
+    def _stream(self):
+        torch = self._torch()
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def upload_roads(self, roads: RoadSet) -> DeviceRoads:
+        torch = self._torch()
+        dev = torch.device("cuda", self.device)
+        return DeviceRoads(torch.from_numpy(np.ascontiguousarray(roads.xy, np.float64)).to(dev),
+                           torch.from_numpy(np.ascontiguousarray(roads.ring_off, np.int32)).to(dev),
+                           torch.from_numpy(np.ascontiguousarray(roads.road_ring_off, np.int32)).to(dev),
+                           torch.from_numpy(np.ascontiguousarray(roads.bbox, np.float64)).to(dev),
+                           roads.n_roads, roads.n_rings, roads.n_verts)
+
+    def upload_pairs(self, pairs: PairList) -> DevicePairs:
+        torch = self._torch()
+        dev = torch.device("cuda", self.device)
+        return DevicePairs(torch.from_numpy(np.ascontiguousarray(pairs.road_pair_off, np.int32)).to(dev),
+                           torch.from_numpy(np.ascontiguousarray(pairs.pair_tile, np.int32)).to(dev), pairs.n_pairs)
+
+    def upload_tiles(self, tiles: TileBatch) -> DeviceTiles:
+        torch = self._torch()
+        dev = torch.device("cuda", self.device)
+        px = np.ascontiguousarray(tiles.pixels)
+        dtype = N.RS_U16 if px.dtype == np.uint16 else N.RS_U8
+        t = torch.from_numpy(px.view(np.int16) if dtype == N.RS_U16 else px).to(dev)
+        return DeviceTiles(t, torch.from_numpy(np.ascontiguousarray(tiles.gt, np.float64)).to(dev), tiles.n_tiles,
+                           tiles.height, tiles.width, tiles.channels, dtype)
+
+    def synth_tiles_dev(self, tile_key, height: int, width: int, channels: int, dtype: str = "u8", kind: int = 0,
+                        seed: int = 20261018, gt=None) -> DeviceTiles:
+        """Generate synthetic tiles on the device (rs_synth_tiles_dev).  tile_key: int64 per tile."""
+        torch = self._torch()
+        dev = torch.device("cuda", self.device)
+        key = torch.as_tensor(np.ascontiguousarray(tile_key, np.int64)).to(dev)
+        T = int(key.numel())
+        code = N.RS_U16 if dtype == "u16" else N.RS_U8
+        px = torch.empty((T, height, width, channels), dtype=torch.int16 if code == N.RS_U16 else torch.uint8, device=dev)
+        st = self.lib.rs_synth_tiles_dev(self._ctx, px.data_ptr(), key.data_ptr(), T, height, width, channels, code, kind,
+                                         C.c_uint64(seed), self._stream())
+        N.check(st, "rs_synth_tiles_dev", self._ctx)
+        g = None if gt is None else torch.from_numpy(np.ascontiguousarray(gt, np.float64)).to(dev)
+        return DeviceTiles(px, g, T, height, width, channels, code)
+
+    def zonal_hist_dev(self, roads: DeviceRoads, tiles: DeviceTiles, pairs: DevicePairs, hist_mode: str = "bands",
+                       window: str = "crop", rescale=None, road_slot=None, out=None, check: bool = True):
+        """Asynchronous on the current torch stream.  Returns (hist, n_allzero) CUDA tensors (int32 storage
+        of the uint32 counters).  ``check`` synchronises and raises on a kernel-side failure."""
+        torch = self._torch()
+        dev = torch.device("cuda", self.device)
+        HC = 3 if hist_mode == "class_score" else tiles.channels
+        if out is None:
+            S = roads.n_roads if road_slot is None else int(road_slot.max().item()) + 1
+            hist = torch.zeros((S, HC, 256), dtype=torch.int32, device=dev) if road_slot is not None else \
+                torch.empty((S, HC, 256), dtype=torch.int32, device=dev)
+            nzero = torch.zeros((S,), dtype=torch.int32, device=dev)
+        else:
+            hist, nzero = out
+        rd = self._roads_desc(roads.xy.data_ptr(), roads.ring_off.data_ptr(), roads.road_ring_off.data_ptr(),
+                              roads.bbox.data_ptr(), roads.n_roads, roads.n_rings, roads.n_verts)
+        td = N.RsTiles(tiles.pixels.data_ptr(), tiles.gt.data_ptr(), tiles.n_tiles, tiles.height, tiles.width,
+                       tiles.channels, tiles.dtype)
+        pd_ = N.RsPairs(pairs.road_pair_off.data_ptr(), pairs.pair_tile.data_ptr() if pairs.n_pairs else None, pairs.n_pairs)
+        prm = self._params(hist_mode, window, rescale, None if road_slot is None else road_slot.data_ptr())
+        st = self.lib.rs_zonal_hist_dev(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
+                                        hist.data_ptr(), nzero.data_ptr(), self._stream())
+        N.check(st, "rs_zonal_hist_dev", self._ctx)
+        if check:
+            self.sync_status()
+        return hist, nzero
+
+    def finalize_stats_dev(self, hist, n_allzero, nodata_mode: str = "none", ddof: int = 1,
+                           percentiles: Sequence[float] = (), check: bool = True):
+        torch = self._torch()
+        R, Cc = int(hist.shape[0]), int(hist.shape[1])
+        pct = np.ascontiguousarray(percentiles, np.float64)
+        out = torch.empty((R, Cc, N.RS_NSTAT + len(pct)), dtype=torch.float64, device=hist.device)
+        st = self.lib.rs_finalize_stats_dev(self._ctx, hist.data_ptr(), None if n_allzero is None else n_allzero.data_ptr(),
+                                            R, Cc, _NODATA_MODES[nodata_mode], int(ddof),
+                                            _np_ptr(pct) if len(pct) else None, len(pct), out.data_ptr(), self._stream())
+        N.check(st, "rs_finalize_stats_dev", self._ctx)
+        if check:
+            self.sync_status()
+        return out
+
+    def vote_metrics_dev(self, joint_hist, gt_class, cutoffs: Sequence[int], rule: str = "count",
+                         min_area_frac: float = 0.0, want_scores: bool = True, check: bool = True):
+        torch = self._torch()
+        dev = joint_hist.device
+        R = int(joint_hist.shape[0])
+        cut = np.ascontiguousarray(cutoffs, np.int32)
+        T = len(cut)
+        cover = torch.empty((T, R), dtype=torch.int8, device=dev)
+        scores = torch.empty((T, R, 3), dtype=torch.float64, device=dev) if want_scores else None
+        conf = torch.empty((T, 2, 4), dtype=torch.int64, device=dev)
+        met = torch.empty((T, N.RS_NMETRIC), dtype=torch.float64, device=dev)
+        st = self.lib.rs_vote_metrics_dev(self._ctx, joint_hist.data_ptr(), None if gt_class is None else gt_class.data_ptr(),
+                                          R, _np_ptr(cut), T, _RULES[rule], float(min_area_frac), cover.data_ptr(),
+                                          None if scores is None else scores.data_ptr(), conf.data_ptr(), met.data_ptr(),
+                                          self._stream())
+        N.check(st, "rs_vote_metrics_dev", self._ctx)
+        if check:
+            self.sync_status()
+        return cover, scores, conf, met
+
+    def sync_status(self):
+        st = self.lib.rs_ctx_sync_status(self._ctx, self._stream())
+        N.check(st, "kernel status", self._ctx)
+
+
+_default: dict = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (the reference-shaped helpers use it)."""
+    e = _default.get(device)
+    if e is None:
+        e = _default[device] = Engine(device)
+    return e
