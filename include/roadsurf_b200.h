@@ -171,6 +171,17 @@ int rs_finalize_stats_host(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_
                            int32_t n_pct, double *stats);
 
 /*
+ * One call from host buffers to the per-road statistics table: rs_zonal_hist + rs_finalize_stats with
+ * the histograms staying on the device in between.  This is the batched form of the whole
+ * statistical_analysis.py:179-246 block (pixel loop + groupby stats) and what bench.py times as e2e.
+ * stats double[n_roads][channels][RS_NSTAT + n_pct] (required); hist / n_allzero optional (NULL = not
+ * copied back).  prm->road_slot must be NULL.
+ */
+int rs_zonal_stats_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                        const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
+                        int32_t n_pct, double *stats, uint32_t *hist, uint32_t *n_allzero);
+
+/*
  * Per-road vote, tags, confusion counts and F1 for a list of score cut-offs in one launch.
  * Replaces determine_class.determine_detected_class (scripts/road_segmentation/determine_class.py:122-190),
  * final_metrics.get_tag / get_metrics (scripts/road_segmentation/final_metrics.py:91-105, :22-89)

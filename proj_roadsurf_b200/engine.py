@@ -144,6 +144,33 @@ class Engine:
         N.check(st, "rs_zonal_hist_host", self._ctx)
         return hist, nzero
 
+    def zonal_stats_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, window: str = "crop", rescale=None,
+                         nodata_mode: str = "none", ddof: int = 1, percentiles: Sequence[float] = (),
+                         want_hist: bool = False):
+        """Host buffers in, statistics table out, in ONE C call (rs_zonal_stats_host): the batched form of
+        statistical_analysis.py:179-246.  Returns stats (R, C, RS_NSTAT + n_pct) [, hist, n_allzero]."""
+        px = np.ascontiguousarray(tiles.pixels) if isinstance(tiles.pixels, np.ndarray) else tiles.pixels
+        dtype = N.RS_U16 if px.dtype == np.uint16 else N.RS_U8
+        R, Cc = roads.n_roads, tiles.channels
+        pct = np.ascontiguousarray(percentiles, np.float64)
+        stats = np.zeros((R, Cc, N.RS_NSTAT + len(pct)), np.float64)
+        hist = np.zeros((R, Cc, 256), np.uint32) if want_hist else None
+        nzero = np.zeros(R, np.uint32) if want_hist else None
+        xy = np.ascontiguousarray(roads.xy, np.float64)
+        ro, rro = np.ascontiguousarray(roads.ring_off, np.int32), np.ascontiguousarray(roads.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        rpo, pt = np.ascontiguousarray(pairs.road_pair_off, np.int32), np.ascontiguousarray(pairs.pair_tile, np.int32)
+        gt = np.ascontiguousarray(tiles.gt, np.float64)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), R, roads.n_rings, roads.n_verts)
+        td = N.RsTiles(_np_ptr(px), _np_ptr(gt), tiles.n_tiles, tiles.height, tiles.width, tiles.channels, dtype)
+        pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
+        prm = self._params("bands", window, rescale, None)
+        st = self.lib.rs_zonal_stats_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
+                                          _NODATA_MODES[nodata_mode], int(ddof), _np_ptr(pct) if len(pct) else None,
+                                          len(pct), _np_ptr(stats), _np_ptr(hist), _np_ptr(nzero))
+        N.check(st, "rs_zonal_stats_host", self._ctx)
+        return (stats, hist, nzero) if want_hist else stats
+
     def rasterize_pairs_host(self, roads: RoadSet, gt: np.ndarray, height: int, width: int, pairs: PairList,
                              window: str = "crop") -> np.ndarray:
         """uint8 masks (n_pairs, H, W), 1 = pixel selected for that (road, tile) pair."""
@@ -269,11 +296,13 @@ class Engine:
         return hist, nzero
 
     def finalize_stats_dev(self, hist, n_allzero, nodata_mode: str = "none", ddof: int = 1,
-                           percentiles: Sequence[float] = (), check: bool = True):
+                           percentiles: Sequence[float] = (), out=None, check: bool = True):
         torch = self._torch()
         R, Cc = int(hist.shape[0]), int(hist.shape[1])
         pct = np.ascontiguousarray(percentiles, np.float64)
-        out = torch.empty((R, Cc, N.RS_NSTAT + len(pct)), dtype=torch.float64, device=hist.device)
+        if out is None:
+            out = torch.empty((R, Cc, N.RS_NSTAT + len(pct)), dtype=torch.float64, device=hist.device)
+        assert tuple(out.shape) == (R, Cc, N.RS_NSTAT + len(pct)) and out.dtype == torch.float64 and out.is_contiguous()
         st = self.lib.rs_finalize_stats_dev(self._ctx, hist.data_ptr(), None if n_allzero is None else n_allzero.data_ptr(),
                                             R, Cc, _NODATA_MODES[nodata_mode], int(ddof),
                                             _np_ptr(pct) if len(pct) else None, len(pct), out.data_ptr(), self._stream())

@@ -122,8 +122,20 @@ class RoadSet:
         return [self.xy[self.ring_off[g]:self.ring_off[g + 1]] for g in range(g0, g1)]
 
     def subset(self, road_idx: np.ndarray) -> "RoadSet":
-        return RoadSet.from_geometries([self.rings(int(r)) for r in road_idx],
-                                       None if self.ids is None else self.ids[road_idx])
+        """The roads `road_idx` (any order, repeats allowed) as a new compact soup; vectorised gathers."""
+        road_idx = np.asarray(road_idx, np.int64)
+        g0 = self.road_ring_off[road_idx].astype(np.int64)
+        ng = self.road_ring_off[road_idx + 1].astype(np.int64) - g0
+        new_rro = np.zeros(len(road_idx) + 1, np.int64)
+        new_rro[1:] = np.cumsum(ng)
+        ring_src = np.repeat(g0 - new_rro[:-1], ng) + np.arange(new_rro[-1])           # old ring of each new ring
+        v0 = self.ring_off[ring_src].astype(np.int64)
+        nv = self.ring_off[ring_src + 1].astype(np.int64) - v0
+        new_ro = np.zeros(len(ring_src) + 1, np.int64)
+        new_ro[1:] = np.cumsum(nv)
+        vert_src = np.repeat(v0 - new_ro[:-1], nv) + np.arange(new_ro[-1])
+        return RoadSet(np.ascontiguousarray(self.xy[vert_src]), new_ro.astype(np.int32), new_rro.astype(np.int32),
+                       np.ascontiguousarray(self.bbox[road_idx]), None if self.ids is None else self.ids[road_idx])
 
 
 def xyz_tile_transform(tx: int, ty: int, z: int, size: int = 256) -> Tuple[float, ...]:
@@ -199,6 +211,24 @@ class PairList:
         if off[-1] >= 2 ** 31 - 1:
             raise ValueError("too many pairs for int32 offsets")
         return PairList(off.astype(np.int32), tile_idx.astype(np.int32))
+
+    def restrict_tiles(self, tile_lo: int, tile_hi: int) -> "PairList":
+        """Pairs whose tile index lies in [tile_lo, tile_hi), tile indices rebased to tile_lo
+        (what a tile shard keeps); road numbering unchanged."""
+        keep = (self.pair_tile >= tile_lo) & (self.pair_tile < tile_hi)
+        csum = np.concatenate([[0], np.cumsum(keep)])
+        off = csum[self.road_pair_off.astype(np.int64)]
+        return PairList(off.astype(np.int32), (self.pair_tile[keep] - tile_lo).astype(np.int32))
+
+    def take_roads(self, road_idx: np.ndarray) -> "PairList":
+        """Pair list of the roads `road_idx`, renumbered 0..len-1 in that order."""
+        road_idx = np.asarray(road_idx, np.int64)
+        p0 = self.road_pair_off[road_idx].astype(np.int64)
+        n = self.road_pair_off[road_idx + 1].astype(np.int64) - p0
+        off = np.zeros(len(road_idx) + 1, np.int64)
+        off[1:] = np.cumsum(n)
+        src = np.repeat(p0 - off[:-1], n) + np.arange(off[-1])
+        return PairList(off.astype(np.int32), np.ascontiguousarray(self.pair_tile[src]))
 
     def road_of_pair(self) -> np.ndarray:
         return np.repeat(np.arange(len(self.road_pair_off) - 1, dtype=np.int32), np.diff(self.road_pair_off))

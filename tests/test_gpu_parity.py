@@ -1,0 +1,394 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: -m gpu.
+
+Integer outputs (masks, histograms, counts, cover codes, confusion counts) must be bit-exact;
+float outputs (mean, std, margin, percentiles, P/R/F1) within 1e-6 relative (north star), and
+in practice they are compared at 1e-12 because both sides evaluate the same float64 formula on
+identical integers.
+"""
+import numpy as np
+import pytest
+
+from oracle import cport, gdal_fill, raster as oraster, stats as ostats, vote as ovote
+from proj_roadsurf_b200 import synth
+from proj_roadsurf_b200.geometry import PairList, RoadSet, TileBatch, pairs_by_bbox
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6       # north-star tolerance for float outputs
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from proj_roadsurf_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def ring(*pts):
+    pts = list(pts)
+    if pts[0] != pts[-1]:
+        pts.append(pts[0])
+    return np.array(pts, np.float64)
+
+
+def oracle_hist(rr_roads: RoadSet, pairs: PairList, tiles, gt, **kw):
+    return cport.zonal_accumulate(rr_roads.xy, rr_roads.ring_off, rr_roads.road_ring_off, pairs.road_pair_off,
+                                  pairs.pair_tile, tiles, gt, **kw)
+
+
+# ------------------------------------------------------------------------------------------
+# masks: rasterio.features.rasterize (identity / north-up transform) and mask.mask(crop=True)
+# ------------------------------------------------------------------------------------------
+KAT_SHAPES = [
+    ("integer_rect", [ring((2, 1), (6, 1), (6, 4), (2, 4))], (8, 8)),
+    ("on_centres_cw", [ring((1.5, 1.5), (4.5, 1.5), (4.5, 3.5), (1.5, 3.5))], (6, 8)),
+    ("on_centres_ccw", [ring((1.5, 1.5), (1.5, 3.5), (4.5, 3.5), (4.5, 1.5))], (6, 8)),
+    ("triangle_vertex_on_scanline", [ring((1, 0), (7, 0), (4, 2.5))], (4, 8)),
+    ("hole", [ring((0, 0), (10, 0), (10, 10), (0, 10)), ring((3, 3), (3, 7), (7, 7), (7, 3))], (10, 10)),
+    ("even_odd_parts", [ring((0, 0), (6, 0), (6, 4), (0, 4)), ring((4, 0), (10, 0), (10, 4), (4, 4))], (4, 10)),
+    ("partly_outside", [ring((-5, -5), (3, -5), (3, 2), (-5, 2))], (8, 8)),
+    ("fully_outside", [ring((20, 20), (30, 20), (30, 30), (20, 30))], (8, 8)),
+    ("covers_all", [ring((-100, -100), (100, -100), (100, 100), (-100, 100))], (8, 8)),
+    ("sliver_empty", [ring((2.6, 0), (2.9, 0), (2.9, 5), (2.6, 5))], (5, 8)),
+    ("sliver_one_col", [ring((2.4, 0), (2.6, 0), (2.6, 5), (2.4, 5))], (5, 8)),
+    ("unclosed", [ring((1, 1), (6, 1), (6, 5), (1, 5))[:-1]], (8, 8)),
+]
+
+
+@pytest.mark.parametrize("name,rings,shape", KAT_SHAPES, ids=[k[0] for k in KAT_SHAPES])
+def test_rasterize_kat(eng, name, rings, shape):
+    H, W = shape
+    roads = RoadSet.from_geometries([rings])
+    pairs = PairList.from_pairs(1, [0], [0])
+    gt = np.array([[1.0, 0, 0, 0, 1.0, 0]])
+    m = eng.rasterize_pairs_host(roads, gt, H, W, pairs, window="full")[0]
+    assert np.array_equal(m, gdal_fill.rasterize(rings, (H, W))), name
+    # crop=True window: same selected pixels (expanded to the full raster by the oracle)
+    m2 = eng.rasterize_pairs_host(roads, gt, H, W, pairs, window="crop")[0]
+    assert np.array_equal(m2, oraster.pair_inside_mask(gt[0], rings, W, H)), name
+
+
+def _random_polygon(rng, W, H, n):
+    ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+    rad = rng.uniform(0.2, 1.0, n) * min(W, H) * 0.6
+    cx, cy = rng.uniform(-0.2 * W, 1.2 * W), rng.uniform(-0.2 * H, 1.2 * H)
+    pts = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], 1)
+    if rng.random() < 0.3:   # half-pixel lattice: ties, horizontal edges on scanlines
+        pts = np.round(pts * 2) / 2
+    return np.concatenate([pts, pts[:1]])
+
+
+@pytest.mark.parametrize("window", ["full", "crop"])
+def test_rasterize_random_polygons_bit_exact(eng, window):
+    rng = np.random.default_rng(20261018)
+    H, W = 48, 40
+    geoms = [[_random_polygon(rng, W, H, int(rng.integers(3, 14))) for _ in range(int(rng.integers(1, 4)))]
+             for _ in range(400)]
+    roads = RoadSet.from_geometries(geoms)
+    n = roads.n_roads
+    pairs = PairList.from_pairs(n, np.arange(n), np.zeros(n, int))
+    gt = np.array([[1.0, 0, 0, 0, 1.0, 0]])
+    masks = eng.rasterize_pairs_host(roads, gt, H, W, pairs, window=window)
+    for i, rings in enumerate(geoms):
+        exp = cport.rasterize(rings, (H, W)) if window == "full" else cport.pair_mask_full(gt[0], rings, W, H)
+        assert np.array_equal(masks[i], exp), i
+
+
+def test_rasterize_world_transform_tiles(eng):
+    """north-up EPSG:3857 zoom-18 transforms: inverse geotransform arithmetic."""
+    g = synth.Grid(4, 4)
+    rr = synth.ribbon_roads(g, 24, seed=5)
+    gt = g.transforms()
+    masks = eng.rasterize_pairs_host(rr.roads, gt, 256, 256, rr.pairs, window="crop")
+    road_of = rr.pairs.road_of_pair()
+    assert rr.pairs.n_pairs > 0
+    total = 0
+    for p in range(rr.pairs.n_pairs):
+        exp = cport.pair_mask_full(gt[rr.pairs.pair_tile[p]], rr.roads.rings(int(road_of[p])), 256, 256)
+        assert np.array_equal(masks[p], exp), p
+        total += int(exp.sum())
+    assert total > 10000
+
+
+# ------------------------------------------------------------------------------------------
+# fused rasterize + zonal histograms
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["uniform", "asphalt"])
+def test_zonal_hist_bands_u8(eng, channels, kind):
+    g = synth.Grid(8, 8)
+    rr = synth.ribbon_roads(g, 48, seed=11 + channels)
+    tiles = synth.host_tiles(g, channels, kind)
+    gt = g.transforms()
+    tb = TileBatch.from_arrays(tiles, gt)
+    hist, nz = eng.zonal_hist_host(rr.roads, tb, rr.pairs)
+    oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt)
+    assert hist.shape == (48, channels, 256)
+    assert oh.sum() > 50000
+    assert np.array_equal(hist.astype(np.uint64), oh)
+    assert np.array_equal(nz.astype(np.uint64), onz)
+    assert onz.sum() > 0          # the all-bands-zero pixels are exercised
+
+
+def test_zonal_hist_python_oracle_cross_check(eng):
+    """the slow numpy/pure-Python oracle (gdal_fill + raster) on a small case"""
+    g = synth.Grid(3, 3)
+    rr = synth.ribbon_roads(g, 6, seed=3)
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    road_of = rr.pairs.road_of_pair()
+    pl = [(int(t), int(r)) for t, r in zip(rr.pairs.pair_tile, road_of)]
+    oh, onz = oraster.zonal_accumulate(tiles, gt, [rr.roads.rings(r) for r in range(6)], pl)
+    hist, nz = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs)
+    assert np.array_equal(hist.astype(np.uint64), oh)
+    assert np.array_equal(nz.astype(np.uint64), onz)
+
+
+def test_zonal_hist_class_score(eng):
+    g = synth.Grid(6, 6)
+    rr = synth.ribbon_roads(g, 32, seed=21)
+    tiles = synth.host_tiles(g, 2, "class_score")
+    gt = g.transforms()
+    hist, nz = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs, hist_mode="class_score")
+    oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt, joint=True)
+    assert hist.shape == (32, 3, 256)
+    assert np.array_equal(hist.astype(np.uint64), oh)
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_zonal_hist_u16_rescale(eng, f32):
+    from proj_roadsurf_b200.engine import scale_params
+    g = synth.Grid(4, 4)
+    rr = synth.ribbon_roads(g, 16, seed=31)
+    tiles = synth.host_tiles(g, 4, dtype=np.uint16)
+    gt = g.transforms()
+    smin, smax = [150.0, 300.0, 300.0, 300.0], [9000.0, 6000.0, 6000.0, 6000.0]   # NIR range, then RGB range x3
+    k, off = scale_params(smin, smax, f32)
+    hist, nz = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs, rescale=(k, off, f32))
+    oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt, scale_k=k, scale_off=off, rescale_f32=f32)
+    assert np.array_equal(hist.astype(np.uint64), oh)
+    assert np.array_equal(nz.astype(np.uint64), onz)
+    # the numpy restatement of gdal.Translate scaleParams agrees with the C one
+    px = tiles.reshape(-1, 4)[:5000]
+    a = oraster.rescale_u16_to_u8(px, smin, smax, f32)
+    ft = np.float32 if f32 else np.float64
+    v = np.clip(px.astype(ft) * k.astype(ft) + off.astype(ft), 0, 255)
+    assert np.array_equal(a, (v + ft(0.5)).astype(np.int32).astype(np.uint8))
+
+
+def test_zonal_long_edge_lists_and_big_tiles(eng):
+    """config 5 shape: 1024 px tiles, wide polygons with thousands of vertices and holes."""
+    g = synth.Grid(2, 2, size=1024)
+    rng = np.random.default_rng(9)
+    X0, Y1 = g.origin
+    geoms = []
+    for i in range(6):
+        n = [300, 1200, 2600, 5000, 130, 9000][i]
+        ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+        rad = g.span * (0.35 + 0.25 * rng.random()) * (1 + 0.15 * np.sin(ang * (7 + i)) + 0.02 * rng.random(n))
+        c = np.array([X0 + g.span * (0.6 + 0.8 * rng.random()), Y1 - g.span * (0.6 + 0.8 * rng.random())])
+        ext = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        ext = np.concatenate([ext, ext[:1]])
+        rings = [ext]
+        for hq in range(i % 4):
+            hc = c + g.span * 0.12 * np.array([np.cos(hq * 2.1), np.sin(hq * 2.1)])
+            hr = g.span * 0.04
+            rings.append(ring((hc[0] - hr, hc[1] - hr), (hc[0] - hr, hc[1] + hr), (hc[0] + hr, hc[1] + hr), (hc[0] + hr, hc[1] - hr)))
+        geoms.append(rings)
+    roads = RoadSet.from_geometries(geoms)
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    tb = TileBatch.from_arrays(tiles, gt)
+    pairs = pairs_by_bbox(roads, tb)
+    assert pairs.n_pairs >= 12
+    hist, nz = eng.zonal_hist_host(roads, tb, pairs)
+    oh, onz = oracle_hist(roads, pairs, tiles, gt)
+    assert oh[:, 0].sum() > 500000
+    assert np.array_equal(hist.astype(np.uint64), oh)
+    assert np.array_equal(nz.astype(np.uint64), onz)
+
+
+def test_zonal_edge_cases(eng):
+    g = synth.Grid(2, 2)
+    gt = g.transforms()
+    tiles = synth.host_tiles(g, 3)
+    tb = TileBatch.from_arrays(tiles, gt)
+    X0, Y1 = g.origin
+    far = ring((X0 - 900, Y1 + 900), (X0 - 800, Y1 + 900), (X0 - 800, Y1 + 800), (X0 - 900, Y1 + 800))
+    inside = ring((X0 + 10, Y1 - 10), (X0 + 60, Y1 - 10), (X0 + 60, Y1 - 50), (X0 + 10, Y1 - 50))
+    roads = RoadSet.from_geometries([[far], [inside], [inside], []])
+    # road 0 paired with tiles it misses; road 1 paired; road 2 has no pair; road 3 has no ring
+    pairs = PairList.from_pairs(4, [0, 0, 1, 1, 3], [0, 3, 0, 1, 0])
+    hist, nz = eng.zonal_hist_host(roads, tb, pairs)
+    oh, onz = oracle_hist(roads, pairs, tiles, gt)
+    assert np.array_equal(hist.astype(np.uint64), oh)
+    assert hist[0].sum() == 0 and hist[2].sum() == 0 and hist[3].sum() == 0 and hist[1].sum() > 0
+    # no roads at all / no pairs at all
+    empty = RoadSet.from_geometries([])
+    h0, z0 = eng.zonal_hist_host(empty, tb, PairList.from_pairs(0, [], []))
+    assert h0.shape == (0, 3, 256)
+    h1, z1 = eng.zonal_hist_host(roads, tb, PairList.from_pairs(4, [], []))
+    assert h1.sum() == 0 and z1.sum() == 0
+
+
+def test_zonal_road_slots_merge_rows(eng):
+    """road_slot lets several polygons (e.g. the pieces of one road) fold into one output row"""
+    g = synth.Grid(4, 4)
+    rr = synth.ribbon_roads(g, 20, seed=77)
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    tb = TileBatch.from_arrays(tiles, gt)
+    slot = (np.arange(20) + 5).astype(np.int32)          # a permutation-free shift into a larger table
+    hist, nz = eng.zonal_hist_host(rr.roads, tb, rr.pairs, road_slot=slot, n_slots=32)
+    oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt)
+    assert hist.shape == (32, 3, 256)
+    assert np.array_equal(hist[5:25].astype(np.uint64), oh)
+    assert hist[:5].sum() == 0 and hist[25:].sum() == 0
+
+
+def test_zonal_rotated_transform_is_rejected(eng):
+    from proj_roadsurf_b200._native import NativeError
+    roads = RoadSet.from_geometries([[ring((1, 1), (5, 1), (5, 5), (1, 5))]])
+    pairs = PairList.from_pairs(1, [0], [0])
+    tiles = np.zeros((1, 8, 8, 3), np.uint8)
+    gt = np.array([[1.0, 0.2, 0, 0.1, 1.0, 0]])
+    with pytest.raises(NativeError) as ei:
+        eng.zonal_hist_host(roads, TileBatch.from_arrays(tiles, gt), pairs)
+    assert ei.value.status == -4
+
+
+def test_device_family_matches_host_family(eng):
+    import torch
+    g = synth.Grid(8, 8)
+    rr = synth.ribbon_roads(g, 48, seed=5)
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    tb = TileBatch.from_arrays(tiles, gt)
+    hist, nz = eng.zonal_hist_host(rr.roads, tb, rr.pairs)
+    dr, dp, dt = eng.upload_roads(rr.roads), eng.upload_pairs(rr.pairs), eng.upload_tiles(tb)
+    dh, dz = eng.zonal_hist_dev(dr, dt, dp)
+    torch.cuda.synchronize()
+    assert np.array_equal(dh.cpu().numpy().view(np.uint32), hist)
+    assert np.array_equal(dz.cpu().numpy().view(np.uint32), nz)
+    # determinism: integer outputs identical run to run
+    dh2, dz2 = eng.zonal_hist_dev(dr, dt, dp)
+    assert torch.equal(dh, dh2) and torch.equal(dz, dz2)
+
+
+def test_synth_tiles_device_generator_feeds_both_sides(eng):
+    """on-device synthetic tiles copied back are what the oracle sees: full-size-style check"""
+    import torch
+    g = synth.Grid(16, 8)
+    rr = synth.ribbon_roads(g, 64, seed=13)
+    gt = g.transforms()
+    dt = eng.synth_tiles_dev(g.keys(), 256, 256, 3, kind=1, gt=gt)
+    dh, dz = eng.zonal_hist_dev(eng.upload_roads(rr.roads), dt, eng.upload_pairs(rr.pairs))
+    torch.cuda.synchronize()
+    tiles = dt.pixels.cpu().numpy()
+    oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt, threads=4)
+    assert np.array_equal(dh.cpu().numpy().view(np.uint32).astype(np.uint64), oh)
+    assert np.array_equal(dz.cpu().numpy().view(np.uint32).astype(np.uint64), onz)
+
+
+# ------------------------------------------------------------------------------------------
+# statistics from histograms
+# ------------------------------------------------------------------------------------------
+def _rand_hists(rng, R, C):
+    h = np.zeros((R, C, 256), np.uint32)
+    for r in range(R):
+        for c in range(C):
+            mode = rng.integers(0, 5)
+            if mode == 0:
+                continue                                   # empty
+            if mode == 1:
+                h[r, c, rng.integers(0, 256)] = 1          # n = 1: std NaN with ddof 1
+            elif mode == 2:
+                h[r, c, rng.integers(0, 256, 2)] += 1
+            elif mode == 3:
+                h[r, c] = rng.integers(0, 50, 256)
+            else:
+                k = rng.integers(100, 120)
+                h[r, c, k - 5:k + 5] = rng.integers(0, 100000, 10)
+    return h
+
+
+@pytest.mark.parametrize("ddof", [0, 1])
+def test_finalize_stats_raw(eng, ddof):
+    rng = np.random.default_rng(1)
+    h = _rand_hists(rng, 40, 3)
+    pct = [0.0, 5.0, 25.0, 50.0, 90.0, 99.5, 100.0]
+    out = eng.finalize_stats_host(h, None, nodata_mode="raw", ddof=ddof, percentiles=pct)
+    from proj_roadsurf_b200._native import STAT_COLS
+    col = {k: i for i, k in enumerate(STAT_COLS)}
+    for r in range(40):
+        for c in range(3):
+            s = ostats.stats_from_hist(h[r, c], ddof=ddof, percentiles=pct)
+            o = out[r, c]
+            assert o[col["count"]] == s["count"]
+            if s["count"] == 0:
+                assert np.isnan(o[1:]).all()
+                continue
+            assert o[col["min"]] == s["min"] and o[col["max"]] == s["max"]          # bit-exact integers
+            assert o[col["median"]] == s["median"]
+            v = ostats.expand_hist(h[r, c])
+            assert o[col["sum"]] == v.sum() and o[col["sumsq"]] == (v * v).sum()
+            np.testing.assert_allclose(o[col["mean"]], s["mean"], rtol=RTOL)
+            if np.isnan(s["std"]):
+                assert np.isnan(o[col["std"]])
+            else:
+                np.testing.assert_allclose(o[col["std"]], s["std"], rtol=RTOL, atol=1e-9)
+                np.testing.assert_allclose(o[col["margin"]], 2 * s["std"] / np.sqrt(s["count"]), rtol=RTOL, atol=1e-9)
+            for i, q in enumerate(pct):
+                np.testing.assert_allclose(o[len(STAT_COLS) + i], s[f"percentile_{q:g}"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("mode,omode", [("none", "N"), ("zero", "Z")])
+def test_finalize_stats_nodata_conventions(eng, mode, omode):
+    g = synth.Grid(4, 4)
+    rr = synth.ribbon_roads(g, 24, seed=8)
+    tiles = synth.host_tiles(g, 3)
+    tiles[..., 1][tiles[..., 0] < 40] = 0          # bands with different numbers of zeros
+    gt = g.transforms()
+    hist, nz = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs)
+    out = eng.finalize_stats_host(hist, nz, nodata_mode=mode, ddof=1)
+    adj = ostats.apply_nodata_convention(hist, nz, omode)
+    for r in range(24):
+        for c in range(3):
+            s = ostats.stats_from_hist(adj[r, c], ddof=1)
+            assert out[r, c, 0] == s["count"]
+            if s["count"] > 1:
+                assert out[r, c, 1] == s["min"] and out[r, c, 2] == s["max"] and out[r, c, 7] == s["median"]
+                np.testing.assert_allclose(out[r, c, 5], s["mean"], rtol=RTOL)
+                np.testing.assert_allclose(out[r, c, 6], s["std"], rtol=RTOL)
+
+
+# ------------------------------------------------------------------------------------------
+# vote + confusion + F1
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rule", ["count", "score"])
+@pytest.mark.parametrize("min_area_frac", [0.0, 0.05])
+def test_vote_metrics_sweep(eng, rule, min_area_frac):
+    g = synth.Grid(8, 8)
+    rr = synth.ribbon_roads(g, 96, seed=41)
+    tiles = synth.host_tiles(g, 2, "class_score")
+    gt = g.transforms()
+    jh, _ = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs, hist_mode="class_score")
+    gtc = rr.gt_class.copy()
+    gtc[::17] = -1                                  # roads outside the ground truth are skipped
+    cuts = ovote.score_cutoffs()
+    cover, scores, conf, met = eng.vote_metrics_host(jh, gtc, cuts, rule=rule, min_area_frac=min_area_frac)
+    keep = gtc >= 0
+    from proj_roadsurf_b200._native import METRIC_COLS
+    for i, c in enumerate(cuts):
+        ocov, ia, inn, diff = ovote.raster_vote(jh, int(c), rule, min_area_frac)
+        assert np.array_equal(cover[i], ocov.astype(np.int8)), (i, c)
+        m = ovote.confusion(ocov[keep], gtc[keep])
+        assert np.array_equal(conf[i], m)
+        om = ovote.metrics_from_confusion(m)
+        np.testing.assert_allclose(scores[i, :, 0], ia, rtol=1e-12)
+        np.testing.assert_allclose(scores[i, :, 1], inn, rtol=1e-12)
+        for j, name in enumerate(METRIC_COLS):
+            key = {"P0": "P_0", "R0": "R_0", "F0": "f1_0", "P1": "P_1", "R1": "R_1", "F1": "f1_1"}.get(name, name)
+            np.testing.assert_allclose(met[i, j], om[key], rtol=RTOL, atol=1e-15)
+    assert len(set(cover[0].tolist())) >= 3
