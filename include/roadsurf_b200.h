@@ -43,10 +43,10 @@ enum rs_status {
     RS_OK = 0,
     RS_ERR_INVALID_ARG = -1,   /* NULL pointer, negative size, misaligned xy, bad enum            */
     RS_ERR_CUDA = -2,          /* a CUDA runtime call failed (rs_ctx_last_cuda_error for details)  */
-    RS_ERR_CAPACITY = -3,      /* a scanline produced more crossings than the on-chip pool holds  */
+    RS_ERR_CAPACITY = -3,      /* reserved (the bit-mask fill has no per-scanline crossing limit)  */
     RS_ERR_ROTATED = -4,       /* a tile transform has b != 0 or d != 0                           */
     RS_ERR_NO_DEVICE = -5,     /* no CUDA device / device is not sm_100                           */
-    RS_ERR_UNSUPPORTED = -6    /* width > 32766, channels not in 1..4, dtype/channels combination */
+    RS_ERR_UNSUPPORTED = -6    /* width > 4096, channels not in 1..4, dtype/channels combination  */
 };
 
 enum rs_dtype { RS_U8 = 0, RS_U16 = 1 };

@@ -5,27 +5,32 @@
 // scripts/functions/fct_misc.py:57-123 get_pixel_values = rasterio.mask.mask(crop=True) (:77,
 // GDAL GDALRasterizeGeometries -> GDALdllImageFilledPolygon) + np.extract (:95).
 //
-// Work decomposition: one TEAM (a warp, or a whole CTA for long edge lists) owns one road and
-// folds all of that road's (tile) pairs into a TEAM-private shared-memory histogram, so every
-// output row is written exactly once with plain 128-bit stores: no global atomics, no output
-// clearing, results independent of scheduling.
+// Work decomposition
+//   item  = up to PPI consecutive (road, tile) pairs of ONE road (prep_items_kernel builds the list);
+//   team  = one warp; teams pull items from a global counter (persistent grid, whole waves of CTAs);
+//   a team folds its item into a team-private shared-memory histogram; a road that fits one item is
+//   written once with plain 128-bit stores, a road split over several items is pre-zeroed by
+//   prep_items_kernel and merged with integer atomics (exact, order-independent).
 //
-// Per pair and per chunk of <= RC scanlines the algorithm is work-optimal, O(E + X + P) for E
-// edges, X scanline crossings and P covered pixels (GDAL's loop is O(rows * E)):
-//   pass 1   each lane takes edges; an edge is active on the contiguous row range
-//            [ya, yb] = { y : y_low <= y + 0.5 < y_high } (GDAL's half-open rule), so per-row
-//            crossing counts are a difference array (two shared atomics per edge) + prefix sum;
-//            per-edge crossing counts are prefix-summed too (load balancing of pass 2)
-//   pass 2   lanes take flattened (edge, row) crossings (binary search in the edge prefix),
-//            evaluate GDAL's intersect expression in IEEE binary64 without FMA contraction,
-//            round floor(x + 0.5) BEFORE sorting, and scatter into the row's slot range
-//   sort     one lane per row, insertion sort of that row's (few) int16 crossings
-//   spans    crossing pairs (2m, 2m+1) are the burn spans; sub-warp groups of G lanes take
-//            spans, lanes take pixels: uint8 interleaved bands -> shared histogram atomics
-//   hburn    horizontal edges lying exactly on a scanline (burnt separately by GDAL, only when
-//            running towards -x) are kept in a side list and folded in without double counting
-// Edge lists are staged in shared memory with TMA bulk copies (cp.async.bulk + mbarrier),
-// in chunks of ECAP vertices when a road is longer than that.
+// Per pair the even-odd scanline fill is evaluated on a BIT MASK instead of sorted crossing lists:
+//   GDAL sorts the rounded crossings c_0 <= c_1 <= ... of a scanline and burns [c_2i, c_2i+1 - 1]; for
+//   the even crossing counts closed rings produce, pixel x is burnt iff #{ j : c_j <= x } is odd.  So
+//   each crossing toggles one bit (atomicXor in shared memory), and the inside mask of a row is the
+//   prefix-XOR of its toggle bits (5 shift-xor steps per 32-bit word + a carry).  No sort, no pairing,
+//   no capacity limit on crossings per scanline; holes and overlapping parts cancel by construction.
+//   Horizontal edges lying exactly on a scanline (burnt separately by GDAL when they run towards -x)
+//   are OR-ed into the inside mask in a second edge pass that only runs when such an edge exists.
+// Phases per (pair, chunk of rows):
+//   cull     per-road vertex chunks carry bounds; a ballot keeps the chunks that can touch the window
+//   edges    lanes take edges (TMA-staged in shared memory), transform both ends with the pair's inverse
+//            geotransform (IEEE binary64, no FMA contraction), derive the contiguous active row range
+//            [ya, yb] = { y : y_low <= y + 0.5 < y_high }; a warp prefix sum flattens (edge, row)
+//            crossings over the lanes; each lane evaluates GDAL's intersect expression, rounds
+//            floor(x + 0.5) and toggles
+//   prefix   lane per row: toggle words -> inside words (in place), clipped to the window columns
+//   pixels   groups of 8 pixels with a non-zero mask byte are compacted into an entry list (warp scan);
+//            lanes take entries: 8 interleaved pixels arrive as 64/128-bit loads, mask bits predicate the
+//            shared-memory histogram atomics
 //
 // This translation unit is compiled with -fmad=false and uses explicit _rn intrinsics for the
 // geometry: the rounding of every operation is part of the specification.
@@ -35,6 +40,17 @@
 #include "rs_internal.h"
 
 namespace rs {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS = 4;        // teams per CTA
+constexpr int PPI = 16;         // pairs per work item
+constexpr int VCAP = 128;       // vertices staged in shared memory per road (longer roads read L2)
+constexpr int MASKW = 1024;     // mask words per team
+constexpr int RCMAX = 256;      // rows per mask chunk
+constexpr int ENTCAP = 512;     // 8-pixel group entries per batch
+constexpr int NCHUNK = 64;      // culling chunks per road
+constexpr int RINGCAP = 16;     // ring starts kept in shared memory
+constexpr int MAX_WIDTH = 8 * ENTCAP;
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copy (global -> shared)
@@ -84,12 +100,12 @@ struct ZonalArgs {
     const double *road_bbox;
     const int *road_pair_off;
     const int *pair_tile;
-    const int *road_list;     // optional: indices of the roads this launch handles
-    const int *n_list_dev;    // optional: device-resident length of road_list
-    int n_roads;              // number of work items when n_list_dev == nullptr
+    const int2 *items;        // (road, first pair)
+    const int *n_items;       // device-resident item count
     const void *pixels;
     const double *gt;
     int H, W;
+    int fast;                 // 1: 64/128-bit group loads are legal (W % 8 == 0, base 16-byte aligned)
     const int *road_slot;
     uint32_t *hist;
     uint32_t *nzero;
@@ -174,73 +190,98 @@ __device__ __forceinline__ int last_row_lt(double v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// pixel policies
+// pixel policies: a group is 8 consecutive pixels = NW 32-bit words in registers
 // ---------------------------------------------------------------------------------------------
+template <int OFF, int N>
+__device__ __forceinline__ uint32_t byte_at(const uint32_t (&r)[N]) { return (r[OFF >> 2] >> ((OFF & 3) * 8)) & 255u; }
+template <int OFF, int N>
+__device__ __forceinline__ uint32_t half_at(const uint32_t (&r)[N]) { return (r[OFF >> 2] >> ((OFF & 3) * 8)) & 0xffffu; }
+
 template <int C_>
 struct PxBandsU8 {
-    static constexpr int C = C_, HC = C_, ELEM = 1;
+    static constexpr int C = C_, HC = C_, BPP = C_, NW = 2 * C_;
     static constexpr bool MASK = false;
-    __device__ static __forceinline__ void pixel(const ZonalArgs &a, size_t tile_idx, size_t pix, uint32_t *hist, uint32_t &nz)
+    template <int I>
+    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &nz)
     {
-        const uint8_t *p = (const uint8_t *)a.pixels + (tile_idx * (size_t)a.H * a.W + pix) * C;
-        uint32_t v[C];
-        if (C == 4) {
-            const uint32_t q = __ldg((const uint32_t *)p);
-            v[0] = q & 255u; v[1] = (q >> 8) & 255u; v[2 % C] = (q >> 16) & 255u; v[3 % C] = q >> 24;
-        } else if (C == 2) {
-            const uint32_t q = __ldg((const uint16_t *)p);
-            v[0] = q & 255u; v[1 % C] = q >> 8;
-        } else {
-#pragma unroll
-            for (int c = 0; c < C; c++) v[c] = __ldg(p + c);
-        }
         uint32_t any = 0;
 #pragma unroll
         for (int c = 0; c < C; c++) {
-            atomicAdd(&hist[c * 256 + v[c]], 1u);
-            any |= v[c];
+            const uint32_t v = (r[(I * C + c) >> 2] >> (((I * C + c) & 3) * 8)) & 255u;
+            atomicAdd(&hist[c * 256 + v], 1u);
+            any |= v;
+        }
+        nz += (any == 0);
+    }
+    __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
+    {
+        const uint8_t *p = (const uint8_t *)a.pixels + pix * C;
+        uint32_t any = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const uint32_t v = __ldg(p + c);
+            atomicAdd(&hist[c * 256 + v], 1u);
+            any |= v;
         }
         nz += (any == 0);
     }
 };
 
 struct PxClassScore {
-    static constexpr int C = 2, HC = 3, ELEM = 1;
+    static constexpr int C = 2, HC = 3, BPP = 2, NW = 4;
     static constexpr bool MASK = false;
-    __device__ static __forceinline__ void pixel(const ZonalArgs &a, size_t tile_idx, size_t pix, uint32_t *hist, uint32_t &nz)
+    __device__ static __forceinline__ void one(uint32_t cls, uint32_t score, uint32_t *hist, uint32_t &nz)
     {
-        const uint8_t *p = (const uint8_t *)a.pixels + (tile_idx * (size_t)a.H * a.W + pix) * 2;
-        const uint32_t q = __ldg((const uint16_t *)p);
-        uint32_t cls = q & 255u;
-        const uint32_t score = q >> 8;
+        nz += ((cls | score) == 0);
         if (cls > 2u) cls = 0u;   // unknown class codes count as "no detection"
         atomicAdd(&hist[cls * 256 + score], 1u);
-        nz += (q == 0);
+    }
+    template <int I>
+    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &nz)
+    {
+        one(byte_at<2 * I>(r), byte_at<2 * I + 1>(r), hist, nz);
+    }
+    __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
+    {
+        const uint8_t *p = (const uint8_t *)a.pixels + pix * 2;
+        one(__ldg(p), __ldg(p + 1), hist, nz);
     }
 };
 
 template <bool F32>
 struct PxU16x4Rescale {
-    static constexpr int C = 4, HC = 4, ELEM = 2;
+    static constexpr int C = 4, HC = 4, BPP = 8, NW = 16;
     static constexpr bool MASK = false;
-    __device__ static __forceinline__ void pixel(const ZonalArgs &a, size_t tile_idx, size_t pix, uint32_t *hist, uint32_t &nz)
+    __device__ static __forceinline__ uint32_t scale(const ZonalArgs &a, uint32_t s, int c)
     {
-        const uint16_t *p = (const uint16_t *)a.pixels + (tile_idx * (size_t)a.H * a.W + pix) * 4;
-        const uint2 q = __ldg((const uint2 *)p);
-        const uint32_t s[4] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16};
+        if (F32) {
+            float f = __fadd_rn(__fmul_rn((float)s, (float)a.sk[c]), (float)a.so[c]);
+            f = fminf(fmaxf(f, 0.0f), 255.0f);
+            return (uint32_t)(int)__fadd_rn(f, 0.5f);
+        }
+        double f = __dadd_rn(__dmul_rn((double)s, a.sk[c]), a.so[c]);
+        f = fmin(fmax(f, 0.0), 255.0);
+        return (uint32_t)(int)__dadd_rn(f, 0.5);
+    }
+    template <int I>
+    __device__ static __forceinline__ void pixel(const ZonalArgs &a, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &nz)
+    {
         uint32_t any = 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            uint32_t o;
-            if (F32) {
-                float f = __fadd_rn(__fmul_rn((float)s[c], (float)a.sk[c]), (float)a.so[c]);
-                f = fminf(fmaxf(f, 0.0f), 255.0f);
-                o = (uint32_t)(int)__fadd_rn(f, 0.5f);
-            } else {
-                double f = __dadd_rn(__dmul_rn((double)s[c], a.sk[c]), a.so[c]);
-                f = fmin(fmax(f, 0.0), 255.0);
-                o = (uint32_t)(int)__dadd_rn(f, 0.5);
-            }
+            const uint32_t o = scale(a, (r[(I * 8 + 2 * c) >> 2] >> (((I * 8 + 2 * c) & 3) * 8)) & 0xffffu, c);
+            atomicAdd(&hist[c * 256 + o], 1u);
+            any |= o;
+        }
+        nz += (any == 0);
+    }
+    __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
+    {
+        const uint16_t *p = (const uint16_t *)a.pixels + pix * 4;
+        uint32_t any = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t o = scale(a, __ldg(p + c), c);
             atomicAdd(&hist[c * 256 + o], 1u);
             any |= o;
         }
@@ -249,373 +290,440 @@ struct PxU16x4Rescale {
 };
 
 struct PxMask {
-    static constexpr int C = 1, HC = 0, ELEM = 1;
+    static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
     static constexpr bool MASK = true;
 };
 
-// ---------------------------------------------------------------------------------------------
-// team-wide helpers (one team per CTA: blockDim.x == TEAM)
-// ---------------------------------------------------------------------------------------------
-template <int TEAM>
-__device__ __forceinline__ void team_sync()
+// 8 pixels x BPP bytes from a (8*BPP)-byte aligned address into NW words
+template <int BPP, int NW>
+__device__ __forceinline__ void load_group(const uint8_t *p, uint32_t (&r)[NW])
 {
-    if (TEAM == 32) __syncwarp();
-    else __syncthreads();
-}
-
-// In-place exclusive prefix sum of a[0..n) in shared memory; returns the total to every thread.
-// If `inclusive`, a[i] becomes the inclusive sum instead.
-template <int TEAM>
-__device__ int team_scan(int *a, int n, bool inclusive, int *wsum)
-{
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int ipt = (n + TEAM - 1) / TEAM;
-    const int b = min(tid * ipt, n), e = min(b + ipt, n);
-    int s = 0;
-    for (int i = b; i < e; i++) s += a[i];
-    int incl = s;
+    if constexpr ((BPP & 1) == 0) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    int base = incl - s, total;
-    if (TEAM > 32) {
-        const int warp = tid >> 5;
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        int wbase = 0;
-        total = 0;
-#pragma unroll
-        for (int w = 0; w < TEAM / 32; w++) {
-            const int v = wsum[w];
-            if (w < warp) wbase += v;
-            total += v;
+        for (int i = 0; i < NW / 4; i++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+            r[4 * i] = q.x; r[4 * i + 1] = q.y; r[4 * i + 2] = q.z; r[4 * i + 3] = q.w;
         }
-        base += wbase;
-        __syncthreads();
     } else {
-        total = __shfl_sync(0xffffffffu, incl, 31);
-    }
-    int run = base;
-    for (int i = b; i < e; i++) {
-        const int v = a[i];
-        run += v;
-        a[i] = inclusive ? run : run - v;
-    }
-    team_sync<TEAM>();
-    return total;
-}
-
-// smallest i in [0, n) with a[i] > q (a non-decreasing); n if none
-__device__ __forceinline__ int upper_bound_smem(const int *a, int n, int q)
-{
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] > q) hi = mid;
-        else lo = mid + 1;
-    }
-    return lo;
-}
-
-// ---------------------------------------------------------------------------------------------
-// shared-memory layout
-// ---------------------------------------------------------------------------------------------
-template <int TEAM>
-struct Cfg;
-template <>
-struct Cfg<32> {
-    static constexpr int ECAP = 128;    // vertices staged per chunk
-    static constexpr int RC = 256;      // scanlines per chunk
-    static constexpr int CAP = 1024;    // crossings per scanline chunk
-    static constexpr int HB = 16;       // horizontal-edge burns per scanline chunk
-    static constexpr int G = 8;         // lanes per span
-};
-template <>
-struct Cfg<256> {
-    static constexpr int ECAP = 2048;
-    static constexpr int RC = 1024;
-    static constexpr int CAP = 16384;
-    static constexpr int HB = 128;
-    static constexpr int G = 32;
-};
-
-template <int TEAM, int HC>
-struct Smem {
-    using K = Cfg<TEAM>;
-    alignas(16) double2 verts[K::ECAP];
-    alignas(16) uint32_t hist[HC > 0 ? HC * 256 : 4];
-    int eoff[K::ECAP + 1];
-    int rowpos[K::RC + 2];
-    int hb[K::HB][4];               // y (chunk-relative), x first, x last, unused
-    int16_t pool[K::CAP];
-    alignas(8) uint64_t mbar;
-    int wsum[TEAM / 32 + 1];
-    int work;
-    int hb_count;
-};
-
-// ---------------------------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------------------------
-template <int TEAM, class PX>
-__global__ void __launch_bounds__(TEAM) zonal_kernel(const ZonalArgs a)
-{
-    using K = Cfg<TEAM>;
-    using S = Smem<TEAM, PX::HC>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    S &s = *reinterpret_cast<S *>(smem_raw);
-    const int tid = threadIdx.x;
-
-    if (tid == 0) mbar_init(&s.mbar, 1);
-    team_sync<TEAM>();
-    uint32_t mbar_phase = 0;
-
-    const int n_work = a.n_list_dev ? *a.n_list_dev : a.n_roads;
-
-    for (;;) {
-        if (tid == 0) s.work = atomicAdd(a.work_counter, 1);
-        team_sync<TEAM>();
-        const int wi = s.work;
-        team_sync<TEAM>();
-        if (wi >= n_work) break;
-        const int road = a.road_list ? a.road_list[wi] : wi;
-
-        if (!PX::MASK) {
-            for (int i = tid; i < PX::HC * 64; i += TEAM) reinterpret_cast<uint4 *>(s.hist)[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < NW / 2; i++) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p) + i);
+            r[2 * i] = q.x; r[2 * i + 1] = q.y;
         }
-        uint32_t nz = 0;
+    }
+}
 
-        const int g0 = a.road_ring_off[road], g1 = a.road_ring_off[road + 1];
-        const int v0 = a.ring_off[g0], v1 = a.ring_off[g1];
-        const int nv = v1 - v0;
-        const int nchunks = (nv + K::ECAP - 1) / K::ECAP;
-        const bool one_ring = (g1 - g0) == 1;
-        int cbase = 0, ccount = 0;      // vertex chunk currently staged in shared memory
-        int staged = -1;
+template <class PX, int I>
+__device__ __forceinline__ void group_pixels(const ZonalArgs &a, const uint32_t (&r)[PX::NW], uint32_t m8, uint32_t *hist, uint32_t &nz)
+{
+    if constexpr (I < 8) {
+        if (m8 & (1u << I)) PX::template pixel<I>(a, r, hist, nz);
+        group_pixels<PX, I + 1>(a, r, m8, hist, nz);
+    }
+}
 
-        auto stage_chunk = [&](int ch) {
-            if (staged == ch) return;
-            team_sync<TEAM>();          // everybody is done reading the previous chunk
-            cbase = ch * K::ECAP;
-            ccount = min(K::ECAP, nv - cbase);
-            if (tid == 0) {
-                const uint32_t bytes = (uint32_t)ccount * 16u;
-                mbar_arrive_expect_tx(&s.mbar, bytes);
-                tma_bulk_g2s(s.verts, a.xy + v0 + cbase, bytes, &s.mbar);
+// ---------------------------------------------------------------------------------------------
+// team shared memory
+// ---------------------------------------------------------------------------------------------
+template <int HC>
+struct TeamSmem {
+    alignas(16) double2 verts[VCAP];
+    alignas(16) uint32_t hist[HC > 0 ? HC * 256 : 4];
+    alignas(16) uint32_t mask[MASKW];
+    alignas(16) uint32_t rowmap[RCMAX];
+    uint32_t entries[ENTCAP];
+    double e_dx1[32], e_dy1[32], e_a[32], e_b[32];
+    int e_ya[32];
+    int e_off[33];
+    float cb_ymin[NCHUNK], cb_ymax[NCHUNK], cb_xmin[NCHUNK], cb_xmax[NCHUNK];
+    int ring_start[RINGCAP + 1];
+    alignas(8) uint64_t mbar;
+};
+
+__device__ __forceinline__ uint32_t prefix_xor32(uint32_t t)
+{
+    t ^= t << 1; t ^= t << 2; t ^= t << 4; t ^= t << 8; t ^= t << 16;
+    return t;
+}
+// bit 7 of every non-zero byte
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t m) { return (((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u; }
+
+// ---------------------------------------------------------------------------------------------
+// one work item
+// ---------------------------------------------------------------------------------------------
+template <class PX>
+__device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC> &s, const int road, const int pb,
+                                             const int lane, uint32_t &mbar_phase)
+{
+    const int rp0 = a.road_pair_off[road], rp1 = a.road_pair_off[road + 1];
+    const int pe = min(pb + PPI, rp1);
+    const bool split = (rp1 - rp0) > PPI;
+    const int g0 = a.road_ring_off[road], g1 = a.road_ring_off[road + 1];
+    const int v0 = a.ring_off[g0], nv = a.ring_off[g1] - v0;
+    const int nrings = g1 - g0;
+    const bool staged = nv > 0 && nv <= VCAP;
+
+    if (staged && lane == 0) {
+        const uint32_t bytes = (uint32_t)nv * 16u;
+        mbar_arrive_expect_tx(&s.mbar, bytes);
+        tma_bulk_g2s(s.verts, a.xy + v0, bytes, &s.mbar);
+    }
+    if constexpr (!PX::MASK) {
+        for (int i = lane; i < PX::HC * 64; i += 32) reinterpret_cast<uint4 *>(s.hist)[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (nrings > 1 && nrings <= RINGCAP)
+        for (int k = lane; k <= nrings; k += 32) s.ring_start[k] = a.ring_off[g0 + k] - v0;
+    uint32_t nz = 0;
+    if (staged) {
+        mbar_wait(&s.mbar, mbar_phase);
+        mbar_phase ^= 1u;
+    }
+    __syncwarp();
+
+    auto vertex = [&](int i) -> double2 { return staged ? s.verts[i] : __ldg(&a.xy[v0 + i]); };
+    // previous vertex of i along its ring (GDAL: the first index of a ring pairs with its last)
+    auto prev_index = [&](int i) -> int {
+        if (nrings == 1) return i == 0 ? nv - 1 : i - 1;
+        if (nrings <= RINGCAP) {
+            int p = i - 1;
+            for (int k = 0; k < nrings; k++)
+                if (s.ring_start[k] == i) p = s.ring_start[k + 1] - 1;
+            return p;
+        }
+        int lo = g0, hi = g1;       // ring containing vertex v0 + i
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (a.ring_off[mid] - v0 <= i) lo = mid;
+            else hi = mid;
+        }
+        const int rs_ = a.ring_off[lo] - v0, re_ = a.ring_off[lo + 1] - v0;
+        return i == rs_ ? re_ - 1 : i - 1;
+    };
+
+    // ---------------- culling chunks: bounds over the edges (i, prev(i)) of each vertex chunk ----------------
+    int cshift = 5;
+    while (((nv + (1 << cshift) - 1) >> cshift) > NCHUNK) cshift++;
+    const int nchunks = (nv + (1 << cshift) - 1) >> cshift;
+    for (int c = 0; c < nchunks; c++) {
+        float ymin = INFINITY, ymax = -INFINITY, xmin = INFINITY, xmax = -INFINITY;
+        const int cend = min(nv, (c + 1) << cshift);
+        for (int i = (c << cshift) + lane; i < cend; i += 32) {
+            const double2 q2 = vertex(i), q1 = vertex(prev_index(i));
+            ymin = fminf(ymin, __double2float_rd(fmin(q1.y, q2.y)));
+            ymax = fmaxf(ymax, __double2float_ru(fmax(q1.y, q2.y)));
+            xmin = fminf(xmin, __double2float_rd(fmin(q1.x, q2.x)));
+            xmax = fmaxf(xmax, __double2float_ru(fmax(q1.x, q2.x)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, o));
+            ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, o));
+            xmin = fminf(xmin, __shfl_xor_sync(FULL, xmin, o));
+            xmax = fmaxf(xmax, __shfl_xor_sync(FULL, xmax, o));
+        }
+        if (lane == 0) { s.cb_ymin[c] = ymin; s.cb_ymax[c] = ymax; s.cb_xmin[c] = xmin; s.cb_xmax[c] = xmax; }
+    }
+    __syncwarp();
+
+    const double *bb = a.road_bbox + 4 * (size_t)road;
+
+    for (int p = pb; p < pe && nv > 0; p++) {
+        const int t = a.pair_tile[p];
+        PairGeom g;
+        const int gr = pair_geometry(a.gt + 6 * (size_t)t, bb, a.W, a.H, a.window_mode, g);
+        if (gr < 0) {
+            if (lane == 0) atomicMin(a.status, gr);
+            continue;
+        }
+        if (gr == 0) continue;
+        const int cbcol = g.col_off & ~31;                              // absolute column of mask bit 0
+        const int pitch = ((g.col_off + g.w - 1) >> 5) - (cbcol >> 5) + 1;   // mask words per row
+        const int pp = pitch | 1;                                       // odd row stride: lane-per-row walks are conflict-free
+        const int lo = g.col_off - cbcol;                               // mask bit of window column 0
+        const int rcmax = min((int)RCMAX, (int)MASKW / pp);
+        const int rb_rows = max(1, min(32, (int)ENTCAP / (pitch * 4)));  // rows per entry batch
+
+        // chunks whose bounds can reach a window row and lie left of the window's right edge
+        unsigned long long rel = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int c = lane + 32 * half;
+            bool ok = false;
+            if (c < nchunks) {
+                const double ya_ = __dadd_rn(g.inv3, __dmul_rn((double)s.cb_ymin[c], g.inv5));
+                const double yb_ = __dadd_rn(g.inv3, __dmul_rn((double)s.cb_ymax[c], g.inv5));
+                const double xa_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmin[c], g.inv1));
+                const double xb_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmax[c], g.inv1));
+                ok = (fmax(ya_, yb_) + 1.0 >= 0.0) && (fmin(ya_, yb_) - 1.0 <= (double)g.h) && (fmin(xa_, xb_) - 1.0 <= (double)g.w);
             }
-            mbar_wait(&s.mbar, mbar_phase);
-            mbar_phase ^= 1u;
-            staged = ch;
-        };
-        auto vertex = [&](int i) -> double2 {
-            if (i >= cbase && i < cbase + ccount) return s.verts[i - cbase];
-            return a.xy[v0 + i];
-        };
-        // previous vertex of i along its ring (GDAL: the first index of a ring pairs with its last)
-        auto prev_index = [&](int i) -> int {
-            if (one_ring) return i == 0 ? nv - 1 : i - 1;
-            int lo = g0, hi = g1;       // ring containing vertex v0 + i
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (a.ring_off[mid] - v0 <= i) lo = mid;
-                else hi = mid;
+            rel |= (unsigned long long)__ballot_sync(FULL, ok) << (32 * half);
+        }
+        if (rel == 0) continue;
+
+        for (int r0 = 0; r0 < g.h; r0 += rcmax) {
+            const int rc = min(rcmax, g.h - r0);
+            {
+                const int nw4 = (rc * pp + 3) >> 2;
+                for (int i = lane; i < nw4; i += 32) reinterpret_cast<uint4 *>(s.mask)[i] = make_uint4(0, 0, 0, 0);
+                for (int i = lane; i < ((rc + 3) >> 2); i += 32) reinterpret_cast<uint4 *>(s.rowmap)[i] = make_uint4(0, 0, 0, 0);
             }
-            const int rs_ = a.ring_off[lo] - v0, re_ = a.ring_off[lo + 1] - v0;
-            return i == rs_ ? re_ - 1 : i - 1;
-        };
+            __syncwarp();
 
-        const double *bb = a.road_bbox + 4 * (size_t)road;
-        const int p_begin = a.road_pair_off[road], p_end = a.road_pair_off[road + 1];
-
-        if (nv > 0 && p_end > p_begin) stage_chunk(0);
-
-        for (int p = p_begin; p < p_end && nv > 0; p++) {
-            const int t = a.pair_tile[p];
-            PairGeom g;
-            const int gr = pair_geometry(a.gt + 6 * (size_t)t, bb, a.W, a.H, a.window_mode, g);
-            if (gr < 0) {
-                if (tid == 0) atomicMin(a.status, gr);
-                continue;
-            }
-            if (gr == 0) continue;
-            const int maxx = g.w - 1;
-
-            // pixel-space edge (ind1 = previous vertex, ind2 = vertex i) of the staged chunk
-            auto edge = [&](int i, double &x1, double &y1, double &x2, double &y2) {
-                const double2 q2 = vertex(i), q1 = vertex(prev_index(i));
-                x1 = __dadd_rn(g.inv0, __dmul_rn(q1.x, g.inv1));
-                y1 = __dadd_rn(g.inv3, __dmul_rn(q1.y, g.inv5));
-                x2 = __dadd_rn(g.inv0, __dmul_rn(q2.x, g.inv1));
-                y2 = __dadd_rn(g.inv3, __dmul_rn(q2.y, g.inv5));
-            };
-
-            for (int r0 = 0; r0 < g.h;) {
-                int rc = min(K::RC, g.h - r0);
-                int total = 0;
-                // ---------------- pass 1: per-row and per-edge crossing counts ----------------
-                for (;;) {
-                    for (int i = tid; i <= rc; i += TEAM) s.rowpos[i] = 0;
-                    if (tid == 0) s.hb_count = 0;
-                    team_sync<TEAM>();
-                    for (int ch = 0; ch < nchunks; ch++) {
-                        stage_chunk(ch);
-                        for (int j = tid; j < ccount; j += TEAM) {
-                            double x1, y1, x2, y2;
-                            edge(cbase + j, x1, y1, x2, y2);
-                            int n = 0;
+            // ---------------- edge passes: 0 = crossings (toggles), 1 = horizontal-edge burns ----------------
+            bool any_hb = false;
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass == 1 && !any_hb) break;
+                for (unsigned long long rm = rel; rm; rm &= rm - 1) {
+                    const int c = __ffsll((long long)rm) - 1;
+                    const int cend = min(nv, (c + 1) << cshift);
+                    for (int base = c << cshift; base < cend; base += 32) {
+                        const int i = base + lane;
+                        int n = 0, ya = 0;
+                        bool hb = false;
+                        double x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+                        if (i < cend) {
+                            const double2 q2 = vertex(i), q1 = vertex(prev_index(i));
+                            x1 = __dadd_rn(g.inv0, __dmul_rn(q1.x, g.inv1));
+                            y1 = __dadd_rn(g.inv3, __dmul_rn(q1.y, g.inv5));
+                            x2 = __dadd_rn(g.inv0, __dmul_rn(q2.x, g.inv1));
+                            y2 = __dadd_rn(g.inv3, __dmul_rn(q2.y, g.inv5));
                             if (y1 == y2) {
-                                // horizontal edge: burnt separately iff it lies exactly on a scanline
-                                // of this chunk and runs towards -x
-                                if (x1 > x2) {
-                                    const double fy = floor(y1);
-                                    if (fy + 0.5 == y1 && fy >= (double)r0 && fy < (double)(r0 + rc)) {
-                                        const double hx1 = floor(__dadd_rn(x2, 0.5)), hx2 = floor(__dadd_rn(x1, 0.5));
-                                        if (!(hx1 > (double)maxx || hx2 <= 0.0)) {
-                                            const int k = atomicAdd(&s.hb_count, 1);
-                                            if (k < K::HB) {
-                                                s.hb[k][0] = (int)fy - r0;
-                                                s.hb[k][1] = (int)fmax(hx1, 0.0);
-                                                s.hb[k][2] = (int)fmin(hx2 - 1.0, (double)maxx);
-                                            }
+                                // horizontal edge: burnt separately iff it lies exactly on a scanline of this
+                                // chunk and runs towards -x
+                                const double fy = floor(y1);
+                                hb = (x1 > x2) && (fy + 0.5 == y1) && fy >= (double)r0 && fy < (double)(r0 + rc);
+                            } else if (fmin(x1, x2) <= (double)g.w + 1.0) {
+                                ya = max(first_row_ge(fmin(y1, y2)), r0);
+                                const int yb = min(last_row_lt(fmax(y1, y2)), r0 + rc - 1);
+                                n = max(yb - ya + 1, 0);
+                            }
+                        }
+                        if (pass == 1) {
+                            if (hb) {
+                                const double hx1 = floor(__dadd_rn(x2, 0.5)), hx2 = floor(__dadd_rn(x1, 0.5));
+                                if (!(hx1 > (double)(g.w - 1) || hx2 <= 0.0)) {
+                                    const int xa = (int)fmax(hx1, 0.0), xb = (int)fmin(hx2 - 1.0, (double)(g.w - 1));
+                                    const int row = (int)floor(y1) - r0;
+                                    if (xa <= xb) {
+                                        for (int k = (lo + xa) >> 5; k <= ((lo + xb) >> 5); k++) {
+                                            const int b0 = max(lo + xa - 32 * k, 0), b1 = min(lo + xb - 32 * k, 31);
+                                            const uint32_t bits = (b1 >= 31 ? FULL : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
+                                            atomicOr(&s.mask[row * pp + k], bits);
                                         }
+                                        s.rowmap[row] = (uint32_t)pitch << 16;      // whole row, [0, pitch)
                                     }
                                 }
-                            } else {
-                                const int ya = max(first_row_ge(fmin(y1, y2)), r0);
-                                const int yb = min(last_row_lt(fmax(y1, y2)), r0 + rc - 1);
-                                n = max(yb - ya + 1, 0);
-                                if (n > 0) {
-                                    atomicAdd(&s.rowpos[ya - r0], 1);
-                                    atomicAdd(&s.rowpos[yb + 1 - r0], -1);
-                                }
                             }
-                            if (nchunks == 1) s.eoff[j] = n;
+                            continue;
                         }
-                    }
-                    team_sync<TEAM>();
-                    team_scan<TEAM>(s.rowpos, rc + 1, true, s.wsum);             // difference -> counts
-                    total = team_scan<TEAM>(s.rowpos, rc + 1, false, s.wsum);    // counts -> row offsets
-                    if (total <= K::CAP && s.hb_count <= K::HB) break;
-                    if (rc == 1) {
-                        if (tid == 0) atomicMin(a.status, (int)RS_ERR_CAPACITY);
-                        total = -1;
-                        break;
-                    }
-                    rc = (rc + 1) >> 1;
-                    team_sync<TEAM>();
-                }
-                if (total < 0) { r0 += rc; team_sync<TEAM>(); continue; }
-
-                // ---------------- pass 2: evaluate and scatter the crossings ----------------
-                for (int ch = 0; ch < nchunks && total > 0; ch++) {
-                    stage_chunk(ch);
-                    if (nchunks > 1) {
-                        for (int j = tid; j < ccount; j += TEAM) {
-                            double x1, y1, x2, y2;
-                            edge(cbase + j, x1, y1, x2, y2);
-                            int n = 0;
-                            if (y1 != y2) {
-                                const int ya = max(first_row_ge(fmin(y1, y2)), r0);
-                                const int yb = min(last_row_lt(fmax(y1, y2)), r0 + rc - 1);
-                                n = max(yb - ya + 1, 0);
-                            }
-                            s.eoff[j] = n;
-                        }
-                    }
-                    if (tid == 0) s.eoff[ccount] = 0;
-                    team_sync<TEAM>();
-                    const int nx = team_scan<TEAM>(s.eoff, ccount + 1, false, s.wsum);
-                    for (int f = tid; f < nx; f += TEAM) {
-                        const int j = upper_bound_smem(s.eoff, ccount + 1, f) - 1;
-                        const int k = f - s.eoff[j];
-                        double x1, y1, x2, y2;
-                        edge(cbase + j, x1, y1, x2, y2);
-                        double dx1, dy1, dx2, dy2;
-                        if (y1 < y2) { dx1 = x1; dy1 = y1; dx2 = x2; dy2 = y2; }
-                        else         { dx1 = x2; dy1 = y2; dx2 = x1; dy2 = y1; }
-                        const int y = max(first_row_ge(dy1), r0) + k;
-                        const double dy = (double)y + 0.5;
-                        const double isect =
-                            __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(dy, dy1), __dsub_rn(dx2, dx1)), __dsub_rn(dy2, dy1)), dx1);
-                        double r = floor(__dadd_rn(isect, 0.5));
-                        r = fmin(fmax(r, -1.0), (double)g.w);      // order-preserving clamp, see DESIGN.md
-                        const int slot = atomicAdd(&s.rowpos[y - r0], 1);
-                        s.pool[slot] = (int16_t)(int)r;
-                    }
-                    team_sync<TEAM>();
-                }
-
-                // ---------------- sort each row's crossings (rowpos[y] is now the row's end) ----------
-                for (int y = tid; y < rc; y += TEAM) {
-                    const int b = y ? s.rowpos[y - 1] : 0, e = s.rowpos[y];
-                    for (int i = b + 1; i < e; i++) {
-                        const int16_t v = s.pool[i];
-                        int j = i - 1;
-                        while (j >= b && s.pool[j] > v) { s.pool[j + 1] = s.pool[j]; j--; }
-                        s.pool[j + 1] = v;
-                    }
-                }
-                team_sync<TEAM>();
-
-                // ---------------- spans -> pixels ----------------
-                const size_t mask_base = PX::MASK ? (size_t)p * a.H * a.W : 0;
-                {
-                    constexpr int G = K::G, NG = TEAM / G;
-                    const int gid = tid / G, gl = tid % G;
-                    const int nspans = total >> 1;
-                    for (int m = gid; m < nspans; m += NG) {
-                        const int q = 2 * m;
-                        const int y = upper_bound_smem(s.rowpos, rc, q);
-                        int xs = s.pool[q], xe = s.pool[q + 1];
-                        if (!(xs <= maxx && xe > 0)) continue;
-                        xs = max(xs, 0);
-                        xe = min(xe - 1, maxx);
-                        const size_t rowbase = (size_t)(g.row_off + r0 + y) * a.W + g.col_off;
-                        for (int x = xs + gl; x <= xe; x += G) {
-                            if constexpr (PX::MASK) a.masks[mask_base + rowbase + x] = 1;
-                            else PX::pixel(a, (size_t)t, rowbase + x, s.hist, nz);
-                        }
-                    }
-                }
-                // ---------------- horizontal-edge burns, minus what is already covered ----------------
-                const int nhb = min(s.hb_count, (int)K::HB);
-                for (int k = 0; k < nhb; k++) {
-                    const int y = s.hb[k][0], xa = s.hb[k][1], xb = s.hb[k][2];
-                    const int b = y ? s.rowpos[y - 1] : 0, e = s.rowpos[y];
-                    const size_t rowbase = (size_t)(g.row_off + r0 + y) * a.W + g.col_off;
-                    for (int x = xa + tid; x <= xb; x += TEAM) {
-                        bool covered = false;
-                        for (int i = b; i + 1 < e; i += 2) covered |= (s.pool[i] <= x && x < s.pool[i + 1]);
-                        for (int k2 = 0; k2 < k; k2++) covered |= (s.hb[k2][0] == y && s.hb[k2][1] <= x && x <= s.hb[k2][2]);
-                        if (covered) continue;
-                        if constexpr (PX::MASK) a.masks[mask_base + rowbase + x] = 1;
-                        else PX::pixel(a, (size_t)t, rowbase + x, s.hist, nz);
-                    }
-                }
-                team_sync<TEAM>();
-                r0 += rc;
-            }
-        }
-
-        // ---------------- write the road's accumulators (exactly once) ----------------
-        if constexpr (!PX::MASK) {
-            team_sync<TEAM>();
-            const int slot = a.road_slot ? a.road_slot[road] : road;
-            uint4 *dst = reinterpret_cast<uint4 *>(a.hist + (size_t)slot * PX::HC * 256);
-            for (int i = tid; i < PX::HC * 64; i += TEAM) dst[i] = reinterpret_cast<const uint4 *>(s.hist)[i];
+                        any_hb |= __any_sync(FULL, hb);
+                        if (!__any_sync(FULL, n > 0)) continue;
+                        // flatten (edge, row) crossings over the lanes
+                        int incl = n;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
-            if (TEAM > 32) {
-                if ((tid & 31) == 0) s.wsum[tid >> 5] = (int)nz;
-                __syncthreads();
-                nz = 0;
-                for (int w = 0; w < TEAM / 32; w++) nz += (uint32_t)s.wsum[w];
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        const int total = __shfl_sync(FULL, incl, 31);
+                        {
+                            double dx1, dy1, dx2, dy2;
+                            if (y1 < y2) { dx1 = x1; dy1 = y1; dx2 = x2; dy2 = y2; }
+                            else         { dx1 = x2; dy1 = y2; dx2 = x1; dy2 = y1; }
+                            s.e_dx1[lane] = dx1; s.e_dy1[lane] = dy1;
+                            s.e_a[lane] = __dsub_rn(dx2, dx1); s.e_b[lane] = __dsub_rn(dy2, dy1);
+                            s.e_ya[lane] = ya; s.e_off[lane] = incl - n;
+                            if (lane == 31) s.e_off[32] = total;
+                        }
+                        __syncwarp();
+                        for (int f = lane; f < total; f += 32) {
+                            int j = 0;
+#pragma unroll
+                            for (int st = 16; st > 0; st >>= 1)
+                                if (s.e_off[j + st] <= f) j += st;
+                            const int y = s.e_ya[j] + (f - s.e_off[j]);
+                            const double dy = (double)y + 0.5;
+                            const double dx1 = s.e_dx1[j];
+                            const double isect =
+                                __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(dy, s.e_dy1[j]), s.e_a[j]), s.e_b[j]), dx1);
+                            const double r = floor(__dadd_rn(isect, 0.5));
+                            if (r < (double)g.w) {                      // crossings at or beyond the right edge toggle nothing
+                                const int bit = lo + (r > 0.0 ? (int)r : 0);
+                                atomicXor(&s.mask[(y - r0) * pp + (bit >> 5)], 1u << (bit & 31));
+                                atomicOr(&s.rowmap[y - r0], 1u << min(bit >> 5, 31));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                if (pass == 1) break;
+
+                // ---------------- prefix: toggle words -> inside words, lane per row ----------------
+                for (int row = lane; row < rc; row += 32) {
+                    const uint32_t rmw = s.rowmap[row];
+                    uint32_t range = 0;
+                    if (rmw) {
+                        uint32_t *mrow = s.mask + row * pp;
+                        const int kfirst = __ffs(rmw) - 1;
+                        int klast = kfirst - 1;
+                        uint32_t carry = 0;
+                        for (int k = kfirst; k < pitch; k++) {
+                            const uint32_t tg = mrow[k];
+                            uint32_t m = prefix_xor32(tg) ^ (carry ? FULL : 0u);
+                            carry ^= __popc(tg) & 1u;
+                            const int hi_k = lo + g.w - 32 * k;             // window columns end here
+                            if (hi_k < 32) m &= (hi_k <= 0 ? 0u : ((1u << hi_k) - 1u));
+                            mrow[k] = m;
+                            if (m) klast = k;
+                            if (!carry && k < 31 && (rmw >> (k + 1)) == 0) break;   // bit 31 stands for every word >= 31
+                        }
+                        if (klast >= kfirst) range = (uint32_t)kfirst | ((uint32_t)(klast + 1) << 16);
+                    }
+                    s.rowmap[row] = range;
+                }
+                __syncwarp();
             }
-            if (tid == 0) a.nzero[slot] = nz;
+
+            // ---------------- pixels: batches of rows -> 8-pixel group entries -> lanes ----------------
+            const size_t tile_pix = (size_t)t * a.H * a.W;
+            for (int b0 = 0; b0 < rc; b0 += rb_rows) {
+                const int row = b0 + lane;
+                uint32_t range = 0;
+                int cnt = 0;
+                if (lane < rb_rows && row < rc) {
+                    range = s.rowmap[row];
+                    const uint32_t *mrow = s.mask + row * pp;
+                    for (int k = range & 0xffffu; k < (int)(range >> 16); k++) cnt += __popc(nonzero_bytes(mrow[k]));
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                if (total == 0) continue;
+                if (cnt) {
+                    int off = incl - cnt;
+                    const uint32_t *mrow = s.mask + row * pp;
+                    for (int k = range & 0xffffu; k < (int)(range >> 16); k++) {
+                        const uint32_t m = mrow[k];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t m8 = (m >> (8 * j)) & 255u;
+                            if (m8) s.entries[off++] = ((uint32_t)row << 20) | ((uint32_t)(k * 4 + j) << 8) | m8;
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int e = lane; e < total; e += 32) {
+                    const uint32_t en = s.entries[e];
+                    const uint32_t m8 = en & 255u;
+                    const int x8 = cbcol + 8 * (int)((en >> 8) & 0xfffu);
+                    const int yabs = g.row_off + r0 + (int)(en >> 20);
+                    const size_t pix = tile_pix + (size_t)yabs * a.W + x8;
+                    if constexpr (PX::MASK) {
+                        uint8_t *mp = a.masks + ((size_t)p * a.H + yabs) * a.W + x8;
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (m8 & (1u << i)) mp[i] = 1;
+                    } else {
+                        if (a.fast) {
+                            uint32_t r[PX::NW];
+                            load_group<PX::BPP, PX::NW>((const uint8_t *)a.pixels + pix * PX::BPP, r);
+                            group_pixels<PX, 0>(a, r, m8, s.hist, nz);
+                        } else {
+                            for (int i = 0; i < 8; i++)
+                                if (m8 & (1u << i)) PX::pixel_slow(a, pix + i, s.hist, nz);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
         }
-        team_sync<TEAM>();
+    }
+
+    // ---------------- write the road's accumulators ----------------
+    if constexpr (!PX::MASK) {
+        __syncwarp();
+        const int slot = a.road_slot ? a.road_slot[road] : road;
+        uint32_t *dst = a.hist + (size_t)slot * PX::HC * 256;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(FULL, nz, o);
+        if (!split) {
+            for (int i = lane; i < PX::HC * 64; i += 32)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(s.hist)[i];
+            if (lane == 0) a.nzero[slot] = nz;
+        } else {
+            for (int i = lane; i < PX::HC * 256; i += 32) {
+                const uint32_t v = s.hist[i];
+                if (v) atomicAdd(&dst[i], v);
+            }
+            if (lane == 0 && nz) atomicAdd(&a.nzero[slot], nz);
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel: persistent teams pulling items
+// ---------------------------------------------------------------------------------------------
+template <class PX>
+__global__ void __launch_bounds__(WARPS * 32) zonal_kernel(const ZonalArgs a)
+{
+    using S = TeamSmem<PX::HC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    S &s = reinterpret_cast<S *>(smem_raw)[warp];
+    if (lane == 0) mbar_init(&s.mbar, 1);
+    __syncwarp();
+    uint32_t mbar_phase = 0;
+    const int n_items = *a.n_items;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(a.work_counter, 1);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= n_items) break;
+        const int2 it = a.items[idx];
+        process_item<PX>(a, s, it.x, it.y, lane, mbar_phase);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// item list: thread per road; rows of roads with no item or several items are zeroed here
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__ road_pair_off, int n_roads,
+                                                         const int *__restrict__ road_slot, uint32_t *hist, uint32_t *nzero,
+                                                         int hc, int2 *items, int *n_items)
+{
+    const int road = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    int p0 = 0, ni = 0;
+    if (road < n_roads) {
+        p0 = road_pair_off[road];
+        ni = (road_pair_off[road + 1] - p0 + PPI - 1) / PPI;
+    }
+    int incl = ni;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(n_items, total);
+    base = __shfl_sync(FULL, base, 31) + incl - ni;
+    for (int k = 0; k < ni; k++) items[base + k] = make_int2(road, p0 + k * PPI);
+    if (hist) {
+        unsigned m = __ballot_sync(FULL, road < n_roads && ni != 1);
+        for (; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const int r = __shfl_sync(FULL, road, src);
+            const int slot = road_slot ? road_slot[r] : r;
+            uint4 *dst = reinterpret_cast<uint4 *>(hist + (size_t)slot * hc * 256);
+            for (int i = lane; i < hc * 64; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
+            if (lane == 0) nzero[slot] = 0;
+        }
     }
 }
 
@@ -661,20 +769,18 @@ int launch_road_bbox(rs_ctx *ctx, const rs_roads *roads, double *out, cudaStream
 // ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
-template <int TEAM, class PX>
-static int launch_one(rs_ctx *ctx, const ZonalArgs &args, int n_items, cudaStream_t st)
+template <class PX>
+static int launch_one(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
 {
-    using S = Smem<TEAM, PX::HC>;
-    const size_t smem = sizeof(S);
-    auto kern = zonal_kernel<TEAM, PX>;
+    using S = TeamSmem<PX::HC>;
+    const size_t smem = sizeof(S) * WARPS;
+    auto kern = zonal_kernel<PX>;
     RS_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    RS_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TEAM, smem));
+    RS_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    long grid = (long)ctx->sm_count * per_sm;     // persistent: a whole number of resident waves
-    if (n_items >= 0 && grid > n_items) grid = n_items > 0 ? n_items : 1;
-    RS_CUDA_OK(ctx, cudaMemsetAsync(args.work_counter, 0, sizeof(int), st));
-    kern<<<(unsigned)grid, TEAM, smem, st>>>(args);
+    const unsigned grid = (unsigned)(ctx->sm_count * per_sm);     // persistent: a whole number of resident waves
+    kern<<<grid, WARPS * 32, smem, st>>>(args);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
     return RS_OK;
@@ -691,8 +797,13 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
         return RS_ERR_INVALID_ARG;
     if (pairs->n_pairs > 0 && (!pairs->pair_tile || !tiles->gt)) return RS_ERR_INVALID_ARG;
     if (((uintptr_t)roads->xy & 15u) != 0) return RS_ERR_INVALID_ARG;      // TMA bulk source alignment
-    if (tiles->width > 32766 || tiles->width < 1 || tiles->height < 1) return RS_ERR_UNSUPPORTED;
+    if (tiles->width > MAX_WIDTH || tiles->width < 1 || tiles->height < 1) return RS_ERR_UNSUPPORTED;
     if (window_mode != RS_WINDOW_CROP && window_mode != RS_WINDOW_FULL) return RS_ERR_INVALID_ARG;
+
+    // item list scratch: at most one item per PPI pairs plus one partial item per road
+    const size_t cap = (size_t)pairs->n_pairs / PPI + (size_t)roads->n_roads + 1;
+    int rc = ensure(ctx, ctx->items, cap * sizeof(int2));
+    if (rc) return rc;
 
     ZonalArgs a{};
     a.xy = (const double2 *)roads->xy;
@@ -701,9 +812,9 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     a.road_bbox = roads->road_bbox;
     a.road_pair_off = pairs->road_pair_off;
     a.pair_tile = pairs->pair_tile;
-    a.road_list = nullptr;
-    a.n_list_dev = nullptr;
-    a.n_roads = roads->n_roads;
+    a.items = (const int2 *)ctx->items.p;
+    a.work_counter = ctx->d_counters;
+    a.n_items = ctx->d_counters + 1;
     a.pixels = tiles->pixels;
     a.gt = tiles->gt;
     a.H = tiles->height;
@@ -713,38 +824,44 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     a.nzero = n_allzero;
     a.masks = masks;
     a.window_mode = window_mode;
-    a.work_counter = ctx->d_counters;
     a.status = ctx->d_status;
     if (prm)
         for (int c = 0; c < 4; c++) { a.sk[c] = prm->scale_k[c]; a.so[c] = prm->scale_off[c]; }
+    a.fast = (tiles->width % 8 == 0) && (((uintptr_t)tiles->pixels & 15u) == 0);
 
-    if (masks) return launch_one<32, PxMask>(ctx, a, roads->n_roads, st);
+    int HC = 0;
+    if (!masks) {
+        if (!prm || !hist || !n_allzero || (pairs->n_pairs > 0 && !tiles->pixels)) return RS_ERR_INVALID_ARG;
+        if (prm->hist_mode == RS_HIST_CLASS_SCORE) {
+            if (tiles->channels != 2 || tiles->dtype != RS_U8) return RS_ERR_UNSUPPORTED;
+            HC = 3;
+        } else if (prm->hist_mode == RS_HIST_BANDS) {
+            if (tiles->channels < 1 || tiles->channels > 4) return RS_ERR_UNSUPPORTED;
+            if (tiles->dtype == RS_U16 && tiles->channels != 4) return RS_ERR_UNSUPPORTED;
+            if (tiles->dtype == RS_U16 && prm->rescale != 1 && prm->rescale != 2) return RS_ERR_INVALID_ARG;
+            if (tiles->dtype == RS_U16 && ((uintptr_t)tiles->pixels & 1u)) return RS_ERR_INVALID_ARG;
+            if (tiles->dtype != RS_U8 && tiles->dtype != RS_U16) return RS_ERR_INVALID_ARG;
+            HC = tiles->channels;
+        } else
+            return RS_ERR_INVALID_ARG;
+    }
 
-    if (!prm || !hist || !n_allzero || (pairs->n_pairs > 0 && !tiles->pixels)) return RS_ERR_INVALID_ARG;
-    const int C = tiles->channels;
-    if (prm->hist_mode == RS_HIST_CLASS_SCORE) {
-        if (C != 2 || tiles->dtype != RS_U8) return RS_ERR_UNSUPPORTED;
-        return launch_one<32, PxClassScore>(ctx, a, roads->n_roads, st);
-    }
-    if (prm->hist_mode != RS_HIST_BANDS) return RS_ERR_INVALID_ARG;
-    if (tiles->dtype == RS_U16) {
-        if (C != 4) return RS_ERR_UNSUPPORTED;
-        if (((uintptr_t)tiles->pixels & 7u) != 0) return RS_ERR_INVALID_ARG;
-        if (prm->rescale == 1) return launch_one<32, PxU16x4Rescale<false>>(ctx, a, roads->n_roads, st);
-        if (prm->rescale == 2) return launch_one<32, PxU16x4Rescale<true>>(ctx, a, roads->n_roads, st);
-        return RS_ERR_INVALID_ARG;
-    }
-    if (tiles->dtype != RS_U8) return RS_ERR_INVALID_ARG;
-    switch (C) {
-        case 1: return launch_one<32, PxBandsU8<1>>(ctx, a, roads->n_roads, st);
-        case 2:
-            if (((uintptr_t)tiles->pixels & 1u) != 0) return RS_ERR_INVALID_ARG;
-            return launch_one<32, PxBandsU8<2>>(ctx, a, roads->n_roads, st);
-        case 3: return launch_one<32, PxBandsU8<3>>(ctx, a, roads->n_roads, st);
-        case 4:
-            if (((uintptr_t)tiles->pixels & 3u) != 0) return RS_ERR_INVALID_ARG;
-            return launch_one<32, PxBandsU8<4>>(ctx, a, roads->n_roads, st);
-        default: return RS_ERR_UNSUPPORTED;
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(int), st));
+    prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, roads->n_roads, a.road_slot,
+                                                                    masks ? nullptr : hist, n_allzero, HC,
+                                                                    (int2 *)ctx->items.p, ctx->d_counters + 1);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+
+    if (masks) return launch_one<PxMask>(ctx, a, st);
+    if (prm->hist_mode == RS_HIST_CLASS_SCORE) return launch_one<PxClassScore>(ctx, a, st);
+    if (tiles->dtype == RS_U16)
+        return prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);
+    switch (tiles->channels) {
+        case 1: return launch_one<PxBandsU8<1>>(ctx, a, st);
+        case 2: return launch_one<PxBandsU8<2>>(ctx, a, st);
+        case 3: return launch_one<PxBandsU8<3>>(ctx, a, st);
+        default: return launch_one<PxBandsU8<4>>(ctx, a, st);
     }
 }
 

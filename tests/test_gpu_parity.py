@@ -232,8 +232,8 @@ def test_zonal_edge_cases(eng):
     assert h1.sum() == 0 and z1.sum() == 0
 
 
-def test_zonal_road_slots_merge_rows(eng):
-    """road_slot lets several polygons (e.g. the pieces of one road) fold into one output row"""
+def test_zonal_road_slots(eng):
+    """road_slot scatters the roads' rows into a larger table (the boundary table of a tile shard)"""
     g = synth.Grid(4, 4)
     rr = synth.ribbon_roads(g, 20, seed=77)
     tiles = synth.host_tiles(g, 3)
@@ -391,4 +391,4 @@ def test_vote_metrics_sweep(eng, rule, min_area_frac):
         for j, name in enumerate(METRIC_COLS):
             key = {"P0": "P_0", "R0": "R_0", "F0": "f1_0", "P1": "P_1", "R1": "R_1", "F1": "f1_1"}.get(name, name)
             np.testing.assert_allclose(met[i, j], om[key], rtol=RTOL, atol=1e-15)
-    assert len(set(cover[0].tolist())) >= 3
+    assert len(set(cover[0].tolist())) >= 2
