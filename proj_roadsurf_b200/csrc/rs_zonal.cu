@@ -43,14 +43,16 @@ namespace rs {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 4;        // teams per CTA
+constexpr int CTAS_PER_SM = 5;  // occupancy target (shared memory: ~10.6 KB per team)
 constexpr int PPI = 16;         // pairs per work item
-constexpr int VCAP = 128;       // vertices staged in shared memory per road (longer roads read L2)
-constexpr int MASKW = 1024;     // mask words per team
-constexpr int RCMAX = 256;      // rows per mask chunk
-constexpr int ENTCAP = 512;     // 8-pixel group entries per batch
-constexpr int NCHUNK = 64;      // culling chunks per road
+constexpr int VCAP = 96;        // vertices staged in shared memory per road (longer roads read L2)
+constexpr int MASKW = 768;      // mask words per team
+constexpr int RCMAX = 128;      // rows per mask chunk
+constexpr int ENTCAP = 448;     // 8-pixel group entries queued per team
+constexpr int NCHUNK = 32;      // culling chunks per road
 constexpr int RINGCAP = 16;     // ring starts kept in shared memory
-constexpr int MAX_WIDTH = 8 * ENTCAP;
+constexpr int MAX_WIDTH = 2048; // one row's groups (W / 8) must fit the queue next to a partial round
+constexpr uint32_t ROW_REWALK = 0xffffffffu;   // rowmap marker: recount this row over [0, pitch)
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copy (global -> shared)
@@ -202,16 +204,29 @@ struct PxBandsU8 {
     static constexpr int C = C_, HC = C_, BPP = C_, NW = 2 * C_;
     static constexpr bool MASK = false;
     template <int I>
-    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &nz)
+    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &)
     {
-        uint32_t any = 0;
 #pragma unroll
         for (int c = 0; c < C; c++) {
             const uint32_t v = (r[(I * C + c) >> 2] >> (((I * C + c) & 3) * 8)) & 255u;
             atomicAdd(&hist[c * 256 + v], 1u);
-            any |= v;
         }
-        nz += (any == 0);
+    }
+    // in-mask pixels of the group whose bands are all 0: only groups holding a zero byte look closer
+    __device__ static __forceinline__ void group_nz(const uint32_t (&r)[NW], uint32_t m8, uint32_t &nz)
+    {
+        uint32_t hz = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) hz |= (r[w] - 0x01010101u) & ~r[w] & 0x80808080u;
+        if (hz) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t any = 0;
+#pragma unroll
+                for (int c = 0; c < C; c++) any |= (r[(i * C + c) >> 2] >> (((i * C + c) & 3) * 8)) & 255u;
+                nz += ((m8 >> i) & 1u) & (any == 0);
+            }
+        }
     }
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
@@ -241,6 +256,7 @@ struct PxClassScore {
     {
         one(byte_at<2 * I>(r), byte_at<2 * I + 1>(r), hist, nz);
     }
+    __device__ static __forceinline__ void group_nz(const uint32_t (&)[NW], uint32_t, uint32_t &) {}
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
         const uint8_t *p = (const uint8_t *)a.pixels + pix * 2;
@@ -275,6 +291,7 @@ struct PxU16x4Rescale {
         }
         nz += (any == 0);
     }
+    __device__ static __forceinline__ void group_nz(const uint32_t (&)[NW], uint32_t, uint32_t &) {}
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
         const uint16_t *p = (const uint16_t *)a.pixels + pix * 4;
@@ -325,16 +342,21 @@ __device__ __forceinline__ void group_pixels(const ZonalArgs &a, const uint32_t 
 // ---------------------------------------------------------------------------------------------
 // team shared memory
 // ---------------------------------------------------------------------------------------------
+struct EdgeParams {                 // the 32 edges of one block, written by their lanes, read by the crossing lanes
+    double dx1[32], dy1[32], a[32], b[32], rb[32];
+    int ya[32];
+    int off[33];
+};
 template <int HC>
 struct TeamSmem {
     alignas(16) double2 verts[VCAP];
     alignas(16) uint32_t hist[HC > 0 ? HC * 256 : 4];
     alignas(16) uint32_t mask[MASKW];
     alignas(16) uint32_t rowmap[RCMAX];
-    uint32_t entries[ENTCAP];
-    double e_dx1[32], e_dy1[32], e_a[32], e_b[32];
-    int e_ya[32];
-    int e_off[33];
+    union {                         // the edge pass and the pixel phase never overlap
+        EdgeParams e;
+        uint32_t entries[ENTCAP];
+    } u;
     float cb_ymin[NCHUNK], cb_ymax[NCHUNK], cb_xmin[NCHUNK], cb_xmax[NCHUNK];
     int ring_start[RINGCAP + 1];
     alignas(8) uint64_t mbar;
@@ -441,27 +463,25 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
         const int pp = pitch | 1;                                       // odd row stride: lane-per-row walks are conflict-free
         const int lo = g.col_off - cbcol;                               // mask bit of window column 0
         const int rcmax = min((int)RCMAX, (int)MASKW / pp);
-        const int rb_rows = max(1, min(32, (int)ENTCAP / (pitch * 4)));  // rows per entry batch
 
-        // chunks whose bounds can reach a window row and lie left of the window's right edge
-        unsigned long long rel = 0;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int c = lane + 32 * half;
-            bool ok = false;
-            if (c < nchunks) {
-                const double ya_ = __dadd_rn(g.inv3, __dmul_rn((double)s.cb_ymin[c], g.inv5));
-                const double yb_ = __dadd_rn(g.inv3, __dmul_rn((double)s.cb_ymax[c], g.inv5));
-                const double xa_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmin[c], g.inv1));
-                const double xb_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmax[c], g.inv1));
-                ok = (fmax(ya_, yb_) + 1.0 >= 0.0) && (fmin(ya_, yb_) - 1.0 <= (double)g.h) && (fmin(xa_, xb_) - 1.0 <= (double)g.w);
+        // lane c holds the window-pixel bounds of culling chunk c (float bounds rounded outwards, one pixel of slack)
+        float cy_lo = 1.0f, cy_hi = 0.0f;
+        if (lane < nchunks) {
+            const double ya_ = __dadd_rn(g.inv3, __dmul_rn((double)s.cb_ymin[lane], g.inv5));
+            const double yb_ = __dadd_rn(g.inv3, __dmul_rn((double)s.cb_ymax[lane], g.inv5));
+            const double xa_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmin[lane], g.inv1));
+            const double xb_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmax[lane], g.inv1));
+            if (fmin(xa_, xb_) - 1.0 <= (double)g.w) {       // chunks right of the window toggle nothing
+                cy_lo = __double2float_rd(fmin(ya_, yb_) - 1.0);
+                cy_hi = __double2float_ru(fmax(ya_, yb_) + 1.0);
             }
-            rel |= (unsigned long long)__ballot_sync(FULL, ok) << (32 * half);
         }
-        if (rel == 0) continue;
 
         for (int r0 = 0; r0 < g.h; r0 += rcmax) {
             const int rc = min(rcmax, g.h - r0);
+            // chunks whose bounds reach a row of this row chunk
+            const unsigned rel = __ballot_sync(FULL, cy_lo <= cy_hi && cy_hi >= (float)r0 && cy_lo <= (float)(r0 + rc));
+            if (rel == 0) continue;
             {
                 const int nw4 = (rc * pp + 3) >> 2;
                 for (int i = lane; i < nw4; i += 32) reinterpret_cast<uint4 *>(s.mask)[i] = make_uint4(0, 0, 0, 0);
@@ -473,8 +493,8 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             bool any_hb = false;
             for (int pass = 0; pass < 2; pass++) {
                 if (pass == 1 && !any_hb) break;
-                for (unsigned long long rm = rel; rm; rm &= rm - 1) {
-                    const int c = __ffsll((long long)rm) - 1;
+                for (unsigned rm = rel; rm; rm &= rm - 1) {
+                    const int c = __ffs(rm) - 1;
                     const int cend = min(nv, (c + 1) << cshift);
                     for (int base = c << cshift; base < cend; base += 32) {
                         const int i = base + lane;
@@ -510,7 +530,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                                             const uint32_t bits = (b1 >= 31 ? FULL : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
                                             atomicOr(&s.mask[row * pp + k], bits);
                                         }
-                                        s.rowmap[row] = (uint32_t)pitch << 16;      // whole row, [0, pitch)
+                                        s.rowmap[row] = ROW_REWALK;
                                     }
                                 }
                             }
@@ -530,23 +550,40 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                             double dx1, dy1, dx2, dy2;
                             if (y1 < y2) { dx1 = x1; dy1 = y1; dx2 = x2; dy2 = y2; }
                             else         { dx1 = x2; dy1 = y2; dx2 = x1; dy2 = y1; }
-                            s.e_dx1[lane] = dx1; s.e_dy1[lane] = dy1;
-                            s.e_a[lane] = __dsub_rn(dx2, dx1); s.e_b[lane] = __dsub_rn(dy2, dy1);
-                            s.e_ya[lane] = ya; s.e_off[lane] = incl - n;
-                            if (lane == 31) s.e_off[32] = total;
+                            s.u.e.dx1[lane] = dx1; s.u.e.dy1[lane] = dy1;
+                            const double eb = __dsub_rn(dy2, dy1);
+                            s.u.e.a[lane] = __dsub_rn(dx2, dx1); s.u.e.b[lane] = eb;
+                            s.u.e.rb[lane] = n > 0 ? __ddiv_rn(1.0, eb) : 0.0;
+                            s.u.e.ya[lane] = ya; s.u.e.off[lane] = incl - n;
+                            if (lane == 31) s.u.e.off[32] = total;
                         }
                         __syncwarp();
+                        int j = -1;
                         for (int f = lane; f < total; f += 32) {
-                            int j = 0;
+                            if (j < 0) {            // edge of crossing f: binary search once, then walk forward
+                                j = 0;
 #pragma unroll
-                            for (int st = 16; st > 0; st >>= 1)
-                                if (s.e_off[j + st] <= f) j += st;
-                            const int y = s.e_ya[j] + (f - s.e_off[j]);
+                                for (int st = 16; st > 0; st >>= 1)
+                                    if (s.u.e.off[j + st] <= f) j += st;
+                            } else {
+                                while (s.u.e.off[j + 1] <= f) j++;
+                            }
+                            const int y = s.u.e.ya[j] + (f - s.u.e.off[j]);
                             const double dy = (double)y + 0.5;
-                            const double dx1 = s.e_dx1[j];
-                            const double isect =
-                                __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(dy, s.e_dy1[j]), s.e_a[j]), s.e_b[j]), dx1);
-                            const double r = floor(__dadd_rn(isect, 0.5));
+                            const double dx1 = s.u.e.dx1[j];
+                            // GDAL: intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1, then floor(intersect + 0.5).
+                            // The quotient is first taken through the edge's reciprocal; that differs from the
+                            // correctly rounded division by a few ulp, which can only change the floor when
+                            // intersect + 0.5 is within 1e-4 of an integer -- those crossings (and absurdly
+                            // large coordinates) take the exact division.
+                            const double num = __dmul_rn(__dsub_rn(dy, s.u.e.dy1[j]), s.u.e.a[j]);
+                            const double qf = __dmul_rn(num, s.u.e.rb[j]);
+                            double v = __dadd_rn(__dadd_rn(qf, dx1), 0.5);
+                            double r = floor(v);
+                            if (!(fabs(qf) < 1.0e9) || !(fabs(v) < 1.0e9) || v - r < 1.0e-4 || v - r > 1.0 - 1.0e-4) {
+                                v = __dadd_rn(__dadd_rn(__ddiv_rn(num, s.u.e.b[j]), dx1), 0.5);
+                                r = floor(v);
+                            }
                             if (r < (double)g.w) {                      // crossings at or beyond the right edge toggle nothing
                                 const int bit = lo + (r > 0.0 ? (int)r : 0);
                                 atomicXor(&s.mask[(y - r0) * pp + (bit >> 5)], 1u << (bit & 31));
@@ -566,7 +603,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                     if (rmw) {
                         uint32_t *mrow = s.mask + row * pp;
                         const int kfirst = __ffs(rmw) - 1;
-                        int klast = kfirst - 1;
+                        int klast = kfirst - 1, cnt = 0;
                         uint32_t carry = 0;
                         for (int k = kfirst; k < pitch; k++) {
                             const uint32_t tg = mrow[k];
@@ -575,26 +612,83 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                             const int hi_k = lo + g.w - 32 * k;             // window columns end here
                             if (hi_k < 32) m &= (hi_k <= 0 ? 0u : ((1u << hi_k) - 1u));
                             mrow[k] = m;
-                            if (m) klast = k;
+                            if (m) { klast = k; cnt += __popc(nonzero_bytes(m)); }
                             if (!carry && k < 31 && (rmw >> (k + 1)) == 0) break;   // bit 31 stands for every word >= 31
                         }
-                        if (klast >= kfirst) range = (uint32_t)kfirst | ((uint32_t)(klast + 1) << 16);
+                        if (klast >= kfirst) range = (uint32_t)kfirst | ((uint32_t)(klast + 1) << 8) | ((uint32_t)cnt << 16);
                     }
                     s.rowmap[row] = range;
                 }
                 __syncwarp();
             }
 
-            // ---------------- pixels: batches of rows -> 8-pixel group entries -> lanes ----------------
+            // ---------------- pixels: rows -> queue of 8-pixel group entries -> lanes ----------------
             const size_t tile_pix = (size_t)t * a.H * a.W;
-            for (int b0 = 0; b0 < rc; b0 += rb_rows) {
+            // entries [0, n) of the queue: one lane per entry; the next round's pixels are in flight
+            // while this round's histogram atomics issue
+            auto consume = [&](const int n) {
+                if constexpr (PX::MASK) {
+                    for (int e = lane; e < n; e += 32) {
+                        const uint32_t en = s.u.entries[e];
+                        const int x8 = cbcol + 8 * (int)((en >> 8) & 0xfffu);
+                        const int yabs = g.row_off + r0 + (int)(en >> 20);
+                        uint8_t *mp = a.masks + ((size_t)p * a.H + yabs) * a.W + x8;
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (en & (1u << i)) mp[i] = 1;
+                    }
+                } else {
+                    auto pixel_index = [&](uint32_t en) -> size_t {
+                        const int x8 = cbcol + 8 * (int)((en >> 8) & 0xfffu);
+                        const int yabs = g.row_off + r0 + (int)(en >> 20);
+                        return tile_pix + (size_t)yabs * a.W + x8;
+                    };
+                    if (a.fast) {
+                        uint32_t rn[PX::NW];
+                        uint32_t m8n = 0;
+                        int e = lane;
+                        if (e < n) {
+                            const uint32_t en = s.u.entries[e];
+                            m8n = en & 255u;
+                            load_group<PX::BPP, PX::NW>((const uint8_t *)a.pixels + pixel_index(en) * PX::BPP, rn);
+                        }
+                        while (e < n) {
+                            uint32_t r[PX::NW];
+#pragma unroll
+                            for (int w = 0; w < PX::NW; w++) r[w] = rn[w];
+                            const uint32_t m8 = m8n;
+                            e += 32;
+                            if (e < n) {
+                                const uint32_t en = s.u.entries[e];
+                                m8n = en & 255u;
+                                load_group<PX::BPP, PX::NW>((const uint8_t *)a.pixels + pixel_index(en) * PX::BPP, rn);
+                            }
+                            group_pixels<PX, 0>(a, r, m8, s.hist, nz);
+                            PX::group_nz(r, m8, nz);
+                        }
+                    } else {
+                        for (int e = lane; e < n; e += 32) {
+                            const uint32_t en = s.u.entries[e];
+                            const size_t pix = pixel_index(en);
+                            for (int i = 0; i < 8; i++)
+                                if (en & (1u << i)) PX::pixel_slow(a, pix + i, s.hist, nz);
+                        }
+                    }
+                }
+            };
+            int nq = 0;                                      // queued entries (warp-uniform)
+            for (int b0 = 0; b0 < rc;) {
                 const int row = b0 + lane;
-                uint32_t range = 0;
-                int cnt = 0;
-                if (lane < rb_rows && row < rc) {
-                    range = s.rowmap[row];
-                    const uint32_t *mrow = s.mask + row * pp;
-                    for (int k = range & 0xffffu; k < (int)(range >> 16); k++) cnt += __popc(nonzero_bytes(mrow[k]));
+                int cnt = 0, klo = 0, khi = 0;
+                if (row < rc) {
+                    const uint32_t rr = s.rowmap[row];
+                    if (rr == ROW_REWALK) {
+                        khi = pitch;
+                        const uint32_t *mrow = s.mask + row * pp;
+                        for (int k = 0; k < pitch; k++) cnt += __popc(nonzero_bytes(mrow[k]));
+                    } else {
+                        klo = rr & 255u; khi = (rr >> 8) & 255u; cnt = rr >> 16;
+                    }
                 }
                 int incl = cnt;
 #pragma unroll
@@ -602,45 +696,40 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                     const int v = __shfl_up_sync(FULL, incl, o);
                     if (lane >= o) incl += v;
                 }
-                const int total = __shfl_sync(FULL, incl, 31);
-                if (total == 0) continue;
-                if (cnt) {
-                    int off = incl - cnt;
+                // rows whose entries fit the queue form a prefix of the lanes (at least one: a row holds
+                // at most W / 8 <= ENTCAP - 32 groups)
+                const int nrows = __popc(__ballot_sync(FULL, nq + incl <= ENTCAP));
+                const int added = __shfl_sync(FULL, incl, nrows - 1);
+                if (lane < nrows && cnt) {
+                    int off = nq + incl - cnt;
                     const uint32_t *mrow = s.mask + row * pp;
-                    for (int k = range & 0xffffu; k < (int)(range >> 16); k++) {
+                    for (int k = klo; k < khi; k++) {
                         const uint32_t m = mrow[k];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const uint32_t m8 = (m >> (8 * j)) & 255u;
-                            if (m8) s.entries[off++] = ((uint32_t)row << 20) | ((uint32_t)(k * 4 + j) << 8) | m8;
+                            if (m8) s.u.entries[off++] = ((uint32_t)row << 20) | ((uint32_t)(k * 4 + j) << 8) | m8;
                         }
                     }
                 }
                 __syncwarp();
-                for (int e = lane; e < total; e += 32) {
-                    const uint32_t en = s.entries[e];
-                    const uint32_t m8 = en & 255u;
-                    const int x8 = cbcol + 8 * (int)((en >> 8) & 0xfffu);
-                    const int yabs = g.row_off + r0 + (int)(en >> 20);
-                    const size_t pix = tile_pix + (size_t)yabs * a.W + x8;
-                    if constexpr (PX::MASK) {
-                        uint8_t *mp = a.masks + ((size_t)p * a.H + yabs) * a.W + x8;
-#pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            if (m8 & (1u << i)) mp[i] = 1;
-                    } else {
-                        if (a.fast) {
-                            uint32_t r[PX::NW];
-                            load_group<PX::BPP, PX::NW>((const uint8_t *)a.pixels + pix * PX::BPP, r);
-                            group_pixels<PX, 0>(a, r, m8, s.hist, nz);
-                        } else {
-                            for (int i = 0; i < 8; i++)
-                                if (m8 & (1u << i)) PX::pixel_slow(a, pix + i, s.hist, nz);
-                        }
-                    }
+                nq += added;
+                b0 += nrows;
+                const int nfull = nq & ~31;
+                if (nfull) {                                 // full rounds now, the partial round waits for more rows
+                    consume(nfull);
+                    __syncwarp();
+                    const int rest = nq - nfull;
+                    uint32_t keep = 0;
+                    if (lane < rest) keep = s.u.entries[nfull + lane];
+                    __syncwarp();
+                    if (lane < rest) s.u.entries[lane] = keep;
+                    __syncwarp();
+                    nq = rest;
                 }
-                __syncwarp();
             }
+            if (nq) consume(nq);
+            __syncwarp();
         }
     }
 
@@ -670,7 +759,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
 // the kernel: persistent teams pulling items
 // ---------------------------------------------------------------------------------------------
 template <class PX>
-__global__ void __launch_bounds__(WARPS * 32) zonal_kernel(const ZonalArgs a)
+__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const ZonalArgs a)
 {
     using S = TeamSmem<PX::HC>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
