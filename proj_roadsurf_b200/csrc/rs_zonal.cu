@@ -108,6 +108,7 @@ struct ZonalArgs {
     const double *gt;
     int H, W;
     int fast;                 // 1: 64/128-bit group loads are legal (W % 8 == 0, base 16-byte aligned)
+    uint32_t one;             // 1, opaque to the compiler (see red_inc3)
     const int *road_slot;
     uint32_t *hist;
     uint32_t *nzero;
@@ -199,34 +200,52 @@ __device__ __forceinline__ uint32_t byte_at(const uint32_t (&r)[N]) { return (r[
 template <int OFF, int N>
 __device__ __forceinline__ uint32_t half_at(const uint32_t (&r)[N]) { return (r[OFF >> 2] >> ((OFF & 3) * 8)) & 0xffffu; }
 
+// three (two, one) histogram increments under one predicate: straight-line code, the mask bit only
+// predicates the atomics (no divergent branch per pixel)
+// The addend of the histogram increments is the kernel argument ZonalArgs::one (= 1): with a literal 1
+// ptxas turns every increment into a warp-aggregated ATOMS.POPC.INC, which needs a reconvergence
+// point (BSSY / BRA / BSYNC) per atomic and cannot be predicated.
+__device__ __forceinline__ void red_inc3(uint32_t on, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t one)
+{
+    const uint32_t v = on ? one : 0u;       // shared atomics cannot be predicated: masked-off pixels add 0
+    asm volatile(
+        "red.shared.add.u32 [%0], %3;\n\t"
+        "red.shared.add.u32 [%1], %3;\n\t"
+        "red.shared.add.u32 [%2], %3;"
+        ::"r"(a0), "r"(a1), "r"(a2), "r"(v)
+        : "memory");
+}
+__device__ __forceinline__ void red_inc1(uint32_t on, uint32_t a0, uint32_t one)
+{
+    const uint32_t v = on ? one : 0u;
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(v) : "memory");
+}
+// byte K of w, times 4 (a histogram bin's byte offset)
+__device__ __forceinline__ uint32_t bin_off(uint32_t w, int k)      // k is a compile-time constant after unrolling
+{
+    return k == 0 ? (w << 2) & 0x3fcu : (w >> (8 * k - 2)) & 0x3fcu;
+}
+
 template <int C_>
 struct PxBandsU8 {
     static constexpr int C = C_, HC = C_, BPP = C_, NW = 2 * C_;
     static constexpr bool MASK = false;
+    // pixel I of the group: hist (shared-memory byte address of the team histogram) gets one increment per band
     template <int I>
-    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &)
+    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t one, uint32_t &nz)
     {
+        uint32_t o[C];
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const uint32_t v = (r[(I * C + c) >> 2] >> (((I * C + c) & 3) * 8)) & 255u;
-            atomicAdd(&hist[c * 256 + v], 1u);
+        for (int c = 0; c < C; c++) o[c] = bin_off(r[(I * C + c) >> 2], (I * C + c) & 3);
+        uint32_t any = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) any |= o[c];
+        if constexpr (C == 3) red_inc3(on, hist + o[0], hist + 1024 + o[1], hist + 2048 + o[2], one);
+        else {
+#pragma unroll
+            for (int c = 0; c < C; c++) red_inc1(on, hist + 1024 * c + o[c], one);
         }
-    }
-    // in-mask pixels of the group whose bands are all 0: only groups holding a zero byte look closer
-    __device__ static __forceinline__ void group_nz(const uint32_t (&r)[NW], uint32_t m8, uint32_t &nz)
-    {
-        uint32_t hz = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) hz |= (r[w] - 0x01010101u) & ~r[w] & 0x80808080u;
-        if (hz) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                uint32_t any = 0;
-#pragma unroll
-                for (int c = 0; c < C; c++) any |= (r[(i * C + c) >> 2] >> (((i * C + c) & 3) * 8)) & 255u;
-                nz += ((m8 >> i) & 1u) & (any == 0);
-            }
-        }
+        nz += (on != 0) & (any == 0);
     }
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
@@ -252,11 +271,14 @@ struct PxClassScore {
         atomicAdd(&hist[cls * 256 + score], 1u);
     }
     template <int I>
-    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &nz)
+    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t one, uint32_t &nz)
     {
-        one(byte_at<2 * I>(r), byte_at<2 * I + 1>(r), hist, nz);
+        uint32_t cls = byte_at<2 * I>(r);
+        const uint32_t score = byte_at<2 * I + 1>(r);
+        nz += (on != 0) & ((cls | score) == 0);
+        if (cls > 2u) cls = 0u;   // unknown class codes count as "no detection"
+        red_inc1(on, hist + 4u * (cls * 256u + score), one);
     }
-    __device__ static __forceinline__ void group_nz(const uint32_t (&)[NW], uint32_t, uint32_t &) {}
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
         const uint8_t *p = (const uint8_t *)a.pixels + pix * 2;
@@ -280,18 +302,17 @@ struct PxU16x4Rescale {
         return (uint32_t)(int)__dadd_rn(f, 0.5);
     }
     template <int I>
-    __device__ static __forceinline__ void pixel(const ZonalArgs &a, const uint32_t (&r)[NW], uint32_t *hist, uint32_t &nz)
+    __device__ static __forceinline__ void pixel(const ZonalArgs &a, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t one, uint32_t &nz)
     {
         uint32_t any = 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const uint32_t o = scale(a, (r[(I * 8 + 2 * c) >> 2] >> (((I * 8 + 2 * c) & 3) * 8)) & 0xffffu, c);
-            atomicAdd(&hist[c * 256 + o], 1u);
+            red_inc1(on, hist + 4u * (c * 256u + o), one);
             any |= o;
         }
-        nz += (any == 0);
+        nz += (on != 0) & (any == 0);
     }
-    __device__ static __forceinline__ void group_nz(const uint32_t (&)[NW], uint32_t, uint32_t &) {}
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
         const uint16_t *p = (const uint16_t *)a.pixels + pix * 4;
@@ -331,11 +352,12 @@ __device__ __forceinline__ void load_group(const uint8_t *p, uint32_t (&r)[NW])
 }
 
 template <class PX, int I>
-__device__ __forceinline__ void group_pixels(const ZonalArgs &a, const uint32_t (&r)[PX::NW], uint32_t m8, uint32_t *hist, uint32_t &nz)
+__device__ __forceinline__ void group_pixels(const ZonalArgs &a, const uint32_t (&r)[PX::NW], uint32_t m8, uint32_t hist, uint32_t one,
+                                             uint32_t &nz)
 {
     if constexpr (I < 8) {
-        if (m8 & (1u << I)) PX::template pixel<I>(a, r, hist, nz);
-        group_pixels<PX, I + 1>(a, r, m8, hist, nz);
+        PX::template pixel<I>(a, r, m8 & (1u << I), hist, one, nz);
+        group_pixels<PX, I + 1>(a, r, m8, hist, one, nz);
     }
 }
 
@@ -373,10 +395,11 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t m) { return (((m & 0x
 // ---------------------------------------------------------------------------------------------
 // one work item
 // ---------------------------------------------------------------------------------------------
-template <class PX>
+template <class PX, bool FAST>
 __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC> &s, const int road, const int pb,
                                              const int lane, uint32_t &mbar_phase)
 {
+    const uint32_t hist_addr = smem_u32(s.hist), one = a.one;
     const int rp0 = a.road_pair_off[road], rp1 = a.road_pair_off[road + 1];
     const int pe = min(pb + PPI, rp1);
     const bool split = (rp1 - rp0) > PPI;
@@ -643,7 +666,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                         const int yabs = g.row_off + r0 + (int)(en >> 20);
                         return tile_pix + (size_t)yabs * a.W + x8;
                     };
-                    if (a.fast) {
+                    if constexpr (FAST) {
                         uint32_t rn[PX::NW];
                         uint32_t m8n = 0;
                         int e = lane;
@@ -663,8 +686,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                                 m8n = en & 255u;
                                 load_group<PX::BPP, PX::NW>((const uint8_t *)a.pixels + pixel_index(en) * PX::BPP, rn);
                             }
-                            group_pixels<PX, 0>(a, r, m8, s.hist, nz);
-                            PX::group_nz(r, m8, nz);
+                            group_pixels<PX, 0>(a, r, m8, hist_addr, one, nz);
                         }
                     } else {
                         for (int e = lane; e < n; e += 32) {
@@ -758,7 +780,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
 // ---------------------------------------------------------------------------------------------
 // the kernel: persistent teams pulling items
 // ---------------------------------------------------------------------------------------------
-template <class PX>
+template <class PX, bool FAST>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const ZonalArgs a)
 {
     using S = TeamSmem<PX::HC>;
@@ -775,7 +797,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const Zo
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= n_items) break;
         const int2 it = a.items[idx];
-        process_item<PX>(a, s, it.x, it.y, lane, mbar_phase);
+        process_item<PX, FAST>(a, s, it.x, it.y, lane, mbar_phase);
     }
 }
 
@@ -858,12 +880,12 @@ int launch_road_bbox(rs_ctx *ctx, const rs_roads *roads, double *out, cudaStream
 // ---------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------
-template <class PX>
-static int launch_one(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
+template <class PX, bool FAST>
+static int launch_fast(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
 {
     using S = TeamSmem<PX::HC>;
     const size_t smem = sizeof(S) * WARPS;
-    auto kern = zonal_kernel<PX>;
+    auto kern = zonal_kernel<PX, FAST>;
     RS_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     RS_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -873,6 +895,13 @@ static int launch_one(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
     return RS_OK;
+}
+
+template <class PX>
+static int launch_one(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
+{
+    if constexpr (PX::MASK) return launch_fast<PX, false>(ctx, args, st);
+    else return args.fast ? launch_fast<PX, true>(ctx, args, st) : launch_fast<PX, false>(ctx, args, st);
 }
 
 int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
@@ -916,6 +945,7 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     a.status = ctx->d_status;
     if (prm)
         for (int c = 0; c < 4; c++) { a.sk[c] = prm->scale_k[c]; a.so[c] = prm->scale_off[c]; }
+    a.one = 1u;
     a.fast = (tiles->width % 8 == 0) && (((uintptr_t)tiles->pixels & 15u) == 0);
 
     int HC = 0;
