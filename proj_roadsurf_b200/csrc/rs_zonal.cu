@@ -46,7 +46,7 @@ constexpr int WARPS = 4;        // teams per CTA
 constexpr int CTAS_PER_SM = 5;  // occupancy target (shared memory: ~10.6 KB per team)
 constexpr int PPI = 16;         // pairs per work item
 constexpr int VCAP = 96;        // vertices staged in shared memory per road (longer roads read L2)
-constexpr int MASKW = 768;      // mask words per team
+constexpr int MASKW = 896;      // mask words per team
 constexpr int RCMAX = 128;      // rows per mask chunk
 constexpr int ENTCAP = 448;     // 8-pixel group entries queued per team
 constexpr int NCHUNK = 32;      // culling chunks per road
@@ -174,23 +174,31 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     return 1;
 }
 
-// smallest integer y with y + 0.5 >= v / largest integer y with y + 0.5 < v (exact comparisons)
+// Integer <-> binary64 without the conversion unit (F2I / I2F / FRND run on the quarter-rate XU pipe):
+// adding 1.5 * 2^52 leaves rint(v) in the low mantissa word; every step is an exact or correctly rounded
+// binary64 add, so the results below are the same integers floor()/ceil()/(int) casts would give.
+constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
+__device__ __forceinline__ int rint_magic(double v, double &t)      // |v| < 2^31; t = (double)result
+{
+    const double sft = __dadd_rn(v, MAGIC);
+    t = __dsub_rn(sft, MAGIC);
+    return __double2loint(sft);
+}
+__device__ __forceinline__ double int2double_magic(int y)          // exact for every int32
+{
+    return __dsub_rn(__hiloint2double(0x43300000, y ^ (int)0x80000000), 4503601774854144.0);   // 2^52 + 2^31
+}
+// smallest integer y with y + 0.5 >= v (exact comparisons); the largest y with y + 0.5 < v is that minus 1
 __device__ __forceinline__ int first_row_ge(double v)
 {
-    double t = fmin(fmax(v - 0.5, -4.0), 1.0e6);
-    int y = (int)ceil(t);
-    if ((double)(y - 1) + 0.5 >= v) y--;
-    if ((double)y + 0.5 < v) y++;
-    return y;
+    const double vc = fmin(fmax(v, -4.0), 1.0e6);
+    double t;
+    const int ti = rint_magic(__dsub_rn(vc, 0.5), t);
+    if (__dadd_rn(t, 0.5) < vc) return ti + 1;
+    if (__dsub_rn(t, 0.5) >= vc) return ti - 1;
+    return ti;
 }
-__device__ __forceinline__ int last_row_lt(double v)
-{
-    double t = fmin(fmax(v - 0.5, -4.0), 1.0e6);
-    int y = (int)ceil(t) - 1;
-    if ((double)(y + 1) + 0.5 < v) y++;
-    if ((double)y + 0.5 >= v) y--;
-    return y;
-}
+__device__ __forceinline__ int last_row_lt(double v) { return first_row_ge(v) - 1; }
 
 // ---------------------------------------------------------------------------------------------
 // pixel policies: a group is 8 consecutive pixels = NW 32-bit words in registers
@@ -207,18 +215,17 @@ __device__ __forceinline__ uint32_t half_at(const uint32_t (&r)[N]) { return (r[
 // point (BSSY / BRA / BSYNC) per atomic and cannot be predicated.
 __device__ __forceinline__ void red_inc3(uint32_t on, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t one)
 {
-    const uint32_t v = on ? one : 0u;       // shared atomics cannot be predicated: masked-off pixels add 0
+    // shared atomics cannot be predicated: `on` is the pixel's mask bit (0 / 1), masked-off pixels add 0
     asm volatile(
         "red.shared.add.u32 [%0], %3;\n\t"
         "red.shared.add.u32 [%1], %3;\n\t"
         "red.shared.add.u32 [%2], %3;"
-        ::"r"(a0), "r"(a1), "r"(a2), "r"(v)
+        ::"r"(a0), "r"(a1), "r"(a2), "r"(on & one)
         : "memory");
 }
 __device__ __forceinline__ void red_inc1(uint32_t on, uint32_t a0, uint32_t one)
 {
-    const uint32_t v = on ? one : 0u;
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(v) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(on & one) : "memory");
 }
 // byte K of w, times 4 (a histogram bin's byte offset)
 __device__ __forceinline__ uint32_t bin_off(uint32_t w, int k)      // k is a compile-time constant after unrolling
@@ -240,12 +247,13 @@ struct PxBandsU8 {
         uint32_t any = 0;
 #pragma unroll
         for (int c = 0; c < C; c++) any |= o[c];
-        if constexpr (C == 3) red_inc3(on, hist + o[0], hist + 1024 + o[1], hist + 2048 + o[2], one);
+        // the team histogram is 1 KiB aligned: band base | bin offset is one LOP3
+        if constexpr (C == 3) red_inc3(on, hist | o[0], (hist + 1024) | o[1], (hist + 2048) | o[2], one);
         else {
 #pragma unroll
-            for (int c = 0; c < C; c++) red_inc1(on, hist + 1024 * c + o[c], one);
+            for (int c = 0; c < C; c++) red_inc1(on, (hist + 1024 * c) | o[c], one);
         }
-        nz += (on != 0) & (any == 0);
+        nz += (any == 0) ? on : 0u;
     }
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
@@ -275,7 +283,7 @@ struct PxClassScore {
     {
         uint32_t cls = byte_at<2 * I>(r);
         const uint32_t score = byte_at<2 * I + 1>(r);
-        nz += (on != 0) & ((cls | score) == 0);
+        nz += ((cls | score) == 0) ? on : 0u;
         if (cls > 2u) cls = 0u;   // unknown class codes count as "no detection"
         red_inc1(on, hist + 4u * (cls * 256u + score), one);
     }
@@ -311,7 +319,7 @@ struct PxU16x4Rescale {
             red_inc1(on, hist + 4u * (c * 256u + o), one);
             any |= o;
         }
-        nz += (on != 0) & (any == 0);
+        nz += (any == 0) ? on : 0u;
     }
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
@@ -356,7 +364,7 @@ __device__ __forceinline__ void group_pixels(const ZonalArgs &a, const uint32_t 
                                              uint32_t &nz)
 {
     if constexpr (I < 8) {
-        PX::template pixel<I>(a, r, m8 & (1u << I), hist, one, nz);
+        PX::template pixel<I>(a, r, (m8 >> I) & 1u, hist, one, nz);
         group_pixels<PX, I + 1>(a, r, m8, hist, one, nz);
     }
 }
@@ -370,9 +378,9 @@ struct EdgeParams {                 // the 32 edges of one block, written by the
     int off[33];
 };
 template <int HC>
-struct TeamSmem {
+struct alignas(1024) TeamSmem {
+    alignas(1024) uint32_t hist[HC > 0 ? HC * 256 : 4];
     alignas(16) double2 verts[VCAP];
-    alignas(16) uint32_t hist[HC > 0 ? HC * 256 : 4];
     alignas(16) uint32_t mask[MASKW];
     alignas(16) uint32_t rowmap[RCMAX];
     union {                         // the edge pass and the pixel phase never overlap
@@ -500,8 +508,9 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             }
         }
 
-        for (int r0 = 0; r0 < g.h; r0 += rcmax) {
-            const int rc = min(rcmax, g.h - r0);
+        const int rcbal = (g.h + (g.h + rcmax - 1) / rcmax - 1) / ((g.h + rcmax - 1) / rcmax);   // balanced row chunks
+        for (int r0 = 0; r0 < g.h; r0 += rcbal) {
+            const int rc = min(rcbal, g.h - r0);
             // chunks whose bounds reach a row of this row chunk
             const unsigned rel = __ballot_sync(FULL, cy_lo <= cy_hi && cy_hi >= (float)r0 && cy_lo <= (float)(r0 + rc));
             if (rel == 0) continue;
@@ -592,7 +601,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                                 while (s.u.e.off[j + 1] <= f) j++;
                             }
                             const int y = s.u.e.ya[j] + (f - s.u.e.off[j]);
-                            const double dy = (double)y + 0.5;
+                            const double dy = __dadd_rn(int2double_magic(y), 0.5);
                             const double dx1 = s.u.e.dx1[j];
                             // GDAL: intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1, then floor(intersect + 0.5).
                             // The quotient is first taken through the edge's reciprocal; that differs from the
@@ -602,16 +611,20 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                             const double num = __dmul_rn(__dsub_rn(dy, s.u.e.dy1[j]), s.u.e.a[j]);
                             const double qf = __dmul_rn(num, s.u.e.rb[j]);
                             double v = __dadd_rn(__dadd_rn(qf, dx1), 0.5);
-                            double r = floor(v);
-                            if (!(fabs(qf) < 1.0e9) || !(fabs(v) < 1.0e9) || v - r < 1.0e-4 || v - r > 1.0 - 1.0e-4) {
+                            double t;
+                            int ti = rint_magic(fmin(fmax(v, -1.0e9), 1.0e9), t);
+                            if (!(fabs(qf) < 1.0e9) || !(fabs(v) < 1.0e9) || fabs(__dsub_rn(v, t)) < 1.0e-4) {
                                 v = __dadd_rn(__dadd_rn(__ddiv_rn(num, s.u.e.b[j]), dx1), 0.5);
-                                r = floor(v);
+                                v = fmin(fmax(v, -1.0e9), 1.0e9);          // order-preserving: far outside either way
+                                ti = rint_magic(v, t);
                             }
-                            if (r < (double)g.w) {                      // crossings at or beyond the right edge toggle nothing
-                                const int bit = lo + (r > 0.0 ? (int)r : 0);
-                                atomicXor(&s.mask[(y - r0) * pp + (bit >> 5)], 1u << (bit & 31));
-                                atomicOr(&s.rowmap[y - r0], 1u << min(bit >> 5, 31));
-                            }
+                            const int fl = ti - (__dsub_rn(v, t) < 0.0 ? 1 : 0);     // floor(intersect + 0.5)
+                            // crossings at or beyond the right edge toggle nothing (xor / or with 0, no branch)
+                            const int bit = lo + max(fl, 0);
+                            const int word = min(bit >> 5, pitch - 1);
+                            const uint32_t onbit = fl < g.w ? 1u : 0u;
+                            atomicXor(&s.mask[(y - r0) * pp + word], onbit << (bit & 31));
+                            atomicOr(&s.rowmap[y - r0], onbit << min(word, 31));
                         }
                         __syncwarp();
                     }
@@ -784,8 +797,12 @@ template <class PX, bool FAST>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const ZonalArgs a)
 {
     using S = TeamSmem<PX::HC>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) {       // team histograms must be 1 KiB aligned (band base | bin offset)
+        if (threadIdx.x == 0) atomicMin(a.status, (int)RS_ERR_CUDA);
+        return;
+    }
     S &s = reinterpret_cast<S *>(smem_raw)[warp];
     if (lane == 0) mbar_init(&s.mbar, 1);
     __syncwarp();
