@@ -59,8 +59,11 @@ enum rs_hist_mode {
 enum rs_window_mode {
     RS_WINDOW_CROP = 0,        /* rasterio.mask.mask(crop=True): per-pair integer window and its   */
                                /* window transform (fct_misc.py:77)                                */
-    RS_WINDOW_FULL = 1         /* rasterio.features.rasterize(shapes, out_shape, transform): the   */
+    RS_WINDOW_FULL = 1,        /* rasterio.features.rasterize(shapes, out_shape, transform): the   */
                                /* tile transform itself (add_tile_mask.py:112-113)                 */
+    RS_WINDOW_BOUNDLESS = 2    /* rasterstats.zonal_stats: the window of the geometry bounds, NOT   */
+                               /* clipped to the raster (its origin may be negative); pixels off   */
+                               /* the raster are nodata (fct_rasters.py:162-163)                   */
 };
 
 enum rs_nodata_mode {
@@ -197,6 +200,42 @@ int rs_vote_metrics_dev(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *g
 int rs_vote_metrics_host(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int32_t n_roads,
                          const int32_t *cutoffs, int32_t n_thr, int32_t rule, double min_area_frac,
                          int8_t *cover, double *scores, int64_t *confusion, double *metrics);
+
+/*
+ * Ordered pixel extraction: the in-mask pixels of every pair, row-major inside the pair, pairs in
+ * pair_tile order -- what fct_misc.get_pixel_values collects with np.extract (fct_misc.py:87-99) before its
+ * nodata handling.  pair_off int64[n_pairs+1] (always written; pair_off[n_pairs] = total pixel count,
+ * also returned in *n_total); values [total][channels] of the tile dtype, written only when values != NULL
+ * and capacity_pixels >= total (call once with values == NULL to size the buffer).
+ */
+int rs_extract_pixels_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                           int window_mode, int64_t *pair_off, void *values, int64_t capacity_pixels, int64_t *n_total);
+
+/*
+ * 256-bin histogram per group of a uint8 column: the groupby of fct_statistics.get_df_stats_groupby
+ * (fct_statistics.py:55) / the single group of get_df_stats_no_group (:89-94); finalize with
+ * rs_finalize_stats_*.  group int32[n] in [0, n_groups) (other values are skipped); hist uint32[n_groups][256].
+ */
+int rs_group_hist_host(rs_ctx *ctx, const uint8_t *values, const int32_t *group, int64_t n, int32_t n_groups, uint32_t *hist);
+
+/*
+ * determine_class.determine_detected_class on the detection table (determine_class.py:133-179).  The rows
+ * of road r are row_off[r] .. row_off[r+1] (the table sorted by road, original order kept inside a road);
+ * cls int8 (0 artificial, 1 natural), score / weighted_score / area_pred_in_label float64; thresholds
+ * float64[n_thr] (rows with score >= threshold vote).  cover int8[n_thr][n_roads] (enum rs_cover);
+ * scores double[n_thr][n_roads][3] = artificial index, natural index (unrounded), diff_score.
+ */
+int rs_vote_table_host(rs_ctx *ctx, const int32_t *row_off, const int8_t *cls, const double *score, const double *weighted,
+                       const double *area, int32_t n_roads, const double *thresholds, int32_t n_thr, int8_t *cover,
+                       double *scores);
+
+/*
+ * final_metrics.get_tag + get_metrics (final_metrics.py:22-105) from cover codes and ground-truth classes:
+ * cover int8[n_thr][n_roads], gt_class int8[n_roads] (0 / 1, others skipped); confusion int64[n_thr][2][4],
+ * metrics double[n_thr][RS_NMETRIC].
+ */
+int rs_confusion_metrics_host(rs_ctx *ctx, const int8_t *cover, const int8_t *gt_class, int32_t n_roads, int32_t n_thr,
+                              int64_t *confusion, double *metrics);
 
 /*
  * Deterministic synthetic tiles (bench / tests only; the reference ships no imagery,

@@ -168,9 +168,9 @@ def zonal_stats(vectors: Sequence[Sequence[np.ndarray]], raster: np.ndarray, aff
             win[rr0 - r0:rr1 - r0, cc0 - c0:cc1 - c0] = raster[rr0:rr1, cc0:cc1]
         wt = gdal_fill.affine_mul_translation((a, b, c, d, e, f), c0, r0)
         rv = gdal_fill.rasterize(rings, (h, w), wt).astype(bool)
-        masked = ~rv | np.isnan(win)
-        if nodata is not None:
-            masked |= (win == nodata)
+        # rasterstats io.Raster: nodata None becomes -999 (with a warning) and the comparison below still
+        # runs, so the padding of a boundless window is always masked
+        masked = ~rv | np.isnan(win) | (win == fill)
         vals = win[~masked]
         res = {}
         if vals.size == 0:

@@ -17,7 +17,7 @@ STATUS = {
 }
 RS_U8, RS_U16 = 0, 1
 RS_HIST_BANDS, RS_HIST_CLASS_SCORE = 0, 1
-RS_WINDOW_CROP, RS_WINDOW_FULL = 0, 1
+RS_WINDOW_CROP, RS_WINDOW_FULL, RS_WINDOW_BOUNDLESS = 0, 1, 2
 RS_NODATA_RAW, RS_NODATA_NONE, RS_NODATA_ZERO, RS_NODATA_ZERO_MASKED = 0, 1, 2, 3
 RS_NSTAT = 9
 STAT_COLS = ("count", "min", "max", "sum", "sumsq", "mean", "std", "median", "margin")
@@ -31,6 +31,7 @@ EXPORTS = (
     "rs_ctx_last_cuda_error", "rs_ctx_launch_count", "rs_road_bbox_dev", "rs_zonal_hist_dev",
     "rs_zonal_hist_host", "rs_zonal_stats_host", "rs_rasterize_pairs_dev", "rs_rasterize_pairs_host", "rs_finalize_stats_dev",
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
+    "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
 )
 
 
@@ -103,6 +104,11 @@ def load():
     L.rs_finalize_stats_host.argtypes = L.rs_finalize_stats_dev.argtypes[:-1]
     L.rs_vote_metrics_dev.argtypes = [P, P, P, C.c_int32, P, C.c_int32, C.c_int32, C.c_double, P, P, P, P, P]
     L.rs_vote_metrics_host.argtypes = L.rs_vote_metrics_dev.argtypes[:-1]
+    L.rs_extract_pixels_host.argtypes = [P, C.POINTER(RsRoads), C.POINTER(RsTiles), C.POINTER(RsPairs), C.c_int, P, P,
+                                         C.c_int64, C.POINTER(C.c_int64)]
+    L.rs_group_hist_host.argtypes = [P, P, P, C.c_int64, C.c_int32, P]
+    L.rs_vote_table_host.argtypes = [P, P, P, P, P, P, C.c_int32, P, C.c_int32, P, P]
+    L.rs_confusion_metrics_host.argtypes = [P, P, P, C.c_int32, C.c_int32, P, P]
     L.rs_synth_tiles_dev.argtypes = [P, P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_uint64, P]
     for name in EXPORTS:

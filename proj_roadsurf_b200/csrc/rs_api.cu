@@ -361,6 +361,107 @@ int rs_vote_metrics_host(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *
     return finish(ctx);
 }
 
+int rs_extract_pixels_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, int window_mode,
+                           int64_t *pair_off, void *values, int64_t capacity_pixels, int64_t *n_total)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!pairs || !tiles || !roads || !pair_off || !n_total) return RS_ERR_INVALID_ARG;
+    *n_total = 0;
+    const int P = pairs->n_pairs;
+    if (P == 0) { pair_off[0] = 0; return RS_OK; }
+    rs_roads dr;
+    rs_tiles dt;
+    rs_pairs dp;
+    if ((rc = stage_inputs(ctx, roads, tiles, pairs, values != nullptr, dr, dt, dp))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    const size_t mb = (size_t)P * tiles->height * tiles->width;
+    if ((rc = ensure(ctx, ctx->stage[9], mb))) return rc;
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[9].p, 0, mb, st));
+    if ((rc = launch_zonal(ctx, &dr, &dt, &dp, nullptr, nullptr, nullptr, (uint8_t *)ctx->stage[9].p, window_mode, st))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], sizeof(int64_t) * ((size_t)P + 1)))) return rc;
+    const int bpp = tiles->channels * (int)elem_bytes(tiles->dtype);
+    if ((rc = launch_extract(ctx, (const uint8_t *)ctx->stage[9].p, nullptr, dp.pair_tile, P, tiles->height, tiles->width, bpp,
+                             (long long *)ctx->stage[10].p, nullptr, 0, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(pair_off, ctx->stage[10].p, sizeof(int64_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, st));
+    if ((rc = finish(ctx))) return rc;
+    const int64_t total = pair_off[P];
+    *n_total = total;
+    if (!values || capacity_pixels < total || total == 0) return RS_OK;
+    if ((rc = ensure(ctx, ctx->stage[11], (size_t)total * bpp))) return rc;
+    if ((rc = launch_extract(ctx, (const uint8_t *)ctx->stage[9].p, dt.pixels, dp.pair_tile, P, tiles->height, tiles->width, bpp,
+                             nullptr, (uint8_t *)ctx->stage[11].p, 1, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(values, ctx->stage[11].p, (size_t)total * bpp, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
+int rs_group_hist_host(rs_ctx *ctx, const uint8_t *values, const int32_t *group, int64_t n, int32_t n_groups, uint32_t *hist)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || n_groups < 0 || (n > 0 && (!values || !group)) || (n_groups > 0 && !hist)) return RS_ERR_INVALID_ARG;
+    if (n_groups == 0) return RS_OK;
+    if ((rc = up(ctx, ctx->stage[9], values, (size_t)n))) return rc;
+    if ((rc = up(ctx, ctx->stage[10], group, sizeof(int32_t) * (size_t)n))) return rc;
+    const size_t hb = sizeof(uint32_t) * 256 * (size_t)n_groups;
+    if ((rc = ensure(ctx, ctx->stage[11], hb))) return rc;
+    if ((rc = launch_group_hist(ctx, (const uint8_t *)ctx->stage[9].p, (const int *)ctx->stage[10].p, n, n_groups,
+                                (uint32_t *)ctx->stage[11].p, ctx->host_stream)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(hist, ctx->stage[11].p, hb, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
+int rs_vote_table_host(rs_ctx *ctx, const int32_t *row_off, const int8_t *cls, const double *score, const double *weighted,
+                       const double *area, int32_t n_roads, const double *thresholds, int32_t n_thr, int8_t *cover, double *scores)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_roads < 0 || n_thr < 1 || n_thr > 32 || !thresholds || (n_roads > 0 && (!row_off || !cover))) return RS_ERR_INVALID_ARG;
+    if (n_roads == 0) return RS_OK;
+    const size_t N = (size_t)row_off[n_roads], R = (size_t)n_roads, T = (size_t)n_thr;
+    if (N > 0 && (!cls || !score || !weighted || !area)) return RS_ERR_INVALID_ARG;
+    if ((rc = up(ctx, ctx->stage[0], row_off, sizeof(int32_t) * (R + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[1], cls, N))) return rc;
+    if ((rc = up(ctx, ctx->stage[2], score, sizeof(double) * N))) return rc;
+    if ((rc = up(ctx, ctx->stage[3], weighted, sizeof(double) * N))) return rc;
+    if ((rc = up(ctx, ctx->stage[4], area, sizeof(double) * N))) return rc;
+    if ((rc = up(ctx, ctx->stage[5], thresholds, sizeof(double) * T))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], T * R))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[12], sizeof(double) * 3 * T * R))) return rc;
+    if ((rc = launch_vote_table(ctx, (const int *)ctx->stage[0].p, (const int8_t *)ctx->stage[1].p, (const double *)ctx->stage[2].p,
+                                (const double *)ctx->stage[3].p, (const double *)ctx->stage[4].p, n_roads,
+                                (const double *)ctx->stage[5].p, n_thr, (int8_t *)ctx->stage[11].p,
+                                scores ? (double *)ctx->stage[12].p : nullptr, ctx->host_stream)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(cover, ctx->stage[11].p, T * R, cudaMemcpyDeviceToHost, ctx->host_stream));
+    if (scores)
+        RS_CUDA_OK(ctx, cudaMemcpyAsync(scores, ctx->stage[12].p, sizeof(double) * 3 * T * R, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
+int rs_confusion_metrics_host(rs_ctx *ctx, const int8_t *cover, const int8_t *gt_class, int32_t n_roads, int32_t n_thr,
+                              int64_t *confusion, double *metrics)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_roads < 0 || n_thr < 1 || n_thr > 32 || !confusion || (n_roads > 0 && (!cover || !gt_class))) return RS_ERR_INVALID_ARG;
+    const size_t R = (size_t)n_roads, T = (size_t)n_thr;
+    if ((rc = up(ctx, ctx->stage[11], cover, T * R))) return rc;
+    if ((rc = up(ctx, ctx->stage[10], gt_class, R))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[13], sizeof(int64_t) * 8 * T))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[14], sizeof(double) * RS_NMETRIC * T))) return rc;
+    if ((rc = launch_confusion(ctx, (const int8_t *)ctx->stage[11].p, (const int8_t *)ctx->stage[10].p, n_roads, n_thr,
+                               (int64_t *)ctx->stage[13].p, metrics ? (double *)ctx->stage[14].p : nullptr, ctx->host_stream)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(confusion, ctx->stage[13].p, sizeof(int64_t) * 8 * T, cudaMemcpyDeviceToHost, ctx->host_stream));
+    if (metrics)
+        RS_CUDA_OK(ctx, cudaMemcpyAsync(metrics, ctx->stage[14].p, sizeof(double) * RS_NMETRIC * T, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
 int rs_synth_tiles_dev(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int32_t n_tiles, int32_t height, int32_t width,
                        int32_t channels, int32_t dtype, int32_t kind, uint64_t seed, void *stream)
 {

@@ -1,0 +1,209 @@
+// Table-shaped entry points around the overlay kernels (sm_100a):
+//   ordered pixel extraction   fct_misc.get_pixel_values' return value: the in-mask pixels of every (road, tile)
+//                              pair in row-major order (scripts/functions/fct_misc.py:87-99, np.extract)
+//   group histograms           the groupby of fct_statistics.get_df_stats_groupby (scripts/functions/fct_statistics.py:55)
+//                              on uint8 pixel tables: 256-bin histogram per group, finalized by rs_finalize_stats
+//   table vote                 determine_class.determine_detected_class on the detection table
+//                              (scripts/road_segmentation/determine_class.py:133-179)
+//   confusion + metrics        final_metrics.get_tag / get_metrics from cover / ground-truth codes
+//                              (scripts/road_segmentation/final_metrics.py:22-105)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_scan.cuh>
+
+#include "rs_internal.h"
+
+namespace rs {
+
+constexpr unsigned FULLM = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// ordered extraction: masks uint8[P][H][W] -> per-row counts -> exclusive scan -> packed pixel rows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_count_kernel(const uint8_t *__restrict__ masks, int W, long long n_rows, int *__restrict__ cnt)
+{
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const uint8_t *m = masks + row * W;
+    int c = 0;
+    for (int x = lane; x < W; x += 32) c += m[x] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULLM, c, o);
+    if (lane == 0) cnt[row] = c;
+}
+
+// one warp per (pair, row): ballot-compacts the row's in-mask pixels, in x order, behind the row's offset
+__global__ void __launch_bounds__(256) row_write_kernel(const uint8_t *__restrict__ masks, const uint8_t *__restrict__ pixels,
+                                                        const int *__restrict__ pair_tile, int H, int W, int bpp, long long n_rows,
+                                                        const int *__restrict__ row_off, uint8_t *__restrict__ out)
+{
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const int p = (int)(row / H), y = (int)(row - (long long)p * H);
+    const uint8_t *m = masks + row * W;
+    const uint8_t *src = pixels + ((size_t)pair_tile[p] * H + y) * (size_t)W * bpp;
+    long long base = row_off[row];
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        const bool on = x < W && m[x] != 0;
+        const unsigned b = __ballot_sync(FULLM, on);
+        if (on) {
+            uint8_t *d = out + (size_t)(base + __popc(b & ((1u << lane) - 1u))) * bpp;
+            for (int k = 0; k < bpp; k++) d[k] = src[(size_t)x * bpp + k];
+        }
+        base += __popc(b);
+    }
+}
+
+__global__ void pair_offsets_kernel(const int *__restrict__ row_off, const int *__restrict__ row_cnt, int H, int n_pairs,
+                                    long long n_rows, long long *__restrict__ pair_off)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_pairs) pair_off[p] = row_off[(long long)p * H];
+    if (p == n_pairs) pair_off[p] = n_rows ? (long long)row_off[n_rows - 1] + row_cnt[n_rows - 1] : 0;
+}
+
+int launch_extract(rs_ctx *ctx, const uint8_t *masks, const void *pixels, const int *pair_tile, int n_pairs, int H, int W, int bpp,
+                   long long *pair_off_dev, uint8_t *values_dev, int phase, cudaStream_t st)
+{
+    const long long n_rows = (long long)n_pairs * H;
+    if (n_rows * W >= (1ll << 31)) return RS_ERR_UNSUPPORTED;          // int32 offsets
+    int rc;
+    if ((rc = ensure(ctx, ctx->stage[12], sizeof(int) * (size_t)(n_rows + 1)))) return rc;    // counts
+    if ((rc = ensure(ctx, ctx->stage[13], sizeof(int) * (size_t)(n_rows + 1)))) return rc;    // offsets
+    int *cnt = (int *)ctx->stage[12].p, *off = (int *)ctx->stage[13].p;
+    const unsigned blocks = (unsigned)((n_rows * 32 + 255) / 256);
+    if (phase == 0) {
+        if (n_rows) {
+            row_count_kernel<<<blocks, 256, 0, st>>>(masks, W, n_rows, cnt);
+            ctx->launches++;
+            size_t tmp = 0;
+            RS_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, off, (int)n_rows, st));
+            if ((rc = ensure(ctx, ctx->stage[14], tmp))) return rc;
+            RS_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->stage[14].p, tmp, cnt, off, (int)n_rows, st));
+        }
+        pair_offsets_kernel<<<(n_pairs + 256) / 256, 256, 0, st>>>(off, cnt, H, n_pairs, n_rows, pair_off_dev);
+        ctx->launches++;
+    } else if (n_rows) {
+        row_write_kernel<<<blocks, 256, 0, st>>>(masks, (const uint8_t *)pixels, pair_tile, H, W, bpp, n_rows, off, values_dev);
+        ctx->launches++;
+    }
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// group histograms of a uint8 column
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) group_hist_kernel(const uint8_t *__restrict__ values, const int *__restrict__ group, long long n,
+                                                         int n_groups, uint32_t *__restrict__ hist)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int g = group[i];
+        if (g >= 0 && g < n_groups) atomicAdd(&hist[(size_t)g * 256 + values[i]], 1u);
+    }
+}
+
+int launch_group_hist(rs_ctx *ctx, const uint8_t *values, const int *group, long long n, int n_groups, uint32_t *hist, cudaStream_t st)
+{
+    RS_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * (size_t)n_groups, st));
+    if (n > 0) {
+        const int blocks = (int)((n + 255) / 256 < (long long)ctx->sm_count * 8 ? (n + 255) / 256 : (long long)ctx->sm_count * 8);
+        group_hist_kernel<<<blocks, 256, 0, st>>>(values, group, n, n_groups, hist);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+    }
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// table vote: thread per (road, threshold); rows of a road are contiguous and summed in row order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) vote_table_kernel(const int *__restrict__ row_off, const int8_t *__restrict__ cls,
+                                                         const double *__restrict__ score, const double *__restrict__ weighted,
+                                                         const double *__restrict__ area, int n_roads, const double *__restrict__ thr,
+                                                         int n_thr, int8_t *__restrict__ cover, double *__restrict__ scores)
+{
+    const int road = blockIdx.x * blockDim.x + threadIdx.x, ti = blockIdx.y;
+    if (road >= n_roads || ti >= n_thr) return;
+    const double th = thr[ti];
+    double sw[2] = {0.0, 0.0}, sa[2] = {0.0, 0.0};
+    int seen[2] = {0, 0}, any = 0;
+    for (int i = row_off[road]; i < row_off[road + 1]; i++) {
+        if (!(score[i] >= th)) continue;                       // valid_predictions: score >= threshold
+        any = 1;
+        const int k = cls[i];
+        if (k == 0 || k == 1) {
+            sw[k] = __dadd_rn(sw[k], weighted[i]);
+            sa[k] = __dadd_rn(sa[k], area[i]);
+            seen[k] = 1;
+        }
+    }
+    // index_k = sum(weighted) / sum(area), 0 when the class is absent or its weighted sum is 0
+    const double ia = (seen[0] && sw[0] != 0.0) ? __ddiv_rn(sw[0], sa[0]) : 0.0;
+    const double in_ = (seen[1] && sw[1] != 0.0) ? __ddiv_rn(sw[1], sa[1]) : 0.0;
+    int cov;
+    double diff = 0.0;
+    if (!any) cov = RS_COVER_UNDETECTED;
+    else if (ia == in_) cov = RS_COVER_UNDETERMINED;
+    else {
+        cov = ia > in_ ? RS_COVER_ARTIFICIAL : RS_COVER_NATURAL;
+        diff = fabs(__dsub_rn(ia, in_));
+    }
+    const size_t o = (size_t)ti * n_roads + road;
+    cover[o] = (int8_t)cov;
+    if (scores) {
+        scores[3 * o + 0] = any ? ia : 0.0;
+        scores[3 * o + 1] = any ? in_ : 0.0;
+        scores[3 * o + 2] = diff;
+    }
+}
+
+int launch_vote_table(rs_ctx *ctx, const int *row_off, const int8_t *cls, const double *score, const double *weighted,
+                      const double *area, int n_roads, const double *thr_dev, int n_thr, int8_t *cover, double *scores, cudaStream_t st)
+{
+    if (n_roads == 0) return RS_OK;
+    dim3 grid((n_roads + 127) / 128, n_thr);
+    vote_table_kernel<<<grid, 128, 0, st>>>(row_off, cls, score, weighted, area, n_roads, thr_dev, n_thr, cover, scores);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// confusion counts of cover codes against ground-truth codes (then metrics_kernel of rs_tables.cu)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) confusion_kernel(const int8_t *__restrict__ cover, const int8_t *__restrict__ gt, int n_roads,
+                                                        unsigned long long *__restrict__ confusion)
+{
+    __shared__ unsigned int c[8];
+    if (threadIdx.x < 8) c[threadIdx.x] = 0;
+    __syncthreads();
+    const int ti = blockIdx.y;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_roads; r += gridDim.x * blockDim.x) {
+        const int g = gt[r], cv = cover[(size_t)ti * n_roads + r];
+        if ((g == 0 || g == 1) && cv >= 0 && cv < 4) atomicAdd(&c[g * 4 + cv], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && c[threadIdx.x]) atomicAdd(&confusion[(size_t)ti * 8 + threadIdx.x], (unsigned long long)c[threadIdx.x]);
+}
+
+int launch_confusion(rs_ctx *ctx, const int8_t *cover, const int8_t *gt, int n_roads, int n_thr, int64_t *confusion, double *metrics,
+                     cudaStream_t st)
+{
+    RS_CUDA_OK(ctx, cudaMemsetAsync(confusion, 0, sizeof(int64_t) * 8 * (size_t)n_thr, st));
+    if (n_roads > 0) {
+        int bx = (n_roads + 255) / 256;
+        if (bx > ctx->sm_count * 4) bx = ctx->sm_count * 4;
+        confusion_kernel<<<dim3(bx, n_thr), 256, 0, st>>>(cover, gt, n_roads, (unsigned long long *)confusion);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+    }
+    if (metrics) return launch_metrics(ctx, confusion, n_thr, metrics, st);
+    return RS_OK;
+}
+
+}  // namespace rs

@@ -57,6 +57,14 @@ int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero
 int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int n_roads,
                 const int32_t *cutoffs_host, int n_thr, int rule, double min_area_frac, int8_t *cover,
                 double *scores, int64_t *confusion, double *metrics, cudaStream_t st);
+int launch_metrics(rs_ctx *ctx, const int64_t *confusion, int n_thr, double *metrics, cudaStream_t st);
+int launch_extract(rs_ctx *ctx, const uint8_t *masks, const void *pixels, const int *pair_tile, int n_pairs, int H, int W, int bpp,
+                   long long *pair_off_dev, uint8_t *values_dev, int phase, cudaStream_t st);
+int launch_group_hist(rs_ctx *ctx, const uint8_t *values, const int *group, long long n, int n_groups, uint32_t *hist, cudaStream_t st);
+int launch_vote_table(rs_ctx *ctx, const int *row_off, const int8_t *cls, const double *score, const double *weighted,
+                      const double *area, int n_roads, const double *thr_dev, int n_thr, int8_t *cover, double *scores, cudaStream_t st);
+int launch_confusion(rs_ctx *ctx, const int8_t *cover, const int8_t *gt, int n_roads, int n_thr, int64_t *confusion, double *metrics,
+                     cudaStream_t st);
 int launch_synth(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int n_tiles, int H, int W, int C, int dtype,
                  int kind, uint64_t seed, cudaStream_t st);
 

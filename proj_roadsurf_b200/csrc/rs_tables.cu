@@ -301,6 +301,15 @@ __global__ void metrics_kernel(const u64 *confusion, int n_thr, double *metrics)
     o[RS_MET_PB] = pb; o[RS_MET_RB] = rb; o[RS_MET_F1B] = f1b;
 }
 
+int launch_metrics(rs_ctx *ctx, const int64_t *confusion, int n_thr, double *metrics, cudaStream_t st)
+{
+    if (n_thr < 1 || n_thr > RS_MAX_THR || !confusion || !metrics) return RS_ERR_INVALID_ARG;
+    metrics_kernel<<<1, RS_MAX_THR, 0, st>>>((const u64 *)confusion, n_thr, metrics);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
 int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int n_roads,
                 const int32_t *cutoffs_host, int n_thr, int rule, double min_area_frac, int8_t *cover, double *scores,
                 int64_t *confusion, double *metrics, cudaStream_t st)
@@ -321,11 +330,7 @@ int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class,
         ctx->launches++;
         RS_CUDA_OK(ctx, cudaGetLastError());
     }
-    if (metrics) {
-        metrics_kernel<<<1, RS_MAX_THR, 0, st>>>((const u64 *)confusion, n_thr, metrics);
-        ctx->launches++;
-        RS_CUDA_OK(ctx, cudaGetLastError());
-    }
+    if (metrics) return launch_metrics(ctx, confusion, n_thr, metrics, st);
     return RS_OK;
 }
 

@@ -121,7 +121,9 @@ struct ZonalArgs {
 
 // per-pair geometry: integer window inside the tile + world->window-pixel transform
 struct PairGeom {
-    int col_off, row_off, w, h;
+    int col_off, row_off, w, h;     // window inside the tile (what is masked and read)
+    int xshift, yshift, wu;         // RS_WINDOW_BOUNDLESS: the rasterized window starts xshift columns / yshift rows
+                                    // before the visible one and is wu columns wide (0, 0, w otherwise)
     double inv0, inv1, inv3, inv5;
 };
 
@@ -135,6 +137,7 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     if (sb != 0.0 || sd != 0.0 || sa == 0.0 || se == 0.0) return RS_ERR_ROTATED;
     if (window_mode == RS_WINDOW_FULL) {
         g.col_off = 0; g.row_off = 0; g.w = W; g.h = H;
+        g.xshift = 0; g.yshift = 0; g.wu = W;
         g.inv0 = __ddiv_rn(-sc, sa); g.inv1 = __ddiv_rn(1.0, sa);
         g.inv3 = __ddiv_rn(-sf, se); g.inv5 = __ddiv_rn(1.0, se);
         return 1;
@@ -163,8 +166,14 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     const int ic0 = (int)fmax(c0, 0.0), ic1 = (int)fmin(c1, (double)W);
     g.col_off = ic0; g.row_off = ir0; g.w = ic1 - ic0; g.h = ir1 - ir0;
     if (g.w <= 0 || g.h <= 0) return 0;
-    // transform * Affine.translation(col_off, row_off), then GDALInvGeoTransform (north-up branch)
-    const double xo = (double)ic0, yo = (double)ir0;
+    g.xshift = 0; g.yshift = 0; g.wu = g.w;
+    double xo = (double)ic0, yo = (double)ir0;
+    if (window_mode == RS_WINDOW_BOUNDLESS) {       // rasterstats: the window keeps its unclipped origin
+        if (c0 < -1.0e9 || r0 < -1.0e9 || ww > 2.0e9) return RS_ERR_UNSUPPORTED;
+        xo = c0; yo = r0;
+        g.xshift = ic0 - (int)c0; g.yshift = ir0 - (int)r0; g.wu = (int)fmin(ww, 2.0e9);
+    }
+    // transform * Affine.translation(xo, yo), then GDALInvGeoTransform (north-up branch)
     const double wa = __dadd_rn(__dmul_rn(sa, 1.0), __dmul_rn(sb, 0.0));
     const double wc = __dadd_rn(__dadd_rn(__dmul_rn(sa, xo), __dmul_rn(sb, yo)), sc);
     const double we = __dadd_rn(__dmul_rn(sd, 0.0), __dmul_rn(se, 1.0));
@@ -502,9 +511,9 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             const double yb_ = __dadd_rn(g.inv3, __dmul_rn((double)s.cb_ymax[lane], g.inv5));
             const double xa_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmin[lane], g.inv1));
             const double xb_ = __dadd_rn(g.inv0, __dmul_rn((double)s.cb_xmax[lane], g.inv1));
-            if (fmin(xa_, xb_) - 1.0 <= (double)g.w) {       // chunks right of the window toggle nothing
-                cy_lo = __double2float_rd(fmin(ya_, yb_) - 1.0);
-                cy_hi = __double2float_ru(fmax(ya_, yb_) + 1.0);
+            if (fmin(xa_, xb_) - 1.0 <= (double)(g.xshift + g.w)) {       // chunks right of the window toggle nothing
+                cy_lo = __double2float_rd(fmin(ya_, yb_) - 1.0 - (double)g.yshift);
+                cy_hi = __double2float_ru(fmax(ya_, yb_) + 1.0 - (double)g.yshift);
             }
         }
 
@@ -543,19 +552,20 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                                 // horizontal edge: burnt separately iff it lies exactly on a scanline of this
                                 // chunk and runs towards -x
                                 const double fy = floor(y1);
-                                hb = (x1 > x2) && (fy + 0.5 == y1) && fy >= (double)r0 && fy < (double)(r0 + rc);
-                            } else if (fmin(x1, x2) <= (double)g.w + 1.0) {
-                                ya = max(first_row_ge(fmin(y1, y2)), r0);
-                                const int yb = min(last_row_lt(fmax(y1, y2)), r0 + rc - 1);
+                                hb = (x1 > x2) && (fy + 0.5 == y1) && fy >= (double)(r0 + g.yshift) && fy < (double)(r0 + g.yshift + rc);
+                            } else if (fmin(x1, x2) <= (double)(g.xshift + g.w) + 1.0) {
+                                ya = max(first_row_ge(fmin(y1, y2)) - g.yshift, r0);
+                                const int yb = min(last_row_lt(fmax(y1, y2)) - g.yshift, r0 + rc - 1);
                                 n = max(yb - ya + 1, 0);
                             }
                         }
                         if (pass == 1) {
                             if (hb) {
                                 const double hx1 = floor(__dadd_rn(x2, 0.5)), hx2 = floor(__dadd_rn(x1, 0.5));
-                                if (!(hx1 > (double)(g.w - 1) || hx2 <= 0.0)) {
-                                    const int xa = (int)fmax(hx1, 0.0), xb = (int)fmin(hx2 - 1.0, (double)(g.w - 1));
-                                    const int row = (int)floor(y1) - r0;
+                                if (!(hx1 > (double)(g.wu - 1) || hx2 <= 0.0)) {
+                                    const int xa = max((int)fmax(hx1, 0.0) - g.xshift, 0);
+                                    const int xb = min((int)fmin(hx2 - 1.0, (double)(g.wu - 1)) - g.xshift, g.w - 1);
+                                    const int row = (int)floor(y1) - g.yshift - r0;
                                     if (xa <= xb) {
                                         for (int k = (lo + xa) >> 5; k <= ((lo + xb) >> 5); k++) {
                                             const int b0 = max(lo + xa - 32 * k, 0), b1 = min(lo + xb - 32 * k, 31);
@@ -601,7 +611,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                                 while (s.u.e.off[j + 1] <= f) j++;
                             }
                             const int y = s.u.e.ya[j] + (f - s.u.e.off[j]);
-                            const double dy = __dadd_rn(int2double_magic(y), 0.5);
+                            const double dy = __dadd_rn(int2double_magic(y + g.yshift), 0.5);
                             const double dx1 = s.u.e.dx1[j];
                             // GDAL: intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1, then floor(intersect + 0.5).
                             // The quotient is first taken through the edge's reciprocal; that differs from the
@@ -618,7 +628,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                                 v = fmin(fmax(v, -1.0e9), 1.0e9);          // order-preserving: far outside either way
                                 ti = rint_magic(v, t);
                             }
-                            const int fl = ti - (__dsub_rn(v, t) < 0.0 ? 1 : 0);     // floor(intersect + 0.5)
+                            const int fl = ti - (__dsub_rn(v, t) < 0.0 ? 1 : 0) - g.xshift;     // floor(intersect + 0.5), visible column
                             // crossings at or beyond the right edge toggle nothing (xor / or with 0, no branch)
                             const int bit = lo + max(fl, 0);
                             const int word = min(bit >> 5, pitch - 1);
@@ -933,7 +943,7 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     if (pairs->n_pairs > 0 && (!pairs->pair_tile || !tiles->gt)) return RS_ERR_INVALID_ARG;
     if (((uintptr_t)roads->xy & 15u) != 0) return RS_ERR_INVALID_ARG;      // TMA bulk source alignment
     if (tiles->width > MAX_WIDTH || tiles->width < 1 || tiles->height < 1) return RS_ERR_UNSUPPORTED;
-    if (window_mode != RS_WINDOW_CROP && window_mode != RS_WINDOW_FULL) return RS_ERR_INVALID_ARG;
+    if (window_mode != RS_WINDOW_CROP && window_mode != RS_WINDOW_FULL && window_mode != RS_WINDOW_BOUNDLESS) return RS_ERR_INVALID_ARG;
 
     // item list scratch: at most one item per PPI pairs plus one partial item per road
     const size_t cap = (size_t)pairs->n_pairs / PPI + (size_t)roads->n_roads + 1;

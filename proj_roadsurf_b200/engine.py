@@ -20,7 +20,7 @@ from . import _native as N
 from .geometry import PairList, RoadSet, TileBatch
 
 _HIST_MODES = {"bands": N.RS_HIST_BANDS, "class_score": N.RS_HIST_CLASS_SCORE}
-_WINDOW_MODES = {"crop": N.RS_WINDOW_CROP, "full": N.RS_WINDOW_FULL}
+_WINDOW_MODES = {"crop": N.RS_WINDOW_CROP, "full": N.RS_WINDOW_FULL, "boundless": N.RS_WINDOW_BOUNDLESS}
 _NODATA_MODES = {"raw": N.RS_NODATA_RAW, "none": N.RS_NODATA_NONE, "zero": N.RS_NODATA_ZERO,
                  "zero_masked": N.RS_NODATA_ZERO_MASKED}
 _RULES = {"count": N.RS_VOTE_COUNT, "score": N.RS_VOTE_SCORE}
@@ -219,6 +219,68 @@ class Engine:
                                            float(min_area_frac), _np_ptr(cover), _np_ptr(scores), _np_ptr(conf), _np_ptr(met))
         N.check(st, "rs_vote_metrics_host", self._ctx)
         return cover, scores, conf, met
+
+    def extract_pixels_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, window: str = "crop"):
+        """In-mask pixels of every pair, row-major inside a pair (rs_extract_pixels_host).
+        Returns pair_off (n_pairs + 1,) int64 and values (total, C) of the tile dtype."""
+        px = np.ascontiguousarray(tiles.pixels)
+        dtype = N.RS_U16 if px.dtype == np.uint16 else N.RS_U8
+        xy = np.ascontiguousarray(roads.xy, np.float64)
+        ro, rro = np.ascontiguousarray(roads.ring_off, np.int32), np.ascontiguousarray(roads.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        rpo, pt = np.ascontiguousarray(pairs.road_pair_off, np.int32), np.ascontiguousarray(pairs.pair_tile, np.int32)
+        gt = np.ascontiguousarray(tiles.gt, np.float64)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), roads.n_roads, roads.n_rings, roads.n_verts)
+        td = N.RsTiles(_np_ptr(px), _np_ptr(gt), tiles.n_tiles, tiles.height, tiles.width, tiles.channels, dtype)
+        pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
+        pair_off = np.zeros(pairs.n_pairs + 1, np.int64)
+        total = C.c_int64(0)
+        st = self.lib.rs_extract_pixels_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), _WINDOW_MODES[window],
+                                             _np_ptr(pair_off), None, 0, C.byref(total))
+        N.check(st, "rs_extract_pixels_host", self._ctx)
+        values = np.zeros((int(total.value), tiles.channels), px.dtype)
+        if total.value:
+            st = self.lib.rs_extract_pixels_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), _WINDOW_MODES[window],
+                                                 _np_ptr(pair_off), _np_ptr(values), int(total.value), C.byref(total))
+            N.check(st, "rs_extract_pixels_host", self._ctx)
+        return pair_off, values
+
+    def group_hist_host(self, values: np.ndarray, group: np.ndarray, n_groups: int) -> np.ndarray:
+        """(n_groups, 256) uint32 histograms of a uint8 column by group index (rs_group_hist_host)."""
+        v = np.ascontiguousarray(values, np.uint8)
+        g = np.ascontiguousarray(group, np.int32)
+        assert v.shape == g.shape and v.ndim == 1
+        hist = np.zeros((int(n_groups), 256), np.uint32)
+        st = self.lib.rs_group_hist_host(self._ctx, _np_ptr(v), _np_ptr(g), int(v.shape[0]), int(n_groups), _np_ptr(hist))
+        N.check(st, "rs_group_hist_host", self._ctx)
+        return hist
+
+    def vote_table_host(self, row_off, cls, score, weighted, area, thresholds):
+        """determine_detected_class on a detection table sorted by road (rs_vote_table_host).
+        Returns cover (T, R) int8 and scores (T, R, 3) = artificial index, natural index, diff."""
+        row_off = np.ascontiguousarray(row_off, np.int32)
+        R = len(row_off) - 1
+        cls = np.ascontiguousarray(cls, np.int8)
+        score, weighted, area = (np.ascontiguousarray(a, np.float64) for a in (score, weighted, area))
+        thr = np.ascontiguousarray(thresholds, np.float64)
+        T = len(thr)
+        cover = np.zeros((T, R), np.int8)
+        scores = np.zeros((T, R, 3), np.float64)
+        st = self.lib.rs_vote_table_host(self._ctx, _np_ptr(row_off), _np_ptr(cls), _np_ptr(score), _np_ptr(weighted),
+                                         _np_ptr(area), R, _np_ptr(thr), T, _np_ptr(cover), _np_ptr(scores))
+        N.check(st, "rs_vote_table_host", self._ctx)
+        return cover, scores
+
+    def confusion_metrics_host(self, cover: np.ndarray, gt_class: np.ndarray):
+        """cover (T, R) int8 codes vs gt_class (R,) -> confusion (T, 2, 4) int64, metrics (T, 12)."""
+        cover = np.ascontiguousarray(np.atleast_2d(cover), np.int8)
+        gt = np.ascontiguousarray(gt_class, np.int8)
+        T, R = cover.shape
+        conf = np.zeros((T, 2, 4), np.int64)
+        met = np.zeros((T, N.RS_NMETRIC), np.float64)
+        st = self.lib.rs_confusion_metrics_host(self._ctx, _np_ptr(cover), _np_ptr(gt), R, T, _np_ptr(conf), _np_ptr(met))
+        N.check(st, "rs_confusion_metrics_host", self._ctx)
+        return conf, met
 
     # ------------------------------------------------------------------ device family (torch tensors)
     def _torch(self):

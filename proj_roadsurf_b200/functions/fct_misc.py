@@ -1,0 +1,173 @@
+"""Mirror of scripts/functions/fct_misc.py for the overlay path.
+
+``get_pixel_values`` keeps the reference signature and return value (fct_misc.py:57-123); the mask and the
+ordered pixel extraction run on the GPU (rs_extract_pixels_host), the reference's nodata handling
+(:87-119) is applied to the extracted rows.  ``get_pixel_values_batch`` is the batched form the double loop
+of statistical_analysis.py:180-193 collapses into.  Tile decoding is outside the path: a tile is either
+registered in memory (``register_tile``) or opened through rasterio when that is installed.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import Dict, Optional
+
+import numpy as np
+import pandas as pd
+
+try:
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+    logger = logging.getLogger("roadsurf_b200")
+
+from ..engine import default_engine
+from ..geometry import PairList, RoadSet, TileBatch, rasterio_window
+
+_TILES: Dict[str, dict] = {}
+
+
+def format_logger(logger):
+    """fct_misc.py:16-26 -- four level-specific stderr sinks."""
+    logger.remove()
+    logger.add(sys.stderr, format="{time:YYYY-MM-DD HH:mm:ss} - {level} - {message}",
+               level="INFO", filter=lambda record: record["level"].no < 25)
+    logger.add(sys.stderr, format="{time:YYYY-MM-DD HH:mm:ss} - <green>{level}</green> - {message}",
+               level="SUCCESS", filter=lambda record: record["level"].no < 30)
+    logger.add(sys.stderr, format="{time:YYYY-MM-DD HH:mm:ss} - <yellow>{level}</yellow> - {message}",
+               level="WARNING", filter=lambda record: record["level"].no < 40)
+    logger.add(sys.stderr, format="{time:YYYY-MM-DD HH:mm:ss} - <red>{level}</red> - <level>{message}</level>",
+               level="ERROR")
+    return logger
+
+
+def test_crs(crs1, crs2="EPSG:2056"):
+    """fct_misc.py:28-41 -- print and sys.exit(1) on mismatch.  Accepts anything with a ``crs`` attribute."""
+    crs1 = getattr(crs1, "crs", crs1)
+    crs2 = getattr(crs2, "crs", crs2)
+    try:
+        assert (crs1 == crs2), f"CRS mismatch between the two files ({crs1} vs {crs2})."
+    except Exception as e:  # noqa: BLE001
+        print(e)
+        sys.exit(1)
+
+
+test_crs.__test__ = False       # not a pytest test
+
+
+def ensure_dir_exists(dirpath):
+    """fct_misc.py:43-54"""
+    if not os.path.exists(dirpath):
+        os.makedirs(dirpath)
+        print(f"The directory {dirpath} was created.")
+    return dirpath
+
+
+# ------------------------------------------------------------------------------------------
+# tiles
+# ------------------------------------------------------------------------------------------
+def register_tile(path: str, data: np.ndarray, transform, nodata=None, layout: str = "HWC") -> None:
+    """Make an in-memory tile available under ``path`` (what rasterio.open(path) would read)."""
+    a = np.asarray(data)
+    if a.ndim == 2:
+        a = a[..., None]
+    elif layout == "CHW":
+        a = np.moveaxis(a, 0, 2)
+    _TILES[path] = {"data": np.ascontiguousarray(a), "transform": tuple(float(v) for v in transform)[:6], "nodata": nodata}
+
+
+def clear_tiles() -> None:
+    _TILES.clear()
+
+
+def open_tile(tile) -> Optional[dict]:
+    """dict {'data' (H, W, C), 'transform' (a, b, c, d, e, f), 'nodata'} of a tile given as such a dict, a
+    registered path, or a file rasterio can open; None where the reference catches RasterioIOError."""
+    if isinstance(tile, dict):
+        return tile
+    if tile in _TILES:
+        return _TILES[tile]
+    try:
+        import rasterio                       # not part of this image; used when the deployment has it
+    except Exception:  # noqa: BLE001
+        return None
+    try:
+        with rasterio.open(tile) as src:
+            t = src.transform
+            return {"data": np.ascontiguousarray(np.moveaxis(src.read(), 0, 2)), "transform": (t.a, t.b, t.c, t.d, t.e, t.f),
+                    "nodata": src.nodata}
+    except Exception:  # noqa: BLE001  (RasterioIOError)
+        return None
+
+
+# ------------------------------------------------------------------------------------------
+# get_pixel_values
+# ------------------------------------------------------------------------------------------
+def _frames_from_rows(values: np.ndarray, no_data, BANDS, tile_name: str, kwargs: dict) -> pd.DataFrame:
+    """fct_misc.py:87-119 on the ordered in-mask rows `values` (n, C)."""
+    bands = list(BANDS)
+    dico = {}
+    length_bands = []
+    for band in bands:
+        data = values[:, band - 1]
+        # outside the mask rasterio fills with nodata (or 0): those pixels never reach this table when the
+        # tile has a nodata value, and are dropped by the all-zero rule below when it has none
+        val = data if no_data is None else data[data != no_data]
+        dico[f"band{band}"] = val
+        length_bands.append(len(val))
+    max_length = max(length_bands) if length_bands else 0
+    for band in bands:
+        n = length_bands[band - 1]                 # the reference indexes with band-1 (BANDS starts at 1)
+        if n < max_length:
+            dico[f"band{band}"] = np.append(dico[f"band{band}"], [no_data] * (max_length - n))
+            logger.warning(f"{max_length - n} pixels was/were missing on the band {band} on the tile {tile_name[-18:]} and"
+                           + f" got replaced with the value used of no data ({no_data}).")
+    dico.update(**kwargs)
+    frame = pd.DataFrame(dico)
+    if no_data is None:
+        cols = [f"band{band}" for band in bands]
+        frame = frame.drop(frame[frame[cols].max(axis=1) == 0].index)
+    return frame
+
+
+def get_pixel_values(geoms, tile, BANDS=range(1, 4), pixel_values=pd.DataFrame(), **kwargs):
+    """Pixels of ``tile`` under the polygon ``geoms`` as DataFrame rows ``band{b}`` (+ kwargs columns), appended
+    to ``pixel_values`` -- same signature, row order (row-major) and nodata quirks as fct_misc.py:57-123.
+    A missing tile logs an error and returns an empty DataFrame (:83-85); shapes that miss the raster raise
+    ValueError like rasterio.mask.mask."""
+    t = open_tile(tile)
+    if t is None:
+        logger.error(f"The tile {tile} not found")
+        return pd.DataFrame()
+    data = np.asarray(t["data"])
+    roads = RoadSet.from_geometries([geoms])
+    tb = TileBatch.from_arrays(data[None], np.asarray(t["transform"], np.float64)[None], t.get("nodata"))
+    pairs = PairList.from_pairs(1, [0], [0])
+    eng = default_engine()
+    if roads.n_verts == 0 or rasterio_window(tb.gt[0], roads.bbox[0], tb.width, tb.height) is None:
+        raise ValueError("Input shapes do not overlap raster.")
+    _, values = eng.extract_pixels_host(roads, tb, pairs, window="crop")
+    frame = _frames_from_rows(values, t.get("nodata"), BANDS, tile if isinstance(tile, str) else "<memory>", kwargs)
+    return pd.concat([pixel_values, frame], ignore_index=True)
+
+
+def get_pixel_values_batch(roads: RoadSet, tiles: TileBatch, pairs: PairList, BANDS=range(1, 4), road_ids=None,
+                           engine=None) -> pd.DataFrame:
+    """The whole double loop of statistical_analysis.py:180-193 in one call: the concatenated
+    ``pixels_per_band`` table (columns band{b}, road_id), roads in order, tiles in pair order inside a road."""
+    eng = engine or default_engine()
+    pair_off, values = eng.extract_pixels_host(roads, tiles, pairs, window="crop")
+    ids = np.arange(roads.n_roads) if road_ids is None else np.asarray(road_ids)
+    road_of_pair = pairs.road_of_pair()
+    frames = []
+    for p in range(pairs.n_pairs):
+        rows = values[pair_off[p]:pair_off[p + 1]]
+        if len(rows) == 0 and tiles.nodata is not None:
+            continue
+        frames.append(_frames_from_rows(rows, tiles.nodata, BANDS, str(p), {"road_id": ids[road_of_pair[p]]}))
+    if not frames:
+        return pd.DataFrame()
+    return pd.concat(frames, ignore_index=True)
+
+
+logger = format_logger(logger) if hasattr(logger, "remove") else logger

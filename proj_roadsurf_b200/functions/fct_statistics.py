@@ -1,0 +1,111 @@
+"""Mirror of the statistics helpers of scripts/functions/fct_statistics.py (:44-105).
+
+The reference groups a table of pixel rows with pandas; here the grouped column is folded into 256-bin
+histograms on the GPU (rs_group_hist_host) and the statistics come from the histogram kernel
+(rs_finalize_stats_host, ddof = 1 like pandas ``std``).  Rounding and column naming follow the reference.
+``road_stats_from_accumulators`` builds the same table straight from the fused kernel's per-road
+histograms, without ever materialising pixel rows (what bench.py times).
+The plotting / PCA helpers of the reference file are presentation code and are not part of this path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from .._native import STAT_COLS
+from ..engine import default_engine
+
+Z = 2       # "Coefficient of 1.96 rounded up" (fct_statistics.py:58, :98)
+_COL = {k: i for i, k in enumerate(STAT_COLS)}
+
+
+def _uint8_column(series: pd.Series, col: str) -> np.ndarray:
+    a = series.to_numpy()
+    if a.dtype == np.uint8:
+        return a
+    if np.issubdtype(a.dtype, np.integer) or np.issubdtype(a.dtype, np.floating):
+        if len(a) == 0 or (np.all(a == np.floor(a)) and a.min() >= 0 and a.max() <= 255):
+            return a.astype(np.uint8)
+    raise TypeError(f"column {col!r}: the GPU statistics path takes 8-bit pixel values (uint8 band columns)")
+
+
+def _stats_table(values: np.ndarray, codes: np.ndarray, n_groups: int, engine=None) -> np.ndarray:
+    eng = engine or default_engine()
+    hist = eng.group_hist_host(values, codes, n_groups)
+    return eng.finalize_stats_host(hist[:, None, :], None, nodata_mode="raw", ddof=1)[:, 0, :]
+
+
+def get_df_stats_groupby(dataframe, col, groups, suffix=''):
+    """min, max, median, mean, count, std (ddof 1) of ``col`` per group + margin = Z*std/sqrt(count);
+    mean, std, margin rounded to 2 decimals; columns suffixed -- fct_statistics.py:44-70."""
+    keys = dataframe[groups[0]] if len(groups) == 1 else pd.MultiIndex.from_frame(dataframe[groups])
+    codes, uniques = pd.factorize(keys, sort=True)
+    st = _stats_table(_uint8_column(dataframe[col], col), codes.astype(np.int32), len(uniques))
+    index = pd.Index(uniques, name=groups[0]) if len(groups) == 1 else pd.MultiIndex.from_tuples(list(uniques), names=groups)
+    src_dtype = dataframe[col].dtype
+    stats_df = pd.DataFrame({
+        'min': st[:, _COL['min']].astype(src_dtype), 'max': st[:, _COL['max']].astype(src_dtype),
+        'median': st[:, _COL['median']], 'mean': st[:, _COL['mean']], 'count': st[:, _COL['count']].astype(np.int64),
+        'std': st[:, _COL['std']],
+    }, index=index)
+    stats_df[f'margin{suffix}'] = Z * stats_df['std'] / (stats_df['count'] ** (1 / 2))
+    stats_df['mean'] = stats_df['mean'].round(2)
+    stats_df['std'] = stats_df['std'].round(2)
+    stats_df[f'margin{suffix}'] = stats_df[f'margin{suffix}'].round(2)
+    if suffix != '':
+        stats_df.rename(columns={k: f'{k}{suffix}' for k in ('min', 'max', 'median', 'mean', 'count', 'std')}, inplace=True)
+    return stats_df
+
+
+def get_df_stats_no_group(dataframe, col, results_dict=None, suffix='', to_df=False):
+    """Same statistics over the whole column, appended to a dict of lists -- fct_statistics.py:72-105."""
+    if results_dict is None:
+        results_dict = {f'min{suffix}': [], f'max{suffix}': [], f'mean{suffix}': [], f'median{suffix}': [],
+                        f'std{suffix}': [], f'count{suffix}': [], f'margin{suffix}': []}
+    values = _uint8_column(dataframe[col], col)
+    st = _stats_table(values, np.zeros(len(values), np.int32), 1)[0]
+    results_dict[f'min{suffix}'].append(int(st[_COL['min']]))
+    results_dict[f'max{suffix}'].append(int(st[_COL['max']]))
+    results_dict[f'mean{suffix}'].append(np.float64(st[_COL['mean']]).round(2))
+    results_dict[f'median{suffix}'].append(float(st[_COL['median']]))
+    results_dict[f'std{suffix}'].append(np.float64(st[_COL['std']]).round(2))
+    results_dict[f'count{suffix}'].append(int(st[_COL['count']]))
+    results_dict[f'margin{suffix}'].append(np.round(Z * results_dict[f'std{suffix}'][-1] / (results_dict[f'count{suffix}'][-1] ** (1 / 2)),
+                                                    decimals=3))
+    if to_df:
+        return pd.DataFrame(results_dict)
+    return results_dict
+
+
+# ------------------------------------------------------------------------------------------
+# batched forms on the fused kernel's accumulators
+# ------------------------------------------------------------------------------------------
+def road_stats_from_accumulators(stats: np.ndarray, road_ids: Sequence, BANDS: Sequence[int] = (1, 2, 3)) -> pd.DataFrame:
+    """statistical_analysis.py:235-246 from the statistics table of rs_zonal_stats / rs_finalize_stats
+    (shape (R, C, RS_NSTAT [+ percentiles])): one row per road that has pixels, columns
+    min_b, max_b, median_b, mean_b, std_b, margin_b per band, then ``count`` (= count of band 1)."""
+    stats = np.asarray(stats)
+    keep = stats[:, 0, _COL['count']] > 0
+    out = {'road_id': np.asarray(road_ids)[keep]}
+    for ci, b in enumerate(BANDS):
+        s = stats[keep, ci]
+        margin = Z * s[:, _COL['std']] / np.sqrt(s[:, _COL['count']])
+        out[f'min_{b}'] = s[:, _COL['min']].astype(np.uint8)
+        out[f'max_{b}'] = s[:, _COL['max']].astype(np.uint8)
+        out[f'median_{b}'] = s[:, _COL['median']]
+        out[f'mean_{b}'] = np.round(s[:, _COL['mean']], 2)
+        out[f'std_{b}'] = np.round(s[:, _COL['std']], 2)
+        out[f'margin_{b}'] = np.round(margin, 2)
+    out['count'] = stats[keep, 0, _COL['count']].astype(np.int64)
+    return pd.DataFrame(out)
+
+
+def filter_roads(roads_stats_df: pd.DataFrame, BANDS: Sequence[int], COUNT_THRESHOLD=10, MAX_MOE=12.5) -> pd.DataFrame:
+    """statistical_analysis.py:264-270: keep count > threshold and any margin below MAX_MOE."""
+    ok = np.zeros(len(roads_stats_df), bool)
+    for b in BANDS:
+        ok |= (roads_stats_df[f'margin_{b}'] < MAX_MOE).to_numpy()
+    keep = (roads_stats_df['count'] > COUNT_THRESHOLD).to_numpy() & ok
+    return roads_stats_df[keep].drop(columns=[f'margin_{b}' for b in BANDS] + ['count'])

@@ -291,3 +291,28 @@ def pairs_by_bbox(roads: RoadSet, tiles: TileBatch, chunk: int = 4096) -> PairLi
         rr.append(r + s)
         tt.append(t)
     return PairList.from_pairs(R, np.concatenate(rr), np.concatenate(tt))
+
+
+def rasterio_window(transform, bbox, width: int, height: int):
+    """rasterio.features.geometry_window (pad 0, not boundless) of a geometry's bounds on a north-up raster,
+    with affine's arithmetic order: (col_off, row_off, w, h), or None where rasterio raises WindowError
+    ("Input shapes do not overlap raster." from rasterio.mask.mask, fct_misc.py:77)."""
+    import math
+    sa, sb, sc, sd, se, sf = (float(v) for v in transform)
+    det = sa * se - sb * sd
+    if det == 0.0:
+        return None
+    idet = 1.0 / det
+    ra, rb, rd, re = se * idet, -sb * idet, -sd * idet, sa * idet
+    rc, rf = -sc * ra - sf * rb, -sc * rd - sf * re
+    xmin, ymin, xmax, ymax = (float(v) for v in bbox)
+    if not all(math.isfinite(v) for v in (xmin, ymin, xmax, ymax)):
+        return None
+    xs = [vx * ra + vy * rb + rc for vx in (xmin, xmax) for vy in (ymin, ymax)]
+    ys = [vx * rd + vy * re + rf for vx in (xmin, xmax) for vy in (ymin, ymax)]
+    c0, r0 = math.floor(min(xs)), math.floor(min(ys))
+    w, h = max(math.ceil(max(xs)) - c0, 0), max(math.ceil(max(ys)) - r0, 0)
+    if r0 >= height or r0 + h <= 0 or c0 >= width or c0 + w <= 0:
+        return None
+    cc0, rr0 = max(c0, 0), max(r0, 0)
+    return (cc0, rr0, min(c0 + w, width) - cc0, min(r0 + h, height) - rr0)

@@ -1,0 +1,123 @@
+"""Mirror of the vote helpers of scripts/road_segmentation/determine_class.py.
+
+Two forms of the per-road vote:
+  * ``determine_detected_class(predictions, roads, threshold)`` -- the reference's table form (:122-190):
+    rows of (OBJECTID, score, det_class_name, weighted_score, area_pred_in_label) are summed per road and
+    class on the GPU (rs_vote_table_host) and the class indices compared;
+  * ``raster_vote(...)`` / ``accumulate_class_planes(...)`` -- the raster form named by the north star: class
+    and score planes are counted inside each road polygon by the fused kernel (joint histogram of
+    (class, score) per road), then argmax of the pixel counts ('count') or of the mean scores ('score').
+The GEOS overlay of get_weighted_scores (:97-120) is replaced by the raster accumulation; the vector
+preprocessing helpers (quarries, clip_labels) are outside the path.
+"""
+from __future__ import annotations
+
+import sys
+from typing import Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+try:
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+    logger = logging.getLogger("roadsurf_b200")
+
+from ..engine import default_engine
+from ..geometry import PairList, RoadSet, TileBatch
+
+COVER_NAMES = np.array(["artificial", "natural", "undetermined", "undetected"], dtype=object)
+CLASS_CODE = {"artificial": 0, "natural": 1}
+
+
+def get_corresponding_class(row, labels_id):
+    """determine_class.py:19-28: detector class id 0 / 1 -> name of labels id 1 / 2."""
+    if row['det_class'] == 0:
+        return labels_id.loc[labels_id['id'] == 1, 'name'].item()
+    elif row['det_class'] == 1:
+        return labels_id.loc[labels_id['id'] == 2, 'name'].item()
+    else:
+        logger.error(f"Unexpected class: {row['det_class']}")
+        sys.exit(1)
+
+
+def determine_category(row):
+    """determine_class.py:30-39: BELAGSART 100 -> artificial, 200 -> natural."""
+    if row['BELAGSART'] == 100:
+        return 'artificial'
+    if row['BELAGSART'] == 200:
+        return 'natural'
+    else:
+        logger.error(f"Unexpected class: {row['BELAGSART']}")
+        sys.exit(1)
+
+
+def determine_detected_class(predictions, roads, threshold=0):
+    """Per road: detections with score >= threshold vote; index_k = sum(weighted_score) / sum(area_pred_in_label)
+    per class (0 if absent or the weighted sum is 0); artificial > natural -> 'artificial', < -> 'natural',
+    == -> 'undetermined', no valid detection -> 'undetected'.  Returns the reference's comparison table
+    (road_id, cover_type, nat_score, art_score, diff_score, OBJECTID, geometry [, CATEGORY, gt_type])."""
+    return determine_detected_class_sweep(predictions, roads, [threshold])[0]
+
+
+def determine_detected_class_sweep(predictions, roads, thresholds: Sequence[float]):
+    """All thresholds of the sweep (final_metrics.py:277-316) in one GPU call; one comparison table each."""
+    road_ids = pd.unique(roads['OBJECTID'])
+    R = len(road_ids)
+    code_of = pd.Series(np.arange(R), index=road_ids)
+    pred_code = predictions['OBJECTID'].map(code_of)
+    known = pred_code.notna().to_numpy()
+    p = predictions[known]
+    codes = pred_code[known].to_numpy().astype(np.int64)
+    order = np.argsort(codes, kind="stable")                      # group by road, keep the table order inside a road
+    codes = codes[order]
+    row_off = np.zeros(R + 1, np.int64)
+    np.add.at(row_off, codes + 1, 1)
+    row_off = np.cumsum(row_off)
+    cls = p['det_class_name'].map(CLASS_CODE).fillna(-1).to_numpy().astype(np.int8)[order]
+    score = p['score'].to_numpy(np.float64)[order]
+    weighted = p['weighted_score'].to_numpy(np.float64)[order]
+    area = p['area_pred_in_label'].to_numpy(np.float64)[order]
+    cover, scores = default_engine().vote_table_host(row_off, cls, score, weighted, area, np.asarray(thresholds, np.float64))
+
+    columns_to_keep = ['OBJECTID'] + (['geometry'] if 'geometry' in roads.columns else [])
+    if 'gt_type' in roads.columns:
+        columns_to_keep.extend(['CATEGORY', 'gt_type'])
+    out = []
+    for t in range(len(thresholds)):
+        detected = cover[t] != 3
+        final_type_df = pd.DataFrame({
+            'road_id': road_ids,
+            'cover_type': COVER_NAMES[cover[t]],
+            'nat_score': [round(float(v), 3) if d else 0 for v, d in zip(scores[t, :, 1], detected)],
+            'art_score': [round(float(v), 3) if d else 0 for v, d in zip(scores[t, :, 0], detected)],
+            'diff_score': scores[t, :, 2],
+        })
+        out.append(final_type_df.merge(roads[columns_to_keep], how='inner', left_on='road_id', right_on='OBJECTID'))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# raster form
+# ------------------------------------------------------------------------------------------
+def accumulate_class_planes(roads: RoadSet, tiles: TileBatch, pairs: PairList, engine=None) -> np.ndarray:
+    """Joint (class, score) histogram per road, uint32 (R, 3, 256): tiles hold two uint8 channels, the class
+    plane (0 none, 1 artificial, 2 natural) and the score plane (score * 255)."""
+    eng = engine or default_engine()
+    hist, _ = eng.zonal_hist_host(roads, tiles, pairs, hist_mode="class_score")
+    return hist
+
+
+def score_cutoffs(thresholds: Sequence[float]) -> np.ndarray:
+    """smallest uint8 score s with s / 255 >= threshold (256: none)"""
+    s = np.arange(256) / 255.0
+    return np.array([int(np.argmax(s >= t)) if (s >= t).any() else 256 for t in thresholds], np.int32)
+
+
+def raster_vote(joint_hist: np.ndarray, gt_class: Optional[np.ndarray], thresholds: Sequence[float], rule: str = "count",
+                min_area_frac: float = 0.0, engine=None):
+    """Vote, tags, confusion counts and metrics for every threshold in one launch (rs_vote_metrics_host).
+    Returns cover (T, R) int8 codes, scores (T, R, 3), confusion (T, 2, 4), metrics (T, 12)."""
+    eng = engine or default_engine()
+    return eng.vote_metrics_host(joint_hist, gt_class, score_cutoffs(thresholds), rule=rule, min_area_frac=min_area_frac)

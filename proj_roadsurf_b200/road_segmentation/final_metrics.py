@@ -1,0 +1,113 @@
+"""Mirror of the metric helpers of scripts/road_segmentation/final_metrics.py (:22-105, :277-316).
+
+``get_tag`` and ``get_metrics`` keep the reference's table interface; the counting and the P / R / F1
+arithmetic run on the GPU (rs_confusion_metrics_host).  ``threshold_sweep`` is the batched form of the
+20-threshold loop (:277-316) on raster accumulators.
+"""
+from __future__ import annotations
+
+import sys
+from typing import Sequence
+
+import numpy as np
+import pandas as pd
+
+try:
+    from loguru import logger
+except Exception:  # pragma: no cover
+    import logging
+    logger = logging.getLogger("roadsurf_b200")
+
+from .._native import METRIC_COLS
+from ..engine import default_engine
+from . import determine_class
+
+_M = {k: i for i, k in enumerate(METRIC_COLS)}
+COVER_CODE = {"artificial": 0, "natural": 1, "undetermined": 2, "undetected": 3}
+
+
+def get_tag(row):
+    'final_metrics.py:91-105: FN for undetermined / undetected, TP when the classes agree, else wrong class.'
+    det_class = row.cover_type
+    gt_class = row.CATEGORY
+    if det_class == 'undetermined' or det_class == 'undetected':
+        return 'FN'
+    elif det_class == gt_class:
+        return 'TP'
+    elif det_class != gt_class:
+        return 'wrong class'
+    else:
+        logger.error(f'Unexpected configuration: prediction class is {det_class} and ground truth class is {gt_class}.')
+        sys.exit(1)
+
+
+def tags_from_codes(cover: np.ndarray, gt: np.ndarray) -> np.ndarray:
+    """vectorised get_tag on cover / ground-truth codes"""
+    out = np.where(cover >= 2, 'FN', np.where(cover == gt, 'TP', 'wrong class'))
+    return out.astype(object)
+
+
+def get_metrics(comparison_df, CLASSES):
+    """Per-class TP / FP / FN / Pk / Rk / f1k / count and the global Pw, Rw, f1w, Pb, Rb, f1b
+    (balanced metrics divide by the literal 2 of final_metrics.py:78-79).  The reference reads the ``tag``
+    column; tags are a function of (cover_type, CATEGORY), which is what is counted here."""
+    if list(CLASSES) != ['artificial', 'natural']:
+        raise ValueError("the GPU metrics path is built for CLASSES == ['artificial', 'natural']")
+    cover = comparison_df['cover_type'].map(COVER_CODE).fillna(-1).to_numpy().astype(np.int8)
+    gt = comparison_df['CATEGORY'].map(determine_class.CLASS_CODE).fillna(-1).to_numpy().astype(np.int8)
+    if 'tag' in comparison_df.columns:              # honour a tag column that disagrees with get_tag (it never does)
+        expect = tags_from_codes(cover, gt)
+        if not np.array_equal(expect[(gt >= 0) & (cover >= 0)], comparison_df['tag'].to_numpy()[(gt >= 0) & (cover >= 0)]):
+            raise ValueError("tag column is not get_tag(cover_type, CATEGORY)")
+    conf, met = default_engine().confusion_metrics_host(cover[None, :], gt)
+    return metrics_frames(conf[0], met[0], CLASSES)
+
+
+def metrics_frames(conf: np.ndarray, met: np.ndarray, CLASSES=('artificial', 'natural')):
+    """(2, 4) confusion counts + 12 metrics -> the reference's two DataFrames."""
+    rows = {'cover_class': [], 'TP': [], 'FP': [], 'FN': [], 'Pk': [], 'Rk': [], 'f1k': [], 'count': []}
+    for k, name in enumerate(CLASSES):
+        tp = int(conf[k, k])
+        rows['cover_class'].append(name)
+        rows['TP'].append(tp)
+        rows['FP'].append(int(conf[1 - k, k]))
+        rows['FN'].append(int(conf[k, 2] + conf[k, 3] + conf[k, 1 - k]))
+        # the reference stores integer 0 when TP == 0, floats otherwise
+        rows['Pk'].append(0 if tp == 0 else float(met[_M[f'P{k}']]))
+        rows['Rk'].append(0 if tp == 0 else float(met[_M[f'R{k}']]))
+        rows['f1k'].append(0 if tp == 0 else float(met[_M[f'F{k}']]))
+        rows['count'].append(int(conf[k].sum()))
+    metrics_df = pd.DataFrame(rows)
+    pw, rw, pb, rb = (float(met[_M[k]]) for k in ('Pw', 'Rw', 'Pb', 'Rb'))
+    global_metrics_df = pd.DataFrame({'Pw': [pw], 'Rw': [rw], 'f1w': [0 if (pw == 0 and rw == 0) else float(met[_M['f1w']])],
+                                      'Pb': [pb], 'Rb': [rb], 'f1b': [0 if (pb == 0 and rb == 0) else float(met[_M['f1b']])]})
+    return metrics_df, global_metrics_df
+
+
+def best_threshold(f1b: Sequence[float], Pb: Sequence[float], thresholds: Sequence[float]):
+    """final_metrics.py:295-312: maximise f1b, a tie goes to the larger Pb, otherwise the earlier threshold;
+    the first threshold is reported as 0, later ones as round(threshold, 2)."""
+    best, max_f1, max_p = 0, f1b[0], Pb[0]
+    for i in range(1, len(thresholds)):
+        if f1b[i] > max_f1 or (f1b[i] == max_f1 and Pb[i] > max_p):
+            best, max_f1, max_p = i, f1b[i], Pb[i]
+    return best, (0 if best == 0 else round(float(thresholds[best]), 2))
+
+
+def threshold_sweep(joint_hist: np.ndarray, gt_class: np.ndarray, thresholds=None, rule: str = "count",
+                    min_area_frac: float = 0.0):
+    """The 20-threshold loop of final_metrics.py:277-316 on raster accumulators, one GPU launch.
+    Returns (all_metrics_by_class, all_global_metrics, best_index, best_threshold, cover)."""
+    thresholds = np.arange(0, 1., 0.05) if thresholds is None else np.asarray(thresholds, float)
+    cover, scores, conf, met = determine_class.raster_vote(joint_hist, gt_class, thresholds, rule, min_area_frac)
+    by_class, glob = [], []
+    for i, thr in enumerate(thresholds):
+        a, b = metrics_frames(conf[i], met[i])
+        a['threshold'] = thr
+        b['threshold'] = thr
+        by_class.append(a)
+        glob.append(b)
+    all_by_class = pd.concat(by_class, ignore_index=True)
+    all_global = pd.concat(glob, ignore_index=True)
+    bi, bt = best_threshold(all_global['f1b'].tolist(), all_global['Pb'].tolist(), thresholds)
+    return all_by_class, all_global, bi, bt, cover

@@ -1,0 +1,203 @@
+"""The reference-shaped helpers (proj_roadsurf_b200.functions / .road_segmentation) on the GPU against the golden
+fixtures produced by the reference's own code (tests/golden/) and against the CPU oracle.  -m gpu."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import cport, gdal_fill, raster as oraster, stats as ostats, vote as ovote
+from proj_roadsurf_b200 import synth
+from proj_roadsurf_b200.geometry import PairList, RoadSet, TileBatch
+from test_golden import assert_frame_matches, frame, load
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from proj_roadsurf_b200.functions import fct_misc, fct_rasters, fct_statistics
+    from proj_roadsurf_b200.road_segmentation import determine_class, final_metrics
+    return fct_misc, fct_statistics, fct_rasters, determine_class, final_metrics
+
+
+def test_get_pixel_values_golden(mods):
+    fct_misc = mods[0]
+    g = load("pixel_values")
+    data = np.array(g["data"], np.uint8)
+    acc = {None: pd.DataFrame(), 0: pd.DataFrame()}
+    for case in g["cases"]:
+        nodata = case["nodata"]
+        fct_misc.register_tile("18_1_1.tif", data, g["transform"], nodata)
+        if case["geom"] == "__accumulated__":
+            assert_frame_matches(case["result"], acc[nodata])
+            continue
+        geom = g["geoms"][case["geom"]]
+        one = fct_misc.get_pixel_values(geom, "18_1_1.tif", range(1, 4), pd.DataFrame(), road_id=case["geom"])
+        assert_frame_matches(case["result"], one)
+        acc[nodata] = fct_misc.get_pixel_values(geom, "18_1_1.tif", range(1, 4), acc[nodata], road_id=case["geom"])
+    # missing tile: error logged, empty frame (fct_misc.py:83-85)
+    assert len(fct_misc.get_pixel_values(g["geoms"]["rect"], "nope.tif", range(1, 4), pd.DataFrame(), road_id=1)) == 0
+    # shapes that miss the raster: rasterio.mask.mask raises ValueError
+    far = {"type": "Polygon", "coordinates": [[[0, 0], [1, 0], [1, 1], [0, 0]]]}
+    with pytest.raises(ValueError):
+        fct_misc.get_pixel_values(far, "18_1_1.tif", range(1, 4), pd.DataFrame())
+    fct_misc.clear_tiles()
+
+
+def test_get_pixel_values_batch_equals_the_reference_double_loop(mods):
+    fct_misc = mods[0]
+    g = synth.Grid(3, 3)
+    rr = synth.ribbon_roads(g, 8, seed=6)
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    for nodata in (None, 0):
+        tb = TileBatch.from_arrays(tiles, gt, nodata)
+        got = fct_misc.get_pixel_values_batch(rr.roads, tb, rr.pairs, range(1, 4), road_ids=np.arange(100, 108))
+        exp = pd.DataFrame()
+        road_of = rr.pairs.road_of_pair()
+        for p in range(rr.pairs.n_pairs):                      # statistical_analysis.py:180-193 with the oracle
+            t = int(rr.pairs.pair_tile[p])
+            tile = {"data": tiles[t], "transform": tuple(gt[t]), "nodata": nodata}
+            try:
+                exp = oraster.get_pixel_values(rr.roads.rings(int(road_of[p])), tile, range(1, 4), exp, road_id=100 + int(road_of[p]))
+            except ValueError:
+                pass
+        assert len(exp) > 1000
+        assert list(got.columns) == list(exp.columns)
+        for c in exp.columns:
+            assert np.array_equal(got[c].to_numpy().astype(np.int64), exp[c].to_numpy().astype(np.int64)), (nodata, c)
+
+
+def test_stats_helpers_golden(mods):
+    fs = mods[1]
+    g = load("stats_groupby")
+    px = frame(g["pixels"], {"band1": np.uint8, "band2": np.uint8})
+    for case in g["cases"]:
+        assert_frame_matches(case["result"], fs.get_df_stats_groupby(px, case["col"], ["road_id"], case["suffix"]))
+    g = load("stats_no_group")
+    px = frame(g["pixels"], {"band1": np.uint8, "band2": np.uint8})
+    d = None
+    for grp in g["groups"]:
+        d = fs.get_df_stats_no_group(px.loc[grp["rows"]], "band1", d, "_1")
+    from test_golden import same
+    for k, v in g["result"].items():
+        assert all(same(x, y) for x, y in zip(v, d[k])) and len(v) == len(d[k]), k
+    assert_frame_matches(g["as_df"], fs.get_df_stats_no_group(px, "band2", None, "", True))
+
+
+def test_vote_and_metrics_golden(mods):
+    determine_class, final_metrics = mods[3], mods[4]
+    g = load("vote")
+    roads = frame(g["roads"])
+    preds = frame(g["predictions"])
+    thresholds = [s["threshold"] for s in g["sweep"]]
+    sweep = determine_class.determine_detected_class_sweep(preds, roads, thresholds)
+    for step, comp in zip(g["sweep"], sweep):
+        comp["tag"] = comp.apply(lambda row: final_metrics.get_tag(row), axis=1)
+        gold = frame(step["comparison"])
+        assert comp["road_id"].tolist() == gold["road_id"].tolist()
+        assert comp["cover_type"].tolist() == gold["cover_type"].tolist()          # bit-exact classes
+        assert comp["tag"].tolist() == gold["tag"].tolist()
+        for col in ("nat_score", "art_score", "diff_score"):
+            np.testing.assert_allclose(comp[col].astype(float), gold[col].astype(float), rtol=1e-6, atol=1e-12)
+        by_class, glob = final_metrics.get_metrics(comp, ["artificial", "natural"])
+        assert_frame_matches(step["by_class"], by_class)
+        assert_frame_matches(step["global"], glob)
+    one = determine_class.determine_detected_class(preds, roads, thresholds[3])
+    assert one["cover_type"].tolist() == frame(g["sweep"][3]["comparison"])["cover_type"].tolist()
+
+
+def test_zonal_stats_like_rasterstats(mods):
+    fr = mods[2]
+    rng = np.random.default_rng(4)
+    raster = rng.integers(0, 256, (40, 50), dtype=np.uint8)
+    raster[rng.random((40, 50)) < 0.1] = 0
+    affine = (2.0, 0.0, 600000.0, 0.0, -2.0, 200000.0)
+
+    def poly(cx, cy, r, n):
+        a = np.linspace(0, 2 * np.pi, n, endpoint=False)
+        pts = np.stack([cx + r * np.cos(a), cy + r * np.sin(a)], 1)
+        return np.concatenate([pts, pts[:1]])
+    vectors = [[poly(600040, 199960, 25, 9)], [poly(600095, 199930, 30, 7)],          # the second one hangs off the raster
+               [poly(599990, 200010, 18, 5)], [poly(600300, 199960, 5, 4)],            # the last one misses it entirely
+               [poly(600050, 199950, 30, 12), poly(600050, 199950, 10, 6)]]           # with a hole
+    stats = ["min", "max", "mean", "median", "std", "count", "sum", "percentile_10", "percentile_90"]
+    for nodata in (None, 0):
+        got = fr.zonal_stats(vectors, raster, affine=affine, stats=stats, nodata=nodata)
+        exp = ostats.zonal_stats(vectors, raster, affine, stats=[s for s in stats if not s.startswith("percentile")], nodata=nodata,
+                                 percentiles=[10, 90])
+        assert len(got) == len(exp) == 5
+        for a, b in zip(got, exp):
+            assert a["count"] == b["count"]
+            for k in stats:
+                if b[k] is None:
+                    assert a[k] is None
+                elif k in ("min", "max", "median", "count", "sum"):
+                    assert a[k] == b[k], k
+                else:
+                    assert abs(a[k] - b[k]) <= 1e-6 * abs(b[k]), k
+        assert got[3]["count"] == 0 and got[0]["count"] > 100
+
+
+def test_rasterize_like_rasterio(mods):
+    fr = mods[2]
+    rng = np.random.default_rng(8)
+    shapes = []
+    for i in range(5):
+        a = np.sort(rng.uniform(0, 2 * np.pi, 7))
+        pts = np.stack([30 + 20 * rng.random() + 18 * np.cos(a), 25 + 10 * rng.random() + 15 * np.sin(a)], 1)
+        shapes.append({"type": "Polygon", "coordinates": [np.concatenate([pts, pts[:1]]).tolist()]})
+    got = fr.rasterize(shapes, (64, 80))
+    exp = np.zeros((64, 80), np.uint8)
+    for sh in shapes:
+        exp |= gdal_fill.rasterize(gdal_fill.rings_from_geojson(sh), (64, 80))
+    assert np.array_equal(got, exp) and exp.sum() > 500
+    valued = fr.rasterize([(shapes[0], 7), (shapes[1], 9)], (64, 80), fill=1)
+    m0 = gdal_fill.rasterize(gdal_fill.rings_from_geojson(shapes[0]), (64, 80)).astype(bool)
+    m1 = gdal_fill.rasterize(gdal_fill.rings_from_geojson(shapes[1]), (64, 80)).astype(bool)
+    exp2 = np.ones((64, 80), np.uint8); exp2[m0] = 7; exp2[m1] = 9
+    assert np.array_equal(valued, exp2)
+
+
+def test_road_stats_table_and_filter(mods):
+    fs = mods[1]
+    from proj_roadsurf_b200.engine import default_engine
+    g = synth.Grid(6, 6)
+    rr = synth.ribbon_roads(g, 30, seed=15)
+    tiles = synth.host_tiles(g, 3, "asphalt")
+    gt = g.transforms()
+    tb = TileBatch.from_arrays(tiles, gt)
+    stats, hist, nz = default_engine().zonal_stats_host(rr.roads, tb, rr.pairs, nodata_mode="none", ddof=1, want_hist=True)
+    oh, onz = cport.zonal_accumulate(rr.roads.xy, rr.roads.ring_off, rr.roads.road_ring_off, rr.pairs.road_pair_off,
+                                     rr.pairs.pair_tile, tiles, gt)
+    assert np.array_equal(hist.astype(np.uint64), oh)
+    ids = np.arange(30) + 1000
+    got = fs.road_stats_from_accumulators(stats, ids, (1, 2, 3))
+    exp = ostats.road_stats_table(oh, onz, ids, "N", (1, 2, 3))
+    assert list(got["road_id"]) == list(exp["road_id"]) and len(got) > 10
+    for c in exp.columns:
+        a, b = got[c].to_numpy().astype(float), exp[c].to_numpy().astype(float)
+        ok = (a == b) | (np.isnan(a) & np.isnan(b)) | (np.abs(a - b) <= 0.0100001)     # 2-decimal rounding ties
+        assert ok.all(), c
+        if c.startswith(("min", "max", "median")) or c == "count":
+            assert np.array_equal(a, b), c
+    f1 = fs.filter_roads(got, (1, 2, 3))
+    f2 = ostats.filter_roads(exp, (1, 2, 3))
+    assert list(f1["road_id"]) == list(f2["road_id"])
+
+
+def test_threshold_sweep_raster(mods):
+    determine_class, final_metrics = mods[3], mods[4]
+    g = synth.Grid(8, 8)
+    rr = synth.ribbon_roads(g, 80, seed=23)
+    tiles = synth.host_tiles(g, 2, "class_score")
+    tb = TileBatch.from_arrays(tiles, g.transforms())
+    jh = determine_class.accumulate_class_planes(rr.roads, tb, rr.pairs)
+    by_class, glob, bi, bt, cover = final_metrics.threshold_sweep(jh, rr.gt_class)
+    rows, obest = ovote.sweep(jh, rr.gt_class)
+    assert bi == obest and len(glob) == 20
+    for i, r in enumerate(rows):
+        assert abs(glob["f1b"][i] - r["f1b"]) <= 1e-6 and abs(glob["Pw"][i] - r["Pw"]) <= 1e-6
+        assert by_class["TP"][2 * i] == r["TP_0"] and by_class["FN"][2 * i + 1] == r["FN_1"]
