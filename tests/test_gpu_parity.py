@@ -392,3 +392,38 @@ def test_vote_metrics_sweep(eng, rule, min_area_frac):
             key = {"P0": "P_0", "R0": "R_0", "F0": "f1_0", "P1": "P_1", "R1": "R_1", "F1": "f1_1"}.get(name, name)
             np.testing.assert_allclose(met[i, j], om[key], rtol=RTOL, atol=1e-15)
     assert len(set(cover[0].tolist())) >= 2
+
+
+# ------------------------------------------------------------------------------------------
+# tile sharding: the ranks of a multi-GPU run, emulated one after the other on this GPU
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 4])
+def test_tile_sharded_accumulation_equals_single_shot(eng, world):
+    from proj_roadsurf_b200.distributed import global_rows, plan_shards
+    g = synth.Grid(8, 12)
+    rr = synth.ribbon_roads(g, 90, seed=61)
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    full_h, full_z = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs)
+    shards = plan_shards(rr.roads, rr.pairs, g.n_tiles, world)
+    nb = shards[0].n_boundary
+    assert nb > 0
+    boundary_h = np.zeros((nb, 3, 256), np.uint32)
+    boundary_z = np.zeros(nb, np.uint32)
+    outs = []
+    for sh in shards:
+        tb = TileBatch.from_arrays(tiles[sh.tile_lo:sh.tile_hi], gt[sh.tile_lo:sh.tile_hi])
+        h, z = eng.zonal_hist_host(sh.roads, tb, sh.pairs, road_slot=sh.slot, n_slots=sh.n_rows)
+        boundary_h += h[sh.n_own:]                         # what the all-reduce(SUM) of the boundary table does
+        boundary_z += z[sh.n_own:]
+        outs.append((h, z))
+    seen = np.zeros(90, int)
+    for sh, (h, z) in zip(shards, outs):
+        rows = global_rows(sh)
+        assert np.array_equal(h[:sh.n_own], full_h[rows[:sh.n_own]])
+        assert np.array_equal(z[:sh.n_own], full_z[rows[:sh.n_own]])
+        seen[rows[:sh.n_own]] += 1
+    assert np.array_equal(boundary_h, full_h[shards[0].boundary_global])
+    assert np.array_equal(boundary_z, full_z[shards[0].boundary_global])
+    seen[shards[0].boundary_global] += 1
+    assert np.array_equal(seen > 0, np.diff(rr.pairs.road_pair_off) > 0) and seen.max() == 1
