@@ -43,6 +43,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB_PATH]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("RS_NVCC_EXTRA", "").split()
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return LIB_PATH

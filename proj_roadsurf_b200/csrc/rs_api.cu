@@ -150,6 +150,7 @@ int rs_ctx_destroy(rs_ctx *ctx)
     for (auto &b : ctx->stage)
         if (b.p) cudaFree(b.p);
     if (ctx->items.p) cudaFree(ctx->items.p);
+    if (ctx->pgeom.p) cudaFree(ctx->pgeom.p);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_status_pinned) cudaFreeHost(ctx->h_status_pinned);

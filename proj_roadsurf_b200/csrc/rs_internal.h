@@ -29,6 +29,7 @@ struct rs_ctx {
     cudaStream_t host_stream = nullptr;   // stream of the _host entry points
     rs::DevBuf stage[16];                 // grow-only device staging of the _host entry points
     rs::DevBuf items;                     // grow-only work-item list of the zonal kernel
+    rs::DevBuf pgeom;                     // grow-only per-pair geometry records of the zonal kernel
 };
 
 namespace rs {

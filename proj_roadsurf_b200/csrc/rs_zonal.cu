@@ -95,6 +95,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // ---------------------------------------------------------------------------------------------
 // kernel arguments
 // ---------------------------------------------------------------------------------------------
+struct PairGeom;
+
 struct ZonalArgs {
     const double2 *xy;
     const int *ring_off;
@@ -103,6 +105,7 @@ struct ZonalArgs {
     const int *road_pair_off;
     const int *pair_tile;
     const int2 *items;        // (road, first pair)
+    const PairGeom *pgeom;    // per pair
     const int *n_items;       // device-resident item count
     const void *pixels;
     const double *gt;
@@ -120,11 +123,12 @@ struct ZonalArgs {
 };
 
 // per-pair geometry: integer window inside the tile + world->window-pixel transform
-struct PairGeom {
+struct alignas(16) PairGeom {       // 64 bytes, computed once per pair by pair_geom_kernel
+    double inv0, inv1, inv3, inv5;
     int col_off, row_off, w, h;     // window inside the tile (what is masked and read)
     int xshift, yshift, wu;         // RS_WINDOW_BOUNDLESS: the rasterized window starts xshift columns / yshift rows
                                     // before the visible one and is wu columns wide (0, 0, w otherwise)
-    double inv0, inv1, inv3, inv5;
+    int status;                     // 1: rasterize; 0: shapes do not overlap the raster; < 0: rs_status
 };
 
 // rasterio geometry_window + window_transform + GDALInvGeoTransform, from the road bbox
@@ -181,6 +185,24 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     g.inv0 = __ddiv_rn(-wc, wa); g.inv1 = __ddiv_rn(1.0, wa);
     g.inv3 = __ddiv_rn(-wf, we); g.inv5 = __ddiv_rn(1.0, we);
     return 1;
+}
+
+// thread per road: the geometry record of each of its pairs
+__global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ road_pair_off, const int *__restrict__ pair_tile,
+                                                        const double *__restrict__ road_bbox, const double *__restrict__ gt, int n_roads,
+                                                        int W, int H, int window_mode, PairGeom *__restrict__ out, int *status)
+{
+    const int road = blockIdx.x * blockDim.x + threadIdx.x;
+    if (road >= n_roads) return;
+    const double *bb = road_bbox + 4 * (size_t)road;
+    for (int p = road_pair_off[road]; p < road_pair_off[road + 1]; p++) {
+        PairGeom g;
+        g.inv0 = g.inv1 = g.inv3 = g.inv5 = 0.0;
+        g.col_off = g.row_off = g.w = g.h = g.xshift = g.yshift = g.wu = 0;
+        g.status = pair_geometry(gt + 6 * (size_t)pair_tile[p], bb, W, H, window_mode, g);
+        if (g.status < 0) atomicMin(status, g.status);
+        out[p] = g;
+    }
 }
 
 // Integer <-> binary64 without the conversion unit (F2I / I2F / FRND run on the quarter-rate XU pipe):
@@ -353,6 +375,11 @@ struct PxMask {
 template <int BPP, int NW>
 __device__ __forceinline__ void load_group(const uint8_t *p, uint32_t (&r)[NW])
 {
+#ifdef RS_EXP_NOLOAD      // experiment only: how much of the kernel time is pixel-load latency?
+#pragma unroll
+    for (int i = 0; i < NW; i++) r[i] = (uint32_t)(uintptr_t)p * 2654435761u + i;
+    return;
+#endif
     if constexpr ((BPP & 1) == 0) {
 #pragma unroll
         for (int i = 0; i < NW / 4; i++) {
@@ -384,6 +411,7 @@ __device__ __forceinline__ void group_pixels(const ZonalArgs &a, const uint32_t 
 struct EdgeParams {                 // the 32 edges of one block, written by their lanes, read by the crossing lanes
     double dx1[32], dy1[32], a[32], b[32], rb[32];
     int ya[32];
+    int n[32];
     int off[33];
 };
 template <int HC>
@@ -487,17 +515,19 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
     }
     __syncwarp();
 
-    const double *bb = a.road_bbox + 4 * (size_t)road;
 
     for (int p = pb; p < pe && nv > 0; p++) {
         const int t = a.pair_tile[p];
         PairGeom g;
-        const int gr = pair_geometry(a.gt + 6 * (size_t)t, bb, a.W, a.H, a.window_mode, g);
-        if (gr < 0) {
-            if (lane == 0) atomicMin(a.status, gr);
-            continue;
+        {
+            const int4 *gp = reinterpret_cast<const int4 *>(a.pgeom + p);        // same address in every lane: broadcast loads
+            const int4 q0 = __ldg(gp), q1 = __ldg(gp + 1), q2 = __ldg(gp + 2), q3 = __ldg(gp + 3);
+            g.inv0 = __hiloint2double(q0.y, q0.x); g.inv1 = __hiloint2double(q0.w, q0.z);
+            g.inv3 = __hiloint2double(q1.y, q1.x); g.inv5 = __hiloint2double(q1.w, q1.z);
+            g.col_off = q2.x; g.row_off = q2.y; g.w = q2.z; g.h = q2.w;
+            g.xshift = q3.x; g.yshift = q3.y; g.wu = q3.z; g.status = q3.w;
         }
-        if (gr == 0) continue;
+        if (g.status <= 0) continue;
         const int cbcol = g.col_off & ~31;                              // absolute column of mask bit 0
         const int pitch = ((g.col_off + g.w - 1) >> 5) - (cbcol >> 5) + 1;   // mask words per row
         const int pp = pitch | 1;                                       // odd row stride: lane-per-row walks are conflict-free
@@ -523,15 +553,66 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             // chunks whose bounds reach a row of this row chunk
             const unsigned rel = __ballot_sync(FULL, cy_lo <= cy_hi && cy_hi >= (float)r0 && cy_lo <= (float)(r0 + rc));
             if (rel == 0) continue;
-            {
-                const int nw4 = (rc * pp + 3) >> 2;
-                for (int i = lane; i < nw4; i += 32) reinterpret_cast<uint4 *>(s.mask)[i] = make_uint4(0, 0, 0, 0);
-                for (int i = lane; i < ((rc + 3) >> 2); i += 32) reinterpret_cast<uint4 *>(s.rowmap)[i] = make_uint4(0, 0, 0, 0);
-            }
-            __syncwarp();
+            // invariant: mask and rowmap are all zero here (zeroed at kernel start; the pixel phase clears what
+            // it consumes)
 
             // ---------------- edge passes: 0 = crossings (toggles), 1 = horizontal-edge burns ----------------
             bool any_hb = false;
+            int nact = 0;                                   // active edges waiting in s.u.e (warp-uniform)
+            // evaluate the crossings of the queued edges: a warp prefix sum flattens (edge, row) over the lanes
+            auto flush_edges = [&]() {
+                if (nact == 0) return;
+                __syncwarp();
+                const int n = lane < nact ? s.u.e.n[lane] : 0;
+                int incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                s.u.e.off[lane] = incl - n;
+                if (lane == 31) s.u.e.off[32] = total;
+                __syncwarp();
+                int j = -1;
+                for (int f = lane; f < total; f += 32) {
+                    if (j < 0) {            // edge of crossing f: binary search once, then walk forward
+                        j = 0;
+#pragma unroll
+                        for (int st = 16; st > 0; st >>= 1)
+                            if (s.u.e.off[j + st] <= f) j += st;
+                    } else {
+                        while (s.u.e.off[j + 1] <= f) j++;
+                    }
+                    const int y = s.u.e.ya[j] + (f - s.u.e.off[j]);
+                    const double dy = __dadd_rn(int2double_magic(y + g.yshift), 0.5);
+                    const double dx1 = s.u.e.dx1[j];
+                    // GDAL: intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1, then floor(intersect + 0.5).
+                    // The quotient is first taken through the edge's reciprocal; that differs from the
+                    // correctly rounded division by a few ulp, which can only change the floor when
+                    // intersect + 0.5 is within 1e-4 of an integer -- those crossings (and absurdly
+                    // large coordinates) take the exact division.
+                    const double num = __dmul_rn(__dsub_rn(dy, s.u.e.dy1[j]), s.u.e.a[j]);
+                    const double qf = __dmul_rn(num, s.u.e.rb[j]);
+                    double v = __dadd_rn(__dadd_rn(qf, dx1), 0.5);
+                    double t;
+                    int ti = rint_magic(fmin(fmax(v, -1.0e9), 1.0e9), t);
+                    if (!(fabs(qf) < 1.0e9) || !(fabs(v) < 1.0e9) || fabs(__dsub_rn(v, t)) < 1.0e-4) {
+                        v = __dadd_rn(__dadd_rn(__ddiv_rn(num, s.u.e.b[j]), dx1), 0.5);
+                        v = fmin(fmax(v, -1.0e9), 1.0e9);          // order-preserving: far outside either way
+                        ti = rint_magic(v, t);
+                    }
+                    const int fl = ti - (__dsub_rn(v, t) < 0.0 ? 1 : 0) - g.xshift;     // floor(intersect + 0.5), visible column
+                    // crossings at or beyond the right edge toggle nothing (xor / or with 0, no branch)
+                    const int bit = lo + max(fl, 0);
+                    const int word = min(bit >> 5, pitch - 1);
+                    const uint32_t onbit = fl < g.w ? 1u : 0u;
+                    atomicXor(&s.mask[(y - r0) * pp + word], onbit << (bit & 31));
+                    atomicOr(&s.rowmap[y - r0], onbit << min(word, 31));
+                }
+                __syncwarp();
+                nact = 0;
+            };
             for (int pass = 0; pass < 2; pass++) {
                 if (pass == 1 && !any_hb) break;
                 for (unsigned rm = rel; rm; rm &= rm - 1) {
@@ -579,66 +660,26 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                             continue;
                         }
                         any_hb |= __any_sync(FULL, hb);
-                        if (!__any_sync(FULL, n > 0)) continue;
-                        // flatten (edge, row) crossings over the lanes
-                        int incl = n;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int v = __shfl_up_sync(FULL, incl, o);
-                            if (lane >= o) incl += v;
-                        }
-                        const int total = __shfl_sync(FULL, incl, 31);
-                        {
+                        // active edges (n > 0) are compacted into the 32 parameter slots; the slots are flushed
+                        // (crossings evaluated) when the next block does not fit
+                        const unsigned act = __ballot_sync(FULL, n > 0);
+                        if (!act) continue;
+                        if (nact + __popc(act) > 32) flush_edges();
+                        if (n > 0) {
+                            const int slot = nact + __popc(act & ((1u << lane) - 1u));
                             double dx1, dy1, dx2, dy2;
                             if (y1 < y2) { dx1 = x1; dy1 = y1; dx2 = x2; dy2 = y2; }
                             else         { dx1 = x2; dy1 = y2; dx2 = x1; dy2 = y1; }
-                            s.u.e.dx1[lane] = dx1; s.u.e.dy1[lane] = dy1;
                             const double eb = __dsub_rn(dy2, dy1);
-                            s.u.e.a[lane] = __dsub_rn(dx2, dx1); s.u.e.b[lane] = eb;
-                            s.u.e.rb[lane] = n > 0 ? __ddiv_rn(1.0, eb) : 0.0;
-                            s.u.e.ya[lane] = ya; s.u.e.off[lane] = incl - n;
-                            if (lane == 31) s.u.e.off[32] = total;
+                            s.u.e.dx1[slot] = dx1; s.u.e.dy1[slot] = dy1;
+                            s.u.e.a[slot] = __dsub_rn(dx2, dx1); s.u.e.b[slot] = eb;
+                            s.u.e.rb[slot] = __ddiv_rn(1.0, eb);
+                            s.u.e.ya[slot] = ya; s.u.e.n[slot] = n;
                         }
-                        __syncwarp();
-                        int j = -1;
-                        for (int f = lane; f < total; f += 32) {
-                            if (j < 0) {            // edge of crossing f: binary search once, then walk forward
-                                j = 0;
-#pragma unroll
-                                for (int st = 16; st > 0; st >>= 1)
-                                    if (s.u.e.off[j + st] <= f) j += st;
-                            } else {
-                                while (s.u.e.off[j + 1] <= f) j++;
-                            }
-                            const int y = s.u.e.ya[j] + (f - s.u.e.off[j]);
-                            const double dy = __dadd_rn(int2double_magic(y + g.yshift), 0.5);
-                            const double dx1 = s.u.e.dx1[j];
-                            // GDAL: intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1, then floor(intersect + 0.5).
-                            // The quotient is first taken through the edge's reciprocal; that differs from the
-                            // correctly rounded division by a few ulp, which can only change the floor when
-                            // intersect + 0.5 is within 1e-4 of an integer -- those crossings (and absurdly
-                            // large coordinates) take the exact division.
-                            const double num = __dmul_rn(__dsub_rn(dy, s.u.e.dy1[j]), s.u.e.a[j]);
-                            const double qf = __dmul_rn(num, s.u.e.rb[j]);
-                            double v = __dadd_rn(__dadd_rn(qf, dx1), 0.5);
-                            double t;
-                            int ti = rint_magic(fmin(fmax(v, -1.0e9), 1.0e9), t);
-                            if (!(fabs(qf) < 1.0e9) || !(fabs(v) < 1.0e9) || fabs(__dsub_rn(v, t)) < 1.0e-4) {
-                                v = __dadd_rn(__dadd_rn(__ddiv_rn(num, s.u.e.b[j]), dx1), 0.5);
-                                v = fmin(fmax(v, -1.0e9), 1.0e9);          // order-preserving: far outside either way
-                                ti = rint_magic(v, t);
-                            }
-                            const int fl = ti - (__dsub_rn(v, t) < 0.0 ? 1 : 0) - g.xshift;     // floor(intersect + 0.5), visible column
-                            // crossings at or beyond the right edge toggle nothing (xor / or with 0, no branch)
-                            const int bit = lo + max(fl, 0);
-                            const int word = min(bit >> 5, pitch - 1);
-                            const uint32_t onbit = fl < g.w ? 1u : 0u;
-                            atomicXor(&s.mask[(y - r0) * pp + word], onbit << (bit & 31));
-                            atomicOr(&s.rowmap[y - r0], onbit << min(word, 31));
-                        }
-                        __syncwarp();
+                        nact += __popc(act);
                     }
                 }
+                if (pass == 0) flush_edges();
                 __syncwarp();
                 if (pass == 1) break;
 
@@ -741,27 +782,13 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                     const int v = __shfl_up_sync(FULL, incl, o);
                     if (lane >= o) incl += v;
                 }
-                // rows whose entries fit the queue form a prefix of the lanes (at least one: a row holds
-                // at most W / 8 <= ENTCAP - 32 groups)
+                // rows whose entries fit the queue form a prefix of the lanes (at least one once the queue holds
+                // less than a round: a row has at most W / 8 <= ENTCAP - 32 groups)
                 const int nrows = __popc(__ballot_sync(FULL, nq + incl <= ENTCAP));
-                const int added = __shfl_sync(FULL, incl, nrows - 1);
-                if (lane < nrows && cnt) {
-                    int off = nq + incl - cnt;
-                    const uint32_t *mrow = s.mask + row * pp;
-                    for (int k = klo; k < khi; k++) {
-                        const uint32_t m = mrow[k];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint32_t m8 = (m >> (8 * j)) & 255u;
-                            if (m8) s.u.entries[off++] = ((uint32_t)row << 20) | ((uint32_t)(k * 4 + j) << 8) | m8;
-                        }
-                    }
-                }
-                __syncwarp();
-                nq += added;
-                b0 += nrows;
-                const int nfull = nq & ~31;
-                if (nfull) {                                 // full rounds now, the partial round waits for more rows
+                if (nrows < min(32, rc - b0) && nq >= 32) {
+                    // the queue is full: drain the full rounds (their pixels were prefetched to L2 when they were
+                    // queued, several row batches ago), keep the partial round, retry these rows
+                    const int nfull = nq & ~31;
                     consume(nfull);
                     __syncwarp();
                     const int rest = nq - nfull;
@@ -771,7 +798,36 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                     if (lane < rest) s.u.entries[lane] = keep;
                     __syncwarp();
                     nq = rest;
+                    continue;
                 }
+                const int added = __shfl_sync(FULL, incl, nrows - 1);
+                if (lane < nrows && row < rc) s.rowmap[row] = 0;                 // consumed: restore the all-zero invariant
+                if (lane < nrows && cnt) {
+                    int off = nq + incl - cnt;
+                    uint32_t *mrow = s.mask + row * pp;
+                    [[maybe_unused]] const uint8_t *rowp =
+                        (const uint8_t *)a.pixels + (tile_pix + (size_t)(g.row_off + r0 + row) * a.W + cbcol) * PX::BPP;
+                    for (int k = klo; k < khi; k++) {
+                        const uint32_t m = mrow[k];
+                        mrow[k] = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t m8 = (m >> (8 * j)) & 255u;
+                            if (m8) {
+                                s.u.entries[off++] = ((uint32_t)row << 20) | ((uint32_t)(k * 4 + j) << 8) | m8;
+                                if constexpr (FAST && !PX::MASK) {      // start the DRAM fetch now, the loads come later
+                                    const uint8_t *gp = rowp + (size_t)(k * 4 + j) * 8 * PX::BPP;
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
+                                    if constexpr ((8 * PX::BPP) % 32 != 0)
+                                        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + 8 * PX::BPP - 1));
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                nq += added;
+                b0 += nrows;
             }
             if (nq) consume(nq);
             __syncwarp();
@@ -815,6 +871,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const Zo
     }
     S &s = reinterpret_cast<S *>(smem_raw)[warp];
     if (lane == 0) mbar_init(&s.mbar, 1);
+    for (int i = lane; i < MASKW / 4; i += 32) reinterpret_cast<uint4 *>(s.mask)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < RCMAX / 4; i += 32) reinterpret_cast<uint4 *>(s.rowmap)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     uint32_t mbar_phase = 0;
     const int n_items = *a.n_items;
@@ -949,6 +1007,7 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     const size_t cap = (size_t)pairs->n_pairs / PPI + (size_t)roads->n_roads + 1;
     int rc = ensure(ctx, ctx->items, cap * sizeof(int2));
     if (rc) return rc;
+    if ((rc = ensure(ctx, ctx->pgeom, (size_t)pairs->n_pairs * sizeof(PairGeom)))) return rc;
 
     ZonalArgs a{};
     a.xy = (const double2 *)roads->xy;
@@ -958,6 +1017,7 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     a.road_pair_off = pairs->road_pair_off;
     a.pair_tile = pairs->pair_tile;
     a.items = (const int2 *)ctx->items.p;
+    a.pgeom = (const PairGeom *)ctx->pgeom.p;
     a.work_counter = ctx->d_counters;
     a.n_items = ctx->d_counters + 1;
     a.pixels = tiles->pixels;
@@ -998,6 +1058,13 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
                                                                     (int2 *)ctx->items.p, ctx->d_counters + 1);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
+    if (pairs->n_pairs > 0) {
+        pair_geom_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
+                                                                       roads->n_roads, tiles->width, tiles->height, window_mode,
+                                                                       (PairGeom *)ctx->pgeom.p, ctx->d_status);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+    }
 
     if (masks) return launch_one<PxMask>(ctx, a, st);
     if (prm->hist_mode == RS_HIST_CLASS_SCORE) return launch_one<PxClassScore>(ctx, a, st);
