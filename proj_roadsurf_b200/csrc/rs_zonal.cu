@@ -44,7 +44,7 @@ namespace rs {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 4;        // teams per CTA
 constexpr int CTAS_PER_SM = 5;  // occupancy target (shared memory: ~10.6 KB per team)
-constexpr int PPI = 16;         // pairs per work item
+constexpr int PPI = 8;          // pairs per work item
 constexpr int VCAP = 96;        // vertices staged in shared memory per road (longer roads read L2)
 constexpr int MASKW = 896;      // mask words per team
 constexpr int RCMAX = 128;      // rows per mask chunk
@@ -786,8 +786,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                 // less than a round: a row has at most W / 8 <= ENTCAP - 32 groups)
                 const int nrows = __popc(__ballot_sync(FULL, nq + incl <= ENTCAP));
                 if (nrows < min(32, rc - b0) && nq >= 32) {
-                    // the queue is full: drain the full rounds (their pixels were prefetched to L2 when they were
-                    // queued, several row batches ago), keep the partial round, retry these rows
+                    // the queue is full: drain the full rounds, keep the partial round, retry these rows
                     const int nfull = nq & ~31;
                     consume(nfull);
                     __syncwarp();
@@ -805,23 +804,13 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                 if (lane < nrows && cnt) {
                     int off = nq + incl - cnt;
                     uint32_t *mrow = s.mask + row * pp;
-                    [[maybe_unused]] const uint8_t *rowp =
-                        (const uint8_t *)a.pixels + (tile_pix + (size_t)(g.row_off + r0 + row) * a.W + cbcol) * PX::BPP;
                     for (int k = klo; k < khi; k++) {
                         const uint32_t m = mrow[k];
                         mrow[k] = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const uint32_t m8 = (m >> (8 * j)) & 255u;
-                            if (m8) {
-                                s.u.entries[off++] = ((uint32_t)row << 20) | ((uint32_t)(k * 4 + j) << 8) | m8;
-                                if constexpr (FAST && !PX::MASK) {      // start the DRAM fetch now, the loads come later
-                                    const uint8_t *gp = rowp + (size_t)(k * 4 + j) * 8 * PX::BPP;
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gp));
-                                    if constexpr ((8 * PX::BPP) % 32 != 0)
-                                        asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + 8 * PX::BPP - 1));
-                                }
-                            }
+                            if (m8) s.u.entries[off++] = ((uint32_t)row << 20) | ((uint32_t)(k * 4 + j) << 8) | m8;
                         }
                     }
                 }
