@@ -238,6 +238,23 @@ int rs_confusion_metrics_host(rs_ctx *ctx, const int8_t *cover, const int8_t *gt
                               int64_t *confusion, double *metrics);
 
 /*
+ * GPU broad phase: the (road, tile) pair list of gpd.sjoin(tiles, roads) + drop_duplicates
+ * (scripts/statistical_analysis/statistical_analysis.py:170-171) for tiles on a regular lattice, as road-major CSR
+ * with each road's tiles sorted by index.  Predicate: closed bounding-box overlap of road_bbox[r] with
+ * tile_ext[t] (xmin, ymin, xmax, ymax) -- a superset of 'intersects'; the extra pairs contribute no pixel.
+ * Lattice cell (ix, iy) covers [x0 + ix*tile_w, +tile_w] x [y0 + iy*tile_h, +tile_h]; lut int32[ny][nx] gives the
+ * tile index of a cell or -1.  road_pair_off int32[n_roads+1] is always written and *n_pairs returned; pair_tile
+ * is written when it is non-NULL and capacity >= *n_pairs (call once with NULL to size it).
+ */
+typedef struct rs_lattice {
+    double x0, y0, tile_w, tile_h;
+    int32_t nx, ny;
+    const int32_t *lut;
+} rs_lattice;
+int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, const double *tile_ext, int32_t n_tiles,
+                       const rs_lattice *lattice, int32_t *road_pair_off, int32_t *pair_tile, int64_t capacity, int64_t *n_pairs);
+
+/*
  * Deterministic synthetic tiles (bench / tests only; the reference ships no imagery,
  * data/readme.md:20-21).  value = f(seed, tile_key[t], pixel, band), see DESIGN.md.
  * kind 0: iid uniform; 1: low-entropy "asphalt"; 2: class/score planes (channels == 2).

@@ -32,6 +32,7 @@ EXPORTS = (
     "rs_zonal_hist_host", "rs_zonal_stats_host", "rs_rasterize_pairs_dev", "rs_rasterize_pairs_host", "rs_finalize_stats_dev",
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
     "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
+    "rs_pairs_bbox_host",
 )
 
 
@@ -52,6 +53,11 @@ class RsPairs(C.Structure):
 class RsZonalParams(C.Structure):
     _fields_ = [("hist_mode", C.c_int32), ("window_mode", C.c_int32), ("rescale", C.c_int32), ("reserved", C.c_int32),
                 ("scale_k", C.c_double * 4), ("scale_off", C.c_double * 4), ("road_slot", C.c_void_p)]
+
+
+class RsLattice(C.Structure):
+    _fields_ = [("x0", C.c_double), ("y0", C.c_double), ("tile_w", C.c_double), ("tile_h", C.c_double),
+                ("nx", C.c_int32), ("ny", C.c_int32), ("lut", C.c_void_p)]
 
 
 class NativeError(RuntimeError):
@@ -109,6 +115,7 @@ def load():
     L.rs_group_hist_host.argtypes = [P, P, P, C.c_int64, C.c_int32, P]
     L.rs_vote_table_host.argtypes = [P, P, P, P, P, P, C.c_int32, P, C.c_int32, P, P]
     L.rs_confusion_metrics_host.argtypes = [P, P, P, C.c_int32, C.c_int32, P, P]
+    L.rs_pairs_bbox_host.argtypes = [P, P, C.c_int32, P, C.c_int32, C.POINTER(RsLattice), P, P, C.c_int64, C.POINTER(C.c_int64)]
     L.rs_synth_tiles_dev.argtypes = [P, P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_uint64, P]
     for name in EXPORTS:

@@ -463,6 +463,38 @@ int rs_confusion_metrics_host(rs_ctx *ctx, const int8_t *cover, const int8_t *gt
     return finish(ctx);
 }
 
+int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, const double *tile_ext, int32_t n_tiles,
+                       const rs_lattice *lattice, int32_t *road_pair_off, int32_t *pair_tile, int64_t capacity, int64_t *n_pairs)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_roads < 0 || n_tiles < 0 || !lattice || !road_pair_off || !n_pairs) return RS_ERR_INVALID_ARG;
+    if (lattice->nx < 1 || lattice->ny < 1 || !(lattice->tile_w > 0.0) || !(lattice->tile_h > 0.0) || !lattice->lut) return RS_ERR_INVALID_ARG;
+    if (n_roads > 0 && !road_bbox) return RS_ERR_INVALID_ARG;
+    if (n_tiles > 0 && !tile_ext) return RS_ERR_INVALID_ARG;
+    *n_pairs = 0;
+    const size_t R = (size_t)n_roads;
+    if ((rc = up(ctx, ctx->stage[0], road_bbox, sizeof(double) * 4 * R))) return rc;
+    if ((rc = up(ctx, ctx->stage[1], tile_ext, sizeof(double) * 4 * (size_t)n_tiles))) return rc;
+    if ((rc = up(ctx, ctx->stage[2], lattice->lut, sizeof(int32_t) * (size_t)lattice->nx * lattice->ny))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[3], sizeof(int32_t) * (R + 1)))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if ((rc = launch_pairs_bbox(ctx, (const double *)ctx->stage[0].p, n_roads, (const double *)ctx->stage[1].p, lattice,
+                                (const int *)ctx->stage[2].p, (int *)ctx->stage[3].p, nullptr, 0, 0, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(road_pair_off, ctx->stage[3].p, sizeof(int32_t) * (R + 1), cudaMemcpyDeviceToHost, st));
+    if ((rc = finish(ctx))) return rc;
+    const int64_t total = road_pair_off[n_roads];
+    *n_pairs = total;
+    if (!pair_tile || capacity < total || total == 0) return RS_OK;
+    if ((rc = ensure(ctx, ctx->stage[4], sizeof(int32_t) * (size_t)total))) return rc;
+    if ((rc = launch_pairs_bbox(ctx, (const double *)ctx->stage[0].p, n_roads, (const double *)ctx->stage[1].p, lattice,
+                                (const int *)ctx->stage[2].p, (int *)ctx->stage[3].p, (int *)ctx->stage[4].p, total, 1, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(pair_tile, ctx->stage[4].p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
 int rs_synth_tiles_dev(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int32_t n_tiles, int32_t height, int32_t width,
                        int32_t channels, int32_t dtype, int32_t kind, uint64_t seed, void *stream)
 {

@@ -66,6 +66,8 @@ int launch_vote_table(rs_ctx *ctx, const int *row_off, const int8_t *cls, const 
                       const double *area, int n_roads, const double *thr_dev, int n_thr, int8_t *cover, double *scores, cudaStream_t st);
 int launch_confusion(rs_ctx *ctx, const int8_t *cover, const int8_t *gt, int n_roads, int n_thr, int64_t *confusion, double *metrics,
                      cudaStream_t st);
+int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, const rs_lattice *lat, const int *lut_dev,
+                      int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);
 int launch_synth(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int n_tiles, int H, int W, int C, int dtype,
                  int kind, uint64_t seed, cudaStream_t st);
 

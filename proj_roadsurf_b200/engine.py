@@ -245,6 +245,30 @@ class Engine:
             N.check(st, "rs_extract_pixels_host", self._ctx)
         return pair_off, values
 
+    def pairs_bbox_host(self, roads: RoadSet, tiles: TileBatch) -> PairList:
+        """GPU broad phase (rs_pairs_bbox_host): every (road, tile) whose bounding boxes overlap, tiles on a
+        regular lattice -- the pair list gpd.sjoin(tiles, roads) gives, as a superset."""
+        from .geometry import lattice_of
+        lat = lattice_of(tiles)
+        if lat is None:
+            raise ValueError("tiles are not on a regular lattice: build the pair list with geometry.pairs_by_bbox")
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        ext = np.ascontiguousarray(tiles.extents(), np.float64)
+        lut = np.ascontiguousarray(lat.lut, np.int32)
+        ld = N.RsLattice(lat.x0, lat.y0, lat.tile_w, lat.tile_h, lat.nx, lat.ny, _np_ptr(lut))
+        R = roads.n_roads
+        off = np.zeros(R + 1, np.int32)
+        total = C.c_int64(0)
+        st = self.lib.rs_pairs_bbox_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), tiles.n_tiles, C.byref(ld), _np_ptr(off), None, 0,
+                                         C.byref(total))
+        N.check(st, "rs_pairs_bbox_host", self._ctx)
+        pt = np.zeros(int(total.value), np.int32)
+        if total.value:
+            st = self.lib.rs_pairs_bbox_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), tiles.n_tiles, C.byref(ld), _np_ptr(off),
+                                             _np_ptr(pt), int(total.value), C.byref(total))
+            N.check(st, "rs_pairs_bbox_host", self._ctx)
+        return PairList(off, pt)
+
     def group_hist_host(self, values: np.ndarray, group: np.ndarray, n_groups: int) -> np.ndarray:
         """(n_groups, 256) uint32 histograms of a uint8 column by group index (rs_group_hist_host)."""
         v = np.ascontiguousarray(values, np.uint8)

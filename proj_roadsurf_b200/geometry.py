@@ -234,6 +234,48 @@ class PairList:
         return np.repeat(np.arange(len(self.road_pair_off) - 1, dtype=np.int32), np.diff(self.road_pair_off))
 
 
+@dataclass
+class Lattice:
+    """Regular lattice a tile set sits on: cell (ix, iy) = [x0 + ix*tile_w, +tile_w] x [y0 + iy*tile_h, +tile_h],
+    lut[iy, ix] = tile index or -1."""
+    x0: float
+    y0: float
+    tile_w: float
+    tile_h: float
+    lut: np.ndarray
+
+    @property
+    def nx(self) -> int:
+        return int(self.lut.shape[1])
+
+    @property
+    def ny(self) -> int:
+        return int(self.lut.shape[0])
+
+
+def lattice_of(tiles: TileBatch, max_cells_factor: int = 4) -> Optional[Lattice]:
+    """The lattice of an XYZ-style tile set (equal, axis-aligned, snapped tiles), or None."""
+    T = tiles.n_tiles
+    if T == 0:
+        return None
+    ext = tiles.extents()
+    tw, th = ext[:, 2] - ext[:, 0], ext[:, 3] - ext[:, 1]
+    if not (np.allclose(tw, tw[0], rtol=1e-9, atol=0) and np.allclose(th, th[0], rtol=1e-9, atol=0)):
+        return None
+    X0, Y0 = float(ext[:, 0].min()), float(ext[:, 1].min())
+    ix = np.rint((ext[:, 0] - X0) / tw[0]).astype(np.int64)
+    iy = np.rint((ext[:, 1] - Y0) / th[0]).astype(np.int64)
+    if not (np.allclose(X0 + ix * tw[0], ext[:, 0], rtol=0, atol=1e-6 * tw[0]) and
+            np.allclose(Y0 + iy * th[0], ext[:, 1], rtol=0, atol=1e-6 * th[0])):
+        return None
+    nx, ny = int(ix.max()) + 1, int(iy.max()) + 1
+    if nx * ny > max(max_cells_factor * T, 1 << 22):
+        return None
+    lut = np.full((ny, nx), -1, np.int32)
+    lut[iy, ix] = np.arange(T, dtype=np.int32)
+    return Lattice(X0, Y0, float(tw[0]), float(th[0]), lut)
+
+
 def pairs_by_bbox(roads: RoadSet, tiles: TileBatch, chunk: int = 4096) -> PairList:
     """Host broad phase: every (road, tile) whose bounding boxes overlap (closed comparison).
 

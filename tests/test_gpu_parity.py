@@ -427,3 +427,33 @@ def test_tile_sharded_accumulation_equals_single_shot(eng, world):
     assert np.array_equal(boundary_z, full_z[shards[0].boundary_global])
     seen[shards[0].boundary_global] += 1
     assert np.array_equal(seen > 0, np.diff(rr.pairs.road_pair_off) > 0) and seen.max() == 1
+
+
+# ------------------------------------------------------------------------------------------
+# GPU broad phase
+# ------------------------------------------------------------------------------------------
+def test_pairs_bbox_gpu_equals_host_broad_phase(eng):
+    g = synth.Grid(24, 17)
+    rr = synth.ribbon_roads(g, 700, seed=71)
+    gt = g.transforms()
+    keep = np.ones(g.n_tiles, bool)
+    keep[::7] = False                                       # a lattice with missing tiles
+    tb = TileBatch(None, gt[keep], 256, 256, 3)
+    host = pairs_by_bbox(rr.roads, tb)
+    dev = eng.pairs_bbox_host(rr.roads, tb)
+    assert np.array_equal(dev.road_pair_off, host.road_pair_off)
+    assert np.array_equal(dev.pair_tile, host.pair_tile)
+    assert dev.n_pairs > 3000
+    # and it loses no pixel-carrying pair of the (tighter) generator list
+    full = TileBatch(None, gt, 256, 256, 3)
+    dev_full = eng.pairs_bbox_host(rr.roads, full)
+    have = set(zip(dev_full.road_of_pair().tolist(), dev_full.pair_tile.tolist()))
+    assert set(zip(rr.pairs.road_of_pair().tolist(), rr.pairs.pair_tile.tolist())) <= have
+    # results through either pair list are identical
+    tiles = synth.host_tiles(synth.Grid(6, 6), 3)
+    g2 = synth.Grid(6, 6)
+    rr2 = synth.ribbon_roads(g2, 40, seed=72)
+    tb2 = TileBatch.from_arrays(tiles, g2.transforms())
+    h1, z1 = eng.zonal_hist_host(rr2.roads, tb2, rr2.pairs)
+    h2, z2 = eng.zonal_hist_host(rr2.roads, tb2, eng.pairs_bbox_host(rr2.roads, tb2))
+    assert np.array_equal(h1, h2) and np.array_equal(z1, z2)
