@@ -457,3 +457,53 @@ def test_pairs_bbox_gpu_equals_host_broad_phase(eng):
     h1, z1 = eng.zonal_hist_host(rr2.roads, tb2, rr2.pairs)
     h2, z2 = eng.zonal_hist_host(rr2.roads, tb2, eng.pairs_bbox_host(rr2.roads, tb2))
     assert np.array_equal(h1, h2) and np.array_equal(z1, z2)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json's full single-GPU size: size-independent properties + oracle on a sample of roads
+# ------------------------------------------------------------------------------------------
+def test_full_size_properties(eng):
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    nx = ny = 512 if free > 70e9 else 128                    # 262 144 tiles (51.5 GB) when the GPU is free
+    g = synth.Grid(nx, ny)
+    R = nx * ny // 2
+    rr = synth.ribbon_roads(g, R)
+    gt = g.transforms()
+    dt = eng.synth_tiles_dev(g.keys(), 256, 256, 3, kind=0, gt=gt)
+    dr, dp = eng.upload_roads(rr.roads), eng.upload_pairs(rr.pairs)
+    dh, dz = eng.zonal_hist_dev(dr, dt, dp)
+    torch.cuda.synchronize()
+    h = dh.view(torch.int32)
+    # (1) every band histogram of a road sums to the same pixel count
+    cnt = h.sum(dim=2, dtype=torch.int64)
+    assert bool((cnt[:, 0] == cnt[:, 1]).all()) and bool((cnt[:, 0] == cnt[:, 2]).all())
+    total_px = int(cnt[:, 0].sum().item())
+    assert 0.03 < total_px / (g.n_tiles * 65536.0) < 0.15        # ribbons cover a few per cent of the pixels
+    assert int(dz.sum().item()) > 0 and bool((dz.to(torch.int64) <= cnt[:, 0]).all())
+    # (2) determinism: bit-identical accumulators run to run (scheduling differs, integers do not)
+    dh2, dz2 = eng.zonal_hist_dev(dr, dt, dp)
+    assert torch.equal(dh, dh2) and torch.equal(dz, dz2)
+    # (3) invariance to road order: reversing the roads reverses the rows
+    rev = np.arange(R)[::-1].copy()
+    roads_r, pairs_r = rr.roads.subset(rev), rr.pairs.take_roads(rev)
+    dh3, dz3 = eng.zonal_hist_dev(eng.upload_roads(roads_r), dt, eng.upload_pairs(pairs_r))
+    assert torch.equal(dh3.flip(0), dh) and torch.equal(dz3.flip(0), dz)
+    # (4) statistics consistent with the histograms: count, sum and min/max of band 0
+    st = eng.finalize_stats_dev(dh, dz, nodata_mode="raw", ddof=1)
+    vals = torch.arange(256, device=h.device, dtype=torch.int64)
+    s1 = (h[:, 0].to(torch.int64) * vals).sum(dim=1)
+    assert torch.equal(st[:, 0, 0].to(torch.int64), cnt[:, 0]) and torch.equal(st[:, 0, 3].to(torch.int64), s1)
+    # (5) the CPU oracle on a sample of roads (their tiles are copied back)
+    rng = np.random.default_rng(5)
+    sample = np.sort(rng.choice(R, 48, replace=False))
+    sub_pairs = rr.pairs.take_roads(sample)
+    tiles_needed, inv = np.unique(sub_pairs.pair_tile, return_inverse=True)
+    host_tiles = dt.pixels[torch.from_numpy(tiles_needed.astype(np.int64)).to(h.device)].cpu().numpy()
+    sub_roads = rr.roads.subset(sample)
+    oh, onz = cport.zonal_accumulate(sub_roads.xy, sub_roads.ring_off, sub_roads.road_ring_off, sub_pairs.road_pair_off,
+                                     inv.astype(np.int32), host_tiles, gt[tiles_needed], threads=4)
+    got = dh[torch.from_numpy(sample).to(h.device)].cpu().numpy().view(np.uint32)
+    assert np.array_equal(got.astype(np.uint64), oh)
+    assert np.array_equal(dz[torch.from_numpy(sample).to(h.device)].cpu().numpy().view(np.uint32).astype(np.uint64), onz)
+    assert oh.sum() > 100000
