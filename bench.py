@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--kind", default="uniform", choices=["uniform", "asphalt"])
     ap.add_argument("--e2e-rows", type=int, default=64, help="tile rows of the host-buffer (e2e) leg")
     ap.add_argument("--cpu-rows", type=int, default=32, help="tile rows of the CPU baseline sample")
+    ap.add_argument("--extras", action="store_true", help="also time the class/score (config 2) and uint16 rescale (config 3) kernels")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -316,6 +317,58 @@ def run_b200(args):
                          "one pass of the plain-C oracle, one thread per core",
                "gpu_matches_oracle_on_sample": ok}
 
+    # ---- optional: the other tile formats of BASELINE.json configs[1] / configs[2] on a 128 x 128 tile block ----
+    extras = None
+    if args.extras and world == 1:
+        from proj_roadsurf_b200.engine import scale_params
+        g2 = synth.Grid(128, 128)
+        rr2 = synth.ribbon_roads(g2, 8192)
+        dr2, dp2 = eng.upload_roads(rr2.roads), eng.upload_pairs(rr2.pairs)
+        gt2 = g2.transforms()
+        extras = {}
+        for name, ch, dtype, kind, kw, bpp in (("class_score_u8x2", 2, "u8", 2, {"hist_mode": "class_score"}, 2),
+                                               ("rescale_u16x4", 4, "u16", 0, {"rescale": scale_params([150.0] * 4, [9000.0] * 4) + (False,)}, 8),
+                                               ("bands_u8x3", 3, "u8", 0, {}, 3)):
+            t2 = eng.synth_tiles_dev(g2.keys(), H, W, ch, dtype=dtype, kind=kind, gt=gt2)
+            for _ in range(3):
+                out2 = eng.zonal_hist_dev(dr2, t2, dp2, check=False, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                eng.zonal_hist_dev(dr2, t2, dp2, out=out2, check=False, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            eng.sync_status()
+            ms2 = e0.elapsed_time(e1) / 10
+            gpx = g2.n_tiles * H * W / (ms2 * 1e-3) / 1e9
+            extras[name] = {"Gpixel/s": gpx, "kernel_ms": ms2, "bytes_per_pixel": bpp,
+                            "roofline_frac": gpx * bpp / peak, "tiles": g2.n_tiles}
+            del t2, out2
+
+    # ---- reference-shaped CPU variant: per-pair Python loop + DataFrame concat + groupby, 1 core ----
+    if cpu is not None:
+        from oracle import raster as oraster, stats as ostats
+        import pandas as pd
+        gA = synth.Grid(4, 4)
+        rrA = synth.ribbon_roads(gA, 8, seed=3)
+        tA = synth.host_tiles(gA, 3)
+        gtA = gA.transforms()
+        road_of = rrA.pairs.road_of_pair()
+        t0 = time.perf_counter()
+        pix = pd.DataFrame()
+        for pA in range(rrA.pairs.n_pairs):
+            tile = {"data": tA[rrA.pairs.pair_tile[pA]], "transform": tuple(gtA[rrA.pairs.pair_tile[pA]]), "nodata": None}
+            try:
+                pix = oraster.get_pixel_values(rrA.roads.rings(int(road_of[pA])), tile, range(1, 4), pix, road_id=int(road_of[pA]))
+            except ValueError:
+                pass
+        for b in (1, 2, 3):
+            ostats.get_df_stats_groupby(pix, f"band{b}", ["road_id"], f"_{b}")
+        t1 = time.perf_counter()
+        cpu["reference_shaped"] = {"value": gA.n_tiles * H * W / (t1 - t0) / 1e9, "unit": "Gpixel/s", "cores": 1,
+                                   "sample": f"4x4 tiles, 8 roads, {rrA.pairs.n_pairs} pairs: per-pair Python loop + DataFrame concat + "
+                                             "pandas groupby (statistical_analysis.py:180-246 shape), pure-Python oracle"}
+
     if rank == 0:
         line = {
             "metric": "Gpixel/s rasterize+per-road zonal stats", "value": value, "unit": "Gpixel/s", "n_gpus": world,
@@ -326,6 +379,8 @@ def run_b200(args):
                        "l2": f"inputs ({n_tiles * H * W * C / 1e9:.1f} GB per GPU) are larger than L2; no flush"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         }
+        if extras is not None:
+            line["extras"] = extras
         print(json.dumps(line))
     eng.close()
     if world > 1:
