@@ -182,6 +182,15 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    if world > 1:
+        # one block of host cores per rank (GPU i sits behind the socket that holds cores [i*n/N, (i+1)*n/N) on HGX
+        # boards): the pinned buffers of the e2e leg are then allocated on the NUMA node next to the GPU
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except Exception:  # noqa: BLE001
+            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -344,6 +353,24 @@ def run_b200(args):
             extras[name] = {"Gpixel/s": gpx, "kernel_ms": ms2, "bytes_per_pixel": bpp,
                             "roofline_frac": gpx * bpp / peak, "tiles": g2.n_tiles}
             del t2, out2
+        # the materialising 16 -> 8 bit pass (tif2cog.py:260-270): 8 B read + 4 B written per pixel, pure HBM streaming
+        n_t = 16384
+        t16 = eng.synth_tiles_dev(np.arange(n_t, dtype=np.int64), H, W, 4, dtype="u16", kind=0)
+        o8 = torch.empty((n_t, H, W, 4), dtype=torch.uint8, device=dev)
+        for f32 in (False, True):
+            for _ in range(3):
+                eng.rescale_u16_dev(t16.pixels, [150.0] * 4, [9000.0] * 4, bidx=[1, 2, 3, 0], f32=f32, out=o8)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                eng.rescale_u16_dev(t16.pixels, [150.0] * 4, [9000.0] * 4, bidx=[1, 2, 3, 0], f32=f32, out=o8)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / 10
+            gbs = n_t * H * W * 12 / (ms2 * 1e-3) / 1e9
+            extras["rescale_u16_to_u8_" + ("f32" if f32 else "f64")] = {"Gpixel/s": n_t * H * W / (ms2 * 1e-3) / 1e9, "kernel_ms": ms2,
+                                                                      "bytes_per_pixel": 12, "GB/s": gbs, "roofline_frac": gbs / peak}
+        del t16, o8
 
     # ---- reference-shaped CPU variant: per-pair Python loop + DataFrame concat + groupby, 1 core ----
     if cpu is not None:

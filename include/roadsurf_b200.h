@@ -255,6 +255,18 @@ int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, co
                        const rs_lattice *lattice, int32_t *road_pair_off, int32_t *pair_tile, int64_t capacity, int64_t *n_pairs);
 
 /*
+ * 16 -> 8 bit rescale as a materialising pass: gdal.Translate(outputType=GDT_Byte, scaleParams=[[smin, smax, 0, 255]...])
+ * (scripts/preprocessing/tif2cog.py:260-270) plus the band selection of the tile URL (config/config_stats.yaml:39).
+ * dst[px][c] = byte(clamp(src[px][bidx[c]] * k[c] + off[c], 0, 255) + 0.5); k / off / bidx (NULL = identity) are host
+ * arrays of c_out entries; f32 != 0 evaluates in float32 (GDAL's working precision is not pinned).
+ * (rs_zonal_hist with RS_U16 applies the same formula on the fly without materialising the 8-bit tiles.)
+ */
+int rs_rescale_u16_dev(rs_ctx *ctx, const uint16_t *src, int64_t n_pixels, int32_t c_in, int32_t c_out, const int32_t *bidx,
+                       const double *k, const double *off, int32_t f32, uint8_t *dst, void *stream);
+int rs_rescale_u16_host(rs_ctx *ctx, const uint16_t *src, int64_t n_pixels, int32_t c_in, int32_t c_out, const int32_t *bidx,
+                        const double *k, const double *off, int32_t f32, uint8_t *dst);
+
+/*
  * Deterministic synthetic tiles (bench / tests only; the reference ships no imagery,
  * data/readme.md:20-21).  value = f(seed, tile_key[t], pixel, band), see DESIGN.md.
  * kind 0: iid uniform; 1: low-entropy "asphalt"; 2: class/score planes (channels == 2).

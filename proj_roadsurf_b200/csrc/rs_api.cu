@@ -495,6 +495,32 @@ int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, co
     return finish(ctx);
 }
 
+int rs_rescale_u16_dev(rs_ctx *ctx, const uint16_t *src, int64_t n_pixels, int32_t c_in, int32_t c_out, const int32_t *bidx,
+                       const double *k, const double *off, int32_t f32, uint8_t *dst, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    return launch_rescale(ctx, src, n_pixels, c_in, c_out, bidx, k, off, f32, dst, (cudaStream_t)stream);
+}
+
+int rs_rescale_u16_host(rs_ctx *ctx, const uint16_t *src, int64_t n_pixels, int32_t c_in, int32_t c_out, const int32_t *bidx,
+                        const double *k, const double *off, int32_t f32, uint8_t *dst)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_pixels < 0 || c_in < 1 || c_in > 4 || c_out < 1 || c_out > 4) return RS_ERR_INVALID_ARG;
+    if (n_pixels == 0) return RS_OK;
+    if (!src || !dst) return RS_ERR_INVALID_ARG;
+    const size_t ib = sizeof(uint16_t) * (size_t)n_pixels * c_in, ob = (size_t)n_pixels * c_out;
+    if ((rc = up(ctx, ctx->stage[7], src, ib))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[9], ob))) return rc;
+    if ((rc = launch_rescale(ctx, (const uint16_t *)ctx->stage[7].p, n_pixels, c_in, c_out, bidx, k, off, f32, (uint8_t *)ctx->stage[9].p,
+                             ctx->host_stream)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(dst, ctx->stage[9].p, ob, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
 int rs_synth_tiles_dev(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int32_t n_tiles, int32_t height, int32_t width,
                        int32_t channels, int32_t dtype, int32_t kind, uint64_t seed, void *stream)
 {

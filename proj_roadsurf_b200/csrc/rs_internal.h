@@ -68,6 +68,8 @@ int launch_confusion(rs_ctx *ctx, const int8_t *cover, const int8_t *gt, int n_r
                      cudaStream_t st);
 int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, const rs_lattice *lat, const int *lut_dev,
                       int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);
+int launch_rescale(rs_ctx *ctx, const uint16_t *src, long long n_px, int c_in, int c_out, const int32_t *bidx_host, const double *k_host,
+                   const double *off_host, int f32, uint8_t *dst, cudaStream_t st);
 int launch_synth(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int n_tiles, int H, int W, int C, int dtype,
                  int kind, uint64_t seed, cudaStream_t st);
 

@@ -335,6 +335,104 @@ int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class,
 }
 
 // ---------------------------------------------------------------------------------------------
+// 16 -> 8 bit rescale as a materialising pass: gdal.Translate(outputType=GDT_Byte, scaleParams=...)
+// (scripts/preprocessing/tif2cog.py:260-270), with the band selection of the tile URL
+// (config/config_stats.yaml:39, bidx=2&bidx=3&bidx=4&bidx=1).  HBM-bound: 2*C_in bytes read + C_out written per pixel.
+// ---------------------------------------------------------------------------------------------
+struct RescaleArgs {
+    const uint16_t *src;
+    uint8_t *dst;
+    long long n_px;
+    int bidx[4];
+    double k[4], off[4];
+};
+
+// dst = (int)(clamp(src * k + off, 0, 255) + 0.5), every operation correctly rounded in the working precision.
+// The uint16 -> float conversion goes through the 2^23 / 2^52 magic constants (one add on the FP pipe) so that only
+// the final float -> int conversion uses the quarter-rate conversion pipe (measured: both conversions there make the
+// float32 kernel XU-bound at 75 % of the HBM roofline; replacing the float -> int one as well costs more FP64 adds
+// than it saves).
+template <bool F32>
+__device__ __forceinline__ uint32_t rescale_one(uint32_t v, double k, double off)
+{
+    if (F32) {
+        const float x = __fsub_rn(__int_as_float(0x4b000000 | (int)v), 8388608.0f);        // exact (float)v, v < 2^16
+        float f = __fadd_rn(__fmul_rn(x, (float)k), (float)off);
+        f = fminf(fmaxf(f, 0.0f), 255.0f);
+        return (uint32_t)(int)__fadd_rn(f, 0.5f);
+    }
+    const double x = __dsub_rn(__hiloint2double(0x43300000, (int)v), 4503599627370496.0); // exact (double)v
+    double f = __dadd_rn(__dmul_rn(x, k), off);
+    f = fmin(fmax(f, 0.0), 255.0);
+    return (uint32_t)(int)__dadd_rn(f, 0.5);
+}
+
+// C_IN == C_OUT == 4: a thread converts 4 pixels (2 x 128-bit loads, 1 x 128-bit store)
+template <bool F32>
+__global__ void __launch_bounds__(256) rescale4_kernel(const RescaleArgs a)
+{
+    const long long n4 = a.n_px >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(a.src) + 2 * i);
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(a.src) + 2 * i + 1);
+        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const uint32_t s4[4] = {w[2 * p] & 0xffffu, w[2 * p] >> 16, w[2 * p + 1] & 0xffffu, w[2 * p + 1] >> 16};
+            uint32_t r = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int b = a.bidx[c];
+                const uint32_t v = b == 0 ? s4[0] : (b == 1 ? s4[1] : (b == 2 ? s4[2] : s4[3]));
+                r |= rescale_one<F32>(v, a.k[c], a.off[c]) << (8 * c);
+            }
+            o[p] = r;
+        }
+        reinterpret_cast<uint4 *>(a.dst)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    // tail pixels
+    for (long long px = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; px < a.n_px; px += (long long)gridDim.x * blockDim.x)
+        for (int c = 0; c < 4; c++) a.dst[px * 4 + c] = (uint8_t)rescale_one<F32>(a.src[px * 4 + a.bidx[c]], a.k[c], a.off[c]);
+}
+
+// any 1 <= C_IN, C_OUT <= 4: a thread per pixel
+template <bool F32>
+__global__ void __launch_bounds__(256) rescale_generic_kernel(const RescaleArgs a, int c_in, int c_out)
+{
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < a.n_px; px += (long long)gridDim.x * blockDim.x)
+        for (int c = 0; c < c_out; c++) a.dst[px * c_out + c] = (uint8_t)rescale_one<F32>(a.src[px * c_in + a.bidx[c]], a.k[c], a.off[c]);
+}
+
+int launch_rescale(rs_ctx *ctx, const uint16_t *src, long long n_px, int c_in, int c_out, const int32_t *bidx_host, const double *k_host,
+                   const double *off_host, int f32, uint8_t *dst, cudaStream_t st)
+{
+    if (n_px < 0 || c_in < 1 || c_in > 4 || c_out < 1 || c_out > 4 || !k_host || !off_host) return RS_ERR_INVALID_ARG;
+    if (n_px == 0) return RS_OK;
+    if (!src || !dst) return RS_ERR_INVALID_ARG;
+    RescaleArgs a{};
+    a.src = src; a.dst = dst; a.n_px = n_px;
+    for (int c = 0; c < 4; c++) {
+        a.bidx[c] = c < c_out ? (bidx_host ? bidx_host[c] : c) : 0;
+        if (a.bidx[c] < 0 || a.bidx[c] >= c_in) return RS_ERR_INVALID_ARG;
+        a.k[c] = c < c_out ? k_host[c] : 1.0;
+        a.off[c] = c < c_out ? off_host[c] : 0.0;
+    }
+    const int grid = ctx->sm_count * 8;
+    const bool vec = c_in == 4 && c_out == 4 && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0;
+    if (vec) {
+        if (f32) rescale4_kernel<true><<<grid, 256, 0, st>>>(a);
+        else rescale4_kernel<false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (f32) rescale_generic_kernel<true><<<grid, 256, 0, st>>>(a, c_in, c_out);
+        else rescale_generic_kernel<false><<<grid, 256, 0, st>>>(a, c_in, c_out);
+    }
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // synthetic tiles: counter-based, any shard regenerates its own tiles from (seed, tile_key)
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ u64 mix64(u64 z)

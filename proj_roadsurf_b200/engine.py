@@ -269,6 +269,36 @@ class Engine:
             N.check(st, "rs_pairs_bbox_host", self._ctx)
         return PairList(off, pt)
 
+    def rescale_u16_host(self, src: np.ndarray, smin: Sequence[float], smax: Sequence[float], bidx: Optional[Sequence[int]] = None,
+                         f32: bool = False) -> np.ndarray:
+        """gdal.Translate -scale smin smax 0 255 -ot Byte per OUTPUT band (tif2cog.py:260-270): src (..., C_in) uint16 ->
+        (..., C_out) uint8, output band c read from source band bidx[c]."""
+        src = np.ascontiguousarray(src, np.uint16)
+        c_in = src.shape[-1]
+        k, off = scale_params(smin, smax, f32)
+        c_out = len(k)
+        bi = None if bidx is None else np.ascontiguousarray(bidx, np.int32)
+        out = np.zeros(src.shape[:-1] + (c_out,), np.uint8)
+        n = int(np.prod(src.shape[:-1]))
+        st = self.lib.rs_rescale_u16_host(self._ctx, _np_ptr(src), n, c_in, c_out, _np_ptr(bi), _np_ptr(k), _np_ptr(off), int(f32), _np_ptr(out))
+        N.check(st, "rs_rescale_u16_host", self._ctx)
+        return out
+
+    def rescale_u16_dev(self, src, smin, smax, bidx=None, f32: bool = False, out=None):
+        """device form: src int16-viewed uint16 CUDA tensor (..., C_in) -> uint8 CUDA tensor (..., C_out), asynchronous"""
+        torch = self._torch()
+        c_in = int(src.shape[-1])
+        k, off = scale_params(smin, smax, f32)
+        c_out = len(k)
+        bi = None if bidx is None else np.ascontiguousarray(bidx, np.int32)
+        if out is None:
+            out = torch.empty(tuple(src.shape[:-1]) + (c_out,), dtype=torch.uint8, device=src.device)
+        n = int(src.numel() // c_in)
+        st = self.lib.rs_rescale_u16_dev(self._ctx, src.data_ptr(), n, c_in, c_out, _np_ptr(bi), _np_ptr(k), _np_ptr(off), int(f32),
+                                         out.data_ptr(), self._stream())
+        N.check(st, "rs_rescale_u16_dev", self._ctx)
+        return out
+
     def group_hist_host(self, values: np.ndarray, group: np.ndarray, n_groups: int) -> np.ndarray:
         """(n_groups, 256) uint32 histograms of a uint8 column by group index (rs_group_hist_host)."""
         v = np.ascontiguousarray(values, np.uint8)

@@ -201,3 +201,55 @@ def test_threshold_sweep_raster(mods):
     for i, r in enumerate(rows):
         assert abs(glob["f1b"][i] - r["f1b"]) <= 1e-6 and abs(glob["Pw"][i] - r["Pw"]) <= 1e-6
         assert by_class["TP"][2 * i] == r["TP_0"] and by_class["FN"][2 * i + 1] == r["FN_1"]
+
+
+def test_workflows_match_the_reference_shaped_pipeline(mods):
+    """workflows.road_band_statistics == the reference pipeline (per-pair get_pixel_values -> groupby stats -> filter) run
+    with the oracle; workflows.road_surface_vote == the oracle sweep."""
+    from proj_roadsurf_b200 import workflows
+    g = synth.Grid(4, 4)
+    rr = synth.ribbon_roads(g, 14, seed=33)
+    tiles = synth.host_tiles(g, 3, "asphalt")
+    gt = g.transforms()
+    for nodata in (None, 0):
+        tb = TileBatch.from_arrays(tiles, gt, nodata)
+        table, filtered = workflows.road_band_statistics(rr.roads, tb, BANDS=(1, 2, 3))        # GPU broad phase inside
+        # reference shape with the oracle: statistical_analysis.py:180-246
+        bb = pairs_by_bbox_local(rr.roads, tb)
+        pix = pd.DataFrame()
+        road_of = bb.road_of_pair()
+        for p in range(bb.n_pairs):
+            t = int(bb.pair_tile[p])
+            try:
+                pix = oraster.get_pixel_values(rr.roads.rings(int(road_of[p])), {"data": tiles[t], "transform": tuple(gt[t]), "nodata": nodata},
+                                               range(1, 4), pix, road_id=int(road_of[p]))
+            except ValueError:
+                pass
+        exp = None
+        for b in (1, 2, 3):
+            sub = ostats.get_df_stats_groupby(pix, f"band{b}", ["road_id"], f"_{b}")
+            sub["road_id"] = sub.index
+            sub = sub.reset_index(drop=True)
+            exp = sub if exp is None else pd.merge(exp, sub, on="road_id")
+        exp["count"] = exp["count_1"]
+        assert table["road_id"].tolist() == exp["road_id"].tolist()
+        for c in ("count",) + tuple(f"{k}_{b}" for b in (1, 2, 3) for k in ("min", "max", "median")):
+            assert np.array_equal(table[c].to_numpy().astype(np.int64) if c != f"median_{c[-1]}" else table[c].to_numpy(),
+                                  exp[c].to_numpy().astype(np.int64) if c != f"median_{c[-1]}" else exp[c].to_numpy()), (nodata, c)
+        for b in (1, 2, 3):
+            for k in ("mean", "std", "margin"):
+                a, e = table[f"{k}_{b}"].to_numpy(float), exp[f"{k}_{b}"].to_numpy(float)
+                ok = (np.abs(a - e) <= 0.0100001) | (np.isnan(a) & np.isnan(e))
+                assert ok.all(), (nodata, k, b)
+        assert len(filtered) <= len(table)
+    cs = synth.host_tiles(g, 2, "class_score")
+    res = workflows.road_surface_vote(rr.roads, TileBatch.from_arrays(cs, gt), rr.gt_class)
+    rows, best = ovote.sweep(res["joint_hist"], rr.gt_class)
+    assert res["best_index"] == best
+    assert abs(res["global_metrics"]["f1b"][best] - rows[best]["f1b"]) <= 1e-6
+    assert set(res["comparison"]["tag"]) <= {"TP", "FN", "wrong class"}
+
+
+def pairs_by_bbox_local(roads, tb):
+    from proj_roadsurf_b200.geometry import pairs_by_bbox
+    return pairs_by_bbox(roads, tb)

@@ -507,3 +507,39 @@ def test_full_size_properties(eng):
     assert np.array_equal(got.astype(np.uint64), oh)
     assert np.array_equal(dz[torch.from_numpy(sample).to(h.device)].cpu().numpy().view(np.uint32).astype(np.uint64), onz)
     assert oh.sum() > 100000
+
+
+# ------------------------------------------------------------------------------------------
+# 16 -> 8 bit rescale as a materialising pass (tif2cog.py:260-270) + band selection (config_stats.yaml:39)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("f32", [False, True])
+def test_rescale_u16_matches_gdal_translate_restatement(eng, f32):
+    import torch
+    rng = np.random.default_rng(12)
+    src = np.clip(rng.lognormal(7.5, 0.9, (3, 70, 65, 4)), 0, 65535).astype(np.uint16)      # NIR, R, G, B
+    src[0, :3, :3] = [0, 65535, 150, 9000]
+    nir, rgb = (150.0, 9000.0), (300.0, 6000.0)
+    # output bands R, G, B, NIR = source bands 1, 2, 3, 0 (bidx=2,3,4,1), each with its own range
+    bidx = [1, 2, 3, 0]
+    smin, smax = [rgb[0]] * 3 + [nir[0]], [rgb[1]] * 3 + [nir[1]]
+    got = eng.rescale_u16_host(src, smin, smax, bidx=bidx, f32=f32)
+    exp = oraster.rescale_u16_to_u8(src[..., bidx], smin, smax, f32)
+    assert got.shape == (3, 70, 65, 4) and np.array_equal(got, exp)
+    assert len(np.unique(got)) > 200
+    # device form, identity band order, and a 3-band output (generic kernel)
+    d = torch.from_numpy(src.view(np.int16)).cuda()
+    out = eng.rescale_u16_dev(d, [nir[0]] + [rgb[0]] * 3, [nir[1]] + [rgb[1]] * 3, f32=f32)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), oraster.rescale_u16_to_u8(src, [nir[0]] + [rgb[0]] * 3, [nir[1]] + [rgb[1]] * 3, f32))
+    got3 = eng.rescale_u16_host(src, smin[:3], smax[:3], bidx=[1, 2, 3], f32=f32)
+    assert np.array_equal(got3, exp[..., :3])
+    # rescale then 8-bit statistics == fused RS_U16 statistics
+    g = synth.Grid(2, 2)
+    rr = synth.ribbon_roads(g, 6, seed=2)
+    t16 = synth.host_tiles(g, 4, dtype=np.uint16)
+    from proj_roadsurf_b200.engine import scale_params
+    k, off = scale_params([nir[0]] + [rgb[0]] * 3, [nir[1]] + [rgb[1]] * 3, f32)
+    h_fused, _ = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(t16, g.transforms()), rr.pairs, rescale=(k, off, f32))
+    t8 = eng.rescale_u16_host(t16, [nir[0]] + [rgb[0]] * 3, [nir[1]] + [rgb[1]] * 3, f32=f32)
+    h_two, _ = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(t8, g.transforms()), rr.pairs)
+    assert np.array_equal(h_fused, h_two)
