@@ -543,3 +543,68 @@ def test_rescale_u16_matches_gdal_translate_restatement(eng, f32):
     t8 = eng.rescale_u16_host(t16, [nir[0]] + [rgb[0]] * 3, [nir[1]] + [rgb[1]] * 3, f32=f32)
     h_two, _ = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(t8, g.transforms()), rr.pairs)
     assert np.array_equal(h_fused, h_two)
+
+
+# ------------------------------------------------------------------------------------------
+# degenerate geometry, extreme shapes, size limits
+# ------------------------------------------------------------------------------------------
+def test_degenerate_and_self_intersecting_geometry(eng):
+    H, W = 33, 45                                    # odd sizes: the generic (unaligned) pixel path
+    shapes = [
+        [ring((3, 3), (20, 3))[:2]],                                  # 2 vertices: no area
+        [np.array([[5.0, 5.0]])],                                     # a single vertex
+        [ring((2, 2), (30, 2), (30, 2), (30, 20), (2, 20), (2, 20))], # repeated vertices
+        [ring((2, 2), (40, 30), (40, 2), (2, 30))],                   # bow-tie (self-intersecting): even-odd
+        [ring((1, 1), (10, 1), (20, 1), (20, 10), (20, 25), (1, 25))],            # collinear vertices
+        [ring((0.5, 0.5), (44.5, 0.5), (44.5, 32.5), (0.5, 32.5))],  # edges through pixel centres on the raster border
+        [ring((-1e7, -1e7), (1e7, -1e7), (1e7, 1e7), (-1e7, 1e7))],  # enormous
+        [ring((10, 10), (10.2, 10), (10.2, 30), (10, 30))],          # sliver
+        [ring((5, 5), (25, 5), (25, 25), (5, 25)), ring((5, 5), (25, 5), (25, 25), (5, 25))],   # identical rings cancel
+        [ring(*[(22 + 18 * np.cos(a), 16 + 14 * np.sin(a)) for a in np.linspace(0, 4 * np.pi, 41)[:-1]])],   # winds twice
+    ]
+    roads = RoadSet.from_geometries(shapes)
+    n = roads.n_roads
+    pairs = PairList.from_pairs(n, np.arange(n), np.zeros(n, int))
+    gt = np.array([[1.0, 0, 0, 0, 1.0, 0]])
+    for window in ("full", "crop"):
+        masks = eng.rasterize_pairs_host(roads, gt, H, W, pairs, window=window)
+        for i, rings in enumerate(shapes):
+            exp = cport.rasterize(rings, (H, W)) if window == "full" else cport.pair_mask_full(gt[0], rings, W, H)
+            assert np.array_equal(masks[i], exp), (window, i)
+    rng = np.random.default_rng(3)
+    tiles = rng.integers(0, 256, (1, H, W, 3), dtype=np.uint8)
+    h, z = eng.zonal_hist_host(roads, TileBatch.from_arrays(tiles, gt), pairs)
+    oh, oz = oracle_hist(roads, pairs, tiles, gt)
+    assert np.array_equal(h.astype(np.uint64), oh) and np.array_equal(z.astype(np.uint64), oz)
+
+
+def test_nan_coordinates_do_not_fault(eng):
+    bad = ring((2, 2), (float("nan"), 5), (20, 20), (2, 20))
+    roads = RoadSet.from_geometries([[bad], [ring((1, 1), (9, 1), (9, 9), (1, 9))]])
+    pairs = PairList.from_pairs(2, [0, 1], [0, 0])
+    tiles = np.full((1, 16, 16, 3), 7, np.uint8)
+    h, _ = eng.zonal_hist_host(roads, TileBatch.from_arrays(tiles, np.array([[1.0, 0, 0, 0, 1.0, 0]])), pairs)
+    assert h[1, 0, 7] == 64                          # the valid road is unaffected; the NaN road may hold anything finite
+    assert h[0].sum() <= 3 * 256
+
+
+def test_width_limits(eng):
+    from proj_roadsurf_b200._native import NativeError
+    roads = RoadSet.from_geometries([[ring((100, 1), (1900, 1), (1900, 3), (100, 3))]])
+    pairs = PairList.from_pairs(1, [0], [0])
+    wide = np.zeros((1, 4, 2048, 3), np.uint8)
+    wide[0, :, :, 1] = (np.arange(2048) % 251).astype(np.uint8)[None, :]
+    gt = np.array([[1.0, 0, 0, 0, 1.0, 0]])
+    h, _ = eng.zonal_hist_host(roads, TileBatch.from_arrays(wide, gt), pairs)          # the widest supported tile
+    oh, _ = oracle_hist(roads, pairs, wide, gt)
+    assert np.array_equal(h.astype(np.uint64), oh) and oh[0, 0].sum() == 2 * 1800
+    too_wide = np.zeros((1, 2, 2056, 3), np.uint8)
+    with pytest.raises(NativeError) as ei:
+        eng.zonal_hist_host(roads, TileBatch.from_arrays(too_wide, gt), pairs)
+    assert ei.value.status == -6                     # RS_ERR_UNSUPPORTED, never a silent wrong answer
+    tall = np.zeros((1, 5000, 8, 1), np.uint8)       # tall rasters are fine
+    tall[0, :, :, 0] = (np.arange(5000) % 200).astype(np.uint8)[:, None]
+    r2 = RoadSet.from_geometries([[ring((1, 10), (7, 10), (7, 4990), (1, 4990))]])
+    h2, _ = eng.zonal_hist_host(r2, TileBatch.from_arrays(tall, gt), pairs)
+    oh2, _ = oracle_hist(r2, pairs, tall, gt)
+    assert np.array_equal(h2.astype(np.uint64), oh2) and oh2.sum() == 6 * 4980
