@@ -187,22 +187,25 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     return 1;
 }
 
-// thread per road: the geometry record of each of its pairs
+// thread per pair: its geometry record (the road of pair p is found by bisection of the CSR offsets)
 __global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ road_pair_off, const int *__restrict__ pair_tile,
                                                         const double *__restrict__ road_bbox, const double *__restrict__ gt, int n_roads,
-                                                        int W, int H, int window_mode, PairGeom *__restrict__ out, int *status)
+                                                        int n_pairs, int W, int H, int window_mode, PairGeom *__restrict__ out, int *status)
 {
-    const int road = blockIdx.x * blockDim.x + threadIdx.x;
-    if (road >= n_roads) return;
-    const double *bb = road_bbox + 4 * (size_t)road;
-    for (int p = road_pair_off[road]; p < road_pair_off[road + 1]; p++) {
-        PairGeom g;
-        g.inv0 = g.inv1 = g.inv3 = g.inv5 = 0.0;
-        g.col_off = g.row_off = g.w = g.h = g.xshift = g.yshift = g.wu = 0;
-        g.status = pair_geometry(gt + 6 * (size_t)pair_tile[p], bb, W, H, window_mode, g);
-        if (g.status < 0) atomicMin(status, g.status);
-        out[p] = g;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    int lo = 0, hi = n_roads;                    // largest road with road_pair_off[road] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(road_pair_off + mid) <= p) lo = mid;
+        else hi = mid;
     }
+    PairGeom g;
+    g.inv0 = g.inv1 = g.inv3 = g.inv5 = 0.0;
+    g.col_off = g.row_off = g.w = g.h = g.xshift = g.yshift = g.wu = 0;
+    g.status = pair_geometry(gt + 6 * (size_t)pair_tile[p], road_bbox + 4 * (size_t)lo, W, H, window_mode, g);
+    if (g.status < 0) atomicMin(status, g.status);
+    out[p] = g;
 }
 
 // Integer <-> binary64 without the conversion unit (F2I / I2F / FRND run on the quarter-rate XU pipe):
@@ -1048,9 +1051,9 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
     if (pairs->n_pairs > 0) {
-        pair_geom_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
-                                                                       roads->n_roads, tiles->width, tiles->height, window_mode,
-                                                                       (PairGeom *)ctx->pgeom.p, ctx->d_status);
+        pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
+                                                                       roads->n_roads, pairs->n_pairs, tiles->width, tiles->height,
+                                                                       window_mode, (PairGeom *)ctx->pgeom.p, ctx->d_status);
         ctx->launches++;
         RS_CUDA_OK(ctx, cudaGetLastError());
     }
