@@ -353,6 +353,27 @@ def run_b200(args):
             extras[name] = {"Gpixel/s": gpx, "kernel_ms": ms2, "bytes_per_pixel": bpp,
                             "roofline_frac": gpx * bpp / peak, "tiles": g2.n_tiles}
             del t2, out2
+        # BASELINE configs[4]: 1024 px tiles, wide polygons with holes and 1 k - 10 k vertices (long edge lists)
+        g5 = synth.Grid(32, 32, size=1024)
+        wp = synth.wide_polygons(g5, 384)
+        t5 = eng.synth_tiles_dev(g5.keys(), 1024, 1024, 3, kind=0, gt=g5.transforms())
+        d5r, d5p = eng.upload_roads(wp.roads), eng.upload_pairs(wp.pairs)
+        for _ in range(2):
+            o5 = eng.zonal_hist_dev(d5r, t5, d5p, check=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            eng.zonal_hist_dev(d5r, t5, d5p, out=o5, check=False)
+        e1.record()
+        torch.cuda.synchronize()
+        eng.sync_status()
+        ms5 = e0.elapsed_time(e1) / 5
+        cov5 = float(o5[0][:, 0].sum().item()) / (g5.n_tiles * 1024.0 * 1024.0)
+        gpx5 = g5.n_tiles * 1024 * 1024 / (ms5 * 1e-3) / 1e9
+        extras["wide_polygons_1024px"] = {"Gpixel/s": gpx5, "kernel_ms": ms5, "bytes_per_pixel": 3, "roofline_frac": gpx5 * 3 / peak,
+                                          "tiles": g5.n_tiles, "polygons": 384, "pairs": wp.pairs.n_pairs, "covered_fraction": cov5,
+                                          "mean_vertices": float(np.diff(wp.roads.ring_off[wp.roads.road_ring_off]).mean())}
+        del t5, o5
         # the materialising 16 -> 8 bit pass (tif2cog.py:260-270): 8 B read + 4 B written per pixel, pure HBM streaming
         n_t = 16384
         t16 = eng.synth_tiles_dev(np.arange(n_t, dtype=np.int64), H, W, 4, dtype="u16", kind=0)

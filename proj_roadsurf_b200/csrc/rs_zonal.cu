@@ -44,7 +44,9 @@ namespace rs {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 4;        // teams per CTA
 constexpr int CTAS_PER_SM = 5;  // occupancy target (shared memory: ~10.6 KB per team)
-constexpr int PPI = 8;          // pairs per work item
+constexpr int PPI = 8;          // pairs per work item, at most
+constexpr int AREA_MAX = 6 * 65536;   // window pixels per work item (a pair above it gets an item of its own)
+constexpr int ROWS_ITEM = 256;  // a window taller than this is split by rows over several items
 constexpr int VCAP = 96;        // vertices staged in shared memory per road (longer roads read L2)
 constexpr int MASKW = 896;      // mask words per team
 constexpr int RCMAX = 128;      // rows per mask chunk
@@ -52,6 +54,7 @@ constexpr int ENTCAP = 448;     // 8-pixel group entries queued per team
 constexpr int NCHUNK = 32;      // culling chunks per road
 constexpr int RINGCAP = 16;     // ring starts kept in shared memory
 constexpr int MAX_WIDTH = 2048; // one row's groups (W / 8) must fit the queue next to a partial round
+constexpr int ITEM_SPLIT = 1 << 30;           // item flag: the road has several items (accumulate with atomics)
 constexpr uint32_t ROW_REWALK = 0xffffffffu;   // rowmap marker: recount this row over [0, pitch)
 
 // ---------------------------------------------------------------------------------------------
@@ -104,7 +107,7 @@ struct ZonalArgs {
     const double *road_bbox;
     const int *road_pair_off;
     const int *pair_tile;
-    const int2 *items;        // (road, first pair)
+    const int4 *items;        // (road, first pair, pairs | ITEM_SPLIT, first row or -1)
     const PairGeom *pgeom;    // per pair
     const int *n_items;       // device-resident item count
     const void *pixels;
@@ -444,13 +447,12 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t m) { return (((m & 0x
 // one work item
 // ---------------------------------------------------------------------------------------------
 template <class PX, bool FAST>
-__device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC> &s, const int road, const int pb,
-                                             const int lane, uint32_t &mbar_phase)
+__device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC> &s, const int4 item, const int lane,
+                                             uint32_t &mbar_phase)
 {
     const uint32_t hist_addr = smem_u32(s.hist), one = a.one;
-    const int rp0 = a.road_pair_off[road], rp1 = a.road_pair_off[road + 1];
-    const int pe = min(pb + PPI, rp1);
-    const bool split = (rp1 - rp0) > PPI;
+    const int road = item.x, pb = item.y, pe = item.y + (item.z & ~ITEM_SPLIT), row_first = item.w;
+    const bool split = (item.z & ITEM_SPLIT) != 0;
     const int g0 = a.road_ring_off[road], g1 = a.road_ring_off[road + 1];
     const int v0 = a.ring_off[g0], nv = a.ring_off[g1] - v0;
     const int nrings = g1 - g0;
@@ -550,9 +552,12 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             }
         }
 
-        const int rcbal = (g.h + (g.h + rcmax - 1) / rcmax - 1) / ((g.h + rcmax - 1) / rcmax);   // balanced row chunks
-        for (int r0 = 0; r0 < g.h; r0 += rcbal) {
-            const int rc = min(rcbal, g.h - r0);
+        // rows of this item: the whole window, or ROWS_ITEM rows of a tall one
+        const int rbeg = row_first < 0 ? 0 : row_first, rend = row_first < 0 ? g.h : min(g.h, row_first + ROWS_ITEM);
+        const int nrow = rend - rbeg, nchunk_r = (nrow + rcmax - 1) / rcmax;
+        const int rcbal = nchunk_r > 0 ? (nrow + nchunk_r - 1) / nchunk_r : 1;                   // balanced row chunks
+        for (int r0 = rbeg; r0 < rend; r0 += rcbal) {
+            const int rc = min(rcbal, rend - r0);
             // chunks whose bounds reach a row of this row chunk
             const unsigned rel = __ballot_sync(FULL, cy_lo <= cy_hi && cy_hi >= (float)r0 && cy_lo <= (float)(r0 + rc));
             if (rel == 0) continue;
@@ -873,23 +878,61 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const Zo
         if (lane == 0) idx = atomicAdd(a.work_counter, 1);
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= n_items) break;
-        const int2 it = a.items[idx];
-        process_item<PX, FAST>(a, s, it.x, it.y, lane, mbar_phase);
+        process_item<PX, FAST>(a, s, __ldg(a.items + idx), lane, mbar_phase);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// item list: thread per road; rows of roads with no item or several items are zeroed here
+// item list: thread per road.  An item is up to PPI consecutive pairs of the road whose windows sum to at most AREA_MAX
+// pixels; a window taller than ROWS_ITEM rows becomes ceil(h / ROWS_ITEM) single-pair items.  Rows of roads with no item
+// or several items are zeroed here (their teams accumulate with atomics).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__ road_pair_off, int n_roads,
-                                                         const int *__restrict__ road_slot, uint32_t *hist, uint32_t *nzero,
-                                                         int hc, int2 *items, int *n_items)
+template <bool WRITE>
+__device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, int road, int p0, int p1, int4 *items, int base, int flag,
+                                          bool tall)
+{
+    if (!tall) {            // no window can exceed ROWS_ITEM rows (tile height <= ROWS_ITEM): groups of PPI pairs, no geometry reads
+        const int ni = (p1 - p0 + PPI - 1) / PPI;
+        if (WRITE)
+            for (int k = 0; k < ni; k++) items[base + k] = make_int4(road, p0 + k * PPI, min(PPI, p1 - p0 - k * PPI) | flag, -1);
+        return ni;
+    }
+    int ni = 0, gp = p0, gn = 0, garea = 0;
+    auto close = [&]() {
+        if (gn > 0) {
+            if (WRITE) items[base + ni] = make_int4(road, gp, gn | flag, -1);
+            ni++;
+        }
+        gn = 0; garea = 0;
+    };
+    for (int p = p0; p < p1; p++) {
+        const int st = pgeom[p].status, h = st > 0 ? pgeom[p].h : 0, area = st > 0 ? pgeom[p].w * h : 0;
+        if (h > ROWS_ITEM) {
+            close();
+            for (int r = 0; r < h; r += ROWS_ITEM) {
+                if (WRITE) items[base + ni] = make_int4(road, p, 1 | flag, r);
+                ni++;
+            }
+            gp = p + 1;
+            continue;
+        }
+        if (gn == PPI || (gn > 0 && garea + area > AREA_MAX)) close();
+        if (gn == 0) gp = p;
+        gn++; garea += area;
+    }
+    close();
+    return ni;
+}
+
+__global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__ road_pair_off, const PairGeom *__restrict__ pgeom,
+                                                         int n_roads, const int *__restrict__ road_slot, uint32_t *hist, uint32_t *nzero,
+                                                         int hc, int4 *items, int *n_items, int tall)
 {
     const int road = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    int p0 = 0, ni = 0;
+    int p0 = 0, p1 = 0, ni = 0;
     if (road < n_roads) {
-        p0 = road_pair_off[road];
-        ni = (road_pair_off[road + 1] - p0 + PPI - 1) / PPI;
+        p0 = road_pair_off[road]; p1 = road_pair_off[road + 1];
+        ni = road_items<false>(pgeom, road, p0, p1, nullptr, 0, 0, tall != 0);
     }
     int incl = ni;
 #pragma unroll
@@ -901,7 +944,7 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__
     int base = 0;
     if (lane == 31 && total > 0) base = atomicAdd(n_items, total);
     base = __shfl_sync(FULL, base, 31) + incl - ni;
-    for (int k = 0; k < ni; k++) items[base + k] = make_int2(road, p0 + k * PPI);
+    if (ni > 0) road_items<true>(pgeom, road, p0, p1, items, base, ni > 1 ? ITEM_SPLIT : 0, tall != 0);
     if (hist) {
         unsigned m = __ballot_sync(FULL, road < n_roads && ni != 1);
         for (; m; m &= m - 1) {
@@ -995,9 +1038,9 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     if (tiles->width > MAX_WIDTH || tiles->width < 1 || tiles->height < 1) return RS_ERR_UNSUPPORTED;
     if (window_mode != RS_WINDOW_CROP && window_mode != RS_WINDOW_FULL && window_mode != RS_WINDOW_BOUNDLESS) return RS_ERR_INVALID_ARG;
 
-    // item list scratch: at most one item per PPI pairs plus one partial item per road
-    const size_t cap = (size_t)pairs->n_pairs / PPI + (size_t)roads->n_roads + 1;
-    int rc = ensure(ctx, ctx->items, cap * sizeof(int2));
+    // item list scratch: every pair can close one group and a tall window adds ceil(H / ROWS_ITEM) row items
+    const size_t cap = (size_t)pairs->n_pairs * (1 + (size_t)(tiles->height + ROWS_ITEM - 1) / ROWS_ITEM) + (size_t)roads->n_roads + 1;
+    int rc = ensure(ctx, ctx->items, cap * sizeof(int4));
     if (rc) return rc;
     if ((rc = ensure(ctx, ctx->pgeom, (size_t)pairs->n_pairs * sizeof(PairGeom)))) return rc;
 
@@ -1008,7 +1051,7 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     a.road_bbox = roads->road_bbox;
     a.road_pair_off = pairs->road_pair_off;
     a.pair_tile = pairs->pair_tile;
-    a.items = (const int2 *)ctx->items.p;
+    a.items = (const int4 *)ctx->items.p;
     a.pgeom = (const PairGeom *)ctx->pgeom.p;
     a.work_counter = ctx->d_counters;
     a.n_items = ctx->d_counters + 1;
@@ -1045,11 +1088,6 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     }
 
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(int), st));
-    prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, roads->n_roads, a.road_slot,
-                                                                    masks ? nullptr : hist, n_allzero, HC,
-                                                                    (int2 *)ctx->items.p, ctx->d_counters + 1);
-    ctx->launches++;
-    RS_CUDA_OK(ctx, cudaGetLastError());
     if (pairs->n_pairs > 0) {
         pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
                                                                        roads->n_roads, pairs->n_pairs, tiles->width, tiles->height,
@@ -1057,6 +1095,11 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
         ctx->launches++;
         RS_CUDA_OK(ctx, cudaGetLastError());
     }
+    prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
+                                                                    a.road_slot, masks ? nullptr : hist, n_allzero, HC,
+                                                                    (int4 *)ctx->items.p, ctx->d_counters + 1, tiles->height > ROWS_ITEM);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
 
     if (masks) return launch_one<PxMask>(ctx, a, st);
     if (prm->hist_mode == RS_HIST_CLASS_SCORE) return launch_one<PxClassScore>(ctx, a, st);

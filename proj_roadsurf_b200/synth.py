@@ -113,7 +113,9 @@ class RibbonRoads:
 
 
 def ribbon_roads(grid: Grid, n_roads: int, seed: int = SEED, hole_frac: float = 0.10, multi_frac: float = 0.05,
-                 max_vertices: int = 1042, width_scale: float = 1.0, order: str = "rowband") -> RibbonRoads:
+                 max_vertices: int = 1042, width_scale: float = 1.0, order: str = "rowband",
+                 n_vertices: Optional[Tuple[int, int]] = None, step: Tuple[float, float] = (20.0, 60.0),
+                 jitter_deg: float = 15.0, max_holes: int = 3, width_range: Optional[Tuple[float, float]] = None) -> RibbonRoads:
     """n_roads ribbon polygons scattered over `grid`, with their (road, tile) pair list.
 
     order: 'rowband' sorts roads by (tile row of the first vertex, x) so that a row-band shard of the
@@ -125,7 +127,10 @@ def ribbon_roads(grid: Grid, n_roads: int, seed: int = SEED, hole_frac: float = 
     X0, Y1 = grid.origin
     ext_w, ext_h = grid.nx * span, grid.ny * span
 
-    n = np.clip(np.rint(rng.lognormal(np.log(11.0), 1.065, R)), 2, max_vertices).astype(np.int64)
+    if n_vertices is None:
+        n = np.clip(np.rint(rng.lognormal(np.log(11.0), 1.065, R)), 2, max_vertices).astype(np.int64)
+    else:                                                         # config 5: long edge lists, log-uniform vertex counts
+        n = np.rint(np.exp(rng.uniform(np.log(n_vertices[0]), np.log(n_vertices[1]), R))).astype(np.int64)
     start = np.stack([X0 + rng.random(R) * ext_w, Y1 - rng.random(R) * ext_h], 1)
     sx = np.floor((start[:, 0] - X0) / span).astype(np.int64)
     sy = np.floor((Y1 - start[:, 1]) / span).astype(np.int64)
@@ -142,13 +147,15 @@ def ribbon_roads(grid: Grid, n_roads: int, seed: int = SEED, hole_frac: float = 
     is_first[first] = True
 
     width = rng.choice(ROAD_WIDTHS_M, R, p=ROAD_WIDTH_P / ROAD_WIDTH_P.sum()) * width_scale
+    if width_range is not None:
+        width = width_range[0] + (width_range[1] - width_range[0]) * rng.random(R)
     hw = width / (2.0 * COS_LAT)                              # half width in EPSG:3857 units
 
-    dhead = rng.normal(0.0, np.deg2rad(15.0), V)
+    dhead = rng.normal(0.0, np.deg2rad(jitter_deg), V)
     dhead[first] = rng.random(R) * 2.0 * np.pi
     head = _seg_cumsum(dhead, first, n)                       # heading of the segment ARRIVING at each vertex
-    step = 20.0 + 40.0 * rng.random(V)
-    dxy = np.stack([np.cos(head), np.sin(head)], 1) * step[:, None]
+    step_len = step[0] + (step[1] - step[0]) * rng.random(V)
+    dxy = np.stack([np.cos(head), np.sin(head)], 1) * step_len[:, None]
     dxy[first] = 0.0
     pos = _seg_cumsum(dxy, first, n) + np.repeat(start, n, axis=0)
 
@@ -177,7 +184,7 @@ def ribbon_roads(grid: Grid, n_roads: int, seed: int = SEED, hole_frac: float = 
     xy[ring_first + 2 * n] = left[first]
 
     # ---- holes and second parts: extra rings appended per road ----
-    n_holes = np.where(rng.random(R) < hole_frac, rng.integers(1, 4, R), 0)
+    n_holes = np.where(rng.random(R) < hole_frac, rng.integers(1, max_holes + 1, R), 0)
     is_multi = rng.random(R) < multi_frac
     extra_rings = n_holes + is_multi
     rings_per_road = 1 + extra_rings
@@ -283,3 +290,11 @@ def host_tiles(grid: Grid, channels: int = 3, kind: str = "uniform", seed: int =
     holes = rng.random((T, S, S)) < 0.01
     px[holes] = 0
     return px
+
+
+def wide_polygons(grid: Grid, n_polys: int, seed: int = SEED) -> RibbonRoads:
+    """BASELINE.json configs[4]: wide multi-lane polygons with holes and long edge lists for 1024 px tiles --
+    15-45 m wide (100-300 px at 0.15 m pixels), 1 k-10 k ring vertices (centreline vertices every 1-3 m),
+    1-8 rectangular holes each."""
+    return ribbon_roads(grid, n_polys, seed=seed, hole_frac=1.0, multi_frac=0.0, n_vertices=(500, 5000), step=(1.0, 3.0),
+                        jitter_deg=1.0, max_holes=8, width_range=(15.0, 45.0))

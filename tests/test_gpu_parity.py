@@ -608,3 +608,17 @@ def test_width_limits(eng):
     h2, _ = eng.zonal_hist_host(r2, TileBatch.from_arrays(tall, gt), pairs)
     oh2, _ = oracle_hist(r2, pairs, tall, gt)
     assert np.array_equal(h2.astype(np.uint64), oh2) and oh2.sum() == 6 * 4980
+
+
+def test_wide_polygons_config5(eng):
+    """BASELINE configs[4]: 1024 px tiles, wide polygons with up to ~10 k vertices and 1-8 holes"""
+    g = synth.Grid(4, 4, size=1024)
+    wp = synth.wide_polygons(g, 10, seed=9)
+    nv = np.diff(wp.roads.ring_off[wp.roads.road_ring_off])
+    assert nv.max() > 3000 and wp.roads.n_rings > wp.roads.n_roads
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    h, z = eng.zonal_hist_host(wp.roads, TileBatch.from_arrays(tiles, gt), wp.pairs)
+    oh, oz = oracle_hist(wp.roads, wp.pairs, tiles, gt, threads=4)
+    assert oh[:, 0].sum() > 2_000_000
+    assert np.array_equal(h.astype(np.uint64), oh) and np.array_equal(z.astype(np.uint64), oz)
