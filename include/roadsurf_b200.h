@@ -100,7 +100,8 @@ typedef struct rs_zonal_params {
     int32_t hist_mode;          /* enum rs_hist_mode */
     int32_t window_mode;        /* enum rs_window_mode */
     int32_t rescale;            /* RS_U16 only: 0 = none (illegal), 1 = float64, 2 = float32 working precision */
-    int32_t reserved;
+    int32_t border_px;          /* ignore the outermost border_px pixels of every tile: the raster form of determine_class.clip_labels,
+                                   labels clipped to the tile scaled by 0.99 (determine_class.py:62-95); 0 = whole tile */
     double  scale_k[4];         /* dst = clamp(src*k + off, 0, 255) + 0.5 truncated -- gdal.Translate    */
     double  scale_off[4];       /* scaleParams (scripts/preprocessing/tif2cog.py:260-270)                */
     const int32_t *road_slot;   /* optional int32[n_roads]: output row of each road (NULL = identity)    */

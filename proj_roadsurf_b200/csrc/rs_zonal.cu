@@ -138,7 +138,7 @@ struct alignas(16) PairGeom {       // 64 bytes, computed once per pair by pair_
 // (px/py are monotone in x/y for north-up transforms, so the vertex-wise bounds rasterio takes
 // are attained at the bbox corners).  Returns 0 (shapes do not overlap raster), 1, or <0.
 __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, const double *__restrict__ bb, int W, int H,
-                                             int window_mode, PairGeom &g)
+                                             int window_mode, int border, PairGeom &g)
 {
     const double sa = gt[0], sb = gt[1], sc = gt[2], sd = gt[3], se = gt[4], sf = gt[5];
     if (sb != 0.0 || sd != 0.0 || sa == 0.0 || se == 0.0) return RS_ERR_ROTATED;
@@ -147,6 +147,11 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
         g.xshift = 0; g.yshift = 0; g.wu = W;
         g.inv0 = __ddiv_rn(-sc, sa); g.inv1 = __ddiv_rn(1.0, sa);
         g.inv3 = __ddiv_rn(-sf, se); g.inv5 = __ddiv_rn(1.0, se);
+        if (border > 0) {          // keep the transform of the whole raster, look at the inner rectangle only
+            if (2 * border >= W || 2 * border >= H) return 0;
+            g.col_off = border; g.row_off = border; g.w = W - 2 * border; g.h = H - 2 * border;
+            g.xshift = border; g.yshift = border;
+        }
         return 1;
     }
     // Affine.__invert__
@@ -187,13 +192,23 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     const double wf = __dadd_rn(__dadd_rn(__dmul_rn(sd, xo), __dmul_rn(se, yo)), sf);
     g.inv0 = __ddiv_rn(-wc, wa); g.inv1 = __ddiv_rn(1.0, wa);
     g.inv3 = __ddiv_rn(-wf, we); g.inv5 = __ddiv_rn(1.0, we);
+    if (border > 0) {
+        // the rasterized window keeps its origin and size; only the pixels at least `border` away from the tile edge
+        // are looked at (determine_class.clip_labels: labels clipped to the tile scaled by 0.99)
+        const int c_lo = max(g.col_off, border), c_hi = min(g.col_off + g.w, W - border);
+        const int r_lo = max(g.row_off, border), r_hi = min(g.row_off + g.h, H - border);
+        if (c_hi <= c_lo || r_hi <= r_lo) return 0;
+        g.xshift += c_lo - g.col_off; g.yshift += r_lo - g.row_off;
+        g.col_off = c_lo; g.row_off = r_lo; g.w = c_hi - c_lo; g.h = r_hi - r_lo;
+    }
     return 1;
 }
 
 // thread per pair: its geometry record (the road of pair p is found by bisection of the CSR offsets)
 __global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ road_pair_off, const int *__restrict__ pair_tile,
                                                         const double *__restrict__ road_bbox, const double *__restrict__ gt, int n_roads,
-                                                        int n_pairs, int W, int H, int window_mode, PairGeom *__restrict__ out, int *status)
+                                                        int n_pairs, int W, int H, int window_mode, int border,
+                                                        PairGeom *__restrict__ out, int *status)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ 
     PairGeom g;
     g.inv0 = g.inv1 = g.inv3 = g.inv5 = 0.0;
     g.col_off = g.row_off = g.w = g.h = g.xshift = g.yshift = g.wu = 0;
-    g.status = pair_geometry(gt + 6 * (size_t)pair_tile[p], road_bbox + 4 * (size_t)lo, W, H, window_mode, g);
+    g.status = pair_geometry(gt + 6 * (size_t)pair_tile[p], road_bbox + 4 * (size_t)lo, W, H, window_mode, border, g);
     if (g.status < 0) atomicMin(status, g.status);
     out[p] = g;
 }
@@ -1037,6 +1052,7 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     if (((uintptr_t)roads->xy & 15u) != 0) return RS_ERR_INVALID_ARG;      // TMA bulk source alignment
     if (tiles->width > MAX_WIDTH || tiles->width < 1 || tiles->height < 1) return RS_ERR_UNSUPPORTED;
     if (window_mode != RS_WINDOW_CROP && window_mode != RS_WINDOW_FULL && window_mode != RS_WINDOW_BOUNDLESS) return RS_ERR_INVALID_ARG;
+    if (prm && (prm->border_px < 0 || prm->border_px > 4096)) return RS_ERR_INVALID_ARG;
 
     // item list scratch: every pair can close one group and a tall window adds ceil(H / ROWS_ITEM) row items
     const size_t cap = (size_t)pairs->n_pairs * (1 + (size_t)(tiles->height + ROWS_ITEM - 1) / ROWS_ITEM) + (size_t)roads->n_roads + 1;
@@ -1091,7 +1107,8 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     if (pairs->n_pairs > 0) {
         pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
                                                                        roads->n_roads, pairs->n_pairs, tiles->width, tiles->height,
-                                                                       window_mode, (PairGeom *)ctx->pgeom.p, ctx->d_status);
+                                                                       window_mode, prm ? prm->border_px : 0, (PairGeom *)ctx->pgeom.p,
+                                                                       ctx->d_status);
         ctx->launches++;
         RS_CUDA_OK(ctx, cudaGetLastError());
     }

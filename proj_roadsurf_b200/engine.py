@@ -100,10 +100,11 @@ class Engine:
         return N.RsRoads(xy, ring_off, road_ring_off, bbox, n_roads, n_rings, n_verts)
 
     @staticmethod
-    def _params(hist_mode, window, rescale, road_slot_ptr) -> N.RsZonalParams:
+    def _params(hist_mode, window, rescale, road_slot_ptr, border_px: int = 0) -> N.RsZonalParams:
         p = N.RsZonalParams()
         p.hist_mode = _HIST_MODES[hist_mode]
         p.window_mode = _WINDOW_MODES[window]
+        p.border_px = int(border_px)
         p.rescale = 0
         if rescale is not None:
             k, off, f32 = rescale
@@ -117,7 +118,7 @@ class Engine:
     # ------------------------------------------------------------------ host family
     def zonal_hist_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, hist_mode: str = "bands",
                         window: str = "crop", rescale=None, road_slot: Optional[np.ndarray] = None,
-                        n_slots: Optional[int] = None):
+                        n_slots: Optional[int] = None, border_px: int = 0):
         """Per-road histograms (n_slots, HC, 256) uint32 and all-zero-pixel counts (n_slots,) uint32."""
         px = np.ascontiguousarray(tiles.pixels)
         dtype = N.RS_U16 if px.dtype == np.uint16 else N.RS_U8
@@ -138,7 +139,7 @@ class Engine:
         rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), R, roads.n_rings, roads.n_verts)
         td = N.RsTiles(_np_ptr(px), _np_ptr(gt), tiles.n_tiles, tiles.height, tiles.width, tiles.channels, dtype)
         pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
-        prm = self._params(hist_mode, window, rescale, _np_ptr(slot))
+        prm = self._params(hist_mode, window, rescale, _np_ptr(slot), border_px)
         st = self.lib.rs_zonal_hist_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
                                          _np_ptr(hist), _np_ptr(nzero))
         N.check(st, "rs_zonal_hist_host", self._ctx)

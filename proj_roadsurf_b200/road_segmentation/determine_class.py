@@ -101,11 +101,22 @@ def determine_detected_class_sweep(predictions, roads, thresholds: Sequence[floa
 # ------------------------------------------------------------------------------------------
 # raster form
 # ------------------------------------------------------------------------------------------
-def accumulate_class_planes(roads: RoadSet, tiles: TileBatch, pairs: PairList, engine=None) -> np.ndarray:
+def clip_border_px(tile_size: int, fact: float = 0.99) -> int:
+    """Raster form of clip_labels (determine_class.py:62-95), which intersects the labels with every tile scaled by
+    ``fact`` about its centre: the number of outermost pixel rows / columns whose centres fall outside the scaled
+    tile (1 for 256 px tiles, 5 for 1024 px tiles at fact = 0.99)."""
+    import math
+    margin = tile_size * (1.0 - fact) / 2.0          # 1.28 px for 256 px tiles
+    return max(0, int(math.ceil(margin - 0.5)))
+
+
+def accumulate_class_planes(roads: RoadSet, tiles: TileBatch, pairs: PairList, engine=None, clip_fact: Optional[float] = None) -> np.ndarray:
     """Joint (class, score) histogram per road, uint32 (R, 3, 256): tiles hold two uint8 channels, the class
-    plane (0 none, 1 artificial, 2 natural) and the score plane (score * 255)."""
+    plane (0 none, 1 artificial, 2 natural) and the score plane (score * 255).  ``clip_fact`` (0.99 in the
+    reference) ignores the tile border like clip_labels does."""
     eng = engine or default_engine()
-    hist, _ = eng.zonal_hist_host(roads, tiles, pairs, hist_mode="class_score")
+    border = 0 if clip_fact is None else clip_border_px(tiles.width, clip_fact)
+    hist, _ = eng.zonal_hist_host(roads, tiles, pairs, hist_mode="class_score", border_px=border)
     return hist
 
 

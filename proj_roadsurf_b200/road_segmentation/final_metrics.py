@@ -111,3 +111,32 @@ def threshold_sweep(joint_hist: np.ndarray, gt_class: np.ndarray, thresholds=Non
     all_global = pd.concat(glob, ignore_index=True)
     bi, bt = best_threshold(all_global['f1b'].tolist(), all_global['Pb'].tolist(), thresholds)
     return all_by_class, all_global, bi, bt, cover
+
+
+def diff_score_sweep(comparison_df, thresholds=None, CLASSES=('artificial', 'natural')):
+    """final_metrics.py:429-478: for every threshold, roads whose diff_score is below it become 'undetermined', tags
+    and metrics are recomputed (all thresholds in one GPU call); the best threshold maximises f1b (strictly greater
+    wins, the first threshold is reported as 0).  Returns (metrics_by_class, global_metrics, best_threshold, best_results)
+    where best_results is the comparison table at the best threshold."""
+    thresholds = np.arange(0, 1., 0.05) if thresholds is None else np.asarray(thresholds, float)
+    cover = comparison_df['cover_type'].map(COVER_CODE).fillna(-1).to_numpy().astype(np.int8)
+    gt = comparison_df['CATEGORY'].map(determine_class.CLASS_CODE).fillna(-1).to_numpy().astype(np.int8)
+    diff = comparison_df['diff_score'].to_numpy(float)
+    cover_t = np.where(diff[None, :] < thresholds[:, None], np.int8(2), cover[None, :]).astype(np.int8)
+    conf, met = default_engine().confusion_metrics_host(cover_t, gt)
+    by_class, glob = [], []
+    best, max_f1 = 0, None
+    for i, thr in enumerate(thresholds):
+        a, b = metrics_frames(conf[i], met[i], CLASSES)
+        a['threshold'] = thr
+        b['threshold'] = thr
+        by_class.append(a)
+        glob.append(b)
+        f1 = b['f1b'][0]
+        if i == 0 or f1 > max_f1:
+            best, max_f1 = i, f1
+    best_results = comparison_df.copy()
+    best_results['cover_type'] = determine_class.COVER_NAMES[cover_t[best]]
+    best_results['tag'] = tags_from_codes(cover_t[best], gt)
+    return (pd.concat(by_class, ignore_index=True), pd.concat(glob, ignore_index=True),
+            0 if best == 0 else round(float(thresholds[best]), 2), best_results)

@@ -253,3 +253,52 @@ def test_workflows_match_the_reference_shaped_pipeline(mods):
 def pairs_by_bbox_local(roads, tb):
     from proj_roadsurf_b200.geometry import pairs_by_bbox
     return pairs_by_bbox(roads, tb)
+
+
+def test_border_px_is_clip_labels_in_raster_form(mods):
+    determine_class = mods[3]
+    from proj_roadsurf_b200.engine import default_engine
+    assert determine_class.clip_border_px(256) == 1 and determine_class.clip_border_px(1024) == 5
+    g = synth.Grid(3, 3)
+    rr = synth.ribbon_roads(g, 10, seed=44)
+    tiles = synth.host_tiles(g, 3)
+    gt = g.transforms()
+    for border in (1, 7):
+        h, z = default_engine().zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs, border_px=border)
+        inner = tiles.copy()
+        exp = np.zeros_like(h, dtype=np.uint64)
+        road_of = rr.pairs.road_of_pair()
+        for p in range(rr.pairs.n_pairs):
+            t = int(rr.pairs.pair_tile[p])
+            m = cport.pair_mask_full(gt[t], rr.roads.rings(int(road_of[p])), 256, 256).astype(bool)
+            m[:border] = False; m[-border:] = False; m[:, :border] = False; m[:, -border:] = False
+            px = inner[t][m]
+            for c in range(3):
+                exp[road_of[p], c] += np.bincount(px[:, c], minlength=256).astype(np.uint64)
+        assert np.array_equal(h.astype(np.uint64), exp), border
+    assert exp.sum() > 10000
+
+
+def test_diff_score_sweep_matches_the_reference_loop(mods):
+    determine_class, final_metrics = mods[3], mods[4]
+    g = load("vote")
+    roads = frame(g["roads"])
+    preds = frame(g["predictions"])
+    comp = determine_class.determine_detected_class(preds, roads, 0.1)
+    comp["tag"] = comp.apply(lambda row: final_metrics.get_tag(row), axis=1)
+    thresholds = np.arange(0, 1., 0.05)
+    by_class, glob, best_thr, best_results = final_metrics.diff_score_sweep(comp, thresholds)
+    # final_metrics.py:429-478 with the oracle
+    best, max_f1 = 0, None
+    for i, thr in enumerate(thresholds):
+        f = comp.copy().drop(columns=["tag"])
+        f.loc[f["diff_score"] < thr, "cover_type"] = "undetermined"
+        f["tag"] = [ovote.get_tag(c, k) for c, k in zip(f["cover_type"], f["CATEGORY"])]
+        obc, og = ovote.get_metrics(f)
+        for col in ("Pw", "Rw", "f1w", "Pb", "Rb", "f1b"):
+            assert abs(glob[col][i] - og[col][0]) <= 1e-6
+        assert by_class["TP"][2 * i] == obc["TP"][0] and by_class["FN"][2 * i + 1] == obc["FN"][1]
+        if i == 0 or og["f1b"][0] > max_f1:
+            best, max_f1 = i, og["f1b"][0]
+    assert best_thr == (0 if best == 0 else round(float(thresholds[best]), 2))
+    assert set(best_results["tag"]) <= {"TP", "FN", "wrong class"}
