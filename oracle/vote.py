@@ -199,3 +199,31 @@ def sweep(joint_hist: np.ndarray, gt: np.ndarray, thresholds: Sequence[float] = 
         if i == 0 or met["f1b"] > best[1] or (met["f1b"] == best[1] and met["Pb"] > best[2]):
             best = (i, met["f1b"], met["Pb"])
     return rows, best[0]
+
+
+# ----------------------------------------------------------------------------
+# instance-faithful raster form of get_weighted_scores (determine_class.py:97-120)
+# ----------------------------------------------------------------------------
+def weighted_scores_raster(inside_masks, instance_tiles, road_of_pair, pair_tile, road_ids, inst_score, inst_class_name,
+                           min_area: float = 0.05) -> pd.DataFrame:
+    """inside_masks[p] (H, W) bool mask of pair p; instance_tiles (T, H, W) uint16 instance ids (0 = no detection).
+    area_label = pixels of the road (all its pairs); per (road, instance): area_pred_in_label =
+    round(n_pixels / area_label, 2), weighted_score = area_pred_in_label * score, kept when area_pred_in_label > min_area
+    -- the reference's overlay areas (determine_class.py:107-118) counted in pixels."""
+    R = len(road_ids)
+    area_label = np.zeros(R, np.int64)
+    counts: Dict[Tuple[int, int], int] = {}
+    for p, m in enumerate(inside_masks):
+        r = int(road_of_pair[p])
+        area_label[r] += int(m.sum())
+        ids, c = np.unique(instance_tiles[int(pair_tile[p])][m], return_counts=True)
+        for i, k in zip(ids.tolist(), c.tolist()):
+            if i:
+                counts[(r, i)] = counts.get((r, i), 0) + k
+    rows = []
+    for (r, i), k in sorted(counts.items()):
+        frac = round(k / area_label[r], 2)
+        if frac > min_area:
+            rows.append({"OBJECTID": road_ids[r], "instance": i, "score": float(inst_score[i]), "det_class_name": inst_class_name[i],
+                         "area_pred_in_label": frac, "weighted_score": frac * float(inst_score[i])})
+    return pd.DataFrame(rows, columns=["OBJECTID", "instance", "score", "det_class_name", "area_pred_in_label", "weighted_score"])

@@ -120,6 +120,47 @@ def accumulate_class_planes(roads: RoadSet, tiles: TileBatch, pairs: PairList, e
     return hist
 
 
+def get_weighted_scores_raster(roads: RoadSet, instance_tiles: TileBatch, pairs: PairList, inst_score, inst_class_name,
+                               road_ids=None, clip_fact: Optional[float] = None, min_area: float = 0.05, engine=None) -> pd.DataFrame:
+    """Instance-faithful raster form of get_weighted_scores (determine_class.py:97-120).
+
+    ``instance_tiles``: one uint16 channel holding the id of the detection covering each pixel (0 = none);
+    ``inst_score[i]`` / ``inst_class_name[i]``: confidence and class name of detection i.  The GEOS overlay areas become
+    pixel counts: area_label = pixels of the road polygon, joined_area = pixels of detection i inside it;
+    area_pred_in_label = round(joined / label, 2), weighted_score = area_pred_in_label * score, rows with
+    area_pred_in_label <= 0.05 dropped (:115-118).  The in-mask pixels come from the GPU extraction
+    (rs_extract_pixels_host); the result feeds determine_detected_class unchanged."""
+    eng = engine or default_engine()
+    if instance_tiles.channels != 1:
+        raise ValueError("instance tiles have one channel (the detection id of every pixel)")
+    ids = np.arange(roads.n_roads) if road_ids is None else np.asarray(road_ids)
+    px = np.asarray(instance_tiles.pixels)
+    if clip_fact is not None:                    # clip_labels: ignore the tile border (ids there count as outside the label)
+        b = clip_border_px(instance_tiles.width, clip_fact)
+        inner = np.zeros(px.shape, bool)
+        inner[:, b:px.shape[1] - b, b:px.shape[2] - b] = True
+    pair_off, values = eng.extract_pixels_host(roads, instance_tiles, pairs, window="crop")
+    road_of_pixel = np.repeat(pairs.road_of_pair().astype(np.int64), np.diff(pair_off))
+    inst = values[:, 0].astype(np.int64)
+    if clip_fact is not None:
+        # the same extraction on a 0/1 plane tells which extracted pixels lie in the inner rectangle
+        flag = TileBatch(inner.astype(np.uint8), instance_tiles.gt, instance_tiles.height, instance_tiles.width, 1)
+        _, inside = eng.extract_pixels_host(roads, flag, pairs, window="crop")
+        keep = inside[:, 0] != 0
+        road_of_pixel, inst = road_of_pixel[keep], inst[keep]
+    area_label = np.bincount(road_of_pixel, minlength=roads.n_roads)
+    key = road_of_pixel * 65536 + inst
+    uk, cnt = np.unique(key[inst > 0], return_counts=True)
+    r, i = uk // 65536, uk % 65536
+    frac = np.array([round(c / area_label[rr], 2) for c, rr in zip(cnt.tolist(), r.tolist())], float)
+    score = np.asarray(inst_score, float)[i] if len(i) else np.zeros(0)
+    keep = frac > min_area
+    names = np.asarray(inst_class_name, object)
+    return pd.DataFrame({"OBJECTID": ids[r[keep]], "instance": i[keep], "score": score[keep],
+                         "det_class_name": names[i[keep]] if len(i) else np.zeros(0, object),
+                         "area_pred_in_label": frac[keep], "weighted_score": frac[keep] * score[keep]})
+
+
 def score_cutoffs(thresholds: Sequence[float]) -> np.ndarray:
     """smallest uint8 score s with s / 255 >= threshold (256: none)"""
     s = np.arange(256) / 255.0

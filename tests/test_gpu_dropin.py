@@ -302,3 +302,39 @@ def test_diff_score_sweep_matches_the_reference_loop(mods):
             best, max_f1 = i, og["f1b"][0]
     assert best_thr == (0 if best == 0 else round(float(thresholds[best]), 2))
     assert set(best_results["tag"]) <= {"TP", "FN", "wrong class"}
+
+
+def test_instance_faithful_weighted_scores(mods):
+    """get_weighted_scores with overlay areas counted in pixels per (road, detection) -> determine_detected_class -> metrics"""
+    determine_class, final_metrics = mods[3], mods[4]
+    g = synth.Grid(4, 4)
+    rr = synth.ribbon_roads(g, 16, seed=52)
+    gt = g.transforms()
+    rng = np.random.default_rng(6)
+    # blobby detections: 32 px blocks, ~60 % of them carry a detection id
+    blocks = rng.integers(1, 200, (g.n_tiles, 8, 8)).astype(np.uint16)
+    blocks[rng.random(blocks.shape) < 0.4] = 0
+    inst = np.repeat(np.repeat(blocks, 32, 1), 32, 2)
+    score = np.round(rng.uniform(0.05, 1.0, 200), 3)
+    cls = np.where(rng.random(200) < 0.6, "artificial", "natural").astype(object)
+    tb = TileBatch.from_arrays(inst[..., None], gt)
+    ids = np.arange(16) + 500
+    got = determine_class.get_weighted_scores_raster(rr.roads, tb, rr.pairs, score, cls, road_ids=ids)
+    road_of = rr.pairs.road_of_pair()
+    masks = [cport.pair_mask_full(gt[rr.pairs.pair_tile[p]], rr.roads.rings(int(road_of[p])), 256, 256).astype(bool)
+             for p in range(rr.pairs.n_pairs)]
+    exp = ovote.weighted_scores_raster(masks, inst, road_of, rr.pairs.pair_tile, ids, score, cls)
+    assert len(exp) > 10
+    a = got.sort_values(["OBJECTID", "instance"]).reset_index(drop=True)
+    b = exp.sort_values(["OBJECTID", "instance"]).reset_index(drop=True)
+    assert a["OBJECTID"].tolist() == b["OBJECTID"].tolist() and a["instance"].tolist() == b["instance"].tolist()
+    assert a["det_class_name"].tolist() == b["det_class_name"].tolist()
+    assert np.array_equal(a["area_pred_in_label"].to_numpy(), b["area_pred_in_label"].to_numpy())      # 2-dp rounded, exact
+    np.testing.assert_allclose(a["weighted_score"], b["weighted_score"], rtol=1e-12)
+    roads_df = pd.DataFrame({"OBJECTID": ids, "CATEGORY": np.where(rr.gt_class == 0, "artificial", "natural"), "gt_type": "gt"})
+    comp = determine_class.determine_detected_class(got, roads_df, 0.2)
+    ocomp = ovote.determine_detected_class(exp, roads_df, 0.2)
+    assert comp["cover_type"].tolist() == ocomp["cover_type"].tolist()
+    # with the clip_labels border the label area shrinks
+    clipped = determine_class.get_weighted_scores_raster(rr.roads, tb, rr.pairs, score, cls, road_ids=ids, clip_fact=0.99)
+    assert len(clipped) > 0 and set(clipped["OBJECTID"]) <= set(ids.tolist())
