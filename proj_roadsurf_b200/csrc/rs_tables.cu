@@ -24,7 +24,7 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: one warp per road; lane l owns bins [8l, 8l+8)
+// K3: one warp per (road, band); lane l owns bins [8l, 8l+8)
 // ---------------------------------------------------------------------------------------------
 struct FinalizeArgs {
     const uint32_t *hist;
@@ -53,9 +53,12 @@ __device__ __forceinline__ int order_stat(const u64 c[8], u64 excl, u64 nl, u64 
 
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a)
 {
-    const int road = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (road >= a.n_roads) return;
+    // one warp per (road, band)
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const int C = a.C, NS = RS_NSTAT + a.n_pct;
+    if (wid >= (long long)a.n_roads * C) return;
+    const int road = (int)(wid / C), b_only = (int)(wid - (long long)road * C);
     const uint32_t *hr = a.hist + (size_t)road * C * 256;
 
     u64 longest = 0;
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a)
     }
     const u64 allzero = a.nzero ? (u64)a.nzero[road] : 0ull;
 
-    for (int b = 0; b < C; b++) {
+    for (int b = b_only; b <= b_only; b++) {
         const uint4 q0 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane);
         const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane + 4);
         u64 c[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
@@ -171,7 +174,7 @@ int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero
     for (int i = 0; i < n_pct; i++) a.pct[i] = pct_host[i];
     a.stats = stats;
     const int threads = 256;
-    const unsigned blocks = (unsigned)(((size_t)n_roads * 32 + threads - 1) / threads);
+    const unsigned blocks = (unsigned)(((size_t)n_roads * channels * 32 + threads - 1) / threads);
     finalize_kernel<<<blocks, threads, 0, st>>>(a);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
