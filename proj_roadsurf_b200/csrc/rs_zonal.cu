@@ -265,19 +265,20 @@ __device__ __forceinline__ uint32_t half_at(const uint32_t (&r)[N]) { return (r[
 // The addend of the histogram increments is the kernel argument ZonalArgs::one (= 1): with a literal 1
 // ptxas turns every increment into a warp-aggregated ATOMS.POPC.INC, which needs a reconvergence
 // point (BSSY / BRA / BSYNC) per atomic and cannot be predicated.
-__device__ __forceinline__ void red_inc3(uint32_t on, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t one)
+__device__ __forceinline__ void red_inc3(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t v)
 {
-    // shared atomics cannot be predicated: `on` is the pixel's mask bit (0 / 1), masked-off pixels add 0
+    // shared atomics cannot be predicated: v is the pixel's mask bit (0 / 1, derived from ZonalArgs::one), masked-off
+    // pixels add 0
     asm volatile(
         "red.shared.add.u32 [%0], %3;\n\t"
         "red.shared.add.u32 [%1], %3;\n\t"
         "red.shared.add.u32 [%2], %3;"
-        ::"r"(a0), "r"(a1), "r"(a2), "r"(on & one)
+        ::"r"(a0), "r"(a1), "r"(a2), "r"(v)
         : "memory");
 }
-__device__ __forceinline__ void red_inc1(uint32_t on, uint32_t a0, uint32_t one)
+__device__ __forceinline__ void red_inc1(uint32_t a0, uint32_t v)
 {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(on & one) : "memory");
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(v) : "memory");
 }
 // byte K of w, times 4 (a histogram bin's byte offset)
 __device__ __forceinline__ uint32_t bin_off(uint32_t w, int k)      // k is a compile-time constant after unrolling
@@ -290,21 +291,24 @@ struct PxBandsU8 {
     static constexpr int C = C_, HC = C_, BPP = C_, NW = 2 * C_;
     static constexpr bool MASK = false;
     // pixel I of the group: hist (shared-memory byte address of the team histogram) gets one increment per band
+    // `on` is the pixel's mask bit (0 / 1), also the addend of its increments
     template <int I>
-    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t one, uint32_t &nz)
+    __device__ static __forceinline__ void pixel(const ZonalArgs &, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t, uint32_t &nz)
     {
-        uint32_t o[C];
+        // the team histogram is 1 KiB aligned: band base | bin offset is one LOP3 after the shift
+        uint32_t ad[C];
 #pragma unroll
-        for (int c = 0; c < C; c++) o[c] = bin_off(r[(I * C + c) >> 2], (I * C + c) & 3);
-        uint32_t any = 0;
-#pragma unroll
-        for (int c = 0; c < C; c++) any |= o[c];
-        // the team histogram is 1 KiB aligned: band base | bin offset is one LOP3
-        if constexpr (C == 3) red_inc3(on, hist | o[0], (hist + 1024) | o[1], (hist + 2048) | o[2], one);
+        for (int c = 0; c < C; c++) ad[c] = (hist + 1024 * c) | bin_off(r[(I * C + c) >> 2], (I * C + c) & 3);
+        if constexpr (C == 3) red_inc3(ad[0], ad[1], ad[2], on);
         else {
 #pragma unroll
-            for (int c = 0; c < C; c++) red_inc1(on, (hist + 1024 * c) | o[c], one);
+            for (int c = 0; c < C; c++) red_inc1(ad[c], on);
         }
+        // all bands zero: a mask test on the raw words (the pixel's C bytes start at byte I * C)
+        constexpr int B0 = I * C, K = B0 & 3, NB = K + C;          // bytes K .. NB-1 of the two words at r[B0 >> 2]
+        constexpr uint32_t M0 = (NB >= 4 ? 0xffffffffu : ((1u << (8 * NB)) - 1u)) & ~((1u << (8 * K)) - 1u);
+        uint32_t any = r[B0 >> 2] & M0;
+        if constexpr (NB > 4) any |= r[(B0 >> 2) + 1] & ((1u << (8 * (NB - 4))) - 1u);
         nz += (any == 0) ? on : 0u;
     }
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
@@ -337,7 +341,7 @@ struct PxClassScore {
         const uint32_t score = byte_at<2 * I + 1>(r);
         nz += ((cls | score) == 0) ? on : 0u;
         if (cls > 2u) cls = 0u;   // unknown class codes count as "no detection"
-        red_inc1(on, hist + 4u * (cls * 256u + score), one);
+        red_inc1(hist + 4u * (cls * 256u + score), on);
     }
     __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
     {
@@ -368,7 +372,7 @@ struct PxU16x4Rescale {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const uint32_t o = scale(a, (r[(I * 8 + 2 * c) >> 2] >> (((I * 8 + 2 * c) & 3) * 8)) & 0xffffu, c);
-            red_inc1(on, hist + 4u * (c * 256u + o), one);
+            red_inc1(hist + 4u * (c * 256u + o), on);
             any |= o;
         }
         nz += (any == 0) ? on : 0u;
@@ -421,7 +425,7 @@ __device__ __forceinline__ void group_pixels(const ZonalArgs &a, const uint32_t 
                                              uint32_t &nz)
 {
     if constexpr (I < 8) {
-        PX::template pixel<I>(a, r, (m8 >> I) & 1u, hist, one, nz);
+        PX::template pixel<I>(a, r, (m8 >> I) & one, hist, one, nz);        // one == 1, opaque to the compiler
         group_pixels<PX, I + 1>(a, r, m8, hist, one, nz);
     }
 }
