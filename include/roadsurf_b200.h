@@ -151,6 +151,16 @@ int rs_zonal_hist_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero);
 
 /*
+ * rs_zonal_stats_host for tile sets larger than the device (or than one wants resident): the tiles stay in (pinned) host
+ * memory and are streamed through two device buffers of tiles_per_chunk tiles; the copy of chunk k+1 overlaps the
+ * kernel of chunk k, the per-road histograms accumulate on the device (integer atomics, exact) and are finalized once.
+ * Same arguments and results as rs_zonal_stats_host.
+ */
+int rs_zonal_stats_stream_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                               const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
+                               int32_t n_pct, int32_t tiles_per_chunk, double *stats, uint32_t *hist, uint32_t *n_allzero);
+
+/*
  * Pixel masks.  Replaces rasterio.features.rasterize (scripts/sandbox/add_tile_mask.py:112-113,
  * window_mode FULL) and the shape mask of rasterio.mask.mask (fct_misc.py:77, window_mode CROP).
  * masks uint8[n_pairs][height][width] (pair order = pair_tile order), 1 = selected; the

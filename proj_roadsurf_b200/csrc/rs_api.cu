@@ -155,6 +155,11 @@ int rs_ctx_destroy(rs_ctx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_status_pinned) cudaFreeHost(ctx->h_status_pinned);
     if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_used[i]) cudaEventDestroy(ctx->ev_used[i]);
+    }
     delete ctx;
     return RS_OK;
 }
@@ -265,6 +270,65 @@ int rs_zonal_stats_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tile
     rc = launch_zonal(ctx, &dr, &dt, &dp, prm, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
                       prm->window_mode, st);
     if (rc) return rc;
+    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, (const uint32_t *)ctx->stage[10].p, R, C, nodata_mode, ddof,
+                         percentiles, n_pct, (double *)ctx->stage[11].p, st);
+    if (rc) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[11].p, sb, cudaMemcpyDeviceToHost, st));
+    if (hist) RS_CUDA_OK(ctx, cudaMemcpyAsync(hist, ctx->stage[9].p, hb, cudaMemcpyDeviceToHost, st));
+    if (n_allzero) RS_CUDA_OK(ctx, cudaMemcpyAsync(n_allzero, ctx->stage[10].p, zb, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
+int rs_zonal_stats_stream_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                               const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
+                               int32_t n_pct, int32_t tiles_per_chunk, double *stats, uint32_t *hist, uint32_t *n_allzero)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!prm || !stats || prm->road_slot || n_pct < 0 || n_pct > 16 || tiles_per_chunk < 1) return RS_ERR_INVALID_ARG;
+    if (prm->hist_mode != RS_HIST_BANDS) return RS_ERR_INVALID_ARG;
+    rs_roads dr;
+    rs_tiles dt;
+    rs_pairs dp;
+    if ((rc = stage_inputs(ctx, roads, tiles, pairs, false, dr, dt, dp))) return rc;     // geometry + pairs + transforms, no pixels
+    if (tiles->n_tiles > 0 && !tiles->pixels) return RS_ERR_INVALID_ARG;
+    const int R = roads->n_roads, C = tiles->channels;
+    if (R == 0) return RS_OK;
+    if (!ctx->copy_stream) {
+        RS_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            RS_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            RS_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t tile_bytes = (size_t)tiles->height * tiles->width * C * elem_bytes(tiles->dtype);
+    const size_t hb = sizeof(uint32_t) * 256 * (size_t)C * R, zb = sizeof(uint32_t) * (size_t)R;
+    const size_t sb = sizeof(double) * (size_t)(RS_NSTAT + n_pct) * C * R;
+    const int per = tiles_per_chunk < tiles->n_tiles ? tiles_per_chunk : (tiles->n_tiles > 0 ? tiles->n_tiles : 1);
+    if ((rc = ensure(ctx, ctx->stage[7], tile_bytes * per))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[8], tile_bytes * per))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[9], hb))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], sb))) return rc;
+    cudaStream_t st = ctx->host_stream, cs = ctx->copy_stream;
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[9].p, 0, hb, st));
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[10].p, 0, zb, st));
+    int k = 0;
+    for (int lo = 0; lo < tiles->n_tiles; lo += per, k++) {
+        const int hi = lo + per < tiles->n_tiles ? lo + per : tiles->n_tiles, b = k & 1;
+        void *buf = b ? ctx->stage[8].p : ctx->stage[7].p;
+        if (k >= 2) RS_CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->ev_used[b], 0));          // the kernel of chunk k-2 is done with it
+        RS_CUDA_OK(ctx, cudaMemcpyAsync(buf, (const uint8_t *)tiles->pixels + (size_t)lo * tile_bytes, (size_t)(hi - lo) * tile_bytes,
+                                        cudaMemcpyHostToDevice, cs));
+        RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
+        RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[b], 0));
+        rs_tiles chunk = dt;
+        chunk.pixels = (const uint8_t *)buf - (size_t)lo * tile_bytes;                     // indexed with the global tile index
+        rc = launch_zonal_chunk(ctx, &dr, &chunk, &dp, prm, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
+                                prm->window_mode, lo, hi, 1, st);
+        if (rc) return rc;
+        RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_used[b], st));
+    }
     rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, (const uint32_t *)ctx->stage[10].p, R, C, nodata_mode, ddof,
                          percentiles, n_pct, (double *)ctx->stage[11].p, st);
     if (rc) return rc;

@@ -27,6 +27,8 @@ struct rs_ctx {
     int *d_counters = nullptr;    // work counters / list sizes, RS_NCOUNTERS ints
     int *h_status_pinned = nullptr;
     cudaStream_t host_stream = nullptr;   // stream of the _host entry points
+    cudaStream_t copy_stream = nullptr;   // H2D stream of the streaming entry point (created on first use)
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
     rs::DevBuf stage[16];                 // grow-only device staging of the _host entry points
     rs::DevBuf items;                     // grow-only work-item list of the zonal kernel
     rs::DevBuf pgeom;                     // grow-only per-pair geometry records of the zonal kernel
@@ -52,6 +54,9 @@ int ensure(rs_ctx *ctx, DevBuf &b, size_t bytes);
 int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                  const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks,
                  int window_mode, cudaStream_t st);
+int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                       const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
+                       int tile_lo, int tile_hi, int accumulate, cudaStream_t st);
 int launch_road_bbox(rs_ctx *ctx, const rs_roads *roads, double *out, cudaStream_t st);
 int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int n_roads, int channels,
                     int nodata_mode, int ddof, const double *pct_host, int n_pct, double *stats, cudaStream_t st);

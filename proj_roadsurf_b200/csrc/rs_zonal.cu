@@ -207,7 +207,7 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
 // thread per pair: its geometry record (the road of pair p is found by bisection of the CSR offsets)
 __global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ road_pair_off, const int *__restrict__ pair_tile,
                                                         const double *__restrict__ road_bbox, const double *__restrict__ gt, int n_roads,
-                                                        int n_pairs, int W, int H, int window_mode, int border,
+                                                        int n_pairs, int W, int H, int window_mode, int border, int tile_lo, int tile_hi,
                                                         PairGeom *__restrict__ out, int *status)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,7 +221,9 @@ __global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ 
     PairGeom g;
     g.inv0 = g.inv1 = g.inv3 = g.inv5 = 0.0;
     g.col_off = g.row_off = g.w = g.h = g.xshift = g.yshift = g.wu = 0;
-    g.status = pair_geometry(gt + 6 * (size_t)pair_tile[p], road_bbox + 4 * (size_t)lo, W, H, window_mode, border, g);
+    const int t = pair_tile[p];
+    if (t < tile_lo || t >= tile_hi) g.status = 0;          // streaming: this launch only sees the tiles of one chunk
+    else g.status = pair_geometry(gt + 6 * (size_t)t, road_bbox + 4 * (size_t)lo, W, H, window_mode, border, g);
     if (g.status < 0) atomicMin(status, g.status);
     out[p] = g;
 }
@@ -945,7 +947,7 @@ __device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, in
 
 __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__ road_pair_off, const PairGeom *__restrict__ pgeom,
                                                          int n_roads, const int *__restrict__ road_slot, uint32_t *hist, uint32_t *nzero,
-                                                         int hc, int4 *items, int *n_items, int tall)
+                                                         int hc, int4 *items, int *n_items, int tall, int accumulate)
 {
     const int road = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     int p0 = 0, p1 = 0, ni = 0;
@@ -963,8 +965,8 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__
     int base = 0;
     if (lane == 31 && total > 0) base = atomicAdd(n_items, total);
     base = __shfl_sync(FULL, base, 31) + incl - ni;
-    if (ni > 0) road_items<true>(pgeom, road, p0, p1, items, base, ni > 1 ? ITEM_SPLIT : 0, tall != 0);
-    if (hist) {
+    if (ni > 0) road_items<true>(pgeom, road, p0, p1, items, base, (ni > 1 || accumulate) ? ITEM_SPLIT : 0, tall != 0);
+    if (hist && !accumulate) {
         unsigned m = __ballot_sync(FULL, road < n_roads && ni != 1);
         for (; m; m &= m - 1) {
             const int src = __ffs(m) - 1;
@@ -1047,6 +1049,16 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
                  const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
                  cudaStream_t st)
 {
+    return launch_zonal_chunk(ctx, roads, tiles, pairs, prm, hist, n_allzero, masks, window_mode, 0, 0x7fffffff, 0, st);
+}
+
+// tile_lo / tile_hi: only pairs whose tile index lies in [tile_lo, tile_hi) are processed (tiles->pixels is then indexed with
+// the global tile index, so a caller that holds one chunk passes chunk_base - tile_lo * tile_bytes);
+// accumulate: add into hist / n_allzero (zeroed by the caller) instead of writing every row once
+int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                       const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
+                       int tile_lo, int tile_hi, int accumulate, cudaStream_t st)
+{
     if (!roads || !tiles || !pairs) return RS_ERR_INVALID_ARG;
     if (roads->n_roads < 0 || roads->n_verts < 0 || tiles->n_tiles < 0 || pairs->n_pairs < 0) return RS_ERR_INVALID_ARG;
     if (roads->n_roads == 0) return RS_OK;
@@ -1111,14 +1123,14 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
     if (pairs->n_pairs > 0) {
         pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
                                                                        roads->n_roads, pairs->n_pairs, tiles->width, tiles->height,
-                                                                       window_mode, prm ? prm->border_px : 0, (PairGeom *)ctx->pgeom.p,
-                                                                       ctx->d_status);
+                                                                       window_mode, prm ? prm->border_px : 0, tile_lo, tile_hi,
+                                                                       (PairGeom *)ctx->pgeom.p, ctx->d_status);
         ctx->launches++;
         RS_CUDA_OK(ctx, cudaGetLastError());
     }
     prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
                                                                     a.road_slot, masks ? nullptr : hist, n_allzero, HC,
-                                                                    (int4 *)ctx->items.p, ctx->d_counters + 1, tiles->height > ROWS_ITEM);
+                                                                    (int4 *)ctx->items.p, ctx->d_counters + 1, tiles->height > ROWS_ITEM, accumulate);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
 

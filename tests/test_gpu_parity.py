@@ -622,3 +622,19 @@ def test_wide_polygons_config5(eng):
     oh, oz = oracle_hist(wp.roads, wp.pairs, tiles, gt, threads=4)
     assert oh[:, 0].sum() > 2_000_000
     assert np.array_equal(h.astype(np.uint64), oh) and np.array_equal(z.astype(np.uint64), oz)
+
+
+def test_streaming_from_host_equals_resident(eng):
+    """rs_zonal_stats_stream_host: tiles streamed through two device buffers, histograms accumulated on the device"""
+    g = synth.Grid(7, 5)
+    rr = synth.ribbon_roads(g, 40, seed=81)
+    tiles = synth.host_tiles(g, 3)
+    tb = TileBatch.from_arrays(tiles, g.transforms())
+    ref = eng.zonal_stats_host(rr.roads, tb, rr.pairs, nodata_mode="none", ddof=1, percentiles=(10.0, 90.0), want_hist=True)
+    for per in (1, 4, 9, 35, 100):
+        got = eng.zonal_stats_host(rr.roads, tb, rr.pairs, nodata_mode="none", ddof=1, percentiles=(10.0, 90.0), want_hist=True,
+                                   tiles_per_chunk=per)
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]), per
+        assert np.array_equal(got[0], ref[0], equal_nan=True), per
+    oh, _ = oracle_hist(rr.roads, rr.pairs, tiles, g.transforms())
+    assert np.array_equal(ref[1].astype(np.uint64), oh)
