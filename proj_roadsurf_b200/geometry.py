@@ -103,18 +103,12 @@ class RoadSet:
         nonempty = v1 > v0
         bbox[~nonempty] = [np.inf, np.inf, -np.inf, -np.inf]
         if nonempty.any():
-            # reduceat over contiguous vertex ranges
-            starts = v0[nonempty]
-            order = np.argsort(starts, kind="stable")
-            assert np.all(np.diff(starts) >= 0), "roads must be stored in vertex order"
-            idx = starts.astype(np.intp)
-            mins_x = np.minimum.reduceat(xy[:, 0], idx)
-            mins_y = np.minimum.reduceat(xy[:, 1], idx)
-            maxs_x = np.maximum.reduceat(xy[:, 0], idx)
-            maxs_y = np.maximum.reduceat(xy[:, 1], idx)
-            # reduceat runs to the next start; roads are contiguous so that equals v1 unless empty roads interleave
-            bbox[nonempty] = np.stack([mins_x, mins_y, maxs_x, maxs_y], 1)
-            del order
+            # reduceat over contiguous vertex ranges: roads are stored in vertex order, so the range of a non-empty
+            # road ends where the next non-empty road starts
+            idx = v0[nonempty].astype(np.intp)
+            assert np.all(np.diff(idx) >= 0), "roads must be stored in vertex order"
+            bbox[nonempty] = np.stack([np.minimum.reduceat(xy[:, 0], idx), np.minimum.reduceat(xy[:, 1], idx),
+                                       np.maximum.reduceat(xy[:, 0], idx), np.maximum.reduceat(xy[:, 1], idx)], 1)
         return RoadSet(xy, ring_off, road_ring_off, bbox, None if ids is None else np.asarray(ids))
 
     def rings(self, r: int) -> List[np.ndarray]:

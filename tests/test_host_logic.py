@@ -1,0 +1,75 @@
+"""Host-side logic of the product package against the oracle (no GPU)."""
+import numpy as np
+
+from oracle import gdal_fill
+from proj_roadsurf_b200 import synth
+from proj_roadsurf_b200.geometry import (PairList, RoadSet, TileBatch, lattice_of, pairs_by_bbox, rasterio_window, rings_of)
+
+
+def test_rasterio_window_matches_the_oracle_geometry_window():
+    rng = np.random.default_rng(3)
+    t = (0.5971642834779395, 0.0, 815000.3, 0.0, -0.5971642834779395, 5935000.7)
+    n_none = 0
+    for _ in range(500):
+        c = np.array([815000.3 + rng.uniform(-60, 215), 5935000.7 - rng.uniform(-60, 215)])
+        pts = c + rng.normal(0, rng.uniform(1, 60), (6, 2))
+        if rng.random() < 0.2:
+            pts = np.round(pts / 0.5971642834779395) * 0.5971642834779395      # vertices on pixel corners
+        ring = np.concatenate([pts, pts[:1]])
+        rs = RoadSet.from_geometries([[ring]])
+        got = rasterio_window(t, rs.bbox[0], 256, 256)
+        exp = gdal_fill.geometry_window(t, [ring], 256, 256)
+        assert got == exp
+        n_none += exp is None
+    assert 0 < n_none < 450
+
+
+def test_rings_of_accepts_every_geometry_form():
+    sq = [[0, 0], [4, 0], [4, 4], [0, 4], [0, 0]]
+    hole = [[1, 1], [1, 2], [2, 2], [2, 1], [1, 1]]
+    assert len(rings_of({"type": "Polygon", "coordinates": [sq, hole]})) == 2
+    assert len(rings_of({"type": "MultiPolygon", "coordinates": [[sq], [sq, hole]]})) == 3
+    assert len(rings_of({"type": "Feature", "geometry": {"type": "Polygon", "coordinates": [sq]}})) == 1
+    assert len(rings_of({"type": "GeometryCollection", "geometries": [{"type": "Polygon", "coordinates": [sq]}] * 2})) == 2
+
+    class Shp:
+        __geo_interface__ = {"type": "Polygon", "coordinates": [sq]}
+    assert len(rings_of(Shp())) == 1
+    assert rings_of(np.array(sq, float))[0].shape == (5, 2)
+    rs = RoadSet.from_geometries([{"type": "Polygon", "coordinates": [[[0, 0, 9], [4, 0, 9], [4, 4, 9], [0, 0, 9]]]}])   # Z dropped
+    assert rs.xy.shape == (4, 2) and list(rs.bbox[0]) == [0, 0, 4, 4]
+
+
+def test_pair_list_dedup_order_and_filters():
+    p = PairList.from_pairs(4, [2, 0, 2, 2, 0, 3], [5, 1, 5, 3, 0, 9])          # duplicates dropped like drop_duplicates
+    assert p.road_pair_off.tolist() == [0, 2, 2, 4, 5]
+    assert p.pair_tile.tolist() == [0, 1, 3, 5, 9]
+    q = p.restrict_tiles(1, 6)
+    assert q.road_pair_off.tolist() == [0, 1, 1, 3, 3] and q.pair_tile.tolist() == [0, 2, 4]
+    r = p.take_roads([3, 0])
+    assert r.road_pair_off.tolist() == [0, 1, 3] and r.pair_tile.tolist() == [9, 0, 1]
+
+
+def test_lattice_detection_and_host_broad_phase():
+    g = synth.Grid(9, 6)
+    rr = synth.ribbon_roads(g, 60, seed=9)
+    tb = TileBatch(None, g.transforms(), 256, 256, 3)
+    lat = lattice_of(tb)
+    assert lat is not None and (lat.nx, lat.ny) == (9, 6) and (lat.lut >= 0).all()
+    # irregular tile set: no lattice, brute-force broad phase still works and agrees with the lattice one
+    gt = g.transforms().copy()
+    shuffled = TileBatch(None, gt[::-1].copy(), 256, 256, 3)
+    a = pairs_by_bbox(rr.roads, tb)
+    b = pairs_by_bbox(rr.roads, shuffled)
+    assert a.n_pairs == b.n_pairs
+    bad = gt.copy()
+    bad[3, 0] *= 1.5                                       # one tile with another resolution
+    assert lattice_of(TileBatch(None, bad, 256, 256, 3)) is None
+    c = pairs_by_bbox(rr.roads, TileBatch(None, bad, 256, 256, 3))
+    assert c.n_pairs >= a.n_pairs - 20
+
+
+def test_clip_border_px():
+    from proj_roadsurf_b200.road_segmentation.determine_class import clip_border_px
+    assert [clip_border_px(w) for w in (64, 256, 512, 1024)] == [0, 1, 3, 5]
+    assert clip_border_px(256, 1.0) == 0
