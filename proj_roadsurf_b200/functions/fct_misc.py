@@ -90,7 +90,7 @@ def open_tile(tile) -> Optional[dict]:
     try:
         import rasterio                       # not part of this image; used when the deployment has it
     except Exception:  # noqa: BLE001
-        return None
+        return _open_geotiff_pil(tile)
     try:
         with rasterio.open(tile) as src:
             t = src.transform
@@ -98,6 +98,41 @@ def open_tile(tile) -> Optional[dict]:
                     "nodata": src.nodata}
     except Exception:  # noqa: BLE001  (RasterioIOError)
         return None
+
+
+def _open_geotiff_pil(path) -> Optional[dict]:
+    """Minimal GeoTIFF reader for north-up 8-bit tiles (what the tile server / generate_tilesets writes:
+    "<z>_<x>_<y>.tif", statistical_analysis.py:138-139): pixels through PIL, the affine from ModelPixelScale (33550) +
+    ModelTiepoint (33922) or ModelTransformation (34264), nodata from GDAL_NODATA (42113)."""
+    try:
+        from PIL import Image
+        with Image.open(path) as im:
+            data = np.asarray(im)
+            tags = im.tag_v2 if hasattr(im, "tag_v2") else {}
+            scale, tie, mt, nd = tags.get(33550), tags.get(33922), tags.get(34264), tags.get(42113)
+    except Exception:  # noqa: BLE001  (missing or unreadable file: the RasterioIOError branch of the reference)
+        return None
+    if data.ndim == 2:
+        data = data[..., None]
+    if data.dtype not in (np.uint8, np.uint16):
+        return None
+    if scale is not None and tie is not None:
+        i, j, _, x, y, _ = [float(v) for v in tie[:6]]
+        sx, sy = float(scale[0]), float(scale[1])
+        transform = (sx, 0.0, x - i * sx, 0.0, -sy, y + j * sy)
+    elif mt is not None:
+        m = [float(v) for v in mt]
+        transform = (m[0], m[1], m[3], m[4], m[5], m[7])
+    else:
+        transform = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+    nodata = None
+    if nd is not None:
+        try:
+            nodata = float(str(nd).strip().strip("\x00"))
+            nodata = int(nodata) if nodata == int(nodata) else nodata
+        except ValueError:
+            nodata = None
+    return {"data": np.ascontiguousarray(data), "transform": transform, "nodata": nodata}
 
 
 # ------------------------------------------------------------------------------------------

@@ -338,3 +338,25 @@ def test_instance_faithful_weighted_scores(mods):
     # with the clip_labels border the label area shrinks
     clipped = determine_class.get_weighted_scores_raster(rr.roads, tb, rr.pairs, score, cls, road_ids=ids, clip_fact=0.99)
     assert len(clipped) > 0 and set(clipped["OBJECTID"]) <= set(ids.tolist())
+
+
+def test_get_pixel_values_from_a_geotiff_file(mods, tmp_path):
+    """the reference's call shape: get_pixel_values(geometry, '<z>_<x>_<y>.tif', BANDS, df, road_id=...)"""
+    from PIL import Image, TiffImagePlugin
+    fct_misc = mods[0]
+    g = load("pixel_values")
+    data = np.array(g["data"], np.uint8)
+    for nodata in (None, 0):
+        ifd = TiffImagePlugin.ImageFileDirectory_v2()
+        t = g["transform"]
+        ifd[33550] = (t[0], -t[4], 0.0); ifd.tagtype[33550] = 12
+        ifd[33922] = (0.0, 0.0, 0.0, t[2], t[5], 0.0); ifd.tagtype[33922] = 12
+        if nodata is not None:
+            ifd[42113] = str(nodata); ifd.tagtype[42113] = 2
+        path = str(tmp_path / f"18_1_{0 if nodata is None else 1}.tif")
+        Image.fromarray(data).save(path, tiffinfo=ifd)
+        for case in g["cases"]:
+            if case["nodata"] != nodata or case["geom"] == "__accumulated__":
+                continue
+            one = fct_misc.get_pixel_values(g["geoms"][case["geom"]], path, range(1, 4), pd.DataFrame(), road_id=case["geom"])
+            assert_frame_matches(case["result"], one)

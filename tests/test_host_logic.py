@@ -73,3 +73,23 @@ def test_clip_border_px():
     from proj_roadsurf_b200.road_segmentation.determine_class import clip_border_px
     assert [clip_border_px(w) for w in (64, 256, 512, 1024)] == [0, 1, 3, 5]
     assert clip_border_px(256, 1.0) == 0
+
+
+def test_geotiff_tiles_open_without_rasterio(tmp_path):
+    from PIL import Image, TiffImagePlugin
+    from proj_roadsurf_b200.functions import fct_misc
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (16, 24, 3), dtype=np.uint8)
+    ifd = TiffImagePlugin.ImageFileDirectory_v2()
+    ifd[33550] = (0.5, 0.5, 0.0); ifd.tagtype[33550] = 12
+    ifd[33922] = (0.0, 0.0, 0.0, 1000.0, 5000.0, 0.0); ifd.tagtype[33922] = 12
+    ifd[42113] = "0"; ifd.tagtype[42113] = 2
+    path = str(tmp_path / "18_136678_92197.tif")
+    Image.fromarray(a).save(path, tiffinfo=ifd)
+    t = fct_misc.open_tile(path)
+    assert np.array_equal(t["data"], a) and t["transform"] == (0.5, 0.0, 1000.0, 0.0, -0.5, 5000.0) and t["nodata"] == 0
+    assert fct_misc.open_tile(str(tmp_path / "missing.tif")) is None
+    plain = str(tmp_path / "plain.tif")
+    Image.fromarray(a[..., 0]).save(plain)
+    t2 = fct_misc.open_tile(plain)
+    assert t2["data"].shape == (16, 24, 1) and t2["nodata"] is None and t2["transform"][0] == 1.0
