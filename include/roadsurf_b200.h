@@ -10,7 +10,7 @@
  *  - every function returns an int status (RS_OK == 0, negative = error); nothing throws;
  *  - "_dev" entry points take DEVICE pointers, enqueue on `stream` (a cudaStream_t passed as
  *    void*, NULL = default stream) and return without synchronising; kernel-side failures
- *    (capacity overflow ...) are latched in the context and read with rs_ctx_sync_status();
+ *    (a rotated tile transform ...) are latched in the context and read with rs_ctx_sync_status();
  *  - "_host" entry points take HOST pointers, do their own host<->device copies and return
  *    after the results are in the host buffers;
  *  - the caller owns every input and output buffer; the library only owns its context.
@@ -46,7 +46,7 @@ enum rs_status {
     RS_ERR_CAPACITY = -3,      /* reserved (the bit-mask fill has no per-scanline crossing limit)  */
     RS_ERR_ROTATED = -4,       /* a tile transform has b != 0 or d != 0                           */
     RS_ERR_NO_DEVICE = -5,     /* no CUDA device / device is not sm_100                           */
-    RS_ERR_UNSUPPORTED = -6    /* width > 4096, channels not in 1..4, dtype/channels combination  */
+    RS_ERR_UNSUPPORTED = -6    /* width > 2048, channels not in 1..4, dtype/channels combination  */
 };
 
 enum rs_dtype { RS_U8 = 0, RS_U16 = 1 };
@@ -143,7 +143,9 @@ int rs_road_bbox_dev(rs_ctx *ctx, const rs_roads *roads, double *road_bbox_out, 
  * hist      uint32[n_slots][HC][256], HC = channels (RS_HIST_BANDS) or 3 (RS_HIST_CLASS_SCORE)
  * n_allzero uint32[n_slots]: in-mask pixels whose bands are all 0
  * Every road's slot is written exactly once (zeros if the road has no pixels): outputs need
- * no clearing.  Integer outputs are bit-exact and independent of scheduling.
+ * no clearing (road_slot, when given, must be injective).  Integer outputs are bit-exact and independent of
+ * scheduling.  Limits: tile width <= 2048 pixels, any height; 64/128-bit pixel loads need width % 8 == 0 and a
+ * 16-byte aligned pixel base (other shapes take a byte-wise path).
  */
 int rs_zonal_hist_dev(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                       const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, void *stream);
