@@ -268,6 +268,16 @@ int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, co
                        const rs_lattice *lattice, int32_t *road_pair_off, int32_t *pair_tile, int64_t capacity, int64_t *n_pairs);
 
 /*
+ * Two-sample Kolmogorov-Smirnov statistic of every road's pixel values on one band against a reference distribution,
+ * from histograms: scipy.stats.kstest(road_values, general_values) of statistical_analysis.py:441-451 (the pixels of the
+ * road against all pixels of its road type).  hist uint32[n_roads][256] (one band), ref_hist uint64[n_refs][256],
+ * ref_of_road int32[n_roads] (NULL = reference 0; negative = skip, D = NaN).  D double[n_roads], n double[n_roads]
+ * (sample size of the road, for the p-value: scipy evaluates kstwo.sf(D, round(m n / (m + n))) for large samples).
+ */
+int rs_ks_hist_host(rs_ctx *ctx, const uint32_t *hist, const int32_t *ref_of_road, const uint64_t *ref_hist, int32_t n_roads,
+                    int32_t n_refs, double *D, double *n);
+
+/*
  * 16 -> 8 bit rescale as a materialising pass: gdal.Translate(outputType=GDT_Byte, scaleParams=[[smin, smax, 0, 255]...])
  * (scripts/preprocessing/tif2cog.py:260-270) plus the band selection of the tile URL (config/config_stats.yaml:39).
  * dst[px][c] = byte(clamp(src[px][bidx[c]] * k[c] + off[c], 0, 255) + 0.5); k / off / bidx (NULL = identity) are host

@@ -32,7 +32,7 @@ EXPORTS = (
     "rs_zonal_hist_host", "rs_zonal_stats_host", "rs_zonal_stats_stream_host", "rs_rasterize_pairs_dev", "rs_rasterize_pairs_host", "rs_finalize_stats_dev",
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
     "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
-    "rs_pairs_bbox_host", "rs_rescale_u16_dev", "rs_rescale_u16_host",
+    "rs_pairs_bbox_host", "rs_rescale_u16_dev", "rs_rescale_u16_host", "rs_ks_hist_host",
 )
 
 
@@ -118,6 +118,7 @@ def load():
     L.rs_vote_table_host.argtypes = [P, P, P, P, P, P, C.c_int32, P, C.c_int32, P, P]
     L.rs_confusion_metrics_host.argtypes = [P, P, P, C.c_int32, C.c_int32, P, P]
     L.rs_pairs_bbox_host.argtypes = [P, P, C.c_int32, P, C.c_int32, C.POINTER(RsLattice), P, P, C.c_int64, C.POINTER(C.c_int64)]
+    L.rs_ks_hist_host.argtypes = [P, P, P, P, C.c_int32, C.c_int32, P, P]
     L.rs_rescale_u16_dev.argtypes = [P, P, C.c_int64, C.c_int32, C.c_int32, P, P, P, C.c_int32, P, P]
     L.rs_rescale_u16_host.argtypes = L.rs_rescale_u16_dev.argtypes[:-1]
     L.rs_synth_tiles_dev.argtypes = [P, P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

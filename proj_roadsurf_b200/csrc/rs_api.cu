@@ -559,6 +559,31 @@ int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, co
     return finish(ctx);
 }
 
+int rs_ks_hist_host(rs_ctx *ctx, const uint32_t *hist, const int32_t *ref_of_road, const uint64_t *ref_hist, int32_t n_roads,
+                    int32_t n_refs, double *D, double *n)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_roads < 0 || n_refs < 1 || !ref_hist || (n_roads > 0 && (!hist || !D))) return RS_ERR_INVALID_ARG;
+    if (n_roads == 0) return RS_OK;
+    const size_t R = (size_t)n_roads;
+    if (ref_of_road)
+        for (size_t i = 0; i < R; i++)
+            if (ref_of_road[i] >= n_refs) return RS_ERR_INVALID_ARG;
+    if ((rc = up(ctx, ctx->stage[9], hist, sizeof(uint32_t) * 256 * R))) return rc;
+    if ((rc = up(ctx, ctx->stage[10], ref_hist, sizeof(uint64_t) * 256 * (size_t)n_refs))) return rc;
+    if (ref_of_road && (rc = up(ctx, ctx->stage[8], ref_of_road, sizeof(int32_t) * R))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], sizeof(double) * R))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[12], sizeof(double) * R))) return rc;
+    if ((rc = launch_ks(ctx, (const uint32_t *)ctx->stage[9].p, ref_of_road ? (const int *)ctx->stage[8].p : nullptr,
+                        (const unsigned long long *)ctx->stage[10].p, n_roads, 256, (double *)ctx->stage[11].p,
+                        (double *)ctx->stage[12].p, ctx->host_stream)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(D, ctx->stage[11].p, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->host_stream));
+    if (n) RS_CUDA_OK(ctx, cudaMemcpyAsync(n, ctx->stage[12].p, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
 int rs_rescale_u16_dev(rs_ctx *ctx, const uint16_t *src, int64_t n_pixels, int32_t c_in, int32_t c_out, const int32_t *bidx,
                        const double *k, const double *off, int32_t f32, uint8_t *dst, void *stream)
 {

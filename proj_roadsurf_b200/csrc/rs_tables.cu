@@ -338,6 +338,59 @@ int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class,
 }
 
 // ---------------------------------------------------------------------------------------------
+// two-sample Kolmogorov-Smirnov D of each road's pixel values against a reference distribution, from
+// histograms (scripts/statistical_analysis/statistical_analysis.py:441-451 kstest(road_values, general_values)):
+// D = max_v | F_road(v) - F_ref(v) | over the 256 values, exact for integer data.  One warp per road.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ks_kernel(const uint32_t *__restrict__ hist, const int *__restrict__ ref_of_road,
+                                                 const unsigned long long *__restrict__ ref_hist, int n_roads, int stride,
+                                                 double *__restrict__ d_out, double *__restrict__ n_out)
+{
+    const int road = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (road >= n_roads) return;
+    const uint32_t *h = hist + (size_t)road * stride;
+    const int ri = ref_of_road ? ref_of_road[road] : 0;
+    const u64 *g = ref_hist + (size_t)(ri < 0 ? 0 : ri) * 256;
+    u64 a[8], b[8], sa = 0, sb = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { a[j] = h[8 * lane + j]; b[j] = g[8 * lane + j]; sa += a[j]; sb += b[j]; }
+    u64 ia = sa, ib = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+    }
+    const u64 na = __shfl_sync(0xffffffffu, ia, 31), nb = __shfl_sync(0xffffffffu, ib, 31);
+    double d = 0.0;
+    if (na > 0 && nb > 0 && ri >= 0) {
+        u64 ca = ia - sa, cb = ib - sb;
+        const double da = (double)na, db = (double)nb;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            ca += a[j]; cb += b[j];
+            d = fmax(d, fabs((double)ca / da - (double)cb / db));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if (lane == 0) {
+        d_out[road] = (na > 0 && nb > 0 && ri >= 0) ? d : __longlong_as_double(0x7ff8000000000000ll);
+        if (n_out) n_out[road] = (double)na;
+    }
+}
+
+int launch_ks(rs_ctx *ctx, const uint32_t *hist, const int *ref_of_road, const unsigned long long *ref_hist, int n_roads, int stride,
+              double *d_out, double *n_out, cudaStream_t st)
+{
+    if (n_roads <= 0) return RS_OK;
+    const unsigned blocks = (unsigned)(((size_t)n_roads * 32 + 255) / 256);
+    ks_kernel<<<blocks, 256, 0, st>>>(hist, ref_of_road, ref_hist, n_roads, stride, d_out, n_out);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // 16 -> 8 bit rescale as a materialising pass: gdal.Translate(outputType=GDT_Byte, scaleParams=...)
 // (scripts/preprocessing/tif2cog.py:260-270), with the band selection of the tile URL
 // (config/config_stats.yaml:39, bidx=2&bidx=3&bidx=4&bidx=1).  HBM-bound: 2*C_in bytes read + C_out written per pixel.

@@ -305,6 +305,17 @@ class Engine:
         N.check(st, "rs_rescale_u16_dev", self._ctx)
         return out
 
+    def ks_hist_host(self, hist: np.ndarray, ref_hist: np.ndarray, ref_of_road: Optional[np.ndarray] = None):
+        """KS D of every road's (R, 256) histogram against ref_hist (n_refs, 256) (rs_ks_hist_host).  Returns D (R,), n (R,)."""
+        h = np.ascontiguousarray(hist, np.uint32)
+        ref = np.ascontiguousarray(np.atleast_2d(ref_hist), np.uint64)
+        ror = None if ref_of_road is None else np.ascontiguousarray(ref_of_road, np.int32)
+        R = h.shape[0]
+        D, n = np.zeros(R, np.float64), np.zeros(R, np.float64)
+        st = self.lib.rs_ks_hist_host(self._ctx, _np_ptr(h), _np_ptr(ror), _np_ptr(ref), R, ref.shape[0], _np_ptr(D), _np_ptr(n))
+        N.check(st, "rs_ks_hist_host", self._ctx)
+        return D, n
+
     def group_hist_host(self, values: np.ndarray, group: np.ndarray, n_groups: int) -> np.ndarray:
         """(n_groups, 256) uint32 histograms of a uint8 column by group index (rs_group_hist_host)."""
         v = np.ascontiguousarray(values, np.uint8)

@@ -109,3 +109,24 @@ def filter_roads(roads_stats_df: pd.DataFrame, BANDS: Sequence[int], COUNT_THRES
         ok |= (roads_stats_df[f'margin_{b}'] < MAX_MOE).to_numpy()
     keep = (roads_stats_df['count'] > COUNT_THRESHOLD).to_numpy() & ok
     return roads_stats_df[keep].drop(columns=[f'margin_{b}' for b in BANDS] + ['count'])
+
+
+def ks_test_from_hists(hist_band: np.ndarray, road_type: Sequence, engine=None) -> pd.DataFrame:
+    """statistical_analysis.py:441-461 without the pixel table: for every road, scipy.stats.kstest(pixels of the road,
+    all pixels of the road's type) on one band.  hist_band (R, 256): per-road histogram of the band (what
+    get_pixel_values would have returned for the road); road_type (R,): cover of each road.  The reference compares a
+    road with the pooled pixels of its type, the road itself included.  Returns columns ks_D (round 3) and ks_p
+    ('{:0.3e}'-rounded), D exact from the histograms, p from scipy's large-sample branch
+    kstwo.sf(D, round(m n / (m + n))) (ks_2samp mode 'asymp', which 'auto' takes when a sample exceeds 10 000)."""
+    from scipy.stats import distributions
+    eng = engine or default_engine()
+    h = np.ascontiguousarray(hist_band, np.uint32)
+    types, code = np.unique(np.asarray(road_type), return_inverse=True)
+    ref = np.zeros((len(types), 256), np.uint64)
+    np.add.at(ref, code, h.astype(np.uint64))
+    D, m = eng.ks_hist_host(h, ref, code.astype(np.int32))
+    n = ref.sum(axis=1).astype(np.float64)[code]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        en = np.round(m * n / (m + n))
+    p = np.array([distributions.kstwo.sf(d, e) if e >= 1 and d == d else np.nan for d, e in zip(D, en)])
+    return pd.DataFrame({"ks_D": np.round(D, 3), "ks_p": [float("{:0.3e}".format(v)) if v == v else np.nan for v in p]})

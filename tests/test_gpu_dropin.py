@@ -360,3 +360,24 @@ def test_get_pixel_values_from_a_geotiff_file(mods, tmp_path):
                 continue
             one = fct_misc.get_pixel_values(g["geoms"][case["geom"]], path, range(1, 4), pd.DataFrame(), road_id=case["geom"])
             assert_frame_matches(case["result"], one)
+
+
+def test_ks_from_histograms_matches_scipy(mods):
+    from scipy import stats as sstats
+    fs = mods[1]
+    rng = np.random.default_rng(17)
+    R = 12
+    hist = np.zeros((R, 256), np.uint32)
+    samples = []
+    for r in range(R):
+        n = int(rng.integers(30, 4000))
+        v = np.clip(np.rint(rng.normal(100 + 6 * (r % 3), 5 + r, n)), 0, 255).astype(np.int64)
+        samples.append(v)
+        hist[r] = np.bincount(v, minlength=256)
+    road_type = np.array([100, 200] * 6)
+    got = fs.ks_test_from_hists(hist, road_type)
+    for r in range(R):
+        pooled = np.concatenate([samples[i] for i in range(R) if road_type[i] == road_type[r]])
+        ref = sstats.ks_2samp(samples[r], pooled, method="asymp")
+        assert abs(got["ks_D"][r] - round(float(ref.statistic), 3)) < 1e-12
+        assert abs(got["ks_p"][r] - float("{:0.3e}".format(ref.pvalue))) <= 1e-6 * max(ref.pvalue, 1e-300) + 1e-300
