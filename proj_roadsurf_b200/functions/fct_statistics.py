@@ -130,3 +130,41 @@ def ks_test_from_hists(hist_band: np.ndarray, road_type: Sequence, engine=None) 
         en = np.round(m * n / (m + n))
     p = np.array([distributions.kstwo.sf(d, e) if e >= 1 and d == d else np.nan for d, e in zip(D, en)])
     return pd.DataFrame({"ks_D": np.round(D, 3), "ks_p": [float("{:0.3e}".format(v)) if v == v else np.nan for v in p]})
+
+
+def cover_stats_from_accumulators(hist: np.ndarray, n_allzero: np.ndarray, road_type: Sequence, BANDS: Sequence[int] = (1, 2, 3),
+                                  nodata_mode: str = "none", engine=None) -> pd.DataFrame:
+    """statistical_analysis.py:296-316 from the per-road accumulators: the statistics of all pixels of each road type
+    (cover) per band -- what get_df_stats_no_group returns on ``pixels_per_band[road_type == cover]`` -- with the
+    reference's rounding (mean / std to 2 decimals and margin to 3 inside get_df_stats_no_group, then 1 decimal in the
+    table, :314-316).  hist (R, C, 256), n_allzero (R,), road_type (R,)."""
+    eng = engine or default_engine()
+    h = np.asarray(hist)
+    types, code = np.unique(np.asarray(road_type), return_inverse=True)
+    pooled = np.zeros((len(types),) + h.shape[1:], np.uint64)
+    np.add.at(pooled, code, h.astype(np.uint64))
+    nz = np.zeros(len(types), np.uint64)
+    np.add.at(nz, code, np.asarray(n_allzero, np.uint64))
+    if pooled.max(initial=0) >= 2 ** 32:
+        raise OverflowError("a pooled histogram bin exceeds 32 bits")
+    st = eng.finalize_stats_host(pooled.astype(np.uint32), nz.astype(np.uint32), nodata_mode=nodata_mode, ddof=1)
+    rows = {'cover': [], 'band': [], 'min': [], 'max': [], 'mean': [], 'median': [], 'std': [], 'margin': [], 'count': []}
+    for ti, cover in enumerate(types):
+        for ci, b in enumerate(BANDS):
+            s_ = st[ti, b - 1]
+            std2 = np.float64(s_[_COL['std']]).round(2)
+            n = int(s_[_COL['count']])
+            rows['cover'].append(cover)
+            rows['band'].append(b)
+            rows['min'].append(int(s_[_COL['min']]))
+            rows['max'].append(int(s_[_COL['max']]))
+            rows['mean'].append(np.float64(s_[_COL['mean']]).round(2))
+            rows['median'].append(float(s_[_COL['median']]))
+            rows['std'].append(std2)
+            rows['count'].append(n)
+            rows['margin'].append(np.round(Z * std2 / (n ** (1 / 2)), decimals=3))
+    df = pd.DataFrame(rows)
+    df['mean'] = df['mean'].round(1)
+    df['std'] = df['std'].round(1)
+    df['margin'] = df['margin'].round(1)
+    return df

@@ -381,3 +381,32 @@ def test_ks_from_histograms_matches_scipy(mods):
         ref = sstats.ks_2samp(samples[r], pooled, method="asymp")
         assert abs(got["ks_D"][r] - round(float(ref.statistic), 3)) < 1e-12
         assert abs(got["ks_p"][r] - float("{:0.3e}".format(ref.pvalue))) <= 1e-6 * max(ref.pvalue, 1e-300) + 1e-300
+
+
+def test_cover_stats_from_accumulators(mods):
+    fct_misc, fs = mods[0], mods[1]
+    from proj_roadsurf_b200.engine import default_engine
+    g = synth.Grid(3, 3)
+    rr = synth.ribbon_roads(g, 9, seed=5)
+    tiles = synth.host_tiles(g, 3, "asphalt")
+    tb = TileBatch.from_arrays(tiles, g.transforms())
+    hist, nz = default_engine().zonal_hist_host(rr.roads, tb, rr.pairs)
+    road_type = np.array([100, 200, 100, 100, 200, 100, 200, 100, 100])
+    got = fs.cover_stats_from_accumulators(hist, nz, road_type, (1, 2, 3))
+    # reference shape: pixel table -> get_df_stats_no_group per (cover, band), statistical_analysis.py:296-316
+    pix = fct_misc.get_pixel_values_batch(rr.roads, tb, rr.pairs, range(1, 4))
+    pix["road_type"] = road_type[pix["road_id"].to_numpy()]
+    cover_stats = {'cover': [], 'band': [], 'min': [], 'max': [], 'mean': [], 'median': [], 'std': [], 'margin': [], 'count': []}
+    for cover in sorted(pix["road_type"].unique().tolist()):
+        for b in (1, 2, 3):
+            sub = pix[pix["road_type"] == cover]
+            cover_stats['cover'].append(cover)
+            cover_stats['band'].append(b)
+            cover_stats = ostats.get_df_stats_no_group(sub, f"band{b}", cover_stats)
+    exp = pd.DataFrame(cover_stats)
+    exp['mean'] = exp['mean'].round(1); exp['std'] = exp['std'].round(1); exp['margin'] = exp['margin'].round(1)
+    assert got["cover"].tolist() == exp["cover"].tolist() and got["band"].tolist() == exp["band"].tolist()
+    for c in ("min", "max", "median", "count"):
+        assert got[c].tolist() == exp[c].tolist(), c
+    for c in ("mean", "std", "margin"):
+        assert np.all(np.abs(got[c].to_numpy(float) - exp[c].to_numpy(float)) <= 0.1000001), c
