@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--e2e-rows", type=int, default=0, help="tile rows of each rank's shard in the host-buffer (e2e) leg; 0 = the whole "
                     "shard when half of the free host memory per rank can hold it pinned")
     ap.add_argument("--e2e-chunk", type=int, default=8192, help="tiles per streamed chunk of the e2e leg")
+    ap.add_argument("--e2e-mode", default="both", choices=["both", "stream", "mapped"], help="host-buffer transport(s) to time; the "
+                    "faster one is reported as e2e")
     ap.add_argument("--cpu-rows", type=int, default=32, help="tile rows of the CPU baseline sample")
     ap.add_argument("--extras", action="store_true", help="also time the class/score (config 2) and uint16 rescale (config 3) kernels")
     ap.add_argument("--no-e2e", action="store_true")
@@ -294,23 +296,42 @@ def run_b200(args):
         torch.cuda.synchronize()
         tb = TileBatch(host_px.numpy(), gt[:n_sub], H, W, C)
         chunk = min(args.e2e_chunk, n_sub)
-        eng.zonal_stats_host(roads_s, tb, pairs_s, tiles_per_chunk=chunk)          # warm-up (allocates the staging buffers)
-        n_e2e = 3
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            st_host = eng.zonal_stats_host(roads_s, tb, pairs_s, tiles_per_chunk=chunk)
-        t1 = time.perf_counter()
-        et = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        h2d = host_px.numel() + roads_s.xy.nbytes + roads_s.bbox.nbytes + roads_s.ring_off.nbytes + \
-            roads_s.road_ring_off.nbytes + pairs_s.road_pair_off.nbytes + pairs_s.pair_tile.nbytes + gt[:n_sub].nbytes
-        e2e = {"value": world * n_sub * H * W * n_e2e / float(et.item()) / 1e9, "unit": "Gpixel/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(st_host.nbytes), "steps": n_e2e,
-               "sample": f"first {rows} of {args.tiles_y} tile rows of each rank's shard ({n_sub} tiles, {roads_s.n_roads} roads) from pinned "
-                         f"host memory through rs_zonal_stats_stream_host ({chunk}-tile chunks, copy overlapped with compute); "
-                         "statistics table read back"}
+        h2d_meta = roads_s.xy.nbytes + roads_s.bbox.nbytes + roads_s.ring_off.nbytes + roads_s.road_ring_off.nbytes + \
+            pairs_s.road_pair_off.nbytes + pairs_s.pair_tile.nbytes + gt[:n_sub].nbytes
+        modes = {"stream": dict(tiles_per_chunk=chunk), "mapped": dict(mapped=True)}
+        if args.e2e_mode != "both":
+            modes = {args.e2e_mode: modes[args.e2e_mode]}
+        n_e2e, legs, st_ref = 3, {}, None
+        for name, kw in modes.items():
+            eng.zonal_stats_host(roads_s, tb, pairs_s, **kw)                       # warm-up (allocates the staging buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                st_host = eng.zonal_stats_host(roads_s, tb, pairs_s, **kw)
+            t1 = time.perf_counter()
+            et = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            legs[name] = world * n_sub * H * W * n_e2e / float(et.item()) / 1e9
+            if st_ref is None:
+                st_ref = st_host
+            elif not np.array_equal(st_ref, st_host, equal_nan=True):
+                raise SystemExit("e2e transports disagree")
+        best = max(legs, key=legs.get)
+        # bytes that cross the host link per step: every tile byte when streamed; when the kernel reads the page-locked tiles
+        # in place, the sectors it touches (profiles/traffic.json holds the ncu DRAM figure of the same launch, used as estimate)
+        h2d_px = host_px.numel() if best == "stream" else None
+        how = {"stream": f"rs_zonal_stats_stream_host ({chunk}-tile chunks through two device buffers, copy overlapped with compute)",
+               "mapped": "rs_zonal_stats_mapped_host (zonal_kernel reads the page-locked tiles in place; only the sectors under "
+                         "road pixels cross the host link)"}[best]
+        if h2d_px is None:
+            frac = (traffic / alg_bytes) if (traffic and n_sub == n_tiles) else 1.0
+            h2d_px = int(host_px.numel() * min(1.0, frac))
+        e2e = {"value": legs[best], "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d_px + h2d_meta),
+               "d2h_bytes_per_step": int(st_host.nbytes), "steps": n_e2e, "transport": best,
+               "transports_Gpixel_s": legs, "host_tile_bytes": int(host_px.numel()),
+               "sample": f"first {rows} of {args.tiles_y} tile rows of each rank's shard ({n_sub} tiles, {roads_s.n_roads} roads) in pinned "
+                         f"host memory through {how}; statistics table read back"}
         del host_px
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the same sample ----

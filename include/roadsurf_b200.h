@@ -46,7 +46,8 @@ enum rs_status {
     RS_ERR_CAPACITY = -3,      /* reserved (the bit-mask fill has no per-scanline crossing limit)  */
     RS_ERR_ROTATED = -4,       /* a tile transform has b != 0 or d != 0                           */
     RS_ERR_NO_DEVICE = -5,     /* no CUDA device / device is not sm_100                           */
-    RS_ERR_UNSUPPORTED = -6    /* width > 2048, channels not in 1..4, dtype/channels combination  */
+    RS_ERR_UNSUPPORTED = -6,   /* width > 2048, channels not in 1..4, dtype/channels combination  */
+    RS_ERR_NOT_PINNED = -7     /* rs_zonal_stats_mapped_host: tiles->pixels is not page-locked    */
 };
 
 enum rs_dtype { RS_U8 = 0, RS_U16 = 1 };
@@ -161,6 +162,16 @@ int rs_zonal_hist_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
 int rs_zonal_stats_stream_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                                const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
                                int32_t n_pct, int32_t tiles_per_chunk, double *stats, uint32_t *hist, uint32_t *n_allzero);
+
+/*
+ * rs_zonal_stats_host without a copy of the tiles: tiles->pixels must be page-locked host memory (cudaHostAlloc /
+ * cudaHostRegister, else RS_ERR_NOT_PINNED) and zonal_kernel reads it in place through the unified address space.
+ * The kernel is span-driven, so only the 32-byte sectors under road pixels cross the host link instead of every tile
+ * byte.  Same arguments and results as rs_zonal_stats_host.
+ */
+int rs_zonal_stats_mapped_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                               const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
+                               int32_t n_pct, double *stats, uint32_t *hist, uint32_t *n_allzero);
 
 /*
  * Pixel masks.  Replaces rasterio.features.rasterize (scripts/sandbox/add_tile_mask.py:112-113,

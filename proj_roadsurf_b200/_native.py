@@ -13,7 +13,7 @@ from . import _build
 RS_OK = 0
 STATUS = {
     0: "RS_OK", -1: "RS_ERR_INVALID_ARG", -2: "RS_ERR_CUDA", -3: "RS_ERR_CAPACITY",
-    -4: "RS_ERR_ROTATED", -5: "RS_ERR_NO_DEVICE", -6: "RS_ERR_UNSUPPORTED",
+    -4: "RS_ERR_ROTATED", -5: "RS_ERR_NO_DEVICE", -6: "RS_ERR_UNSUPPORTED", -7: "RS_ERR_NOT_PINNED",
 }
 RS_U8, RS_U16 = 0, 1
 RS_HIST_BANDS, RS_HIST_CLASS_SCORE = 0, 1
@@ -29,7 +29,7 @@ RS_VOTE_COUNT, RS_VOTE_SCORE = 0, 1
 EXPORTS = (
     "rs_version", "rs_status_string", "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_sync_status",
     "rs_ctx_last_cuda_error", "rs_ctx_launch_count", "rs_road_bbox_dev", "rs_zonal_hist_dev",
-    "rs_zonal_hist_host", "rs_zonal_stats_host", "rs_zonal_stats_stream_host", "rs_rasterize_pairs_dev", "rs_rasterize_pairs_host", "rs_finalize_stats_dev",
+    "rs_zonal_hist_host", "rs_zonal_stats_host", "rs_zonal_stats_stream_host", "rs_zonal_stats_mapped_host", "rs_rasterize_pairs_dev", "rs_rasterize_pairs_host", "rs_finalize_stats_dev",
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
     "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
     "rs_pairs_bbox_host", "rs_rescale_u16_dev", "rs_rescale_u16_host", "rs_ks_hist_host",
@@ -106,6 +106,7 @@ def load():
                                       C.POINTER(RsZonalParams), C.c_int32, C.c_int32, P, C.c_int32, P, P, P]
     L.rs_zonal_stats_stream_host.argtypes = [P, C.POINTER(RsRoads), C.POINTER(RsTiles), C.POINTER(RsPairs),
                                              C.POINTER(RsZonalParams), C.c_int32, C.c_int32, P, C.c_int32, C.c_int32, P, P, P]
+    L.rs_zonal_stats_mapped_host.argtypes = L.rs_zonal_stats_host.argtypes
     L.rs_rasterize_pairs_dev.argtypes = [P, C.POINTER(RsRoads), C.POINTER(RsTiles), C.POINTER(RsPairs), C.c_int, P, P]
     L.rs_rasterize_pairs_host.argtypes = L.rs_rasterize_pairs_dev.argtypes[:-1]
     L.rs_finalize_stats_dev.argtypes = [P, P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, C.c_int32, P, P]

@@ -111,6 +111,7 @@ const char *rs_status_string(int status)
         case RS_ERR_ROTATED: return "rotated tile transform is not supported on this path";
         case RS_ERR_NO_DEVICE: return "no sm_100 CUDA device";
         case RS_ERR_UNSUPPORTED: return "unsupported tile shape or dtype";
+        case RS_ERR_NOT_PINNED: return "the tile buffer is not page-locked host memory";
         default: return "unknown status";
     }
 }
@@ -329,6 +330,46 @@ int rs_zonal_stats_stream_host(rs_ctx *ctx, const rs_roads *roads, const rs_tile
         if (rc) return rc;
         RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_used[b], st));
     }
+    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, (const uint32_t *)ctx->stage[10].p, R, C, nodata_mode, ddof,
+                         percentiles, n_pct, (double *)ctx->stage[11].p, st);
+    if (rc) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[11].p, sb, cudaMemcpyDeviceToHost, st));
+    if (hist) RS_CUDA_OK(ctx, cudaMemcpyAsync(hist, ctx->stage[9].p, hb, cudaMemcpyDeviceToHost, st));
+    if (n_allzero) RS_CUDA_OK(ctx, cudaMemcpyAsync(n_allzero, ctx->stage[10].p, zb, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
+int rs_zonal_stats_mapped_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                               const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
+                               int32_t n_pct, double *stats, uint32_t *hist, uint32_t *n_allzero)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!prm || !stats || prm->road_slot || n_pct < 0 || n_pct > 16) return RS_ERR_INVALID_ARG;
+    if (prm->hist_mode != RS_HIST_BANDS) return RS_ERR_INVALID_ARG;
+    rs_roads dr;
+    rs_tiles dt;
+    rs_pairs dp;
+    if ((rc = stage_inputs(ctx, roads, tiles, pairs, false, dr, dt, dp))) return rc;     // geometry + pairs + transforms, no pixels
+    if (tiles->n_tiles > 0 && !tiles->pixels) return RS_ERR_INVALID_ARG;
+    const int R = roads->n_roads, C = tiles->channels;
+    if (R == 0) return RS_OK;
+    // the tiles must be page-locked (cudaHostAlloc / cudaHostRegister): the kernel reads them in place over PCIe / C2C
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, tiles->pixels) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+        cudaGetLastError();
+        return RS_ERR_NOT_PINNED;
+    }
+    dt.pixels = attr.devicePointer;
+    const size_t hb = sizeof(uint32_t) * 256 * (size_t)C * R, zb = sizeof(uint32_t) * (size_t)R;
+    const size_t sb = sizeof(double) * (size_t)(RS_NSTAT + n_pct) * C * R;
+    if ((rc = ensure(ctx, ctx->stage[9], hb))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], sb))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    rc = launch_zonal(ctx, &dr, &dt, &dp, prm, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
+                      prm->window_mode, st);
+    if (rc) return rc;
     rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, (const uint32_t *)ctx->stage[10].p, R, C, nodata_mode, ddof,
                          percentiles, n_pct, (double *)ctx->stage[11].p, st);
     if (rc) return rc;

@@ -147,7 +147,8 @@ class Engine:
 
     def zonal_stats_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, window: str = "crop", rescale=None,
                          nodata_mode: str = "none", ddof: int = 1, percentiles: Sequence[float] = (),
-                         want_hist: bool = False, tiles_per_chunk: Optional[int] = None):
+                         want_hist: bool = False, tiles_per_chunk: Optional[int] = None,
+                         mapped: bool = False):
         """Host buffers in, statistics table out, in ONE C call (rs_zonal_stats_host): the batched form of
         statistical_analysis.py:179-246.  Returns stats (R, C, RS_NSTAT + n_pct) [, hist, n_allzero]."""
         px = np.ascontiguousarray(tiles.pixels) if isinstance(tiles.pixels, np.ndarray) else tiles.pixels
@@ -166,7 +167,11 @@ class Engine:
         td = N.RsTiles(_np_ptr(px), _np_ptr(gt), tiles.n_tiles, tiles.height, tiles.width, tiles.channels, dtype)
         pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
         prm = self._params("bands", window, rescale, None)
-        if tiles_per_chunk is None:
+        if mapped:  # page-locked tiles read in place by the kernel (only the sectors under road pixels cross the host link)
+            st = self.lib.rs_zonal_stats_mapped_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
+                                                     _NODATA_MODES[nodata_mode], int(ddof), _np_ptr(pct) if len(pct) else None,
+                                                     len(pct), _np_ptr(stats), _np_ptr(hist), _np_ptr(nzero))
+        elif tiles_per_chunk is None:
             st = self.lib.rs_zonal_stats_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
                                               _NODATA_MODES[nodata_mode], int(ddof), _np_ptr(pct) if len(pct) else None,
                                               len(pct), _np_ptr(stats), _np_ptr(hist), _np_ptr(nzero))

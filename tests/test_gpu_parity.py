@@ -638,3 +638,21 @@ def test_streaming_from_host_equals_resident(eng):
         assert np.array_equal(got[0], ref[0], equal_nan=True), per
     oh, _ = oracle_hist(rr.roads, rr.pairs, tiles, g.transforms())
     assert np.array_equal(ref[1].astype(np.uint64), oh)
+
+
+def test_mapped_host_tiles_equal_resident(eng):
+    """rs_zonal_stats_mapped_host: the kernel reads page-locked host tiles in place; pageable memory is refused"""
+    import torch
+    from proj_roadsurf_b200 import _native as N
+    g = synth.Grid(7, 5)
+    rr = synth.ribbon_roads(g, 40, seed=82)
+    tiles = synth.host_tiles(g, 3)
+    ref = eng.zonal_stats_host(rr.roads, TileBatch.from_arrays(tiles, g.transforms()), rr.pairs, percentiles=(25.0,), want_hist=True)
+    pinned = torch.empty(tiles.shape, dtype=torch.uint8, pin_memory=True)
+    pinned.copy_(torch.from_numpy(tiles))
+    tb = TileBatch(pinned.numpy(), g.transforms(), tiles.shape[1], tiles.shape[2], tiles.shape[3])
+    got = eng.zonal_stats_host(rr.roads, tb, rr.pairs, percentiles=(25.0,), want_hist=True, mapped=True)
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+    assert np.array_equal(got[0], ref[0], equal_nan=True)
+    with pytest.raises(Exception, match="RS_ERR_NOT_PINNED"):
+        eng.zonal_stats_host(rr.roads, TileBatch.from_arrays(tiles.copy(), g.transforms()), rr.pairs, mapped=True)
