@@ -236,6 +236,28 @@ int rs_extract_pixels_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *t
                            int window_mode, int64_t *pair_off, void *values, int64_t capacity_pixels, int64_t *n_total);
 
 /*
+ * Per-pixel derived columns of scripts/statistical_analysis/statistical_analysis.py:279-293 on the uint8 pixel table
+ * values[n][channels] (bands 1..channels): the ratios band_a / band_b for a < b in the reference's loop order
+ * (1/2, 1/3, 1/4, 2/3, 2/4, 3/4 = R/G, R/B, R/NIR, G/B, G/NIR, B/NIR), float64, rounded to 3 decimals the numpy way,
+ * NaN -> 0 then inf -> 1; with 4 bands one more column VgNIR-BI = (band2 - band4) / (band2 + band4) rounded to 5
+ * decimals (0/0 stays NaN, as in the reference).  out is column-major double[rs_band_ratio_columns(channels)][n]
+ * (a DataFrame column each).  channels in 2..4.
+ */
+int rs_band_ratio_columns(int32_t channels);
+int rs_band_ratios_dev(rs_ctx *ctx, const uint8_t *values, int64_t n, int32_t channels, double *out, void *stream);
+int rs_band_ratios_host(rs_ctx *ctx, const uint8_t *values, int64_t n, int32_t channels, double *out);
+
+/*
+ * Calibration bins of scripts/road_segmentation/final_metrics.py:541-571: for every group g (gt_type), value column k
+ * and threshold t, counts[g][k][t] = { rows with sel[k][r] != 0 and lo[t] < values[k][r] <= hi[t],  those of them with
+ * hit[k][r] != 0 }; the bin accuracy is their quotient where the first is non-zero.  values double[n_cols][n],
+ * sel / hit int8[n_cols][n], group int32[n] in [0, n_groups) (other rows skipped), counts int64[n_groups][n_cols][n_thr][2].
+ * The reference's bounds are lo = threshold - 0.5, hi = threshold (the 0.5 is the reference's, :557).
+ */
+int rs_bin_counts_host(rs_ctx *ctx, const double *values, const int8_t *sel, const int8_t *hit, const int32_t *group, int32_t n,
+                       int32_t n_cols, int32_t n_groups, const double *lo, const double *hi, int32_t n_thr, int64_t *counts);
+
+/*
  * 256-bin histogram per group of a uint8 column: the groupby of fct_statistics.get_df_stats_groupby
  * (fct_statistics.py:55) / the single group of get_df_stats_no_group (:89-94); finalize with
  * rs_finalize_stats_*.  group int32[n] in [0, n_groups) (other values are skipped); hist uint32[n_groups][256].

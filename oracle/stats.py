@@ -200,3 +200,26 @@ def zonal_stats(vectors: Sequence[Sequence[np.ndarray]], raster: np.ndarray, aff
                 res[f"percentile_{q:g}"] = float(np.percentile(vals, q))
         out.append(res)
     return out
+
+
+RATIO_NAMES = {'1/2': 'R/G', '1/3': 'R/B', '1/4': 'R/NIR', '2/3': 'G/B', '2/4': 'G/NIR', '3/4': 'B/NIR'}
+
+
+def band_ratios(pixels_per_band: pd.DataFrame, BANDS: Sequence[int] = range(1, 5)) -> pd.DataFrame:
+    """scripts/statistical_analysis/statistical_analysis.py:279-293: ratios between bands (float64 division, round(3), NaN -> 0,
+    then non-finite -> 1) and VgNIR-BI = (band2 - band4) / (band2 + band4), round(5), NaN kept.  Same pandas statements,
+    on a copy."""
+    df = pixels_per_band.copy()
+    for band in BANDS:
+        for sec_band in range(band + 1, max(BANDS) + 1):
+            name = RATIO_NAMES[f'{band}/{sec_band}']
+            with np.errstate(divide='ignore', invalid='ignore'):
+                df[name] = df[f'band{band}'].astype('float64') / df[f'band{sec_band}'].astype('float64')
+            df[name] = df[name].round(3)
+            df.loc[np.isnan(df[name]), name] = 0
+            df.loc[~np.isfinite(df[name]), name] = 1
+    with np.errstate(divide='ignore', invalid='ignore'):
+        df['VgNIR-BI'] = (df['band2'].astype('float64') - df['band4'].astype('float64')) / (
+            df['band2'].astype('float64') + df['band4'].astype('float64'))
+    df['VgNIR-BI'] = df['VgNIR-BI'].round(5)
+    return df

@@ -227,3 +227,27 @@ def weighted_scores_raster(inside_masks, instance_tiles, road_of_pair, pair_tile
             rows.append({"OBJECTID": road_ids[r], "instance": i, "score": float(inst_score[i]), "det_class_name": inst_class_name[i],
                          "area_pred_in_label": frac, "weighted_score": frac * float(inst_score[i])})
     return pd.DataFrame(rows, columns=["OBJECTID", "instance", "score", "det_class_name", "area_pred_in_label", "weighted_score"])
+
+
+def bin_accuracy(best_comparison_df: pd.DataFrame) -> list:
+    """scripts/road_segmentation/final_metrics.py:541-571 (script body): calibration tables, one per (gt_type, parameter) --
+    roads of the parameter's CATEGORY with threshold - 0.5 < score <= threshold (sic, :557), accuracy = share of them whose
+    cover_type is the parameter's class; thresholds np.arange(0, 1.05, 0.05); empty bins are skipped."""
+    params = {'artificial': ['art_score', 'artificial', 'artifical score'],
+              'natural': ['nat_score', 'natural', 'natural score'],
+              'artificial_diff': ['diff_score', 'artificial', 'score diff in artificial roads'],
+              'naturall_diff': ['diff_score', 'natural', 'score diff in natural roads']}
+    out = []
+    for gt_type in best_comparison_df['gt_type'].unique():
+        sub = best_comparison_df[best_comparison_df['gt_type'] == gt_type]
+        for col, cls, label in params.values():
+            acc, thr = [], []
+            for threshold in np.arange(0, 1.05, 0.05):
+                in_bin = sub[(sub[col] > threshold - 0.5) & (sub[col] <= threshold) & (sub['CATEGORY'] == cls)]
+                if not in_bin.empty:
+                    acc.append(in_bin[in_bin['cover_type'] == cls].shape[0] / in_bin.shape[0])
+                    thr.append(threshold)
+            df = pd.DataFrame({'threshold': thr, 'accuracy': acc})
+            df.name = label + ' for ' + gt_type
+            out.append(df)
+    return out

@@ -520,6 +520,55 @@ int rs_group_hist_host(rs_ctx *ctx, const uint8_t *values, const int32_t *group,
     return finish(ctx);
 }
 
+int rs_band_ratio_columns(int32_t channels) { return channels < 2 || channels > 4 ? 0 : channels * (channels - 1) / 2 + (channels == 4); }
+
+int rs_band_ratios_dev(rs_ctx *ctx, const uint8_t *values, int64_t n, int32_t channels, double *out, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!values || !out))) return RS_ERR_INVALID_ARG;
+    return launch_band_ratios(ctx, values, n, channels, out, (cudaStream_t)stream);
+}
+
+int rs_band_ratios_host(rs_ctx *ctx, const uint8_t *values, int64_t n, int32_t channels, double *out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!values || !out))) return RS_ERR_INVALID_ARG;
+    const int K = rs_band_ratio_columns(channels);
+    if (K == 0) return RS_ERR_UNSUPPORTED;
+    if (n == 0) return RS_OK;
+    if ((rc = up(ctx, ctx->stage[9], values, (size_t)n * channels))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], sizeof(double) * (size_t)K * n))) return rc;
+    if ((rc = launch_band_ratios(ctx, (const uint8_t *)ctx->stage[9].p, n, channels, (double *)ctx->stage[10].p, ctx->host_stream)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->stage[10].p, sizeof(double) * (size_t)K * n, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
+int rs_bin_counts_host(rs_ctx *ctx, const double *values, const int8_t *sel, const int8_t *hit, const int32_t *group, int32_t n,
+                       int32_t n_cols, int32_t n_groups, const double *lo, const double *hi, int32_t n_thr, int64_t *counts)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n < 0 || n_cols < 1 || n_groups < 1 || n_thr < 1 || !lo || !hi || !counts) return RS_ERR_INVALID_ARG;
+    if (n > 0 && (!values || !sel || !hit || !group)) return RS_ERR_INVALID_ARG;
+    const size_t nk = (size_t)n * n_cols, nc = 2 * (size_t)n_groups * n_cols * n_thr;
+    if ((rc = up(ctx, ctx->stage[9], values, sizeof(double) * nk))) return rc;
+    if ((rc = up(ctx, ctx->stage[10], sel, nk))) return rc;
+    if ((rc = up(ctx, ctx->stage[11], hit, nk))) return rc;
+    if ((rc = up(ctx, ctx->stage[12], group, sizeof(int32_t) * (size_t)n))) return rc;
+    if ((rc = up(ctx, ctx->stage[13], lo, sizeof(double) * (size_t)n_thr))) return rc;
+    if ((rc = up(ctx, ctx->stage[14], hi, sizeof(double) * (size_t)n_thr))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[15], sizeof(int64_t) * nc))) return rc;
+    rc = launch_bin_counts(ctx, (const double *)ctx->stage[9].p, (const int8_t *)ctx->stage[10].p, (const int8_t *)ctx->stage[11].p,
+                           (const int *)ctx->stage[12].p, n, n_cols, n_groups, (const double *)ctx->stage[13].p,
+                           (const double *)ctx->stage[14].p, n_thr, (int64_t *)ctx->stage[15].p, ctx->host_stream);
+    if (rc) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(counts, ctx->stage[15].p, sizeof(int64_t) * nc, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
 int rs_vote_table_host(rs_ctx *ctx, const int32_t *row_off, const int8_t *cls, const double *score, const double *weighted,
                        const double *area, int32_t n_roads, const double *thresholds, int32_t n_thr, int8_t *cover, double *scores)
 {

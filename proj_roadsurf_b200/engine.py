@@ -331,6 +331,34 @@ class Engine:
         N.check(st, "rs_group_hist_host", self._ctx)
         return hist
 
+    def band_ratios_host(self, values: np.ndarray) -> np.ndarray:
+        """(K, n) float64 derived columns of a uint8 pixel table (n, C): band ratios rounded to 3 decimals (+ VgNIR-BI for
+        C = 4), statistical_analysis.py:279-293 (rs_band_ratios_host)."""
+        v = np.ascontiguousarray(values, np.uint8)
+        assert v.ndim == 2
+        K = int(self.lib.rs_band_ratio_columns(int(v.shape[1])))
+        if K == 0:
+            raise ValueError("band ratios need 2 to 4 bands")
+        out = np.zeros((K, v.shape[0]), np.float64)
+        st = self.lib.rs_band_ratios_host(self._ctx, _np_ptr(v), int(v.shape[0]), int(v.shape[1]), _np_ptr(out))
+        N.check(st, "rs_band_ratios_host", self._ctx)
+        return out
+
+    def bin_counts_host(self, values, sel, hit, group, n_groups: int, lo, hi) -> np.ndarray:
+        """(n_groups, K, T, 2) int64: rows per (group, column, bin lo < v <= hi) and the hits among them (rs_bin_counts_host)."""
+        v = np.ascontiguousarray(np.atleast_2d(values), np.float64)
+        s_ = np.ascontiguousarray(np.atleast_2d(sel), np.int8)
+        h = np.ascontiguousarray(np.atleast_2d(hit), np.int8)
+        g = np.ascontiguousarray(group, np.int32)
+        lo, hi = np.ascontiguousarray(lo, np.float64), np.ascontiguousarray(hi, np.float64)
+        K, n = v.shape
+        assert s_.shape == v.shape and h.shape == v.shape and g.shape == (n,) and lo.shape == hi.shape
+        out = np.zeros((int(n_groups), K, len(lo), 2), np.int64)
+        st = self.lib.rs_bin_counts_host(self._ctx, _np_ptr(v), _np_ptr(s_), _np_ptr(h), _np_ptr(g), n, K, int(n_groups),
+                                         _np_ptr(lo), _np_ptr(hi), len(lo), _np_ptr(out))
+        N.check(st, "rs_bin_counts_host", self._ctx)
+        return out
+
     def vote_table_host(self, row_off, cls, score, weighted, area, thresholds):
         """determine_detected_class on a detection table sorted by road (rs_vote_table_host).
         Returns cover (T, R) int8 and scores (T, R, 3) = artificial index, natural index, diff."""

@@ -168,3 +168,28 @@ def cover_stats_from_accumulators(hist: np.ndarray, n_allzero: np.ndarray, road_
     df['std'] = df['std'].round(1)
     df['margin'] = df['margin'].round(1)
     return df
+
+
+RATIO_NAMES = {'1/2': 'R/G', '1/3': 'R/B', '1/4': 'R/NIR', '2/3': 'G/B', '2/4': 'G/NIR', '3/4': 'B/NIR'}
+
+
+def add_band_ratios(pixels_per_band: pd.DataFrame, BANDS: Sequence[int] = range(1, 5), engine=None) -> pd.DataFrame:
+    """The derived per-pixel columns of scripts/statistical_analysis/statistical_analysis.py:279-293, added in place and
+    returned: 'R/G', 'R/B', 'R/NIR', 'G/B', 'G/NIR', 'B/NIR' (band_a / band_b rounded to 3 decimals, NaN -> 0, inf -> 1) and
+    'VgNIR-BI' (rounded to 5 decimals), one kernel over the uint8 band table (rs_band_ratios_host).  BANDS must be the
+    consecutive bands 1..max(BANDS) of the reference's loops; like the reference, VgNIR-BI needs band2 and band4
+    (KeyError otherwise)."""
+    BANDS = list(BANDS)
+    if BANDS != list(range(1, len(BANDS) + 1)) or not 2 <= len(BANDS) <= 4:
+        raise ValueError("BANDS must be range(1, n+1) with n in 2..4")
+    if len(BANDS) < 4:
+        raise KeyError('band4')                      # statistical_analysis.py:289-291 reads band2 and band4 unconditionally
+    values = np.stack([_uint8_column(pixels_per_band[f'band{b}'], f'band{b}') for b in BANDS], axis=1)
+    out = (engine or default_engine()).band_ratios_host(values)
+    k = 0
+    for band in BANDS:
+        for sec_band in range(band + 1, max(BANDS) + 1):
+            pixels_per_band[RATIO_NAMES[f'{band}/{sec_band}']] = out[k]
+            k += 1
+    pixels_per_band['VgNIR-BI'] = out[k]
+    return pixels_per_band

@@ -140,3 +140,35 @@ def diff_score_sweep(comparison_df, thresholds=None, CLASSES=('artificial', 'nat
     best_results['tag'] = tags_from_codes(cover_t[best], gt)
     return (pd.concat(by_class, ignore_index=True), pd.concat(glob, ignore_index=True),
             0 if best == 0 else round(float(thresholds[best]), 2), best_results)
+
+
+BIN_ACCURACY_PARAM = {'artificial': ['art_score', 'artificial', 'artifical score'],
+                      'natural': ['nat_score', 'natural', 'natural score'],
+                      'artificial_diff': ['diff_score', 'artificial', 'score diff in artificial roads'],
+                      'naturall_diff': ['diff_score', 'natural', 'score diff in natural roads']}
+
+
+def bin_accuracy(best_comparison_df, thresholds_bins=None):
+    """final_metrics.py:541-571: the calibration tables.  For every gt_type (in order of first appearance) and every entry of
+    BIN_ACCURACY_PARAM, the share of roads with cover_type == the entry's class among the roads of that CATEGORY whose
+    score lies in (threshold - 0.5, threshold] -- the 0.5 is the reference's (:557) -- for the thresholds
+    np.arange(0, 1.05, 0.05) with a non-empty bin.  Returns the list of DataFrames (threshold, accuracy), each with the
+    reference's ``name``; all counts come from one rs_bin_counts_host call."""
+    thresholds_bins = np.arange(0, 1.05, 0.05) if thresholds_bins is None else np.asarray(thresholds_bins, float)
+    df = best_comparison_df
+    gt_types = list(pd.unique(df['gt_type']))
+    group = df['gt_type'].map({g: i for i, g in enumerate(gt_types)}).to_numpy().astype(np.int32)
+    params = list(BIN_ACCURACY_PARAM.values())
+    values = np.stack([df[p[0]].to_numpy(float) for p in params])
+    sel = np.stack([(df['CATEGORY'] == p[1]).to_numpy() for p in params]).astype(np.int8)
+    hit = np.stack([(df['cover_type'] == p[1]).to_numpy() for p in params]).astype(np.int8)
+    counts = default_engine().bin_counts_host(values, sel, hit, group, max(len(gt_types), 1), thresholds_bins - 0.5, thresholds_bins)
+    tables = []
+    for gi, gt_type in enumerate(gt_types):
+        for ki, p in enumerate(params):
+            keep = counts[gi, ki, :, 0] > 0
+            t = pd.DataFrame({'threshold': [float(x) for x in thresholds_bins[keep]],
+                              'accuracy': [int(h) / int(c) for c, h in counts[gi, ki][keep]]})
+            t.name = p[2] + ' for ' + gt_type
+            tables.append(t)
+    return tables

@@ -410,3 +410,47 @@ def test_cover_stats_from_accumulators(mods):
         assert got[c].tolist() == exp[c].tolist(), c
     for c in ("mean", "std", "margin"):
         assert np.all(np.abs(got[c].to_numpy(float) - exp[c].to_numpy(float)) <= 0.1000001), c
+
+
+def test_band_ratios_exhaustive(mods):
+    """add_band_ratios (statistical_analysis.py:279-293): every (a, b) uint8 combination on every band pair, bit-exact
+    against the reference's pandas statements (oracle/stats.band_ratios)"""
+    fs = mods[1]
+    hi, lo = np.repeat(np.arange(256, dtype=np.uint8), 256), np.tile(np.arange(256, dtype=np.uint8), 256)
+    df = pd.DataFrame({"band1": np.concatenate([hi, hi]), "band2": np.concatenate([lo, hi]),
+                       "band3": np.concatenate([hi, lo]), "band4": np.concatenate([lo, lo]),
+                       "road_id": np.arange(131072) % 7})
+    exp = ostats.band_ratios(df)
+    got = fs.add_band_ratios(df.copy())
+    assert list(got.columns) == list(exp.columns)
+    for c in exp.columns:
+        assert got[c].dtype == exp[c].dtype, c
+        assert np.array_equal(got[c].to_numpy(), exp[c].to_numpy(), equal_nan=True), c
+    assert np.isnan(got["VgNIR-BI"].to_numpy()).sum() == 2          # 0/0 rows keep their NaN, as in the reference
+    with pytest.raises(KeyError):
+        fs.add_band_ratios(df[["band1", "band2", "band3"]].copy(), range(1, 4))
+
+
+def test_bin_accuracy_matches_the_script_body(mods):
+    """final_metrics.bin_accuracy (calibration tables, final_metrics.py:541-571) against the oracle restatement"""
+    fm = mods[4]
+    rng = np.random.default_rng(12)
+    n = 5000
+    art = np.round(rng.random(n), 3)
+    nat = np.round(rng.random(n), 3)
+    art[:200] = np.arange(0, 1.05, 0.05)[rng.integers(0, 21, 200)]            # scores exactly on bin edges
+    nat[100:300] = (np.arange(0, 1.05, 0.05) - 0.5)[rng.integers(0, 21, 200)]
+    df = pd.DataFrame({"art_score": art, "nat_score": nat, "diff_score": np.abs(art - nat),
+                       "CATEGORY": rng.choice(["artificial", "natural"], n, p=[0.8, 0.2]),
+                       "cover_type": rng.choice(["artificial", "natural", "undetermined", "undetected"], n, p=[0.6, 0.25, 0.05, 0.1]),
+                       "gt_type": rng.choice(["val", "trn", "tst", "oth"], n)})
+    exp = ovote.bin_accuracy(df)
+    got = fm.bin_accuracy(df)
+    assert len(got) == len(exp) == 16
+    for a, b in zip(got, exp):
+        assert a.name == b.name
+        assert a["threshold"].tolist() == b["threshold"].tolist()
+        assert a["accuracy"].tolist() == b["accuracy"].tolist()
+    one = fm.bin_accuracy(df[df["gt_type"] == "tst"].iloc[:3])
+    ref = ovote.bin_accuracy(df[df["gt_type"] == "tst"].iloc[:3])
+    assert [t["accuracy"].tolist() for t in one] == [t["accuracy"].tolist() for t in ref]

@@ -140,3 +140,18 @@ def test_python_and_c_oracles_agree_on_random_polygons():
         a = gdal_fill.rasterize(rings, (H, W))
         b = cport.rasterize(rings, (H, W))
         assert np.array_equal(a, b), i
+
+
+def test_band_ratios_known_answers():
+    """statistical_analysis.py:279-293 restated (oracle/stats.band_ratios): hand-checked rows"""
+    import pandas as pd
+    from oracle import stats as ostats
+    df = pd.DataFrame({"band1": np.array([1, 0, 5, 200, 2], np.uint8), "band2": np.array([3, 0, 0, 100, 3], np.uint8),
+                       "band3": np.array([2, 7, 1, 255, 0], np.uint8), "band4": np.array([4, 0, 9, 100, 6], np.uint8)})
+    out = ostats.band_ratios(df)
+    assert out["R/G"].tolist() == [0.333, 0.0, 1.0, 2.0, 0.667]          # 1/3, 0/0 -> 0, 5/0 -> 1, 200/100, 2/3
+    assert out["R/B"].tolist() == [0.5, 0.0, 5.0, 0.784, 1.0]            # 2/0 -> inf -> 1
+    assert out["B/NIR"].tolist() == [0.5, 1.0, 0.111, 2.55, 0.0]
+    v = out["VgNIR-BI"].tolist()
+    assert v[0] == -0.14286 and np.isnan(v[1]) and v[2] == -1.0 and v[3] == 0.0 and v[4] == -0.33333
+    assert list(out.columns) == ["band1", "band2", "band3", "band4", "R/G", "R/B", "R/NIR", "G/B", "G/NIR", "B/NIR", "VgNIR-BI"]
