@@ -454,3 +454,19 @@ def test_bin_accuracy_matches_the_script_body(mods):
     one = fm.bin_accuracy(df[df["gt_type"] == "tst"].iloc[:3])
     ref = ovote.bin_accuracy(df[df["gt_type"] == "tst"].iloc[:3])
     assert [t["accuracy"].tolist() for t in one] == [t["accuracy"].tolist() for t in ref]
+
+
+def test_rasterio_suite_known_answers_on_the_gpu(mods):
+    """The vectors rasterio's own tests publish for this call chain (tests/test_oracle_kat.py, RIO_*): rasterize,
+    geometry_mask and mask(crop=True) through the CUDA-backed drop-ins."""
+    from test_oracle_kat import RIO_BASIC_GEOMETRY, RIO_SHAPE, rio_basic_image, rio_basic_image_2x2
+    fct_misc, _, fct_rasters = mods[0], mods[1], mods[2]
+    geom = {"type": "Polygon", "coordinates": [RIO_BASIC_GEOMETRY.tolist()]}
+    assert np.array_equal(fct_rasters.rasterize([geom], out_shape=RIO_SHAPE), rio_basic_image_2x2())
+    outside = fct_rasters.rasterize([geom], out_shape=RIO_SHAPE, fill=1, default_value=0).astype(bool)    # geometry_mask
+    assert np.array_equal(outside, rio_basic_image_2x2() == 0)
+    # mask(crop=True) on basic_image: the 3 x 3 window keeps the 2 x 2 block of ones -> get_pixel_values returns 4 rows of 1
+    fct_misc.register_tile("rio_basic.tif", rio_basic_image()[..., None], (1.0, 0.0, 0.0, 0.0, 1.0, 0.0), None)
+    df = fct_misc.get_pixel_values(geom, "rio_basic.tif", range(1, 2), pd.DataFrame(), road_id=7)
+    assert df["band1"].tolist() == [1, 1, 1, 1] and df["road_id"].tolist() == [7] * 4
+    fct_misc.clear_tiles()

@@ -155,3 +155,50 @@ def test_band_ratios_known_answers():
     v = out["VgNIR-BI"].tolist()
     assert v[0] == -0.14286 and np.isnan(v[1]) and v[2] == -1.0 and v[3] == 0.0 and v[4] == -0.33333
     assert list(out.columns) == ["band1", "band2", "band3", "band4", "R/G", "R/B", "R/NIR", "G/B", "G/NIR", "B/NIR", "VgNIR-BI"]
+
+
+# ------------------------------------------------------------------------------------------
+# Known answers published in rasterio's OWN test suite (rasterio 1.3.x tests/conftest.py: basic_geometry, basic_image,
+# basic_image_2x2; tests/test_features.py: test_rasterize, test_geometry_mask, test_geometry_window_no_pad;
+# tests/test_mask.py: test_mask_crop).  rasterio is the third-party module behind fct_misc.py:77 and
+# add_tile_mask.py:112; it is not installable here, so the vectors are restated from that suite (they are the only
+# published input/output pairs for this call chain the reference's dependencies carry).
+# ------------------------------------------------------------------------------------------
+RIO_BASIC_GEOMETRY = ring((2, 2), (2, 4.25), (4.25, 4.25), (4.25, 2), (2, 2))
+RIO_SHAPE = (10, 10)
+
+
+def rio_basic_image():              # all_touched=True answer; its [2:4, 2:4] part is the pixel-centre answer
+    im = np.zeros(RIO_SHAPE, np.uint8)
+    im[2:5, 2:5] = 1
+    return im
+
+
+def rio_basic_image_2x2():
+    im = np.zeros(RIO_SHAPE, np.uint8)
+    im[2:4, 2:4] = 1
+    return im
+
+
+@pytest.mark.parametrize("name,rast", IMPLS)
+def test_rasterio_suite_rasterize_and_geometry_mask(name, rast):
+    m = rast([RIO_BASIC_GEOMETRY], RIO_SHAPE)                       # test_rasterize: == basic_image_2x2
+    assert np.array_equal(m, rio_basic_image_2x2())
+    # test_geometry_mask: geometry_mask(...) == (basic_image_2x2 == 0), i.e. True outside
+    assert np.array_equal(m == 0, rio_basic_image_2x2() == 0)
+
+
+def test_rasterio_suite_geometry_window_and_mask_crop():
+    ident = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0)
+    # test_geometry_window_no_pad: window.flatten() == (2, 2, 3, 3)  (col_off, row_off, width, height)
+    assert gdal_fill.geometry_window(ident, [RIO_BASIC_GEOMETRY], 10, 10) == (2, 2, 3, 3)
+    assert cport.geometry_window(ident, [RIO_BASIC_GEOMETRY], 10, 10) == (2, 2, 3, 3)
+    # test_mask_crop: masked.shape == (1, 3, 3) and masked[0] == image[2:5, 2:5] after image[4, :] = 0; image[:, 4] = 0
+    from oracle import raster as oraster
+    tile = {"data": rio_basic_image()[..., None], "transform": ident, "nodata": None}
+    masked = oraster.mask_crop(tile, [RIO_BASIC_GEOMETRY])
+    image = rio_basic_image()
+    image[4, :] = 0
+    image[:, 4] = 0
+    assert masked.shape == (1, 3, 3)
+    assert np.array_equal(masked[0], image[2:5, 2:5])
