@@ -106,6 +106,43 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+class PcieRxSampler:
+    """NVML PCIe RX throughput (host -> device, KB/s over the driver's 20 ms window) sampled during an e2e leg: the measured
+    count of the bytes that crossed the host link, next to the bytes counted from the buffers."""
+
+    def __init__(self, index: int):
+        self.vals, self._stop, self._thr = [], threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv.nvmlDeviceGetPcieThroughput(self.h, self.nv.NVML_PCIE_UTIL_RX_BYTES)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.vals.append(float(self.nv.nvmlDeviceGetPcieThroughput(self.h, self.nv.NVML_PCIE_UTIL_RX_BYTES)))
+            except Exception:  # noqa: BLE001
+                self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def stop(self, seconds: float):
+        """bytes received over `seconds`, or None when NVML gave no samples"""
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        if not self.vals:
+            return None
+        return float(np.mean(self.vals)) * 1024.0 * seconds
+
+
 def build_inputs(args, world):
     from proj_roadsurf_b200 import synth
     grid = synth.Grid(args.tiles_x, args.tiles_y * world)
@@ -301,14 +338,17 @@ def run_b200(args):
         modes = {"stream": dict(tiles_per_chunk=chunk), "mapped": dict(mapped=True)}
         if args.e2e_mode != "both":
             modes = {args.e2e_mode: modes[args.e2e_mode]}
-        n_e2e, legs, st_ref = 3, {}, None
+        n_e2e, legs, st_ref, rx = 3, {}, None, {}
         for name, kw in modes.items():
             eng.zonal_stats_host(roads_s, tb, pairs_s, **kw)                       # warm-up (allocates the staging buffers)
             barrier()
+            pcie = PcieRxSampler(local).start()
             t0 = time.perf_counter()
             for _ in range(n_e2e):
                 st_host = eng.zonal_stats_host(roads_s, tb, pairs_s, **kw)
             t1 = time.perf_counter()
+            got = pcie.stop(t1 - t0)
+            rx[name] = None if got is None else int(got / n_e2e)
             et = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(et, op=dist.ReduceOp.MAX)
@@ -330,6 +370,7 @@ def run_b200(args):
         e2e = {"value": legs[best], "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d_px + h2d_meta),
                "d2h_bytes_per_step": int(st_host.nbytes), "steps": n_e2e, "transport": best,
                "transports_Gpixel_s": legs, "host_tile_bytes": int(host_px.numel()),
+               "pcie_rx_bytes_per_step_nvml": rx,
                "sample": f"first {rows} of {args.tiles_y} tile rows of each rank's shard ({n_sub} tiles, {roads_s.n_roads} roads) in pinned "
                          f"host memory through {how}; statistics table read back"}
         del host_px
