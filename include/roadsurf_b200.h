@@ -248,6 +248,15 @@ int rs_band_ratios_dev(rs_ctx *ctx, const uint8_t *values, int64_t n, int32_t ch
 int rs_band_ratios_host(rs_ctx *ctx, const uint8_t *values, int64_t n, int32_t channels, double *out);
 
 /*
+ * 'within' join of two polygon sets: scripts/road_segmentation/determine_class.py:41-62 get_roads_in_quarries =
+ * gpd.sjoin(roads, buffered_quarries, predicate='within').  within uint8[a->n_roads][b->n_roads], 1 where polygon i of `a`
+ * lies within polygon j of `b` (touching allowed): no vertex of a outside b (even-odd over b's rings), no proper edge
+ * crossing, no vertex of b strictly inside a.  road_bbox may be NULL in both sets.  Binary64 orientation signs; can differ from
+ * GEOS' robust predicates only for vertices within rounding distance of b's boundary.
+ */
+int rs_within_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *within);
+
+/*
  * Calibration bins of scripts/road_segmentation/final_metrics.py:541-571: for every group g (gt_type), value column k
  * and threshold t, counts[g][k][t] = { rows with sel[k][r] != 0 and lo[t] < values[k][r] <= hi[t],  those of them with
  * hit[k][r] != 0 }; the bin accuracy is their quotient where the first is non-zero.  values double[n_cols][n],

@@ -251,3 +251,57 @@ def bin_accuracy(best_comparison_df: pd.DataFrame) -> list:
             df.name = label + ' for ' + gt_type
             out.append(df)
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# 'within' (determine_class.py:57: gpd.sjoin(roads, buffered_quarries, predicate='within'))
+# ------------------------------------------------------------------------------------------
+def _orient(p, q, r):
+    """sign of the cross product (q - p) x (r - p), exact (rational arithmetic on the binary64 inputs)"""
+    from fractions import Fraction as F
+    v = (F(q[0]) - F(p[0])) * (F(r[1]) - F(p[1])) - (F(q[1]) - F(p[1])) * (F(r[0]) - F(p[0]))
+    return (v > 0) - (v < 0)
+
+
+def _edges(rings):
+    for ring in rings:
+        n = len(ring)
+        for k in range(n):
+            a, b = ring[k], ring[(k + 1) % n]
+            if a[0] != b[0] or a[1] != b[1]:
+                yield a, b
+
+
+def point_in_rings(rings, p) -> int:
+    """0 outside, 1 inside, 2 on the boundary; even-odd over all rings"""
+    inside = 0
+    for a, b in _edges(rings):
+        o = _orient(a, b, p)
+        if o == 0 and min(a[0], b[0]) <= p[0] <= max(a[0], b[0]) and min(a[1], b[1]) <= p[1] <= max(a[1], b[1]):
+            return 2
+        if (a[1] <= p[1]) != (b[1] <= p[1]):
+            if (o > 0) == (b[1] > a[1]):
+                inside ^= 1
+    return inside
+
+
+def polygon_within(a_rings, b_rings) -> bool:
+    """Polygon a within polygon b (GEOS / DE-9IM 'within' for areal geometries: no point of a in the exterior of b; touching
+    boundaries allowed): every vertex of a in or on b, no proper crossing between their edges, no vertex of b strictly
+    inside a.  Exact predicates (GEOS evaluates orientation robustly too)."""
+    if not a_rings or not b_rings:
+        return False
+    for ring in a_rings:
+        for p in ring:
+            if point_in_rings(b_rings, p) == 0:
+                return False
+    for p, q in _edges(a_rings):
+        for c, d in _edges(b_rings):
+            o1, o2, o3, o4 = _orient(p, q, c), _orient(p, q, d), _orient(c, d, p), _orient(c, d, q)
+            if o1 * o2 < 0 and o3 * o4 < 0:
+                return False
+    for ring in b_rings:
+        for p in ring:
+            if point_in_rings(a_rings, p) == 1:
+                return False
+    return True

@@ -649,6 +649,44 @@ int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, co
     return finish(ctx);
 }
 
+// stage one polygon set in stage[base .. base + 3] (xy, ring_off, road_ring_off, bbox)
+static int stage_polys(rs_ctx *ctx, const rs_roads *r, int base, rs_roads &d)
+{
+    if (!r || r->n_roads < 0 || r->n_rings < 0 || r->n_verts < 0) return RS_ERR_INVALID_ARG;
+    if (r->n_roads > 0 && (!r->xy || !r->ring_off || !r->road_ring_off)) return RS_ERR_INVALID_ARG;
+    int rc;
+    d = *r;
+    if ((rc = up(ctx, ctx->stage[base], r->xy, sizeof(double) * 2 * (size_t)r->n_verts))) return rc;
+    if ((rc = up(ctx, ctx->stage[base + 1], r->ring_off, sizeof(int32_t) * ((size_t)r->n_rings + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[base + 2], r->road_ring_off, sizeof(int32_t) * ((size_t)r->n_roads + 1)))) return rc;
+    d.xy = (const double *)ctx->stage[base].p;
+    d.ring_off = (const int32_t *)ctx->stage[base + 1].p;
+    d.road_ring_off = (const int32_t *)ctx->stage[base + 2].p;
+    if ((rc = ensure(ctx, ctx->stage[base + 3], sizeof(double) * 4 * (size_t)r->n_roads))) return rc;
+    if (r->road_bbox) {
+        if ((rc = up(ctx, ctx->stage[base + 3], r->road_bbox, sizeof(double) * 4 * (size_t)r->n_roads))) return rc;
+    } else if ((rc = launch_road_bbox(ctx, &d, (double *)ctx->stage[base + 3].p, ctx->host_stream)))
+        return rc;
+    d.road_bbox = (const double *)ctx->stage[base + 3].p;
+    return RS_OK;
+}
+
+int rs_within_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *within)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    rs_roads da, db;
+    if ((rc = stage_polys(ctx, a, 0, da))) return rc;
+    if ((rc = stage_polys(ctx, b, 4, db))) return rc;
+    const size_t n = (size_t)a->n_roads * b->n_roads;
+    if (n == 0) return RS_OK;
+    if (!within) return RS_ERR_INVALID_ARG;
+    if ((rc = ensure(ctx, ctx->stage[8], n))) return rc;
+    if ((rc = launch_within(ctx, &da, &db, (uint8_t *)ctx->stage[8].p, ctx->host_stream))) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(within, ctx->stage[8].p, n, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
 int rs_ks_hist_host(rs_ctx *ctx, const uint32_t *hist, const int32_t *ref_of_road, const uint64_t *ref_hist, int32_t n_roads,
                     int32_t n_refs, double *D, double *n)
 {

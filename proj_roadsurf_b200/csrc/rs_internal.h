@@ -74,6 +74,7 @@ int launch_confusion(rs_ctx *ctx, const int8_t *cover, const int8_t *gt, int n_r
 int launch_band_ratios(rs_ctx *ctx, const uint8_t *values, long long n, int channels, double *out, cudaStream_t st);
 int launch_bin_counts(rs_ctx *ctx, const double *values, const int8_t *sel, const int8_t *hit, const int *group, int n, int n_cols,
                       int n_groups, const double *lo, const double *hi, int n_thr, int64_t *counts, cudaStream_t st);
+int launch_within(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *out, cudaStream_t st);
 int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, const rs_lattice *lat, const int *lut_dev,
                       int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);
 int launch_rescale(rs_ctx *ctx, const uint16_t *src, long long n_px, int c_in, int c_out, const int32_t *bidx_host, const double *k_host,

@@ -359,6 +359,24 @@ class Engine:
         N.check(st, "rs_bin_counts_host", self._ctx)
         return out
 
+    def within_host(self, a: RoadSet, b: RoadSet) -> np.ndarray:
+        """(Ra, Rb) uint8, 1 where polygon i of ``a`` lies within polygon j of ``b`` (rs_within_host): the predicate of
+        gpd.sjoin(roads, buffered_quarries, predicate='within'), determine_class.py:57."""
+        out = np.zeros((a.n_roads, b.n_roads), np.uint8)
+        if out.size == 0:
+            return out
+        keep = []
+        def desc(r):
+            xy = np.ascontiguousarray(r.xy, np.float64)
+            ro, rro = np.ascontiguousarray(r.ring_off, np.int32), np.ascontiguousarray(r.road_ring_off, np.int32)
+            bb = np.ascontiguousarray(r.bbox, np.float64)
+            keep.extend([xy, ro, rro, bb])
+            return self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), r.n_roads, r.n_rings, r.n_verts)
+        da, db = desc(a), desc(b)
+        st = self.lib.rs_within_host(self._ctx, C.byref(da), C.byref(db), _np_ptr(out))
+        N.check(st, "rs_within_host", self._ctx)
+        return out
+
     def vote_table_host(self, row_off, cls, score, weighted, area, thresholds):
         """determine_detected_class on a detection table sorted by road (rs_vote_table_host).
         Returns cover (T, R) int8 and scores (T, R, 3) = artificial index, natural index, diff."""

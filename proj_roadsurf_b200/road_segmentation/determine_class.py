@@ -8,7 +8,8 @@ Two forms of the per-road vote:
     and score planes are counted inside each road polygon by the fused kernel (joint histogram of
     (class, score) per road), then argmax of the pixel counts ('count') or of the mean scores ('score').
 The GEOS overlay of get_weighted_scores (:97-120) is replaced by the raster accumulation; the vector
-preprocessing helpers (quarries, clip_labels) are outside the path.
+preprocessing helpers keep their host (GEOS) buffering; the 'within' join of get_roads_in_quarries (:41-62) runs on the
+GPU (rs_within_host) and clip_labels is the ``border_px`` window option of the raster accumulation.
 """
 from __future__ import annotations
 
@@ -51,6 +52,40 @@ def determine_category(row):
     else:
         logger.error(f"Unexpected class: {row['BELAGSART']}")
         sys.exit(1)
+
+
+def get_roads_in_quarries(quarries, roads, engine=None):
+    """determine_class.py:41-62: the roads lying within a quarry buffered by 5 (gpd.sjoin(roads, buffered, predicate='within'))
+    and the other roads.  ``roads``: table with 'OBJECTID' and 'geometry' columns.  ``quarries``: a GeoDataFrame (buffered
+    by 5 in its own CRS and reprojected to EPSG:4326 with geopandas, as the reference does -- GEOS / PROJ preprocessing that
+    stays on the host) or, where geopandas is not installed, a table / list of ALREADY buffered geometries in the CRS of the
+    roads.  The 'within' predicate of every (road, quarry) combination runs on the GPU (rs_within_host).
+    Returns (roads_in_quarries, roads_not_in_quarries): the join rows (road columns + 'index_right' + quarry columns) and
+    the remaining roads with a fresh index."""
+    if hasattr(quarries, 'buffer') and hasattr(quarries, 'to_crs'):
+        buffered = quarries.copy()
+        buffered['geometry'] = buffered.buffer(5)
+        buffered = buffered.to_crs(epsg=4326)
+        from ..functions import fct_misc
+        fct_misc.test_crs(roads.crs, buffered.crs)
+    elif isinstance(quarries, pd.DataFrame):
+        buffered = quarries
+    else:
+        buffered = pd.DataFrame({'geometry': list(quarries)})
+    rs_a = RoadSet.from_geometries(list(roads['geometry']))
+    rs_b = RoadSet.from_geometries(list(buffered['geometry']))
+    hit = (engine or default_engine()).within_host(rs_a, rs_b)
+    ia, ib = np.nonzero(hit)                                     # row-major: road order, then quarry order (sjoin's order)
+    left = roads.iloc[ia]
+    right = buffered.drop(columns=['geometry']).iloc[ib]
+    joined = left.copy()
+    joined['index_right'] = buffered.index.to_numpy()[ib]
+    for c in right.columns:
+        name = c if c not in left.columns else f'{c}_right'
+        joined[name] = right[c].to_numpy()
+    in_ids = joined['OBJECTID'].unique().tolist()
+    roads_not_in_quarries = roads[~roads['OBJECTID'].isin(in_ids)].reset_index(drop=True)
+    return joined, roads_not_in_quarries
 
 
 def determine_detected_class(predictions, roads, threshold=0):

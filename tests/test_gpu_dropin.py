@@ -470,3 +470,51 @@ def test_rasterio_suite_known_answers_on_the_gpu(mods):
     df = fct_misc.get_pixel_values(geom, "rio_basic.tif", range(1, 2), pd.DataFrame(), road_id=7)
     assert df["band1"].tolist() == [1, 1, 1, 1] and df["road_id"].tolist() == [7] * 4
     fct_misc.clear_tiles()
+
+
+def test_roads_in_quarries_within_join(mods):
+    """determine_class.get_roads_in_quarries (determine_class.py:41-62): the 'within' join on the GPU against the oracle's
+    exact-predicate restatement, on random roads over buffered-quarry-like polygons (with holes and concave outlines)"""
+    from test_oracle_kat import ring
+    dc = mods[3]
+    rng = np.random.default_rng(5)
+    quarries = []
+    for q in range(6):
+        c = rng.uniform(20, 80, 2)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, 24))
+        rad = rng.uniform(8, 22, 24)
+        ext = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        rings = [np.concatenate([ext, ext[:1]])]
+        if q % 2 == 0:
+            rings.append(ring((c[0] - 2, c[1] - 2), (c[0] - 2, c[1] + 2), (c[0] + 2, c[1] + 2), (c[0] + 2, c[1] - 2)))
+        quarries.append({"type": "Polygon", "coordinates": [r.tolist() for r in rings]})
+    roads, ids = [], []
+    for i in range(400):
+        c = rng.uniform(5, 95, 2)
+        w, h = rng.uniform(0.5, 6, 2)
+        th = rng.uniform(0, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        pts = (np.array([[-w, -h], [w, -h], [w, h], [-w, h]]) @ R.T) + c
+        roads.append({"type": "Polygon", "coordinates": [np.concatenate([pts, pts[:1]]).tolist()]})
+        ids.append(1000 + i)
+    roads_df = pd.DataFrame({"OBJECTID": ids, "BELAGSART": 100, "geometry": roads})
+    quarries_df = pd.DataFrame({"id": np.arange(6) + 1, "geometry": quarries})
+    inq, notq = dc.get_roads_in_quarries(quarries_df, roads_df)
+    exp = [(ids[i], j + 1) for i, r in enumerate(roads) for j, q in enumerate(quarries)
+           if ovote.polygon_within([np.array(x) for x in r["coordinates"]], [np.array(x) for x in q["coordinates"]])]
+    assert len(exp) > 10
+    assert list(zip(inq["OBJECTID"].tolist(), inq["id"].tolist())) == exp
+    assert inq["index_right"].tolist() == [j - 1 for _, j in exp]
+    assert notq["OBJECTID"].tolist() == [i for i in ids if i not in {e[0] for e in exp}]
+    assert list(notq.index) == list(range(len(notq)))
+    # the hand-derived cases of tests/test_oracle_kat.py::test_polygon_within_known_answers through the kernel
+    big = {"type": "Polygon", "coordinates": [ring((0, 0), (10, 0), (10, 10), (0, 10)).tolist()]}
+    holed = {"type": "Polygon", "coordinates": [ring((0, 0), (10, 0), (10, 10), (0, 10)).tolist(), ring((4, 4), (4, 6), (6, 6), (6, 4)).tolist()]}
+    notch = {"type": "Polygon", "coordinates": [ring((0, 0), (10, 0), (10, 10), (6, 10), (6, 4), (4, 4), (4, 10), (0, 10)).tolist()]}
+    cases = [ring((1, 1), (3, 1), (3, 3), (1, 3)), ring((0, 0), (3, 0), (3, 3), (0, 3)), ring((8, 8), (12, 8), (12, 12), (8, 12)),
+             ring((4.5, 4.5), (5.5, 4.5), (5.5, 5.5), (4.5, 5.5)), ring((3, 3), (7, 3), (7, 7), (3, 7)), ring((1, 6), (9, 6), (9, 8), (1, 8)),
+             ring((1, 1), (9, 1), (9, 3), (1, 3)), ring((0, 0), (10, 0), (10, 10), (0, 10))]
+    rd = pd.DataFrame({"OBJECTID": np.arange(len(cases)), "geometry": [{"type": "Polygon", "coordinates": [c.tolist()]} for c in cases]})
+    inq, _ = dc.get_roads_in_quarries([big, holed, notch], rd)
+    got = sorted(zip(inq["OBJECTID"].tolist(), inq["index_right"].tolist()))
+    assert got == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (3, 0), (4, 0), (5, 0), (5, 1), (6, 0), (6, 1), (6, 2), (7, 0)]

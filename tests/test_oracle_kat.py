@@ -202,3 +202,23 @@ def test_rasterio_suite_geometry_window_and_mask_crop():
     image[:, 4] = 0
     assert masked.shape == (1, 3, 3)
     assert np.array_equal(masked[0], image[2:5, 2:5])
+
+
+def test_polygon_within_known_answers():
+    """'within' of gpd.sjoin(roads, buffered_quarries, predicate='within') (determine_class.py:57), oracle/vote.polygon_within"""
+    from oracle import vote as ovote
+    big = [ring((0, 0), (10, 0), (10, 10), (0, 10))]
+    holed = big + [ring((4, 4), (4, 6), (6, 6), (6, 4))]
+    notch = [ring((0, 0), (10, 0), (10, 10), (6, 10), (6, 4), (4, 4), (4, 10), (0, 10))]       # U shape
+    W = ovote.polygon_within
+    assert W([ring((1, 1), (3, 1), (3, 3), (1, 3))], big)
+    assert W([ring((0, 0), (3, 0), (3, 3), (0, 3))], big)                      # touching from inside
+    assert W(big, big)                                                          # equal polygons
+    assert not W([ring((8, 8), (12, 8), (12, 12), (8, 12))], big)              # partly outside
+    assert not W([ring((20, 20), (21, 20), (21, 21), (20, 21))], big)          # disjoint
+    assert not W([ring((4.5, 4.5), (5.5, 4.5), (5.5, 5.5), (4.5, 5.5))], holed)   # inside the hole
+    assert not W([ring((3, 3), (7, 3), (7, 7), (3, 7))], holed)                # covers the hole
+    assert W([ring((1, 1), (3, 1), (3, 9), (1, 9))], holed)
+    assert not W([ring((1, 6), (9, 6), (9, 8), (1, 8))], notch)                # all vertices inside, bridges the notch
+    assert W([ring((1, 1), (9, 1), (9, 3), (1, 3))], notch)
+    assert not W(big, [ring((1, 1), (3, 1), (3, 3), (1, 3))])                  # contains, not within
