@@ -332,6 +332,22 @@ int rs_rescale_u16_host(rs_ctx *ctx, const uint16_t *src, int64_t n_pixels, int3
                         const double *k, const double *off, int32_t f32, uint8_t *dst);
 
 /*
+ * Tile ingest: decompressed TIFF segments of n_tiles equally shaped tiles -> the pixel-interleaved batch rs_zonal_* reads
+ * (what rasterio's src.read() + np.moveaxis deliver in fct_misc.py:76-77, and the band selection bidx=2,3,4,1 of
+ * config/config_stats.yaml:39).  raw holds, per tile, height*width*c_in samples of sample_bytes (1 | 2) bytes:
+ * planar 1 = [H][W][c_in] (PlanarConfiguration chunky), 2 = [c_in][H][W] (band-sequential); predictor 2 = TIFF horizontal
+ * differencing (undone per row and sample, modulo the sample width), 1 = none; big_endian: byte order of 16-bit samples.
+ * out[n_tiles][H][W][c_out], band c = input band bidx[c] (NULL = identity); rescale 0 keeps the sample width, 1 / 2 apply
+ * dst = clamp_round(src * k[c] + off[c]) in float64 / float32 to uint8 (tif2cog.py:260-270, as rs_rescale_u16_*).
+ */
+int rs_assemble_tiles_dev(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in,
+                          int32_t planar, int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out,
+                          const int32_t *bidx, int32_t rescale, const double *k, const double *off, void *out, void *stream);
+int rs_assemble_tiles_host(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in,
+                           int32_t planar, int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out,
+                           const int32_t *bidx, int32_t rescale, const double *k, const double *off, void *out);
+
+/*
  * Deterministic synthetic tiles (bench / tests only; the reference ships no imagery,
  * data/readme.md:20-21).  value = f(seed, tile_key[t], pixel, band), see DESIGN.md.
  * kind 0: iid uniform; 1: low-entropy "asphalt"; 2: class/score planes (channels == 2).

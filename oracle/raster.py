@@ -136,3 +136,21 @@ def rescale_u16_to_u8(px: np.ndarray, smin: Sequence[float], smax: Sequence[floa
         v = np.clip(v, ft(0.0), ft(255.0))
         out[..., c] = (v + ft(0.5)).astype(np.int32).astype(np.uint8)
     return out
+
+
+def tiff_assemble(raw: np.ndarray, height: int, width: int, channels: int, sample_bytes: int, planar: int, predictor: int,
+                  big_endian: bool, bidx: Optional[Sequence[int]] = None) -> np.ndarray:
+    """What a TIFF decoder (libtiff under GDAL under rasterio, fct_misc.py:76-77) does after decompression, for one tile:
+    samples in file byte order, TIFF 6.0 section 14 horizontal differencing (predictor 2: every sample is the difference to
+    the same sample of the pixel on its left, modulo the sample width), PlanarConfiguration 1 (chunky) or 2 (planes).
+    raw: uint8 buffer of the decompressed segments ([H][W][C] or [C][H][W] samples).  bidx: 1-based band selection.
+    Returns (H, W, C_out) uint8 | uint16."""
+    dt = np.dtype(np.uint8) if sample_bytes == 1 else np.dtype(">u2" if big_endian else "<u2")
+    a = np.frombuffer(np.ascontiguousarray(raw, np.uint8).tobytes(), dt)
+    a = a.reshape(height, width, channels) if planar == 1 else np.moveaxis(a.reshape(channels, height, width), 0, 2)
+    a = a.astype(np.uint8 if sample_bytes == 1 else np.uint16)
+    if predictor == 2:
+        a = np.cumsum(a.astype(np.uint64), axis=1).astype(a.dtype)          # wraps modulo 2^bits
+    if bidx is not None:
+        a = a[..., [b - 1 for b in bidx]]
+    return np.ascontiguousarray(a)

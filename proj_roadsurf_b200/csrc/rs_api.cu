@@ -738,6 +738,36 @@ int rs_rescale_u16_host(rs_ctx *ctx, const uint16_t *src, int64_t n_pixels, int3
     return finish(ctx);
 }
 
+int rs_assemble_tiles_dev(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in,
+                          int32_t planar, int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out,
+                          const int32_t *bidx, int32_t rescale, const double *k, const double *off, void *out, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    return launch_assemble(ctx, raw, n_tiles, height, width, c_in, planar, predictor, sample_bytes, big_endian, c_out, bidx, rescale,
+                           k, off, out, (cudaStream_t)stream);
+}
+
+int rs_assemble_tiles_host(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in,
+                           int32_t planar, int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out,
+                           const int32_t *bidx, int32_t rescale, const double *k, const double *off, void *out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_tiles < 0 || height < 1 || width < 1 || c_in < 1 || c_out < 1 || (sample_bytes != 1 && sample_bytes != 2)) return RS_ERR_INVALID_ARG;
+    if (n_tiles == 0) return RS_OK;
+    if (!raw || !out) return RS_ERR_INVALID_ARG;
+    const size_t npx = (size_t)n_tiles * height * width;
+    const size_t in_b = npx * c_in * sample_bytes, out_b = npx * c_out * ((sample_bytes == 1 || rescale) ? 1 : 2);
+    if ((rc = up(ctx, ctx->stage[7], raw, in_b))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[9], out_b))) return rc;
+    if ((rc = launch_assemble(ctx, (const uint8_t *)ctx->stage[7].p, n_tiles, height, width, c_in, planar, predictor, sample_bytes,
+                              big_endian, c_out, bidx, rescale, k, off, ctx->stage[9].p, ctx->host_stream)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->stage[9].p, out_b, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
 int rs_synth_tiles_dev(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int32_t n_tiles, int32_t height, int32_t width,
                        int32_t channels, int32_t dtype, int32_t kind, uint64_t seed, void *stream)
 {

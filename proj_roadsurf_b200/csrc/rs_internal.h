@@ -79,6 +79,9 @@ int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const do
                       int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);
 int launch_rescale(rs_ctx *ctx, const uint16_t *src, long long n_px, int c_in, int c_out, const int32_t *bidx_host, const double *k_host,
                    const double *off_host, int f32, uint8_t *dst, cudaStream_t st);
+int launch_assemble(rs_ctx *ctx, const uint8_t *raw, int n_tiles, int H, int W, int c_in, int planar, int predictor, int bytes,
+                    int big_endian, int c_out, const int32_t *bidx_host, int rescale, const double *k_host, const double *off_host,
+                    void *out, cudaStream_t st);
 int launch_ks(rs_ctx *ctx, const uint32_t *hist, const int *ref_of_road, const unsigned long long *ref_hist, int n_roads, int stride,
               double *d_out, double *n_out, cudaStream_t st);
 int launch_synth(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int n_tiles, int H, int W, int C, int dtype,

@@ -489,6 +489,101 @@ int launch_rescale(rs_ctx *ctx, const uint16_t *src, long long n_px, int c_in, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// tile ingest: decompressed TIFF segments -> the pixel-interleaved batches the overlay kernels read.
+// One warp per (tile, row): undoes TIFF predictor 2 (horizontal differencing, per sample, modulo the sample width) with a
+// lane-chunk sum + warp scan, swaps the bytes of big-endian 16-bit samples, turns band-sequential planes into interleaved
+// pixels, selects / reorders bands (bidx) and optionally applies the 16 -> 8 bit rescale of tif2cog.py:260-270.
+// ---------------------------------------------------------------------------------------------
+struct AssembleArgs {
+    const uint8_t *raw;
+    void *out;
+    int n_tiles, H, W, c_in, c_out;
+    int planar;         // 1: [H][W][c_in] samples, 2: [c_in][H][W]
+    int predictor;      // 1 none, 2 horizontal differencing
+    int bytes;          // 1 or 2 per sample
+    int big_endian;
+    int rescale;        // 0 none (output keeps the sample width), 1 float64, 2 float32 (uint8 output)
+    int bidx[4];
+    double k[4], off[4];
+};
+
+__device__ __forceinline__ uint32_t raw_sample(const AssembleArgs &a, const uint8_t *tile, int y, int x, int c)
+{
+    const size_t idx = a.planar == 1 ? ((size_t)y * a.W + x) * a.c_in + c : ((size_t)c * a.H + y) * a.W + x;
+    if (a.bytes == 1) return tile[idx];
+    const uint32_t b0 = tile[2 * idx], b1 = tile[2 * idx + 1];
+    return a.big_endian ? (b0 << 8) | b1 : (b1 << 8) | b0;
+}
+
+__global__ void __launch_bounds__(256) assemble_kernel(const AssembleArgs a)
+{
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= (long long)a.n_tiles * a.H) return;
+    const int t = (int)(row / a.H), y = (int)(row - (long long)t * a.H);
+    const uint8_t *tile = a.raw + (size_t)t * a.H * a.W * a.c_in * a.bytes;
+    const int chunk = (a.W + 31) >> 5, x0 = min(lane * chunk, a.W), x1 = min(x0 + chunk, a.W);
+    const uint32_t smask = a.bytes == 1 ? 0xffu : 0xffffu;
+    uint32_t run[4] = {0, 0, 0, 0};
+    if (a.predictor == 2) {
+        for (int c = 0; c < a.c_in; c++) {
+            uint32_t sum = 0;
+            for (int x = x0; x < x1; x++) sum += raw_sample(a, tile, y, x, c);
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            run[c] = incl - sum;                  // sum of the differences left of this lane's chunk
+        }
+    }
+    for (int x = x0; x < x1; x++) {
+        uint32_t v[4] = {0, 0, 0, 0};
+        for (int c = 0; c < a.c_in; c++) {
+            const uint32_t sm = raw_sample(a, tile, y, x, c);
+            if (a.predictor == 2) { run[c] += sm; v[c] = run[c] & smask; }
+            else v[c] = sm;
+        }
+        const size_t o = (((size_t)t * a.H + y) * a.W + x) * a.c_out;
+        for (int c = 0; c < a.c_out; c++) {
+            uint32_t s = v[a.bidx[c]];
+            if (a.rescale == 1) s = rescale_one<false>(s, a.k[c], a.off[c]);
+            else if (a.rescale == 2) s = rescale_one<true>(s, a.k[c], a.off[c]);
+            if (a.bytes == 1 || a.rescale) ((uint8_t *)a.out)[o + c] = (uint8_t)s;
+            else ((uint16_t *)a.out)[o + c] = (uint16_t)s;
+        }
+    }
+}
+
+int launch_assemble(rs_ctx *ctx, const uint8_t *raw, int n_tiles, int H, int W, int c_in, int planar, int predictor, int bytes,
+                    int big_endian, int c_out, const int32_t *bidx_host, int rescale, const double *k_host, const double *off_host,
+                    void *out, cudaStream_t st)
+{
+    if (n_tiles < 0 || H < 1 || W < 1 || c_in < 1 || c_in > 4 || c_out < 1 || c_out > 4) return RS_ERR_INVALID_ARG;
+    if ((planar != 1 && planar != 2) || (predictor != 1 && predictor != 2) || (bytes != 1 && bytes != 2)) return RS_ERR_UNSUPPORTED;
+    if (rescale < 0 || rescale > 2 || (rescale && (!k_host || !off_host))) return RS_ERR_INVALID_ARG;
+    if (n_tiles == 0) return RS_OK;
+    if (!raw || !out) return RS_ERR_INVALID_ARG;
+    AssembleArgs a{};
+    a.raw = raw; a.out = out; a.n_tiles = n_tiles; a.H = H; a.W = W; a.c_in = c_in; a.c_out = c_out;
+    a.planar = planar; a.predictor = predictor; a.bytes = bytes; a.big_endian = big_endian; a.rescale = rescale;
+    for (int c = 0; c < 4; c++) {
+        a.bidx[c] = c < c_out ? (bidx_host ? bidx_host[c] : c) : 0;
+        if (a.bidx[c] < 0 || a.bidx[c] >= c_in) return RS_ERR_INVALID_ARG;
+        a.k[c] = (rescale && c < c_out) ? k_host[c] : 1.0;
+        a.off[c] = (rescale && c < c_out) ? off_host[c] : 0.0;
+    }
+    const long long warps = (long long)n_tiles * H;
+    const long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return RS_ERR_UNSUPPORTED;
+    assemble_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // synthetic tiles: counter-based, any shard regenerates its own tiles from (seed, tile_key)
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ u64 mix64(u64 z)

@@ -377,6 +377,28 @@ class Engine:
         N.check(st, "rs_within_host", self._ctx)
         return out
 
+    def assemble_tiles_host(self, raw: np.ndarray, info, bidx=None, rescale: Optional[dict] = None) -> np.ndarray:
+        """(T, H, W, C_out) uint8 | uint16 tiles from decompressed TIFF samples (rs_assemble_tiles_host): predictor, byte
+        order, planar -> interleaved, band selection (``bidx`` 1-based) and optional 16 -> 8 bit rescale in one kernel.
+        ``info``: ingest.TiffInfo (height, width, channels, sample_bytes, planar, predictor, big_endian)."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        T = raw.shape[0]
+        H, W, Cin, sb = info.height, info.width, info.channels, info.sample_bytes
+        assert raw.size == T * H * W * Cin * sb, "raw sample buffer does not match the tile layout"
+        bi = np.arange(Cin, dtype=np.int32) if bidx is None else np.ascontiguousarray(bidx, np.int32) - 1
+        Cout = len(bi)
+        mode, k, off = 0, None, None
+        if rescale is not None:
+            k, off = scale_params(rescale["smin"], rescale["smax"], bool(rescale.get("f32")))
+            assert len(k) == Cout, "one scale range per output band"
+            mode = 2 if rescale.get("f32") else 1
+        out = np.zeros((T, H, W, Cout), np.uint8 if (sb == 1 or mode) else np.uint16)
+        st = self.lib.rs_assemble_tiles_host(self._ctx, _np_ptr(raw), T, H, W, Cin, int(info.planar), int(info.predictor), sb,
+                                             int(bool(info.big_endian)), Cout, _np_ptr(bi), mode, _np_ptr(k), _np_ptr(off),
+                                             _np_ptr(out))
+        N.check(st, "rs_assemble_tiles_host", self._ctx)
+        return out
+
     def vote_table_host(self, row_off, cls, score, weighted, area, thresholds):
         """determine_detected_class on a detection table sorted by road (rs_vote_table_host).
         Returns cover (T, R) int8 and scores (T, R, 3) = artificial index, natural index, diff."""

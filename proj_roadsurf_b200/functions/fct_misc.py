@@ -3,8 +3,9 @@
 ``get_pixel_values`` keeps the reference signature and return value (fct_misc.py:57-123); the mask and the
 ordered pixel extraction run on the GPU (rs_extract_pixels_host), the reference's nodata handling
 (:87-119) is applied to the extracted rows.  ``get_pixel_values_batch`` is the batched form the double loop
-of statistical_analysis.py:180-193 collapses into.  Tile decoding is outside the path: a tile is either
-registered in memory (``register_tile``) or opened through rasterio when that is installed.
+of statistical_analysis.py:180-193 collapses into.  A tile is either registered in memory
+(``register_tile``), opened through rasterio when that is installed, or read by the package's own GeoTIFF ingest
+(``proj_roadsurf_b200.ingest``; PIL for the TIFF layouts it does not cover).
 """
 from __future__ import annotations
 
@@ -90,7 +91,7 @@ def open_tile(tile) -> Optional[dict]:
     try:
         import rasterio                       # not part of this image; used when the deployment has it
     except Exception:  # noqa: BLE001
-        return _open_geotiff_pil(tile)
+        return _open_geotiff(tile)
     try:
         with rasterio.open(tile) as src:
             t = src.transform
@@ -98,6 +99,22 @@ def open_tile(tile) -> Optional[dict]:
                     "nodata": src.nodata}
     except Exception:  # noqa: BLE001  (RasterioIOError)
         return None
+
+
+def _open_geotiff(path) -> Optional[dict]:
+    """The package's own ingest (ingest.load_tiles: directory parse + inflate on the host, predictor / interleave on the
+    GPU); layouts it does not cover go through PIL; None for a missing or unreadable file (the reference's RasterioIOError
+    branch, fct_misc.py:83-85)."""
+    from .. import ingest
+    if not os.path.exists(path):
+        return None
+    try:
+        tb = ingest.load_tiles([path], threads=1)
+    except ingest.UnsupportedTiff:
+        return _open_geotiff_pil(path)
+    except Exception:  # noqa: BLE001
+        return None
+    return {"data": tb.pixels[0], "transform": tuple(float(v) for v in tb.gt[0]), "nodata": tb.nodata}
 
 
 def _open_geotiff_pil(path) -> Optional[dict]:

@@ -1,0 +1,114 @@
+"""Tile ingest (proj_roadsurf_b200/ingest.py): the TIFF directory parser and segment reader on the CPU, the oracle's
+restatement of the post-decompression steps, PIL (libtiff) as the third-party decoder where it can read the file, and the
+assemble kernel on the GPU."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from oracle import raster as oraster
+from proj_roadsurf_b200 import ingest
+from tiff_util import write_tiff
+
+T = (0.5971642834779395, 0.0, 815000.25, 0.0, -0.5971642834779395, 5935000.75)
+VARIANTS = [dict(compression=c, predictor=p, planar=pl, big_endian=be, rows_per_strip=rps, tile=tl)
+            for c, p, pl, be, (rps, tl) in itertools.product((1, 8), (1, 2), (1, 2), (False, True), ((None, None), (7, None), (None, (64, 48))))
+            if not (c == 1 and p == 2)]          # libtiff ignores the predictor tag of uncompressed data (see below)
+
+
+def _image(rng, C, dtype, H=40, W=52):
+    hi = 256 if dtype == np.uint8 else 65536
+    a = rng.integers(0, hi, (H, W, C)).astype(dtype)
+    a[5:9, :, :] = hi - 1                      # runs of equal and extreme values: differences wrap
+    a[9:12, ::2, :] = 0
+    return a
+
+
+def _decode(path, bidx=None):
+    raw, info = ingest.read_raw(path)
+    return oraster.tiff_assemble(raw, info.height, info.width, info.channels, info.sample_bytes, info.planar, info.predictor,
+                                 info.big_endian, bidx), info
+
+
+@pytest.mark.parametrize("C,dtype", [(1, np.uint8), (3, np.uint8), (4, np.uint8), (1, np.uint16), (4, np.uint16)])
+def test_reader_and_oracle_round_trip_every_layout(tmp_path, C, dtype):
+    rng = np.random.default_rng(C * 7 + np.dtype(dtype).itemsize)
+    img = _image(rng, C, dtype)
+    for i, v in enumerate(VARIANTS):
+        p = str(tmp_path / f"t{i}.tif")
+        write_tiff(p, img, transform=T, nodata=0, **v)
+        got, info = _decode(p)
+        assert np.array_equal(got, img), v
+        assert info.transform == T and info.nodata == 0
+    got, _ = _decode(p, bidx=[C, 1])
+    assert np.array_equal(got, img[..., [C - 1, 0]])
+
+
+def test_pil_libtiff_agrees_where_it_can_read(tmp_path):
+    """PIL decodes through libtiff, the decoder under GDAL / rasterio: files written here are read identically by it, and
+    files written by PIL are read identically here"""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    rgb, gray16 = _image(rng, 3, np.uint8), _image(rng, 1, np.uint16)[..., 0]
+    n = 0
+    for i, v in enumerate(VARIANTS):
+        p = str(tmp_path / f"w{i}.tif")
+        write_tiff(p, rgb, **v)
+        try:
+            with Image.open(p) as im:
+                pil = np.asarray(im)
+        except Exception:  # noqa: BLE001  (a layout this PIL build does not read)
+            continue
+        assert np.array_equal(pil, rgb), v
+        n += 1
+    assert n >= 8
+    # uncompressed + predictor tag: libtiff (and this reader) ignore the tag; the samples are taken as stored
+    p = str(tmp_path / "nopred.tif")
+    write_tiff(p, rgb, compression=1, predictor=2)
+    raw, info = ingest.read_raw(p)
+    assert info.predictor == 1
+    with Image.open(p) as im:
+        assert np.array_equal(np.asarray(im), _decode(p)[0])
+    for comp in ("raw", "tiff_adobe_deflate", "tiff_deflate"):
+        p = str(tmp_path / f"pil_{comp}.tif")
+        Image.fromarray(rgb).save(p, compression=comp)
+        assert np.array_equal(_decode(p)[0], rgb), comp
+        p16 = str(tmp_path / f"pil16_{comp}.tif")
+        Image.fromarray(gray16).save(p16, compression=comp)
+        assert np.array_equal(_decode(p16)[0][..., 0], gray16), comp
+
+
+def test_unsupported_files_are_refused(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    p = str(tmp_path / "lzw.tif")
+    Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(p, compression="tiff_lzw")
+    with pytest.raises(ingest.UnsupportedTiff):
+        ingest.read_raw(p)
+    with pytest.raises(ingest.UnsupportedTiff):
+        ingest.parse_tiff(b"not a tiff at all")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,dtype", [(3, np.uint8), (4, np.uint8), (1, np.uint16), (4, np.uint16)])
+def test_load_tiles_on_the_gpu(tmp_path, C, dtype):
+    rng = np.random.default_rng(11 + C)
+    for vi, v in enumerate(VARIANTS[::5]):
+        imgs, paths = [], []
+        for k in range(3):
+            img = _image(rng, C, dtype, H=33, W=70)
+            p = str(tmp_path / f"g{vi}_{k}.tif")
+            write_tiff(p, img, transform=(T[0], 0.0, T[2] + 10.0 * k, 0.0, T[4], T[5]), nodata=0, **v)
+            imgs.append(img); paths.append(p)
+        tb = ingest.load_tiles(paths)
+        assert tb.pixels.dtype == dtype and np.array_equal(tb.pixels, np.stack(imgs)), v
+        assert np.array_equal(tb.gt[:, 2], T[2] + 10.0 * np.arange(3)) and tb.nodata == 0
+        if C == 4:
+            bidx = [2, 3, 4, 1]                                     # config_stats.yaml:39
+            assert np.array_equal(ingest.load_tiles(paths, bidx=bidx).pixels, np.stack(imgs)[..., [1, 2, 3, 0]])
+            if dtype == np.uint16:                                  # tif2cog.py:260-270 on ingest
+                smin, smax = [100.0, 100.0, 100.0, 300.0], [20000.0, 20000.0, 20000.0, 40000.0]
+                for f32 in (False, True):
+                    got = ingest.load_tiles(paths, bidx=bidx, rescale={"smin": smin, "smax": smax, "f32": f32}).pixels
+                    exp = oraster.rescale_u16_to_u8(np.stack(imgs)[..., [1, 2, 3, 0]], smin, smax, f32)
+                    assert got.dtype == np.uint8 and np.array_equal(got, exp), (v, f32)
