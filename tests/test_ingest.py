@@ -96,7 +96,7 @@ def test_load_tiles_on_the_gpu(tmp_path, C, dtype):
     for vi, v in enumerate(VARIANTS[::5]):
         imgs, paths = [], []
         for k in range(3):
-            img = _image(rng, C, dtype, H=33, W=70)
+            img = _image(rng, C, dtype, H=33, W=61)
             p = str(tmp_path / f"g{vi}_{k}.tif")
             write_tiff(p, img, transform=(T[0], 0.0, T[2] + 10.0 * k, 0.0, T[4], T[5]), nodata=0, **v)
             imgs.append(img); paths.append(p)
