@@ -359,13 +359,15 @@ def run_b200(args):
                 raise SystemExit("e2e transports disagree")
         best = max(legs, key=legs.get)
         # bytes that cross the host link per step: every tile byte when streamed; when the kernel reads the page-locked tiles
-        # in place, the sectors it touches (profiles/traffic.json holds the ncu DRAM figure of the same launch, used as estimate)
+        # in place, the PCIe read bytes ncu counted for that kernel per tile byte (profiles/traffic.json, mapped_host_tiles)
         h2d_px = host_px.numel() if best == "stream" else None
         how = {"stream": f"rs_zonal_stats_stream_host ({chunk}-tile chunks through two device buffers, copy overlapped with compute)",
                "mapped": "rs_zonal_stats_mapped_host (zonal_kernel reads the page-locked tiles in place; only the sectors under "
                          "road pixels cross the host link)"}[best]
         if h2d_px is None:
-            frac = (traffic / alg_bytes) if (traffic and n_sub == n_tiles) else 1.0
+            frac = 1.0
+            if os.path.exists(tpath):            # ncu pcie__read_bytes of the in-place kernel per tile byte (same synthetic roads)
+                frac = json.load(open(tpath)).get("mapped_host_tiles", {}).get("pcie_read_bytes_per_tile_byte", 1.0)
             h2d_px = int(host_px.numel() * min(1.0, frac))
         e2e = {"value": legs[best], "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d_px + h2d_meta),
                "d2h_bytes_per_step": int(st_host.nbytes), "steps": n_e2e, "transport": best,
