@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libroadsurf_b200.so")
+LIB_PATH = os.environ.get("ROADSURF_B200_LIB") or os.path.join(LIB_DIR, "libroadsurf_b200.so")   # env: an experiment build
 SOURCES = ["rs_zonal.cu", "rs_tables.cu", "rs_extract.cu", "rs_pairs.cu", "rs_api.cu"]
 HEADERS = [os.path.join(CSRC, "rs_internal.h"), os.path.join(ROOT, "include", "roadsurf_b200.h")]
 
@@ -29,6 +29,8 @@ def nvcc_path() -> str:
 
 
 def is_stale() -> bool:
+    if os.environ.get("ROADSURF_B200_LIB"):
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
