@@ -133,6 +133,14 @@ int rs_ctx_last_cuda_error(rs_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py: gpu_launches) */
 int64_t rs_ctx_launch_count(rs_ctx *ctx);
 
+/*
+ * Page-lock a caller-owned host buffer (cudaHostRegister, portable + mapped) so that rs_zonal_stats_mapped_host can read
+ * it in place and the other _host entry points copy from it at full link speed; a buffer that is already page-locked is
+ * left alone.  The caller unregisters it before freeing the memory.
+ */
+int rs_host_register(rs_ctx *ctx, void *ptr, size_t bytes);
+int rs_host_unregister(rs_ctx *ctx, void *ptr);
+
 /* road_bbox from xy (device pointers).  Host code normally has it from geometry.bounds. */
 int rs_road_bbox_dev(rs_ctx *ctx, const rs_roads *roads, double *road_bbox_out, void *stream);
 

@@ -183,6 +183,27 @@ int rs_ctx_sync_status(rs_ctx *ctx, void *stream)
 int rs_ctx_last_cuda_error(rs_ctx *ctx) { return ctx ? ctx->last_cuda_error : 0; }
 int64_t rs_ctx_launch_count(rs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int rs_host_register(rs_ctx *ctx, void *ptr, size_t bytes)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!ptr || bytes == 0) return RS_ERR_INVALID_ARG;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost) return RS_OK;    // already page-locked
+    cudaGetLastError();
+    RS_CUDA_OK(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return RS_OK;
+}
+
+int rs_host_unregister(rs_ctx *ctx, void *ptr)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!ptr) return RS_ERR_INVALID_ARG;
+    RS_CUDA_OK(ctx, cudaHostUnregister(ptr));
+    return RS_OK;
+}
+
 int rs_road_bbox_dev(rs_ctx *ctx, const rs_roads *roads, double *road_bbox_out, void *stream)
 {
     int rc = bind(ctx);

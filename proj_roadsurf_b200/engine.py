@@ -148,9 +148,12 @@ class Engine:
     def zonal_stats_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, window: str = "crop", rescale=None,
                          nodata_mode: str = "none", ddof: int = 1, percentiles: Sequence[float] = (),
                          want_hist: bool = False, tiles_per_chunk: Optional[int] = None,
-                         mapped: bool = False):
+                         mapped: Optional[bool] = None):
         """Host buffers in, statistics table out, in ONE C call (rs_zonal_stats_host): the batched form of
-        statistical_analysis.py:179-246.  Returns stats (R, C, RS_NSTAT + n_pct) [, hist, n_allzero]."""
+        statistical_analysis.py:179-246.  Returns stats (R, C, RS_NSTAT + n_pct) [, hist, n_allzero].
+        mapped: True = the kernel reads the page-locked tiles in place (rs_zonal_stats_mapped_host; RS_ERR_NOT_PINNED for
+        pageable memory), False = the tiles are copied (whole, or streamed in chunks of tiles_per_chunk), None = in place
+        when the buffer is page-locked (``pin_host`` / torch pin_memory), copied otherwise."""
         px = np.ascontiguousarray(tiles.pixels) if isinstance(tiles.pixels, np.ndarray) else tiles.pixels
         dtype = N.RS_U16 if px.dtype == np.uint16 else N.RS_U8
         R, Cc = roads.n_roads, tiles.channels
@@ -167,10 +170,16 @@ class Engine:
         td = N.RsTiles(_np_ptr(px), _np_ptr(gt), tiles.n_tiles, tiles.height, tiles.width, tiles.channels, dtype)
         pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
         prm = self._params("bands", window, rescale, None)
-        if mapped:  # page-locked tiles read in place by the kernel (only the sectors under road pixels cross the host link)
+        st = None
+        if mapped or (mapped is None and tiles_per_chunk is None):
+            # page-locked tiles read in place by the kernel (only the sectors under road pixels cross the host link)
             st = self.lib.rs_zonal_stats_mapped_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
                                                      _NODATA_MODES[nodata_mode], int(ddof), _np_ptr(pct) if len(pct) else None,
                                                      len(pct), _np_ptr(stats), _np_ptr(hist), _np_ptr(nzero))
+            if st == N.RS_ERR_NOT_PINNED and mapped is None:
+                st = None                                   # pageable tiles: copy them
+        if st is not None:
+            pass
         elif tiles_per_chunk is None:
             st = self.lib.rs_zonal_stats_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
                                               _NODATA_MODES[nodata_mode], int(ddof), _np_ptr(pct) if len(pct) else None,
@@ -181,6 +190,16 @@ class Engine:
                                                      len(pct), int(tiles_per_chunk), _np_ptr(stats), _np_ptr(hist), _np_ptr(nzero))
         N.check(st, "rs_zonal_stats_host", self._ctx)
         return (stats, hist, nzero) if want_hist else stats
+
+    def pin_host(self, array: np.ndarray) -> np.ndarray:
+        """Page-lock a numpy buffer in place (rs_host_register) so that zonal_stats_host reads it without a copy; call
+        unpin_host before the array is freed.  Returns the array."""
+        st = self.lib.rs_host_register(self._ctx, array.ctypes.data, array.nbytes)
+        N.check(st, "rs_host_register", self._ctx)
+        return array
+
+    def unpin_host(self, array: np.ndarray) -> None:
+        N.check(self.lib.rs_host_unregister(self._ctx, array.ctypes.data), "rs_host_unregister", self._ctx)
 
     def rasterize_pairs_host(self, roads: RoadSet, gt: np.ndarray, height: int, width: int, pairs: PairList,
                              window: str = "crop") -> np.ndarray:

@@ -656,3 +656,26 @@ def test_mapped_host_tiles_equal_resident(eng):
     assert np.array_equal(got[0], ref[0], equal_nan=True)
     with pytest.raises(Exception, match="RS_ERR_NOT_PINNED"):
         eng.zonal_stats_host(rr.roads, TileBatch.from_arrays(tiles.copy(), g.transforms()), rr.pairs, mapped=True)
+
+
+def test_pin_host_makes_numpy_tiles_readable_in_place(eng):
+    """rs_host_register: a plain numpy tile buffer is page-locked in place, then read by the kernel without a copy; the
+    default (mapped=None) picks the transport from the buffer"""
+    g = synth.Grid(6, 4)
+    rr = synth.ribbon_roads(g, 30, seed=83)
+    tiles = synth.host_tiles(g, 3)
+    tb = TileBatch.from_arrays(tiles, g.transforms())
+    ref = eng.zonal_stats_host(rr.roads, tb, rr.pairs, want_hist=True, mapped=False)
+    auto = eng.zonal_stats_host(rr.roads, tb, rr.pairs, want_hist=True)                 # pageable: copied
+    assert np.array_equal(auto[1], ref[1]) and np.array_equal(auto[0], ref[0], equal_nan=True)
+    eng.pin_host(tb.pixels)
+    try:
+        for kw in (dict(mapped=True), dict()):
+            got = eng.zonal_stats_host(rr.roads, tb, rr.pairs, want_hist=True, **kw)
+            assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+            assert np.array_equal(got[0], ref[0], equal_nan=True)
+        eng.pin_host(tb.pixels)                                                          # already page-locked: no-op
+    finally:
+        eng.unpin_host(tb.pixels)
+    with pytest.raises(Exception, match="RS_ERR_NOT_PINNED"):
+        eng.zonal_stats_host(rr.roads, tb, rr.pairs, mapped=True)
