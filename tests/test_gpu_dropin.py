@@ -518,3 +518,31 @@ def test_roads_in_quarries_within_join(mods):
     inq, _ = dc.get_roads_in_quarries([big, holed, notch], rd)
     got = sorted(zip(inq["OBJECTID"].tolist(), inq["index_right"].tolist()))
     assert got == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (3, 0), (4, 0), (5, 0), (5, 1), (6, 0), (6, 1), (6, 2), (7, 0)]
+
+
+def test_statistical_analysis_example_end_to_end(tmp_path):
+    """examples/statistical_analysis_b200.py: GeoTIFF tiles on disk -> ingest -> pairs -> statistics -> pixel table ->
+    ratios -> per-type statistics -> KS, checked for consistency between the accumulator path and the pixel-table path"""
+    pytest.importorskip("PIL.Image")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sa_example", os.path.join(os.path.dirname(__file__), "..", "examples",
+                                                                             "statistical_analysis_b200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--out", str(tmp_path), "--tiles-x", "4", "--tiles-y", "3", "--roads", "14"])
+    grid = synth.Grid(4, 3)
+    assert np.array_equal(out["tiles"].pixels, synth.host_tiles(grid, 4, "asphalt"))          # the ingest read back what was written
+    assert np.allclose(out["tiles"].gt, grid.transforms(), rtol=0, atol=1e-6)
+    px, st = out["pixels_per_band"], out["roads_stats"]
+    assert len(st) > 5 and len(px) == int(st["count"].sum())
+    for b in range(1, 5):                       # per-road statistics from the accumulators == pandas on the pixel table
+        grp = ostats.get_df_stats_groupby(px, f"band{b}", ["road_id"], f"_{b}")
+        m = st.merge(grp, on="road_id", suffixes=("", "_tbl"))
+        assert len(m) == len(st)
+        for c in ("min", "max", "median", "mean", "std", "margin"):
+            a, e = m[f"{c}_{b}"].to_numpy(float), m[f"{c}_{b}_tbl"].to_numpy(float)
+            assert np.allclose(a, e, rtol=0, atol=0.0051, equal_nan=True), (c, b)
+    assert {"R/G", "B/NIR", "VgNIR-BI"} <= set(px.columns)
+    assert sorted(out["cover_stats"]["cover"].unique().tolist()) == sorted(np.unique(out["road_type"]).tolist())
+    assert os.path.exists(os.path.join(str(tmp_path), "tables", "ks_test.csv"))
+    assert {"ks_p_band1", "ks_D_band4"} <= set(out["ks"].columns)
