@@ -105,9 +105,10 @@ def main(argv=None) -> dict:
         h = hist.copy()
         h[:, :, 0] -= np.minimum(h[:, :, 0], n_allzero[:, None])     # the pixel table drops all-zero pixels
         for b in BANDS:
-            res = fs.ks_test_from_hists(h[keep][:, b - 1], road_type[keep])
-            ks[f"ks_p_band{b}"] = res["ks_p"].to_numpy()
-            ks[f"ks_D_band{b}"] = res["ks_D"].to_numpy()
+            # every road against ALL pixels of its type (pixels_per_band is not filtered, :447), reported for the kept roads
+            res = fs.ks_test_from_hists(h[:, b - 1], road_type)
+            ks[f"ks_p_band{b}"] = res["ks_p"].to_numpy()[keep]
+            ks[f"ks_D_band{b}"] = res["ks_D"].to_numpy()[keep]
         ks.to_csv(os.path.join(tables, "ks_test.csv"), index=False)
         written_files.append(os.path.join(tables, "ks_test.csv"))
 
