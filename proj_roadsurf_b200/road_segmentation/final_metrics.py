@@ -95,9 +95,10 @@ def best_threshold(f1b: Sequence[float], Pb: Sequence[float], thresholds: Sequen
 
 
 def threshold_sweep(joint_hist: np.ndarray, gt_class: np.ndarray, thresholds=None, rule: str = "count",
-                    min_area_frac: float = 0.0):
+                    min_area_frac: float = 0.0, *, return_scores: bool = False):
     """The 20-threshold loop of final_metrics.py:277-316 on raster accumulators, one GPU launch.
-    Returns (all_metrics_by_class, all_global_metrics, best_index, best_threshold, cover)."""
+    Returns (all_metrics_by_class, all_global_metrics, best_index, best_threshold, cover[, scores (T, R, 3) = artificial
+    index, natural index, |difference| when return_scores])."""
     thresholds = np.arange(0, 1., 0.05) if thresholds is None else np.asarray(thresholds, float)
     cover, scores, conf, met = determine_class.raster_vote(joint_hist, gt_class, thresholds, rule, min_area_frac)
     by_class, glob = [], []
@@ -110,6 +111,8 @@ def threshold_sweep(joint_hist: np.ndarray, gt_class: np.ndarray, thresholds=Non
     all_by_class = pd.concat(by_class, ignore_index=True)
     all_global = pd.concat(glob, ignore_index=True)
     bi, bt = best_threshold(all_global['f1b'].tolist(), all_global['Pb'].tolist(), thresholds)
+    if return_scores:
+        return all_by_class, all_global, bi, bt, cover, scores
     return all_by_class, all_global, bi, bt, cover
 
 

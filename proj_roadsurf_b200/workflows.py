@@ -61,7 +61,8 @@ def road_surface_vote(roads: RoadSet, detection_tiles: TileBatch, gt_class: np.n
     if pairs is None:
         pairs = pair_list(roads, detection_tiles, eng)
     jh = determine_class.accumulate_class_planes(roads, detection_tiles, pairs, eng)
-    by_class, glob, bi, bt, cover = final_metrics.threshold_sweep(jh, gt_class, thresholds, rule, min_area_frac)
+    by_class, glob, bi, bt, cover, scores = final_metrics.threshold_sweep(jh, gt_class, thresholds, rule, min_area_frac,
+                                                                          return_scores=True)
     ids = np.arange(roads.n_roads) if roads.ids is None else roads.ids
     gt = np.asarray(gt_class)
     known = (gt == 0) | (gt == 1)
@@ -71,5 +72,9 @@ def road_surface_vote(roads: RoadSet, detection_tiles: TileBatch, gt_class: np.n
         "CATEGORY": np.where(gt[known] == 0, "artificial", "natural"),
     })
     comparison["tag"] = final_metrics.tags_from_codes(cover[bi][known], gt[known])
+    # art_score / nat_score rounded to 3 decimals, diff_score as is (determine_class.py:150-167)
+    comparison["art_score"] = np.round(scores[bi][known, 0], 3)
+    comparison["nat_score"] = np.round(scores[bi][known, 1], 3)
+    comparison["diff_score"] = scores[bi][known, 2]
     return {"by_class": by_class, "global_metrics": glob, "best_index": bi, "best_threshold": bt, "comparison": comparison,
             "joint_hist": jh}

@@ -546,3 +546,30 @@ def test_statistical_analysis_example_end_to_end(tmp_path):
     assert sorted(out["cover_stats"]["cover"].unique().tolist()) == sorted(np.unique(out["road_type"]).tolist())
     assert os.path.exists(os.path.join(str(tmp_path), "tables", "ks_test.csv"))
     assert {"ks_p_band1", "ks_D_band4"} <= set(out["ks"].columns)
+
+
+def test_final_metrics_example_end_to_end(tmp_path):
+    """examples/final_metrics_b200.py: quarries rule -> raster vote sweep -> tags / metrics -> diff-score sweep -> calibration
+    bins; the vote of the example is re-derived with the oracle from the same accumulators"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fm_example", os.path.join(os.path.dirname(__file__), "..", "examples",
+                                                                             "final_metrics_b200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--out", str(tmp_path), "--tiles-x", "5", "--tiles-y", "4", "--roads", "40"])
+    keep, comp = out["keep"], out["comparison"]
+    assert len(out["in_quarries"]) > 0 and len(keep) + out["in_quarries"]["OBJECTID"].nunique() == 40
+    assert set(comp["road_id"]) <= set(keep.tolist())
+    assert set(comp["tag"]) <= {"TP", "FN", "wrong class"}
+    assert len(out["accuracy_tables"]) == 4 and all(list(t.columns) == ["threshold", "accuracy"] for t in out["accuracy_tables"])
+    # oracle re-derivation of the best-threshold vote from the joint histogram the workflow returns
+    jh = out["vote"]["joint_hist"]
+    thr = np.arange(0, 1., 0.05)
+    bi = out["vote"]["best_index"]
+    from proj_roadsurf_b200.road_segmentation.determine_class import score_cutoffs
+    cover_o = ovote.raster_vote(jh, int(score_cutoffs(thr)[bi]), rule="score", min_area_frac=0.05)[0]
+    known = np.isin(out["gt_class"][keep], (0, 1))
+    names = np.array(["artificial", "natural", "undetermined", "undetected"], dtype=object)
+    assert comp["cover_type"].tolist() == names[np.asarray(cover_o)[known]].tolist()
+    for f in ("by_class_metrics.csv", "global metrics.csv", "comparison_best_threshold.csv"):
+        assert os.path.exists(os.path.join(str(tmp_path), "tables", f))
