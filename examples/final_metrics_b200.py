@@ -43,7 +43,7 @@ def main(argv=None) -> dict:
     grid = synth.Grid(args.tiles_x, args.tiles_y)
     rr = synth.ribbon_roads(grid, args.roads, seed=11)
     roads, gt_class = rr.roads, rr.gt_class
-    ids = np.arange(roads.n_roads)
+    ids = np.arange(roads.n_roads) if roads.ids is None else np.asarray(roads.ids)
     detections = TileBatch.from_arrays(synth.host_tiles(grid, 2, "class_score"), grid.transforms())
 
     print("-- Roads in quarries are always naturals...")
@@ -55,13 +55,14 @@ def main(argv=None) -> dict:
     roads_df = pd.DataFrame({"OBJECTID": ids, "CATEGORY": np.where(gt_class == 0, "artificial", "natural"), "geometry": geoms})
     in_quarries, filtered = determine_class.get_roads_in_quarries([quarry], roads_df)       # already buffered geometry
     print(f"{len(in_quarries)} roads lie within the quarry and are set aside")
-    keep = filtered["OBJECTID"].to_numpy()
+    keep = np.nonzero(np.isin(ids, filtered["OBJECTID"].to_numpy()))[0]          # positions of the remaining roads
 
     print("Determining the detected class of every road for every threshold...")
     sub = roads.subset(keep)
     res = workflows.road_surface_vote(sub, detections, gt_class[keep], rule="score", min_area_frac=0.05)
     comparison = res["comparison"].copy()
-    comparison["road_id"] = keep[comparison["road_id"].to_numpy()]
+    if roads.ids is None:                                    # road_id counts the roads of `sub`: back to the ids of `roads`
+        comparison["road_id"] = ids[keep][comparison["road_id"].to_numpy()]
     comparison["gt_type"] = "val"
     print(f"best threshold {res['best_threshold']}: f1b = {res['global_metrics']['f1b'][res['best_index']]:.3f}")
 

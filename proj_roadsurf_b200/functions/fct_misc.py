@@ -110,10 +110,8 @@ def _open_geotiff(path) -> Optional[dict]:
         return None
     try:
         tb = ingest.load_tiles([path], threads=1)
-    except ingest.UnsupportedTiff:
+    except Exception:  # noqa: BLE001  (a layout outside the ingest's scope, or a host without the GPU: decode with PIL)
         return _open_geotiff_pil(path)
-    except Exception:  # noqa: BLE001
-        return None
     return {"data": tb.pixels[0], "transform": tuple(float(v) for v in tb.gt[0]), "nodata": tb.nodata}
 
 

@@ -559,7 +559,8 @@ def test_final_metrics_example_end_to_end(tmp_path):
     out = mod.main(["--out", str(tmp_path), "--tiles-x", "5", "--tiles-y", "4", "--roads", "40"])
     keep, comp = out["keep"], out["comparison"]
     assert len(out["in_quarries"]) > 0 and len(keep) + out["in_quarries"]["OBJECTID"].nunique() == 40
-    assert set(comp["road_id"]) <= set(keep.tolist())
+    ids = np.arange(40) if out["roads"].ids is None else np.asarray(out["roads"].ids)
+    assert set(comp["road_id"]) <= set(ids[keep].tolist())
     assert set(comp["tag"]) <= {"TP", "FN", "wrong class"}
     assert len(out["accuracy_tables"]) == 4 and all(list(t.columns) == ["threshold", "accuracy"] for t in out["accuracy_tables"])
     # oracle re-derivation of the best-threshold vote from the joint histogram the workflow returns
