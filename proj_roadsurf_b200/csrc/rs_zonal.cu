@@ -1125,9 +1125,13 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     a.one = 1u;
     a.fast = (tiles->width % 8 == 0) && (((uintptr_t)tiles->pixels & 15u) == 0);
     if (tiles->pixels) {
+        // where do the tiles live?  (the first tile this launch reads: a streamed chunk is addressed through a shifted base)
+        const size_t tile_bytes = (size_t)tiles->height * tiles->width * tiles->channels * (tiles->dtype == RS_U16 ? 2 : 1);
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, tiles->pixels) == cudaSuccess) a.sparse = attr.type == cudaMemoryTypeHost;
-        else cudaGetLastError();
+        if (cudaPointerGetAttributes(&attr, (const uint8_t *)tiles->pixels + (size_t)tile_lo * tile_bytes) == cudaSuccess)
+            a.sparse = attr.type == cudaMemoryTypeHost;
+        else
+            cudaGetLastError();
     }
 
     int HC = 0;
