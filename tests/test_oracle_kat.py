@@ -222,3 +222,24 @@ def test_polygon_within_known_answers():
     assert not W([ring((1, 6), (9, 6), (9, 8), (1, 8))], notch)                # all vertices inside, bridges the notch
     assert W([ring((1, 1), (9, 1), (9, 3), (1, 3))], notch)
     assert not W(big, [ring((1, 1), (3, 1), (3, 3), (1, 3))])                  # contains, not within
+
+
+def test_bin_accuracy_known_answers():
+    """calibration bins of final_metrics.py:541-571 (oracle/vote.bin_accuracy): hand-counted.  The lower bound of a bin is
+    threshold - 0.5 (the reference's constant), so a score of 0.30 falls in every bin from 0.30 to 0.75."""
+    import pandas as pd
+    from oracle import vote as ovote
+    df = pd.DataFrame({
+        "art_score": [0.30, 0.30, 0.90, 0.10], "nat_score": [0.10, 0.20, 0.00, 0.80], "diff_score": [0.20, 0.10, 0.90, 0.70],
+        "CATEGORY": ["artificial", "artificial", "artificial", "natural"],
+        "cover_type": ["artificial", "natural", "artificial", "natural"], "gt_type": ["val"] * 4})
+    t = ovote.bin_accuracy(df)
+    assert [x.name for x in t] == ["artifical score for val", "natural score for val", "score diff in artificial roads for val",
+                                   "score diff in natural roads for val"]
+    art = dict(zip(np.round(t[0]["threshold"], 2), t[0]["accuracy"]))
+    # artificial roads: scores 0.30 (hit), 0.30 (miss), 0.90 (hit).  Bin 0.30 holds the first two; bins 0.90-1.00 hold the
+    # third only (0.30 is no longer above threshold - 0.5); bins 0.80 and 0.85 are empty.
+    assert art[0.3] == 0.5 and art[0.75] == 0.5 and 0.85 not in art and 0.25 not in art
+    assert art[0.9] == 1.0 and art[1.0] == 1.0 and 0.8 not in art
+    nat = dict(zip(np.round(t[1]["threshold"], 2), t[1]["accuracy"]))
+    assert nat[0.8] == 1.0 and 0.75 not in nat                      # the only natural road has nat_score 0.80
