@@ -84,6 +84,39 @@ def metrics_frames(conf: np.ndarray, met: np.ndarray, CLASSES=('artificial', 'na
     return metrics_df, global_metrics_df
 
 
+CLASSES = ['artificial', 'natural']          # final_metrics.py:186 (module-level constant of the reference script)
+
+
+def show_metrics(metrics_by_class, global_metrics):
+    """final_metrics.py:107-123: log the by-class precision / recall and the balanced f1, precision and recall."""
+    for metric in metrics_by_class.itertuples():
+        logger.info(f"The {metric.cover_class} roads have a precision of {round(metric.Pk, 2)}"
+                    + f" and a recall of {round(metric.Rk, 2)}.")
+    logger.info(f"The final f1-score is {round(global_metrics.f1b[0], 2)}"
+                + f" with a precision of {round(global_metrics.Pb[0], 2)} and a recall of"
+                + f" {round(global_metrics.Rb[0], 2)}.")
+
+
+def from_preds_to_metrics(predictions, ground_truth, by_class_metrics, global_metrics, dataset_name, threshold=0, show=False):
+    """final_metrics.py:126-159: detected class of every road at ``threshold`` (determine_detected_class), tags, metrics,
+    appended to the running by-class and global tables with their ``dataset`` and ``threshold`` columns.
+    Returns (comparison_df, by_class_metrics, global_metrics)."""
+    comparison_df = determine_class.determine_detected_class(predictions, ground_truth, threshold)
+    cover = comparison_df['cover_type'].map(COVER_CODE).fillna(-1).to_numpy().astype(np.int8)
+    gt = comparison_df['CATEGORY'].map(determine_class.CLASS_CODE).fillna(-1).to_numpy().astype(np.int8)
+    comparison_df['tag'] = tags_from_codes(cover, gt)                    # get_tag row by row in the reference
+    dst_metrics_by_class, dst_global_metrics = get_metrics(comparison_df, CLASSES)
+    if show:
+        show_metrics(dst_metrics_by_class, dst_global_metrics)
+    dst_metrics_by_class['dataset'] = dataset_name
+    dst_metrics_by_class['threshold'] = threshold
+    by_class_metrics = pd.concat([by_class_metrics, dst_metrics_by_class], ignore_index=True)
+    dst_global_metrics['dataset'] = dataset_name
+    dst_global_metrics['threshold'] = threshold
+    global_metrics = pd.concat([global_metrics, dst_global_metrics], ignore_index=True)
+    return comparison_df, by_class_metrics, global_metrics
+
+
 def best_threshold(f1b: Sequence[float], Pb: Sequence[float], thresholds: Sequence[float]):
     """final_metrics.py:295-312: maximise f1b, a tie goes to the larger Pb, otherwise the earlier threshold;
     the first threshold is reported as 0, later ones as round(threshold, 2)."""

@@ -107,6 +107,12 @@ def test_vote_and_metrics_golden(mods):
         assert_frame_matches(step["global"], glob)
     one = determine_class.determine_detected_class(preds, roads, thresholds[3])
     assert one["cover_type"].tolist() == frame(g["sweep"][3]["comparison"])["cover_type"].tolist()
+    # from_preds_to_metrics (final_metrics.py:126-159): the same step through the reference's accumulating call
+    comp, bc, gl = final_metrics.from_preds_to_metrics(preds, roads, pd.DataFrame(), pd.DataFrame(), "val", thresholds[3], show=True)
+    assert comp["tag"].tolist() == frame(g["sweep"][3]["comparison"])["tag"].tolist()
+    assert bc["dataset"].tolist() == ["val", "val"] and gl["threshold"].tolist() == [thresholds[3]]
+    assert_frame_matches(g["sweep"][3]["by_class"], bc.drop(columns=["dataset", "threshold"]))
+    assert_frame_matches(g["sweep"][3]["global"], gl.drop(columns=["dataset", "threshold"]))
 
 
 def test_zonal_stats_like_rasterstats(mods):
