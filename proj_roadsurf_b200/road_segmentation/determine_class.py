@@ -196,6 +196,48 @@ def get_weighted_scores_raster(roads: RoadSet, instance_tiles: TileBatch, pairs:
                          "area_pred_in_label": frac[keep], "weighted_score": frac[keep] * score[keep]})
 
 
+def detections_to_planes(detections, tiles: TileBatch, engine=None, batch_pairs: int = 1024):
+    """Burn detection polygons into the raster inputs of the vote: the detector's output is a table of polygons with
+    ``score`` and ``det_class`` (0 / 1, determine_class.py:19-28) in the CRS of the tiles.  Every (detection, tile) pair is
+    rasterized on the GPU with the same pixel-centre fill as the roads (rs_rasterize_pairs_host); detections are laid down in
+    ascending score order, so where two overlap the more confident one is kept.
+    Returns (class_score, instance): TileBatch (T, H, W, 2) uint8 -- class plane 0 none / 1 artificial / 2 natural and score
+    plane rint(score * 255) -- for accumulate_class_planes / road_surface_vote, and TileBatch (T, H, W, 1) uint16 holding
+    1 + the row number of the detection for get_weighted_scores_raster."""
+    eng = engine or default_engine()
+    n = len(detections)
+    if n >= 65535:
+        raise ValueError("at most 65534 detections per call (uint16 instance plane)")
+    T, H, W = tiles.n_tiles, tiles.height, tiles.width
+    cs = np.zeros((T, H, W, 2), np.uint8)
+    inst = np.zeros((T, H, W, 1), np.uint16)
+    if n:
+        score = np.asarray(detections['score'], float)
+        det_class = np.asarray(detections['det_class'])
+        if not np.isin(det_class, (0, 1)).all():
+            logger.error(f"Unexpected class: {det_class[~np.isin(det_class, (0, 1))][0]}")
+            sys.exit(1)
+        order = np.argsort(score, kind="stable")
+        dets = RoadSet.from_geometries([list(detections['geometry'])[i] for i in order])
+        from ..geometry import pairs_by_bbox
+        pairs = pairs_by_bbox(dets, tiles)
+        road_of = pairs.road_of_pair()
+        q = np.rint(score * 255.0).clip(0, 255).astype(np.uint8)
+        for lo in range(0, pairs.n_pairs, batch_pairs):            # masks are (pairs, H, W) bytes: bounded batches
+            hi = min(pairs.n_pairs, lo + batch_pairs)
+            sub = PairList.from_pairs(dets.n_roads, road_of[lo:hi], pairs.pair_tile[lo:hi])
+            masks = eng.rasterize_pairs_host(dets, tiles.gt, H, W, sub, window="crop")
+            sub_road = sub.road_of_pair()
+            for k in range(sub.n_pairs):                           # pair order = ascending score
+                d = int(order[sub_road[k]])
+                m = masks[k] != 0
+                t = int(sub.pair_tile[k])
+                cs[t, :, :, 0][m] = 1 + int(det_class[d])
+                cs[t, :, :, 1][m] = q[d]
+                inst[t, :, :, 0][m] = d + 1
+    return (TileBatch(cs, tiles.gt, H, W, 2, None, tiles.ids), TileBatch(inst, tiles.gt, H, W, 1, None, tiles.ids))
+
+
 def score_cutoffs(thresholds: Sequence[float]) -> np.ndarray:
     """smallest uint8 score s with s / 255 >= threshold (256: none)"""
     s = np.arange(256) / 255.0

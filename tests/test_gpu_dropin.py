@@ -580,3 +580,38 @@ def test_final_metrics_example_end_to_end(tmp_path):
     assert comp["cover_type"].tolist() == names[np.asarray(cover_o)[known]].tolist()
     for f in ("by_class_metrics.csv", "global metrics.csv", "comparison_best_threshold.csv"):
         assert os.path.exists(os.path.join(str(tmp_path), "tables", f))
+
+
+def test_detections_to_planes(mods):
+    """determine_class.detections_to_planes: detection polygons (score, det_class) burnt into the class / score / instance
+    planes of the raster vote, against the oracle fill composed in ascending score order"""
+    dc = mods[3]
+    g = synth.Grid(3, 2)
+    gt = g.transforms()
+    rng = np.random.default_rng(21)
+    X0, Y1 = g.origin
+    span = g.span
+    dets, rows = [], []
+    for i in range(25):
+        c = np.array([X0 + rng.uniform(0, 3 * span), Y1 - rng.uniform(0, 2 * span)])
+        ang = np.sort(rng.uniform(0, 2 * np.pi, 7))
+        rad = rng.uniform(5, 45, 7)
+        pts = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        dets.append({"type": "Polygon", "coordinates": [np.concatenate([pts, pts[:1]]).tolist()]})
+        rows.append((float(np.round(rng.uniform(0.05, 1.0), 3)), int(rng.integers(0, 2))))
+    df = pd.DataFrame({"geometry": dets, "score": [r[0] for r in rows], "det_class": [r[1] for r in rows]})
+    tiles = TileBatch(None, gt, 256, 256, 1)
+    cs, inst = dc.detections_to_planes(df, tiles, batch_pairs=7)
+    exp_cs = np.zeros((6, 256, 256, 2), np.uint8)
+    exp_in = np.zeros((6, 256, 256, 1), np.uint16)
+    for d in np.argsort(df["score"].to_numpy(), kind="stable"):
+        ring = [np.array(dets[d]["coordinates"][0])]
+        for t in range(6):
+            m = oraster.pair_inside_mask(gt[t], ring, 256, 256) != 0
+            exp_cs[t, :, :, 0][m] = 1 + rows[d][1]
+            exp_cs[t, :, :, 1][m] = int(np.rint(rows[d][0] * 255.0))
+            exp_in[t, :, :, 0][m] = d + 1
+    assert exp_in.any() and (exp_cs[..., 0] == 2).any()
+    assert np.array_equal(cs.pixels, exp_cs) and np.array_equal(inst.pixels, exp_in)
+    with pytest.raises(SystemExit):
+        dc.detections_to_planes(pd.DataFrame({"geometry": dets[:1], "score": [0.5], "det_class": [3]}), tiles)
