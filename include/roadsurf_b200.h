@@ -265,6 +265,16 @@ int rs_band_ratios_host(rs_ctx *ctx, const uint8_t *values, int64_t n, int32_t c
 int rs_within_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *within);
 
 /*
+ * Overlay areas: scripts/road_segmentation/determine_class.py:107-118 get_weighted_scores =
+ * gpd.overlay(ground_truth, predictions, how='intersection').area and ground_truth.area.  For every candidate pair
+ * (pair_a[k], pair_b[k]) the area of polygon pair_a[k] of `a` intersected with polygon pair_b[k] of `b` (0 when they do not
+ * overlap) -> area_pair[k]; the area of every polygon of `a` -> area_a (may be NULL).  Rings may have either orientation;
+ * holes and parts follow the even-odd rule.  Binary64 boundary integrals: agree with GEOS' noded overlay to rounding.
+ */
+int rs_overlay_area_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, const int32_t *pair_a, const int32_t *pair_b,
+                         int32_t n_pairs, double *area_pair, double *area_a);
+
+/*
  * Calibration bins of scripts/road_segmentation/final_metrics.py:541-571: for every group g (gt_type), value column k
  * and threshold t, counts[g][k][t] = { rows with sel[k][r] != 0 and lo[t] < values[k][r] <= hi[t],  those of them with
  * hit[k][r] != 0 }; the bin accuracy is their quotient where the first is non-zero.  values double[n_cols][n],

@@ -30,7 +30,7 @@ RS_VOTE_COUNT, RS_VOTE_SCORE = 0, 1
 EXPORTS = (
     "rs_version", "rs_status_string", "rs_ctx_create", "rs_ctx_destroy", "rs_ctx_sync_status",
     "rs_ctx_last_cuda_error", "rs_ctx_launch_count", "rs_road_bbox_dev", "rs_zonal_hist_dev",
-    "rs_zonal_hist_host", "rs_zonal_stats_host", "rs_zonal_stats_stream_host", "rs_zonal_stats_mapped_host", "rs_band_ratio_columns", "rs_band_ratios_dev", "rs_band_ratios_host", "rs_bin_counts_host", "rs_within_host", "rs_host_register", "rs_host_unregister", "rs_assemble_tiles_dev", "rs_assemble_tiles_host", "rs_rasterize_pairs_dev", "rs_rasterize_pairs_host", "rs_finalize_stats_dev",
+    "rs_zonal_hist_host", "rs_zonal_stats_host", "rs_zonal_stats_stream_host", "rs_zonal_stats_mapped_host", "rs_band_ratio_columns", "rs_band_ratios_dev", "rs_band_ratios_host", "rs_bin_counts_host", "rs_within_host", "rs_overlay_area_host", "rs_host_register", "rs_host_unregister", "rs_assemble_tiles_dev", "rs_assemble_tiles_host", "rs_rasterize_pairs_dev", "rs_rasterize_pairs_host", "rs_finalize_stats_dev",
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
     "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
     "rs_pairs_bbox_host", "rs_rescale_u16_dev", "rs_rescale_u16_host", "rs_ks_hist_host",
@@ -125,6 +125,7 @@ def load():
     L.rs_assemble_tiles_host.argtypes = L.rs_assemble_tiles_dev.argtypes[:-1]
     L.rs_host_register.argtypes = [P, P, C.c_size_t]
     L.rs_host_unregister.argtypes = [P, P]
+    L.rs_overlay_area_host.argtypes = [P, C.POINTER(RsRoads), C.POINTER(RsRoads), P, P, C.c_int32, P, P]
     L.rs_group_hist_host.argtypes = [P, P, P, C.c_int64, C.c_int32, P]
     L.rs_vote_table_host.argtypes = [P, P, P, P, P, P, C.c_int32, P, C.c_int32, P, P]
     L.rs_confusion_metrics_host.argtypes = [P, P, P, C.c_int32, C.c_int32, P, P]

@@ -708,6 +708,53 @@ int rs_within_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *w
     return finish(ctx);
 }
 
+// polygon index of every ring, built on the host from the CSR offsets and staged in stage[slot]
+static int stage_ring_poly(rs_ctx *ctx, const rs_roads *r, int slot)
+{
+    int32_t *h = (int32_t *)malloc(sizeof(int32_t) * ((size_t)r->n_rings + 1));
+    if (!h) return RS_ERR_INVALID_ARG;
+    for (int i = 0; i < r->n_roads; i++)
+        for (int g = r->road_ring_off[i]; g < r->road_ring_off[i + 1] && g < r->n_rings; g++) h[g] = i;
+    int rc = ensure(ctx, ctx->stage[slot], sizeof(int32_t) * ((size_t)r->n_rings + 1));
+    if (!rc && r->n_rings > 0) {
+        cudaError_t e = cudaMemcpyAsync(ctx->stage[slot].p, h, sizeof(int32_t) * (size_t)r->n_rings, cudaMemcpyHostToDevice, ctx->host_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->host_stream);            // h is freed below
+        if (e != cudaSuccess) { ctx->last_cuda_error = (int)e; rc = RS_ERR_CUDA; }
+    }
+    free(h);
+    return rc;
+}
+
+int rs_overlay_area_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, const int32_t *pair_a, const int32_t *pair_b,
+                         int32_t n_pairs, double *area_pair, double *area_a)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_pairs < 0 || (n_pairs > 0 && (!pair_a || !pair_b || !area_pair))) return RS_ERR_INVALID_ARG;
+    rs_roads da, db;
+    if ((rc = stage_polys(ctx, a, 0, da))) return rc;
+    if ((rc = stage_polys(ctx, b, 4, db))) return rc;
+    for (int i = 0; i < n_pairs; i++)
+        if (pair_a[i] < 0 || pair_a[i] >= a->n_roads || pair_b[i] < 0 || pair_b[i] >= b->n_roads) return RS_ERR_INVALID_ARG;
+    if ((rc = stage_ring_poly(ctx, a, 8))) return rc;
+    if ((rc = stage_ring_poly(ctx, b, 9))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], (size_t)a->n_rings + 1))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], (size_t)b->n_rings + 1))) return rc;
+    if ((rc = up(ctx, ctx->stage[12], pair_a, sizeof(int32_t) * (size_t)n_pairs))) return rc;
+    if ((rc = up(ctx, ctx->stage[13], pair_b, sizeof(int32_t) * (size_t)n_pairs))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[14], sizeof(double) * (size_t)n_pairs))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[15], sizeof(double) * (size_t)a->n_roads))) return rc;
+    rc = launch_overlay_area(ctx, &da, &db, (const int *)ctx->stage[8].p, (const int *)ctx->stage[9].p, (int8_t *)ctx->stage[10].p,
+                             (int8_t *)ctx->stage[11].p, (const int *)ctx->stage[12].p, (const int *)ctx->stage[13].p, n_pairs,
+                             (double *)ctx->stage[14].p, area_a ? (double *)ctx->stage[15].p : nullptr, ctx->host_stream);
+    if (rc) return rc;
+    if (n_pairs > 0)
+        RS_CUDA_OK(ctx, cudaMemcpyAsync(area_pair, ctx->stage[14].p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->host_stream));
+    if (area_a && a->n_roads > 0)
+        RS_CUDA_OK(ctx, cudaMemcpyAsync(area_a, ctx->stage[15].p, sizeof(double) * (size_t)a->n_roads, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
 int rs_ks_hist_host(rs_ctx *ctx, const uint32_t *hist, const int32_t *ref_of_road, const uint64_t *ref_hist, int32_t n_roads,
                     int32_t n_refs, double *D, double *n)
 {

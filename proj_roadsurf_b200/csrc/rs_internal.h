@@ -74,6 +74,9 @@ int launch_confusion(rs_ctx *ctx, const int8_t *cover, const int8_t *gt, int n_r
 int launch_band_ratios(rs_ctx *ctx, const uint8_t *values, long long n, int channels, double *out, cudaStream_t st);
 int launch_bin_counts(rs_ctx *ctx, const double *values, const int8_t *sel, const int8_t *hit, const int *group, int n, int n_cols,
                       int n_groups, const double *lo, const double *hi, int n_thr, int64_t *counts, cudaStream_t st);
+int launch_overlay_area(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, const int *ring_poly_a, const int *ring_poly_b,
+                        int8_t *sign_a, int8_t *sign_b, const int *pair_a, const int *pair_b, int n_pairs, double *area_pair,
+                        double *area_a, cudaStream_t st);
 int launch_within(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *out, cudaStream_t st);
 int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, const rs_lattice *lat, const int *lut_dev,
                       int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);

@@ -222,4 +222,192 @@ int launch_within(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *ou
     return RS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// overlay areas: scripts/road_segmentation/determine_class.py:107-118 get_weighted_scores
+//   gpd.overlay(ground_truth, predictions, how='intersection').area  and  ground_truth.area
+// area(A and B) = closed integral of x dy over the boundary of the intersection = the pieces of A's boundary inside B plus the
+// pieces of B's boundary inside A, every ring taken with its interior on the left.  One warp per candidate pair; lanes take
+// edges, cut them at the crossings with the other polygon (next-cut search, no per-edge crossing capacity) and classify each
+// piece by its midpoint (even-odd over all rings).  A piece lying ON the other boundary is counted once, from A's side, and
+// only when both interiors lie on the same side of it.  Plain binary64: agrees with GEOS' noded overlay to rounding.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// interior-on-the-left sign of every ring: +1 when (counter-clockwise) == (even nesting depth inside its polygon)
+__global__ void __launch_bounds__(128) ring_sign_kernel(const PolySet S, int n_rings_total, const int *__restrict__ ring_poly,
+                                                        int8_t *__restrict__ sign)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_rings_total) return;
+    const int v0 = S.ring_off[g], v1 = S.ring_off[g + 1];
+    if (v1 - v0 < 3) { sign[g] = 0; return; }
+    double a2 = 0.0;
+    for (int k = v0; k < v1; k++) {
+        const double2 p = S.xy[k], q = S.xy[k + 1 < v1 ? k + 1 : v0];
+        a2 = __dadd_rn(a2, __dsub_rn(__dmul_rn(p.x, q.y), __dmul_rn(q.x, p.y)));
+    }
+    const int poly = ring_poly[g];
+    int depth = 0;
+    const double2 rep = S.xy[v0];
+    for (int h = S.road_ring_off[poly]; h < S.road_ring_off[poly + 1]; h++) {
+        if (h == g) continue;
+        PolySet one = S;
+        if (point_in_rings(one, h, h + 1, rep) == 1) depth ^= 1;
+    }
+    const bool ccw = a2 > 0.0;
+    sign[g] = a2 == 0.0 ? 0 : ((ccw != (depth != 0)) ? 1 : -1);
+}
+
+// 0 outside, 1 inside, 2 on the boundary; on_edge / on_ring: the first edge that carries the point
+__device__ int locate(const PolySet &s, int g0, int g1, double2 p, int &on_edge, int &on_ring)
+{
+    int inside = 0;
+    for (int g = g0; g < g1; g++) {
+        const int v0 = s.ring_off[g], v1 = s.ring_off[g + 1];
+        for (int k = v0; k < v1; k++) {
+            const double2 a = s.xy[k], b = s.xy[k + 1 < v1 ? k + 1 : v0];
+            if (a.x == b.x && a.y == b.y) continue;
+            const double o = orient(a, b, p);
+            if (o == 0.0 && fmin(a.x, b.x) <= p.x && p.x <= fmax(a.x, b.x) && fmin(a.y, b.y) <= p.y && p.y <= fmax(a.y, b.y)) {
+                on_edge = k; on_ring = g;
+                return 2;
+            }
+            if ((a.y <= p.y) != (b.y <= p.y)) {
+                const bool up = b.y > a.y;
+                if ((o > 0.0) == up) inside ^= 1;
+            }
+        }
+    }
+    return inside;
+}
+
+// integral of x dy over the pieces of the edges of P (rings [g0, g1)) that lie inside Q, interiors on the left.
+// count_on: pieces on Q's boundary are counted when both interiors are on the same side (P = A), never (P = B).
+__device__ double clipped_boundary_integral(const PolySet &P, int g0, int g1, const int8_t *signP, const PolySet &Q, int h0, int h1,
+                                            const int8_t *signQ, bool count_on, int lane)
+{
+    double sum = 0.0;
+    for (int g = g0; g < g1; g++) {
+        const int r0 = P.ring_off[g], r1 = P.ring_off[g + 1];
+        const double sp = (double)signP[g];
+        if (sp == 0.0) continue;
+        for (int k = r0 + lane; k < r1; k += 32) {
+            const double2 p = P.xy[k], q = P.xy[k + 1 < r1 ? k + 1 : r0];
+            if (p.y == q.y) continue;                         // x dy vanishes on horizontal edges
+            const double ex = __dsub_rn(q.x, p.x), ey = __dsub_rn(q.y, p.y);
+            double t0 = 0.0;
+            while (t0 < 1.0) {
+                // next cut after t0: the smallest crossing parameter with any edge of Q (collinear edges cut at their ends)
+                double t1 = 1.0;
+                for (int h = h0; h < h1; h++) {
+                    const int s0 = Q.ring_off[h], s1 = Q.ring_off[h + 1];
+                    for (int j = s0; j < s1; j++) {
+                        const double2 c = Q.xy[j], d = Q.xy[j + 1 < s1 ? j + 1 : s0];
+                        const double fx = __dsub_rn(d.x, c.x), fy = __dsub_rn(d.y, c.y);
+                        const double den = __dsub_rn(__dmul_rn(ex, fy), __dmul_rn(ey, fx));
+                        const double wx = __dsub_rn(c.x, p.x), wy = __dsub_rn(c.y, p.y);
+                        if (den != 0.0) {
+                            const double t = __ddiv_rn(__dsub_rn(__dmul_rn(wx, fy), __dmul_rn(wy, fx)), den);
+                            const double u = __ddiv_rn(__dsub_rn(__dmul_rn(wx, ey), __dmul_rn(wy, ex)), den);
+                            if (u >= 0.0 && u <= 1.0 && t > t0 && t < t1) t1 = t;
+                        } else if (__dsub_rn(__dmul_rn(wx, ey), __dmul_rn(wy, ex)) == 0.0) {        // collinear
+                            const double ee = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+                            const double tc = __ddiv_rn(__dadd_rn(__dmul_rn(wx, ex), __dmul_rn(wy, ey)), ee);
+                            const double td = __ddiv_rn(__dadd_rn(__dmul_rn(__dsub_rn(d.x, p.x), ex), __dmul_rn(__dsub_rn(d.y, p.y), ey)), ee);
+                            if (tc > t0 && tc < t1) t1 = tc;
+                            if (td > t0 && td < t1) t1 = td;
+                        }
+                    }
+                }
+                const double tm = __dmul_rn(0.5, __dadd_rn(t0, t1));
+                const double2 m = make_double2(__dadd_rn(p.x, __dmul_rn(tm, ex)), __dadd_rn(p.y, __dmul_rn(tm, ey)));
+                int oe = 0, orr = 0;
+                const int where = locate(Q, h0, h1, m, oe, orr);
+                bool take = where == 1;
+                if (where == 2 && count_on) {
+                    const int s0 = Q.ring_off[orr], s1 = Q.ring_off[orr + 1];
+                    const double2 c = Q.xy[oe], d = Q.xy[oe + 1 < s1 ? oe + 1 : s0];
+                    const double dot = __dadd_rn(__dmul_rn(ex, __dsub_rn(d.x, c.x)), __dmul_rn(ey, __dsub_rn(d.y, c.y)));
+                    take = dot * sp * (double)signQ[orr] > 0.0;
+                }
+                if (take) {
+                    const double xa = __dadd_rn(p.x, __dmul_rn(t0, ex)), xb = __dadd_rn(p.x, __dmul_rn(t1, ex));
+                    const double dy = __dmul_rn(__dsub_rn(t1, t0), ey);
+                    sum = __dadd_rn(sum, __dmul_rn(sp, __dmul_rn(__dmul_rn(0.5, __dadd_rn(xa, xb)), dy)));
+                }
+                t0 = t1;
+            }
+        }
+    }
+    return sum;
+}
+
+__global__ void __launch_bounds__(128) overlay_area_kernel(const PolySet A, const int8_t *__restrict__ signA, const PolySet B,
+                                                           const int8_t *__restrict__ signB, const int *__restrict__ pair_a,
+                                                           const int *__restrict__ pair_b, int n_pairs, double *__restrict__ out)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_pairs) return;
+    const int ia = pair_a[w], ib = pair_b[w];
+    const int ga0 = A.road_ring_off[ia], ga1 = A.road_ring_off[ia + 1];
+    const int gb0 = B.road_ring_off[ib], gb1 = B.road_ring_off[ib + 1];
+    double sum = clipped_boundary_integral(A, ga0, ga1, signA, B, gb0, gb1, signB, true, lane);
+    sum = __dadd_rn(sum, clipped_boundary_integral(B, gb0, gb1, signB, A, ga0, ga1, signA, false, lane));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) out[w] = fmax(sum, 0.0);
+}
+
+// even-odd area of every polygon: the sum of the signed shoelace areas of its rings, interiors on the left
+__global__ void __launch_bounds__(128) poly_area_kernel(const PolySet S, const int8_t *__restrict__ sign, double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n) return;
+    double tot = 0.0;
+    for (int g = S.road_ring_off[i]; g < S.road_ring_off[i + 1]; g++) {
+        const int v0 = S.ring_off[g], v1 = S.ring_off[g + 1];
+        double a2 = 0.0;
+        for (int k = v0; k < v1; k++) {
+            const double2 p = S.xy[k], q = S.xy[k + 1 < v1 ? k + 1 : v0];
+            a2 = __dadd_rn(a2, __dsub_rn(__dmul_rn(p.x, q.y), __dmul_rn(q.x, p.y)));
+        }
+        // |a2| / 2 for a ring at even depth, - |a2| / 2 for a hole
+        const double mag = __dmul_rn(0.5, fabs(a2));
+        const bool ccw = a2 > 0.0;
+        tot = __dadd_rn(tot, (sign[g] > 0) == ccw ? mag : -mag);
+    }
+    out[i] = tot;
+}
+
+}  // namespace
+
+// sign_a / sign_b: int8[n_rings] scratch; ring_poly_*: int32[n_rings] polygon of every ring (device)
+int launch_overlay_area(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, const int *ring_poly_a, const int *ring_poly_b,
+                        int8_t *sign_a, int8_t *sign_b, const int *pair_a, const int *pair_b, int n_pairs, double *area_pair,
+                        double *area_a, cudaStream_t st)
+{
+    PolySet A{(const double2 *)a->xy, a->ring_off, a->road_ring_off, a->road_bbox, a->n_roads};
+    PolySet B{(const double2 *)b->xy, b->ring_off, b->road_ring_off, b->road_bbox, b->n_roads};
+    if (a->n_rings > 0) {
+        ring_sign_kernel<<<(a->n_rings + 127) / 128, 128, 0, st>>>(A, a->n_rings, ring_poly_a, sign_a);
+        ctx->launches++;
+    }
+    if (b->n_rings > 0) {
+        ring_sign_kernel<<<(b->n_rings + 127) / 128, 128, 0, st>>>(B, b->n_rings, ring_poly_b, sign_b);
+        ctx->launches++;
+    }
+    if (area_a && a->n_roads > 0) {
+        poly_area_kernel<<<(a->n_roads + 127) / 128, 128, 0, st>>>(A, sign_a, area_a);
+        ctx->launches++;
+    }
+    if (n_pairs > 0) {
+        const long long blocks = ((long long)n_pairs * 32 + 127) / 128;
+        if (blocks > 0x7fffffffLL) return RS_ERR_UNSUPPORTED;
+        overlay_area_kernel<<<(unsigned)blocks, 128, 0, st>>>(A, sign_a, B, sign_b, pair_a, pair_b, n_pairs, area_pair);
+        ctx->launches++;
+    }
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
 }  // namespace rs

@@ -418,6 +418,26 @@ class Engine:
         N.check(st, "rs_assemble_tiles_host", self._ctx)
         return out
 
+    def overlay_area_host(self, a: RoadSet, b: RoadSet, pair_a, pair_b):
+        """(area of a[pair_a[k]] intersected with b[pair_b[k]] for every k, area of every polygon of ``a``):
+        gpd.overlay(...).area and GeoSeries.area of determine_class.py:107-114 (rs_overlay_area_host)."""
+        pa, pb = np.ascontiguousarray(pair_a, np.int32), np.ascontiguousarray(pair_b, np.int32)
+        assert pa.shape == pb.shape and pa.ndim == 1
+        out = np.zeros(len(pa), np.float64)
+        area_a = np.zeros(a.n_roads, np.float64)
+        keep = []
+        def desc(r):
+            xy = np.ascontiguousarray(r.xy, np.float64)
+            ro, rro = np.ascontiguousarray(r.ring_off, np.int32), np.ascontiguousarray(r.road_ring_off, np.int32)
+            bb = np.ascontiguousarray(r.bbox, np.float64)
+            keep.extend([xy, ro, rro, bb])
+            return self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), r.n_roads, r.n_rings, r.n_verts)
+        da, db = desc(a), desc(b)
+        st = self.lib.rs_overlay_area_host(self._ctx, C.byref(da), C.byref(db), _np_ptr(pa), _np_ptr(pb), len(pa), _np_ptr(out),
+                                           _np_ptr(area_a))
+        N.check(st, "rs_overlay_area_host", self._ctx)
+        return out, area_a
+
     def vote_table_host(self, row_off, cls, score, weighted, area, thresholds):
         """determine_detected_class on a detection table sorted by road (rs_vote_table_host).
         Returns cover (T, R) int8 and scores (T, R, 3) = artificial index, natural index, diff."""

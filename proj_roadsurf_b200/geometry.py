@@ -352,3 +352,21 @@ def rasterio_window(transform, bbox, width: int, height: int):
         return None
     cc0, rr0 = max(c0, 0), max(r0, 0)
     return (cc0, rr0, min(c0 + w, width) - cc0, min(r0 + h, height) - rr0)
+
+
+def bbox_pairs(a_bbox: np.ndarray, b_bbox: np.ndarray, chunk: int = 512):
+    """(ia, ib) of every pair of boxes (xmin, ymin, xmax, ymax) that overlap (closed), ordered by ia then ib: the candidate
+    pairs of gpd.overlay / sjoin before the exact test."""
+    a = np.asarray(a_bbox, np.float64).reshape(-1, 4)
+    b = np.asarray(b_bbox, np.float64).reshape(-1, 4)
+    ia_all, ib_all = [], []
+    for lo in range(0, len(a), chunk):
+        c = a[lo:lo + chunk]
+        hit = ((c[:, None, 0] <= b[None, :, 2]) & (c[:, None, 2] >= b[None, :, 0]) &
+               (c[:, None, 1] <= b[None, :, 3]) & (c[:, None, 3] >= b[None, :, 1]))
+        i, j = np.nonzero(hit)
+        ia_all.append(i + lo)
+        ib_all.append(j)
+    if not ia_all:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    return np.concatenate(ia_all).astype(np.int64), np.concatenate(ib_all).astype(np.int64)

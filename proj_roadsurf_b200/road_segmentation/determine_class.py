@@ -155,6 +155,41 @@ def accumulate_class_planes(roads: RoadSet, tiles: TileBatch, pairs: PairList, e
     return hist
 
 
+def get_weighted_scores(ground_truth, predictions, engine=None):
+    """determine_class.py:97-120 in its vector form: the overlay of the labels with the predictions, the share of every label
+    covered by every prediction (rounded to 2 decimals) and the confidence weighted by it; pairs covering 5 % of the label
+    or less are dropped.  ``ground_truth`` / ``predictions``: tables with a 'geometry' column (anything with
+    __geo_interface__, GeoJSON dicts or ring lists), 'BELAGSART' on the labels and 'score' on the predictions.  The areas of
+    gpd.overlay(how='intersection') and GeoSeries.area come from one GPU call (rs_overlay_area_host) over the bounding-box
+    candidate pairs; rows are in (label, prediction) order like the overlay's.  The result carries the columns of both
+    tables (duplicated names get _1 / _2) plus area_label, joined_area, area_pred_in_label, weighted_score; the geometry of
+    the intersections is not materialised (``geometry`` is None), nothing downstream reads it."""
+    from ..geometry import bbox_pairs
+    if hasattr(ground_truth, 'crs') and hasattr(predictions, 'crs'):
+        from ..functions import fct_misc
+        fct_misc.test_crs(ground_truth.crs, predictions.crs)
+    eng = engine or default_engine()
+    a = RoadSet.from_geometries(list(ground_truth['geometry']))
+    b = RoadSet.from_geometries(list(predictions['geometry']))
+    ia, ib = bbox_pairs(a.bbox, b.bbox)
+    joined, area_label = eng.overlay_area_host(a, b, ia, ib)
+    ground_truth['area_label'] = area_label                       # the reference adds the column to its argument too (:107)
+    keep = joined > 0.0                                           # overlay keeps polygonal intersections only
+    ia, ib, joined = ia[keep], ib[keep], joined[keep]
+    left = ground_truth.drop(columns=['geometry']).iloc[ia].reset_index(drop=True)
+    right = predictions.drop(columns=['geometry']).iloc[ib].reset_index(drop=True)
+    dup = set(left.columns) & set(right.columns)
+    left = left.rename(columns={c: f'{c}_1' for c in dup})
+    right = right.rename(columns={c: f'{c}_2' for c in dup})
+    out = pd.concat([left, right], axis=1)
+    out['geometry'] = None
+    out = out[(~out['BELAGSART'].isna()) & (~out['score'].isna())].copy()
+    out['joined_area'] = joined[out.index.to_numpy()]
+    out['area_pred_in_label'] = round(out['joined_area'] / out['area_label'], 2)
+    out['weighted_score'] = out['area_pred_in_label'] * out['score']
+    return out[out.area_pred_in_label > 0.05].copy()
+
+
 def get_weighted_scores_raster(roads: RoadSet, instance_tiles: TileBatch, pairs: PairList, inst_score, inst_class_name,
                                road_ids=None, clip_fact: Optional[float] = None, min_area: float = 0.05, engine=None) -> pd.DataFrame:
     """Instance-faithful raster form of get_weighted_scores (determine_class.py:97-120).

@@ -615,3 +615,65 @@ def test_detections_to_planes(mods):
     assert np.array_equal(cs.pixels, exp_cs) and np.array_equal(inst.pixels, exp_in)
     with pytest.raises(SystemExit):
         dc.detections_to_planes(pd.DataFrame({"geometry": dets[:1], "score": [0.5], "det_class": [3]}), tiles)
+
+
+def test_overlay_areas_and_vector_get_weighted_scores(mods):
+    """rs_overlay_area_host / determine_class.get_weighted_scores (determine_class.py:97-120, vector form) against the
+    strip-decomposition oracle (oracle/overlay.py): hand cases with shared edges, holes, containment and both ring
+    orientations, then random star polygons with holes"""
+    from oracle import overlay as ov
+    from proj_roadsurf_b200.engine import default_engine
+    from test_oracle_kat import ring
+    dc = mods[3]
+    eng = default_engine()
+
+    def sq(x0, y0, x1, y1, cw=False):
+        r = ring((x0, y0), (x1, y0), (x1, y1), (x0, y1))
+        return [r[::-1].copy() if cw else r]
+    A = [sq(0, 0, 4, 3), sq(0, 0, 4, 3, cw=True), sq(0, 0, 10, 10) + sq(4, 4, 6, 6), sq(0, 0, 10, 10, cw=True) + sq(4, 4, 6, 6, cw=True),
+         [ring((0, 0), (4, 0), (0, 4))]]
+    B = [sq(2, 1, 6, 5), sq(4, 0, 6, 3), sq(1, 1, 2, 2, cw=True), sq(3, 3, 7, 7), sq(4.5, 4.5, 5.5, 5.5), sq(0, 0, 2, 2), sq(1, 1, 3, 3),
+         sq(0, 0, 4, 3), sq(-5, -5, 20, 20) + sq(1, 1, 3, 2)]
+    ia, ib = np.repeat(np.arange(len(A)), len(B)), np.tile(np.arange(len(B)), len(A))
+    got, area_a = eng.overlay_area_host(RoadSet.from_geometries(A), RoadSet.from_geometries(B), ia, ib)
+    exp = np.array([ov.intersection_area(A[i], B[j]) for i, j in zip(ia, ib)])
+    assert np.array_equal(got, exp), np.stack([ia, ib, got, exp], 1)[got != exp]     # small integers and halves: exact
+    assert area_a.tolist() == [12.0, 12.0, 96.0, 96.0, 8.0]
+
+    rng = np.random.default_rng(31)
+
+    def star(c, rmin, rmax, n):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        rad = rng.uniform(rmin, rmax, n)
+        pts = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        return pts[::-1].copy() if rng.random() < 0.5 else pts
+    labels, preds = [], []
+    for i in range(40):
+        c = rng.uniform(0, 100, 2)
+        rings_ = [star(c, 6, 14, int(rng.integers(5, 24)))]
+        if i % 3 == 0:
+            rings_.append(star(c, 1, 3, 6))                        # a hole around the centre
+        labels.append(rings_)
+    for j in range(60):
+        preds.append([star(rng.uniform(0, 100, 2), 3, 12, int(rng.integers(4, 30)))])
+    a, b = RoadSet.from_geometries(labels), RoadSet.from_geometries(preds)
+    from proj_roadsurf_b200.geometry import bbox_pairs
+    ia, ib = bbox_pairs(a.bbox, b.bbox)
+    assert len(ia) > 100
+    got, area_a = eng.overlay_area_host(a, b, ia, ib)
+    exp = np.array([ov.intersection_area(labels[i], preds[j]) for i, j in zip(ia, ib)])
+    assert np.allclose(got, exp, rtol=1e-9, atol=1e-9) and (exp > 1.0).sum() > 30
+    assert np.allclose(area_a, [ov.polygon_area(l) for l in labels], rtol=1e-12)
+    # the table form
+    score = np.round(rng.uniform(0.05, 1.0, len(preds)), 3)
+    gt_df = pd.DataFrame({"OBJECTID": np.arange(len(labels)) + 500, "BELAGSART": 100, "geometry": labels})
+    pr_df = pd.DataFrame({"score": score, "det_class_name": "artificial", "geometry": preds})
+    out = dc.get_weighted_scores(gt_df, pr_df)
+    rows = ov.get_weighted_scores(labels, preds, score)
+    assert len(rows) > 20 and len(out) == len(rows)
+    assert out["OBJECTID"].tolist() == [500 + r[0] for r in rows]
+    assert np.allclose(out["score"].to_numpy(), [score[r[1]] for r in rows])
+    assert np.allclose(out["joined_area"].to_numpy(), [r[2] for r in rows], rtol=1e-9)
+    assert out["area_pred_in_label"].tolist() == [r[3] for r in rows]
+    assert np.allclose(out["weighted_score"].to_numpy(), [r[4] for r in rows], rtol=1e-12)
+    assert "area_label" in gt_df.columns

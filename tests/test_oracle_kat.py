@@ -243,3 +243,24 @@ def test_bin_accuracy_known_answers():
     assert art[0.9] == 1.0 and art[1.0] == 1.0 and 0.8 not in art
     nat = dict(zip(np.round(t[1]["threshold"], 2), t[1]["accuracy"]))
     assert nat[0.8] == 1.0 and 0.75 not in nat                      # the only natural road has nat_score 0.80
+
+
+def test_overlay_area_known_answers():
+    """area of polygon intersections (gpd.overlay(how='intersection').area, determine_class.py:110-114), oracle/overlay.py"""
+    from oracle import overlay as ov
+
+    def sq(x0, y0, x1, y1, cw=False):
+        r = ring((x0, y0), (x1, y0), (x1, y1), (x0, y1))
+        return [r[::-1].copy() if cw else r]
+    assert ov.polygon_area(sq(0, 0, 4, 3)) == 12.0 and ov.polygon_area(sq(0, 0, 4, 3, cw=True)) == 12.0
+    assert ov.intersection_area(sq(0, 0, 4, 3), sq(2, 1, 6, 5)) == 4.0
+    assert ov.intersection_area(sq(0, 0, 4, 3), sq(4, 0, 6, 3)) == 0.0             # sharing an edge only
+    assert ov.intersection_area(sq(0, 0, 4, 4), sq(1, 1, 2, 2)) == 1.0             # containment
+    holed = sq(0, 0, 10, 10) + sq(4, 4, 6, 6)
+    assert ov.polygon_area(holed) == 96.0
+    assert ov.intersection_area(holed, sq(3, 3, 7, 7)) == 12.0                      # 16 minus the hole
+    assert ov.intersection_area(holed, sq(4.5, 4.5, 5.5, 5.5)) == 0.0              # inside the hole
+    tri = [ring((0, 0), (4, 0), (0, 4))]
+    assert ov.intersection_area(tri, sq(0, 0, 2, 2)) == 4.0 and ov.intersection_area(tri, sq(1, 1, 3, 3)) == 2.0
+    rows = ov.get_weighted_scores([sq(0, 0, 10, 2)], [sq(0, 0, 5, 2), sq(9.6, 0, 12, 2), sq(20, 0, 21, 1)], [0.9, 0.8, 0.7])
+    assert rows == [(0, 0, 10.0, 0.5, 0.45)]                                        # the second covers 4 % <= 5 %, the third nothing
