@@ -269,7 +269,8 @@ int rs_within_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *w
  * gpd.overlay(ground_truth, predictions, how='intersection').area and ground_truth.area.  For every candidate pair
  * (pair_a[k], pair_b[k]) the area of polygon pair_a[k] of `a` intersected with polygon pair_b[k] of `b` (0 when they do not
  * overlap) -> area_pair[k]; the area of every polygon of `a` -> area_a (may be NULL).  Rings may have either orientation;
- * holes and parts follow the even-odd rule.  Binary64 boundary integrals: agree with GEOS' noded overlay to rounding.
+ * holes and parts follow the even-odd rule; the rings of one polygon must not cross each other (valid polygons, as GEOS
+ * requires too).  Binary64 boundary integrals: agree with GEOS' noded overlay to rounding.
  */
 int rs_overlay_area_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, const int32_t *pair_a, const int32_t *pair_b,
                          int32_t n_pairs, double *area_pair, double *area_a);

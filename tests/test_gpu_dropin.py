@@ -643,14 +643,14 @@ def test_overlay_areas_and_vector_get_weighted_scores(mods):
     rng = np.random.default_rng(31)
 
     def star(c, rmin, rmax, n):
-        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        ang = (np.arange(n) + rng.uniform(0.0, 0.8, n)) * (2 * np.pi / n)     # bounded gaps: a valid ring around c
         rad = rng.uniform(rmin, rmax, n)
         pts = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
         return pts[::-1].copy() if rng.random() < 0.5 else pts
     labels, preds = [], []
     for i in range(40):
         c = rng.uniform(0, 100, 2)
-        rings_ = [star(c, 6, 14, int(rng.integers(5, 24)))]
+        rings_ = [star(c, 6, 14, int(rng.integers(8, 24)))]
         if i % 3 == 0:
             rings_.append(star(c, 1, 3, 6))                        # a hole around the centre
         labels.append(rings_)
