@@ -96,10 +96,17 @@ def get_weighted_scores(labels: List[Sequence[np.ndarray]], preds: List[Sequence
     """rows (label index, prediction index, joined_area, area_pred_in_label, weighted_score) of determine_class.py:107-118:
     every (label, prediction) pair with a positive intersection area, in (label, prediction) order, filtered to
     area_pred_in_label > 0.05 with area_pred_in_label = round(joined_area / area_label, 2)"""
+    def box(rings):
+        v = np.concatenate([np.asarray(r, float) for r in rings])
+        return v[:, 0].min(), v[:, 1].min(), v[:, 0].max(), v[:, 1].max()
+    pb = [box(b) for b in preds]
     rows = []
     for i, a in enumerate(labels):
         area_label = polygon_area(a)
+        ab = box(a)
         for j, b in enumerate(preds):
+            if ab[0] > pb[j][2] or ab[2] < pb[j][0] or ab[1] > pb[j][3] or ab[3] < pb[j][1]:
+                continue                                   # disjoint boxes: no intersection
             joined = intersection_area(a, b)
             if joined <= 0.0:
                 continue
