@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <string.h>
 
 template <int SHAPE>
 __global__ void reader(const uint8_t *base, size_t n_lines, int iters, unsigned long long *sink)
@@ -34,14 +36,8 @@ __global__ void reader(const uint8_t *base, size_t n_lines, int iters, unsigned 
     if (acc == 0x1234567887654321ull) *sink = acc;
 }
 
-int main()
+static void run_all(const char *what, uint8_t *h, size_t bytes, unsigned long long *sink)
 {
-    const size_t bytes = 32ull << 30;
-    uint8_t *h;
-    if (cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess) { printf("alloc failed\n"); return 1; }
-    for (size_t i = 0; i < bytes; i += 4096) h[i] = (uint8_t)i;
-    unsigned long long *sink;
-    cudaMalloc(&sink, 8);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int blocks = 148 * 8, threads = 256, iters = 64;
@@ -58,9 +54,30 @@ int main()
             float ms;
             cudaEventElapsedTime(&ms, e0, e1);
             const double sectors = (double)blocks * threads * iters * (s == 3 ? 2 : 1);
-            if (rep) printf("%-20s %8.2f ms  %7.1f M sectors/s  %6.2f GB/s of sectors\n", names[s], ms, sectors / ms / 1e3, sectors * 32 / ms / 1e6);
+            if (rep) printf("%-12s %-20s %8.2f ms  %7.1f M sectors/s  %6.2f GB/s of sectors\n", what, names[s], ms, sectors / ms / 1e3, sectors * 32 / ms / 1e6);
         }
     }
+}
+
+int main()
+{
+    const size_t bytes = 32ull << 30;
+    unsigned long long *sink;
+    cudaMalloc(&sink, 8);
+    uint8_t *h;
+    if (cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess) { printf("alloc failed\n"); return 1; }
+    for (size_t i = 0; i < bytes; i += 4096) h[i] = (uint8_t)i;
+    run_all("cudaHostAlloc", h, bytes, sink);
+    cudaFreeHost(h);
+    // the same buffer backed by transparent huge pages (2 MiB), page-locked with cudaHostRegister
+    void *m = mmap(nullptr, bytes + (2u << 20), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m == MAP_FAILED) { printf("mmap failed\n"); return 1; }
+    uint8_t *hp = (uint8_t *)(((uintptr_t)m + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1));
+    printf("madvise(MADV_HUGEPAGE) -> %d\n", madvise(hp, bytes, MADV_HUGEPAGE));
+    for (size_t i = 0; i < bytes; i += 4096) hp[i] = (uint8_t)i;
+    cudaError_t e = cudaHostRegister(hp, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    printf("cudaHostRegister -> %s\n", cudaGetErrorString(e));
+    if (e == cudaSuccess) run_all("THP+register", hp, bytes, sink);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

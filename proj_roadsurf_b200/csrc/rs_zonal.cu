@@ -399,32 +399,16 @@ struct PxMask {
     static constexpr bool MASK = true;
 };
 
-// 8 pixels x BPP bytes from a (8*BPP)-byte aligned address into NW words.  m8 is the group's pixel mask: for the 24-byte
-// groups of 3-band tiles (8-byte aligned, so a group can straddle two 32-byte sectors) each 8-byte piece is loaded only
-// when a selected pixel has bytes in it (pixels 0-2 | 2-5 | 5-7); the words of a skipped piece keep their previous
-// contents, which only feed increments of 0.  Fewer sectors per road row: what crosses the host link when the tiles
-// are read in place (rs_zonal_stats_mapped_host, SPARSE); with the tiles in HBM the unconditional loads are faster
-// (9.3 vs 9.95 ms on the benchmark shard).
-template <int BPP, int NW, bool SPARSE>
-__device__ __forceinline__ void load_group(const uint8_t *p, uint32_t (&r)[NW], uint32_t m8)
+// 8 pixels x BPP bytes from a (8*BPP)-byte aligned address into NW words
+template <int BPP, int NW>
+__device__ __forceinline__ void load_group(const uint8_t *p, uint32_t (&r)[NW])
 {
 #ifdef RS_EXP_NOLOAD      // experiment only: how much of the kernel time is pixel-load latency?
 #pragma unroll
     for (int i = 0; i < NW; i++) r[i] = (uint32_t)(uintptr_t)p * 2654435761u + i;
     return;
 #endif
-    if constexpr (BPP == 3 && SPARSE) {
-        asm volatile(
-            "{\n\t.reg .pred p0, p1, p2;\n\t.reg .b32 t;\n\t"
-            "and.b32 t, %6, 0x07;\n\tsetp.ne.u32 p0, t, 0;\n\t"
-            "and.b32 t, %6, 0x3c;\n\tsetp.ne.u32 p1, t, 0;\n\t"
-            "and.b32 t, %6, 0xe0;\n\tsetp.ne.u32 p2, t, 0;\n\t"
-            "@p0 ld.global.nc.v2.u32 {%0, %1}, [%7];\n\t"
-            "@p1 ld.global.nc.v2.u32 {%2, %3}, [%7+8];\n\t"
-            "@p2 ld.global.nc.v2.u32 {%4, %5}, [%7+16];\n\t}"
-            : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5])
-            : "r"(m8), "l"(p));
-    } else if constexpr ((BPP & 1) == 0) {
+    if constexpr ((BPP & 1) == 0) {
 #pragma unroll
         for (int i = 0; i < NW / 4; i++) {
             const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + i);
@@ -458,7 +442,7 @@ struct EdgeParams {                 // the 32 edges of one block, written by the
     int n[32];
     int off[33];
 };
-template <int HC>
+template <int HC, bool SPARSE = false>
 struct alignas(1024) TeamSmem {
     alignas(1024) uint32_t hist[HC > 0 ? HC * 256 : 4];
     alignas(16) double2 verts[VCAP];
@@ -471,6 +455,10 @@ struct alignas(1024) TeamSmem {
     float cb_ymin[NCHUNK], cb_ymax[NCHUNK], cb_xmin[NCHUNK], cb_xmax[NCHUNK];
     int ring_start[RINGCAP + 1];
     alignas(8) uint64_t mbar;
+    // SPARSE (tiles read in place from host memory): one round of 8-byte pieces, at most 3 per entry
+    alignas(8) unsigned long long paddr[SPARSE ? 96 : 1];      // address of every needed piece, in entry order
+    alignas(8) uint2 stage[SPARSE ? 96 : 1];                    // the loaded pieces, slot = 3 * lane of the entry + piece
+    uint8_t pdst[SPARSE ? 96 : 1];
 };
 
 __device__ __forceinline__ uint32_t prefix_xor32(uint32_t t)
@@ -485,7 +473,7 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t m) { return (((m & 0x
 // one work item
 // ---------------------------------------------------------------------------------------------
 template <class PX, bool FAST, bool SPARSE>
-__device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC> &s, const int4 item, const int lane,
+__device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC, SPARSE> &s, const int4 item, const int lane,
                                              uint32_t &mbar_phase)
 {
     const uint32_t hist_addr = smem_u32(s.hist), one = a.one;
@@ -776,16 +764,63 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                         const int yabs = g.row_off + r0 + (int)(en >> 20);
                         return tile_pix + (size_t)yabs * a.W + x8;
                     };
-                    if constexpr (FAST) {
-                        uint32_t rn[PX::NW];
+                    if constexpr (FAST && SPARSE && PX::BPP == 3) {
+                        // Tiles read in place from host memory.  The host link serves a fixed number of read requests per
+                        // second, each up to a 128-byte line (profiles/microbench/sysmem_read.cu: ~330 M/s with 1, 2 or 4
+                        // sectors), and one warp-wide load instruction makes one request per line it touches.  So the loads
+                        // are issued per 8-byte PIECE, not per entry: the needed pieces of a round's entries are listed in
+                        // entry order -- row-major, so the pieces of one road row sit in consecutive lanes -- and each lane
+                        // loads one piece.  A row costs one request instead of one per piece instruction.  The pieces
+                        // come back through shared memory to the lane that owns the entry.
+                        const uint8_t *px = (const uint8_t *)a.pixels;
+                        for (int base = 0; base < n; base += 32) {
+                            const int e = base + lane;
+                            uint32_t en = 0, need = 0;
+                            const uint8_t *gp = px;
+                            if (e < n) {
+                                en = s.u.entries[e];
+                                gp = px + pixel_index(en) * 3;
+                                need = ((en & 0x07u) ? 1u : 0u) | ((en & 0x3cu) ? 2u : 0u) | ((en & 0xe0u) ? 4u : 0u);
+                            }
+                            const int c = __popc(need);
+                            int incl = c;
 #pragma unroll
-                        for (int w = 0; w < PX::NW; w++) rn[w] = 0;
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int v = __shfl_up_sync(FULL, incl, o);
+                                if (lane >= o) incl += v;
+                            }
+                            const int np = __shfl_sync(FULL, incl, 31);
+                            int k = incl - c;
+#pragma unroll
+                            for (int pc = 0; pc < 3; pc++)
+                                if ((need >> pc) & 1u) {
+                                    s.paddr[k] = (unsigned long long)(uintptr_t)(gp + 8 * pc);
+                                    s.pdst[k] = (uint8_t)(3 * lane + pc);
+                                    k++;
+                                }
+                            __syncwarp();
+                            for (int pi = lane; pi < np; pi += 32)
+                                s.stage[s.pdst[pi]] = __ldg(reinterpret_cast<const uint2 *>((uintptr_t)s.paddr[pi]));
+                            __syncwarp();
+                            if (e < n) {
+                                uint32_t r[PX::NW];
+#pragma unroll
+                                for (int pc = 0; pc < 3; pc++) {
+                                    const uint2 v = s.stage[3 * lane + pc];          // pieces that were not loaded feed increments of 0
+                                    r[2 * pc] = v.x; r[2 * pc + 1] = v.y;
+                                }
+                                group_pixels<PX, 0>(a, r, en & 255u, hist_addr, one, nz);
+                            }
+                            __syncwarp();
+                        }
+                    } else if constexpr (FAST) {
+                        uint32_t rn[PX::NW];
                         uint32_t m8n = 0;
                         int e = lane;
                         if (e < n) {
                             const uint32_t en = s.u.entries[e];
                             m8n = en & 255u;
-                            load_group<PX::BPP, PX::NW, SPARSE>((const uint8_t *)a.pixels + pixel_index(en) * PX::BPP, rn, m8n);
+                            load_group<PX::BPP, PX::NW>((const uint8_t *)a.pixels + pixel_index(en) * PX::BPP, rn);
                         }
                         while (e < n) {
                             uint32_t r[PX::NW];
@@ -796,7 +831,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                             if (e < n) {
                                 const uint32_t en = s.u.entries[e];
                                 m8n = en & 255u;
-                                load_group<PX::BPP, PX::NW, SPARSE>((const uint8_t *)a.pixels + pixel_index(en) * PX::BPP, rn, m8n);
+                                load_group<PX::BPP, PX::NW>((const uint8_t *)a.pixels + pixel_index(en) * PX::BPP, rn);
                             }
                             group_pixels<PX, 0>(a, r, m8, hist_addr, one, nz);
                         }
@@ -899,7 +934,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
 template <class PX, bool FAST, bool SPARSE = false>
 __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const ZonalArgs a)
 {
-    using S = TeamSmem<PX::HC>;
+    using S = TeamSmem<PX::HC, SPARSE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if ((smem_u32(smem_raw) & 1023u) != 0u) {       // team histograms must be 1 KiB aligned (band base | bin offset)
@@ -1043,7 +1078,7 @@ int launch_road_bbox(rs_ctx *ctx, const rs_roads *roads, double *out, cudaStream
 template <class PX, bool FAST, bool SPARSE = false>
 static int launch_fast(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
 {
-    using S = TeamSmem<PX::HC>;
+    using S = TeamSmem<PX::HC, SPARSE>;
     const size_t smem = sizeof(S) * WARPS;
     auto kern = zonal_kernel<PX, FAST, SPARSE>;
     RS_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
