@@ -656,6 +656,14 @@ def test_mapped_host_tiles_equal_resident(eng):
     assert np.array_equal(got[0], ref[0], equal_nan=True)
     with pytest.raises(Exception, match="RS_ERR_NOT_PINNED"):
         eng.zonal_stats_host(rr.roads, TileBatch.from_arrays(tiles.copy(), g.transforms()), rr.pairs, mapped=True)
+    for ch in (1, 2, 4):                     # the other band counts read host memory through the resident load path
+        t2 = synth.host_tiles(g, ch)
+        ref2 = eng.zonal_stats_host(rr.roads, TileBatch.from_arrays(t2, g.transforms()), rr.pairs, want_hist=True, mapped=False)
+        pin2 = torch.empty(t2.shape, dtype=torch.uint8, pin_memory=True)
+        pin2.copy_(torch.from_numpy(t2))
+        got2 = eng.zonal_stats_host(rr.roads, TileBatch(pin2.numpy(), g.transforms(), t2.shape[1], t2.shape[2], ch), rr.pairs,
+                                    want_hist=True, mapped=True)
+        assert np.array_equal(got2[1], ref2[1]) and np.array_equal(got2[2], ref2[2]), ch
 
 
 def test_pin_host_makes_numpy_tiles_readable_in_place(eng):
