@@ -371,16 +371,21 @@ int rs_zonal_stats_mapped_host(rs_ctx *ctx, const rs_roads *roads, const rs_tile
     rs_roads dr;
     rs_tiles dt;
     rs_pairs dp;
+    if (!roads || !tiles || !pairs) return RS_ERR_INVALID_ARG;
+    // the tiles must be page-locked (cudaHostAlloc / cudaHostRegister): the kernel reads them in place over PCIe / C2C
+    // (checked before anything is staged, so that a caller probing the transport pays nothing for a refusal)
+    cudaPointerAttributes attr;
+    attr.devicePointer = nullptr;
+    if (tiles->n_tiles > 0 && roads->n_roads > 0) {
+        if (!tiles->pixels) return RS_ERR_INVALID_ARG;
+        if (cudaPointerGetAttributes(&attr, tiles->pixels) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+            cudaGetLastError();
+            return RS_ERR_NOT_PINNED;
+        }
+    }
     if ((rc = stage_inputs(ctx, roads, tiles, pairs, false, dr, dt, dp))) return rc;     // geometry + pairs + transforms, no pixels
-    if (tiles->n_tiles > 0 && !tiles->pixels) return RS_ERR_INVALID_ARG;
     const int R = roads->n_roads, C = tiles->channels;
     if (R == 0) return RS_OK;
-    // the tiles must be page-locked (cudaHostAlloc / cudaHostRegister): the kernel reads them in place over PCIe / C2C
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, tiles->pixels) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
-        cudaGetLastError();
-        return RS_ERR_NOT_PINNED;
-    }
     dt.pixels = attr.devicePointer;
     const size_t hb = sizeof(uint32_t) * 256 * (size_t)C * R, zb = sizeof(uint32_t) * (size_t)R;
     const size_t sb = sizeof(double) * (size_t)(RS_NSTAT + n_pct) * C * R;
