@@ -109,7 +109,8 @@ struct ZonalArgs {
     const int *pair_tile;
     const int4 *items;        // (road, first pair, pairs | ITEM_SPLIT, first row or -1)
     const PairGeom *pgeom;    // per pair
-    const int *n_items;       // device-resident item count
+    const int *n_items;       // device-resident item counts: [0] big items (front of the list), [1] small items (back)
+    int items_cap;            // capacity of the item list: small item k sits at items[items_cap - 1 - k]
     const void *pixels;
     const double *gt;
     int H, W;
@@ -947,13 +948,16 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const Zo
     for (int i = lane; i < RCMAX / 4; i += 32) reinterpret_cast<uint4 *>(s.rowmap)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     uint32_t mbar_phase = 0;
-    const int n_items = *a.n_items;
+    // longest items first: the tail of the dynamic queue (teams finishing their last item while the others idle) is then made
+    // of the short items
+    const int n_big = a.n_items[0], n_items = n_big + a.n_items[1];
     for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(a.work_counter, 1);
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= n_items) break;
-        process_item<PX, FAST, SPARSE>(a, s, __ldg(a.items + idx), lane, mbar_phase);
+        const int at = idx < n_big ? idx : a.items_cap - 1 - (idx - n_big);
+        process_item<PX, FAST, SPARSE>(a, s, __ldg(a.items + at), lane, mbar_phase);
     }
 }
 
@@ -962,32 +966,38 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const Zo
 // pixels; a window taller than ROWS_ITEM rows becomes ceil(h / ROWS_ITEM) single-pair items.  Rows of roads with no item
 // or several items are zeroed here (their teams accumulate with atomics).
 // ---------------------------------------------------------------------------------------------
+constexpr int BIG_PAIRS = 4;    // an item of at least this many pairs (or a row slice of a tall window) is queued in the first wave
+
+// Items of one road.  COUNT pass (WRITE = false): returns the number of items, n_big = how many of them are big.
+// WRITE pass: big items go to items[big_base++], small ones to items[cap - 1 - small_base++].
 template <bool WRITE>
-__device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, int road, int p0, int p1, int4 *items, int base, int flag,
-                                          bool tall)
+__device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, int road, int p0, int p1, int4 *items, int big_base,
+                                          int small_base, int cap, int flag, bool tall, int &n_big)
 {
+    int ni = 0;
+    n_big = 0;
+    auto emit = [&](int first, int count, int row, bool big) {
+        if (WRITE) items[big ? big_base + n_big : cap - 1 - (small_base + (ni - n_big))] = make_int4(road, first, count | flag, row);
+        ni++;
+        n_big += big ? 1 : 0;
+    };
     if (!tall) {            // no window can exceed ROWS_ITEM rows (tile height <= ROWS_ITEM): groups of PPI pairs, no geometry reads
-        const int ni = (p1 - p0 + PPI - 1) / PPI;
-        if (WRITE)
-            for (int k = 0; k < ni; k++) items[base + k] = make_int4(road, p0 + k * PPI, min(PPI, p1 - p0 - k * PPI) | flag, -1);
+        for (int p = p0; p < p1; p += PPI) {
+            const int cnt = min(PPI, p1 - p);
+            emit(p, cnt, -1, cnt >= BIG_PAIRS);
+        }
         return ni;
     }
-    int ni = 0, gp = p0, gn = 0, garea = 0;
+    int gp = p0, gn = 0, garea = 0;
     auto close = [&]() {
-        if (gn > 0) {
-            if (WRITE) items[base + ni] = make_int4(road, gp, gn | flag, -1);
-            ni++;
-        }
+        if (gn > 0) emit(gp, gn, -1, gn >= BIG_PAIRS || garea >= AREA_MAX / 2);
         gn = 0; garea = 0;
     };
     for (int p = p0; p < p1; p++) {
         const int st = pgeom[p].status, h = st > 0 ? pgeom[p].h : 0, area = st > 0 ? pgeom[p].w * h : 0;
         if (h > ROWS_ITEM) {
             close();
-            for (int r = 0; r < h; r += ROWS_ITEM) {
-                if (WRITE) items[base + ni] = make_int4(road, p, 1 | flag, r);
-                ni++;
-            }
+            for (int r = 0; r < h; r += ROWS_ITEM) emit(p, 1, r, true);
             gp = p + 1;
             continue;
         }
@@ -1001,25 +1011,31 @@ __device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, in
 
 __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__ road_pair_off, const PairGeom *__restrict__ pgeom,
                                                          int n_roads, const int *__restrict__ road_slot, uint32_t *hist, uint32_t *nzero,
-                                                         int hc, int4 *items, int *n_items, int tall, int accumulate)
+                                                         int hc, int4 *items, int *n_items, int items_cap, int tall, int accumulate)
 {
     const int road = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    int p0 = 0, p1 = 0, ni = 0;
+    int p0 = 0, p1 = 0, ni = 0, nb = 0;
     if (road < n_roads) {
         p0 = road_pair_off[road]; p1 = road_pair_off[road + 1];
-        ni = road_items<false>(pgeom, road, p0, p1, nullptr, 0, 0, tall != 0);
+        ni = road_items<false>(pgeom, road, p0, p1, nullptr, 0, 0, items_cap, 0, tall != 0, nb);
     }
-    int incl = ni;
+    // two warp scans (big, small), one atomicAdd per warp and list
+    int ib = nb, is = ni - nb;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
+        const int vb = __shfl_up_sync(FULL, ib, o), vs = __shfl_up_sync(FULL, is, o);
+        if (lane >= o) { ib += vb; is += vs; }
     }
-    const int total = __shfl_sync(FULL, incl, 31);
-    int base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(n_items, total);
-    base = __shfl_sync(FULL, base, 31) + incl - ni;
-    if (ni > 0) road_items<true>(pgeom, road, p0, p1, items, base, (ni > 1 || accumulate) ? ITEM_SPLIT : 0, tall != 0);
+    const int tb = __shfl_sync(FULL, ib, 31), ts = __shfl_sync(FULL, is, 31);
+    int bb = 0, bs = 0;
+    if (lane == 31 && tb > 0) bb = atomicAdd(n_items, tb);
+    if (lane == 31 && ts > 0) bs = atomicAdd(n_items + 1, ts);
+    bb = __shfl_sync(FULL, bb, 31) + ib - nb;
+    bs = __shfl_sync(FULL, bs, 31) + is - (ni - nb);
+    if (ni > 0) {
+        int dummy;
+        road_items<true>(pgeom, road, p0, p1, items, bb, bs, items_cap, (ni > 1 || accumulate) ? ITEM_SPLIT : 0, tall != 0, dummy);
+    }
     if (hist && !accumulate) {
         unsigned m = __ballot_sync(FULL, road < n_roads && ni != 1);
         for (; m; m &= m - 1) {
@@ -1130,6 +1146,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
 
     // item list scratch: every pair can close one group and a tall window adds ceil(H / ROWS_ITEM) row items
     const size_t cap = (size_t)pairs->n_pairs * (1 + (size_t)(tiles->height + ROWS_ITEM - 1) / ROWS_ITEM) + (size_t)roads->n_roads + 1;
+    if (cap > 0x7fffffffu) return RS_ERR_UNSUPPORTED;
     int rc = ensure(ctx, ctx->items, cap * sizeof(int4));
     if (rc) return rc;
     if ((rc = ensure(ctx, ctx->pgeom, (size_t)pairs->n_pairs * sizeof(PairGeom)))) return rc;
@@ -1145,6 +1162,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     a.pgeom = (const PairGeom *)ctx->pgeom.p;
     a.work_counter = ctx->d_counters;
     a.n_items = ctx->d_counters + 1;
+    a.items_cap = (int)cap;
     a.pixels = tiles->pixels;
     a.gt = tiles->gt;
     a.H = tiles->height;
@@ -1186,7 +1204,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
             return RS_ERR_INVALID_ARG;
     }
 
-    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(int), st));
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(int), st));      // work counter, big items, small items
     if (pairs->n_pairs > 0) {
         pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
                                                                        roads->n_roads, pairs->n_pairs, tiles->width, tiles->height,
@@ -1197,7 +1215,8 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     }
     prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
                                                                     a.road_slot, masks ? nullptr : hist, n_allzero, HC,
-                                                                    (int4 *)ctx->items.p, ctx->d_counters + 1, tiles->height > ROWS_ITEM, accumulate);
+                                                                    (int4 *)ctx->items.p, ctx->d_counters + 1, (int)cap, tiles->height > ROWS_ITEM,
+                                                                    accumulate);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
 
