@@ -93,3 +93,17 @@ def test_geotiff_tiles_open_without_rasterio(tmp_path):
     Image.fromarray(a[..., 0]).save(plain)
     t2 = fct_misc.open_tile(plain)
     assert t2["data"].shape == (16, 24, 1) and t2["nodata"] is None and t2["transform"][0] == 1.0
+
+
+def test_bbox_pairs_matches_brute_force():
+    from proj_roadsurf_b200.geometry import bbox_pairs
+    rng = np.random.default_rng(9)
+    a = rng.uniform(0, 100, (700, 2)); a = np.concatenate([a, a + rng.uniform(0, 8, (700, 2))], 1)
+    b = rng.uniform(0, 100, (300, 2)); b = np.concatenate([b, b + rng.uniform(0, 12, (300, 2))], 1)
+    b[0] = [a[5, 2], a[5, 1], a[5, 2] + 1, a[5, 3]]                 # touching boxes overlap (closed comparison)
+    ia, ib = bbox_pairs(a, b, chunk=128)
+    exp = [(i, j) for i in range(len(a)) for j in range(len(b))
+           if a[i, 0] <= b[j, 2] and a[i, 2] >= b[j, 0] and a[i, 1] <= b[j, 3] and a[i, 3] >= b[j, 1]]
+    assert list(zip(ia.tolist(), ib.tolist())) == exp and (5, 0) in exp
+    ia, ib = bbox_pairs(np.zeros((0, 4)), b)
+    assert len(ia) == 0 and len(ib) == 0
