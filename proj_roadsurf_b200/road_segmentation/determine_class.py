@@ -155,6 +155,77 @@ def accumulate_class_planes(roads: RoadSet, tiles: TileBatch, pairs: PairList, e
     return hist
 
 
+def _clip_ring_to_rect(ring: np.ndarray, x0: float, y0: float, x1: float, y1: float) -> np.ndarray:
+    """Sutherland-Hodgman: a ring clipped to the closed axis-aligned rectangle, one half-plane at a time.  Pieces of a
+    concave ring that leave and re-enter the rectangle stay connected by zero-width runs along the rectangle's edge, which
+    carry no area (even-odd fill and the shoelace sum ignore them)."""
+    pts = np.asarray(ring, np.float64)[:, :2]
+    if len(pts) > 1 and pts[0, 0] == pts[-1, 0] and pts[0, 1] == pts[-1, 1]:
+        pts = pts[:-1]
+    for axis, bound, keep_ge in ((0, x0, True), (0, x1, False), (1, y0, True), (1, y1, False)):
+        if len(pts) == 0:
+            break
+        v = pts[:, axis]
+        inside = v >= bound if keep_ge else v <= bound
+        nxt = np.roll(pts, -1, axis=0)
+        nin = np.roll(inside, -1)
+        out = []
+        for k in range(len(pts)):
+            p, q = pts[k], nxt[k]
+            if inside[k]:
+                out.append(p)
+            if inside[k] != nin[k]:                              # the edge crosses the boundary line
+                t = (bound - p[axis]) / (q[axis] - p[axis])
+                c = p + t * (q - p)
+                c[axis] = bound
+                out.append(c)
+        pts = np.array(out, np.float64).reshape(-1, 2)
+    if len(pts) >= 3:
+        pts = np.concatenate([pts, pts[:1]])                      # closed, like shapely's rings
+    return pts
+
+
+def clip_labels(labels_gdf, tiles_gdf, fact=0.99):
+    """determine_class.py:62-95 (copied there from the object detector's helpers): every label joined to every tile it
+    intersects and cut to that tile scaled by ``fact`` about its centre (shapely.affinity.scale's default origin).
+    ``labels_gdf`` / ``tiles_gdf``: tables with a 'geometry' column; tile geometries are axis-aligned rectangles (XYZ tiles).
+    Vector preprocessing on the host, like the reference (GEOS there; a rectangle clip of every ring here, which gives the
+    same areas -- the geometry comes back as a GeoJSON-like dict whose rings follow the even-odd rule, see
+    ``_clip_ring_to_rect``).  Returns the joined table: label columns + tile columns ('id' renamed 'tile_id'), geometry =
+    the clipped label; labels that only reach the outer 1 % frame of a tile keep an empty geometry, as in the reference."""
+    from ..geometry import bbox_pairs, rings_of
+    if hasattr(labels_gdf, 'crs') and hasattr(tiles_gdf, 'crs'):
+        assert (labels_gdf.crs == tiles_gdf.crs)
+    lab_rings = [rings_of(g) for g in labels_gdf['geometry']]
+    tile_rings = [rings_of(g) for g in tiles_gdf['geometry']]
+
+    def box(rings):
+        v = np.concatenate(rings) if rings else np.zeros((0, 2))
+        return [v[:, 0].min(), v[:, 1].min(), v[:, 0].max(), v[:, 1].max()] if len(v) else [np.inf, np.inf, -np.inf, -np.inf]
+    lb = np.array([box(r) for r in lab_rings], np.float64).reshape(-1, 4)
+    tb = np.array([box(r) for r in tile_rings], np.float64).reshape(-1, 4)
+    ia, ib = bbox_pairs(lb, tb)
+    keep, geoms = [], []
+    for k, (i, j) in enumerate(zip(ia.tolist(), ib.tolist())):
+        x0, y0, x1, y1 = tb[j]
+        # 'intersects' of the spatial join: some part of the label lies in the closed tile
+        if not any(len(_clip_ring_to_rect(r, x0, y0, x1, y1)) for r in lab_rings[i]):
+            continue
+        cx, cy, hw, hh = (x0 + x1) / 2, (y0 + y1) / 2, (x1 - x0) / 2 * fact, (y1 - y0) / 2 * fact
+        rings = [c for c in (_clip_ring_to_rect(r, cx - hw, cy - hh, cx + hw, cy + hh) for r in lab_rings[i]) if len(c) >= 4]
+        keep.append(k)
+        geoms.append({"type": "Polygon", "coordinates": [c.tolist() for c in rings]})
+    ia, ib = ia[keep], ib[keep]
+    left = labels_gdf.drop(columns=['geometry']).iloc[ia].reset_index(drop=True)
+    right = tiles_gdf.drop(columns=['geometry']).iloc[ib].reset_index(drop=True).rename(columns={'id': 'tile_id'})
+    dup = set(left.columns) & set(right.columns)
+    left = left.rename(columns={c: f'{c}_left' for c in dup})
+    right = right.rename(columns={c: f'{c}_right' for c in dup})
+    out = pd.concat([left, right], axis=1)
+    out['geometry'] = geoms
+    return out
+
+
 def get_weighted_scores(ground_truth, predictions, engine=None):
     """determine_class.py:97-120 in its vector form: the overlay of the labels with the predictions, the share of every label
     covered by every prediction (rounded to 2 decimals) and the confidence weighted by it; pairs covering 5 % of the label

@@ -107,3 +107,48 @@ def test_bbox_pairs_matches_brute_force():
     assert list(zip(ia.tolist(), ib.tolist())) == exp and (5, 0) in exp
     ia, ib = bbox_pairs(np.zeros((0, 4)), b)
     assert len(ia) == 0 and len(ib) == 0
+
+
+def test_clip_labels_areas_match_the_overlay_oracle():
+    """determine_class.clip_labels (determine_class.py:62-95, host preprocessing): the clipped label has the area of
+    label AND scaled tile (oracle/overlay.py), rows follow the (label, tile) join"""
+    import pandas as pd
+    from oracle import overlay as ov
+    from proj_roadsurf_b200.road_segmentation import determine_class as dc
+    rng = np.random.default_rng(13)
+
+    def star(c, rmin, rmax, n):
+        ang = (np.arange(n) + rng.uniform(0.0, 0.8, n)) * (2 * np.pi / n)
+        rad = rng.uniform(rmin, rmax, n)
+        pts = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        return np.concatenate([pts, pts[:1]])
+    labels = []
+    for i in range(12):
+        c = rng.uniform(5, 35, 2)
+        rings = [star(c, 4, 9, int(rng.integers(8, 20)))]
+        if i % 2 == 0:
+            rings.append(star(c, 0.5, 2, 6))
+        labels.append({"type": "Polygon", "coordinates": [r.tolist() for r in rings]})
+    tiles, tid = [], []
+    for ty in range(4):
+        for tx in range(4):
+            x0, y0 = 10.0 * tx, 10.0 * ty
+            tiles.append({"type": "Polygon", "coordinates": [[[x0, y0], [x0 + 10, y0], [x0 + 10, y0 + 10], [x0, y0 + 10], [x0, y0]]]})
+            tid.append(f"({tx}, {ty}, 18)")
+    lab_df = pd.DataFrame({"OBJECTID": np.arange(12) + 1, "BELAGSART": 100, "geometry": labels})
+    til_df = pd.DataFrame({"id": tid, "title": "t", "geometry": tiles})
+    out = dc.clip_labels(lab_df, til_df, fact=0.99)
+    assert list(out.columns) == ["OBJECTID", "BELAGSART", "tile_id", "title", "geometry"] and len(out) > 20
+    n_checked = 0
+    for row in out.itertuples():
+        lab = [np.array(r) for r in labels[row.OBJECTID - 1]["coordinates"]]
+        tx, ty = [int(v) for v in row.tile_id.strip("()").split(",")[:2]]
+        cx, cy, h = 10.0 * tx + 5, 10.0 * ty + 5, 5 * 0.99
+        rect = [np.array([[cx - h, cy - h], [cx + h, cy - h], [cx + h, cy + h], [cx - h, cy + h]])]
+        exp = ov.intersection_area(lab, rect)
+        got = ov.polygon_area([np.array(r) for r in row.geometry["coordinates"]]) if row.geometry["coordinates"] else 0.0
+        assert abs(got - exp) <= 1e-9 * max(1.0, exp), (row.OBJECTID, row.tile_id, got, exp)
+        n_checked += exp > 0
+    assert n_checked > 15
+    # every (label, tile) pair whose closed shapes intersect is a row, in label-major order
+    assert out["OBJECTID"].tolist() == sorted(out["OBJECTID"].tolist())
