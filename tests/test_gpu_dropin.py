@@ -677,3 +677,48 @@ def test_overlay_areas_and_vector_get_weighted_scores(mods):
     assert out["area_pred_in_label"].tolist() == [r[3] for r in rows]
     assert np.allclose(out["weighted_score"].to_numpy(), [r[4] for r in rows], rtol=1e-12)
     assert "area_label" in gt_df.columns
+
+
+def test_vector_flow_clip_overlay_vote_metrics(mods):
+    """The vector chain of final_metrics.py:254-316 on synthetic polygons: clip_labels -> get_weighted_scores (overlay areas on
+    the GPU) -> determine_detected_class -> tags -> metrics, against the same chain through the oracles"""
+    from oracle import overlay as ov
+    dc, fm = mods[3], mods[4]
+    rng = np.random.default_rng(41)
+
+    def star(c, rmin, rmax, n):
+        ang = (np.arange(n) + rng.uniform(0.0, 0.8, n)) * (2 * np.pi / n)
+        rad = rng.uniform(rmin, rmax, n)
+        pts = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        return np.concatenate([pts, pts[:1]])
+    labels = [{"type": "Polygon", "coordinates": [star(rng.uniform(3, 37, 2), 2, 5, int(rng.integers(8, 16))).tolist()]} for _ in range(30)]
+    cat = rng.choice([100, 200], 30, p=[0.7, 0.3])
+    tiles = [{"type": "Polygon", "coordinates": [[[10.0 * tx, 10.0 * ty], [10.0 * tx + 10, 10.0 * ty], [10.0 * tx + 10, 10.0 * ty + 10],
+                                                   [10.0 * tx, 10.0 * ty + 10], [10.0 * tx, 10.0 * ty]]]} for ty in range(4) for tx in range(4)]
+    preds = [{"type": "Polygon", "coordinates": [star(rng.uniform(3, 37, 2), 1.5, 5, int(rng.integers(6, 14))).tolist()]} for _ in range(80)]
+    lab_df = pd.DataFrame({"OBJECTID": np.arange(30) + 1, "BELAGSART": cat, "geometry": labels})
+    lab_df["CATEGORY"] = lab_df.apply(dc.determine_category, axis=1)
+    lab_df["gt_type"] = "val"
+    til_df = pd.DataFrame({"id": [f"({i % 4}, {i // 4}, 18)" for i in range(16)], "geometry": tiles})
+    pr_df = pd.DataFrame({"score": np.round(rng.uniform(0.05, 1.0, 80), 3), "det_class_name": rng.choice(["artificial", "natural"], 80),
+                          "dataset": "val", "geometry": preds})
+    visible = dc.clip_labels(lab_df, til_df)
+    visible = visible[[len(g["coordinates"]) > 0 for g in visible["geometry"]]].reset_index(drop=True)
+    got = dc.get_weighted_scores(visible, pr_df)
+    lab_rings = [[np.array(r) for r in g["coordinates"]] for g in visible["geometry"]]
+    pr_rings = [[np.array(r) for r in g["coordinates"]] for g in preds]
+    rows = ov.get_weighted_scores(lab_rings, pr_rings, pr_df["score"].to_numpy())
+    assert len(rows) > 30 and len(got) == len(rows)
+    assert got["OBJECTID"].tolist() == [int(visible["OBJECTID"][r[0]]) for r in rows]
+    assert got["area_pred_in_label"].tolist() == [r[3] for r in rows]
+    assert np.allclose(got["weighted_score"].to_numpy(), [r[4] for r in rows], rtol=1e-12)
+    roads = lab_df[["OBJECTID", "CATEGORY", "gt_type", "geometry"]]
+    got = got.drop(columns=["BELAGSART", "CATEGORY", "gt_type", "tile_id", "area_label", "joined_area"], errors="ignore")   # :263-265
+    for thr in (0.0, 0.3, 0.6):
+        comp, bc, gl = fm.from_preds_to_metrics(got, roads, pd.DataFrame(), pd.DataFrame(), "val", thr)
+        exp = ovote.determine_detected_class(got, roads, thr)
+        assert comp["road_id"].tolist() == exp["road_id"].tolist() and comp["cover_type"].tolist() == exp["cover_type"].tolist()
+        exp["tag"] = [ovote.get_tag(c, k) for c, k in zip(exp["cover_type"], exp["CATEGORY"])]
+        assert comp["tag"].tolist() == exp["tag"].tolist()
+        obc, ogl = ovote.get_metrics(exp)
+        assert np.allclose(gl[["Pb", "Rb", "f1b"]].to_numpy(float), ogl[["Pb", "Rb", "f1b"]].to_numpy(float), rtol=1e-9, atol=1e-12)
