@@ -70,7 +70,8 @@ enum rs_window_mode {
 enum rs_nodata_mode {
     RS_NODATA_RAW = 0,         /* statistics over every in-mask pixel                              */
     RS_NODATA_NONE = 1,        /* tile nodata is None: pixels with all bands 0 dropped (fct_misc.py:117-119) */
-    RS_NODATA_ZERO = 2,        /* tile nodata == 0: per band zeros dropped, short bands zero-padded (fct_misc.py:95-111) */
+    RS_NODATA_ZERO = 2,        /* tile nodata == 0: per band zeros dropped, short bands zero-padded per (road, tile) call
+                                  (fct_misc.py:95-111); rs_finalize_stats_* then takes rs_zonal_params::min_zero as `n_allzero` */
     RS_NODATA_ZERO_MASKED = 3  /* rasterstats nodata=0: per band zeros masked (statistical_analysis.py:221) */
 };
 
@@ -106,6 +107,10 @@ typedef struct rs_zonal_params {
     double  scale_k[4];         /* dst = clamp(src*k + off, 0, 255) + 0.5 truncated -- gdal.Translate    */
     double  scale_off[4];       /* scaleParams (scripts/preprocessing/tif2cog.py:260-270)                */
     const int32_t *road_slot;   /* optional int32[n_roads]: output row of each road (NULL = identity)    */
+    uint32_t *min_zero;         /* optional output uint32[n_slots] (RS_HIST_BANDS only; device pointer for _dev, host pointer for
+                                   rs_zonal_hist_host): sum over the road's (road, tile) pairs of min over bands of the pair's
+                                   zero-valued in-mask pixels -- the per-call zero padding of get_pixel_values when the tile's
+                                   nodata is 0 (fct_misc.py:95-111); rs_finalize_stats_* takes it in RS_NODATA_ZERO mode */
 } rs_zonal_params;
 
 /* statistics row produced by rs_finalize_stats_*: doubles, RS_NSTAT fixed columns then the
@@ -123,8 +128,11 @@ enum rs_cover { RS_COVER_ARTIFICIAL = 0, RS_COVER_NATURAL = 1, RS_COVER_UNDETERM
 int         rs_version(void);
 const char *rs_status_string(int status);
 
-/* one context per device: owns the work counters, the status word and the staging buffers
- * of the _host entry points */
+/* one context per device: owns the work counters, the status word, the work-item scratch of the zonal kernel and the
+ * staging buffers of the _host entry points.  A context is used by ONE host thread at a time.  _dev calls on different
+ * streams through one context are ordered by the library (each waits for the previous user of the scratch), so they do
+ * not overlap; use one context per stream for concurrency.  A _dev call may synchronise the device once when its scratch
+ * has to grow (first call, or a larger pair list than any before). */
 int rs_ctx_create(int device, rs_ctx **out);
 int rs_ctx_destroy(rs_ctx *ctx);
 /* synchronise `stream`, return and clear the latched kernel-side status */

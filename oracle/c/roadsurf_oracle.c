@@ -229,7 +229,7 @@ int orc_zonal_accumulate(const double *xy, const int *ring_off, const int *road_
                          const int *road_pair_off, const int *pair_tile,
                          const void *tiles, const double *tile_gt, int H, int W, int C, int elem_bytes,
                          const double *scale_k, const double *scale_off, int rescale_f32, int joint,
-                         int road_begin, int road_end, uint64_t *hist, uint64_t *n_allzero)
+                         int road_begin, int road_end, uint64_t *hist, uint64_t *n_allzero, uint64_t *min_zero)
 {
     uint8_t *scratch = (uint8_t *)malloc((size_t)W * H + 1);
     int maxrings = 0;
@@ -251,6 +251,8 @@ int orc_zonal_accumulate(const double *xy, const int *ring_off, const int *road_
             int k = pair_mask(tile_gt + 6 * (size_t)t, g1 - g0, psize, xy + 2 * (size_t)v0, v1 - v0, W, H, scratch, win);
             if (k < 0) { rc = -1; break; }
             if (k == 0) continue;
+            /* zero-valued in-mask pixels of THIS (road, tile) call per band: fct_misc.py:95-111 pads per call */
+            uint64_t zcall[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             for (int y = 0; y < win[3]; y++)
                 for (int x = 0; x < win[2]; x++) {
                     if (!scratch[(size_t)y * win[2] + x]) continue;
@@ -281,10 +283,19 @@ int orc_zonal_accumulate(const double *xy, const int *ring_off, const int *road_
                         int cls = v[0] > 2 ? 0 : v[0];       /* unknown class codes count as "none" */
                         hr[cls * 256 + v[1]]++;
                     } else {
-                        for (int c = 0; c < C; c++) hr[c * 256 + v[c]]++;
+                        for (int c = 0; c < C; c++) {
+                            hr[c * 256 + v[c]]++;
+                            if (v[c] == 0) zcall[c]++;
+                        }
                     }
                     if (allzero) n_allzero[r]++;
                 }
+            if (min_zero && !joint) {
+                uint64_t m = zcall[0];
+                for (int c = 1; c < C; c++)
+                    if (zcall[c] < m) m = zcall[c];
+                min_zero[r] += m;
+            }
         }
     }
     free(psize);

@@ -76,8 +76,10 @@ def geometry_window(transform, rings, W, H):
 
 
 def zonal_accumulate(xy, ring_off, road_ring_off, road_pair_off, pair_tile, tiles, tile_gt,
-                     scale_k=None, scale_off=None, rescale_f32=False, joint=False, threads: int = 1):
+                     scale_k=None, scale_off=None, rescale_f32=False, joint=False, threads: int = 1, want_min_zero: bool = False):
     """Per-road histograms over a road-major pair list.  tiles (T,H,W,C) uint8|uint16.
+    want_min_zero: also return, per road, the sum over its (road, tile) calls of min over bands of the call's
+    zero-valued in-mask pixels (what the per-call zero padding of fct_misc.py:95-111 leaves out).
     threads > 1 splits the road range over a thread pool (the C call releases the GIL);
     every road is owned by one thread, so results do not depend on the split."""
     xy = np.ascontiguousarray(xy, np.float64)
@@ -94,6 +96,7 @@ def zonal_accumulate(xy, ring_off, road_ring_off, road_pair_off, pair_tile, tile
     HC = 3 if joint else C
     hist = np.zeros((R, HC, 256), np.uint64)
     nzero = np.zeros(R, np.uint64)
+    minz = np.zeros(R, np.uint64) if want_min_zero else None
     k = None if scale_k is None else np.ascontiguousarray(scale_k, np.float64)
     o = None if scale_off is None else np.ascontiguousarray(scale_off, np.float64)
     if eb == 2:
@@ -104,7 +107,7 @@ def zonal_accumulate(xy, ring_off, road_ring_off, road_pair_off, pair_tile, tile
             _p(xy), _p(ring_off), _p(road_ring_off), _p(road_pair_off), _p(pair_tile), _p(tiles), _p(tile_gt),
             ctypes.c_int(H), ctypes.c_int(W), ctypes.c_int(C), ctypes.c_int(eb), _p(k), _p(o),
             ctypes.c_int(int(rescale_f32)), ctypes.c_int(int(joint)), ctypes.c_int(lo), ctypes.c_int(hi),
-            _p(hist), _p(nzero))
+            _p(hist), _p(nzero), _p(minz))
 
     if threads <= 1 or R < 2 * threads:
         rcs = [run(0, R)]
@@ -116,4 +119,4 @@ def zonal_accumulate(xy, ring_off, road_ring_off, road_pair_off, pair_tile, tile
             rcs = list(ex.map(lambda ab: run(*ab), zip(bounds[:-1], bounds[1:])))
     if any(rc != 0 for rc in rcs):
         raise ValueError("rotated/degenerate transform")
-    return hist, nzero
+    return (hist, nzero, minz) if want_min_zero else (hist, nzero)

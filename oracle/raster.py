@@ -95,19 +95,23 @@ def pair_inside_mask(tile_transform, rings, W: int, H: int):
 
 
 def zonal_accumulate(tiles: np.ndarray, transforms: np.ndarray, roads: Sequence[Sequence[np.ndarray]],
-                     pairs: Iterable[Tuple[int, int]], rescale=None):
+                     pairs: Iterable[Tuple[int, int]], rescale=None, want_min_zero: bool = False):
     """Per-road histograms over the pair list.
 
     tiles (T, H, W, C) uint8 (or uint16 with ``rescale``); transforms (T, 6);
     roads[r] = list of rings; pairs = iterable of (tile_idx, road_idx).
     Returns hist uint64 (R, C, 256) and n_allzero uint64 (R,) = in-mask pixels
     whose bands are all 0 (fct_misc.py:117-119 drops exactly those rows when the
-    tile has no nodata value).
+    tile has no nodata value).  want_min_zero: third result min_zero uint64 (R,) = sum over the road's
+    (road, tile) calls of min over bands of the call's zero-valued in-mask pixels: with tile nodata 0 every
+    call drops the zeros per band and pads each band with zeros up to the call's longest band (fct_misc.py:95-111),
+    so over all calls band b keeps  zeros(b) - min_zero  zeros.
     """
     T, H, W, C = tiles.shape
     R = len(roads)
     hist = np.zeros((R, C, 256), np.uint64)
     nzero = np.zeros(R, np.uint64)
+    minz = np.zeros(R, np.uint64)
     for t, r in pairs:
         m = pair_inside_mask(transforms[t], roads[r], W, H).astype(bool)
         if not m.any():
@@ -118,7 +122,8 @@ def zonal_accumulate(tiles: np.ndarray, transforms: np.ndarray, roads: Sequence[
         for c in range(C):
             hist[r, c] += np.bincount(px[:, c], minlength=256).astype(np.uint64)
         nzero[r] += np.uint64(np.count_nonzero(px.max(axis=1) == 0))
-    return hist, nzero
+        minz[r] += np.uint64(min(int(np.count_nonzero(px[:, c] == 0)) for c in range(C)))
+    return (hist, nzero, minz) if want_min_zero else (hist, nzero)
 
 
 def rescale_u16_to_u8(px: np.ndarray, smin: Sequence[float], smax: Sequence[float], f32: bool = False) -> np.ndarray:

@@ -83,16 +83,22 @@ def stats_from_hist(h: np.ndarray, ddof: int = 1, percentiles: Sequence[float] =
     return out
 
 
-def apply_nodata_convention(hist: np.ndarray, n_allzero: np.ndarray, mode: str) -> np.ndarray:
+def apply_nodata_convention(hist: np.ndarray, n_allzero: np.ndarray, mode: str, min_zero=None) -> np.ndarray:
     """Turn raw in-mask histograms (R, C, 256) into the multiset get_pixel_values returns
     (SURVEY.md A.4).  mode 'N': tile nodata None -> rows with every band 0 dropped.
     mode 'Z': tile nodata 0 -> per band the zeros are dropped, then the band is padded with
-    zeros up to the longest band (fct_misc.py:95-111).  mode 'raw': unchanged."""
+    zeros up to the longest band OF THE SAME (road, tile) CALL (fct_misc.py:95-111); the calls of a road are
+    concatenated afterwards (statistical_analysis.py:187-193).  ``min_zero`` (R,) = sum over the road's calls of
+    min over bands of the call's zero count (oracle.raster.zonal_accumulate(want_min_zero=True)); without it the
+    road is taken as ONE call (exact for single-tile roads only).  mode 'raw': unchanged."""
     h = np.array(hist, dtype=np.int64, copy=True)
     if mode == "raw":
         return h
     if mode == "N":
         h[:, :, 0] -= np.asarray(n_allzero, np.int64)[:, None]
+        return h
+    if mode == "Z" and min_zero is not None:
+        h[:, :, 0] -= np.asarray(min_zero, np.int64)[:, None]
         return h
     if mode == "Z":
         nonzero = h[:, :, 1:].sum(axis=2)                 # (R, C) = L_b

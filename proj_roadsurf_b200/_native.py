@@ -53,7 +53,8 @@ class RsPairs(C.Structure):
 
 class RsZonalParams(C.Structure):
     _fields_ = [("hist_mode", C.c_int32), ("window_mode", C.c_int32), ("rescale", C.c_int32), ("border_px", C.c_int32),
-                ("scale_k", C.c_double * 4), ("scale_off", C.c_double * 4), ("road_slot", C.c_void_p)]
+                ("scale_k", C.c_double * 4), ("scale_off", C.c_double * 4), ("road_slot", C.c_void_p),
+                ("min_zero", C.c_void_p)]
 
 
 class RsLattice(C.Structure):

@@ -136,6 +136,7 @@ int rs_ctx_create(int device, rs_ctx **out)
     if (e == cudaSuccess) e = cudaMemset(ctx->d_counters, 0, sizeof(int) * RS_NCOUNTERS);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_status_pinned, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_scratch, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         rs_ctx_destroy(ctx);
         return RS_ERR_CUDA;
@@ -152,6 +153,8 @@ int rs_ctx_destroy(rs_ctx *ctx)
         if (b.p) cudaFree(b.p);
     if (ctx->items.p) cudaFree(ctx->items.p);
     if (ctx->pgeom.p) cudaFree(ctx->pgeom.p);
+    if (ctx->pair_zero.p) cudaFree(ctx->pair_zero.p);
+    if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->h_status_pinned) cudaFreeHost(ctx->h_status_pinned);
@@ -257,15 +260,21 @@ int rs_zonal_hist_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     const size_t hb = sizeof(uint32_t) * 256 * (size_t)HC * n_slots, zb = sizeof(uint32_t) * (size_t)n_slots;
     if ((rc = ensure(ctx, ctx->stage[9], hb))) return rc;
     if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
+    if (prm->min_zero) {
+        if ((rc = ensure(ctx, ctx->stage[12], zb))) return rc;
+        p.min_zero = (uint32_t *)ctx->stage[12].p;
+    }
     if (prm->road_slot) {      // slots no road maps to stay zero
         RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[9].p, 0, hb, ctx->host_stream));
         RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[10].p, 0, zb, ctx->host_stream));
+        if (prm->min_zero) RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[12].p, 0, zb, ctx->host_stream));
     }
     rc = launch_zonal(ctx, &dr, &dt, &dp, &p, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
                       prm->window_mode, ctx->host_stream);
     if (rc) return rc;
     RS_CUDA_OK(ctx, cudaMemcpyAsync(hist, ctx->stage[9].p, hb, cudaMemcpyDeviceToHost, ctx->host_stream));
     RS_CUDA_OK(ctx, cudaMemcpyAsync(n_allzero, ctx->stage[10].p, zb, cudaMemcpyDeviceToHost, ctx->host_stream));
+    if (prm->min_zero) RS_CUDA_OK(ctx, cudaMemcpyAsync(prm->min_zero, ctx->stage[12].p, zb, cudaMemcpyDeviceToHost, ctx->host_stream));
     return finish(ctx);
 }
 
@@ -289,10 +298,17 @@ int rs_zonal_stats_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tile
     if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
     if ((rc = ensure(ctx, ctx->stage[11], sb))) return rc;
     cudaStream_t st = ctx->host_stream;
-    rc = launch_zonal(ctx, &dr, &dt, &dp, prm, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
+    rs_zonal_params p = *prm;
+    const uint32_t *aux = (const uint32_t *)ctx->stage[10].p;
+    p.min_zero = nullptr;
+    if (nodata_mode == RS_NODATA_ZERO) {        // the per-call zero padding of get_pixel_values needs the per-pair minima
+        if ((rc = ensure(ctx, ctx->stage[12], zb))) return rc;
+        aux = p.min_zero = (uint32_t *)ctx->stage[12].p;
+    }
+    rc = launch_zonal(ctx, &dr, &dt, &dp, &p, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
                       prm->window_mode, st);
     if (rc) return rc;
-    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, (const uint32_t *)ctx->stage[10].p, R, C, nodata_mode, ddof,
+    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, aux, R, C, nodata_mode, ddof,
                          percentiles, n_pct, (double *)ctx->stage[11].p, st);
     if (rc) return rc;
     RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[11].p, sb, cudaMemcpyDeviceToHost, st));
@@ -335,6 +351,14 @@ int rs_zonal_stats_stream_host(rs_ctx *ctx, const rs_roads *roads, const rs_tile
     cudaStream_t st = ctx->host_stream, cs = ctx->copy_stream;
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[9].p, 0, hb, st));
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[10].p, 0, zb, st));
+    rs_zonal_params p = *prm;
+    const uint32_t *aux = (const uint32_t *)ctx->stage[10].p;
+    p.min_zero = nullptr;
+    if (nodata_mode == RS_NODATA_ZERO) {
+        if ((rc = ensure(ctx, ctx->stage[12], zb))) return rc;
+        aux = p.min_zero = (uint32_t *)ctx->stage[12].p;
+        RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[12].p, 0, zb, st));
+    }
     int k = 0;
     for (int lo = 0; lo < tiles->n_tiles; lo += per, k++) {
         const int hi = lo + per < tiles->n_tiles ? lo + per : tiles->n_tiles, b = k & 1;
@@ -346,12 +370,12 @@ int rs_zonal_stats_stream_host(rs_ctx *ctx, const rs_roads *roads, const rs_tile
         RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[b], 0));
         rs_tiles chunk = dt;
         chunk.pixels = (const uint8_t *)buf - (size_t)lo * tile_bytes;                     // indexed with the global tile index
-        rc = launch_zonal_chunk(ctx, &dr, &chunk, &dp, prm, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
+        rc = launch_zonal_chunk(ctx, &dr, &chunk, &dp, &p, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
                                 prm->window_mode, lo, hi, 1, st);
         if (rc) return rc;
         RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_used[b], st));
     }
-    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, (const uint32_t *)ctx->stage[10].p, R, C, nodata_mode, ddof,
+    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, aux, R, C, nodata_mode, ddof,
                          percentiles, n_pct, (double *)ctx->stage[11].p, st);
     if (rc) return rc;
     RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[11].p, sb, cudaMemcpyDeviceToHost, st));
@@ -393,10 +417,17 @@ int rs_zonal_stats_mapped_host(rs_ctx *ctx, const rs_roads *roads, const rs_tile
     if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
     if ((rc = ensure(ctx, ctx->stage[11], sb))) return rc;
     cudaStream_t st = ctx->host_stream;
-    rc = launch_zonal(ctx, &dr, &dt, &dp, prm, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
+    rs_zonal_params p = *prm;
+    const uint32_t *aux = (const uint32_t *)ctx->stage[10].p;
+    p.min_zero = nullptr;
+    if (nodata_mode == RS_NODATA_ZERO) {        // the per-call zero padding of get_pixel_values needs the per-pair minima
+        if ((rc = ensure(ctx, ctx->stage[12], zb))) return rc;
+        aux = p.min_zero = (uint32_t *)ctx->stage[12].p;
+    }
+    rc = launch_zonal(ctx, &dr, &dt, &dp, &p, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr,
                       prm->window_mode, st);
     if (rc) return rc;
-    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, (const uint32_t *)ctx->stage[10].p, R, C, nodata_mode, ddof,
+    rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, aux, R, C, nodata_mode, ddof,
                          percentiles, n_pct, (double *)ctx->stage[11].p, st);
     if (rc) return rc;
     RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[11].p, sb, cudaMemcpyDeviceToHost, st));

@@ -133,15 +133,23 @@ __global__ void __launch_bounds__(128) vote_table_kernel(const int *__restrict__
     const int road = blockIdx.x * blockDim.x + threadIdx.x, ti = blockIdx.y;
     if (road >= n_roads || ti >= n_thr) return;
     const double th = thr[ti];
-    double sw[2] = {0.0, 0.0}, sa[2] = {0.0, 0.0};
+    // pandas' groupby(...).sum() (libgroupby.group_sum, pandas >= 1.2) is Kahan-compensated; same update order here, so the
+    // exact tie test below sees the sums the reference sees
+    double sw[2] = {0.0, 0.0}, sa[2] = {0.0, 0.0}, cw[2] = {0.0, 0.0}, ca[2] = {0.0, 0.0};
     int seen[2] = {0, 0}, any = 0;
     for (int i = row_off[road]; i < row_off[road + 1]; i++) {
         if (!(score[i] >= th)) continue;                       // valid_predictions: score >= threshold
         any = 1;
         const int k = cls[i];
         if (k == 0 || k == 1) {
-            sw[k] = __dadd_rn(sw[k], weighted[i]);
-            sa[k] = __dadd_rn(sa[k], area[i]);
+            const double yw = __dsub_rn(weighted[i], cw[k]), tw = __dadd_rn(sw[k], yw);
+            cw[k] = __dsub_rn(__dsub_rn(tw, sw[k]), yw);
+            if (cw[k] != cw[k]) cw[k] = 0.0;                   // pandas resets a NaN compensation (inf sums)
+            sw[k] = tw;
+            const double ya = __dsub_rn(area[i], ca[k]), ta = __dadd_rn(sa[k], ya);
+            ca[k] = __dsub_rn(__dsub_rn(ta, sa[k]), ya);
+            if (ca[k] != ca[k]) ca[k] = 0.0;
+            sa[k] = ta;
             seen[k] = 1;
         }
     }

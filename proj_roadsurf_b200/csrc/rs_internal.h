@@ -32,6 +32,10 @@ struct rs_ctx {
     rs::DevBuf stage[16];                 // grow-only device staging of the _host entry points
     rs::DevBuf items;                     // grow-only work-item list of the zonal kernel
     rs::DevBuf pgeom;                     // grow-only per-pair geometry records of the zonal kernel
+    rs::DevBuf pair_zero;                 // grow-only per-pair zero counts (min_zero of row-split pairs on tall tiles)
+    cudaEvent_t ev_scratch = nullptr;     // recorded after every launch that uses the scratch above
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_used = false;
 };
 
 namespace rs {

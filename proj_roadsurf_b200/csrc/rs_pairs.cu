@@ -247,12 +247,27 @@ __global__ void __launch_bounds__(128) ring_sign_kernel(const PolySet S, int n_r
         a2 = __dadd_rn(a2, __dsub_rn(__dmul_rn(p.x, q.y), __dmul_rn(q.x, p.y)));
     }
     const int poly = ring_poly[g];
+    // nesting depth of the ring inside its polygon, from a point of the ring that lies on no other ring: a valid hole may
+    // touch its shell (and parts may touch each other) at single vertices, where containment is undecided.  Candidates:
+    // the ring's vertices in order, then its edge midpoints; the first one off every other ring decides.
     int depth = 0;
-    const double2 rep = S.xy[v0];
-    for (int h = S.road_ring_off[poly]; h < S.road_ring_off[poly + 1]; h++) {
-        if (h == g) continue;
-        PolySet one = S;
-        if (point_in_rings(one, h, h + 1, rep) == 1) depth ^= 1;
+    const int nv = v1 - v0;
+    for (int c = 0; c < 2 * nv; c++) {
+        double2 rep = S.xy[v0 + (c < nv ? c : c - nv)];
+        if (c >= nv) {
+            const double2 q = S.xy[c - nv + 1 < nv ? v0 + c - nv + 1 : v0];
+            rep.x = __dmul_rn(__dadd_rn(rep.x, q.x), 0.5);
+            rep.y = __dmul_rn(__dadd_rn(rep.y, q.y), 0.5);
+        }
+        int d = 0;
+        bool undecided = false;
+        for (int h = S.road_ring_off[poly]; h < S.road_ring_off[poly + 1] && !undecided; h++) {
+            if (h == g) continue;
+            const int w = point_in_rings(S, h, h + 1, rep);
+            if (w == 2) undecided = true;
+            else if (w == 1) d ^= 1;
+        }
+        if (!undecided || c == 2 * nv - 1) { depth = d; break; }
     }
     const bool ccw = a2 > 0.0;
     sign[g] = a2 == 0.0 ? 0 : ((ccw != (depth != 0)) ? 1 : -1);

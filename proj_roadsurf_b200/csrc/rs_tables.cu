@@ -61,16 +61,6 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a)
     const int road = (int)(wid / C), b_only = (int)(wid - (long long)road * C);
     const uint32_t *hr = a.hist + (size_t)road * C * 256;
 
-    u64 longest = 0;
-    if (a.mode == RS_NODATA_ZERO) {
-        for (int b = 0; b < C; b++) {
-            const uint4 q0 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane);
-            const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane + 4);
-            u64 nzv = (u64)q0.y + q0.z + q0.w + q1.x + q1.y + q1.z + q1.w + (lane ? (u64)q0.x : 0ull);
-            nzv = warp_sum_u64(nzv);
-            longest = nzv > longest ? nzv : longest;
-        }
-    }
     const u64 allzero = a.nzero ? (u64)a.nzero[road] : 0ull;
 
     for (int b = b_only; b <= b_only; b++) {
@@ -78,11 +68,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a)
         const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane + 4);
         u64 c[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         if (a.mode != RS_NODATA_RAW) {
-            u64 nzv = c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7] + (lane ? c[0] : 0ull);
-            if (a.mode == RS_NODATA_ZERO) nzv = warp_sum_u64(nzv);
             if (lane == 0) {
-                if (a.mode == RS_NODATA_NONE) c[0] = c[0] >= allzero ? c[0] - allzero : 0ull;
-                else if (a.mode == RS_NODATA_ZERO) c[0] = longest - nzv;
+                // NONE: rows with every band 0 are dropped (allzero = their count).  ZERO: per (road, tile) call the zeros of a
+                // band are dropped and the band is padded with zeros up to the call's longest band; over the road's calls
+                // the band keeps zeros(band) - sum over calls of min over bands of zeros(call, band)  (allzero = that sum,
+                // rs_zonal_params::min_zero)
+                if (a.mode == RS_NODATA_NONE || a.mode == RS_NODATA_ZERO) c[0] = c[0] >= allzero ? c[0] - allzero : 0ull;
                 else c[0] = 0ull;                       // RS_NODATA_ZERO_MASKED
             }
         }
@@ -167,7 +158,7 @@ int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero
     if (nodata_mode < RS_NODATA_RAW || nodata_mode > RS_NODATA_ZERO_MASKED) return RS_ERR_INVALID_ARG;
     if (n_roads == 0) return RS_OK;
     if (!hist || !stats || (n_pct > 0 && !pct_host)) return RS_ERR_INVALID_ARG;
-    if (nodata_mode == RS_NODATA_NONE && !n_allzero) return RS_ERR_INVALID_ARG;
+    if ((nodata_mode == RS_NODATA_NONE || nodata_mode == RS_NODATA_ZERO) && !n_allzero) return RS_ERR_INVALID_ARG;
     FinalizeArgs a{};
     a.hist = hist; a.nzero = n_allzero; a.n_roads = n_roads; a.C = channels; a.mode = nodata_mode; a.ddof = ddof;
     a.n_pct = n_pct;

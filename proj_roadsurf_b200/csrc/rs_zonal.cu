@@ -120,6 +120,8 @@ struct ZonalArgs {
     const int *road_slot;
     uint32_t *hist;
     uint32_t *nzero;
+    uint32_t *minzero;        // optional, per slot: sum over the road's pairs of min over bands of the pair's zero-valued in-mask pixels
+    uint32_t *pair_zero;      // [n_pairs][4] scratch of the row-split pairs of tall tiles (their rows live in several items)
     uint8_t *masks;
     int window_mode;
     double sk[4], so[4];
@@ -495,7 +497,10 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
     }
     if (nrings > 1 && nrings <= RINGCAP)
         for (int k = lane; k <= nrings; k += 32) s.ring_start[k] = a.ring_off[g0 + k] - v0;
-    uint32_t nz = 0;
+    uint32_t nz = 0, mz = 0;
+    uint32_t zprev[PX::MASK ? 1 : PX::HC];          // hist[band][0] after the previous pair (a.minzero only)
+#pragma unroll
+    for (int c = 0; c < (PX::MASK ? 1 : PX::HC); c++) zprev[c] = 0;
     if (staged) {
         mbar_wait(&s.mbar, mbar_phase);
         mbar_phase ^= 1u;
@@ -905,6 +910,21 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             if (nq) consume(nq);
             __syncwarp();
         }
+        if constexpr (!PX::MASK) {
+            // get_pixel_values with tile nodata == 0 pads every band of ONE (road, tile) call up to that call's longest band
+            // (fct_misc.py:95-111): the per-road total of the padding needs min over bands of the pair's zero count
+            if (a.minzero) {
+                uint32_t m = 0xffffffffu;
+#pragma unroll
+                for (int c = 0; c < PX::HC; c++) {
+                    const uint32_t z = s.hist[c * 256], d = z - zprev[c];
+                    zprev[c] = z;
+                    m = min(m, d);
+                    if (row_first >= 0 && d && lane == 0) atomicAdd(&a.pair_zero[4 * (size_t)p + c], d);
+                }
+                if (row_first < 0) mz += m;
+            }
+        }
     }
 
     // ---------------- write the road's accumulators ----------------
@@ -918,12 +938,14 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             for (int i = lane; i < PX::HC * 64; i += 32)
                 reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(s.hist)[i];
             if (lane == 0) a.nzero[slot] = nz;
+            if (lane == 0 && a.minzero) a.minzero[slot] = mz;
         } else {
             for (int i = lane; i < PX::HC * 256; i += 32) {
                 const uint32_t v = s.hist[i];
                 if (v) atomicAdd(&dst[i], v);
             }
             if (lane == 0 && nz) atomicAdd(&a.nzero[slot], nz);
+            if (lane == 0 && mz) atomicAdd(&a.minzero[slot], mz);          // mz != 0 only when a.minzero is set
         }
     }
     __syncwarp();
@@ -1011,7 +1033,8 @@ __device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, in
 
 __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__ road_pair_off, const PairGeom *__restrict__ pgeom,
                                                          int n_roads, const int *__restrict__ road_slot, uint32_t *hist, uint32_t *nzero,
-                                                         int hc, int4 *items, int *n_items, int items_cap, int tall, int accumulate)
+                                                         uint32_t *minzero, int hc, int4 *items, int *n_items, int items_cap, int tall,
+                                                         int accumulate)
 {
     const int road = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     int p0 = 0, p1 = 0, ni = 0, nb = 0;
@@ -1045,8 +1068,29 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__
             uint4 *dst = reinterpret_cast<uint4 *>(hist + (size_t)slot * hc * 256);
             for (int i = lane; i < hc * 64; i += 32) dst[i] = make_uint4(0, 0, 0, 0);
             if (lane == 0) nzero[slot] = 0;
+            if (lane == 0 && minzero) minzero[slot] = 0;
         }
     }
+}
+
+// rows of a pair taller than ROWS_ITEM live in several items: their per-band zero counts met in pair_zero; thread per pair
+__global__ void __launch_bounds__(256) pair_minzero_kernel(const int *__restrict__ road_pair_off, const PairGeom *__restrict__ pgeom,
+                                                           const uint32_t *__restrict__ pair_zero, int n_roads, int n_pairs, int hc,
+                                                           const int *__restrict__ road_slot, uint32_t *minzero)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    if (pgeom[p].status <= 0 || pgeom[p].h <= ROWS_ITEM) return;
+    uint32_t m = 0xffffffffu;
+    for (int c = 0; c < hc; c++) m = min(m, pair_zero[4 * (size_t)p + c]);
+    if (m == 0) return;
+    int lo = 0, hi = n_roads;                    // largest road with road_pair_off[road] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(road_pair_off + mid) <= p) lo = mid;
+        else hi = mid;
+    }
+    atomicAdd(&minzero[road_slot ? road_slot[lo] : lo], m);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1170,6 +1214,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     a.road_slot = prm ? prm->road_slot : nullptr;
     a.hist = hist;
     a.nzero = n_allzero;
+    a.minzero = (prm && !masks) ? prm->min_zero : nullptr;
     a.masks = masks;
     a.window_mode = window_mode;
     a.status = ctx->d_status;
@@ -1204,6 +1249,14 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
             return RS_ERR_INVALID_ARG;
     }
 
+    if (a.minzero && prm->hist_mode != RS_HIST_BANDS) return RS_ERR_INVALID_ARG;
+    // one context = one set of scratch buffers: a launch on another stream than the previous one waits for it
+    if (ctx->scratch_used && ctx->scratch_stream != st) RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
+    if (a.minzero && tiles->height > ROWS_ITEM && pairs->n_pairs > 0) {
+        if ((rc = ensure(ctx, ctx->pair_zero, (size_t)pairs->n_pairs * 4 * sizeof(uint32_t)))) return rc;
+        RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->pair_zero.p, 0, (size_t)pairs->n_pairs * 4 * sizeof(uint32_t), st));
+        a.pair_zero = (uint32_t *)ctx->pair_zero.p;
+    }
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(int), st));      // work counter, big items, small items
     if (pairs->n_pairs > 0) {
         pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
@@ -1214,22 +1267,35 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
         RS_CUDA_OK(ctx, cudaGetLastError());
     }
     prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
-                                                                    a.road_slot, masks ? nullptr : hist, n_allzero, HC,
+                                                                    a.road_slot, masks ? nullptr : hist, n_allzero, a.minzero, HC,
                                                                     (int4 *)ctx->items.p, ctx->d_counters + 1, (int)cap, tiles->height > ROWS_ITEM,
                                                                     accumulate);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
 
-    if (masks) return launch_one<PxMask>(ctx, a, st);
-    if (prm->hist_mode == RS_HIST_CLASS_SCORE) return launch_one<PxClassScore>(ctx, a, st);
-    if (tiles->dtype == RS_U16)
-        return prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);
-    switch (tiles->channels) {
-        case 1: return launch_one<PxBandsU8<1>>(ctx, a, st);
-        case 2: return launch_one<PxBandsU8<2>>(ctx, a, st);
-        case 3: return launch_one<PxBandsU8<3>>(ctx, a, st);
-        default: return launch_one<PxBandsU8<4>>(ctx, a, st);
+    if (masks) rc = launch_one<PxMask>(ctx, a, st);
+    else if (prm->hist_mode == RS_HIST_CLASS_SCORE) rc = launch_one<PxClassScore>(ctx, a, st);
+    else if (tiles->dtype == RS_U16)
+        rc = prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);
+    else
+        switch (tiles->channels) {
+            case 1: rc = launch_one<PxBandsU8<1>>(ctx, a, st); break;
+            case 2: rc = launch_one<PxBandsU8<2>>(ctx, a, st); break;
+            case 3: rc = launch_one<PxBandsU8<3>>(ctx, a, st); break;
+            default: rc = launch_one<PxBandsU8<4>>(ctx, a, st); break;
+        }
+    if (rc) return rc;
+    if (a.pair_zero) {
+        pair_minzero_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, a.pair_zero,
+                                                                          roads->n_roads, pairs->n_pairs, HC, a.road_slot, a.minzero);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
     }
+    // the scratch (items, pair records, counters) is busy until this point of `st`: a call on another stream waits for it
+    RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_scratch, st));
+    ctx->scratch_stream = st;
+    ctx->scratch_used = true;
+    return RS_OK;
 }
 
 }  // namespace rs

@@ -100,7 +100,7 @@ class Engine:
         return N.RsRoads(xy, ring_off, road_ring_off, bbox, n_roads, n_rings, n_verts)
 
     @staticmethod
-    def _params(hist_mode, window, rescale, road_slot_ptr, border_px: int = 0) -> N.RsZonalParams:
+    def _params(hist_mode, window, rescale, road_slot_ptr, border_px: int = 0, min_zero_ptr=None) -> N.RsZonalParams:
         p = N.RsZonalParams()
         p.hist_mode = _HIST_MODES[hist_mode]
         p.window_mode = _WINDOW_MODES[window]
@@ -113,13 +113,15 @@ class Engine:
                 p.scale_k[i] = float(k[i]) if i < len(k) else 1.0
                 p.scale_off[i] = float(off[i]) if i < len(off) else 0.0
         p.road_slot = road_slot_ptr
+        p.min_zero = min_zero_ptr
         return p
 
     # ------------------------------------------------------------------ host family
     def zonal_hist_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, hist_mode: str = "bands",
                         window: str = "crop", rescale=None, road_slot: Optional[np.ndarray] = None,
-                        n_slots: Optional[int] = None, border_px: int = 0):
-        """Per-road histograms (n_slots, HC, 256) uint32 and all-zero-pixel counts (n_slots,) uint32."""
+                        n_slots: Optional[int] = None, border_px: int = 0, want_min_zero: bool = False):
+        """Per-road histograms (n_slots, HC, 256) uint32 and all-zero-pixel counts (n_slots,) uint32; with want_min_zero
+        also the (n_slots,) uint32 zero-padding term of the nodata == 0 convention (rs_zonal_params::min_zero)."""
         px = np.ascontiguousarray(tiles.pixels)
         dtype = N.RS_U16 if px.dtype == np.uint16 else N.RS_U8
         R = roads.n_roads
@@ -139,11 +141,12 @@ class Engine:
         rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), R, roads.n_rings, roads.n_verts)
         td = N.RsTiles(_np_ptr(px), _np_ptr(gt), tiles.n_tiles, tiles.height, tiles.width, tiles.channels, dtype)
         pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
-        prm = self._params(hist_mode, window, rescale, _np_ptr(slot), border_px)
+        minz = np.zeros(S_out, np.uint32) if want_min_zero else None
+        prm = self._params(hist_mode, window, rescale, _np_ptr(slot), border_px, _np_ptr(minz))
         st = self.lib.rs_zonal_hist_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
                                          _np_ptr(hist), _np_ptr(nzero))
         N.check(st, "rs_zonal_hist_host", self._ctx)
-        return hist, nzero
+        return (hist, nzero, minz) if want_min_zero else (hist, nzero)
 
     def zonal_stats_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList, window: str = "crop", rescale=None,
                          nodata_mode: str = "none", ddof: int = 1, percentiles: Sequence[float] = (),
@@ -514,14 +517,24 @@ class Engine:
         return DeviceTiles(px, g, T, height, width, channels, code)
 
     def zonal_hist_dev(self, roads: DeviceRoads, tiles: DeviceTiles, pairs: DevicePairs, hist_mode: str = "bands",
-                       window: str = "crop", rescale=None, road_slot=None, out=None, check: bool = True):
+                       window: str = "crop", rescale=None, road_slot=None, out=None, check: bool = True,
+                       n_slots: Optional[int] = None, min_zero=None):
         """Asynchronous on the current torch stream.  Returns (hist, n_allzero) CUDA tensors (int32 storage
-        of the uint32 counters).  ``check`` synchronises and raises on a kernel-side failure."""
+        of the uint32 counters).  ``check`` synchronises and raises on a kernel-side failure.  With road_slot,
+        n_slots is the number of output rows (rows no local road maps to stay zero; the rows of a shard's boundary
+        table must exist on every rank); min_zero: optional (n_slots,) int32 CUDA tensor, filled with the zero-padding
+        term of the nodata == 0 convention (rs_zonal_params::min_zero)."""
         torch = self._torch()
         dev = torch.device("cuda", self.device)
         HC = 3 if hist_mode == "class_score" else tiles.channels
         if out is None:
-            S = roads.n_roads if road_slot is None else int(road_slot.max().item()) + 1
+            if road_slot is None:
+                S = roads.n_roads
+            else:
+                S = int(road_slot.max().item()) + 1 if roads.n_roads else 0
+                if n_slots is not None:
+                    assert n_slots >= S, "n_slots smaller than the largest slot"
+                    S = int(n_slots)
             hist = torch.zeros((S, HC, 256), dtype=torch.int32, device=dev) if road_slot is not None else \
                 torch.empty((S, HC, 256), dtype=torch.int32, device=dev)
             nzero = torch.zeros((S,), dtype=torch.int32, device=dev)
@@ -532,7 +545,8 @@ class Engine:
         td = N.RsTiles(tiles.pixels.data_ptr(), tiles.gt.data_ptr(), tiles.n_tiles, tiles.height, tiles.width,
                        tiles.channels, tiles.dtype)
         pd_ = N.RsPairs(pairs.road_pair_off.data_ptr(), pairs.pair_tile.data_ptr() if pairs.n_pairs else None, pairs.n_pairs)
-        prm = self._params(hist_mode, window, rescale, None if road_slot is None else road_slot.data_ptr())
+        prm = self._params(hist_mode, window, rescale, None if road_slot is None else road_slot.data_ptr(),
+                           min_zero_ptr=None if min_zero is None else min_zero.data_ptr())
         st = self.lib.rs_zonal_hist_dev(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
                                         hist.data_ptr(), nzero.data_ptr(), self._stream())
         N.check(st, "rs_zonal_hist_dev", self._ctx)

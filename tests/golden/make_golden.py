@@ -170,6 +170,37 @@ def main():
                       "by_class": to_jsonable(by_class), "global": to_jsonable(glob)})
     out["vote"] = {"roads": to_jsonable(roads.drop(columns=["geometry"])), "predictions": to_jsonable(preds), "sweep": sweep}
 
+    # many detections per (road, class) with near-ties: pandas' groupby sum is Kahan-compensated, a plain running sum is not
+    rng2 = np.random.default_rng(77)
+    roads_k = pd.DataFrame({"OBJECTID": np.arange(1, 61), "geometry": [None] * 60,
+                            "CATEGORY": np.where(rng2.random(60) < 0.5, "artificial", "natural"), "gt_type": ["gt"] * 60})
+    rows_k = []
+    for rid in roads_k["OBJECTID"]:
+        m = int(rng2.integers(20, 60))
+        area = np.round(rng2.uniform(0.06, 0.9, m), 2)
+        score = np.round(rng2.uniform(0.3, 1.0, m), 3)
+        perm = rng2.permutation(m)
+        for cls, order in (("artificial", np.arange(m)), ("natural", perm)):      # the same multiset in two orders: an exact tie
+            for i in order:                                                          # only for order-insensitive sums
+                rows_k.append({"OBJECTID": int(rid), "score": float(score[i]), "det_class_name": cls,
+                               "area_pred_in_label": float(area[i]), "weighted_score": float(area[i] * score[i])})
+    preds_k = pd.DataFrame(rows_k).sample(frac=1.0, random_state=3).sort_values("OBJECTID", kind="stable").reset_index(drop=True)
+    comp_k = determine_class.determine_detected_class(preds_k, roads_k, 0.0)
+    # the fixture must separate compensated from plain summation
+    naive_differs = 0
+    for rid, grp in preds_k.groupby("OBJECTID"):
+        idx = {}
+        for cls, sub in grp.groupby("det_class_name"):
+            sw = sa = 0.0
+            for w, a in zip(sub["weighted_score"], sub["area_pred_in_label"]):
+                sw += w; sa += a
+            idx[cls] = sw / sa
+        naive = "undetermined" if idx["artificial"] == idx["natural"] else ("artificial" if idx["artificial"] > idx["natural"] else "natural")
+        naive_differs += naive != comp_k.loc[comp_k["road_id"] == rid, "cover_type"].iloc[0]
+    assert naive_differs > 0, "fixture does not separate Kahan from plain sums"
+    out["vote_many"] = {"roads": to_jsonable(roads_k.drop(columns=["geometry"])), "predictions": to_jsonable(preds_k),
+                        "comparison": to_jsonable(pd.DataFrame(comp_k).drop(columns=["geometry"])), "naive_differs": int(naive_differs)}
+
     # ---------------- fct_misc.get_pixel_values (rasterio stubbed by the oracle) ----------------
     data = rng.integers(0, 256, (12, 16, 3), dtype=np.uint8)
     data[rng.random((12, 16)) < 0.15] = 0                              # all-band zeros
@@ -195,6 +226,41 @@ def main():
     missing = fct_misc.get_pixel_values(geoms["rect"], "nope.tif", range(1, 4), pd.DataFrame(), road_id=1)
     out["pixel_values"] = {"data": data.tolist(), "transform": list(t), "geoms": geoms, "cases": pv,
                            "missing_tile_rows": int(len(missing))}
+
+    # ---------------- a road over several tiles with tile nodata 0: the zero padding is per (road, tile) call ----------------
+    # (fct_misc.py:95-111 pads inside one call; statistical_analysis.py:187-193 concatenates the calls; :238-246 groupby)
+    mt_tiles, mt_t = [], []
+    for k in range(3):
+        d = rng.integers(1, 256, (10, 12, 3), dtype=np.uint8)
+        d[..., k][rng.random((10, 12)) < 0.15 + 0.1 * k] = 0          # a different band loses pixels on every tile
+        for c in range(3):
+            d[..., c][rng.random((10, 12)) < 0.08] = 0                 # independent zeros on every band: min over bands > all-zero rows
+        d[rng.random((10, 12)) < 0.05] = 0
+        mt_tiles.append(d)
+        mt_t.append((0.5, 0.0, 2000.0 + 6.0 * k, 0.0, -0.5, 7000.0))   # three tiles side by side (12 px * 0.5)
+    mt_geoms = {
+        "long": {"type": "Polygon", "coordinates": [ring((2000.7, 6996.2), (2017.4, 6996.9), (2017.4, 6998.8), (2000.7, 6998.1))]},
+        "two_tiles": {"type": "Polygon", "coordinates": [ring((2004.2, 6995.4), (2009.9, 6995.4), (2009.9, 6999.6), (2004.2, 6999.6))]},
+    }
+    mt_cases = []
+    for nodata in (0, None):
+        acc = pd.DataFrame()
+        for name, g in mt_geoms.items():
+            pv_road = pd.DataFrame()
+            for k in range(3):
+                path = f"18_9_{k}.tif"
+                TILES[path] = {"data": mt_tiles[k], "transform": mt_t[k], "nodata": nodata}
+                try:
+                    pv_road = fct_misc.get_pixel_values(g, path, range(1, 4), pv_road, road_id=name)
+                except ValueError:                                     # "Input shapes do not overlap raster."
+                    pass
+            acc = pd.concat([acc, pv_road], ignore_index=True)
+        st = {}
+        for b in (1, 2, 3):
+            st[str(b)] = to_jsonable(fct_statistics.get_df_stats_groupby(acc, f"band{b}", ["road_id"], f"_{b}"))
+        mt_cases.append({"nodata": nodata, "pixels": to_jsonable(acc), "stats": st})
+    out["multi_tile"] = {"tiles": [d.tolist() for d in mt_tiles], "transforms": [list(t) for t in mt_t], "geoms": mt_geoms,
+                         "cases": mt_cases}
 
     for k, v in out.items():
         with open(os.path.join(HERE, f"{k}.json"), "w") as f:

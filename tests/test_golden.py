@@ -104,3 +104,41 @@ def test_get_pixel_values_wrapper_matches_reference():
         n_rows += len(one)
     assert n_rows > 100
     assert g["missing_tile_rows"] == 0 and len(oraster.get_pixel_values([], None)) == 0
+
+
+def test_multi_tile_nodata_padding_matches_reference():
+    """A road over several tiles, tile nodata 0 / None: the accumulator form of the oracle (histograms + n_allzero + min_zero,
+    apply_nodata_convention) reproduces the statistics the reference's get_pixel_values + get_df_stats_groupby give when the
+    calls of a road are concatenated (statistical_analysis.py:187-193, :238-246)."""
+    from oracle import gdal_fill
+    g = load("multi_tile")
+    tiles = np.array(g["tiles"], np.uint8)
+    tr = np.array(g["transforms"], np.float64)
+    names = list(g["geoms"])
+    rings = [gdal_fill.rings_from_geojson(g["geoms"][n]) for n in names]
+    pairs = [(t, r) for r in range(len(names)) for t in range(len(tiles))]
+    hist, nz, mz = oraster.zonal_accumulate(tiles, tr, rings, pairs, want_min_zero=True)
+    assert (mz != nz).any()
+    for case in g["cases"]:
+        mode = "Z" if case["nodata"] == 0 else "N"
+        adj = ostats.apply_nodata_convention(hist, nz, mode, min_zero=mz)
+        for b in (1, 2, 3):
+            gold = case["stats"][str(b)]
+            cols = gold["columns"]
+            for name, row in zip(gold["index"], gold["data"]):
+                s = ostats.stats_from_hist(adj[names.index(name), b - 1], ddof=1)
+                exp = dict(zip(cols, row))
+                assert s["count"] == exp[f"count_{b}"] and s["min"] == exp[f"min_{b}"] and s["max"] == exp[f"max_{b}"]
+                assert s["median"] == exp[f"median_{b}"]
+                assert round(s["mean"], 2) == exp[f"mean_{b}"] and round(s["std"], 2) == exp[f"std_{b}"]
+        if mode == "Z":       # the road-level simplification (one call per road) is NOT what the reference computes
+            wrong = ostats.apply_nodata_convention(hist, nz, "Z")
+            assert (wrong[:, :, 0] != adj[:, :, 0]).any()
+
+
+def test_vote_many_detections_near_ties_match_reference():
+    g = load("vote_many")
+    comp = ovote.determine_detected_class(frame(g["predictions"]), frame(g["roads"]), 0.0)
+    gold = frame(g["comparison"])
+    assert comp["cover_type"].tolist() == gold["cover_type"].tolist()
+    np.testing.assert_allclose(comp["diff_score"].astype(float), gold["diff_score"].astype(float), rtol=1e-12, atol=0)

@@ -216,6 +216,12 @@ def test_workflows_match_the_reference_shaped_pipeline(mods):
     g = synth.Grid(4, 4)
     rr = synth.ribbon_roads(g, 14, seed=33)
     tiles = synth.host_tiles(g, 3, "asphalt")
+    # zero values that differ per band AND per tile: with nodata == 0 get_pixel_values pads every (road, tile) call on its
+    # own (fct_misc.py:95-111), so a multi-tile road is not the same as one call over its merged pixels
+    rng = np.random.default_rng(5)
+    for t in range(g.n_tiles):
+        tiles[t, :, :, t % 3][rng.random((256, 256)) < 0.05 * (1 + t % 4)] = 0
+    tiles[rng.random(tiles.shape[:3]) < 0.02] = 0
     gt = g.transforms()
     for nodata in (None, 0):
         tb = TileBatch.from_arrays(tiles, gt, nodata)
@@ -722,3 +728,64 @@ def test_vector_flow_clip_overlay_vote_metrics(mods):
         assert comp["tag"].tolist() == exp["tag"].tolist()
         obc, ogl = ovote.get_metrics(exp)
         assert np.allclose(gl[["Pb", "Rb", "f1b"]].to_numpy(float), ogl[["Pb", "Rb", "f1b"]].to_numpy(float), rtol=1e-9, atol=1e-12)
+
+
+def test_multi_tile_nodata_padding_golden():
+    """workflows.road_band_statistics on a road over several tiles against the statistics the REFERENCE's get_pixel_values +
+    get_df_stats_groupby produce (tests/golden/multi_tile.json): with tile nodata 0 every (road, tile) call is zero-padded on
+    its own (fct_misc.py:95-111) before the calls are concatenated (statistical_analysis.py:187-193)."""
+    from proj_roadsurf_b200 import workflows
+    g = load("multi_tile")
+    tiles = np.ascontiguousarray(np.array(g["tiles"], np.uint8))
+    tr = np.array(g["transforms"], np.float64)
+    names = list(g["geoms"])
+    roads = RoadSet.from_geometries([g["geoms"][n] for n in names], ids=np.arange(len(names)))
+    for case in g["cases"]:
+        tb = TileBatch.from_arrays(tiles, tr, case["nodata"])
+        table, _ = workflows.road_band_statistics(roads, tb, BANDS=(1, 2, 3))
+        assert table["road_id"].tolist() == list(range(len(names)))
+        for b in (1, 2, 3):
+            gold = case["stats"][str(b)]
+            for name, row in zip(gold["index"], gold["data"]):
+                exp = dict(zip(gold["columns"], row))
+                got = table.iloc[names.index(name)]
+                for k in ("min", "max", "median", "mean", "std", "margin"):
+                    assert abs(float(got[f"{k}_{b}"]) - float(exp[f"{k}_{b}"])) <= 1e-9, (case["nodata"], name, k, b)
+                if b == 1:
+                    assert int(got["count"]) == int(exp["count_1"])
+
+
+def test_vote_many_detections_near_ties_golden(mods):
+    """20-60 detections per (road, class), both classes holding the same multiset in different orders: the reference's
+    groupby(...).sum() is Kahan-compensated (pandas group_sum), which decides the exact tie test of determine_class.py:164;
+    vote_table_kernel sums the same way."""
+    determine_class = mods[3]
+    g = load("vote_many")
+    assert g["naive_differs"] > 0
+    comp = determine_class.determine_detected_class(frame(g["predictions"]), frame(g["roads"]), 0.0)
+    gold = frame(g["comparison"])
+    assert comp["road_id"].tolist() == gold["road_id"].tolist()
+    assert comp["cover_type"].tolist() == gold["cover_type"].tolist()
+    for col in ("nat_score", "art_score", "diff_score"):
+        np.testing.assert_allclose(comp[col].astype(float), gold[col].astype(float), rtol=1e-12, atol=0)
+
+
+def test_overlay_area_hole_touching_its_shell():
+    """A valid OGC hole may touch its shell at single points, and the parts of a MultiPolygon may touch each other: the ring
+    orientation pass (ring_sign_kernel) must not take such a vertex as the ring's representative point."""
+    from oracle import overlay as ov
+    from proj_roadsurf_b200.engine import default_engine
+    from test_oracle_kat import ring
+    eng = default_engine()
+    shell = ring((0, 0), (10, 0), (10, 10), (0, 10))
+    hole_first_on_shell = ring((0, 5), (4, 3), (4, 7))                     # the hole's FIRST vertex lies on the shell's edge x = 0
+    hole_corner = ring((10, 10), (6, 9), (9, 6))                           # ... and one whose first vertex is the shell's corner
+    part_touching = [ring((20, 0), (24, 0), (24, 4), (20, 4)), ring((24, 4), (28, 4), (28, 8), (24, 8))]   # two parts sharing a vertex
+    A = [[shell, hole_first_on_shell], [shell[::-1].copy(), hole_first_on_shell], [shell, hole_corner, hole_first_on_shell],
+         part_touching]
+    B = [[ring((-5, -5), (40, -5), (40, 40), (-5, 40))], [ring((2, 2), (8, 2), (8, 8), (2, 8))], [ring((23, 3), (25, 3), (25, 5), (23, 5))]]
+    ia, ib = np.repeat(np.arange(len(A)), len(B)), np.tile(np.arange(len(B)), len(A))
+    got, area_a = eng.overlay_area_host(RoadSet.from_geometries(A), RoadSet.from_geometries(B), ia, ib)
+    exp = np.array([ov.intersection_area(A[i], B[j]) for i, j in zip(ia, ib)])
+    assert np.array_equal(got, exp), np.stack([ia, ib, got, exp], 1)[got != exp]
+    assert area_a.tolist() == [ov.polygon_area(a) for a in A] == [92.0, 92.0, 84.5, 32.0]

@@ -350,9 +350,16 @@ def test_finalize_stats_nodata_conventions(eng, mode, omode):
     tiles = synth.host_tiles(g, 3)
     tiles[..., 1][tiles[..., 0] < 40] = 0          # bands with different numbers of zeros
     gt = g.transforms()
-    hist, nz = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs)
-    out = eng.finalize_stats_host(hist, nz, nodata_mode=mode, ddof=1)
-    adj = ostats.apply_nodata_convention(hist, nz, omode)
+    for t in range(g.n_tiles):                     # ... and different ones per tile: the zero padding is per (road, tile) call
+        tiles[t, :, :, t % 3][tiles[t, :, :, (t + 1) % 3] > 200 - 10 * t] = 0
+    hist, nz, mz = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, gt), rr.pairs, want_min_zero=True)
+    oh, onz, omz = cport.zonal_accumulate(rr.roads.xy, rr.roads.ring_off, rr.roads.road_ring_off, rr.pairs.road_pair_off,
+                                          rr.pairs.pair_tile, tiles, gt, want_min_zero=True)
+    assert np.array_equal(hist.astype(np.uint64), oh) and np.array_equal(nz.astype(np.uint64), onz)
+    assert np.array_equal(mz.astype(np.uint64), omz)
+    assert (omz != onz).any()                      # the two corrections differ on this input
+    out = eng.finalize_stats_host(hist, mz if mode == "zero" else nz, nodata_mode=mode, ddof=1)
+    adj = ostats.apply_nodata_convention(hist, nz, omode, min_zero=omz)
     for r in range(24):
         for c in range(3):
             s = ostats.stats_from_hist(adj[r, c], ddof=1)
