@@ -48,7 +48,16 @@ def parse():
     ap.add_argument("--e2e-mode", default="both", choices=["both", "stream", "mapped"], help="host-buffer transport(s) to time; the "
                     "faster one is reported as e2e")
     ap.add_argument("--cpu-rows", type=int, default=32, help="tile rows of the CPU baseline sample")
-    ap.add_argument("--extras", action="store_true", help="also time the class/score (config 2) and uint16 rescale (config 3) kernels")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: tiles-y rows and roads-per-gpu roads PER GPU "
+                    "(N = 8 is the canton configuration); strong: that much IN TOTAL, sharded over the GPUs (efficiency = T1 / (N TN))")
+    ap.add_argument("--balance", default="pairs", choices=["tiles", "pairs"], help="shard cuts: equal tile counts, or tile ranges "
+                    "holding equal numbers of (road, tile) pairs")
+    ap.add_argument("--no-legs", action="store_true", help="skip the full-size legs of the other BASELINE configurations (N = 1)")
+    ap.add_argument("--leg-steps", type=int, default=5)
+    ap.add_argument("--wide-grid", type=int, default=64, help="configs[4] leg: tiles per side of the 1024 px lattice (64 -> 4096 tiles)")
+    ap.add_argument("--wide-polys", type=int, default=1536)
+    ap.add_argument("--pageable-rows", type=int, default=96, help="tile rows of the pageable-caller e2e sample")
+    ap.add_argument("--no-pageable", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -144,9 +153,12 @@ class PcieRxSampler:
 
 
 def build_inputs(args, world):
+    """the GLOBAL tile lattice and road set (weak scaling: tiles_y rows and roads_per_gpu roads per GPU; strong scaling: that
+    much in total, whatever the number of GPUs)"""
     from proj_roadsurf_b200 import synth
-    grid = synth.Grid(args.tiles_x, args.tiles_y * world)
-    rr = synth.ribbon_roads(grid, args.roads_per_gpu * world)
+    mult = 1 if args.scaling == "strong" else world
+    grid = synth.Grid(args.tiles_x, args.tiles_y * mult)
+    rr = synth.ribbon_roads(grid, args.roads_per_gpu * mult)
     return grid, rr
 
 
@@ -162,8 +174,80 @@ def cpu_cores():
 
 
 def workload_name(args, world):
+    if args.scaling == "strong":
+        return (f"strong scaling: {args.tiles_x}x{args.tiles_y} zoom-18 tiles of {H}x{W}x{C} uint8 and {args.roads_per_gpu} buffered "
+                f"road polygons IN TOTAL, sharded by tile over {world} GPU(s)")
     return (f"canton-scale shard (BASELINE configs[3] at 8 GPUs): {args.tiles_x}x{args.tiles_y} zoom-18 tiles of "
             f"{H}x{W}x{C} uint8 and {args.roads_per_gpu} buffered road polygons per GPU, x{world} GPU(s), sharded by tile")
+
+
+def load_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """DRAM bytes per launch measured under ncu for the legs of this file (profiles/traffic.json; see profiles/README.md)"""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+
+# ---------------------------------------------------------------------------------------------
+def oracle_rows(eng, grid, roads, pairs, road_idx, resident=None, tile_lo=0, tile_hi=0, channels=C, dtype="u8", kind=0, size=H,
+                joint=False, scale=None):
+    """Per-road histograms of the roads `road_idx` of (roads, pairs) from the plain-C oracle.  pairs holds GLOBAL tile indices of
+    `grid`; the pixels of a tile come from `resident` (this rank's DeviceTiles, tiles [tile_lo, tile_hi)) when the rank owns it
+    and are regenerated with the deterministic generator otherwise (tiles another rank owns: boundary roads)."""
+    import torch
+    from oracle import cport
+    road_idx = np.asarray(road_idx, np.int64)
+    r_s, p_s = roads.subset(road_idx), pairs.take_roads(road_idx)
+    tiles_g, inv = np.unique(p_s.pair_tile.astype(np.int64), return_inverse=True)
+    own = (tiles_g >= tile_lo) & (tiles_g < tile_hi) if resident is not None else np.zeros(len(tiles_g), bool)
+    npdt = np.uint16 if dtype == "u16" else np.uint8
+    host = np.empty((len(tiles_g), size, size, channels), npdt)
+    if own.any():
+        sel = torch.from_numpy(tiles_g[own] - tile_lo).to(resident.pixels.device)
+        got = resident.pixels.index_select(0, sel).cpu().numpy()
+        host[own] = got.view(np.uint16) if dtype == "u16" else got
+    if (~own).any():
+        far = eng.synth_tiles_dev(grid.keys(tiles_g[~own]), size, size, channels, dtype=dtype, kind=kind)
+        got = far.pixels.cpu().numpy()
+        host[~own] = got.view(np.uint16) if dtype == "u16" else got
+        del far
+    gt = grid.transforms(tiles_g)
+    kw = {}
+    if scale is not None:
+        kw = dict(scale_k=scale[0], scale_off=scale[1], rescale_f32=bool(scale[2]))
+    return cport.zonal_accumulate(r_s.xy, r_s.ring_off, r_s.road_ring_off, p_s.road_pair_off, inv.astype(np.int32), host, gt,
+                                  joint=joint, threads=cpu_cores(), **kw)
+
+
+def rows_match(gpu_hist, gpu_nz, rows, oh, onz):
+    import torch
+    sel = torch.as_tensor(np.asarray(rows, np.int64), device=gpu_hist.device)
+    gh = gpu_hist.index_select(0, sel).cpu().numpy().view(np.uint32).astype(np.uint64)
+    gz = gpu_nz.index_select(0, sel).cpu().numpy().view(np.uint32).astype(np.uint64)
+    return bool(np.array_equal(gh, oh) and np.array_equal(gz, onz))
+
+
+def spread(n, k):
+    """k indices spread over range(n)"""
+    return np.unique(np.linspace(0, n - 1, min(n, k)).astype(np.int64)) if n > 0 else np.zeros(0, np.int64)
+
+
+def time_loop(torch, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 # ---------------------------------------------------------------------------------------------
@@ -179,9 +263,9 @@ def run_reference(args):
     world = 1          # the sample is a slice of rank 0's shard, whatever --gpus says
     grid, rr = build_inputs(args, world)
     sh = plan_shards(rr.roads, rr.pairs, grid.n_tiles, 1)[0]
-    n_sub = args.tiles_x * args.cpu_rows
+    n_sub = args.tiles_x * min(args.cpu_rows, args.tiles_y)
     roads, pairs, _ = sub_problem(sh.roads, sh.pairs, n_sub)
-    tiles = synth.host_tiles(synth.Grid(args.tiles_x, args.cpu_rows), C, args.kind)
+    tiles = synth.host_tiles(synth.Grid(args.tiles_x, min(args.cpu_rows, args.tiles_y)), C, args.kind)
     gt = grid.transforms(np.arange(n_sub))
     cores = cpu_cores()
     cport.build()
@@ -197,11 +281,11 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     px = n_sub * H * W
     val = px * args.steps / dt / 1e9
-    sample = f"first {args.cpu_rows} tile rows of the shard: {n_sub} tiles, {roads.n_roads} roads, {pairs.n_pairs} pairs per step"
+    sample = f"first {min(args.cpu_rows, args.tiles_y)} tile rows of the shard: {n_sub} tiles, {roads.n_roads} roads, {pairs.n_pairs} pairs per step"
     print(json.dumps({
         "impl": "reference", "metric": "Gpixel/s rasterize+per-road zonal stats", "value": val, "unit": "Gpixel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(args, args.gpus), "sample": sample},
         "cpu_baseline": {"value": val, "unit": "Gpixel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Gpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,6 +294,118 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def config_legs(args, eng, torch, dev, grid, sh, rr_gt_class, dr, dp, peak, traffic):
+    """The other BASELINE.json configurations, each at full size on this GPU, each with its kernel time, roofline fraction,
+    measured DRAM bytes (when profiles/traffic.json holds them) and its own oracle flag.  Runs on one GPU after the main leg
+    released its tiles."""
+    from oracle import vote as ovote
+    from proj_roadsurf_b200 import synth
+    from proj_roadsurf_b200.engine import scale_params
+    legs = {}
+    n_tiles = sh.tile_hi - sh.tile_lo
+    tile_idx = np.arange(sh.tile_lo, sh.tile_hi)
+    gt = grid.transforms(tile_idx)
+    g_pairs = sh.pairs                                # world == 1: local tile index == global tile index
+    sample = spread(sh.roads.n_roads, 96)
+
+    def leg_entry(ms, px, bpp, name_key, ok, **extra):
+        gpx = px / (ms * 1e-3) / 1e9
+        e = {"Gpixel/s": gpx, "kernel_ms": ms, "bytes_per_pixel": bpp, "roofline_frac": gpx * bpp / peak,
+             "dram_bytes": traffic.get("legs", {}).get(name_key), "gpu_matches_oracle_on_sample": ok}
+        e.update(extra)
+        return e
+
+    # ---- configs[0]/[3] pixel values, low-entropy variant (SURVEY 7.3): N(110, 6) values, same-bin histogram contention ----
+    if args.kind != "asphalt":
+        t = eng.synth_tiles_dev(grid.keys(tile_idx), H, W, C, kind=1, gt=gt)
+        out = eng.zonal_hist_dev(dr, t, dp, check=False)
+        ms = time_loop(torch, lambda: eng.zonal_hist_dev(dr, t, dp, out=out, check=False), args.leg_steps, 3)
+        eng.sync_status()
+        oh, onz = oracle_rows(eng, grid, sh.roads, g_pairs, sample, t, 0, n_tiles, kind=1)
+        legs["asphalt_u8x3"] = leg_entry(ms, n_tiles * H * W, 3, "asphalt_u8x3", rows_match(out[0], out[1], sample, oh, onz),
+                                         config="configs[0]/[3] shapes with low-entropy N(110, 6) pixel values", tiles=n_tiles)
+        del t, out
+        torch.cuda.empty_cache()
+
+    # ---- configs[1]: class/score planes -> per-road joint histogram -> vote + confusion + F1 for 20 thresholds ----
+    t = eng.synth_tiles_dev(grid.keys(tile_idx), H, W, 2, kind=2, gt=gt)
+    out = eng.zonal_hist_dev(dr, t, dp, hist_mode="class_score", check=False)
+    ms = time_loop(torch, lambda: eng.zonal_hist_dev(dr, t, dp, hist_mode="class_score", out=out, check=False), args.leg_steps, 3)
+    eng.sync_status()
+    gtc_h = np.ascontiguousarray(rr_gt_class[sh.road_global], np.int8)
+    gtc = torch.from_numpy(gtc_h).to(dev)
+    cuts = ovote.score_cutoffs()
+    vm = [None]
+
+    def vote():
+        vm[0] = eng.vote_metrics_dev(out[0], gtc, cuts, rule="count", check=False)
+    ms_vote = time_loop(torch, vote, args.leg_steps, 3)
+    oh, onz = oracle_rows(eng, grid, sh.roads, g_pairs, sample, t, 0, n_tiles, channels=2, kind=2, joint=True)
+    ok = rows_match(out[0], out[1], sample, oh, onz)
+    # the vote on the sample rows against the oracle sweep (confusion counts exact, balanced F1 to 1e-6)
+    sel = torch.as_tensor(sample, device=dev)
+    _, _, conf_s, met_s = eng.vote_metrics_dev(out[0].index_select(0, sel).contiguous(), gtc.index_select(0, sel).contiguous(), cuts,
+                                               rule="count")
+    rows, best = ovote.sweep(oh.astype(np.uint32), gtc_h[sample], rule="count")
+    conf_s, met_s = conf_s.cpu().numpy(), met_s.cpu().numpy()
+    ok_vote = all(np.array_equal(conf_s[i], rows[i]["confusion"]) and abs(met_s[i, 11] - rows[i]["f1b"]) <= 1e-6 for i in range(len(cuts)))
+    met_full = vm[0][3].cpu().numpy()
+    legs["class_score_vote_u8x2"] = leg_entry(ms, n_tiles * H * W, 2, "class_score_vote_u8x2", bool(ok and ok_vote),
+                                              config="configs[1]: synthetic class + score planes, pixel-count argmax vote, confusion, F1",
+                                              vote_metrics_ms=ms_vote, thresholds=len(cuts), tiles=n_tiles,
+                                              best_f1b=float(met_full[:, 11].max()))
+    del t, out, vm
+    torch.cuda.empty_cache()
+
+    # ---- configs[2]: 4-band uint16 tiles, tif2cog 16 -> 8 bit rescale fused with the zonal statistics ----
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    rows16 = int(min(args.tiles_y, (free_b * 0.88) // (args.tiles_x * H * W * 8)))
+    if rows16 >= 8:
+        n16 = args.tiles_x * rows16
+        if n16 == n_tiles:
+            roads16, pairs16, dr16, dp16 = sh.roads, g_pairs, dr, dp
+        else:
+            roads16, pairs16, _ = sub_problem(sh.roads, sh.pairs, n16)
+            dr16, dp16 = eng.upload_roads(roads16), eng.upload_pairs(pairs16)
+        t = eng.synth_tiles_dev(grid.keys(tile_idx[:n16]), H, W, 4, dtype="u16", kind=0, gt=gt[:n16])
+        k, off = scale_params([150.0] * 4, [9000.0] * 4)
+        for f32 in (False, True):
+            rs = (k, off, f32) if not f32 else scale_params([150.0] * 4, [9000.0] * 4, True) + (True,)
+            out = eng.zonal_hist_dev(dr16, t, dp16, rescale=rs, check=False)
+            ms = time_loop(torch, lambda: eng.zonal_hist_dev(dr16, t, dp16, rescale=rs, out=out, check=False), args.leg_steps, 3)
+            eng.sync_status()
+            smp = spread(roads16.n_roads, 64)
+            oh, onz = oracle_rows(eng, grid, roads16, pairs16, smp, t, 0, n16, channels=4, dtype="u16", scale=rs)
+            name = "rescale_u16x4_" + ("f32" if f32 else "f64")
+            legs[name] = leg_entry(ms, n16 * H * W, 8, name, rows_match(out[0], out[1], smp, oh, onz),
+                                   config="configs[2]: RGB+NIR uint16 tiles, gdal.Translate -scale fused into the accumulation, "
+                                          + ("float32" if f32 else "float64") + " working precision", tiles=n16)
+            del out
+        del t
+        torch.cuda.empty_cache()
+
+    # ---- configs[4]: 1024 px tiles, wide polygons with holes and 1 k - 10 k vertices (long edge lists) ----
+    g5 = synth.Grid(args.wide_grid, args.wide_grid, size=1024)
+    wp = synth.wide_polygons(g5, args.wide_polys)
+    t5 = eng.synth_tiles_dev(g5.keys(), 1024, 1024, 3, kind=0, gt=g5.transforms())
+    d5r, d5p = eng.upload_roads(wp.roads), eng.upload_pairs(wp.pairs)
+    o5 = eng.zonal_hist_dev(d5r, t5, d5p, check=False)
+    ms5 = time_loop(torch, lambda: eng.zonal_hist_dev(d5r, t5, d5p, out=o5, check=False), args.leg_steps, 2)
+    eng.sync_status()
+    smp = spread(wp.roads.n_roads, 6)
+    oh, onz = oracle_rows(eng, g5, wp.roads, wp.pairs, smp, t5, 0, g5.n_tiles, size=1024)
+    cov5 = float(o5[0][:, 0].sum().item()) / (g5.n_tiles * 1024.0 * 1024.0)
+    nv5 = np.diff(wp.roads.ring_off[wp.roads.road_ring_off])
+    legs["wide_polygons_1024px"] = leg_entry(ms5, g5.n_tiles * 1024 * 1024, 3, "wide_polygons_1024px",
+                                             rows_match(o5[0], o5[1], smp, oh, onz),
+                                             config="configs[4]: 10 cm 1024x1024 tiles, 100-300 px wide polygons with 1-8 holes",
+                                             tiles=g5.n_tiles, polygons=int(wp.roads.n_roads), pairs=int(wp.pairs.n_pairs),
+                                             covered_fraction=cov5, mean_vertices=float(nv5.mean()), max_vertices=int(nv5.max()))
+    del t5, o5
+    torch.cuda.empty_cache()
+    return legs
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -238,12 +434,13 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     grid, rr = build_inputs(args, world)
-    sh = plan_shards(rr.roads, rr.pairs, grid.n_tiles, world, only_rank=rank)[rank]
-    del rr
+    sh = plan_shards(rr.roads, rr.pairs, grid.n_tiles, world, only_rank=rank, balance=args.balance)[rank]
     n_tiles = sh.tile_hi - sh.tile_lo
     tile_idx = np.arange(sh.tile_lo, sh.tile_hi)
     gt = grid.transforms(tile_idx)
     eng = Engine(local)
+    if world > 1:
+        eng.comm_init_from_torch()          # the merge goes through the C ABI (rs_allreduce_accumulators_dev), not torch.distributed
     kind = {"uniform": 0, "asphalt": 1}[args.kind]
     dt_ = eng.synth_tiles_dev(grid.keys(tile_idx), H, W, C, kind=kind, gt=gt)
     dr, dp = eng.upload_roads(sh.roads), eng.upload_pairs(sh.pairs)
@@ -254,7 +451,7 @@ def run_b200(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     def step(i=None):
-        if world > 1:
+        if world > 1:                       # boundary rows of roads this rank does not hold must be zero before the sum
             hist[sh.n_own:].zero_()
             nz[sh.n_own:].zero_()
         if i is not None:
@@ -262,7 +459,7 @@ def run_b200(args):
         eng.zonal_hist_dev(dr, dt_, dp, road_slot=slot, out=(hist, nz), check=False)
         if i is not None:
             ev[i][1].record()
-        merge_boundary(hist, nz, sh.n_own)
+        merge_boundary(hist, nz, sh.n_own, engine=eng)
         eng.finalize_stats_dev(hist, nz, nodata_mode="none", ddof=1, out=stats, check=False)
 
     def barrier():
@@ -296,21 +493,40 @@ def run_b200(args):
     px_total = float(grid.n_tiles) * H * W
     value = px_total * args.steps / (ms_total * 1e-3) / 1e9
 
+    # ---- parity of the timed result, every rank, AFTER the merge: a spread of this rank's own roads and of the boundary
+    #      roads it touches (their pixels live on several ranks: the oracle sees all their tiles) against the plain-C oracle ----
+    parity, parity_note = None, None
+    if not args.no_cpu:
+        from oracle import cport
+        cport.build()
+        own_s = spread(sh.n_own, 48)
+        oh, onz = oracle_rows(eng, grid, rr.roads, rr.pairs, sh.road_global[own_s], dt_, sh.tile_lo, sh.tile_hi, kind=kind)
+        ok = rows_match(hist, nz, sh.slot[own_s], oh, onz)
+        n_b_checked = 0
+        if world > 1 and sh.n_boundary > 0:
+            mine = np.arange(sh.n_own, len(sh.road_global))                   # local roads that are boundary roads
+            b_s = mine[spread(len(mine), 64)]
+            oh, onz = oracle_rows(eng, grid, rr.roads, rr.pairs, sh.road_global[b_s], dt_, sh.tile_lo, sh.tile_hi, kind=kind)
+            ok = ok and rows_match(hist, nz, sh.slot[b_s], oh, onz)
+            n_b_checked = len(b_s)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        cnt = torch.tensor([len(own_s), n_b_checked], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        parity = bool(flag.item())
+        parity_note = (f"{int(cnt[0].item())} own roads and {int(cnt[1].item())} boundary roads (after the NCCL merge; all their tiles, "
+                       f"also those of other ranks) over {world} rank(s) against the plain-C oracle, AND over ranks")
+
     # ---- roofline of the dominant kernel (fused rasterize + histogram), this rank's launch ----
     nv_road = (sh.roads.ring_off[sh.roads.road_ring_off[1:]] - sh.roads.ring_off[sh.roads.road_ring_off[:-1]]).astype(np.int64)
     edge_bytes = 16 * int((nv_road * np.diff(sh.pairs.road_pair_off)).sum())
     alg_bytes = n_tiles * H * W * C + edge_bytes + sh.n_rows * (C * 1024 + 4)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = load_peak()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    traffic = load_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic.get("dram_bytes_per_launch") if args.scaling == "weak" and args.tiles_y == 512 else None,
                 "kernel": "zonal_kernel (fused rasterize + per-road histograms)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "algorithmic bytes = every tile byte once + 16 B per edge per pair + output rows (SURVEY 8d); the kernel is "
@@ -320,6 +536,7 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         rows = min(args.e2e_rows, args.tiles_y) if args.e2e_rows > 0 else args.tiles_y
+        rows = min(rows, n_tiles // args.tiles_x)
         try:                                            # the pinned copy of the tiles must fit comfortably in host memory
             import psutil
             budget = psutil.virtual_memory().available * 0.5 / world
@@ -328,7 +545,9 @@ def run_b200(args):
             rows = min(rows, 64)
         n_sub = args.tiles_x * rows
         roads_s, pairs_s, _ = sub_problem(sh.roads, sh.pairs, n_sub)
+        t0 = time.perf_counter()
         host_px = torch.empty((n_sub, H, W, C), dtype=torch.uint8, pin_memory=True)
+        pin_s = time.perf_counter() - t0
         host_px.copy_(dt_.pixels[:n_sub])
         torch.cuda.synchronize()
         tb = TileBatch(host_px.numpy(), gt[:n_sub], H, W, C)
@@ -338,7 +557,7 @@ def run_b200(args):
         modes = {"stream": dict(tiles_per_chunk=chunk), "mapped": dict(mapped=True)}
         if args.e2e_mode != "both":
             modes = {args.e2e_mode: modes[args.e2e_mode]}
-        n_e2e, legs, st_ref, rx = 3, {}, None, {}
+        n_e2e, legs_e, st_ref, rx = 3, {}, None, {}
         for name, kw in modes.items():
             eng.zonal_stats_host(roads_s, tb, pairs_s, **kw)                       # warm-up (allocates the staging buffers)
             barrier()
@@ -352,29 +571,56 @@ def run_b200(args):
             et = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(et, op=dist.ReduceOp.MAX)
-            legs[name] = world * n_sub * H * W * n_e2e / float(et.item()) / 1e9
+            legs_e[name] = world * n_sub * H * W * n_e2e / float(et.item()) / 1e9
             if st_ref is None:
                 st_ref = st_host
             elif not np.array_equal(st_ref, st_host, equal_nan=True):
                 raise SystemExit("e2e transports disagree")
-        best = max(legs, key=legs.get)
-        # bytes that cross the host link per step: every tile byte when streamed; when the kernel reads the page-locked tiles
-        # in place, the PCIe read bytes ncu counted for that kernel per tile byte (profiles/traffic.json, mapped_host_tiles)
-        h2d_px = host_px.numel() if best == "stream" else None
+        best = max(legs_e, key=legs_e.get)
+        # bytes that cross the host link per step: every tile byte when streamed (counted from the buffer); when the kernel reads
+        # the page-locked tiles in place, what NVML's PCIe RX counter saw over the timed passes of THIS run (fallback: the
+        # ncu pcie__read_bytes ratio kept in profiles/traffic.json)
         how = {"stream": f"rs_zonal_stats_stream_host ({chunk}-tile chunks through two device buffers, copy overlapped with compute)",
                "mapped": "rs_zonal_stats_mapped_host (zonal_kernel reads the page-locked tiles in place; only the sectors under "
                          "road pixels cross the host link)"}[best]
-        if h2d_px is None:
-            frac = 1.0
-            if os.path.exists(tpath):            # ncu pcie__read_bytes of the in-place kernel per tile byte (same synthetic roads)
-                frac = json.load(open(tpath)).get("mapped_host_tiles", {}).get("pcie_read_bytes_per_tile_byte", 1.0)
-            h2d_px = int(host_px.numel() * min(1.0, frac))
-        e2e = {"value": legs[best], "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d_px + h2d_meta),
+        if best == "stream":
+            h2d_px, h2d_src = host_px.numel(), "counted from the copied buffers"
+        elif rx.get("mapped"):
+            h2d_px, h2d_src = max(0, rx["mapped"] - h2d_meta), "NVML PCIe RX counter over the timed passes of this run"
+        else:
+            frac = traffic.get("mapped_host_tiles", {}).get("pcie_read_bytes_per_tile_byte", 1.0)
+            h2d_px, h2d_src = int(host_px.numel() * min(1.0, frac)), "ncu pcie__read_bytes ratio of profiles/traffic.json (NVML gave no samples)"
+        e2e = {"value": legs_e[best], "unit": "Gpixel/s", "h2d_bytes_per_step": int(h2d_px + h2d_meta),
                "d2h_bytes_per_step": int(st_host.nbytes), "steps": n_e2e, "transport": best,
-               "transports_Gpixel_s": legs, "host_tile_bytes": int(host_px.numel()),
-               "pcie_rx_bytes_per_step_nvml": rx,
-               "sample": f"first {rows} of {args.tiles_y} tile rows of each rank's shard ({n_sub} tiles, {roads_s.n_roads} roads) in pinned "
-                         f"host memory through {how}; statistics table read back"}
+               "transports_Gpixel_s": legs_e, "host_tile_bytes": int(host_px.numel()), "h2d_bytes_source": h2d_src,
+               "pcie_rx_bytes_per_step_nvml": rx, "pinned_alloc_s": pin_s,
+               "sample": f"first {rows} of {n_tiles // args.tiles_x} tile rows of each rank's shard ({n_sub} tiles, {roads_s.n_roads} roads) in "
+                         f"pinned host memory through {how}; statistics table read back"}
+        # what a caller with an ordinary (pageable) buffer gets: the streamed copies run from pageable memory, or the buffer is
+        # page-locked first (rs_host_register: the cost is reported, it is a one-off per buffer)
+        if world == 1 and not args.no_pageable:
+            prow = max(1, min(rows, args.pageable_rows))
+            n_p = args.tiles_x * prow
+            roads_p, pairs_p, _ = sub_problem(sh.roads, sh.pairs, n_p)
+            pageable = np.empty((n_p, H, W, C), np.uint8)
+            pageable[:] = host_px.numpy()[:n_p]
+            tbp = TileBatch(pageable, gt[:n_p], H, W, C)
+            eng.zonal_stats_host(roads_p, tbp, pairs_p, tiles_per_chunk=chunk)
+            t0 = time.perf_counter()
+            st_p = eng.zonal_stats_host(roads_p, tbp, pairs_p, tiles_per_chunk=chunk)
+            t1 = time.perf_counter()
+            eng.pin_host(pageable)
+            t2 = time.perf_counter()
+            st_m = eng.zonal_stats_host(roads_p, tbp, pairs_p, mapped=True)
+            t3 = time.perf_counter()
+            eng.unpin_host(pageable)
+            e2e["pageable_caller"] = {
+                "streamed_from_pageable_Gpixel_s": n_p * H * W / (t1 - t0) / 1e9,
+                "register_s": t2 - t1, "register_GB": pageable.nbytes / 1e9,
+                "register_then_in_place_first_call_Gpixel_s": n_p * H * W / (t3 - t1) / 1e9,
+                "results_equal": bool(np.array_equal(st_p, st_m, equal_nan=True)),
+                "sample": f"first {prow} tile rows ({n_p} tiles) in an ordinary numpy buffer"}
+            del pageable
         del host_px
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the same sample ----
@@ -386,86 +632,21 @@ def run_b200(args):
         roads_s, pairs_s, idx = sub_problem(sh.roads, sh.pairs, n_sub)
         tiles_h = dt_.pixels[:n_sub].cpu().numpy()
         cores = cpu_cores()
-        cport.build()
         t0 = time.perf_counter()
         oh, onz = cport.zonal_accumulate(roads_s.xy, roads_s.ring_off, roads_s.road_ring_off, pairs_s.road_pair_off,
                                          pairs_s.pair_tile, tiles_h, gt[:n_sub], threads=cores)
         t1 = time.perf_counter()
         dts = eng.upload_tiles(TileBatch(tiles_h, gt[:n_sub], H, W, C))
-        gh, gz = eng.zonal_hist_dev(eng.upload_roads(roads_s), dts, eng.upload_pairs(pairs_s))
+        drs, dps = eng.upload_roads(roads_s), eng.upload_pairs(pairs_s)
+        gh, gz = eng.zonal_hist_dev(drs, dts, dps)
+        gpu_ms = time_loop(torch, lambda: eng.zonal_hist_dev(drs, dts, dps, out=(gh, gz), check=False), 5, 1)
         ok = bool(np.array_equal(gh.cpu().numpy().view(np.uint32).astype(np.uint64), oh) and
                   np.array_equal(gz.cpu().numpy().view(np.uint32).astype(np.uint64), onz))
         cpu = {"value": n_sub * H * W / (t1 - t0) / 1e9, "unit": "Gpixel/s", "cores": cores, "kind": "port",
                "sample": f"first {rows} tile rows of the shard ({n_sub} tiles, {roads_s.n_roads} roads, {pairs_s.n_pairs} pairs), "
                          "one pass of the plain-C oracle, one thread per core",
-               "gpu_matches_oracle_on_sample": ok}
-
-    # ---- optional: the other tile formats of BASELINE.json configs[1] / configs[2] on a 128 x 128 tile block ----
-    extras = None
-    if args.extras and world == 1:
-        from proj_roadsurf_b200.engine import scale_params
-        g2 = synth.Grid(128, 128)
-        rr2 = synth.ribbon_roads(g2, 8192)
-        dr2, dp2 = eng.upload_roads(rr2.roads), eng.upload_pairs(rr2.pairs)
-        gt2 = g2.transforms()
-        extras = {}
-        for name, ch, dtype, kind, kw, bpp in (("class_score_u8x2", 2, "u8", 2, {"hist_mode": "class_score"}, 2),
-                                               ("rescale_u16x4", 4, "u16", 0, {"rescale": scale_params([150.0] * 4, [9000.0] * 4) + (False,)}, 8),
-                                               ("bands_u8x3", 3, "u8", 0, {}, 3)):
-            t2 = eng.synth_tiles_dev(g2.keys(), H, W, ch, dtype=dtype, kind=kind, gt=gt2)
-            for _ in range(3):
-                out2 = eng.zonal_hist_dev(dr2, t2, dp2, check=False, **kw)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(10):
-                eng.zonal_hist_dev(dr2, t2, dp2, out=out2, check=False, **kw)
-            e1.record()
-            torch.cuda.synchronize()
-            eng.sync_status()
-            ms2 = e0.elapsed_time(e1) / 10
-            gpx = g2.n_tiles * H * W / (ms2 * 1e-3) / 1e9
-            extras[name] = {"Gpixel/s": gpx, "kernel_ms": ms2, "bytes_per_pixel": bpp,
-                            "roofline_frac": gpx * bpp / peak, "tiles": g2.n_tiles}
-            del t2, out2
-        # BASELINE configs[4]: 1024 px tiles, wide polygons with holes and 1 k - 10 k vertices (long edge lists)
-        g5 = synth.Grid(32, 32, size=1024)
-        wp = synth.wide_polygons(g5, 384)
-        t5 = eng.synth_tiles_dev(g5.keys(), 1024, 1024, 3, kind=0, gt=g5.transforms())
-        d5r, d5p = eng.upload_roads(wp.roads), eng.upload_pairs(wp.pairs)
-        for _ in range(2):
-            o5 = eng.zonal_hist_dev(d5r, t5, d5p, check=False)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            eng.zonal_hist_dev(d5r, t5, d5p, out=o5, check=False)
-        e1.record()
-        torch.cuda.synchronize()
-        eng.sync_status()
-        ms5 = e0.elapsed_time(e1) / 5
-        cov5 = float(o5[0][:, 0].sum().item()) / (g5.n_tiles * 1024.0 * 1024.0)
-        gpx5 = g5.n_tiles * 1024 * 1024 / (ms5 * 1e-3) / 1e9
-        extras["wide_polygons_1024px"] = {"Gpixel/s": gpx5, "kernel_ms": ms5, "bytes_per_pixel": 3, "roofline_frac": gpx5 * 3 / peak,
-                                          "tiles": g5.n_tiles, "polygons": 384, "pairs": wp.pairs.n_pairs, "covered_fraction": cov5,
-                                          "mean_vertices": float(np.diff(wp.roads.ring_off[wp.roads.road_ring_off]).mean())}
-        del t5, o5
-        # the materialising 16 -> 8 bit pass (tif2cog.py:260-270): 8 B read + 4 B written per pixel, pure HBM streaming
-        n_t = 16384
-        t16 = eng.synth_tiles_dev(np.arange(n_t, dtype=np.int64), H, W, 4, dtype="u16", kind=0)
-        o8 = torch.empty((n_t, H, W, 4), dtype=torch.uint8, device=dev)
-        for f32 in (False, True):
-            for _ in range(3):
-                eng.rescale_u16_dev(t16.pixels, [150.0] * 4, [9000.0] * 4, bidx=[1, 2, 3, 0], f32=f32, out=o8)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(10):
-                eng.rescale_u16_dev(t16.pixels, [150.0] * 4, [9000.0] * 4, bidx=[1, 2, 3, 0], f32=f32, out=o8)
-            e1.record()
-            torch.cuda.synchronize()
-            ms2 = e0.elapsed_time(e1) / 10
-            gbs = n_t * H * W * 12 / (ms2 * 1e-3) / 1e9
-            extras["rescale_u16_to_u8_" + ("f32" if f32 else "f64")] = {"Gpixel/s": n_t * H * W / (ms2 * 1e-3) / 1e9, "kernel_ms": ms2,
-                                                                      "bytes_per_pixel": 12, "GB/s": gbs, "roofline_frac": gbs / peak}
-        del t16, o8
+               "gpu_matches_oracle_on_sample": ok, "gpu_kernel_ms_same_sample": gpu_ms}
+        del dts, gh, gz
 
     # ---- reference-shaped CPU variant: per-pair Python loop + DataFrame concat + groupby, 1 core ----
     if cpu is not None:
@@ -491,18 +672,28 @@ def run_b200(args):
                                    "sample": f"4x4 tiles, 8 roads, {rrA.pairs.n_pairs} pairs: per-pair Python loop + DataFrame concat + "
                                              "pandas groupby (statistical_analysis.py:180-246 shape), pure-Python oracle"}
 
+    # ---- the other BASELINE configurations at full size (one GPU) ----
+    legs = None
+    if world == 1 and not args.no_legs:
+        del dt_, hist, nz, stats
+        torch.cuda.empty_cache()
+        legs = config_legs(args, eng, torch, dev, grid, sh, rr.gt_class, dr, dp, peak, traffic)
+
     if rank == 0:
         line = {
             "metric": "Gpixel/s rasterize+per-road zonal stats", "value": value, "unit": "Gpixel/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(args, world), "tiles_per_gpu": n_tiles, "roads_rank0": int(sh.roads.n_roads),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "tiles_rank0": n_tiles, "roads_rank0": int(sh.roads.n_roads),
                        "pairs_rank0": int(sh.pairs.n_pairs), "boundary_roads": int(sh.n_boundary), "tile_kind": args.kind,
+                       "shard_cuts": args.balance,
+                       "merge": "rs_allreduce_accumulators_dev: one grouped NCCL all-reduce of the boundary rows" if world > 1 else "none",
                        "l2": f"inputs ({n_tiles * H * W * C / 1e9:.1f} GB per GPU) are larger than L2; no flush"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "gpu_matches_oracle_on_sample": parity, "parity_sample": parity_note,
         }
-        if extras is not None:
-            line["extras"] = extras
+        if legs is not None:
+            line["configs"] = legs
         print(json.dumps(line))
     eng.close()
     if world > 1:

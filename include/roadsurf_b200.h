@@ -47,7 +47,9 @@ enum rs_status {
     RS_ERR_ROTATED = -4,       /* a tile transform has b != 0 or d != 0                           */
     RS_ERR_NO_DEVICE = -5,     /* no CUDA device / device is not sm_100                           */
     RS_ERR_UNSUPPORTED = -6,   /* width > 2048, channels not in 1..4, dtype/channels combination  */
-    RS_ERR_NOT_PINNED = -7     /* rs_zonal_stats_mapped_host: tiles->pixels is not page-locked    */
+    RS_ERR_NOT_PINNED = -7,    /* rs_zonal_stats_mapped_host: tiles->pixels is not page-locked    */
+    RS_ERR_NO_NCCL = -8,       /* rs_comm_*: libnccl.so.2 could not be loaded                     */
+    RS_ERR_NCCL = -9           /* an NCCL call failed                                             */
 };
 
 enum rs_dtype { RS_U8 = 0, RS_U16 = 1 };
@@ -223,6 +225,28 @@ int rs_finalize_stats_host(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_
 int rs_zonal_stats_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                         const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
                         int32_t n_pct, double *stats, uint32_t *hist, uint32_t *n_allzero);
+
+/*
+ * Multi-GPU merge (one process per GPU, tiles sharded over the GPUs of a box).  The reference is single-process: a road's
+ * pixels are concatenated over all its tiles before the groupby (scripts/statistical_analysis/statistical_analysis.py:187-193);
+ * with the tiles spread over devices, the roads that touch tiles of several ranks get a row in a boundary table that has the
+ * same layout on every rank, and one all-reduce(SUM) of the integer accumulators over NVLink completes those rows on every
+ * rank (exact and order-independent; statistics are finalized afterwards, so medians and percentiles are exact).
+ *   rs_comm_unique_id   rank 0 creates the 128-byte rendezvous id and hands it to the other ranks (any channel)
+ *   rs_comm_init        every rank, same id: builds the NCCL communicator of this context (collective call)
+ *   rs_allreduce_accumulators_dev   in-place sum over ranks of hist_rows[n_hist] (the boundary rows of the histogram table,
+ *                       n_hist = rows * HC * 256), n_allzero_rows[n_rows] and, when not NULL, min_zero_rows[n_rows], as ONE
+ *                       grouped NCCL launch on `stream`; device pointers; a context without communicator (single GPU) returns
+ *                       RS_OK without doing anything
+ * NCCL is bound at run time (libnccl.so.2; inside a PyTorch process the copy torch loaded): RS_ERR_NO_NCCL when absent.
+ */
+#define RS_COMM_ID_BYTES 128
+int rs_comm_unique_id(void *id_out);
+int rs_comm_init(rs_ctx *ctx, const void *id, int32_t world, int32_t rank);
+int rs_comm_destroy(rs_ctx *ctx);
+int rs_comm_world(rs_ctx *ctx);
+int rs_allreduce_accumulators_dev(rs_ctx *ctx, uint32_t *hist_rows, int64_t n_hist, uint32_t *n_allzero_rows,
+                                  uint32_t *min_zero_rows, int64_t n_rows, void *stream);
 
 /*
  * Per-road vote, tags, confusion counts and F1 for a list of score cut-offs in one launch.

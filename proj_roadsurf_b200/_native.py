@@ -14,7 +14,9 @@ RS_OK = 0
 STATUS = {
     0: "RS_OK", -1: "RS_ERR_INVALID_ARG", -2: "RS_ERR_CUDA", -3: "RS_ERR_CAPACITY",
     -4: "RS_ERR_ROTATED", -5: "RS_ERR_NO_DEVICE", -6: "RS_ERR_UNSUPPORTED", -7: "RS_ERR_NOT_PINNED",
+    -8: "RS_ERR_NO_NCCL", -9: "RS_ERR_NCCL",
 }
+RS_COMM_ID_BYTES = 128
 RS_ERR_NOT_PINNED = -7
 RS_U8, RS_U16 = 0, 1
 RS_HIST_BANDS, RS_HIST_CLASS_SCORE = 0, 1
@@ -34,6 +36,7 @@ EXPORTS = (
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
     "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
     "rs_pairs_bbox_host", "rs_rescale_u16_dev", "rs_rescale_u16_host", "rs_ks_hist_host",
+    "rs_comm_unique_id", "rs_comm_init", "rs_comm_destroy", "rs_comm_world", "rs_allreduce_accumulators_dev",
 )
 
 
@@ -134,6 +137,11 @@ def load():
     L.rs_ks_hist_host.argtypes = [P, P, P, P, C.c_int32, C.c_int32, P, P]
     L.rs_rescale_u16_dev.argtypes = [P, P, C.c_int64, C.c_int32, C.c_int32, P, P, P, C.c_int32, P, P]
     L.rs_rescale_u16_host.argtypes = L.rs_rescale_u16_dev.argtypes[:-1]
+    L.rs_comm_unique_id.argtypes = [P]
+    L.rs_comm_init.argtypes = [P, P, C.c_int32, C.c_int32]
+    L.rs_comm_destroy.argtypes = [P]
+    L.rs_comm_world.argtypes = [P]
+    L.rs_allreduce_accumulators_dev.argtypes = [P, P, C.c_int64, P, P, C.c_int64, P]
     L.rs_synth_tiles_dev.argtypes = [P, P, P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_uint64, P]
     for name in EXPORTS:

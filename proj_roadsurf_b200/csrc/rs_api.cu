@@ -112,6 +112,8 @@ const char *rs_status_string(int status)
         case RS_ERR_NO_DEVICE: return "no sm_100 CUDA device";
         case RS_ERR_UNSUPPORTED: return "unsupported tile shape or dtype";
         case RS_ERR_NOT_PINNED: return "the tile buffer is not page-locked host memory";
+        case RS_ERR_NO_NCCL: return "libnccl.so.2 could not be loaded";
+        case RS_ERR_NCCL: return "an NCCL call failed";
         default: return "unknown status";
     }
 }
@@ -149,6 +151,7 @@ int rs_ctx_destroy(rs_ctx *ctx)
 {
     if (!ctx) return RS_OK;
     cudaSetDevice(ctx->device);
+    rs_comm_destroy(ctx);
     for (auto &b : ctx->stage)
         if (b.p) cudaFree(b.p);
     if (ctx->items.p) cudaFree(ctx->items.p);

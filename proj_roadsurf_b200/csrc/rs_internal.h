@@ -36,6 +36,8 @@ struct rs_ctx {
     cudaEvent_t ev_scratch = nullptr;     // recorded after every launch that uses the scratch above
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
+    void *comm = nullptr;                 // ncclComm_t of rs_comm_init (rs_comm.cu)
+    int comm_world = 0, comm_rank = 0;
 };
 
 namespace rs {

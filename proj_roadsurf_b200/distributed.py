@@ -44,10 +44,22 @@ def tile_ranges(n_tiles: int, world: int) -> np.ndarray:
     return (np.arange(world + 1, dtype=np.int64) * n_tiles) // world
 
 
+def balanced_tile_ranges(pair_tile: np.ndarray, n_tiles: int, world: int) -> np.ndarray:
+    """(world + 1,) tile index cuts of contiguous blocks that hold (nearly) equal numbers of (road, tile) pairs: the
+    kernel's work follows the pairs, not the tiles, so these cuts level the per-rank kernel times."""
+    per_tile = np.bincount(np.asarray(pair_tile, np.int64), minlength=n_tiles)
+    csum = np.concatenate([[0], np.cumsum(per_tile)])
+    target = csum[-1] * np.arange(world + 1, dtype=np.float64) / world
+    cuts = np.searchsorted(csum, target, side="left").astype(np.int64)
+    cuts[0], cuts[-1] = 0, n_tiles
+    return np.maximum.accumulate(np.minimum(cuts, n_tiles))
+
+
 def plan_shards(roads: Optional[RoadSet], pairs: PairList, n_tiles: int, world: int,
-                only_rank: Optional[int] = None) -> List[Shard]:
-    """Split a global pair list by tile block.  With `roads`, each shard carries its compact road soup."""
-    cuts = tile_ranges(n_tiles, world)
+                only_rank: Optional[int] = None, balance: str = "tiles") -> List[Shard]:
+    """Split a global pair list by tile block.  With `roads`, each shard carries its compact road soup.
+    balance: 'tiles' = equal tile counts per rank, 'pairs' = contiguous tile ranges with equal pair counts."""
+    cuts = tile_ranges(n_tiles, world) if balance == "tiles" or world == 1 else balanced_tile_ranges(pairs.pair_tile, n_tiles, world)
     R = len(pairs.road_pair_off) - 1
     road_of = pairs.road_of_pair().astype(np.int64)
     pair_rank = np.searchsorted(cuts, pairs.pair_tile.astype(np.int64), side="right") - 1
@@ -79,15 +91,22 @@ def plan_shards(roads: Optional[RoadSet], pairs: PairList, n_tiles: int, world: 
     return shards
 
 
-def merge_boundary(hist, n_allzero, n_own: int, group=None):
+def merge_boundary(hist, n_allzero, n_own: int, group=None, engine=None, min_zero=None):
     """In-place all-reduce(SUM) of the boundary rows of a rank's tables (torch tensors, int32 storage of
-    the uint32 counters: two's-complement addition is the same bit pattern)."""
+    the uint32 counters: two's-complement addition is the same bit pattern).  With an ``engine`` that holds a
+    communicator (Engine.comm_init*) the merge is the C ABI's rs_allreduce_accumulators_dev (one grouped NCCL launch);
+    otherwise torch.distributed collectives (gloo in the CPU tests)."""
+    if engine is not None and engine.comm_world > 1:
+        engine.allreduce_accumulators_dev(hist, n_allzero, n_own, min_zero)
+        return
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     if hist.shape[0] > n_own:
         dist.all_reduce(hist[n_own:], op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(n_allzero[n_own:], op=dist.ReduceOp.SUM, group=group)
+        if min_zero is not None:
+            dist.all_reduce(min_zero[n_own:], op=dist.ReduceOp.SUM, group=group)
 
 
 def global_rows(shard: Shard) -> np.ndarray:

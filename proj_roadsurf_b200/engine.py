@@ -590,6 +590,47 @@ class Engine:
             self.sync_status()
         return cover, scores, conf, met
 
+    # ------------------------------------------------------------------ multi-GPU merge (rs_comm.cu)
+    def comm_unique_id(self) -> bytes:
+        """rank 0: the 128-byte NCCL rendezvous id to hand to every rank (rs_comm_unique_id)."""
+        buf = C.create_string_buffer(N.RS_COMM_ID_BYTES)
+        N.check(self.lib.rs_comm_unique_id(buf), "rs_comm_unique_id", self._ctx)
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, world: int, rank: int) -> None:
+        """collective: build this context's NCCL communicator (rs_comm_init)."""
+        assert len(unique_id) == N.RS_COMM_ID_BYTES
+        N.check(self.lib.rs_comm_init(self._ctx, C.c_char_p(unique_id), int(world), int(rank)), "rs_comm_init", self._ctx)
+
+    def comm_init_from_torch(self) -> None:
+        """comm_init with the id passed through the torch.distributed process group that is already up."""
+        torch = self._torch()
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.device("cuda", self.device)
+        t = torch.zeros(N.RS_COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(self.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        self.comm_init(bytes(t.cpu().numpy().tobytes()), world, rank)
+
+    @property
+    def comm_world(self) -> int:
+        return int(self.lib.rs_comm_world(self._ctx))
+
+    def allreduce_accumulators_dev(self, hist, n_allzero, n_own: int, min_zero=None) -> None:
+        """In-place sum over ranks of the boundary rows [n_own:] of a shard's tables, one grouped NCCL launch on the
+        current torch stream (rs_allreduce_accumulators_dev)."""
+        n_b = int(hist.shape[0]) - int(n_own)
+        if n_b <= 0:
+            return
+        assert hist.is_contiguous() and n_allzero.is_contiguous()
+        row = int(hist.shape[1]) * int(hist.shape[2])
+        st = self.lib.rs_allreduce_accumulators_dev(
+            self._ctx, hist.data_ptr() + 4 * row * int(n_own), n_b * row, n_allzero.data_ptr() + 4 * int(n_own),
+            None if min_zero is None else min_zero.data_ptr() + 4 * int(n_own), n_b, self._stream())
+        N.check(st, "rs_allreduce_accumulators_dev", self._ctx)
+
     def sync_status(self):
         st = self.lib.rs_ctx_sync_status(self._ctx, self._stream())
         N.check(st, "kernel status", self._ctx)

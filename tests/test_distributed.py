@@ -83,3 +83,23 @@ def test_plan_invariants():
         assert s.pairs.pair_tile.min() >= 0 and s.pairs.pair_tile.max() < s.tile_hi - s.tile_lo
         assert len(np.unique(s.slot)) == len(s.slot) and s.slot.max() < s.n_rows
         assert np.array_equal(s.boundary_global, shards[0].boundary_global)
+
+
+def test_balanced_cuts_level_the_pair_counts():
+    from proj_roadsurf_b200.distributed import balanced_tile_ranges
+    g = synth.Grid(16, 24)
+    rr = synth.ribbon_roads(g, 400, seed=5)
+    # crowd the roads' pairs towards the first tile rows: equal tile counts are then far from equal work
+    keep = (rr.pairs.pair_tile < g.n_tiles // 3) | (np.arange(rr.pairs.n_pairs) % 4 == 0)
+    road_of = rr.pairs.road_of_pair()[keep]
+    from proj_roadsurf_b200.geometry import PairList
+    pairs = PairList.from_pairs(400, road_of, rr.pairs.pair_tile[keep])
+    world = 4
+    cuts = balanced_tile_ranges(pairs.pair_tile, g.n_tiles, world)
+    assert cuts[0] == 0 and cuts[-1] == g.n_tiles and np.all(np.diff(cuts) >= 0)
+    per = [int(((pairs.pair_tile >= cuts[r]) & (pairs.pair_tile < cuts[r + 1])).sum()) for r in range(world)]
+    even = [int(((pairs.pair_tile >= c0) & (pairs.pair_tile < c1)).sum()) for c0, c1 in zip(tile_ranges(g.n_tiles, world)[:-1],
+                                                                                        tile_ranges(g.n_tiles, world)[1:])]
+    assert max(per) - min(per) < 0.1 * pairs.n_pairs / world + 16 < max(even) - min(even)
+    shards = plan_shards(None, pairs, g.n_tiles, world, balance="pairs")
+    assert [s.tile_lo for s in shards] == list(cuts[:-1]) and sum(s.pairs.n_pairs for s in shards) == pairs.n_pairs
