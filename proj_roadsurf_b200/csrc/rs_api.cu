@@ -157,6 +157,11 @@ int rs_ctx_destroy(rs_ctx *ctx)
     if (ctx->items.p) cudaFree(ctx->items.p);
     if (ctx->pgeom.p) cudaFree(ctx->pgeom.p);
     if (ctx->pair_zero.p) cudaFree(ctx->pair_zero.p);
+    for (rs::DevBuf *b : {&ctx->wide_cnt, &ctx->wide_off, &ctx->wide_bounds, &ctx->wide_pair_road, &ctx->wide_tmp})
+        if (b->p) cudaFree(b->p);
+    if (ctx->pool.p) cudaFree(ctx->pool.p);
+    if (ctx->heads.p) cudaFree(ctx->heads.p);
+    if (ctx->ov_items.p) cudaFree(ctx->ov_items.p);
     if (ctx->ev_scratch) cudaEventDestroy(ctx->ev_scratch);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->d_counters) cudaFree(ctx->d_counters);

@@ -33,6 +33,8 @@ struct rs_ctx {
     rs::DevBuf items;                     // grow-only work-item list of the zonal kernel
     rs::DevBuf pgeom;                     // grow-only per-pair geometry records of the zonal kernel
     rs::DevBuf pair_zero;                 // grow-only per-pair zero counts (min_zero of row-split pairs on tall tiles)
+    rs::DevBuf pool, heads, ov_items;     // grow-only entry pool / per-item segment heads / overflow items of the two-kernel form
+    rs::DevBuf wide_cnt, wide_off, wide_bounds, wide_pair_road, wide_tmp;   // per-launch tables of the wide-window kernel (rs_wide.cu)
     cudaEvent_t ev_scratch = nullptr;     // recorded after every launch that uses the scratch above
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
@@ -64,6 +66,10 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
                        int tile_lo, int tile_hi, int accumulate, cudaStream_t st);
 int launch_road_bbox(rs_ctx *ctx, const rs_roads *roads, double *out, cudaStream_t st);
+// wide-window form (rs_wide.cu): tiles of 512 .. 2048 pixels under wide polygons with long edge lists
+bool wide_eligible(const rs_tiles *tiles, const rs_zonal_params *prm, bool resident);
+int launch_zonal_wide(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, const rs_zonal_params *prm,
+                      uint32_t *hist, uint32_t *n_allzero, int window_mode, int tile_lo, int tile_hi, int accumulate, cudaStream_t st);
 int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int n_roads, int channels,
                     int nodata_mode, int ddof, const double *pct_host, int n_pct, double *stats, cudaStream_t st);
 int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class, int n_roads,

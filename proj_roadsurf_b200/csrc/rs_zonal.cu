@@ -36,17 +36,17 @@
 // geometry: the rounding of every operation is part of the specification.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "rs_internal.h"
+#include "rs_raster.cuh"
 
 namespace rs {
 
-constexpr unsigned FULL = 0xffffffffu;
 constexpr int WARPS = 4;        // teams per CTA
 constexpr int CTAS_PER_SM = 5;  // occupancy target (shared memory: ~10.6 KB per team)
 constexpr int PPI = 8;          // pairs per work item, at most
 constexpr int AREA_MAX = 6 * 65536;   // window pixels per work item (a pair above it gets an item of its own)
-constexpr int ROWS_ITEM = 256;  // a window taller than this is split by rows over several items
 constexpr int VCAP = 96;        // vertices staged in shared memory per road (longer roads read L2)
 constexpr int MASKW = 896;      // mask words per team
 constexpr int RCMAX = 128;      // rows per mask chunk
@@ -55,51 +55,20 @@ constexpr int NCHUNK = 32;      // culling chunks per road
 constexpr int RINGCAP = 16;     // ring starts kept in shared memory
 constexpr int MAX_WIDTH = 2048; // one row's groups (W / 8) must fit the queue next to a partial round
 constexpr int ITEM_SPLIT = 1 << 30;           // item flag: the road has several items (accumulate with atomics)
+// two-kernel form (emit_kernel = zonal_kernel<PxEmit> -> accum_kernel): the rasterizer writes its 8-pixel-group entries to a
+// pool in HBM instead of consuming them; pool addresses are in UNITS of 16 bytes
+constexpr uint32_t CHUNK_UNITS = 4096;        // units a team takes from the pool with one atomicAdd (64 KiB)
+constexpr uint32_t HEAD_OVERFLOW = 0xffffffffu;   // heads[]: the pool ran out under this item, the fused kernel redoes it
+#ifndef RS_EMIT_CTAS
+#define RS_EMIT_CTAS 6
+#endif
+constexpr int EMIT_CTAS = RS_EMIT_CTAS;      // zonal_kernel<PxEmit>: no histogram, no pixel registers
+constexpr int ACC_CTAS = 12;                  // accum_kernel: CTAs of 4 warps per SM (48 warps/SM, <= 40 registers)
 constexpr uint32_t ROW_REWALK = 0xffffffffu;   // rowmap marker: recount this row over [0, pitch)
-
-// ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    const uint32_t a = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-// TMA 1-D bulk copy; dst/src 16-byte aligned, bytes a multiple of 16.
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of dst
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel arguments
 // ---------------------------------------------------------------------------------------------
-struct PairGeom;
-
 struct ZonalArgs {
     const double2 *xy;
     const int *ring_off;
@@ -127,86 +96,21 @@ struct ZonalArgs {
     double sk[4], so[4];
     int *work_counter;
     int *status;
+    // two-kernel form
+    uint32_t *pool;           // segments: 1 header unit {pixel base lo, hi, entries, next segment + 1} then the entries (4 per unit)
+    uint32_t pool_units;
+    uint32_t *pool_cursor;
+    uint32_t *heads;          // per item-queue index: last segment + 1 of the item (0 = no entries, HEAD_OVERFLOW)
+    int4 *ov_items;           // items the pool could not hold ...
+    int *ov_count;            // ... and their number
 };
 
-// per-pair geometry: integer window inside the tile + world->window-pixel transform
-struct alignas(16) PairGeom {       // 64 bytes, computed once per pair by pair_geom_kernel
-    double inv0, inv1, inv3, inv5;
-    int col_off, row_off, w, h;     // window inside the tile (what is masked and read)
-    int xshift, yshift, wu;         // RS_WINDOW_BOUNDLESS: the rasterized window starts xshift columns / yshift rows
-                                    // before the visible one and is wu columns wide (0, 0, w otherwise)
-    int status;                     // 1: rasterize; 0: shapes do not overlap the raster; < 0: rs_status
+// team-local allocation state of the emitting rasterizer (warp-uniform registers)
+struct EmitState {
+    uint32_t pos = 0, end = 0;      // the team's current chunk of the pool
+    uint32_t prev = 0;              // last segment + 1 of the current item
+    uint32_t overflow = 0;          // sticky: the pool is exhausted
 };
-
-// rasterio geometry_window + window_transform + GDALInvGeoTransform, from the road bbox
-// (px/py are monotone in x/y for north-up transforms, so the vertex-wise bounds rasterio takes
-// are attained at the bbox corners).  Returns 0 (shapes do not overlap raster), 1, or <0.
-__device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, const double *__restrict__ bb, int W, int H,
-                                             int window_mode, int border, PairGeom &g)
-{
-    const double sa = gt[0], sb = gt[1], sc = gt[2], sd = gt[3], se = gt[4], sf = gt[5];
-    if (sb != 0.0 || sd != 0.0 || sa == 0.0 || se == 0.0) return RS_ERR_ROTATED;
-    if (window_mode == RS_WINDOW_FULL) {
-        g.col_off = 0; g.row_off = 0; g.w = W; g.h = H;
-        g.xshift = 0; g.yshift = 0; g.wu = W;
-        g.inv0 = __ddiv_rn(-sc, sa); g.inv1 = __ddiv_rn(1.0, sa);
-        g.inv3 = __ddiv_rn(-sf, se); g.inv5 = __ddiv_rn(1.0, se);
-        if (border > 0) {          // keep the transform of the whole raster, look at the inner rectangle only
-            if (2 * border >= W || 2 * border >= H) return 0;
-            g.col_off = border; g.row_off = border; g.w = W - 2 * border; g.h = H - 2 * border;
-            g.xshift = border; g.yshift = border;
-        }
-        return 1;
-    }
-    // Affine.__invert__
-    const double det = __dsub_rn(__dmul_rn(sa, se), __dmul_rn(sb, sd));
-    const double idet = __ddiv_rn(1.0, det);
-    const double ra = __dmul_rn(se, idet), rb = __dmul_rn(-sb, idet);
-    const double rd = __dmul_rn(-sd, idet), re = __dmul_rn(sa, idet);
-    const double rc = __dsub_rn(__dmul_rn(-sc, ra), __dmul_rn(sf, rb));
-    const double rf = __dsub_rn(__dmul_rn(-sc, rd), __dmul_rn(sf, re));
-    const double xmin = bb[0], ymin = bb[1], xmax = bb[2], ymax = bb[3];
-    // (vx*ra + vy*rb) + rc ; (vx*rd + vy*re) + rf
-    const double pxa = __dadd_rn(__dadd_rn(__dmul_rn(xmin, ra), __dmul_rn(ymin, rb)), rc);
-    const double pxb = __dadd_rn(__dadd_rn(__dmul_rn(xmax, ra), __dmul_rn(ymin, rb)), rc);
-    const double pya = __dadd_rn(__dadd_rn(__dmul_rn(xmin, rd), __dmul_rn(ymin, re)), rf);
-    const double pyb = __dadd_rn(__dadd_rn(__dmul_rn(xmin, rd), __dmul_rn(ymax, re)), rf);
-    const double left = fmin(pxa, pxb), right = fmax(pxa, pxb);
-    const double top = fmin(pya, pyb), bottom = fmax(pya, pyb);
-    if (!(left == left) || !(right == right) || !(top == top) || !(bottom == bottom)) return 0;
-    const double r0 = floor(top), c0 = floor(left);
-    const double hh = fmax(ceil(bottom) - r0, 0.0), ww = fmax(ceil(right) - c0, 0.0);
-    const double r1 = r0 + hh, c1 = c0 + ww;
-    if (r0 >= (double)H || r1 <= 0.0 || c0 >= (double)W || c1 <= 0.0) return 0;   // rasterio WindowError
-    const int ir0 = (int)fmax(r0, 0.0), ir1 = (int)fmin(r1, (double)H);
-    const int ic0 = (int)fmax(c0, 0.0), ic1 = (int)fmin(c1, (double)W);
-    g.col_off = ic0; g.row_off = ir0; g.w = ic1 - ic0; g.h = ir1 - ir0;
-    if (g.w <= 0 || g.h <= 0) return 0;
-    g.xshift = 0; g.yshift = 0; g.wu = g.w;
-    double xo = (double)ic0, yo = (double)ir0;
-    if (window_mode == RS_WINDOW_BOUNDLESS) {       // rasterstats: the window keeps its unclipped origin
-        if (c0 < -1.0e9 || r0 < -1.0e9 || ww > 2.0e9) return RS_ERR_UNSUPPORTED;
-        xo = c0; yo = r0;
-        g.xshift = ic0 - (int)c0; g.yshift = ir0 - (int)r0; g.wu = (int)fmin(ww, 2.0e9);
-    }
-    // transform * Affine.translation(xo, yo), then GDALInvGeoTransform (north-up branch)
-    const double wa = __dadd_rn(__dmul_rn(sa, 1.0), __dmul_rn(sb, 0.0));
-    const double wc = __dadd_rn(__dadd_rn(__dmul_rn(sa, xo), __dmul_rn(sb, yo)), sc);
-    const double we = __dadd_rn(__dmul_rn(sd, 0.0), __dmul_rn(se, 1.0));
-    const double wf = __dadd_rn(__dadd_rn(__dmul_rn(sd, xo), __dmul_rn(se, yo)), sf);
-    g.inv0 = __ddiv_rn(-wc, wa); g.inv1 = __ddiv_rn(1.0, wa);
-    g.inv3 = __ddiv_rn(-wf, we); g.inv5 = __ddiv_rn(1.0, we);
-    if (border > 0) {
-        // the rasterized window keeps its origin and size; only the pixels at least `border` away from the tile edge
-        // are looked at (determine_class.clip_labels: labels clipped to the tile scaled by 0.99)
-        const int c_lo = max(g.col_off, border), c_hi = min(g.col_off + g.w, W - border);
-        const int r_lo = max(g.row_off, border), r_hi = min(g.row_off + g.h, H - border);
-        if (c_hi <= c_lo || r_hi <= r_lo) return 0;
-        g.xshift += c_lo - g.col_off; g.yshift += r_lo - g.row_off;
-        g.col_off = c_lo; g.row_off = r_lo; g.w = c_hi - c_lo; g.h = r_hi - r_lo;
-    }
-    return 1;
-}
 
 // thread per pair: its geometry record (the road of pair p is found by bisection of the CSR offsets)
 __global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ road_pair_off, const int *__restrict__ pair_tile,
@@ -232,31 +136,20 @@ __global__ void __launch_bounds__(256) pair_geom_kernel(const int *__restrict__ 
     out[p] = g;
 }
 
-// Integer <-> binary64 without the conversion unit (F2I / I2F / FRND run on the quarter-rate XU pipe):
-// adding 1.5 * 2^52 leaves rint(v) in the low mantissa word; every step is an exact or correctly rounded
-// binary64 add, so the results below are the same integers floor()/ceil()/(int) casts would give.
-constexpr double MAGIC = 6755399441055744.0;            // 1.5 * 2^52
-__device__ __forceinline__ int rint_magic(double v, double &t)      // |v| < 2^31; t = (double)result
+int launch_pair_geom(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, int window_mode, int border,
+                     int tile_lo, int tile_hi, cudaStream_t st)
 {
-    const double sft = __dadd_rn(v, MAGIC);
-    t = __dsub_rn(sft, MAGIC);
-    return __double2loint(sft);
+    if (pairs->n_pairs <= 0) return RS_OK;
+    int rc = ensure(ctx, ctx->pgeom, (size_t)pairs->n_pairs * sizeof(PairGeom));
+    if (rc) return rc;
+    pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
+                                                                   roads->n_roads, pairs->n_pairs, tiles->width, tiles->height,
+                                                                   window_mode, border, tile_lo, tile_hi, (PairGeom *)ctx->pgeom.p,
+                                                                   ctx->d_status);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
 }
-__device__ __forceinline__ double int2double_magic(int y)          // exact for every int32
-{
-    return __dsub_rn(__hiloint2double(0x43300000, y ^ (int)0x80000000), 4503601774854144.0);   // 2^52 + 2^31
-}
-// smallest integer y with y + 0.5 >= v (exact comparisons); the largest y with y + 0.5 < v is that minus 1
-__device__ __forceinline__ int first_row_ge(double v)
-{
-    const double vc = fmin(fmax(v, -4.0), 1.0e6);
-    double t;
-    const int ti = rint_magic(__dsub_rn(vc, 0.5), t);
-    if (__dadd_rn(t, 0.5) < vc) return ti + 1;
-    if (__dsub_rn(t, 0.5) >= vc) return ti - 1;
-    return ti;
-}
-__device__ __forceinline__ int last_row_lt(double v) { return first_row_ge(v) - 1; }
 
 // ---------------------------------------------------------------------------------------------
 // pixel policies: a group is 8 consecutive pixels = NW 32-bit words in registers
@@ -295,7 +188,7 @@ __device__ __forceinline__ uint32_t bin_off(uint32_t w, int k)      // k is a co
 template <int C_>
 struct PxBandsU8 {
     static constexpr int C = C_, HC = C_, BPP = C_, NW = 2 * C_;
-    static constexpr bool MASK = false;
+    static constexpr bool MASK = false, EMIT = false;
     // pixel I of the group: hist (shared-memory byte address of the team histogram) gets one increment per band
     // `on` is the pixel's mask bit (0 / 1), also the addend of its increments
     template <int I>
@@ -333,7 +226,7 @@ struct PxBandsU8 {
 
 struct PxClassScore {
     static constexpr int C = 2, HC = 3, BPP = 2, NW = 4;
-    static constexpr bool MASK = false;
+    static constexpr bool MASK = false, EMIT = false;
     __device__ static __forceinline__ void one(uint32_t cls, uint32_t score, uint32_t *hist, uint32_t &nz)
     {
         nz += ((cls | score) == 0);
@@ -359,7 +252,7 @@ struct PxClassScore {
 template <bool F32>
 struct PxU16x4Rescale {
     static constexpr int C = 4, HC = 4, BPP = 8, NW = 16;
-    static constexpr bool MASK = false;
+    static constexpr bool MASK = false, EMIT = false;
     __device__ static __forceinline__ uint32_t scale(const ZonalArgs &a, uint32_t s, int c)
     {
         if (F32) {
@@ -399,7 +292,11 @@ struct PxU16x4Rescale {
 
 struct PxMask {
     static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
-    static constexpr bool MASK = true;
+    static constexpr bool MASK = true, EMIT = false;
+};
+struct PxEmit {                     // the rasterizer of the two-kernel form: entries go to the pool
+    static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
+    static constexpr bool MASK = true, EMIT = true;
 };
 
 // 8 pixels x BPP bytes from a (8*BPP)-byte aligned address into NW words
@@ -464,21 +361,23 @@ struct alignas(1024) TeamSmem {
     uint8_t pdst[SPARSE ? 96 : 1];
 };
 
-__device__ __forceinline__ uint32_t prefix_xor32(uint32_t t)
-{
-    t ^= t << 1; t ^= t << 2; t ^= t << 4; t ^= t << 8; t ^= t << 16;
-    return t;
-}
-// bit 7 of every non-zero byte
-__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t m) { return (((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m) & 0x80808080u; }
-
 // ---------------------------------------------------------------------------------------------
 // one work item
 // ---------------------------------------------------------------------------------------------
 template <class PX, bool FAST, bool SPARSE>
 __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC, SPARSE> &s, const int4 item, const int lane,
-                                             uint32_t &mbar_phase)
+                                             uint32_t &mbar_phase, EmitState &es, const int qidx)
 {
+    if constexpr (PX::EMIT) {
+        if (es.overflow) {          // nothing can be emitted any more: hand the item to the fused kernel right away
+            if (lane == 0) {
+                a.heads[qidx] = HEAD_OVERFLOW;
+                a.ov_items[atomicAdd(a.ov_count, 1)] = item;
+            }
+            return;
+        }
+        es.prev = 0;
+    }
     const uint32_t hist_addr = smem_u32(s.hist), one = a.one;
     const int road = item.x, pb = item.y, pe = item.y + (item.z & ~ITEM_SPLIT), row_first = item.w;
     const bool split = (item.z & ITEM_SPLIT) != 0;
@@ -754,7 +653,26 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             // entries [0, n) of the queue: one lane per entry; the next round's pixels are in flight
             // while this round's histogram atomics issue
             auto consume = [&](const int n) {
-                if constexpr (PX::MASK) {
+                if constexpr (PX::EMIT) {
+                    // one segment: header unit + entries, from the team's chunk of the pool
+                    const uint32_t units = 1u + (((uint32_t)n + 3u) >> 2);
+                    if (!es.overflow && es.pos + units > es.end) {
+                        uint32_t b = 0;
+                        if (lane == 0) b = atomicAdd(a.pool_cursor, CHUNK_UNITS);
+                        b = __shfl_sync(FULL, b, 0);
+                        if (b > a.pool_units || a.pool_units - b < CHUNK_UNITS) es.overflow = 1;
+                        else { es.pos = b; es.end = b + CHUNK_UNITS; }
+                    }
+                    if (!es.overflow) {
+                        uint32_t *seg = a.pool + 4 * (size_t)es.pos;
+                        const size_t base = tile_pix + (size_t)(g.row_off + r0) * a.W + cbcol;
+                        if (lane == 0)
+                            *reinterpret_cast<uint4 *>(seg) = make_uint4((uint32_t)base, (uint32_t)(base >> 32), (uint32_t)n, es.prev);
+                        for (int e = lane; e < n; e += 32) seg[4 + e] = s.u.entries[e];
+                        es.prev = es.pos + 1u;
+                        es.pos += units;
+                    }
+                } else if constexpr (PX::MASK) {
                     for (int e = lane; e < n; e += 32) {
                         const uint32_t en = s.u.entries[e];
                         const int x8 = cbcol + 8 * (int)((en >> 8) & 0xfffu);
@@ -927,6 +845,12 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
         }
     }
 
+    if constexpr (PX::EMIT) {
+        if (lane == 0) {
+            a.heads[qidx] = es.overflow ? HEAD_OVERFLOW : es.prev;
+            if (es.overflow) a.ov_items[atomicAdd(a.ov_count, 1)] = item;
+        }
+    }
     // ---------------- write the road's accumulators ----------------
     if constexpr (!PX::MASK) {
         __syncwarp();
@@ -955,7 +879,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
 // the kernel: persistent teams pulling items
 // ---------------------------------------------------------------------------------------------
 template <class PX, bool FAST, bool SPARSE = false>
-__global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const ZonalArgs a)
+__global__ void __launch_bounds__(WARPS * 32, PX::EMIT ? EMIT_CTAS : CTAS_PER_SM) zonal_kernel(const ZonalArgs a)
 {
     using S = TeamSmem<PX::HC, SPARSE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -970,6 +894,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const Zo
     for (int i = lane; i < RCMAX / 4; i += 32) reinterpret_cast<uint4 *>(s.rowmap)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     uint32_t mbar_phase = 0;
+    EmitState es;
     // longest items first: the tail of the dynamic queue (teams finishing their last item while the others idle) is then made
     // of the short items
     const int n_big = a.n_items[0], n_items = n_big + a.n_items[1];
@@ -979,7 +904,91 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS_PER_SM) zonal_kernel(const Zo
         idx = __shfl_sync(FULL, idx, 0);
         if (idx >= n_items) break;
         const int at = idx < n_big ? idx : a.items_cap - 1 - (idx - n_big);
-        process_item<PX, FAST, SPARSE>(a, s, __ldg(a.items + at), lane, mbar_phase);
+        process_item<PX, FAST, SPARSE>(a, s, __ldg(a.items + at), lane, mbar_phase, es, idx);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// two-kernel form, second kernel: the entries of an item (segments chained from heads[]) -> the road's histograms.
+// A team needs nothing but its histogram (HC KiB of shared memory) and <= 40 registers: 48 warps per SM hide the
+// dependent entry -> pixel -> atomic chain that the fused kernel (20 warps per SM) stalls on.
+// ---------------------------------------------------------------------------------------------
+template <class PX>
+__global__ void __launch_bounds__(WARPS * 32, ACC_CTAS) accum_kernel(const ZonalArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) {
+        if (threadIdx.x == 0) atomicMin(a.status, (int)RS_ERR_CUDA);
+        return;
+    }
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw) + warp * PX::HC * 256;
+    const uint32_t hist_addr = smem_u32(hist), one = a.one;
+    const int n_big = a.n_items[0], n_items = n_big + a.n_items[1];
+    const uint8_t *px = (const uint8_t *)a.pixels;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(a.work_counter + 6, 1);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= n_items) break;
+        const uint32_t head = __ldg(a.heads + idx);
+        if (head == HEAD_OVERFLOW) continue;                         // the fused kernel redoes this item
+        const int at = idx < n_big ? idx : a.items_cap - 1 - (idx - n_big);
+        const int4 item = __ldg(a.items + at);
+        for (int i = lane; i < PX::HC * 64; i += 32) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        uint32_t nz = 0;
+        for (uint32_t sg = head; sg != 0u;) {
+            const uint32_t *seg = a.pool + 4 * (size_t)(sg - 1u);
+            const uint4 h = __ldg(reinterpret_cast<const uint4 *>(seg));
+            const size_t base = (size_t)h.x | ((size_t)h.y << 32);
+            const int n = (int)h.z;
+            sg = h.w;
+            auto address = [&](uint32_t en) -> const uint8_t * {
+                return px + (base + (size_t)(en >> 20) * a.W + 8u * ((en >> 8) & 0xfffu)) * PX::BPP;
+            };
+            // one lane per entry; the next round's pixels are in flight while this round's atomics issue
+            uint32_t rn[PX::NW];
+            uint32_t m8n = 0;
+            int e = lane;
+            if (e < n) {
+                const uint32_t en = __ldg(seg + 4 + e);
+                m8n = en & 255u;
+                load_group<PX::BPP, PX::NW>(address(en), rn);
+            }
+            while (e < n) {
+                uint32_t r[PX::NW];
+#pragma unroll
+                for (int w = 0; w < PX::NW; w++) r[w] = rn[w];
+                const uint32_t m8 = m8n;
+                e += 32;
+                if (e < n) {
+                    const uint32_t en = __ldg(seg + 4 + e);
+                    m8n = en & 255u;
+                    load_group<PX::BPP, PX::NW>(address(en), rn);
+                }
+                group_pixels<PX, 0>(a, r, m8, hist_addr, one, nz);
+            }
+        }
+        __syncwarp();
+        const int road = item.x;
+        const bool split = (item.z & ITEM_SPLIT) != 0;
+        const int slot = a.road_slot ? a.road_slot[road] : road;
+        uint32_t *dst = a.hist + (size_t)slot * PX::HC * 256;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(FULL, nz, o);
+        if (!split) {
+            for (int i = lane; i < PX::HC * 64; i += 32) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(hist)[i];
+            if (lane == 0) a.nzero[slot] = nz;
+        } else {
+            for (int i = lane; i < PX::HC * 256; i += 32) {
+                const uint32_t v = hist[i];
+                if (v) atomicAdd(&dst[i], v);
+            }
+            if (lane == 0 && nz) atomicAdd(&a.nzero[slot], nz);
+        }
+        __syncwarp();
     }
 }
 
@@ -1152,6 +1161,43 @@ static int launch_fast(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
     return RS_OK;
 }
 
+
+// the two-kernel form: rasterize -> entry pool (zonal_kernel<PxEmit>), entries -> histograms (accum_kernel<PX>), then the fused
+// kernel over the items the pool could not hold (normally none: every CTA of that launch exits on its first queue read)
+template <class PX>
+static int launch_split(rs_ctx *ctx, ZonalArgs a, cudaStream_t st)
+{
+    {
+        using S = TeamSmem<0, false>;
+        const size_t smem = sizeof(S) * WARPS;
+        auto kern = zonal_kernel<PxEmit, false, false>;
+        RS_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        RS_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        kern<<<(unsigned)(ctx->sm_count * per_sm), WARPS * 32, smem, st>>>(a);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+    }
+    {
+        const size_t smem = (size_t)WARPS * PX::HC * 1024;
+        auto kern = accum_kernel<PX>;
+        RS_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        RS_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        kern<<<(unsigned)(ctx->sm_count * per_sm), WARPS * 32, smem, st>>>(a);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+    }
+    // overflow items: the fused kernel, its queue = ov_items[0 .. *ov_count)
+    ZonalArgs f = a;
+    f.items = a.ov_items;
+    f.n_items = a.ov_count;              // {count, 0}: counters [4], [5]
+    f.work_counter = a.work_counter + 7;
+    return launch_fast<PX, true>(ctx, f, st);
+}
+
 template <class PX>
 static int launch_one(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
 {
@@ -1159,6 +1205,8 @@ static int launch_one(rs_ctx *ctx, const ZonalArgs &args, cudaStream_t st)
     else {
         if constexpr (PX::BPP == 3)          // tiles read in place from host memory: fewer sectors over the host link
             if (args.fast && args.sparse) return launch_fast<PX, true, true>(ctx, args, st);
+        if constexpr (PX::BPP != 8)          // (uint16 x 4 keeps the fused kernel: its groups do not fit accum_kernel's 40 registers)
+            if (args.pool && args.fast && !args.sparse) return launch_split<PX>(ctx, args, st);
         return args.fast ? launch_fast<PX, true>(ctx, args, st) : launch_fast<PX, false>(ctx, args, st);
     }
 }
@@ -1250,6 +1298,8 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     }
 
     if (a.minzero && prm->hist_mode != RS_HIST_BANDS) return RS_ERR_INVALID_ARG;
+    if (!masks && wide_eligible(tiles, prm, !a.sparse))
+        return launch_zonal_wide(ctx, roads, tiles, pairs, prm, hist, n_allzero, window_mode, tile_lo, tile_hi, accumulate, st);
     // one context = one set of scratch buffers: a launch on another stream than the previous one waits for it
     if (ctx->scratch_used && ctx->scratch_stream != st) RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
     if (a.minzero && tiles->height > ROWS_ITEM && pairs->n_pairs > 0) {
@@ -1257,15 +1307,43 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
         RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->pair_zero.p, 0, (size_t)pairs->n_pairs * 4 * sizeof(uint32_t), st));
         a.pair_zero = (uint32_t *)ctx->pair_zero.p;
     }
-    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 3 * sizeof(int), st));      // work counter, big items, small items
-    if (pairs->n_pairs > 0) {
-        pair_geom_kernel<<<(pairs->n_pairs + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, pairs->pair_tile, roads->road_bbox, tiles->gt,
-                                                                       roads->n_roads, pairs->n_pairs, tiles->width, tiles->height,
-                                                                       window_mode, prm ? prm->border_px : 0, tile_lo, tile_hi,
-                                                                       (PairGeom *)ctx->pgeom.p, ctx->d_status);
-        ctx->launches++;
-        RS_CUDA_OK(ctx, cudaGetLastError());
+    // two-kernel form (rasterize -> entry pool -> accumulate): resident tiles with 64/128-bit group loads, no per-pair
+    // by-products.  RS_ZONAL_SPLIT=0 keeps the fused kernel (the parity twin).
+    {
+        const char *env = getenv("RS_ZONAL_SPLIT");
+        const bool want = env ? atoi(env) != 0 : true;
+        if (want && !masks && a.fast && !a.sparse && !a.minzero && !accumulate && pairs->n_pairs > 0) {
+            size_t free_b = 0, total_b = 0;
+            RS_CUDA_OK(ctx, cudaMemGetInfo(&free_b, &total_b));
+            size_t units = (size_t)pairs->n_pairs * 96 + (size_t)ctx->sm_count * 32 * CHUNK_UNITS;       // ~1.5 KiB per pair
+            const size_t have = ctx->pool.cap / 16;
+            const char *forced = getenv("RS_ZONAL_POOL_UNITS");        // tests: a pool too small for the work (overflow path)
+            bool ok = true;
+            if (forced) units = (size_t)atoll(forced);
+            else {
+                if (units > have) {
+                    const size_t afford = (free_b / 4 + ctx->pool.cap) / 16;
+                    if (units > afford) units = afford;
+                }
+                if (units < have) units = have;
+                ok = units >= (size_t)ctx->sm_count * 8 * CHUNK_UNITS;
+            }
+            if (units > 0xfffffff0u) units = 0xfffffff0u;
+            if (ok) {
+                if (units > have && (rc = ensure(ctx, ctx->pool, units * 16))) return rc;
+                if ((rc = ensure(ctx, ctx->heads, cap * sizeof(uint32_t)))) return rc;
+                if ((rc = ensure(ctx, ctx->ov_items, cap * sizeof(int4)))) return rc;
+                a.pool = (uint32_t *)ctx->pool.p;
+                a.pool_units = (uint32_t)units;
+                a.pool_cursor = (uint32_t *)(ctx->d_counters + 3);
+                a.heads = (uint32_t *)ctx->heads.p;
+                a.ov_items = (int4 *)ctx->ov_items.p;
+                a.ov_count = ctx->d_counters + 4;
+            }
+        }
     }
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));      // work counter, big items, small items, pool cursor, ...
+    if ((rc = launch_pair_geom(ctx, roads, tiles, pairs, window_mode, prm ? prm->border_px : 0, tile_lo, tile_hi, st))) return rc;
     prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
                                                                     a.road_slot, masks ? nullptr : hist, n_allzero, a.minzero, HC,
                                                                     (int4 *)ctx->items.p, ctx->d_counters + 1, (int)cap, tiles->height > ROWS_ITEM,

@@ -694,3 +694,121 @@ def test_pin_host_makes_numpy_tiles_readable_in_place(eng):
         eng.unpin_host(tb.pixels)
     with pytest.raises(Exception, match="RS_ERR_NOT_PINNED"):
         eng.zonal_stats_host(rr.roads, tb, rr.pairs, mapped=True)
+
+
+@pytest.mark.parametrize("mode", ["bands", "class_score"])
+def test_two_kernel_form_equals_fused_kernel_and_oracle(eng, mode, monkeypatch):
+    """rasterize -> entry pool -> accumulate (RS_ZONAL_SPLIT=1, the default for resident tiles) against the fused kernel
+    (RS_ZONAL_SPLIT=0) and the C oracle: bit-identical histograms, also for roads split over several work items."""
+    import torch
+    g = synth.Grid(16, 16)
+    rr = synth.ribbon_roads(g, 400, seed=17, max_vertices=300)
+    ch, kind = (3, 0) if mode == "bands" else (2, 2)
+    gt = g.transforms()
+    dt = eng.synth_tiles_dev(g.keys(), 256, 256, ch, kind=kind, gt=gt)
+    dr, dp = eng.upload_roads(rr.roads), eng.upload_pairs(rr.pairs)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("RS_ZONAL_SPLIT", flag)
+        l0 = eng.launch_count
+        h, z = eng.zonal_hist_dev(dr, dt, dp, hist_mode=mode)
+        torch.cuda.synchronize()
+        out[flag] = (h.cpu().numpy().view(np.uint32), z.cpu().numpy().view(np.uint32), eng.launch_count - l0)
+    assert out["1"][2] == out["0"][2] + 2                 # emit + accumulate + (empty) fused overflow pass
+    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+    oh, onz = cport.zonal_accumulate(rr.roads.xy, rr.roads.ring_off, rr.roads.road_ring_off, rr.pairs.road_pair_off,
+                                     rr.pairs.pair_tile, dt.pixels.cpu().numpy(), gt, joint=(mode == "class_score"))
+    assert np.array_equal(out["1"][0].astype(np.uint64), oh) and np.array_equal(out["1"][1].astype(np.uint64), onz)
+    assert (np.diff(rr.pairs.road_pair_off) > 8).any()    # some roads span several work items (atomic merge path)
+
+
+def test_two_kernel_form_pool_overflow_falls_back_to_the_fused_kernel(eng, monkeypatch):
+    """a pool that holds a fraction of the entries: the items that do not fit are redone by the fused kernel, same result"""
+    import torch
+    g = synth.Grid(12, 12)
+    rr = synth.ribbon_roads(g, 300, seed=29)
+    gt = g.transforms()
+    dt = eng.synth_tiles_dev(g.keys(), 256, 256, 3, kind=0, gt=gt)
+    dr, dp = eng.upload_roads(rr.roads), eng.upload_pairs(rr.pairs)
+    monkeypatch.setenv("RS_ZONAL_SPLIT", "0")
+    h0, z0 = eng.zonal_hist_dev(dr, dt, dp)
+    monkeypatch.setenv("RS_ZONAL_SPLIT", "1")
+    for units in ("0", "4096", "40960"):                  # nothing fits / one team's chunk / ten chunks
+        monkeypatch.setenv("RS_ZONAL_POOL_UNITS", units)
+        h1, z1 = eng.zonal_hist_dev(dr, dt, dp)
+        torch.cuda.synchronize()
+        assert torch.equal(h0, h1) and torch.equal(z0, z1), units
+
+
+# ------------------------------------------------------------------------------------------
+# wide-window kernel (rs_wide.cu): tiles of 512 .. 2048 px, lane-private histograms, TMA chunk pipeline
+# ------------------------------------------------------------------------------------------
+def _wide_case(size, seed, n_poly=7):
+    g = synth.Grid(2, 3, size=size)
+    rng = np.random.default_rng(seed)
+    X0, Y1 = g.origin
+    res = g.res
+    geoms = []
+    for i in range(n_poly):
+        n = [40, 700, 3100, 260, 5200, 129, 1500][i % 7]
+        ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+        rad = g.span * (0.25 + 0.3 * rng.random()) * (1 + 0.2 * np.sin(ang * (5 + i)) + 0.03 * rng.random(n))
+        c = np.array([X0 + g.span * (0.3 + 1.4 * rng.random()), Y1 - g.span * (0.3 + 2.4 * rng.random())])
+        ext = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        rings = [np.concatenate([ext, ext[:1]])]
+        for hq in range(i % 5):
+            hc = c + g.span * 0.1 * np.array([np.cos(hq * 1.7), np.sin(hq * 1.7)])
+            hr = g.span * 0.03
+            rings.append(ring((hc[0] - hr, hc[1] - hr), (hc[0] - hr, hc[1] + hr), (hc[0] + hr, hc[1] + hr), (hc[0] + hr, hc[1] - hr)))
+        geoms.append(rings)
+    # rectangles on the half-pixel lattice: horizontal edges exactly on scanlines (GDAL's separate burn), vertical on centres
+    for k in range(3):
+        x0, y0 = X0 + res * (40.5 + 90 * k), Y1 - res * (30.5 + 200 * k)
+        geoms.append([ring((x0, y0), (x0 + res * (size * 0.9), y0), (x0 + res * (size * 0.9), y0 - res * 77.0), (x0, y0 - res * 77.0))])
+        geoms.append([ring((x0, y0 - res * 100), (x0, y0 - res * 160), (x0 + res * 333.0, y0 - res * 160), (x0 + res * 333.0, y0 - res * 100))])
+    # a comb of 40 small holes: more rings than the kernel keeps in shared memory
+    cx, cy = X0 + g.span * 1.0, Y1 - g.span * 1.5
+    comb = [ring((cx - g.span * 0.45, cy - g.span * 0.2), (cx + g.span * 0.45, cy - g.span * 0.2), (cx + g.span * 0.45, cy + g.span * 0.2),
+                 (cx - g.span * 0.45, cy + g.span * 0.2))]
+    for k in range(40):
+        hx = cx - g.span * 0.42 + g.span * 0.021 * k
+        comb.append(ring((hx, cy - g.span * 0.1), (hx, cy + g.span * 0.1), (hx + g.span * 0.01, cy + g.span * 0.1), (hx + g.span * 0.01, cy - g.span * 0.1)))
+    geoms.append(comb)
+    geoms.append([ring((X0 - 10 * g.span, Y1 + 9 * g.span), (X0 - 9 * g.span, Y1 + 9 * g.span), (X0 - 9 * g.span, Y1 + 10 * g.span))])   # far away
+    return g, RoadSet.from_geometries(geoms)
+
+
+@pytest.mark.parametrize("size,channels", [(512, 3), (1024, 3), (1024, 1), (1024, 2), (2048, 3)])
+def test_wide_kernel_matches_oracle_and_fused_kernel(eng, size, channels, monkeypatch):
+    g, roads = _wide_case(size, seed=size + channels)
+    tiles = synth.host_tiles(g, channels)
+    gt = g.transforms()
+    tb = TileBatch.from_arrays(tiles, gt)
+    pairs = pairs_by_bbox(roads, tb)
+    l0 = eng.launch_count
+    h, z = eng.zonal_hist_host(roads, tb, pairs)
+    n_wide = eng.launch_count - l0
+    oh, onz = oracle_hist(roads, pairs, tiles, gt)
+    assert np.array_equal(h.astype(np.uint64), oh) and np.array_equal(z.astype(np.uint64), onz)
+    assert oh[:, 0].sum() > 100000 and (oh[-1] == 0).all()
+    monkeypatch.setenv("RS_ZONAL_WIDE", "0")
+    l0 = eng.launch_count
+    hf, zf = eng.zonal_hist_host(roads, tb, pairs)
+    assert eng.launch_count - l0 != n_wide                 # the two calls really took different kernels
+    assert np.array_equal(h, hf) and np.array_equal(z, zf)
+
+
+def test_wide_kernel_window_modes_and_slots(eng, monkeypatch):
+    """full / boundless windows, a border, and a road -> row map through both kernels"""
+    g, roads = _wide_case(1024, seed=3, n_poly=4)
+    tiles = synth.host_tiles(g, 3)
+    tb = TileBatch.from_arrays(tiles, g.transforms())
+    pairs = pairs_by_bbox(roads, tb)
+    slot = np.random.default_rng(0).permutation(roads.n_roads + 5)[:roads.n_roads].astype(np.int32)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("RS_ZONAL_WIDE", flag)
+        res[flag] = [eng.zonal_hist_host(roads, tb, pairs, window=w, border_px=b, road_slot=s_, n_slots=None if s_ is None else roads.n_roads + 5)
+                     for w, b, s_ in (("full", 0, None), ("boundless", 0, None), ("crop", 13, None), ("crop", 0, slot))]
+    for (h1, z1), (h0, z0) in zip(res["1"], res["0"]):
+        assert np.array_equal(h1, h0) and np.array_equal(z1, z0) and h1.sum() > 0
