@@ -46,7 +46,7 @@ enum rs_status {
     RS_ERR_CAPACITY = -3,      /* reserved (the bit-mask fill has no per-scanline crossing limit)  */
     RS_ERR_ROTATED = -4,       /* a tile transform has b != 0 or d != 0                           */
     RS_ERR_NO_DEVICE = -5,     /* no CUDA device / device is not sm_100                           */
-    RS_ERR_UNSUPPORTED = -6,   /* width > 2048, channels not in 1..4, dtype/channels combination  */
+    RS_ERR_UNSUPPORTED = -6,   /* a (road, raster) window wider than 2048 px, channels not in 1..4, dtype/channels combination */
     RS_ERR_NOT_PINNED = -7,    /* rs_zonal_stats_mapped_host: tiles->pixels is not page-locked    */
     RS_ERR_NO_NCCL = -8,       /* rs_comm_*: libnccl.so.2 could not be loaded                     */
     RS_ERR_NCCL = -9           /* an NCCL call failed                                             */
@@ -163,7 +163,8 @@ int rs_road_bbox_dev(rs_ctx *ctx, const rs_roads *roads, double *road_bbox_out, 
  * n_allzero uint32[n_slots]: in-mask pixels whose bands are all 0
  * Every road's slot is written exactly once (zeros if the road has no pixels): outputs need
  * no clearing (road_slot, when given, must be injective).  Integer outputs are bit-exact and independent of
- * scheduling.  Limits: tile width <= 2048 pixels, any height; 64/128-bit pixel loads need width % 8 == 0 and a
+ * scheduling.  Limits: the window of a pair (bounds of the road clipped to the raster) at most 2048 pixels wide, any height,
+ * any raster size; 64/128-bit pixel loads need width % 8 == 0 and a
  * 16-byte aligned pixel base (other shapes take a byte-wise path).
  */
 int rs_zonal_hist_dev(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
@@ -225,6 +226,20 @@ int rs_finalize_stats_host(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_
 int rs_zonal_stats_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                         const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
                         int32_t n_pct, double *stats, uint32_t *hist, uint32_t *n_allzero);
+
+/*
+ * Zonal statistics of polygons over ONE float32 raster: rasterstats.zonal_stats(labels, dem_array, affine=affine,
+ * stats=['min','max','mean','median','std'], nodata=-9999)  (scripts/functions/fct_rasters.py:147-163, the DEM call).
+ * raster float[height][width] (host), gt = its affine; pixels that are NaN or (use_nodata != 0) equal to nodata are masked, as are
+ * the parts of a feature's window that lie off the raster (rasterstats' boundless read).  stats double[n_features][RS_NSTAT +
+ * n_pct], the columns of rs_finalize_stats_*; features without a valid pixel get count 0 and NaN elsewhere.  count / min / max /
+ * median are exact (the median of an even count is the float32 mean of the two middle values, as np.median gives); sum, mean and
+ * std are binary64 reductions in a fixed order (rasterstats reduces in float32: ~1e-7 relative apart).  ddof 0 = rasterstats.
+ * Any raster size; a feature's window may be at most 2048 pixels wide; at most 2^31 - 1 valid pixels in total.
+ */
+int rs_zonal_stats_f32_host(rs_ctx *ctx, const rs_roads *features, const float *raster, int32_t height, int32_t width,
+                            const double *gt, int32_t use_nodata, double nodata, int32_t ddof, const double *percentiles,
+                            int32_t n_pct, double *stats);
 
 /*
  * Multi-GPU merge (one process per GPU, tiles sharded over the GPUs of a box).  The reference is single-process: a road's

@@ -736,6 +736,63 @@ static int stage_polys(rs_ctx *ctx, const rs_roads *r, int base, rs_roads &d)
     return RS_OK;
 }
 
+int rs_zonal_stats_f32_host(rs_ctx *ctx, const rs_roads *features, const float *raster, int32_t height, int32_t width, const double *gt,
+                            int32_t use_nodata, double nodata, int32_t ddof, const double *percentiles, int32_t n_pct, double *stats)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!features || height < 1 || width < 1 || !gt || ddof < 0 || n_pct < 0 || n_pct > 16 || (n_pct > 0 && !percentiles))
+        return RS_ERR_INVALID_ARG;
+    const int n = features->n_roads;
+    if (n == 0) return RS_OK;
+    if (!raster || !stats) return RS_ERR_INVALID_ARG;
+    cudaStream_t st = ctx->host_stream;
+    rs_roads dr;
+    if ((rc = stage_polys(ctx, features, 0, dr))) return rc;
+    const size_t px = (size_t)height * width;
+    if ((rc = up(ctx, ctx->stage[7], raster, sizeof(float) * px))) return rc;
+    if ((rc = up(ctx, ctx->stage[5], gt, sizeof(double) * 6))) return rc;
+    // every feature against the one raster: pairs = identity
+    int32_t *h = (int32_t *)malloc(sizeof(int32_t) * (2 * (size_t)n + 1));
+    if (!h) return RS_ERR_INVALID_ARG;
+    for (int i = 0; i <= n; i++) h[i] = i;
+    for (int i = 0; i < n; i++) h[n + 1 + i] = 0;
+    rc = up(ctx, ctx->stage[4], h, sizeof(int32_t) * (2 * (size_t)n + 1));
+    if (!rc) RS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    free(h);
+    if (rc) return rc;
+    rs_tiles dt{ctx->stage[7].p, (const double *)ctx->stage[5].p, 1, height, width, 1, RS_U8};
+    rs_pairs dp{(const int32_t *)ctx->stage[4].p, (const int32_t *)ctx->stage[4].p + n + 1, n};
+    const size_t NS = (size_t)RS_NSTAT + n_pct;
+    if ((rc = ensure(ctx, ctx->stage[8], sizeof(uint32_t) * 2 * (size_t)n))) return rc;                    // counts | cursors
+    if ((rc = ensure(ctx, ctx->stage[9], sizeof(unsigned long long) * ((size_t)n + 1)))) return rc;        // offsets
+    if ((rc = ensure(ctx, ctx->stage[12], sizeof(double) * NS * n))) return rc;
+    if ((rc = up(ctx, ctx->stage[13], percentiles, sizeof(double) * (size_t)n_pct))) return rc;
+    uint32_t *counts = (uint32_t *)ctx->stage[8].p, *cursor = counts + n;
+    unsigned long long *off = (unsigned long long *)ctx->stage[9].p;
+    RS_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * 2 * (size_t)n, st));
+    // rasterstats reads a boundless window and masks what lies off the raster: same pixels as the window clipped to the raster
+    if ((rc = launch_zonal_f32(ctx, &dr, &dt, &dp, RS_WINDOW_BOUNDLESS, nodata, use_nodata, counts, cursor, off, nullptr, 0, st))) return rc;
+    if ((rc = launch_fstats_offsets(ctx, counts, n, off, st))) return rc;
+    unsigned long long total = 0;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(&total, off + n, sizeof(total), cudaMemcpyDeviceToHost, st));
+    if ((rc = finish(ctx))) return rc;
+    if (total > 0x7fffffffull) return RS_ERR_UNSUPPORTED;
+    if ((rc = ensure(ctx, ctx->stage[10], sizeof(float) * (size_t)total))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], sizeof(float) * (size_t)total))) return rc;
+    if (total > 0) {
+        if ((rc = launch_zonal_f32(ctx, &dr, &dt, &dp, RS_WINDOW_BOUNDLESS, nodata, use_nodata, counts, cursor, off,
+                                   (float *)ctx->stage[10].p, 1, st)))
+            return rc;
+        if ((rc = launch_fstats_sort(ctx, (const float *)ctx->stage[10].p, (float *)ctx->stage[11].p, (long long)total, n, off, st))) return rc;
+    }
+    if ((rc = launch_fstats(ctx, (const float *)ctx->stage[11].p, off, n, ddof, (const double *)ctx->stage[13].p, n_pct,
+                            (double *)ctx->stage[12].p, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[12].p, sizeof(double) * NS * n, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
 int rs_within_host(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *within)
 {
     int rc = bind(ctx);

@@ -65,6 +65,14 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
 int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
                        int tile_lo, int tile_hi, int accumulate, cudaStream_t st);
+int launch_zonal_f32(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, int window_mode, double nodata,
+                     int has_nodata, uint32_t *count, uint32_t *cursor, const unsigned long long *offset, float *values, int write,
+                     cudaStream_t st);
+int launch_fstats_offsets(rs_ctx *ctx, const uint32_t *counts, int n, unsigned long long *offsets, cudaStream_t st);
+int launch_fstats_sort(rs_ctx *ctx, const float *values, float *sorted, long long total, int n, const unsigned long long *offsets,
+                       cudaStream_t st);
+int launch_fstats(rs_ctx *ctx, const float *sorted, const unsigned long long *offsets, int n, int ddof, const double *pct_dev, int n_pct,
+                  double *stats, cudaStream_t st);
 int launch_road_bbox(rs_ctx *ctx, const rs_roads *roads, double *out, cudaStream_t st);
 // wide-window form (rs_wide.cu): tiles of 512 .. 2048 pixels under wide polygons with long edge lists
 bool wide_eligible(const rs_tiles *tiles, const rs_zonal_params *prm, bool resident);

@@ -13,6 +13,7 @@ namespace rs {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int ROWS_ITEM = 256;  // zonal_kernel: a window taller than this is split by rows over several items
+constexpr int RS_MAX_WINDOW_W = 2048;   // widest window of one (road, raster) pair; the raster itself may be wider
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA bulk copy (global -> shared)
@@ -70,6 +71,7 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     const double sa = gt[0], sb = gt[1], sc = gt[2], sd = gt[3], se = gt[4], sf = gt[5];
     if (sb != 0.0 || sd != 0.0 || sa == 0.0 || se == 0.0) return RS_ERR_ROTATED;
     if (window_mode == RS_WINDOW_FULL) {
+        if (W > RS_MAX_WINDOW_W) return RS_ERR_UNSUPPORTED;
         g.col_off = 0; g.row_off = 0; g.w = W; g.h = H;
         g.xshift = 0; g.yshift = 0; g.wu = W;
         g.inv0 = __ddiv_rn(-sc, sa); g.inv1 = __ddiv_rn(1.0, sa);
@@ -105,6 +107,7 @@ __device__ __forceinline__ int pair_geometry(const double *__restrict__ gt, cons
     const int ic0 = (int)fmax(c0, 0.0), ic1 = (int)fmin(c1, (double)W);
     g.col_off = ic0; g.row_off = ir0; g.w = ic1 - ic0; g.h = ir1 - ir0;
     if (g.w <= 0 || g.h <= 0) return 0;
+    if (g.w > RS_MAX_WINDOW_W) return RS_ERR_UNSUPPORTED;      // a row's mask must fit the team's shared memory
     g.xshift = 0; g.yshift = 0; g.wu = g.w;
     double xo = (double)ic0, yo = (double)ir0;
     if (window_mode == RS_WINDOW_BOUNDLESS) {       // rasterstats: the window keeps its unclipped origin

@@ -53,7 +53,6 @@ constexpr int RCMAX = 128;      // rows per mask chunk
 constexpr int ENTCAP = 448;     // 8-pixel group entries queued per team
 constexpr int NCHUNK = 32;      // culling chunks per road
 constexpr int RINGCAP = 16;     // ring starts kept in shared memory
-constexpr int MAX_WIDTH = 2048; // one row's groups (W / 8) must fit the queue next to a partial round
 constexpr int ITEM_SPLIT = 1 << 30;           // item flag: the road has several items (accumulate with atomics)
 // two-kernel form (emit_kernel = zonal_kernel<PxEmit> -> accum_kernel): the rasterizer writes its 8-pixel-group entries to a
 // pool in HBM instead of consuming them; pool addresses are in UNITS of 16 bytes
@@ -69,6 +68,15 @@ constexpr uint32_t ROW_REWALK = 0xffffffffu;   // rowmap marker: recount this ro
 // ---------------------------------------------------------------------------------------------
 // kernel arguments
 // ---------------------------------------------------------------------------------------------
+struct F32Args {
+    double nodata;
+    int has_nodata;
+    uint32_t *count;                      // per feature: valid in-mask pixels (count pass)
+    uint32_t *cursor;                     // per feature: values written so far (write pass)
+    const unsigned long long *offset;     // per feature: start of its slice of `values`
+    float *values;
+};
+
 struct ZonalArgs {
     const double2 *xy;
     const int *ring_off;
@@ -103,6 +111,7 @@ struct ZonalArgs {
     uint32_t *heads;          // per item-queue index: last segment + 1 of the item (0 = no entries, HEAD_OVERFLOW)
     int4 *ov_items;           // items the pool could not hold ...
     int *ov_count;            // ... and their number
+    F32Args f;                // PxF32
 };
 
 // team-local allocation state of the emitting rasterizer (warp-uniform registers)
@@ -188,7 +197,7 @@ __device__ __forceinline__ uint32_t bin_off(uint32_t w, int k)      // k is a co
 template <int C_>
 struct PxBandsU8 {
     static constexpr int C = C_, HC = C_, BPP = C_, NW = 2 * C_;
-    static constexpr bool MASK = false, EMIT = false;
+    static constexpr bool MASK = false, EMIT = false, FLT = false;
     // pixel I of the group: hist (shared-memory byte address of the team histogram) gets one increment per band
     // `on` is the pixel's mask bit (0 / 1), also the addend of its increments
     template <int I>
@@ -226,7 +235,7 @@ struct PxBandsU8 {
 
 struct PxClassScore {
     static constexpr int C = 2, HC = 3, BPP = 2, NW = 4;
-    static constexpr bool MASK = false, EMIT = false;
+    static constexpr bool MASK = false, EMIT = false, FLT = false;
     __device__ static __forceinline__ void one(uint32_t cls, uint32_t score, uint32_t *hist, uint32_t &nz)
     {
         nz += ((cls | score) == 0);
@@ -252,7 +261,7 @@ struct PxClassScore {
 template <bool F32>
 struct PxU16x4Rescale {
     static constexpr int C = 4, HC = 4, BPP = 8, NW = 16;
-    static constexpr bool MASK = false, EMIT = false;
+    static constexpr bool MASK = false, EMIT = false, FLT = false;
     __device__ static __forceinline__ uint32_t scale(const ZonalArgs &a, uint32_t s, int c)
     {
         if (F32) {
@@ -292,11 +301,18 @@ struct PxU16x4Rescale {
 
 struct PxMask {
     static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
-    static constexpr bool MASK = true, EMIT = false;
+    static constexpr bool MASK = true, EMIT = false, FLT = false;
 };
 struct PxEmit {                     // the rasterizer of the two-kernel form: entries go to the pool
     static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
-    static constexpr bool MASK = true, EMIT = true;
+    static constexpr bool MASK = true, EMIT = true, FLT = false;
+};
+// float32 single-band rasters (rasterstats.zonal_stats over a DEM, fct_rasters.py:147-163): the in-mask pixels that are neither
+// NaN nor nodata are counted per feature (WRITE = false) or written to the feature's slice of a compact value array
+template <bool WRITE_>
+struct PxF32 {
+    static constexpr int C = 1, HC = 0, BPP = 4, NW = 8;
+    static constexpr bool MASK = true, EMIT = false, FLT = true, WRITE = WRITE_;
 };
 
 // 8 pixels x BPP bytes from a (8*BPP)-byte aligned address into NW words
@@ -396,7 +412,7 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
     }
     if (nrings > 1 && nrings <= RINGCAP)
         for (int k = lane; k <= nrings; k += 32) s.ring_start[k] = a.ring_off[g0 + k] - v0;
-    uint32_t nz = 0, mz = 0;
+    uint32_t nz = 0, mz = 0, fcnt = 0;
     uint32_t zprev[PX::MASK ? 1 : PX::HC];          // hist[band][0] after the previous pair (a.minzero only)
 #pragma unroll
     for (int c = 0; c < (PX::MASK ? 1 : PX::HC); c++) zprev[c] = 0;
@@ -672,6 +688,50 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                         es.prev = es.pos + 1u;
                         es.pos += units;
                     }
+                } else if constexpr (PX::FLT) {
+                    const float *fpx = (const float *)a.pixels;
+                    for (int base = 0; base < n; base += 32) {
+                        const int e = base + lane;
+                        float v[8];
+                        uint32_t sel = 0;
+                        if (e < n) {
+                            const uint32_t en = s.u.entries[e];
+                            const int x8 = cbcol + 8 * (int)((en >> 8) & 0xfffu);
+                            const int yabs = g.row_off + r0 + (int)(en >> 20);
+                            const float *gp = fpx + tile_pix + (size_t)yabs * a.W + x8;
+                            if constexpr (FAST) {
+                                const float4 q0 = __ldg(reinterpret_cast<const float4 *>(gp)), q1 = __ldg(reinterpret_cast<const float4 *>(gp) + 1);
+                                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) v[i] = (en & (1u << i)) ? __ldg(gp + i) : 0.0f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                // rasterstats: masked where array == nodata or NaN (main.py: isnodata | isnan)
+                                const bool ok = (en & (1u << i)) && (v[i] == v[i]) && !(a.f.has_nodata && (double)v[i] == a.f.nodata);
+                                sel |= ok ? (1u << i) : 0u;
+                            }
+                        }
+                        const int c = __popc(sel);
+                        if constexpr (!PX::WRITE) {
+                            fcnt += (uint32_t)c;
+                        } else {
+                            int incl = c;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int u = __shfl_up_sync(FULL, incl, o);
+                                if (lane >= o) incl += u;
+                            }
+                            uint32_t at = 0;
+                            if (lane == 31 && incl > 0) at = atomicAdd(&a.f.cursor[road], (uint32_t)incl);
+                            at = __shfl_sync(FULL, at, 31);
+                            float *dst = a.f.values + a.f.offset[road] + at + (uint32_t)(incl - c);
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                if (sel & (1u << i)) *dst++ = v[i];
+                        }
+                    }
                 } else if constexpr (PX::MASK) {
                     for (int e = lane; e < n; e += 32) {
                         const uint32_t en = s.u.entries[e];
@@ -845,6 +905,13 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
         }
     }
 
+    if constexpr (PX::FLT) {
+        if constexpr (!PX::WRITE) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fcnt += __shfl_xor_sync(FULL, fcnt, o);
+            if (lane == 0 && fcnt) atomicAdd(&a.f.count[road], fcnt);
+        }
+    }
     if constexpr (PX::EMIT) {
         if (lane == 0) {
             a.heads[qidx] = es.overflow ? HEAD_OVERFLOW : es.prev;
@@ -1221,9 +1288,29 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
 // tile_lo / tile_hi: only pairs whose tile index lies in [tile_lo, tile_hi) are processed (tiles->pixels is then indexed with
 // the global tile index, so a caller that holds one chunk passes chunk_base - tile_lo * tile_bytes);
 // accumulate: add into hist / n_allzero (zeroed by the caller) instead of writing every row once
+static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                       const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
+                       int tile_lo, int tile_hi, int accumulate, const F32Args *f32, int f32_write, cudaStream_t st);
+
 int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
                        int tile_lo, int tile_hi, int accumulate, cudaStream_t st)
+{
+    return launch_impl(ctx, roads, tiles, pairs, prm, hist, n_allzero, masks, window_mode, tile_lo, tile_hi, accumulate, nullptr, 0, st);
+}
+
+// float32 single-band raster: count (write == 0) or write (write == 1) the valid in-mask pixels of every feature
+int launch_zonal_f32(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, int window_mode, double nodata,
+                     int has_nodata, uint32_t *count, uint32_t *cursor, const unsigned long long *offset, float *values, int write,
+                     cudaStream_t st)
+{
+    F32Args f{nodata, has_nodata, count, cursor, offset, values};
+    return launch_impl(ctx, roads, tiles, pairs, nullptr, nullptr, nullptr, nullptr, window_mode, 0, 0x7fffffff, 0, &f, write, st);
+}
+
+static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                       const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
+                       int tile_lo, int tile_hi, int accumulate, const F32Args *f32, int f32_write, cudaStream_t st)
 {
     if (!roads || !tiles || !pairs) return RS_ERR_INVALID_ARG;
     if (roads->n_roads < 0 || roads->n_verts < 0 || tiles->n_tiles < 0 || pairs->n_pairs < 0) return RS_ERR_INVALID_ARG;
@@ -1232,7 +1319,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
         return RS_ERR_INVALID_ARG;
     if (pairs->n_pairs > 0 && (!pairs->pair_tile || !tiles->gt)) return RS_ERR_INVALID_ARG;
     if (((uintptr_t)roads->xy & 15u) != 0) return RS_ERR_INVALID_ARG;      // TMA bulk source alignment
-    if (tiles->width > MAX_WIDTH || tiles->width < 1 || tiles->height < 1) return RS_ERR_UNSUPPORTED;
+    if (tiles->width < 1 || tiles->height < 1) return RS_ERR_UNSUPPORTED;      // (windows wider than 2048 px: pair_geometry)
     if (window_mode != RS_WINDOW_CROP && window_mode != RS_WINDOW_FULL && window_mode != RS_WINDOW_BOUNDLESS) return RS_ERR_INVALID_ARG;
     if (prm && (prm->border_px < 0 || prm->border_px > 4096)) return RS_ERR_INVALID_ARG;
 
@@ -1270,7 +1357,8 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
         for (int c = 0; c < 4; c++) { a.sk[c] = prm->scale_k[c]; a.so[c] = prm->scale_off[c]; }
     a.one = 1u;
     a.fast = (tiles->width % 8 == 0) && (((uintptr_t)tiles->pixels & 15u) == 0);
-    if (tiles->pixels) {
+    if (f32) a.f = *f32;
+    if (tiles->pixels && !f32) {
         // where do the tiles live?  (the first tile this launch reads: a streamed chunk is addressed through a shifted base)
         const size_t tile_bytes = (size_t)tiles->height * tiles->width * tiles->channels * (tiles->dtype == RS_U16 ? 2 : 1);
         cudaPointerAttributes attr;
@@ -1281,7 +1369,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     }
 
     int HC = 0;
-    if (!masks) {
+    if (!masks && !f32) {
         if (!prm || !hist || !n_allzero || (pairs->n_pairs > 0 && !tiles->pixels)) return RS_ERR_INVALID_ARG;
         if (prm->hist_mode == RS_HIST_CLASS_SCORE) {
             if (tiles->channels != 2 || tiles->dtype != RS_U8) return RS_ERR_UNSUPPORTED;
@@ -1298,7 +1386,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     }
 
     if (a.minzero && prm->hist_mode != RS_HIST_BANDS) return RS_ERR_INVALID_ARG;
-    if (!masks && wide_eligible(tiles, prm, !a.sparse))
+    if (!masks && !f32 && wide_eligible(tiles, prm, !a.sparse))
         return launch_zonal_wide(ctx, roads, tiles, pairs, prm, hist, n_allzero, window_mode, tile_lo, tile_hi, accumulate, st);
     // one context = one set of scratch buffers: a launch on another stream than the previous one waits for it
     if (ctx->scratch_used && ctx->scratch_stream != st) RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
@@ -1312,7 +1400,7 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     {
         const char *env = getenv("RS_ZONAL_SPLIT");
         const bool want = env ? atoi(env) != 0 : true;
-        if (want && !masks && a.fast && !a.sparse && !a.minzero && !accumulate && pairs->n_pairs > 0) {
+        if (want && !masks && !f32 && a.fast && !a.sparse && !a.minzero && !accumulate && pairs->n_pairs > 0) {
             size_t free_b = 0, total_b = 0;
             RS_CUDA_OK(ctx, cudaMemGetInfo(&free_b, &total_b));
             size_t units = (size_t)pairs->n_pairs * 96 + (size_t)ctx->sm_count * 32 * CHUNK_UNITS;       // ~1.5 KiB per pair
@@ -1345,13 +1433,16 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));      // work counter, big items, small items, pool cursor, ...
     if ((rc = launch_pair_geom(ctx, roads, tiles, pairs, window_mode, prm ? prm->border_px : 0, tile_lo, tile_hi, st))) return rc;
     prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
-                                                                    a.road_slot, masks ? nullptr : hist, n_allzero, a.minzero, HC,
+                                                                    a.road_slot, (masks || f32) ? nullptr : hist, n_allzero, a.minzero, HC,
                                                                     (int4 *)ctx->items.p, ctx->d_counters + 1, (int)cap, tiles->height > ROWS_ITEM,
                                                                     accumulate);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
 
-    if (masks) rc = launch_one<PxMask>(ctx, a, st);
+    if (f32)
+        rc = f32_write ? (a.fast ? launch_fast<PxF32<true>, true>(ctx, a, st) : launch_fast<PxF32<true>, false>(ctx, a, st))
+                       : (a.fast ? launch_fast<PxF32<false>, true>(ctx, a, st) : launch_fast<PxF32<false>, false>(ctx, a, st));
+    else if (masks) rc = launch_one<PxMask>(ctx, a, st);
     else if (prm->hist_mode == RS_HIST_CLASS_SCORE) rc = launch_one<PxClassScore>(ctx, a, st);
     else if (tiles->dtype == RS_U16)
         rc = prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);

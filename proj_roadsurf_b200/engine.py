@@ -194,6 +194,25 @@ class Engine:
         N.check(st, "rs_zonal_stats_host", self._ctx)
         return (stats, hist, nzero) if want_hist else stats
 
+    def zonal_stats_f32_host(self, features: RoadSet, raster: np.ndarray, affine, nodata: Optional[float] = None, ddof: int = 0,
+                             percentiles: Sequence[float] = ()) -> np.ndarray:
+        """Statistics of every feature over ONE float32 raster (H, W) (rs_zonal_stats_f32_host: rasterstats.zonal_stats over a
+        DEM, fct_rasters.py:147-163).  NaN and ``nodata`` pixels are masked.  Returns (n, RS_NSTAT + n_pct) float64."""
+        arr = np.ascontiguousarray(raster, np.float32)
+        assert arr.ndim == 2
+        pct = np.ascontiguousarray(percentiles, np.float64)
+        gt = np.ascontiguousarray(tuple(affine)[:6], np.float64)
+        xy = np.ascontiguousarray(features.xy, np.float64)
+        ro, rro = np.ascontiguousarray(features.ring_off, np.int32), np.ascontiguousarray(features.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(features.bbox, np.float64)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), features.n_roads, features.n_rings, features.n_verts)
+        out = np.zeros((features.n_roads, N.RS_NSTAT + len(pct)), np.float64)
+        st = self.lib.rs_zonal_stats_f32_host(self._ctx, C.byref(rd), _np_ptr(arr), arr.shape[0], arr.shape[1], _np_ptr(gt),
+                                              0 if nodata is None else 1, 0.0 if nodata is None else float(nodata), int(ddof),
+                                              _np_ptr(pct) if len(pct) else None, len(pct), _np_ptr(out))
+        N.check(st, "rs_zonal_stats_f32_host", self._ctx)
+        return out
+
     def pin_host(self, array: np.ndarray) -> np.ndarray:
         """Page-lock a numpy buffer in place (rs_host_register) so that zonal_stats_host reads it without a copy; call
         unpin_host before the array is freed.  Returns the array."""

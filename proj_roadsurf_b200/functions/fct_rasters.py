@@ -47,10 +47,11 @@ def rasterize(shapes, out_shape, fill=0, transform=IDENTITY, all_touched=False, 
 
 
 def zonal_stats(vectors, raster, affine=None, stats=None, band=1, nodata=None, layer=0, **kwargs) -> List[dict]:
-    """rasterstats-shaped zonal statistics of ``vectors`` over a uint8 raster array (H, W) or (H, W, C)
-    (``band`` is 1-based) with transform ``affine``.  Boundless window, pixels equal to ``nodata`` masked,
-    std with ddof 0, features without valid pixels -> count 0 and None for the other statistics.
-    Percentiles are requested as 'percentile_<q>'."""
+    """rasterstats-shaped zonal statistics of ``vectors`` over a raster array (H, W) or (H, W, C) (``band`` is 1-based) with
+    transform ``affine``.  Boundless window, pixels equal to ``nodata`` (and NaN) masked, std with ddof 0, features without
+    valid pixels -> count 0 and None for the other statistics.  Percentiles are requested as 'percentile_<q>'.
+    uint8 rasters go through the per-feature histograms; every other dtype is taken as float32, the way the reference's DEM
+    call reads its raster (fct_rasters.py:147-163: src.read(1) of swissALTI3D, nodata=-9999): per-feature compaction + sort."""
     if stats is None:
         stats = ["count", "min", "max", "mean"]
     if isinstance(stats, str):
@@ -58,8 +59,6 @@ def zonal_stats(vectors, raster, affine=None, stats=None, band=1, nodata=None, l
     arr = np.asarray(raster)
     if arr.ndim == 3:
         arr = arr[..., band - 1]
-    if arr.dtype != np.uint8:
-        raise TypeError("the GPU zonal statistics path takes 8-bit rasters")
     if affine is None:
         raise ValueError("affine is required for array rasters")
     pct = [float(s.split("_", 1)[1]) for s in stats if s.startswith("percentile_")]
@@ -71,6 +70,13 @@ def zonal_stats(vectors, raster, affine=None, stats=None, band=1, nodata=None, l
     n = roads.n_roads
     if n == 0:
         return []
+    if arr.dtype != np.uint8:
+        if arr.dtype.kind not in "fiu" or (arr.dtype.kind in "iu" and arr.dtype.itemsize > 2) or (arr.dtype.kind == "f" and arr.dtype.itemsize > 4):
+            raise TypeError("the GPU zonal statistics path takes uint8 rasters, or rasters that float32 represents exactly")
+        # rasterstats' Raster gives array inputs without nodata the value -999 (io.py, with a warning), as the oracle does
+        table = default_engine().zonal_stats_f32_host(roads, arr.astype(np.float32), affine, nodata=-999 if nodata is None else nodata,
+                                                      ddof=0, percentiles=pct)
+        return _rows_to_dicts(table, stats, pct, n)
     tb = TileBatch.from_arrays(arr[None, :, :, None], np.asarray(tuple(affine)[:6], np.float64)[None], nodata)
     pairs = PairList.from_pairs(n, np.arange(n), np.zeros(n, int))
     eng = default_engine()
@@ -78,6 +84,10 @@ def zonal_stats(vectors, raster, affine=None, stats=None, band=1, nodata=None, l
     if nodata is not None and 0 <= nodata <= 255 and float(nodata) == int(nodata):
         hist[:, :, int(nodata)] = 0           # masked where array == nodata
     table = eng.finalize_stats_host(hist, None, nodata_mode="raw", ddof=0, percentiles=pct)[:, 0, :]
+    return _rows_to_dicts(table, stats, pct, n)
+
+
+def _rows_to_dicts(table, stats, pct, n) -> List[dict]:
     out = []
     for r in range(n):
         row = table[r]

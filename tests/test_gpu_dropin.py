@@ -789,3 +789,50 @@ def test_overlay_area_hole_touching_its_shell():
     exp = np.array([ov.intersection_area(A[i], B[j]) for i, j in zip(ia, ib)])
     assert np.array_equal(got, exp), np.stack([ia, ib, got, exp], 1)[got != exp]
     assert area_a.tolist() == [ov.polygon_area(a) for a in A] == [92.0, 92.0, 84.5, 32.0]
+
+
+def test_zonal_stats_float_dem_like_rasterstats(mods):
+    """the reference's live zonal_stats call (fct_rasters.py:147-163): polygons over a float32 DEM with nodata=-9999, on a raster
+    wider than 2048 px, with NaN pixels, features partly and wholly off the raster.  count / min / max / median exact, mean / std
+    within the north star's 1e-6 (the oracle reduces in binary64 like the kernel; rasterstats itself in float32)."""
+    fr = mods[2]
+    rng = np.random.default_rng(12)
+    Hh, Ww = 300, 3000
+    yy, xx = np.mgrid[0:Hh, 0:Ww]
+    dem = (450.0 + 0.05 * xx + 0.3 * yy + 3.0 * np.sin(xx / 37.0) + rng.normal(0, 0.2, (Hh, Ww))).astype(np.float32)
+    dem[rng.random((Hh, Ww)) < 0.03] = -9999.0
+    dem[rng.random((Hh, Ww)) < 0.01] = np.nan
+    dem[100:140, 2500:2560] = -9999.0                                   # a feature with no valid pixel
+    affine = (2.0, 0.0, 2600000.0, 0.0, -2.0, 1200000.0)               # swissALTI3D 2 m grid
+    from test_oracle_kat import ring
+
+    def quad(c0, r0, c1, r1, jitter=0.3):
+        pts = [(c0, r0), (c1, r0 + 3), (c1 + 2, r1), (c0 - 1, r1 - 2)]
+        return [ring(*[(affine[2] + (c + rng.uniform(-jitter, jitter)) * 2.0, affine[5] - (r + rng.uniform(-jitter, jitter)) * 2.0) for c, r in pts])]
+    vectors = [quad(10, 10, 80, 40), quad(2100, 50, 2950, 120), quad(-30, -20, 25, 30), quad(2980, 280, 3100, 330),
+               quad(2505, 105, 2555, 135), quad(5000, 5000, 5100, 5100), quad(1000.5, 150.5, 1001.4, 151.4, 0.0),
+               quad(300, 5, 1900, 295)]
+    vectors[0].append(ring(*[(affine[2] + c * 2.0, affine[5] - r * 2.0) for c, r in [(30, 20), (30, 30), (50, 30), (50, 20)]]))   # hole
+    stats = ["count", "min", "max", "mean", "median", "std", "sum", "percentile_10", "percentile_90"]
+    got = fr.zonal_stats(vectors, dem, affine=affine, stats=stats, nodata=-9999)
+    exp = ostats.zonal_stats(vectors, dem, affine, stats=[s for s in stats if not s.startswith("percentile")], nodata=-9999,
+                             percentiles=(10.0, 90.0))
+    assert [g["count"] for g in got] == [e["count"] for e in exp]
+    assert got[4]["count"] == 0 and got[4]["mean"] is None and got[5]["count"] == 0 and got[7]["count"] > 100000
+    for g, e in zip(got, exp):
+        for k in stats:
+            if e[k] is None:
+                assert g[k] is None
+            elif k in ("count", "min", "max"):
+                assert g[k] == e[k], k
+            elif k == "median":
+                assert abs(g[k] - e[k]) <= 1e-6 * abs(e[k]), k          # float32 mean of the two middle values vs binary64
+            else:
+                assert abs(g[k] - e[k]) <= 1e-6 * max(abs(e[k]), 1e-30), (k, g[k], e[k])
+    # other dtypes: int16 goes through the same float path; wide integers and float64 are refused, never rounded silently
+    dem16 = np.nan_to_num(dem, nan=-9999.0).astype(np.int16)
+    g16 = fr.zonal_stats(vectors[:2], dem16, affine=affine, stats=["count", "min", "max", "median"], nodata=-9999)
+    e16 = ostats.zonal_stats(vectors[:2], dem16.astype(np.float64), affine, stats=["count", "min", "max", "median"], nodata=-9999)
+    assert g16 == e16
+    with pytest.raises(TypeError):
+        fr.zonal_stats(vectors[:1], dem.astype(np.float64), affine=affine, nodata=-9999)

@@ -605,10 +605,18 @@ def test_width_limits(eng):
     h, _ = eng.zonal_hist_host(roads, TileBatch.from_arrays(wide, gt), pairs)          # the widest supported tile
     oh, _ = oracle_hist(roads, pairs, wide, gt)
     assert np.array_equal(h.astype(np.uint64), oh) and oh[0, 0].sum() == 2 * 1800
-    too_wide = np.zeros((1, 2, 2056, 3), np.uint8)
+    # the raster may be wider than 2048 px as long as every road's window is not
+    big = np.zeros((1, 4, 6000, 3), np.uint8)
+    big[0, :, :, 2] = (np.arange(6000) % 199).astype(np.uint8)[None, :]
+    r3 = RoadSet.from_geometries([[ring((3100, 1), (4900, 1), (4900, 3), (3100, 3))], [ring((10.5, 0.2), (600.2, 0.2), (600.2, 3.9), (10.5, 3.9))]])
+    p3 = PairList.from_pairs(2, [0, 1], [0, 0])
+    h3, _ = eng.zonal_hist_host(r3, TileBatch.from_arrays(big, gt), p3)
+    oh3, _ = oracle_hist(r3, p3, big, gt)
+    assert np.array_equal(h3.astype(np.uint64), oh3) and oh3[0, 0].sum() == 2 * 1800
+    r4 = RoadSet.from_geometries([[ring((100, 1), (2300, 1), (2300, 3), (100, 3))]])
     with pytest.raises(NativeError) as ei:
-        eng.zonal_hist_host(roads, TileBatch.from_arrays(too_wide, gt), pairs)
-    assert ei.value.status == -6                     # RS_ERR_UNSUPPORTED, never a silent wrong answer
+        eng.zonal_hist_host(r4, TileBatch.from_arrays(big, gt), pairs)
+    assert ei.value.status == -6                     # RS_ERR_UNSUPPORTED (a 2200 px wide window), never a silent wrong answer
     tall = np.zeros((1, 5000, 8, 1), np.uint8)       # tall rasters are fine
     tall[0, :, :, 0] = (np.arange(5000) % 200).astype(np.uint8)[:, None]
     r2 = RoadSet.from_geometries([[ring((1, 10), (7, 10), (7, 4990), (1, 4990))]])
