@@ -55,7 +55,11 @@ def test_fill_properties(rings):
     cancel (even-odd over all rings, the way GDAL collects the parts of a MultiPolygon)"""
     m = cport.rasterize(rings, (H, W))
     assert np.array_equal(m, cport.rasterize(rings[::-1], (H, W)))
-    assert np.array_equal(m, cport.rasterize([r[::-1].copy() for r in rings], (H, W)))
+    # GDAL burns a horizontal edge lying exactly on a scanline only when it runs towards -x (llrasterize.cpp), so the ring
+    # direction matters for such edges and for nothing else
+    on_scanline = any(r[k, 1] == r[k + 1, 1] and r[k, 1] - np.floor(r[k, 1]) == 0.5 for r in rings for k in range(len(r) - 1))
+    if not on_scanline:
+        assert np.array_equal(m, cport.rasterize([r[::-1].copy() for r in rings], (H, W)))
     twice = cport.rasterize(list(rings) + [r.copy() for r in rings], (H, W))
     # the doubled crossings pair up into empty spans: what is left is GDAL's separate burn of horizontal edges lying on
     # scanlines, which the single polygon has too
