@@ -546,24 +546,23 @@ int rs_extract_pixels_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *t
     rs_pairs dp;
     if ((rc = stage_inputs(ctx, roads, tiles, pairs, values != nullptr, dr, dt, dp))) return rc;
     cudaStream_t st = ctx->host_stream;
-    const size_t mb = (size_t)P * tiles->height * tiles->width;
-    if ((rc = ensure(ctx, ctx->stage[9], mb))) return rc;
-    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->stage[9].p, 0, mb, st));
-    if ((rc = launch_zonal(ctx, &dr, &dt, &dp, nullptr, nullptr, nullptr, (uint8_t *)ctx->stage[9].p, window_mode, st))) return rc;
-    if ((rc = ensure(ctx, ctx->stage[10], sizeof(int64_t) * ((size_t)P + 1)))) return rc;
+    // count pass -> per-pair offsets (exclusive scan); the write pass walks every pair in raster order behind its offset.
+    // No P x H x W mask is materialised: scratch is 12 bytes per pair.
+    if ((rc = ensure(ctx, ctx->stage[9], sizeof(uint32_t) * (size_t)P))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], sizeof(unsigned long long) * ((size_t)P + 1)))) return rc;
+    uint32_t *cnt = (uint32_t *)ctx->stage[9].p;
+    unsigned long long *off = (unsigned long long *)ctx->stage[10].p;
     const int bpp = tiles->channels * (int)elem_bytes(tiles->dtype);
-    if ((rc = launch_extract(ctx, (const uint8_t *)ctx->stage[9].p, nullptr, dp.pair_tile, P, tiles->height, tiles->width, bpp,
-                             (long long *)ctx->stage[10].p, nullptr, 0, st)))
-        return rc;
-    RS_CUDA_OK(ctx, cudaMemcpyAsync(pair_off, ctx->stage[10].p, sizeof(int64_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, st));
+    RS_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (size_t)P, st));
+    if ((rc = launch_zonal_extract(ctx, &dr, &dt, &dp, window_mode, cnt, off, nullptr, bpp, 0, st))) return rc;
+    if ((rc = launch_fstats_offsets(ctx, cnt, P, off, st))) return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(pair_off, off, sizeof(int64_t) * ((size_t)P + 1), cudaMemcpyDeviceToHost, st));
     if ((rc = finish(ctx))) return rc;
     const int64_t total = pair_off[P];
     *n_total = total;
     if (!values || capacity_pixels < total || total == 0) return RS_OK;
     if ((rc = ensure(ctx, ctx->stage[11], (size_t)total * bpp))) return rc;
-    if ((rc = launch_extract(ctx, (const uint8_t *)ctx->stage[9].p, dt.pixels, dp.pair_tile, P, tiles->height, tiles->width, bpp,
-                             nullptr, (uint8_t *)ctx->stage[11].p, 1, st)))
-        return rc;
+    if ((rc = launch_zonal_extract(ctx, &dr, &dt, &dp, window_mode, cnt, off, (uint8_t *)ctx->stage[11].p, bpp, 1, st))) return rc;
     RS_CUDA_OK(ctx, cudaMemcpyAsync(values, ctx->stage[11].p, (size_t)total * bpp, cudaMemcpyDeviceToHost, st));
     return finish(ctx);
 }

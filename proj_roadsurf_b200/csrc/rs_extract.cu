@@ -1,6 +1,5 @@
 // Table-shaped entry points around the overlay kernels (sm_100a):
-//   ordered pixel extraction   fct_misc.get_pixel_values' return value: the in-mask pixels of every (road, tile)
-//                              pair in row-major order (scripts/functions/fct_misc.py:87-99, np.extract)
+//   (ordered pixel extraction, fct_misc.get_pixel_values' return value, is zonal_kernel<PxExtract> in rs_zonal.cu)
 //   group histograms           the groupby of fct_statistics.get_df_stats_groupby (scripts/functions/fct_statistics.py:55)
 //                              on uint8 pixel tables: 256-bin histogram per group, finalized by rs_finalize_stats
 //   table vote                 determine_class.determine_detected_class on the detection table
@@ -13,90 +12,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include <cub/device/device_scan.cuh>
-
 #include "rs_internal.h"
 
 namespace rs {
 
 constexpr unsigned FULLM = 0xffffffffu;
-
-// ---------------------------------------------------------------------------------------------
-// ordered extraction: masks uint8[P][H][W] -> per-row counts -> exclusive scan -> packed pixel rows
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) row_count_kernel(const uint8_t *__restrict__ masks, int W, long long n_rows, int *__restrict__ cnt)
-{
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= n_rows) return;
-    const uint8_t *m = masks + row * W;
-    int c = 0;
-    for (int x = lane; x < W; x += 32) c += m[x] != 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULLM, c, o);
-    if (lane == 0) cnt[row] = c;
-}
-
-// one warp per (pair, row): ballot-compacts the row's in-mask pixels, in x order, behind the row's offset
-__global__ void __launch_bounds__(256) row_write_kernel(const uint8_t *__restrict__ masks, const uint8_t *__restrict__ pixels,
-                                                        const int *__restrict__ pair_tile, int H, int W, int bpp, long long n_rows,
-                                                        const int *__restrict__ row_off, uint8_t *__restrict__ out)
-{
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= n_rows) return;
-    const int p = (int)(row / H), y = (int)(row - (long long)p * H);
-    const uint8_t *m = masks + row * W;
-    const uint8_t *src = pixels + ((size_t)pair_tile[p] * H + y) * (size_t)W * bpp;
-    long long base = row_off[row];
-    for (int x0 = 0; x0 < W; x0 += 32) {
-        const int x = x0 + lane;
-        const bool on = x < W && m[x] != 0;
-        const unsigned b = __ballot_sync(FULLM, on);
-        if (on) {
-            uint8_t *d = out + (size_t)(base + __popc(b & ((1u << lane) - 1u))) * bpp;
-            for (int k = 0; k < bpp; k++) d[k] = src[(size_t)x * bpp + k];
-        }
-        base += __popc(b);
-    }
-}
-
-__global__ void pair_offsets_kernel(const int *__restrict__ row_off, const int *__restrict__ row_cnt, int H, int n_pairs,
-                                    long long n_rows, long long *__restrict__ pair_off)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n_pairs) pair_off[p] = row_off[(long long)p * H];
-    if (p == n_pairs) pair_off[p] = n_rows ? (long long)row_off[n_rows - 1] + row_cnt[n_rows - 1] : 0;
-}
-
-int launch_extract(rs_ctx *ctx, const uint8_t *masks, const void *pixels, const int *pair_tile, int n_pairs, int H, int W, int bpp,
-                   long long *pair_off_dev, uint8_t *values_dev, int phase, cudaStream_t st)
-{
-    const long long n_rows = (long long)n_pairs * H;
-    if (n_rows * W >= (1ll << 31)) return RS_ERR_UNSUPPORTED;          // int32 offsets
-    int rc;
-    if ((rc = ensure(ctx, ctx->stage[12], sizeof(int) * (size_t)(n_rows + 1)))) return rc;    // counts
-    if ((rc = ensure(ctx, ctx->stage[13], sizeof(int) * (size_t)(n_rows + 1)))) return rc;    // offsets
-    int *cnt = (int *)ctx->stage[12].p, *off = (int *)ctx->stage[13].p;
-    const unsigned blocks = (unsigned)((n_rows * 32 + 255) / 256);
-    if (phase == 0) {
-        if (n_rows) {
-            row_count_kernel<<<blocks, 256, 0, st>>>(masks, W, n_rows, cnt);
-            ctx->launches++;
-            size_t tmp = 0;
-            RS_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, off, (int)n_rows, st));
-            if ((rc = ensure(ctx, ctx->stage[14], tmp))) return rc;
-            RS_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->stage[14].p, tmp, cnt, off, (int)n_rows, st));
-        }
-        pair_offsets_kernel<<<(n_pairs + 256) / 256, 256, 0, st>>>(off, cnt, H, n_pairs, n_rows, pair_off_dev);
-        ctx->launches++;
-    } else if (n_rows) {
-        row_write_kernel<<<blocks, 256, 0, st>>>(masks, (const uint8_t *)pixels, pair_tile, H, W, bpp, n_rows, off, values_dev);
-        ctx->launches++;
-    }
-    RS_CUDA_OK(ctx, cudaGetLastError());
-    return RS_OK;
-}
 
 // ---------------------------------------------------------------------------------------------
 // group histograms of a uint8 column

@@ -68,6 +68,8 @@ int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
 int launch_zonal_f32(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, int window_mode, double nodata,
                      int has_nodata, uint32_t *count, uint32_t *cursor, const unsigned long long *offset, float *values, int write,
                      cudaStream_t st);
+int launch_zonal_extract(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, int window_mode,
+                         uint32_t *count, const unsigned long long *offset, uint8_t *values, int bpp, int write, cudaStream_t st);
 int launch_fstats_offsets(rs_ctx *ctx, const uint32_t *counts, int n, unsigned long long *offsets, cudaStream_t st);
 int launch_fstats_sort(rs_ctx *ctx, const float *values, float *sorted, long long total, int n, const unsigned long long *offsets,
                        cudaStream_t st);
@@ -84,8 +86,6 @@ int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class,
                 const int32_t *cutoffs_host, int n_thr, int rule, double min_area_frac, int8_t *cover,
                 double *scores, int64_t *confusion, double *metrics, cudaStream_t st);
 int launch_metrics(rs_ctx *ctx, const int64_t *confusion, int n_thr, double *metrics, cudaStream_t st);
-int launch_extract(rs_ctx *ctx, const uint8_t *masks, const void *pixels, const int *pair_tile, int n_pairs, int H, int W, int bpp,
-                   long long *pair_off_dev, uint8_t *values_dev, int phase, cudaStream_t st);
 int launch_group_hist(rs_ctx *ctx, const uint8_t *values, const int *group, long long n, int n_groups, uint32_t *hist, cudaStream_t st);
 int launch_vote_table(rs_ctx *ctx, const int *row_off, const int8_t *cls, const double *score, const double *weighted,
                       const double *area, int n_roads, const double *thr_dev, int n_thr, int8_t *cover, double *scores, cudaStream_t st);

@@ -77,6 +77,13 @@ struct F32Args {
     float *values;
 };
 
+struct ExtractArgs {
+    uint32_t *count;                      // per pair: in-mask pixels (count pass)
+    const unsigned long long *offset;     // per pair: first row of its slice of `values` (write pass)
+    uint8_t *values;                      // [total][bpp]
+    int bpp;                              // bytes per pixel (channels * element size)
+};
+
 struct ZonalArgs {
     const double2 *xy;
     const int *ring_off;
@@ -112,6 +119,7 @@ struct ZonalArgs {
     int4 *ov_items;           // items the pool could not hold ...
     int *ov_count;            // ... and their number
     F32Args f;                // PxF32
+    ExtractArgs x;            // PxExtract
 };
 
 // team-local allocation state of the emitting rasterizer (warp-uniform registers)
@@ -197,7 +205,7 @@ __device__ __forceinline__ uint32_t bin_off(uint32_t w, int k)      // k is a co
 template <int C_>
 struct PxBandsU8 {
     static constexpr int C = C_, HC = C_, BPP = C_, NW = 2 * C_;
-    static constexpr bool MASK = false, EMIT = false, FLT = false;
+    static constexpr bool MASK = false, EMIT = false, FLT = false, EXTRACT = false;
     // pixel I of the group: hist (shared-memory byte address of the team histogram) gets one increment per band
     // `on` is the pixel's mask bit (0 / 1), also the addend of its increments
     template <int I>
@@ -235,7 +243,7 @@ struct PxBandsU8 {
 
 struct PxClassScore {
     static constexpr int C = 2, HC = 3, BPP = 2, NW = 4;
-    static constexpr bool MASK = false, EMIT = false, FLT = false;
+    static constexpr bool MASK = false, EMIT = false, FLT = false, EXTRACT = false;
     __device__ static __forceinline__ void one(uint32_t cls, uint32_t score, uint32_t *hist, uint32_t &nz)
     {
         nz += ((cls | score) == 0);
@@ -261,7 +269,7 @@ struct PxClassScore {
 template <bool F32>
 struct PxU16x4Rescale {
     static constexpr int C = 4, HC = 4, BPP = 8, NW = 16;
-    static constexpr bool MASK = false, EMIT = false, FLT = false;
+    static constexpr bool MASK = false, EMIT = false, FLT = false, EXTRACT = false;
     __device__ static __forceinline__ uint32_t scale(const ZonalArgs &a, uint32_t s, int c)
     {
         if (F32) {
@@ -301,18 +309,26 @@ struct PxU16x4Rescale {
 
 struct PxMask {
     static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
-    static constexpr bool MASK = true, EMIT = false, FLT = false;
+    static constexpr bool MASK = true, EMIT = false, FLT = false, EXTRACT = false;
 };
 struct PxEmit {                     // the rasterizer of the two-kernel form: entries go to the pool
     static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
-    static constexpr bool MASK = true, EMIT = true, FLT = false;
+    static constexpr bool MASK = true, EMIT = true, FLT = false, EXTRACT = false;
 };
 // float32 single-band rasters (rasterstats.zonal_stats over a DEM, fct_rasters.py:147-163): the in-mask pixels that are neither
 // NaN nor nodata are counted per feature (WRITE = false) or written to the feature's slice of a compact value array
 template <bool WRITE_>
 struct PxF32 {
     static constexpr int C = 1, HC = 0, BPP = 4, NW = 8;
-    static constexpr bool MASK = true, EMIT = false, FLT = true, WRITE = WRITE_;
+    static constexpr bool MASK = true, EMIT = false, FLT = true, EXTRACT = false, WRITE = WRITE_;
+};
+// ordered extraction (fct_misc.get_pixel_values' return value, fct_misc.py:87-99): the in-mask pixels of every pair, row-major,
+// counted per pair (WRITE = false) or copied behind the pair's offset (WRITE = true).  A pair is ONE work item here (no row
+// slices), so a team walks it in raster order and a running position is all the ordering needs -- no P x H x W mask.
+template <bool WRITE_>
+struct PxExtract {
+    static constexpr int C = 1, HC = 0, BPP = 1, NW = 2;
+    static constexpr bool MASK = true, EMIT = false, FLT = false, EXTRACT = true, WRITE = WRITE_;
 };
 
 // 8 pixels x BPP bytes from a (8*BPP)-byte aligned address into NW words
@@ -412,7 +428,8 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
     }
     if (nrings > 1 && nrings <= RINGCAP)
         for (int k = lane; k <= nrings; k += 32) s.ring_start[k] = a.ring_off[g0 + k] - v0;
-    uint32_t nz = 0, mz = 0, fcnt = 0;
+    uint32_t nz = 0, mz = 0, fcnt = 0, ecnt = 0;
+    unsigned long long epos = 0;
     uint32_t zprev[PX::MASK ? 1 : PX::HC];          // hist[band][0] after the previous pair (a.minzero only)
 #pragma unroll
     for (int c = 0; c < (PX::MASK ? 1 : PX::HC); c++) zprev[c] = 0;
@@ -480,6 +497,10 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             g.xshift = q3.x; g.yshift = q3.y; g.wu = q3.z; g.status = q3.w;
         }
         if (g.status <= 0) continue;
+        if constexpr (PX::EXTRACT) {
+            ecnt = 0;
+            if constexpr (PX::WRITE) epos = a.x.offset[p];
+        }
         const int cbcol = g.col_off & ~31;                              // absolute column of mask bit 0
         const int pitch = ((g.col_off + g.w - 1) >> 5) - (cbcol >> 5) + 1;   // mask words per row
         const int pp = pitch | 1;                                       // odd row stride: lane-per-row walks are conflict-free
@@ -688,6 +709,36 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
                         es.prev = es.pos + 1u;
                         es.pos += units;
                     }
+                } else if constexpr (PX::EXTRACT) {
+                    for (int base = 0; base < n; base += 32) {
+                        const int e = base + lane;
+                        const uint32_t en = e < n ? s.u.entries[e] : 0u;
+                        const int c = __popc(en & 255u);
+                        if constexpr (!PX::WRITE) {
+                            ecnt += (uint32_t)c;
+                        } else {
+                            int incl = c;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int u = __shfl_up_sync(FULL, incl, o);
+                                if (lane >= o) incl += u;
+                            }
+                            const int total = __shfl_sync(FULL, incl, 31);
+                            if (c) {
+                                const int x8 = cbcol + 8 * (int)((en >> 8) & 0xfffu);
+                                const int yabs = g.row_off + r0 + (int)(en >> 20);
+                                const int bpp = a.x.bpp;
+                                const uint8_t *src = (const uint8_t *)a.pixels + (tile_pix + (size_t)yabs * a.W + x8) * bpp;
+                                uint8_t *dst = a.x.values + (epos + (unsigned long long)(incl - c)) * bpp;
+                                for (int i = 0; i < 8; i++)
+                                    if (en & (1u << i)) {
+                                        for (int k = 0; k < bpp; k++) dst[k] = __ldg(src + i * bpp + k);
+                                        dst += bpp;
+                                    }
+                            }
+                            epos += (unsigned long long)total;
+                        }
+                    }
                 } else if constexpr (PX::FLT) {
                     const float *fpx = (const float *)a.pixels;
                     for (int base = 0; base < n; base += 32) {
@@ -887,6 +938,13 @@ __device__ __forceinline__ void process_item(const ZonalArgs &a, TeamSmem<PX::HC
             }
             if (nq) consume(nq);
             __syncwarp();
+        }
+        if constexpr (PX::EXTRACT) {
+            if constexpr (!PX::WRITE) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ecnt += __shfl_xor_sync(FULL, ecnt, o);
+                if (lane == 0) a.x.count[p] = ecnt;
+            }
         }
         if constexpr (!PX::MASK) {
             // get_pixel_values with tile nodata == 0 pads every band of ONE (road, tile) call up to that call's longest band
@@ -1290,7 +1348,8 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
 // accumulate: add into hist / n_allzero (zeroed by the caller) instead of writing every row once
 static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
-                       int tile_lo, int tile_hi, int accumulate, const F32Args *f32, int f32_write, cudaStream_t st);
+                       int tile_lo, int tile_hi, int accumulate, const F32Args *f32, int f32_write, cudaStream_t st,
+                       const ExtractArgs *ex = nullptr);
 
 int launch_zonal_chunk(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
@@ -1308,9 +1367,18 @@ int launch_zonal_f32(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, 
     return launch_impl(ctx, roads, tiles, pairs, nullptr, nullptr, nullptr, nullptr, window_mode, 0, 0x7fffffff, 0, &f, write, st);
 }
 
+// ordered extraction: count (write == 0: count[p] for every pair) or write (values behind offset[p]) the in-mask pixels
+int launch_zonal_extract(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs, int window_mode,
+                         uint32_t *count, const unsigned long long *offset, uint8_t *values, int bpp, int write, cudaStream_t st)
+{
+    ExtractArgs x{count, offset, values, bpp};
+    return launch_impl(ctx, roads, tiles, pairs, nullptr, nullptr, nullptr, nullptr, window_mode, 0, 0x7fffffff, 0, nullptr, write, st, &x);
+}
+
 static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
-                       int tile_lo, int tile_hi, int accumulate, const F32Args *f32, int f32_write, cudaStream_t st)
+                       int tile_lo, int tile_hi, int accumulate, const F32Args *f32, int f32_write, cudaStream_t st,
+                       const ExtractArgs *ex)
 {
     if (!roads || !tiles || !pairs) return RS_ERR_INVALID_ARG;
     if (roads->n_roads < 0 || roads->n_verts < 0 || tiles->n_tiles < 0 || pairs->n_pairs < 0) return RS_ERR_INVALID_ARG;
@@ -1358,6 +1426,7 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     a.one = 1u;
     a.fast = (tiles->width % 8 == 0) && (((uintptr_t)tiles->pixels & 15u) == 0);
     if (f32) a.f = *f32;
+    if (ex) a.x = *ex;
     if (tiles->pixels && !f32) {
         // where do the tiles live?  (the first tile this launch reads: a streamed chunk is addressed through a shifted base)
         const size_t tile_bytes = (size_t)tiles->height * tiles->width * tiles->channels * (tiles->dtype == RS_U16 ? 2 : 1);
@@ -1369,7 +1438,7 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     }
 
     int HC = 0;
-    if (!masks && !f32) {
+    if (!masks && !f32 && !ex) {
         if (!prm || !hist || !n_allzero || (pairs->n_pairs > 0 && !tiles->pixels)) return RS_ERR_INVALID_ARG;
         if (prm->hist_mode == RS_HIST_CLASS_SCORE) {
             if (tiles->channels != 2 || tiles->dtype != RS_U8) return RS_ERR_UNSUPPORTED;
@@ -1386,7 +1455,7 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     }
 
     if (a.minzero && prm->hist_mode != RS_HIST_BANDS) return RS_ERR_INVALID_ARG;
-    if (!masks && !f32 && wide_eligible(tiles, prm, !a.sparse))
+    if (!masks && !f32 && !ex && wide_eligible(tiles, prm, !a.sparse))
         return launch_zonal_wide(ctx, roads, tiles, pairs, prm, hist, n_allzero, window_mode, tile_lo, tile_hi, accumulate, st);
     // one context = one set of scratch buffers: a launch on another stream than the previous one waits for it
     if (ctx->scratch_used && ctx->scratch_stream != st) RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch, 0));
@@ -1400,7 +1469,7 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     {
         const char *env = getenv("RS_ZONAL_SPLIT");
         const bool want = env ? atoi(env) != 0 : true;
-        if (want && !masks && !f32 && a.fast && !a.sparse && !a.minzero && !accumulate && pairs->n_pairs > 0) {
+        if (want && !masks && !f32 && !ex && a.fast && !a.sparse && !a.minzero && !accumulate && pairs->n_pairs > 0) {
             size_t free_b = 0, total_b = 0;
             RS_CUDA_OK(ctx, cudaMemGetInfo(&free_b, &total_b));
             size_t units = (size_t)pairs->n_pairs * 96 + (size_t)ctx->sm_count * 32 * CHUNK_UNITS;       // ~1.5 KiB per pair
@@ -1433,13 +1502,16 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));      // work counter, big items, small items, pool cursor, ...
     if ((rc = launch_pair_geom(ctx, roads, tiles, pairs, window_mode, prm ? prm->border_px : 0, tile_lo, tile_hi, st))) return rc;
     prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
-                                                                    a.road_slot, (masks || f32) ? nullptr : hist, n_allzero, a.minzero, HC,
-                                                                    (int4 *)ctx->items.p, ctx->d_counters + 1, (int)cap, tiles->height > ROWS_ITEM,
+                                                                    a.road_slot, (masks || f32 || ex) ? nullptr : hist, n_allzero, a.minzero, HC,
+                                                                    (int4 *)ctx->items.p, ctx->d_counters + 1, (int)cap,
+                                                                    !ex && tiles->height > ROWS_ITEM,
                                                                     accumulate);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
 
-    if (f32)
+    if (ex)
+        rc = f32_write ? launch_fast<PxExtract<true>, false>(ctx, a, st) : launch_fast<PxExtract<false>, false>(ctx, a, st);
+    else if (f32)
         rc = f32_write ? (a.fast ? launch_fast<PxF32<true>, true>(ctx, a, st) : launch_fast<PxF32<true>, false>(ctx, a, st))
                        : (a.fast ? launch_fast<PxF32<false>, true>(ctx, a, st) : launch_fast<PxF32<false>, false>(ctx, a, st));
     else if (masks) rc = launch_one<PxMask>(ctx, a, st);

@@ -201,23 +201,65 @@ def get_pixel_values(geoms, tile, BANDS=range(1, 4), pixel_values=pd.DataFrame()
     return pd.concat([pixel_values, frame], ignore_index=True)
 
 
+def table_from_rows(values: np.ndarray, pair_off: np.ndarray, no_data, BANDS, pair_ids, tile_names=None) -> pd.DataFrame:
+    """The concatenation of ``_frames_from_rows`` over every pair as ONE DataFrame, built column-wise (no per-pair frames):
+    values (n, C) = the ordered in-mask rows of all pairs, pair_off (P + 1,) their slices, pair_ids (P,) the ``road_id`` of
+    every pair.  Same rows, order, padding, dtypes and warnings as the per-pair loop (fct_misc.py:87-121 under
+    statistical_analysis.py:180-193)."""
+    bands = list(BANDS)
+    pair_off = np.asarray(pair_off, np.int64)
+    P = len(pair_off) - 1
+    n_in = np.diff(pair_off)
+    pair_of_row = np.repeat(np.arange(P), n_in)
+    pair_ids = np.asarray(pair_ids)
+    if no_data is None:
+        keep = values[:, [b - 1 for b in bands]].max(axis=1) != 0 if len(values) else np.zeros(0, bool)
+        cols = {f"band{b}": values[keep, b - 1] for b in bands}
+        cols["road_id"] = pair_ids[pair_of_row[keep]]
+        return pd.DataFrame(cols)
+    # nodata value: per (pair, band) the pixels equal to it are dropped, then every band of the pair is padded with it up to the
+    # pair's longest band
+    kept, cnt = {}, {}
+    for b in bands:
+        k = values[:, b - 1] != no_data
+        kept[b] = k
+        cs = np.concatenate([[0], np.cumsum(k)])
+        cnt[b] = cs[pair_off[1:]] - cs[pair_off[:-1]]
+    # the reference indexes length_bands with band - 1 (BANDS starts at 1): keep that
+    length_bands = [cnt[b] for b in bands]
+    longest = np.max(np.stack(length_bands), axis=0) if bands else np.zeros(P, np.int64)
+    out_off = np.concatenate([[0], np.cumsum(longest)])
+    total = int(out_off[-1])
+    cols = {}
+    for b in bands:
+        n_b = length_bands[b - 1]                  # IndexError for band lists that do not start at 1, like the reference
+        padded = n_b < longest
+        fill = np.asarray([no_data])
+        dt = np.result_type(values.dtype, fill.dtype) if padded.any() else values.dtype
+        col = np.full(total, no_data, dt)
+        k = kept[b]
+        rank = np.cumsum(k) - 1 - np.repeat(np.concatenate([[0], np.cumsum(cnt[b])])[:-1], n_in)       # rank inside the pair
+        col[(out_off[:-1][pair_of_row] + rank)[k]] = values[k, b - 1]
+        cols[f"band{b}"] = col
+        for p in np.nonzero(padded)[0]:
+            name = str(p) if tile_names is None else str(tile_names[p])
+            logger.warning(f"{int(longest[p] - n_b[p])} pixels was/were missing on the band {b} on the tile {name[-18:]} and"
+                           + f" got replaced with the value used of no data ({no_data}).")
+    cols["road_id"] = np.repeat(pair_ids, longest)
+    return pd.DataFrame(cols)
+
+
 def get_pixel_values_batch(roads: RoadSet, tiles: TileBatch, pairs: PairList, BANDS=range(1, 4), road_ids=None,
                            engine=None) -> pd.DataFrame:
     """The whole double loop of statistical_analysis.py:180-193 in one call: the concatenated
-    ``pixels_per_band`` table (columns band{b}, road_id), roads in order, tiles in pair order inside a road."""
+    ``pixels_per_band`` table (columns band{b}, road_id), roads in order, tiles in pair order inside a road.
+    One extraction call (count pass + ordered write pass on the device), one DataFrame built column-wise."""
     eng = engine or default_engine()
     pair_off, values = eng.extract_pixels_host(roads, tiles, pairs, window="crop")
     ids = np.arange(roads.n_roads) if road_ids is None else np.asarray(road_ids)
-    road_of_pair = pairs.road_of_pair()
-    frames = []
-    for p in range(pairs.n_pairs):
-        rows = values[pair_off[p]:pair_off[p + 1]]
-        if len(rows) == 0 and tiles.nodata is not None:
-            continue
-        frames.append(_frames_from_rows(rows, tiles.nodata, BANDS, str(p), {"road_id": ids[road_of_pair[p]]}))
-    if not frames:
+    if pairs.n_pairs == 0:
         return pd.DataFrame()
-    return pd.concat(frames, ignore_index=True)
+    return table_from_rows(values, pair_off, tiles.nodata, BANDS, ids[pairs.road_of_pair()])
 
 
 logger = format_logger(logger) if hasattr(logger, "remove") else logger

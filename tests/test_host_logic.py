@@ -152,3 +152,35 @@ def test_clip_labels_areas_match_the_overlay_oracle():
     assert n_checked > 15
     # every (label, tile) pair whose closed shapes intersect is a row, in label-major order
     assert out["OBJECTID"].tolist() == sorted(out["OBJECTID"].tolist())
+
+
+def test_table_from_rows_equals_the_per_pair_frames():
+    """the column-wise pixel table of get_pixel_values_batch == the concatenation of the per-pair frames (fct_misc.py:87-121)"""
+    import pandas as pd
+    from proj_roadsurf_b200.functions import fct_misc
+    rng = np.random.default_rng(3)
+    for no_data in (None, 0, 7):
+        for trial in range(6):
+            P = int(rng.integers(1, 9))
+            n = rng.integers(0, 40, P)
+            n[rng.integers(0, P)] = 0                                  # a pair without pixels
+            off = np.concatenate([[0], np.cumsum(n)])
+            vals = rng.integers(0, 4, (int(off[-1]), 3)).astype(np.uint8) * np.uint8(7 if no_data == 7 else 1)
+            vals[rng.random(len(vals)) < 0.2] = 0
+            ids = rng.integers(100, 105, P)
+            bands = (1, 2, 3) if trial % 2 == 0 else (1, 2)        # (the reference indexes with band - 1: lists start at 1)
+            frames = []
+            for p in range(P):
+                rows = vals[off[p]:off[p + 1]]
+                if len(rows) == 0 and no_data is not None:
+                    continue
+                frames.append(fct_misc._frames_from_rows(rows, no_data, bands, str(p), {"road_id": ids[p]}))
+            exp = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame()
+            got = fct_misc.table_from_rows(vals, off, no_data, bands, ids)
+            if len(exp) == 0:
+                assert len(got) == 0
+                continue
+            assert list(got.columns) == list(exp.columns)
+            for c in exp.columns:
+                assert np.array_equal(got[c].to_numpy(), exp[c].to_numpy()), (no_data, trial, c)
+                assert got[c].dtype == exp[c].dtype, (no_data, trial, c, got[c].dtype, exp[c].dtype)
