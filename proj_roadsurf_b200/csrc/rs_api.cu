@@ -159,6 +159,7 @@ int rs_ctx_destroy(rs_ctx *ctx)
     if (ctx->pair_zero.p) cudaFree(ctx->pair_zero.p);
     for (rs::DevBuf *b : {&ctx->wide_cnt, &ctx->wide_off, &ctx->wide_bounds, &ctx->wide_pair_road, &ctx->wide_tmp})
         if (b->p) cudaFree(b->p);
+    if (ctx->lut_dev.p) cudaFree(ctx->lut_dev.p);
     if (ctx->pool.p) cudaFree(ctx->pool.p);
     if (ctx->heads.p) cudaFree(ctx->heads.p);
     if (ctx->ov_items.p) cudaFree(ctx->ov_items.p);

@@ -16,7 +16,6 @@
 
 namespace rs {
 
-constexpr unsigned FULLM = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------
 // group histograms of a uint8 column

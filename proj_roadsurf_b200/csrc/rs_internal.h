@@ -38,6 +38,12 @@ struct rs_ctx {
     cudaEvent_t ev_scratch = nullptr;     // recorded after every launch that uses the scratch above
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
+    rs::DevBuf lut_dev;                   // 16 -> 8 bit rescale thresholds of the last scale parameters (rs_zonal.cu, PxU16x4Lut)
+    bool lut_valid = false, lut_ok = false;
+    int lut_f32 = 0;
+    double lut_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t lut_k[4] = {0, 0, 0, 0};
+    long long lut_b[4] = {0, 0, 0, 0};
     void *comm = nullptr;                 // ncclComm_t of rs_comm_init (rs_comm.cu)
     int comm_world = 0, comm_rank = 0;
 };

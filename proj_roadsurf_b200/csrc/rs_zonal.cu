@@ -36,6 +36,7 @@
 // geometry: the rounding of every operation is part of the specification.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "rs_internal.h"
@@ -109,6 +110,11 @@ struct ZonalArgs {
     uint8_t *masks;
     int window_mode;
     double sk[4], so[4];
+    // integer form of the 16 -> 8 bit rescale (PxU16x4Lut): out = guess +- 1, guess = (s * lut_k + lut_b) >> 32 clamped to 0..255,
+    // corrected with the exact thresholds lut_lohi[band][guess] = first | last << 16 source value that maps to `guess`
+    uint32_t lut_k[4];
+    long long lut_b[4];
+    const uint32_t *lut_lohi;
     int *work_counter;
     int *status;
     // two-kernel form
@@ -280,6 +286,47 @@ struct PxU16x4Rescale {
         double f = __dadd_rn(__dmul_rn((double)s, a.sk[c]), a.so[c]);
         f = fmin(fmax(f, 0.0), 255.0);
         return (uint32_t)(int)__dadd_rn(f, 0.5);
+    }
+    template <int I>
+    __device__ static __forceinline__ void pixel(const ZonalArgs &a, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t one, uint32_t &nz)
+    {
+        uint32_t any = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t o = scale(a, (r[(I * 8 + 2 * c) >> 2] >> (((I * 8 + 2 * c) & 3) * 8)) & 0xffffu, c);
+            red_inc1(hist + 4u * (c * 256u + o), on);
+            any |= o;
+        }
+        nz += (any == 0) ? on : 0u;
+    }
+    __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
+    {
+        const uint16_t *p = (const uint16_t *)a.pixels + pix * 4;
+        uint32_t any = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t o = scale(a, __ldg(p + c), c);
+            atomicAdd(&hist[c * 256 + o], 1u);
+            any |= o;
+        }
+        nz += (any == 0);
+    }
+};
+
+// the same rescale without floating point in the pixel loop: gdal.Translate's  byte(clamp(s k + off, 0, 255) + 0.5)  is a
+// non-decreasing step function of the 16-bit source value, so it is fixed by the 255 source values at which it steps.  The
+// launcher tabulates them per band with the exact arithmetic of PxU16x4Rescale (either precision), checks on ALL 65 536 inputs
+// that a 32.32 fixed-point guess is never more than one step off, and only then selects this policy: bit-identical by
+// construction, four integer instructions and one L1-resident table read per band byte instead of the FP64 / XU pipe.
+struct PxU16x4Lut {
+    static constexpr int C = 4, HC = 4, BPP = 8, NW = 16;
+    static constexpr bool MASK = false, EMIT = false, FLT = false, EXTRACT = false;
+    __device__ static __forceinline__ uint32_t scale(const ZonalArgs &a, uint32_t s, int c)
+    {
+        const long long t = (long long)((unsigned long long)s * a.lut_k[c]) + a.lut_b[c];
+        const int g = min(max((int)(t >> 32), 0), 255);
+        const uint32_t lh = __ldg(a.lut_lohi + c * 256 + g);
+        return (uint32_t)(g + (s > (lh >> 16) ? 1 : 0) - (s < (lh & 0xffffu) ? 1 : 0));
     }
     template <int I>
     __device__ static __forceinline__ void pixel(const ZonalArgs &a, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t one, uint32_t &nz)
@@ -1346,6 +1393,87 @@ int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, cons
 // tile_lo / tile_hi: only pairs whose tile index lies in [tile_lo, tile_hi) are processed (tiles->pixels is then indexed with
 // the global tile index, so a caller that holds one chunk passes chunk_base - tile_lo * tile_bytes);
 // accumulate: add into hist / n_allzero (zeroed by the caller) instead of writing every row once
+
+// ---------------------------------------------------------------------------------------------
+// 16 -> 8 bit rescale tables (PxU16x4Lut): built and verified on the host for one (k, off, precision) set, cached in the context
+// ---------------------------------------------------------------------------------------------
+static inline int rescale_exact(unsigned s, double k, double off, bool f32)
+{
+    if (f32) {
+        volatile float m = (float)s * (float)k;          // separate multiply and add, like __fmul_rn / __fadd_rn
+        float f = m + (float)off;
+        f = f < 0.0f ? 0.0f : f;
+        f = f > 255.0f ? 255.0f : f;
+        return (int)(f + 0.5f);
+    }
+    volatile double m = (double)s * k;
+    double f = m + off;
+    f = f < 0.0 ? 0.0 : f;
+    f = f > 255.0 ? 255.0 : f;
+    return (int)(f + 0.5);
+}
+
+// returns 1 when the integer form is exact for all 65 536 inputs of all 4 bands (tables uploaded, args filled), 0 otherwise
+static int prepare_rescale_lut(rs_ctx *ctx, const rs_zonal_params *prm, ZonalArgs &a, cudaStream_t st)
+{
+    const bool f32 = prm->rescale == 2;
+    bool same = ctx->lut_valid && ctx->lut_f32 == (int)f32;
+    for (int c = 0; c < 4 && same; c++) same = ctx->lut_key[c] == prm->scale_k[c] && ctx->lut_key[4 + c] == prm->scale_off[c];
+    if (!same) {
+        ctx->lut_valid = false;
+        ctx->lut_ok = false;
+        static thread_local uint32_t lohi[4 * 256];
+        bool ok = true;
+        for (int c = 0; c < 4 && ok; c++) {
+            const double k = prm->scale_k[c], off = prm->scale_off[c];
+            if (!(k > 0.0) || !(k < 1.0) || !(off == off) || fabs(off) > 1.0e9) { ok = false; break; }
+            const double kf = f32 ? (double)(float)k : k, of = f32 ? (double)(float)off : off;
+            ctx->lut_k[c] = (uint32_t)llrint(kf * 4294967296.0);
+            ctx->lut_b[c] = (long long)llrint((of + 0.5) * 4294967296.0);
+            int lo[256], hi[256];
+            for (int v = 0; v < 256; v++) { lo[v] = 65536; hi[v] = -1; }
+            int prev = 0;
+            for (unsigned sv = 0; sv < 65536u && ok; sv++) {
+                const int o = rescale_exact(sv, k, off, f32);
+                if (o < prev || o > 255) ok = false;                     // not a non-decreasing step function
+                prev = o;
+                if ((int)sv < lo[o]) lo[o] = (int)sv;
+                hi[o] = (int)sv;
+            }
+            // values no input maps to: an empty interval placed where the neighbours meet, so that the correction moves on
+            int next_lo = 65536;
+            for (int v = 255; v >= 0; v--) {
+                if (hi[v] < 0) { lo[v] = next_lo > 65535 ? 65535 : next_lo; hi[v] = lo[v] - 1; }
+                else next_lo = lo[v];
+            }
+            for (int v = 0; v < 256; v++) lohi[c * 256 + v] = (uint32_t)lo[v] | ((uint32_t)(hi[v] < 0 ? 0 : hi[v]) << 16);
+            // the device expression on every input
+            for (unsigned sv = 0; sv < 65536u && ok; sv++) {
+                const long long t = (long long)((unsigned long long)sv * ctx->lut_k[c]) + ctx->lut_b[c];
+                long long gq = t >> 32;
+                const int g = gq < 0 ? 0 : (gq > 255 ? 255 : (int)gq);
+                const uint32_t lh = lohi[c * 256 + g];
+                const int o = g + (sv > (lh >> 16) ? 1 : 0) - (sv < (lh & 0xffffu) ? 1 : 0);
+                if (o != rescale_exact(sv, k, off, f32)) ok = false;
+            }
+        }
+        if (ok) {
+            int rc = ensure(ctx, ctx->lut_dev, sizeof(lohi));
+            if (rc) return 0;
+            if (cudaMemcpyAsync(ctx->lut_dev.p, lohi, sizeof(lohi), cudaMemcpyHostToDevice, st) != cudaSuccess) return 0;
+            if (cudaStreamSynchronize(st) != cudaSuccess) return 0;     // lohi is reused by the next call
+        }
+        for (int c = 0; c < 4; c++) { ctx->lut_key[c] = prm->scale_k[c]; ctx->lut_key[4 + c] = prm->scale_off[c]; }
+        ctx->lut_f32 = (int)f32;
+        ctx->lut_ok = ok;
+        ctx->lut_valid = true;
+    }
+    if (!ctx->lut_ok) return 0;
+    for (int c = 0; c < 4; c++) { a.lut_k[c] = ctx->lut_k[c]; a.lut_b[c] = ctx->lut_b[c]; }
+    a.lut_lohi = (const uint32_t *)ctx->lut_dev.p;
+    return 1;
+}
+
 static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
                        const rs_zonal_params *prm, uint32_t *hist, uint32_t *n_allzero, uint8_t *masks, int window_mode,
                        int tile_lo, int tile_hi, int accumulate, const F32Args *f32, int f32_write, cudaStream_t st,
@@ -1516,8 +1644,11 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
                        : (a.fast ? launch_fast<PxF32<false>, true>(ctx, a, st) : launch_fast<PxF32<false>, false>(ctx, a, st));
     else if (masks) rc = launch_one<PxMask>(ctx, a, st);
     else if (prm->hist_mode == RS_HIST_CLASS_SCORE) rc = launch_one<PxClassScore>(ctx, a, st);
-    else if (tiles->dtype == RS_U16)
-        rc = prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);
+    else if (tiles->dtype == RS_U16) {
+        const char *env = getenv("RS_ZONAL_LUT");
+        if ((!env || atoi(env) != 0) && prepare_rescale_lut(ctx, prm, a, st)) rc = launch_one<PxU16x4Lut>(ctx, a, st);
+        else rc = prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);
+    }
     else
         switch (tiles->channels) {
             case 1: rc = launch_one<PxBandsU8<1>>(ctx, a, st); break;

@@ -820,3 +820,29 @@ def test_wide_kernel_window_modes_and_slots(eng, monkeypatch):
                      for w, b, s_ in (("full", 0, None), ("boundless", 0, None), ("crop", 13, None), ("crop", 0, slot))]
     for (h1, z1), (h0, z0) in zip(res["1"], res["0"]):
         assert np.array_equal(h1, h0) and np.array_equal(z1, z0) and h1.sum() > 0
+
+
+@pytest.mark.parametrize("f32", [False, True])
+def test_u16_rescale_integer_form_equals_floating_form(eng, f32, monkeypatch):
+    """PxU16x4Lut (thresholds + fixed-point guess, verified on all 65 536 inputs by the launcher) against the floating-point
+    policy (RS_ZONAL_LUT=0) and the oracle, for ordinary ranges, for ranges whose steps fall on exact .5 ties, and for a
+    range narrower than 255 (scale >= 1: the integer form is refused and the floating one runs)."""
+    from proj_roadsurf_b200.engine import scale_params
+    g = synth.Grid(3, 3)
+    rr = synth.ribbon_roads(g, 12, seed=5)
+    rng = np.random.default_rng(2)
+    tiles = rng.integers(0, 65536, (g.n_tiles, 256, 256, 4), dtype=np.uint16)        # every source value, also the clamped tails
+    tiles[..., 3] = rng.integers(0, 700, tiles.shape[:3])
+    gt = g.transforms()
+    tb = TileBatch.from_arrays(tiles, gt)
+    for smin, smax in (([150.0, 300.0, 300.0, 300.0], [9000.0, 6000.0, 6000.0, 6000.0]),
+                       ([0.0, 0.0, 0.0, 0.0], [510.0, 65535.0, 1020.0, 256.0]),          # k = 1/2, 1/257, 1/4: ties at x.5
+                       ([1000.0, 10.0, 0.0, 100.0], [1100.0, 60000.0, 65535.0, 600.0])):   # 100-wide range: scale 2.55
+        k, off = scale_params(smin, smax, f32)
+        monkeypatch.setenv("RS_ZONAL_LUT", "1")
+        h1, z1 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
+        monkeypatch.setenv("RS_ZONAL_LUT", "0")
+        h0, z0 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
+        assert np.array_equal(h1, h0) and np.array_equal(z1, z0), (smin, smax)
+        oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt, scale_k=k, scale_off=off, rescale_f32=f32)
+        assert np.array_equal(h1.astype(np.uint64), oh) and np.array_equal(z1.astype(np.uint64), onz), (smin, smax)
