@@ -376,6 +376,24 @@ int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, co
                        const rs_lattice *lattice, int32_t *road_pair_off, int32_t *pair_tile, int64_t capacity, int64_t *n_pairs);
 
 /*
+ * The same broad phase for tiles that are NOT on a lattice (any extents, any order): the tiles are binned into a uniform grid
+ * on the device, every road looks up the cells under its bounding box.  Same predicate, outputs and two-call protocol as
+ * rs_pairs_bbox_host.
+ */
+int rs_pairs_bbox_grid_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, const double *tile_ext, int32_t n_tiles,
+                            int32_t *road_pair_off, int32_t *pair_tile, int64_t capacity, int64_t *n_pairs);
+
+/*
+ * Exact reject of a candidate pair list: keep[p] = 1 iff the road polygon of pair p (all rings, even-odd) INTERSECTS the closed
+ * rectangle tile_ext[pair_tile[p]] -- the predicate of gpd.sjoin(tiles, roads) (statistical_analysis.py:170-171; touching
+ * counts).  An edge touches the rectangle, or the rectangle lies inside the polygon.  Binary64 orientation signs: can differ
+ * from GEOS only for contacts within rounding distance.  (Pairs the bounding-box phase keeps in excess contribute no pixel, so
+ * this filter changes no statistic; it makes the pair table the reference's and saves their work items.)
+ */
+int rs_pairs_intersect_host(rs_ctx *ctx, const rs_roads *roads, const double *tile_ext, int32_t n_tiles,
+                            const int32_t *road_pair_off, const int32_t *pair_tile, int32_t n_pairs, uint8_t *keep);
+
+/*
  * Two-sample Kolmogorov-Smirnov statistic of every road's pixel values on one band against a reference distribution,
  * from histograms: scipy.stats.kstest(road_values, general_values) of statistical_analysis.py:441-451 (the pixels of the
  * road against all pixels of its road type).  hist uint32[n_roads][256] (one band), ref_hist uint64[n_refs][256],

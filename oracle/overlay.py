@@ -114,3 +114,44 @@ def get_weighted_scores(labels: List[Sequence[np.ndarray]], preds: List[Sequence
             if frac > 0.05:
                 rows.append((i, j, joined, frac, frac * float(score[j])))
     return rows
+
+
+def polygon_intersects_rect(rings: Sequence[np.ndarray], rect) -> bool:
+    """Exact (rational arithmetic) 'intersects' of a polygon given by its rings (even-odd) and the CLOSED rectangle
+    rect = (xmin, ymin, xmax, ymax): the predicate of gpd.sjoin(tiles, roads) (statistical_analysis.py:170-171); touching counts.
+    True iff an edge of the polygon meets the rectangle, or the rectangle lies inside the polygon."""
+    x0, y0, x1, y1 = (F(float(v)) for v in rect)
+    edges = []
+    for ring in rings:
+        n = len(ring)
+        for k in range(n):
+            a, b = ring[k], ring[(k + 1) % n]
+            edges.append((F(float(a[0])), F(float(a[1])), F(float(b[0])), F(float(b[1]))))
+    for ax, ay, bx, by in edges:
+        # clip the segment a + t (b - a), t in [0, 1], against the four half-planes (Liang-Barsky, exact)
+        t0, t1 = F(0), F(1)
+        ok = True
+        for p, q in ((-(bx - ax), ax - x0), (bx - ax, x1 - ax), (-(by - ay), ay - y0), (by - ay, y1 - ay)):
+            if p == 0:
+                if q < 0:
+                    ok = False
+                    break
+            else:
+                r = q / p
+                if p < 0:
+                    t0 = max(t0, r)
+                else:
+                    t1 = min(t1, r)
+                if t0 > t1:
+                    ok = False
+                    break
+        if ok:
+            return True
+    # no edge meets the rectangle: it is wholly inside or wholly outside the polygon; test its lower-left corner (even-odd)
+    inside = False
+    for ax, ay, bx, by in edges:
+        if (ay <= y0) != (by <= y0):
+            xc = ax + (bx - ax) * (y0 - ay) / (by - ay)
+            if xc > x0:
+                inside = not inside
+    return inside

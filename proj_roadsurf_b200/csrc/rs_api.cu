@@ -714,6 +714,77 @@ int rs_pairs_bbox_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, co
     return finish(ctx);
 }
 
+int rs_pairs_bbox_grid_host(rs_ctx *ctx, const double *road_bbox, int32_t n_roads, const double *tile_ext, int32_t n_tiles,
+                            int32_t *road_pair_off, int32_t *pair_tile, int64_t capacity, int64_t *n_pairs)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_roads < 0 || n_tiles < 0 || !road_pair_off || !n_pairs) return RS_ERR_INVALID_ARG;
+    if ((n_roads > 0 && !road_bbox) || (n_tiles > 0 && !tile_ext)) return RS_ERR_INVALID_ARG;
+    *n_pairs = 0;
+    // uniform grid over the tiles: a cell is about one (mean) tile
+    double X0 = 0, Y0 = 0, X1 = 0, Y1 = 0, sw = 0, sh = 0;
+    int nv = 0;
+    for (int t = 0; t < n_tiles; t++) {
+        const double *e = tile_ext + 4 * (size_t)t;
+        if (!(e[0] <= e[2]) || !(e[1] <= e[3])) continue;
+        if (!nv) { X0 = e[0]; Y0 = e[1]; X1 = e[2]; Y1 = e[3]; }
+        X0 = e[0] < X0 ? e[0] : X0; Y0 = e[1] < Y0 ? e[1] : Y0;
+        X1 = e[2] > X1 ? e[2] : X1; Y1 = e[3] > Y1 ? e[3] : Y1;
+        sw += e[2] - e[0]; sh += e[3] - e[1];
+        nv++;
+    }
+    double cw = nv ? sw / nv : 1.0, ch = nv ? sh / nv : 1.0;
+    if (!(cw > 0.0)) cw = (X1 - X0) > 0.0 ? (X1 - X0) : 1.0;
+    if (!(ch > 0.0)) ch = (Y1 - Y0) > 0.0 ? (Y1 - Y0) : 1.0;
+    double fx = (X1 - X0) / cw + 1.0, fy = (Y1 - Y0) / ch + 1.0;
+    while (fx * fy > 4.0e6) { cw *= 1.5; ch *= 1.5; fx = (X1 - X0) / cw + 1.0; fy = (Y1 - Y0) / ch + 1.0; }
+    const int nx = (int)fx < 1 ? 1 : (int)fx, ny = (int)fy < 1 ? 1 : (int)fy;
+    const size_t R = (size_t)n_roads;
+    if ((rc = up(ctx, ctx->stage[0], road_bbox, sizeof(double) * 4 * R))) return rc;
+    if ((rc = up(ctx, ctx->stage[1], tile_ext, sizeof(double) * 4 * (size_t)n_tiles))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[3], sizeof(int32_t) * (R + 1)))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if ((rc = launch_pairs_grid(ctx, (const double *)ctx->stage[0].p, n_roads, (const double *)ctx->stage[1].p, n_tiles, X0, Y0, cw, ch, nx,
+                                ny, (int *)ctx->stage[3].p, nullptr, 0, 0, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(road_pair_off, ctx->stage[3].p, sizeof(int32_t) * (R + 1), cudaMemcpyDeviceToHost, st));
+    if ((rc = finish(ctx))) return rc;
+    const int64_t total = road_pair_off[n_roads];
+    *n_pairs = total;
+    if (!pair_tile || capacity < total || total == 0) return RS_OK;
+    if ((rc = ensure(ctx, ctx->stage[4], sizeof(int32_t) * (size_t)total))) return rc;
+    if ((rc = launch_pairs_grid(ctx, (const double *)ctx->stage[0].p, n_roads, (const double *)ctx->stage[1].p, n_tiles, X0, Y0, cw, ch, nx,
+                                ny, (int *)ctx->stage[3].p, (int *)ctx->stage[4].p, total, 1, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(pair_tile, ctx->stage[4].p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
+static int stage_polys(rs_ctx *ctx, const rs_roads *r, int base, rs_roads &d);
+
+int rs_pairs_intersect_host(rs_ctx *ctx, const rs_roads *roads, const double *tile_ext, int32_t n_tiles, const int32_t *road_pair_off,
+                            const int32_t *pair_tile, int32_t n_pairs, uint8_t *keep)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!roads || n_tiles < 0 || n_pairs < 0) return RS_ERR_INVALID_ARG;
+    if (n_pairs == 0) return RS_OK;
+    if (!tile_ext || !road_pair_off || !pair_tile || !keep) return RS_ERR_INVALID_ARG;
+    rs_roads dr;
+    if ((rc = stage_polys(ctx, roads, 0, dr))) return rc;
+    if ((rc = up(ctx, ctx->stage[4], tile_ext, sizeof(double) * 4 * (size_t)n_tiles))) return rc;
+    if ((rc = up(ctx, ctx->stage[5], road_pair_off, sizeof(int32_t) * ((size_t)roads->n_roads + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[6], pair_tile, sizeof(int32_t) * (size_t)n_pairs))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[7], (size_t)n_pairs))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if ((rc = launch_intersects(ctx, &dr, (const double *)ctx->stage[4].p, (const int *)ctx->stage[5].p, (const int *)ctx->stage[6].p,
+                                n_pairs, (uint8_t *)ctx->stage[7].p, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(keep, ctx->stage[7].p, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
 // stage one polygon set in stage[base .. base + 3] (xy, ring_off, road_ring_off, bbox)
 static int stage_polys(rs_ctx *ctx, const rs_roads *r, int base, rs_roads &d)
 {

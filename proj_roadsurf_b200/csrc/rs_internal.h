@@ -103,6 +103,11 @@ int launch_bin_counts(rs_ctx *ctx, const double *values, const int8_t *sel, cons
 int launch_overlay_area(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, const int *ring_poly_a, const int *ring_poly_b,
                         int8_t *sign_a, int8_t *sign_b, const int *pair_a, const int *pair_b, int n_pairs, double *area_pair,
                         double *area_a, cudaStream_t st);
+int launch_intersects(rs_ctx *ctx, const rs_roads *roads, const double *tile_ext_dev, const int *road_pair_off_dev,
+                      const int *pair_tile_dev, int n_pairs, uint8_t *keep_dev, cudaStream_t st);
+int launch_pairs_grid(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, int n_tiles, double X0, double Y0,
+                      double cw, double ch, int nx, int ny, int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase,
+                      cudaStream_t st);
 int launch_within(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *out, cudaStream_t st);
 int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, const rs_lattice *lat, const int *lut_dev,
                       int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "rs_internal.h"
@@ -419,6 +420,218 @@ int launch_overlay_area(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, const
         const long long blocks = ((long long)n_pairs * 32 + 127) / 128;
         if (blocks > 0x7fffffffLL) return RS_ERR_UNSUPPORTED;
         overlay_area_kernel<<<(unsigned)blocks, 128, 0, st>>>(A, sign_a, B, sign_b, pair_a, pair_b, n_pairs, area_pair);
+        ctx->launches++;
+    }
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact reject of the broad phase: gpd.sjoin(tiles, roads) keeps a (tile, road) pair when the geometries INTERSECT
+// (scripts/statistical_analysis/statistical_analysis.py:170-171), the bounding-box broad phase keeps a superset.
+// One warp per candidate pair; the road (all rings, even-odd) intersects the closed tile rectangle iff
+//   an edge of the road touches the rectangle (an endpoint inside it, or -- separating axes of a segment and a box -- the
+//   boxes overlap and the rectangle's corners are not strictly on one side of the edge's line), or
+//   the rectangle lies inside the road: no edge touches it and one corner is inside (crossing parity over all edges).
+// Binary64 orientation signs: can differ from GEOS only for contacts within rounding distance.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(128) intersects_kernel(const PolySet S, const double *__restrict__ tile_ext,
+                                                         const int *__restrict__ road_pair_off, const int *__restrict__ pair_tile,
+                                                         int n_pairs, uint8_t *__restrict__ keep)
+{
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n_pairs) return;
+    int lo = 0, hi = S.n;                        // largest road with road_pair_off[road] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(road_pair_off + mid) <= p) lo = mid;
+        else hi = mid;
+    }
+    const int road = lo;
+    const double *e = tile_ext + 4 * (size_t)pair_tile[p];
+    const double x0 = e[0], y0 = e[1], x1 = e[2], y1 = e[3];
+    const int g0 = S.road_ring_off[road], g1 = S.road_ring_off[road + 1];
+    bool hit = false;
+    int parity = 0;                              // of the corner (x0, y0)
+    for (int g = g0; g < g1 && !__any_sync(0xffffffffu, hit); g++) {
+        const int v0 = S.ring_off[g], v1 = S.ring_off[g + 1];
+        for (int base = v0; base < v1 && !__any_sync(0xffffffffu, hit); base += 32) {
+            const int k = base + lane;
+            if (k < v1) {
+                const double2 a = S.xy[k], b = S.xy[k + 1 < v1 ? k + 1 : v0];
+                const bool a_in = a.x >= x0 && a.x <= x1 && a.y >= y0 && a.y <= y1;
+                if (a_in) hit = true;
+                else if (fmin(a.x, b.x) <= x1 && fmax(a.x, b.x) >= x0 && fmin(a.y, b.y) <= y1 && fmax(a.y, b.y) >= y0 &&
+                         !(a.x == b.x && a.y == b.y)) {
+                    const double o1 = orient(a, b, make_double2(x0, y0)), o2 = orient(a, b, make_double2(x1, y0));
+                    const double o3 = orient(a, b, make_double2(x1, y1)), o4 = orient(a, b, make_double2(x0, y1));
+                    if (!((o1 > 0.0 && o2 > 0.0 && o3 > 0.0 && o4 > 0.0) || (o1 < 0.0 && o2 < 0.0 && o3 < 0.0 && o4 < 0.0))) hit = true;
+                }
+                if ((a.y <= y0) != (b.y <= y0)) {                 // the edge spans the horizontal line through the corner
+                    const double o = orient(a, b, make_double2(x0, y0));
+                    if ((o > 0.0) == (b.y > a.y)) parity ^= 1;
+                }
+            }
+        }
+    }
+    hit = __any_sync(0xffffffffu, hit);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) parity ^= __shfl_xor_sync(0xffffffffu, parity, o);
+    if (lane == 0) keep[p] = (hit || (parity & 1)) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// broad phase for tiles that are NOT on a lattice: the tiles are binned into a uniform grid (cell ~ a tile), sorted by
+// cell, and every road looks up the cells under its bounding box.  A (road, tile) pair is reported from exactly one cell, the
+// one holding the lower-left corner of the intersection of the two boxes.
+// ---------------------------------------------------------------------------------------------
+struct GridArgs {
+    double X0, Y0, cw, ch;
+    int nx, ny;
+};
+
+__device__ __forceinline__ int cell_of(double v, double o, double c, int n)
+{
+    const double f = floor((v - o) / c);
+    return f < 0.0 ? 0 : (f > (double)(n - 1) ? n - 1 : (int)f);
+}
+
+__global__ void __launch_bounds__(256) grid_tile_kernel(const GridArgs G, const double *__restrict__ ext, int n_tiles,
+                                                        const unsigned long long *__restrict__ off, int *__restrict__ cnt,
+                                                        int *__restrict__ keys, int *__restrict__ vals)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const double *e = ext + 4 * (size_t)t;
+    if (!(e[0] <= e[2]) || !(e[1] <= e[3])) { if (cnt) cnt[t] = 0; return; }
+    const int ix0 = cell_of(e[0], G.X0, G.cw, G.nx), ix1 = cell_of(e[2], G.X0, G.cw, G.nx);
+    const int iy0 = cell_of(e[1], G.Y0, G.ch, G.ny), iy1 = cell_of(e[3], G.Y0, G.ch, G.ny);
+    if (cnt) { cnt[t] = (ix1 - ix0 + 1) * (iy1 - iy0 + 1); return; }
+    unsigned long long k = off[t];
+    for (int iy = iy0; iy <= iy1; iy++)
+        for (int ix = ix0; ix <= ix1; ix++, k++) { keys[k] = iy * G.nx + ix; vals[k] = t; }
+}
+
+__global__ void __launch_bounds__(256) grid_cell_start_kernel(const int *__restrict__ keys, long long n_entries, int n_cells,
+                                                              int *__restrict__ start)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cells) return;
+    long long lo = 0, hi = n_entries;            // first entry with key >= c
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (keys[mid] < c) lo = mid + 1;
+        else hi = mid;
+    }
+    start[c] = (int)lo;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) grid_road_kernel(const GridArgs G, const double *__restrict__ bbox, int n_roads,
+                                                        const double *__restrict__ ext, const int *__restrict__ start,
+                                                        const int *__restrict__ vals, int *__restrict__ cnt,
+                                                        const int *__restrict__ off, long long capacity, int *__restrict__ pair_tile)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_roads) return;
+    const double *b = bbox + 4 * (size_t)r;
+    int c = 0;
+    if ((b[0] <= b[2]) && (b[1] <= b[3])) {
+        const int ix0 = cell_of(b[0], G.X0, G.cw, G.nx), ix1 = cell_of(b[2], G.X0, G.cw, G.nx);
+        const int iy0 = cell_of(b[1], G.Y0, G.ch, G.ny), iy1 = cell_of(b[3], G.Y0, G.ch, G.ny);
+        const long long base = WRITE ? off[r] : 0;
+        for (int iy = iy0; iy <= iy1; iy++)
+            for (int ix = ix0; ix <= ix1; ix++) {
+                const int cell = iy * G.nx + ix;
+                for (int k = start[cell]; k < start[cell + 1]; k++) {
+                    const int t = vals[k];
+                    const double *e = ext + 4 * (size_t)t;
+                    if (!(b[0] <= e[2] && b[2] >= e[0] && b[1] <= e[3] && b[3] >= e[1])) continue;
+                    // reported once: from the cell of the lower-left corner of the boxes' intersection
+                    if (cell_of(fmax(b[0], e[0]), G.X0, G.cw, G.nx) != ix || cell_of(fmax(b[1], e[1]), G.Y0, G.ch, G.ny) != iy) continue;
+                    if (WRITE && base + c < capacity) {
+                        int j = c - 1;                         // keep the road's tiles sorted by index
+                        while (j >= 0 && pair_tile[base + j] > t) { pair_tile[base + j + 1] = pair_tile[base + j]; j--; }
+                        pair_tile[base + j + 1] = t;
+                    }
+                    c++;
+                }
+            }
+    }
+    if (!WRITE) cnt[r] = c;
+}
+
+}  // namespace
+
+int launch_intersects(rs_ctx *ctx, const rs_roads *roads, const double *tile_ext_dev, const int *road_pair_off_dev,
+                      const int *pair_tile_dev, int n_pairs, uint8_t *keep_dev, cudaStream_t st)
+{
+    if (n_pairs <= 0) return RS_OK;
+    PolySet S{(const double2 *)roads->xy, roads->ring_off, roads->road_ring_off, roads->road_bbox, roads->n_roads};
+    const long long blocks = ((long long)n_pairs * 32 + 127) / 128;
+    if (blocks > 0x7fffffffLL) return RS_ERR_UNSUPPORTED;
+    intersects_kernel<<<(unsigned)blocks, 128, 0, st>>>(S, tile_ext_dev, road_pair_off_dev, pair_tile_dev, n_pairs, keep_dev);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+// phase 0: bins the tiles (stage[12..15], wide_tmp), counts per road -> road_pair_off_dev (exclusive scan, [n_roads] = total);
+// phase 1: writes pair_tile_dev.  The grid is rebuilt in both phases (the call protocol is stateless).
+int launch_pairs_grid(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, int n_tiles, double X0, double Y0,
+                      double cw, double ch, int nx, int ny, int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase,
+                      cudaStream_t st)
+{
+    GridArgs G{X0, Y0, cw, ch, nx, ny};
+    const int n_cells = nx * ny;
+    int rc;
+    if ((rc = ensure(ctx, ctx->stage[12], sizeof(int) * ((size_t)(n_tiles > n_roads ? n_tiles : n_roads) + 1)))) return rc;   // counts
+    if ((rc = ensure(ctx, ctx->stage[13], sizeof(unsigned long long) * ((size_t)n_tiles + 1)))) return rc;                   // tile offsets
+    if ((rc = ensure(ctx, ctx->stage[14], sizeof(int) * ((size_t)n_cells + 2)))) return rc;                                   // cell starts
+    int *cnt = (int *)ctx->stage[12].p, *start = (int *)ctx->stage[14].p;
+    unsigned long long *toff = (unsigned long long *)ctx->stage[13].p;
+    long long n_entries = 0;
+    if (n_tiles > 0) {
+        grid_tile_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(G, ext_dev, n_tiles, nullptr, cnt, nullptr, nullptr);
+        ctx->launches++;
+        if ((rc = launch_fstats_offsets(ctx, (const uint32_t *)cnt, n_tiles, toff, st))) return rc;
+        unsigned long long tot = 0;
+        RS_CUDA_OK(ctx, cudaMemcpyAsync(&tot, toff + n_tiles, sizeof(tot), cudaMemcpyDeviceToHost, st));
+        RS_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        if (tot > 0x7fffffffull) return RS_ERR_UNSUPPORTED;
+        n_entries = (long long)tot;
+    }
+    if ((rc = ensure(ctx, ctx->stage[15], sizeof(int) * 4 * ((size_t)n_entries + 1)))) return rc;    // keys | vals | sorted keys | sorted vals
+    int *keys = (int *)ctx->stage[15].p, *vals = keys + n_entries, *skeys = vals + n_entries, *svals = skeys + n_entries;
+    if (n_entries > 0) {
+        grid_tile_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(G, ext_dev, n_tiles, toff, nullptr, keys, vals);
+        ctx->launches++;
+        size_t tmp = 0;
+        RS_CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys, skeys, vals, svals, (int)n_entries, 0, 32, st));
+        if ((rc = ensure(ctx, ctx->wide_tmp, tmp))) return rc;
+        RS_CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(ctx->wide_tmp.p, tmp, keys, skeys, vals, svals, (int)n_entries, 0, 32, st));
+        ctx->launches++;
+    }
+    grid_cell_start_kernel<<<(n_cells + 256) / 256, 256, 0, st>>>(skeys, n_entries, n_cells, start);
+    ctx->launches++;
+    if (n_roads > 0) {
+        if (phase == 0) {
+            grid_road_kernel<false><<<(n_roads + 255) / 256, 256, 0, st>>>(G, bbox_dev, n_roads, ext_dev, start, svals, cnt, nullptr, 0, nullptr);
+            ctx->launches++;
+            size_t tmp = 0;
+            RS_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, road_pair_off_dev, n_roads, st));
+            if ((rc = ensure(ctx, ctx->wide_tmp, tmp))) return rc;
+            RS_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->wide_tmp.p, tmp, cnt, road_pair_off_dev, n_roads, st));
+        } else {
+            grid_road_kernel<true><<<(n_roads + 255) / 256, 256, 0, st>>>(G, bbox_dev, n_roads, ext_dev, start, svals, nullptr, road_pair_off_dev,
+                                                                          capacity, pair_tile_dev);
+            ctx->launches++;
+        }
+    }
+    if (phase == 0) {
+        pairs_total_kernel<<<1, 32, 0, st>>>(cnt, road_pair_off_dev, n_roads);
         ctx->launches++;
     }
     RS_CUDA_OK(ctx, cudaGetLastError());

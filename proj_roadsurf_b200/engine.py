@@ -321,6 +321,41 @@ class Engine:
             N.check(st, "rs_pairs_bbox_host", self._ctx)
         return PairList(off, pt)
 
+    def pairs_bbox_grid_host(self, roads: RoadSet, tiles: TileBatch) -> PairList:
+        """GPU broad phase for tiles that are not on a lattice (rs_pairs_bbox_grid_host): uniform-grid binning on the device."""
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        ext = np.ascontiguousarray(tiles.extents(), np.float64)
+        R = roads.n_roads
+        off = np.zeros(R + 1, np.int32)
+        total = C.c_int64(0)
+        st = self.lib.rs_pairs_bbox_grid_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), tiles.n_tiles, _np_ptr(off), None, 0, C.byref(total))
+        N.check(st, "rs_pairs_bbox_grid_host", self._ctx)
+        pt = np.zeros(int(total.value), np.int32)
+        if total.value:
+            st = self.lib.rs_pairs_bbox_grid_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), tiles.n_tiles, _np_ptr(off), _np_ptr(pt),
+                                                  int(total.value), C.byref(total))
+            N.check(st, "rs_pairs_bbox_grid_host", self._ctx)
+        return PairList(off, pt)
+
+    def pairs_intersect_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList) -> PairList:
+        """Exact reject (rs_pairs_intersect_host): the pairs whose road polygon intersects the tile rectangle -- the pair table
+        gpd.sjoin(tiles, roads) gives (statistical_analysis.py:170-171)."""
+        if pairs.n_pairs == 0:
+            return pairs
+        xy = np.ascontiguousarray(roads.xy, np.float64)
+        ro, rro = np.ascontiguousarray(roads.ring_off, np.int32), np.ascontiguousarray(roads.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), roads.n_roads, roads.n_rings, roads.n_verts)
+        ext = np.ascontiguousarray(tiles.extents(), np.float64)
+        rpo, pt = np.ascontiguousarray(pairs.road_pair_off, np.int32), np.ascontiguousarray(pairs.pair_tile, np.int32)
+        keep = np.zeros(pairs.n_pairs, np.uint8)
+        st = self.lib.rs_pairs_intersect_host(self._ctx, C.byref(rd), _np_ptr(ext), tiles.n_tiles, _np_ptr(rpo), _np_ptr(pt), pairs.n_pairs,
+                                              _np_ptr(keep))
+        N.check(st, "rs_pairs_intersect_host", self._ctx)
+        k = keep.astype(bool)
+        csum = np.concatenate([[0], np.cumsum(k)])
+        return PairList(csum[rpo.astype(np.int64)].astype(np.int32), np.ascontiguousarray(pt[k]))
+
     def rescale_u16_host(self, src: np.ndarray, smin: Sequence[float], smax: Sequence[float], bidx: Optional[Sequence[int]] = None,
                          f32: bool = False) -> np.ndarray:
         """gdal.Translate -scale smin smax 0 255 -ot Byte per OUTPUT band (tif2cog.py:260-270): src (..., C_in) uint16 ->

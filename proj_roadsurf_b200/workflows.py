@@ -17,17 +17,16 @@ import pandas as pd
 
 from .engine import default_engine
 from .functions import fct_statistics
-from .geometry import PairList, RoadSet, TileBatch, lattice_of, pairs_by_bbox
+from .geometry import PairList, RoadSet, TileBatch, lattice_of
 from .road_segmentation import determine_class, final_metrics
 
 
-def pair_list(roads: RoadSet, tiles: TileBatch, engine=None) -> PairList:
-    """gpd.sjoin(tiles, roads) + drop_duplicates (statistical_analysis.py:170-171): GPU broad phase on tile lattices,
-    host broad phase for irregular tile sets."""
+def pair_list(roads: RoadSet, tiles: TileBatch, engine=None, exact: bool = True) -> PairList:
+    """gpd.sjoin(tiles, roads) + drop_duplicates (statistical_analysis.py:170-171) on the GPU: bounding-box broad phase (lattice
+    look-up for XYZ tile sets, uniform-grid binning for any other tile set), then the exact 'intersects' reject."""
     eng = engine or default_engine()
-    if lattice_of(tiles) is not None:
-        return eng.pairs_bbox_host(roads, tiles)
-    return pairs_by_bbox(roads, tiles)
+    pairs = eng.pairs_bbox_host(roads, tiles) if lattice_of(tiles) is not None else eng.pairs_bbox_grid_host(roads, tiles)
+    return eng.pairs_intersect_host(roads, tiles, pairs) if exact else pairs
 
 
 def road_band_statistics(roads: RoadSet, tiles: TileBatch, pairs: Optional[PairList] = None, BANDS: Sequence[int] = (1, 2, 3),

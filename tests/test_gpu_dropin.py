@@ -836,3 +836,70 @@ def test_zonal_stats_float_dem_like_rasterstats(mods):
     assert g16 == e16
     with pytest.raises(TypeError):
         fr.zonal_stats(vectors[:1], dem.astype(np.float64), affine=affine, nodata=-9999)
+
+
+def test_exact_intersects_reject_and_grid_broad_phase():
+    """f1: the exact 'intersects' reject of the bounding-box pairs (gpd.sjoin's predicate, statistical_analysis.py:170-171) against
+    an exact rational oracle, and the GPU broad phase for tile sets that are not on a lattice against the brute-force host one."""
+    from oracle import overlay as ov
+    from proj_roadsurf_b200.engine import default_engine
+    from proj_roadsurf_b200.geometry import pairs_by_bbox
+    from test_oracle_kat import ring
+    eng = default_engine()
+    g = synth.Grid(7, 6)
+    rr = synth.ribbon_roads(g, 70, seed=41)
+    tb = TileBatch.from_arrays(np.zeros((g.n_tiles, 4, 4, 1), np.uint8), g.transforms() * np.array([64.0, 1, 1, 1, 64.0, 1]))   # 4 px tiles, same extents
+    ext = tb.extents()
+    # hand cases on tile 0: a polygon that contains the tile, one whose hole contains the tile, one touching it at a corner,
+    # one touching along an edge, one near-miss, one inside the tile
+    x0, y0, x1, y1 = ext[0]
+    d = x1 - x0
+    hand = [[ring((x0 - d, y0 - d), (x1 + d, y0 - d), (x1 + d, y1 + d), (x0 - d, y1 + d))],
+            [ring((x0 - 2 * d, y0 - 2 * d), (x1 + 2 * d, y0 - 2 * d), (x1 + 2 * d, y1 + 2 * d), (x0 - 2 * d, y1 + 2 * d)),
+             ring((x0 - d, y0 - d), (x0 - d, y1 + d), (x1 + d, y1 + d), (x1 + d, y0 - d))],
+            [ring((x0 - d, y0 - d), (x0, y0), (x0 - d, y0))],
+            [ring((x0 - d, y0), (x0 - d, y1), (x0, y1), (x0, y0))],
+            [ring((x0 - d, y0 - d), (x0 - 1e-6 * d, y0 - 1e-6 * d), (x0 - d, y0 - 1e-6 * d))],
+            [ring((x0 + 0.3 * d, y0 + 0.3 * d), (x0 + 0.6 * d, y0 + 0.3 * d), (x0 + 0.5 * d, y0 + 0.7 * d))]]
+    geoms = [rr.roads.rings(r) for r in range(rr.roads.n_roads)] + hand
+    roads = RoadSet.from_geometries(geoms)
+    cand = pairs_by_bbox(roads, tb)
+    kept = eng.pairs_intersect_host(roads, tb, cand)
+    road_of = cand.road_of_pair()
+    exp = np.array([ov.polygon_intersects_rect(geoms[r], ext[t]) for r, t in zip(road_of, cand.pair_tile)])
+    got = np.zeros(cand.n_pairs, bool)
+    kept_set = set(zip(kept.road_of_pair().tolist(), kept.pair_tile.tolist()))
+    for i, (r, t) in enumerate(zip(road_of.tolist(), cand.pair_tile.tolist())):
+        got[i] = (r, t) in kept_set
+    assert np.array_equal(got, exp), np.nonzero(got != exp)[0][:10]
+    assert 0 < exp.sum() < len(exp)                                       # the reject removes pairs, and keeps some
+    n_r = rr.roads.n_roads
+    hand_rows = {(r - n_r, t) for r, t in kept_set if r >= n_r and t == 0}
+    assert hand_rows == {(0, 0), (2, 0), (3, 0), (5, 0)}                   # contains / corner touch / edge touch / inside: yes
+    # rejected pairs hold no pixel: statistics through either list agree
+    tiles = synth.host_tiles(g, 3)
+    tb2 = TileBatch.from_arrays(tiles, g.transforms())
+    c2 = pairs_by_bbox(rr.roads, tb2)
+    k2 = eng.pairs_intersect_host(rr.roads, tb2, c2)
+    assert k2.n_pairs < c2.n_pairs
+    h_all, z_all = eng.zonal_hist_host(rr.roads, tb2, c2)
+    h_kept, z_kept = eng.zonal_hist_host(rr.roads, tb2, k2)
+    assert np.array_equal(h_all, h_kept) and np.array_equal(z_all, z_kept)
+
+    # ---- tiles that are not on a lattice: random rectangles of very different sizes, shuffled, some degenerate ----
+    rng = np.random.default_rng(8)
+    T = 600
+    cx, cy = rng.uniform(0, 1000, T), rng.uniform(0, 700, T)
+    w, h = rng.uniform(2, 90, T), rng.uniform(2, 60, T)
+    gt = np.stack([w / 4, np.zeros(T), cx, np.zeros(T), -h / 4, cy + h], 1)         # 4 x 4 px rasters of those extents
+    tb3 = TileBatch.from_arrays(np.zeros((T, 4, 4, 1), np.uint8), gt)
+    boxes = []
+    for _ in range(400):
+        bx, by = rng.uniform(-50, 1050), rng.uniform(-50, 750)
+        bw, bh = rng.uniform(0.0, 120), rng.uniform(0.0, 120)
+        boxes.append([ring((bx, by), (bx + bw, by), (bx + bw, by + bh), (bx, by + bh))])
+    r3 = RoadSet.from_geometries(boxes)
+    got3 = eng.pairs_bbox_grid_host(r3, tb3)
+    exp3 = pairs_by_bbox(r3, tb3)
+    assert np.array_equal(got3.road_pair_off, exp3.road_pair_off) and np.array_equal(got3.pair_tile, exp3.pair_tile)
+    assert exp3.n_pairs > 1000
