@@ -394,6 +394,19 @@ int rs_pairs_intersect_host(rs_ctx *ctx, const rs_roads *roads, const double *ti
                             const int32_t *road_pair_off, const int32_t *pair_tile, int32_t n_pairs, uint8_t *keep);
 
 /*
+ * clip_labels (scripts/road_segmentation/determine_class.py:62-95): the rings of label pair_label[p] clipped to the closed
+ * rectangle rect[p] = (xmin, ymin, xmax, ymax) -- the tile scaled by 0.99 about its centre -- for every pair of the
+ * labels x tiles 'intersects' join (rs_pairs_bbox_* + rs_pairs_intersect_host).  A pair-ring is ring k of the label of pair p,
+ * numbered pair_ring_off[p] + k (pair_ring_off int64[n_pairs + 1], the prefix sum of the labels' ring counts).  Two calls:
+ *   xy_out == NULL   ring_count[q] = vertices of the clipped pair-ring q, closed (0 when it misses the rectangle);
+ *   xy_out != NULL   the clipped rings written at xy_out[ring_vert_off[q]] (ring_vert_off int64[n_pair_rings], from ring_count).
+ * Re-entrant Sutherland-Hodgman: parts of a concave ring that leave and re-enter the rectangle stay joined by zero-width runs
+ * along its edge (no area under the even-odd rule); GEOS returns them as separate parts -- same point set, same areas.
+ */
+int rs_clip_rings_host(rs_ctx *ctx, const rs_roads *labels, const int32_t *pair_label, const double *rect, int32_t n_pairs,
+                       const int64_t *pair_ring_off, int32_t *ring_count, const int64_t *ring_vert_off, double *xy_out);
+
+/*
  * Two-sample Kolmogorov-Smirnov statistic of every road's pixel values on one band against a reference distribution,
  * from histograms: scipy.stats.kstest(road_values, general_values) of statistical_analysis.py:441-451 (the pixels of the
  * road against all pixels of its road type).  hist uint32[n_roads][256] (one band), ref_hist uint64[n_refs][256],

@@ -785,6 +785,43 @@ int rs_pairs_intersect_host(rs_ctx *ctx, const rs_roads *roads, const double *ti
     return finish(ctx);
 }
 
+int rs_clip_rings_host(rs_ctx *ctx, const rs_roads *labels, const int32_t *pair_label, const double *rect, int32_t n_pairs,
+                       const int64_t *pair_ring_off, int32_t *ring_count, const int64_t *ring_vert_off, double *xy_out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!labels || n_pairs < 0) return RS_ERR_INVALID_ARG;
+    if (n_pairs == 0) return RS_OK;
+    if (!pair_label || !rect || !pair_ring_off || !ring_count) return RS_ERR_INVALID_ARG;
+    if ((xy_out != nullptr) != (ring_vert_off != nullptr)) return RS_ERR_INVALID_ARG;
+    const int64_t nq = pair_ring_off[n_pairs];
+    if (nq < 0) return RS_ERR_INVALID_ARG;
+    if (nq == 0) return RS_OK;
+    rs_roads dl;
+    if ((rc = stage_polys(ctx, labels, 0, dl))) return rc;
+    if ((rc = up(ctx, ctx->stage[4], pair_label, sizeof(int32_t) * (size_t)n_pairs))) return rc;
+    if ((rc = up(ctx, ctx->stage[5], rect, sizeof(double) * 4 * (size_t)n_pairs))) return rc;
+    if ((rc = up(ctx, ctx->stage[6], pair_ring_off, sizeof(int64_t) * ((size_t)n_pairs + 1)))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if (!xy_out) {
+        if ((rc = ensure(ctx, ctx->stage[7], sizeof(int32_t) * (size_t)nq))) return rc;
+        if ((rc = launch_clip_rings(ctx, &dl, (const int *)ctx->stage[4].p, (const double *)ctx->stage[5].p, (const long long *)ctx->stage[6].p,
+                                    n_pairs, nq, (int *)ctx->stage[7].p, nullptr, nullptr, st)))
+            return rc;
+        RS_CUDA_OK(ctx, cudaMemcpyAsync(ring_count, ctx->stage[7].p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+        return finish(ctx);
+    }
+    int64_t total = 0;
+    for (int64_t q = 0; q < nq; q++) total = ring_vert_off[q] + ring_count[q] > total ? ring_vert_off[q] + ring_count[q] : total;
+    if ((rc = up(ctx, ctx->stage[8], ring_vert_off, sizeof(int64_t) * (size_t)nq))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[9], sizeof(double) * 2 * (size_t)total))) return rc;
+    if ((rc = launch_clip_rings(ctx, &dl, (const int *)ctx->stage[4].p, (const double *)ctx->stage[5].p, (const long long *)ctx->stage[6].p,
+                                n_pairs, nq, nullptr, (const long long *)ctx->stage[8].p, (double *)ctx->stage[9].p, st)))
+        return rc;
+    if (total > 0) RS_CUDA_OK(ctx, cudaMemcpyAsync(xy_out, ctx->stage[9].p, sizeof(double) * 2 * (size_t)total, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
 // stage one polygon set in stage[base .. base + 3] (xy, ring_off, road_ring_off, bbox)
 static int stage_polys(rs_ctx *ctx, const rs_roads *r, int base, rs_roads &d)
 {

@@ -108,6 +108,9 @@ int launch_intersects(rs_ctx *ctx, const rs_roads *roads, const double *tile_ext
 int launch_pairs_grid(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, int n_tiles, double X0, double Y0,
                       double cw, double ch, int nx, int ny, int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase,
                       cudaStream_t st);
+int launch_clip_rings(rs_ctx *ctx, const rs_roads *labels, const int *pair_label, const double *rect, const long long *pair_ring_off,
+                      int n_pairs, long long n_pair_rings, int *ring_count, const long long *ring_vert_off, double *xy_out,
+                      cudaStream_t st);
 int launch_within(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *out, cudaStream_t st);
 int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, const rs_lattice *lat, const int *lut_dev,
                       int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);

@@ -638,4 +638,131 @@ int launch_pairs_grid(rs_ctx *ctx, const double *bbox_dev, int n_roads, const do
     return RS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// clip_labels: scripts/road_segmentation/determine_class.py:62-95 -- every label cut to every tile it intersects, the tile
+// scaled by 0.99 about its centre (old_geo.intersection(scale(tile, 0.99, 0.99))).  One thread per (pair, ring): the
+// re-entrant Sutherland-Hodgman pipeline (four half-plane stages, each keeping only its first and previous point) streams the
+// ring's vertices through the rectangle without intermediate buffers; a count pass sizes the output, a write pass fills it.
+// Pieces of a concave ring that leave and re-enter the rectangle stay connected by zero-width runs along its edge, which carry
+// no area under the even-odd rule (GEOS returns them as separate parts: same point set, same areas, same raster).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct ClipStage {
+    double2 first, prev;
+    bool has;
+};
+
+struct ClipSink {
+    double2 *out;        // nullptr: count only
+    int n;
+    double2 first;
+    __device__ __forceinline__ void put(double2 p)
+    {
+        if (n == 0) first = p;
+        if (out) out[n] = p;
+        n++;
+    }
+};
+
+__device__ __forceinline__ bool clip_inside(int st, double2 p, const double *r)
+{
+    return st == 0 ? p.x >= r[0] : st == 1 ? p.x <= r[2] : st == 2 ? p.y >= r[1] : p.y <= r[3];
+}
+
+// the point where the edge p -> q meets the boundary line of stage st (same expression as the host clip: t along p -> q, the
+// clipped coordinate set to the bound exactly)
+__device__ __forceinline__ double2 clip_cross(int st, double2 p, double2 q, const double *r)
+{
+    const double bound = st == 0 ? r[0] : st == 1 ? r[2] : st == 2 ? r[1] : r[3];
+    double2 c;
+    if (st < 2) {
+        const double t = __ddiv_rn(__dsub_rn(bound, p.x), __dsub_rn(q.x, p.x));
+        c.x = bound;
+        c.y = __dadd_rn(p.y, __dmul_rn(t, __dsub_rn(q.y, p.y)));
+    } else {
+        const double t = __ddiv_rn(__dsub_rn(bound, p.y), __dsub_rn(q.y, p.y));
+        c.x = __dadd_rn(p.x, __dmul_rn(t, __dsub_rn(q.x, p.x)));
+        c.y = bound;
+    }
+    return c;
+}
+
+__device__ void clip_feed(ClipStage *stg, int st, double2 p, const double *r, ClipSink &sink)
+{
+    // iterative form of the re-entrant pipeline: a point entering stage st may release up to two points into stage st + 1
+    double2 queue[16];
+    int qst[16], qn = 0;
+    queue[qn] = p; qst[qn++] = st;
+    while (qn > 0) {
+        const double2 v = queue[--qn];
+        const int s_ = qst[qn];
+        if (s_ == 4) { sink.put(v); continue; }
+        ClipStage &g = stg[s_];
+        const bool vin = clip_inside(s_, v, r);
+        double2 rel[2];
+        int nr = 0;
+        if (!g.has) { g.first = v; g.has = true; }
+        else if (clip_inside(s_, g.prev, r) != vin) rel[nr++] = clip_cross(s_, g.prev, v, r);
+        g.prev = v;
+        if (vin) rel[nr++] = v;
+        for (int k = nr - 1; k >= 0; k--) { queue[qn] = rel[k]; qst[qn++] = s_ + 1; }      // LIFO: push in reverse to keep the order
+    }
+}
+
+__global__ void __launch_bounds__(128) clip_rings_kernel(const PolySet S, const int *__restrict__ pair_label, const double *__restrict__ rect,
+                                                         const long long *__restrict__ pair_ring_off, int n_pairs, long long n_pair_rings,
+                                                         int *__restrict__ ring_count, const long long *__restrict__ ring_vert_off,
+                                                         double2 *__restrict__ xy_out)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pair_rings) return;
+    int lo = 0, hi = n_pairs;                    // largest pair with pair_ring_off[pair] <= q
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pair_ring_off[mid] <= q) lo = mid;
+        else hi = mid;
+    }
+    const int pair = lo, label = pair_label[pair];
+    const int g = S.road_ring_off[label] + (int)(q - pair_ring_off[pair]);
+    const double *r = rect + 4 * (size_t)pair;
+    int v0 = S.ring_off[g], v1 = S.ring_off[g + 1];
+    if (v1 - v0 > 1 && S.xy[v0].x == S.xy[v1 - 1].x && S.xy[v0].y == S.xy[v1 - 1].y) v1--;      // closed ring: the repeat is dropped
+    ClipStage stg[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) stg[k].has = false;
+    ClipSink sink{xy_out ? xy_out + ring_vert_off[q] : nullptr, 0, make_double2(0.0, 0.0)};
+    for (int k = v0; k < v1; k++) clip_feed(stg, 0, S.xy[k], r, sink);
+    // close the stages in order: the edge from a stage's last point back to its first one
+    for (int st = 0; st < 4; st++) {
+        ClipStage &gs = stg[st];
+        if (!gs.has) continue;
+        if (clip_inside(st, gs.prev, r) != clip_inside(st, gs.first, r)) {
+            const double2 c = clip_cross(st, gs.prev, gs.first, r);
+            if (st == 3) sink.put(c);
+            else clip_feed(stg, st + 1, c, r, sink);
+        }
+    }
+    if (sink.n >= 3) sink.put(sink.first);       // closed, like shapely's rings
+    else sink.n = 0;                             // fewer than three points: the ring misses the rectangle
+    if (!xy_out) ring_count[q] = sink.n;
+}
+
+}  // namespace
+
+int launch_clip_rings(rs_ctx *ctx, const rs_roads *labels, const int *pair_label, const double *rect, const long long *pair_ring_off,
+                      int n_pairs, long long n_pair_rings, int *ring_count, const long long *ring_vert_off, double *xy_out,
+                      cudaStream_t st)
+{
+    if (n_pair_rings <= 0) return RS_OK;
+    PolySet S{(const double2 *)labels->xy, labels->ring_off, labels->road_ring_off, labels->road_bbox, labels->n_roads};
+    const long long blocks = (n_pair_rings + 127) / 128;
+    if (blocks > 0x7fffffffLL) return RS_ERR_UNSUPPORTED;
+    clip_rings_kernel<<<(unsigned)blocks, 128, 0, st>>>(S, pair_label, rect, pair_ring_off, n_pairs, n_pair_rings, ring_count,
+                                                       ring_vert_off, (double2 *)xy_out);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
 }  // namespace rs

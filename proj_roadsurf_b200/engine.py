@@ -321,40 +321,74 @@ class Engine:
             N.check(st, "rs_pairs_bbox_host", self._ctx)
         return PairList(off, pt)
 
-    def pairs_bbox_grid_host(self, roads: RoadSet, tiles: TileBatch) -> PairList:
-        """GPU broad phase for tiles that are not on a lattice (rs_pairs_bbox_grid_host): uniform-grid binning on the device."""
+    def pairs_bbox_grid_host(self, roads: RoadSet, tiles) -> PairList:
+        """GPU broad phase for tiles that are not on a lattice (rs_pairs_bbox_grid_host): uniform-grid binning on the device.
+        ``tiles``: a TileBatch, or an (T, 4) array of extents (xmin, ymin, xmax, ymax)."""
         bb = np.ascontiguousarray(roads.bbox, np.float64)
-        ext = np.ascontiguousarray(tiles.extents(), np.float64)
+        ext = np.ascontiguousarray(tiles.extents() if hasattr(tiles, "extents") else tiles, np.float64).reshape(-1, 4)
+        n_tiles = len(ext)
         R = roads.n_roads
         off = np.zeros(R + 1, np.int32)
         total = C.c_int64(0)
-        st = self.lib.rs_pairs_bbox_grid_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), tiles.n_tiles, _np_ptr(off), None, 0, C.byref(total))
+        st = self.lib.rs_pairs_bbox_grid_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), n_tiles, _np_ptr(off), None, 0, C.byref(total))
         N.check(st, "rs_pairs_bbox_grid_host", self._ctx)
         pt = np.zeros(int(total.value), np.int32)
         if total.value:
-            st = self.lib.rs_pairs_bbox_grid_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), tiles.n_tiles, _np_ptr(off), _np_ptr(pt),
+            st = self.lib.rs_pairs_bbox_grid_host(self._ctx, _np_ptr(bb), R, _np_ptr(ext), n_tiles, _np_ptr(off), _np_ptr(pt),
                                                   int(total.value), C.byref(total))
             N.check(st, "rs_pairs_bbox_grid_host", self._ctx)
         return PairList(off, pt)
 
-    def pairs_intersect_host(self, roads: RoadSet, tiles: TileBatch, pairs: PairList) -> PairList:
+    def pairs_intersect_host(self, roads: RoadSet, tiles, pairs: PairList) -> PairList:
         """Exact reject (rs_pairs_intersect_host): the pairs whose road polygon intersects the tile rectangle -- the pair table
-        gpd.sjoin(tiles, roads) gives (statistical_analysis.py:170-171)."""
+        gpd.sjoin(tiles, roads) gives (statistical_analysis.py:170-171).  ``tiles``: a TileBatch or (T, 4) extents."""
         if pairs.n_pairs == 0:
             return pairs
         xy = np.ascontiguousarray(roads.xy, np.float64)
         ro, rro = np.ascontiguousarray(roads.ring_off, np.int32), np.ascontiguousarray(roads.road_ring_off, np.int32)
         bb = np.ascontiguousarray(roads.bbox, np.float64)
         rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), roads.n_roads, roads.n_rings, roads.n_verts)
-        ext = np.ascontiguousarray(tiles.extents(), np.float64)
+        ext = np.ascontiguousarray(tiles.extents() if hasattr(tiles, "extents") else tiles, np.float64).reshape(-1, 4)
         rpo, pt = np.ascontiguousarray(pairs.road_pair_off, np.int32), np.ascontiguousarray(pairs.pair_tile, np.int32)
         keep = np.zeros(pairs.n_pairs, np.uint8)
-        st = self.lib.rs_pairs_intersect_host(self._ctx, C.byref(rd), _np_ptr(ext), tiles.n_tiles, _np_ptr(rpo), _np_ptr(pt), pairs.n_pairs,
+        st = self.lib.rs_pairs_intersect_host(self._ctx, C.byref(rd), _np_ptr(ext), len(ext), _np_ptr(rpo), _np_ptr(pt), pairs.n_pairs,
                                               _np_ptr(keep))
         N.check(st, "rs_pairs_intersect_host", self._ctx)
         k = keep.astype(bool)
         csum = np.concatenate([[0], np.cumsum(k)])
         return PairList(csum[rpo.astype(np.int64)].astype(np.int32), np.ascontiguousarray(pt[k]))
+
+    def clip_rings_host(self, labels: RoadSet, pair_label, rect):
+        """The rings of label pair_label[p] clipped to the rectangle rect[p] (rs_clip_rings_host, determine_class.clip_labels).
+        Returns a RoadSet whose 'road' p is the clipped label of pair p (rings that miss the rectangle are dropped)."""
+        pl = np.ascontiguousarray(pair_label, np.int32)
+        rc_ = np.ascontiguousarray(rect, np.float64).reshape(-1, 4)
+        P = len(pl)
+        nr = np.diff(labels.road_ring_off).astype(np.int64)[pl] if P else np.zeros(0, np.int64)
+        pro = np.zeros(P + 1, np.int64)
+        pro[1:] = np.cumsum(nr)
+        nq = int(pro[-1])
+        if nq == 0:
+            return RoadSet.from_arrays(np.zeros((0, 2)), np.zeros(1, np.int32), np.zeros(P + 1, np.int32))
+        xy = np.ascontiguousarray(labels.xy, np.float64)
+        ro, rro = np.ascontiguousarray(labels.ring_off, np.int32), np.ascontiguousarray(labels.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(labels.bbox, np.float64)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(ro), _np_ptr(rro), _np_ptr(bb), labels.n_roads, labels.n_rings, labels.n_verts)
+        cnt = np.zeros(nq, np.int32)
+        st = self.lib.rs_clip_rings_host(self._ctx, C.byref(rd), _np_ptr(pl), _np_ptr(rc_), P, _np_ptr(pro), _np_ptr(cnt), None, None)
+        N.check(st, "rs_clip_rings_host", self._ctx)
+        voff = np.zeros(nq, np.int64)
+        voff[1:] = np.cumsum(cnt.astype(np.int64))[:-1]
+        total = int(cnt.sum())
+        out = np.zeros((total, 2), np.float64)
+        if total:
+            st = self.lib.rs_clip_rings_host(self._ctx, C.byref(rd), _np_ptr(pl), _np_ptr(rc_), P, _np_ptr(pro), _np_ptr(cnt), _np_ptr(voff),
+                                             _np_ptr(out))
+            N.check(st, "rs_clip_rings_host", self._ctx)
+        keep = cnt > 0                                                 # rings that survive, per pair
+        kcs = np.concatenate([[0], np.cumsum(keep)])
+        ring_off = np.concatenate([[0], np.cumsum(cnt[keep].astype(np.int64))])
+        return RoadSet.from_arrays(out, ring_off.astype(np.int32), kcs[pro].astype(np.int32))
 
     def rescale_u16_host(self, src: np.ndarray, smin: Sequence[float], smax: Sequence[float], bidx: Optional[Sequence[int]] = None,
                          f32: bool = False) -> np.ndarray:

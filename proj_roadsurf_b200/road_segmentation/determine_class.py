@@ -185,8 +185,45 @@ def _clip_ring_to_rect(ring: np.ndarray, x0: float, y0: float, x1: float, y1: fl
     return pts
 
 
-def clip_labels(labels_gdf, tiles_gdf, fact=0.99):
+def clip_labels(labels_gdf, tiles_gdf, fact=0.99, engine=None, as_soup: bool = False):
     """determine_class.py:62-95 (copied there from the object detector's helpers): every label joined to every tile it
+    intersects and cut to that tile scaled by ``fact`` about its centre (shapely.affinity.scale's default origin).
+    ``labels_gdf`` / ``tiles_gdf``: tables with a 'geometry' column; tile geometries are axis-aligned rectangles (XYZ tiles).
+    All three steps run on the GPU: the bounding-box join (rs_pairs_bbox_grid_host), the exact 'intersects' reject
+    (rs_pairs_intersect_host) and the clip of every ring to its rectangle (rs_clip_rings_host, re-entrant Sutherland-Hodgman;
+    same areas and raster as GEOS' intersection, see ``_clip_ring_to_rect`` for the host restatement the tests hold it to).
+    Returns the joined table: label columns + tile columns ('id' renamed 'tile_id'), geometry = the clipped label as a
+    GeoJSON-like dict; labels that only reach the outer 1 % frame of a tile keep an empty geometry, as in the reference.
+    as_soup=True skips the per-row dicts (1 M labels) and returns (table without geometry, RoadSet of the clipped labels)."""
+    from ..geometry import RoadSet, rings_of
+    if hasattr(labels_gdf, 'crs') and hasattr(tiles_gdf, 'crs'):
+        assert (labels_gdf.crs == tiles_gdf.crs)
+    eng = engine or default_engine()
+    labels = labels_gdf if isinstance(labels_gdf, RoadSet) else RoadSet.from_geometries(list(labels_gdf['geometry']))
+    tile_rings = [rings_of(g) for g in tiles_gdf['geometry']]
+    tb = np.array([[np.concatenate(r)[:, 0].min(), np.concatenate(r)[:, 1].min(), np.concatenate(r)[:, 0].max(), np.concatenate(r)[:, 1].max()]
+                   if r else [np.inf, np.inf, -np.inf, -np.inf] for r in tile_rings], np.float64).reshape(-1, 4)
+    pairs = eng.pairs_intersect_host(labels, tb, eng.pairs_bbox_grid_host(labels, tb))     # sjoin(labels, tiles, 'intersects')
+    ia, ib = pairs.road_of_pair().astype(np.int64), pairs.pair_tile.astype(np.int64)
+    cx, cy = (tb[ib, 0] + tb[ib, 2]) / 2, (tb[ib, 1] + tb[ib, 3]) / 2
+    hw, hh = (tb[ib, 2] - tb[ib, 0]) / 2 * fact, (tb[ib, 3] - tb[ib, 1]) / 2 * fact
+    clipped = eng.clip_rings_host(labels, ia, np.stack([cx - hw, cy - hh, cx + hw, cy + hh], 1))
+    left_src = labels_gdf if not isinstance(labels_gdf, RoadSet) else pd.DataFrame({"label": np.arange(labels.n_roads)})
+    left = left_src.drop(columns=[c for c in ['geometry'] if c in left_src.columns]).iloc[ia].reset_index(drop=True)
+    right = tiles_gdf.drop(columns=['geometry']).iloc[ib].reset_index(drop=True).rename(columns={'id': 'tile_id'})
+    dup = set(left.columns) & set(right.columns)
+    left = left.rename(columns={c: f'{c}_left' for c in dup})
+    right = right.rename(columns={c: f'{c}_right' for c in dup})
+    out = pd.concat([left, right], axis=1)
+    if as_soup:
+        return out, clipped
+    out['geometry'] = [{"type": "Polygon", "coordinates": [r.tolist() for r in clipped.rings(k)]} for k in range(clipped.n_roads)]
+    return out
+
+
+def clip_labels_host(labels_gdf, tiles_gdf, fact=0.99):
+    """Host restatement of ``clip_labels`` (numpy, one ring at a time): what the GPU form is held to, vertex for vertex.
+    determine_class.py:62-95 (copied there from the object detector's helpers): every label joined to every tile it
     intersects and cut to that tile scaled by ``fact`` about its centre (shapely.affinity.scale's default origin).
     ``labels_gdf`` / ``tiles_gdf``: tables with a 'geometry' column; tile geometries are axis-aligned rectangles (XYZ tiles).
     Vector preprocessing on the host, like the reference (GEOS there; a rectangle clip of every ring here, which gives the

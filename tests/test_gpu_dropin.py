@@ -903,3 +903,46 @@ def test_exact_intersects_reject_and_grid_broad_phase():
     exp3 = pairs_by_bbox(r3, tb3)
     assert np.array_equal(got3.road_pair_off, exp3.road_pair_off) and np.array_equal(got3.pair_tile, exp3.pair_tile)
     assert exp3.n_pairs > 1000
+
+
+def test_clip_labels_gpu_equals_host_restatement(mods):
+    """determine_class.clip_labels on the GPU (bounding-box join, exact intersects reject, re-entrant Sutherland-Hodgman) against
+    the numpy restatement clip_labels_host: same rows in the same order, same rings vertex for vertex (bit-exact)."""
+    dc = mods[3]
+    rng = np.random.default_rng(21)
+
+    def star(c, rmin, rmax, n):
+        ang = (np.arange(n) + rng.uniform(0.0, 0.8, n)) * (2 * np.pi / n)
+        rad = rng.uniform(rmin, rmax, n)
+        pts = np.stack([c[0] + rad * np.cos(ang), c[1] + rad * np.sin(ang)], 1)
+        return np.concatenate([pts, pts[:1]])
+    labels = []
+    for i in range(60):
+        c = rng.uniform(-3, 63, 2)
+        rings = [star(c, 2, 14, int(rng.integers(5, 40)))]
+        if i % 3 == 0:
+            rings.append(star(c, 0.3, 1.8, 7))
+        labels.append({"type": "Polygon", "coordinates": [r.tolist() for r in rings]})
+    labels.append({"type": "Polygon", "coordinates": [[[10.0, 10.0], [20.0, 10.0], [20.0, 20.0], [10.0, 20.0], [10.0, 10.0]]]})   # exactly a tile
+    labels.append({"type": "Polygon", "coordinates": [[[500.0, 500.0], [501.0, 500.0], [501.0, 501.0], [500.0, 500.0]]]})        # joins no tile
+    tiles, tid = [], []
+    for ty in range(6):
+        for tx in range(6):
+            x0, y0 = 10.0 * tx, 10.0 * ty
+            tiles.append({"type": "Polygon", "coordinates": [[[x0, y0], [x0 + 10, y0], [x0 + 10, y0 + 10], [x0, y0 + 10], [x0, y0]]]})
+            tid.append(f"({tx}, {ty}, 18)")
+    lab_df = pd.DataFrame({"OBJECTID": np.arange(len(labels)) + 1, "BELAGSART": 100, "geometry": labels})
+    til_df = pd.DataFrame({"id": tid, "title": "t", "geometry": tiles})
+    got = dc.clip_labels(lab_df, til_df, fact=0.99)
+    exp = dc.clip_labels_host(lab_df, til_df, fact=0.99)
+    assert list(got.columns) == list(exp.columns) and len(got) == len(exp) > 150
+    assert got["OBJECTID"].tolist() == exp["OBJECTID"].tolist() and got["tile_id"].tolist() == exp["tile_id"].tolist()
+    n_empty = 0
+    for a, b in zip(got["geometry"], exp["geometry"]):
+        assert len(a["coordinates"]) == len(b["coordinates"])
+        n_empty += len(b["coordinates"]) == 0
+        for ra, rb in zip(a["coordinates"], b["coordinates"]):
+            assert np.array_equal(np.array(ra), np.array(rb))
+    assert n_empty < len(exp) // 4
+    table, soup = dc.clip_labels(lab_df, til_df, fact=0.99, as_soup=True)
+    assert len(table) == len(exp) == soup.n_roads and "geometry" not in table.columns

@@ -110,7 +110,7 @@ def test_bbox_pairs_matches_brute_force():
 
 
 def test_clip_labels_areas_match_the_overlay_oracle():
-    """determine_class.clip_labels (determine_class.py:62-95, host preprocessing): the clipped label has the area of
+    """determine_class.clip_labels_host (the numpy restatement of determine_class.py:62-95 the GPU form is held to): the clipped label has the area of
     label AND scaled tile (oracle/overlay.py), rows follow the (label, tile) join"""
     import pandas as pd
     from oracle import overlay as ov
@@ -137,7 +137,7 @@ def test_clip_labels_areas_match_the_overlay_oracle():
             tid.append(f"({tx}, {ty}, 18)")
     lab_df = pd.DataFrame({"OBJECTID": np.arange(12) + 1, "BELAGSART": 100, "geometry": labels})
     til_df = pd.DataFrame({"id": tid, "title": "t", "geometry": tiles})
-    out = dc.clip_labels(lab_df, til_df, fact=0.99)
+    out = dc.clip_labels_host(lab_df, til_df, fact=0.99)
     assert list(out.columns) == ["OBJECTID", "BELAGSART", "tile_id", "title", "geometry"] and len(out) > 20
     n_checked = 0
     for row in out.itertuples():
