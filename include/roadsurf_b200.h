@@ -49,7 +49,8 @@ enum rs_status {
     RS_ERR_UNSUPPORTED = -6,   /* a (road, raster) window wider than 2048 px, channels not in 1..4, dtype/channels combination */
     RS_ERR_NOT_PINNED = -7,    /* rs_zonal_stats_mapped_host: tiles->pixels is not page-locked    */
     RS_ERR_NO_NCCL = -8,       /* rs_comm_*: libnccl.so.2 could not be loaded                     */
-    RS_ERR_NCCL = -9           /* an NCCL call failed                                             */
+    RS_ERR_NCCL = -9,          /* an NCCL call failed                                             */
+    RS_ERR_CODEC = -10         /* rs_decode_segments_*: a compressed segment is corrupt or does not decode to its expected size */
 };
 
 enum rs_dtype { RS_U8 = 0, RS_U16 = 1 };
@@ -443,6 +444,31 @@ int rs_assemble_tiles_dev(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int3
 int rs_assemble_tiles_host(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in,
                            int32_t planar, int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out,
                            const int32_t *bidx, int32_t rescale, const double *k, const double *off, void *out);
+
+/*
+ * Tile ingest, decompression on the device: the compressed segments (strips / internal tiles) of a batch of TIFFs, concatenated
+ * in comp[comp_off[s] .. comp_off[s + 1]), are decoded one thread per segment into raw[raw_off[s] .. raw_off[s + 1]); a segment
+ * must decode to exactly that many bytes (libtiff: rows * row bytes), otherwise RS_ERR_CODEC (latched for _dev, returned by
+ * _host).  codec = the TIFF Compression tag: 1 none, 5 LZW (MSB-first, early change), 8 / 32946 zlib-wrapped DEFLATE.  The
+ * compressed bytes are what crosses the host link; `raw` then feeds rs_assemble_tiles_* (predictor, byte order, bands, rescale).
+ * Replaces the libtiff decode under rasterio's src.read() (scripts/functions/fct_misc.py:76-77).  comp_off / raw_off int64[n + 1].
+ */
+int rs_decode_segments_dev(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec,
+                           uint8_t *raw, const int64_t *raw_off, void *stream);
+int rs_decode_segments_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec,
+                            uint8_t *raw, const int64_t *raw_off);
+
+/*
+ * The whole ingest of a batch of equally shaped TIFF tiles in one call: compressed segments H2D -> rs_decode_segments ->
+ * rs_assemble_tiles -> out[n_tiles][H][W][c_out] D2H.  raw_off must tile the sample buffer of rs_assemble_tiles exactly
+ * (n_tiles * H * W * c_in * sample_bytes bytes: per tile [H][W][c_in] or [c_in][H][W], strips in row order).  With
+ * keep_on_device != 0 the assembled batch also stays in the context's staging buffer (*device_out, valid until the next _host
+ * call on this context) so that a caller can run rs_zonal_hist_dev on it without a second upload; out may then be NULL.
+ */
+int rs_ingest_tiles_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec,
+                         const int64_t *raw_off, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in, int32_t planar,
+                         int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out, const int32_t *bidx,
+                         int32_t rescale, const double *k, const double *off, void *out, int32_t keep_on_device, void **device_out);
 
 /*
  * Deterministic synthetic tiles (bench / tests only; the reference ships no imagery,

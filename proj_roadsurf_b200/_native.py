@@ -14,7 +14,7 @@ RS_OK = 0
 STATUS = {
     0: "RS_OK", -1: "RS_ERR_INVALID_ARG", -2: "RS_ERR_CUDA", -3: "RS_ERR_CAPACITY",
     -4: "RS_ERR_ROTATED", -5: "RS_ERR_NO_DEVICE", -6: "RS_ERR_UNSUPPORTED", -7: "RS_ERR_NOT_PINNED",
-    -8: "RS_ERR_NO_NCCL", -9: "RS_ERR_NCCL",
+    -8: "RS_ERR_NO_NCCL", -9: "RS_ERR_NCCL", -10: "RS_ERR_CODEC",
 }
 RS_COMM_ID_BYTES = 128
 RS_ERR_NOT_PINNED = -7
@@ -36,7 +36,7 @@ EXPORTS = (
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
     "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
     "rs_pairs_bbox_host", "rs_rescale_u16_dev", "rs_rescale_u16_host", "rs_ks_hist_host",
-    "rs_zonal_stats_f32_host", "rs_pairs_bbox_grid_host", "rs_pairs_intersect_host", "rs_clip_rings_host", "rs_comm_unique_id", "rs_comm_init", "rs_comm_destroy", "rs_comm_world", "rs_allreduce_accumulators_dev",
+    "rs_zonal_stats_f32_host", "rs_pairs_bbox_grid_host", "rs_pairs_intersect_host", "rs_clip_rings_host", "rs_decode_segments_dev", "rs_decode_segments_host", "rs_ingest_tiles_host", "rs_comm_unique_id", "rs_comm_init", "rs_comm_destroy", "rs_comm_world", "rs_allreduce_accumulators_dev",
 )
 
 
@@ -142,6 +142,9 @@ def load():
     L.rs_pairs_bbox_grid_host.argtypes = [P, P, C.c_int32, P, C.c_int32, P, P, C.c_int64, C.POINTER(C.c_int64)]
     L.rs_pairs_intersect_host.argtypes = [P, C.POINTER(RsRoads), P, C.c_int32, P, P, C.c_int32, P]
     L.rs_clip_rings_host.argtypes = [P, C.POINTER(RsRoads), P, P, C.c_int32, P, P, P, P]
+    L.rs_decode_segments_dev.argtypes = [P, P, P, C.c_int32, C.c_int32, P, P, P]
+    L.rs_decode_segments_host.argtypes = L.rs_decode_segments_dev.argtypes[:-1]
+    L.rs_ingest_tiles_host.argtypes = [P, P, P, C.c_int32, C.c_int32, P] + [C.c_int32] * 9 + [P, C.c_int32, P, P, P, C.c_int32, P]
     L.rs_comm_unique_id.argtypes = [P]
     L.rs_comm_init.argtypes = [P, P, C.c_int32, C.c_int32]
     L.rs_comm_destroy.argtypes = [P]

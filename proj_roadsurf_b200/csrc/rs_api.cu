@@ -114,6 +114,7 @@ const char *rs_status_string(int status)
         case RS_ERR_NOT_PINNED: return "the tile buffer is not page-locked host memory";
         case RS_ERR_NO_NCCL: return "libnccl.so.2 could not be loaded";
         case RS_ERR_NCCL: return "an NCCL call failed";
+        case RS_ERR_CODEC: return "a compressed tile segment is corrupt or has an unexpected size";
         default: return "unknown status";
     }
 }
@@ -160,6 +161,7 @@ int rs_ctx_destroy(rs_ctx *ctx)
     for (rs::DevBuf *b : {&ctx->wide_cnt, &ctx->wide_off, &ctx->wide_bounds, &ctx->wide_pair_road, &ctx->wide_tmp})
         if (b->p) cudaFree(b->p);
     if (ctx->lut_dev.p) cudaFree(ctx->lut_dev.p);
+    if (ctx->lzw_scratch.p) cudaFree(ctx->lzw_scratch.p);
     if (ctx->pool.p) cudaFree(ctx->pool.p);
     if (ctx->heads.p) cudaFree(ctx->heads.p);
     if (ctx->ov_items.p) cudaFree(ctx->ov_items.p);
@@ -785,6 +787,39 @@ int rs_pairs_intersect_host(rs_ctx *ctx, const rs_roads *roads, const double *ti
     return finish(ctx);
 }
 
+int rs_decode_segments_dev(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec, uint8_t *raw,
+                           const int64_t *raw_off, void *stream)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_segments < 0) return RS_ERR_INVALID_ARG;
+    if (n_segments == 0) return RS_OK;
+    if (!comp || !comp_off || !raw || !raw_off) return RS_ERR_INVALID_ARG;
+    return launch_decode_segments(ctx, comp, (const long long *)comp_off, n_segments, codec, raw, (const long long *)raw_off,
+                                  (cudaStream_t)stream);
+}
+
+int rs_decode_segments_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec, uint8_t *raw,
+                            const int64_t *raw_off)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_segments < 0) return RS_ERR_INVALID_ARG;
+    if (n_segments == 0) return RS_OK;
+    if (!comp || !comp_off || !raw || !raw_off) return RS_ERR_INVALID_ARG;
+    const size_t cb = (size_t)comp_off[n_segments], rb = (size_t)raw_off[n_segments];
+    if ((rc = up(ctx, ctx->stage[0], comp, cb))) return rc;
+    if ((rc = up(ctx, ctx->stage[1], comp_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[2], raw_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[3], rb))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if ((rc = launch_decode_segments(ctx, (const uint8_t *)ctx->stage[0].p, (const long long *)ctx->stage[1].p, n_segments, codec,
+                                     (uint8_t *)ctx->stage[3].p, (const long long *)ctx->stage[2].p, st)))
+        return rc;
+    if (rb) RS_CUDA_OK(ctx, cudaMemcpyAsync(raw, ctx->stage[3].p, rb, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
 int rs_clip_rings_host(rs_ctx *ctx, const rs_roads *labels, const int32_t *pair_label, const double *rect, int32_t n_pairs,
                        const int64_t *pair_ring_off, int32_t *ring_count, const int64_t *ring_vert_off, double *xy_out)
 {
@@ -1042,6 +1077,38 @@ int rs_assemble_tiles_host(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int
                               big_endian, c_out, bidx, rescale, k, off, ctx->stage[9].p, ctx->host_stream)))
         return rc;
     RS_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->stage[9].p, out_b, cudaMemcpyDeviceToHost, ctx->host_stream));
+    return finish(ctx);
+}
+
+int rs_ingest_tiles_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec,
+                         const int64_t *raw_off, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in, int32_t planar,
+                         int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out, const int32_t *bidx, int32_t rescale,
+                         const double *k, const double *off, void *out, int32_t keep_on_device, void **device_out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_tiles < 0 || n_segments < 0 || height < 1 || width < 1 || c_in < 1 || c_out < 1 || (sample_bytes != 1 && sample_bytes != 2))
+        return RS_ERR_INVALID_ARG;
+    if (n_tiles == 0) return RS_OK;
+    if (!comp || !comp_off || !raw_off || (!out && !keep_on_device)) return RS_ERR_INVALID_ARG;
+    const size_t npx = (size_t)n_tiles * height * width;
+    const size_t in_b = npx * c_in * sample_bytes, out_b = npx * c_out * ((sample_bytes == 1 || rescale) ? 1 : 2);
+    if ((size_t)raw_off[n_segments] != in_b) return RS_ERR_INVALID_ARG;           // the segments must tile the sample buffer exactly
+    const size_t cb = (size_t)comp_off[n_segments];
+    if ((rc = up(ctx, ctx->stage[0], comp, cb))) return rc;                        // only the COMPRESSED bytes cross the host link
+    if ((rc = up(ctx, ctx->stage[1], comp_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[2], raw_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[7], in_b))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[9], out_b))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if ((rc = launch_decode_segments(ctx, (const uint8_t *)ctx->stage[0].p, (const long long *)ctx->stage[1].p, n_segments, codec,
+                                     (uint8_t *)ctx->stage[7].p, (const long long *)ctx->stage[2].p, st)))
+        return rc;
+    if ((rc = launch_assemble(ctx, (const uint8_t *)ctx->stage[7].p, n_tiles, height, width, c_in, planar, predictor, sample_bytes,
+                              big_endian, c_out, bidx, rescale, k, off, ctx->stage[9].p, st)))
+        return rc;
+    if (out) RS_CUDA_OK(ctx, cudaMemcpyAsync(out, ctx->stage[9].p, out_b, cudaMemcpyDeviceToHost, st));
+    if (device_out) *device_out = keep_on_device ? ctx->stage[9].p : nullptr;      // valid until the next _host call on this context
     return finish(ctx);
 }
 

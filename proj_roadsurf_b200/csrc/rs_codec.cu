@@ -1,0 +1,88 @@
+// Tile ingest, decompression on the device: the compressed strips / internal tiles of a batch of GeoTIFFs cross
+// the host link as they are in the files and are decoded here, one thread per segment, straight into the sample buffer
+// rs_assemble_tiles_* reads (predictor, byte order, band selection and the 16 -> 8 bit rescale follow in assemble_kernel).
+// This is what rasterio.open(tile).read() does through libtiff inside the reference's pair loop
+// (scripts/functions/fct_misc.py:76-77; the tiles of config/config_stats.yaml:39 are deflate- or LZW-compressed COGs).
+//
+//   codec 8 / 32946  zlib-wrapped DEFLATE (RFC 1950 / 1951): stored, fixed and dynamic Huffman blocks; canonical codes are
+//                    decoded bit by bit from per-length counts (no per-thread look-up tables: a decoder's whole state is
+//                    ~1.3 KB of local memory, so hundreds of thousands of segments decode concurrently); matches copy from the
+//                    output itself (the 32 KiB window is the already written part of the segment)
+//   codec 5          TIFF LZW (MSB-first codes of 9 - 12 bits, ClearCode 256, EOI 257, the "early change" of libtiff); the
+//                    string table (4096 x 6 bytes per decoder) lives in a scratch buffer, decoders run grid-strided
+//   codec 1          none: a copy
+// A decoder is sequential by nature (every code depends on the bits before it); the parallelism is across segments -- a
+// 256 x 256 tile stored in 8-row strips is 32 of them, a canton 67 M.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rs_codec_core.h"
+#include "rs_internal.h"
+
+namespace rs {
+
+namespace {
+
+using namespace codec;
+
+struct CodecArgs {
+    const uint8_t *comp;
+    const long long *comp_off;        // [n_seg + 1]
+    uint8_t *raw;
+    const long long *raw_off;         // [n_seg + 1]: where each segment goes and how many bytes it may produce
+    int n_seg, codec;
+    uint32_t *lzw_tab;                // [n_threads][4096]
+    uint16_t *lzw_len;
+    int *status;                      // latched: RS_ERR_CODEC when a segment does not decode to its expected size
+    int *bad_segment;                 // index of (one of) the failing segments, -1 = none
+};
+
+__global__ void __launch_bounds__(64) decode_kernel(const CodecArgs a)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int s = tid; s < a.n_seg; s += nthr) {
+        const uint8_t *src = a.comp + a.comp_off[s];
+        const long long n = a.comp_off[s + 1] - a.comp_off[s];
+        uint8_t *dst = a.raw + a.raw_off[s];
+        const long long cap = a.raw_off[s + 1] - a.raw_off[s];
+        long long got;
+        if (a.codec == 1) {
+            got = n < cap ? n : cap;
+            for (long long i = 0; i < got; i++) dst[i] = src[i];
+        } else if (a.codec == 5)
+            got = lzw_segment(src, n, dst, cap, a.lzw_tab + (size_t)tid * 4096, a.lzw_len + (size_t)tid * 4096);
+        else
+            got = inflate_segment(src, n, dst, cap, true);
+        // libtiff pads nothing: a strip decodes to exactly rows * row_bytes (the last strip of an image to its remaining rows)
+        if (got != cap) {
+            atomicMin(a.status, (int)RS_ERR_CODEC);
+            atomicMax(a.bad_segment, s);
+        }
+    }
+}
+
+}  // namespace
+
+int launch_decode_segments(rs_ctx *ctx, const uint8_t *comp, const long long *comp_off, int n_seg, int codec, uint8_t *raw,
+                           const long long *raw_off, cudaStream_t st)
+{
+    if (n_seg <= 0) return RS_OK;
+    if (codec != 1 && codec != 5 && codec != 8 && codec != 32946) return RS_ERR_UNSUPPORTED;
+    CodecArgs a{comp, comp_off, raw, raw_off, n_seg, codec == 32946 ? 8 : codec, nullptr, nullptr, ctx->d_status, ctx->d_counters + 8};
+    int blocks = (n_seg + 63) / 64;
+    if (codec == 5) {                                      // string tables: bound the number of concurrent decoders
+        const int max_blocks = ctx->sm_count * 2;
+        if (blocks > max_blocks) blocks = max_blocks;
+        int rc = ensure(ctx, ctx->lzw_scratch, (size_t)blocks * 64 * 4096 * (sizeof(uint32_t) + sizeof(uint16_t)));
+        if (rc) return rc;
+        a.lzw_tab = (uint32_t *)ctx->lzw_scratch.p;
+        a.lzw_len = (uint16_t *)(a.lzw_tab + (size_t)blocks * 64 * 4096);
+    }
+    RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0xff, sizeof(int), st));     // bad_segment = -1
+    decode_kernel<<<blocks, 64, 0, st>>>(a);
+    ctx->launches++;
+    RS_CUDA_OK(ctx, cudaGetLastError());
+    return RS_OK;
+}
+
+}  // namespace rs

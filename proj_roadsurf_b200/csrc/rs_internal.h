@@ -38,6 +38,7 @@ struct rs_ctx {
     cudaEvent_t ev_scratch = nullptr;     // recorded after every launch that uses the scratch above
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
+    rs::DevBuf lzw_scratch;               // LZW string tables of the resident decoders (rs_codec.cu)
     rs::DevBuf lut_dev;                   // 16 -> 8 bit rescale thresholds of the last scale parameters (rs_zonal.cu, PxU16x4Lut)
     bool lut_valid = false, lut_ok = false;
     int lut_f32 = 0;
@@ -111,6 +112,8 @@ int launch_pairs_grid(rs_ctx *ctx, const double *bbox_dev, int n_roads, const do
 int launch_clip_rings(rs_ctx *ctx, const rs_roads *labels, const int *pair_label, const double *rect, const long long *pair_ring_off,
                       int n_pairs, long long n_pair_rings, int *ring_count, const long long *ring_vert_off, double *xy_out,
                       cudaStream_t st);
+int launch_decode_segments(rs_ctx *ctx, const uint8_t *comp, const long long *comp_off, int n_seg, int codec, uint8_t *raw,
+                           const long long *raw_off, cudaStream_t st);
 int launch_within(rs_ctx *ctx, const rs_roads *a, const rs_roads *b, uint8_t *out, cudaStream_t st);
 int launch_pairs_bbox(rs_ctx *ctx, const double *bbox_dev, int n_roads, const double *ext_dev, const rs_lattice *lat, const int *lut_dev,
                       int *road_pair_off_dev, int *pair_tile_dev, long long capacity, int phase, cudaStream_t st);

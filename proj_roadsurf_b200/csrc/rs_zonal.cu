@@ -1120,15 +1120,17 @@ __global__ void __launch_bounds__(WARPS * 32, ACC_CTAS) accum_kernel(const Zonal
             auto address = [&](uint32_t en) -> const uint8_t * {
                 return px + (base + (size_t)(en >> 20) * a.W + 8u * ((en >> 8) & 0xfffu)) * PX::BPP;
             };
-            // one lane per entry; the next round's pixels are in flight while this round's atomics issue
+            // one lane per entry, software-pipelined two deep: while round k's atomics issue, the pixels of round k + 1 are in
+            // flight (their entry word arrived a round ago) and the entry word of round k + 2 is being fetched
             uint32_t rn[PX::NW];
-            uint32_t m8n = 0;
+            uint32_t m8n = 0, en2 = 0;
             int e = lane;
             if (e < n) {
                 const uint32_t en = __ldg(seg + 4 + e);
                 m8n = en & 255u;
                 load_group<PX::BPP, PX::NW>(address(en), rn);
             }
+            if (e + 32 < n) en2 = __ldg(seg + 4 + e + 32);
             while (e < n) {
                 uint32_t r[PX::NW];
 #pragma unroll
@@ -1136,9 +1138,10 @@ __global__ void __launch_bounds__(WARPS * 32, ACC_CTAS) accum_kernel(const Zonal
                 const uint32_t m8 = m8n;
                 e += 32;
                 if (e < n) {
-                    const uint32_t en = __ldg(seg + 4 + e);
+                    const uint32_t en = en2;
                     m8n = en & 255u;
                     load_group<PX::BPP, PX::NW>(address(en), rn);
+                    if (e + 32 < n) en2 = __ldg(seg + 4 + e + 32);
                 }
                 group_pixels<PX, 0>(a, r, m8, hist_addr, one, nz);
             }

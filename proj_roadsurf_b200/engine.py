@@ -509,6 +509,38 @@ class Engine:
         N.check(st, "rs_assemble_tiles_host", self._ctx)
         return out
 
+    def decode_segments_host(self, comp: np.ndarray, comp_off, codec: int, raw_off) -> np.ndarray:
+        """Decompress TIFF segments on the device (rs_decode_segments_host): comp uint8 (all segments concatenated), comp_off /
+        raw_off int64 (n + 1,), codec = TIFF Compression tag (1, 5, 8, 32946).  Returns the raw bytes (raw_off[-1],) uint8."""
+        comp = np.ascontiguousarray(comp, np.uint8)
+        co, ro = np.ascontiguousarray(comp_off, np.int64), np.ascontiguousarray(raw_off, np.int64)
+        n = len(co) - 1
+        raw = np.zeros(int(ro[-1]), np.uint8)
+        st = self.lib.rs_decode_segments_host(self._ctx, _np_ptr(comp), _np_ptr(co), n, int(codec), _np_ptr(raw), _np_ptr(ro))
+        N.check(st, "rs_decode_segments_host", self._ctx)
+        return raw
+
+    def ingest_tiles_host(self, comp: np.ndarray, comp_off, codec: int, raw_off, n_tiles: int, info, bidx=None,
+                          rescale: Optional[dict] = None) -> np.ndarray:
+        """Compressed TIFF segments -> (T, H, W, C_out) tiles in one call (rs_ingest_tiles_host): decompression, predictor, byte
+        order, band selection and rescale all on the device; only the compressed bytes are uploaded."""
+        comp = np.ascontiguousarray(comp, np.uint8)
+        co, ro = np.ascontiguousarray(comp_off, np.int64), np.ascontiguousarray(raw_off, np.int64)
+        H, W, Cin, sb = info.height, info.width, info.channels, info.sample_bytes
+        bi = np.arange(Cin, dtype=np.int32) if bidx is None else np.ascontiguousarray(bidx, np.int32) - 1
+        Cout = len(bi)
+        mode, k, off = 0, None, None
+        if rescale is not None:
+            k, off = scale_params(rescale["smin"], rescale["smax"], bool(rescale.get("f32")))
+            assert len(k) == Cout, "one scale range per output band"
+            mode = 2 if rescale.get("f32") else 1
+        out = np.zeros((n_tiles, H, W, Cout), np.uint8 if (sb == 1 or mode) else np.uint16)
+        st = self.lib.rs_ingest_tiles_host(self._ctx, _np_ptr(comp), _np_ptr(co), len(co) - 1, int(codec), _np_ptr(ro), n_tiles, H, W, Cin,
+                                           int(info.planar), int(info.predictor), sb, int(bool(info.big_endian)), Cout, _np_ptr(bi),
+                                           mode, _np_ptr(k), _np_ptr(off), _np_ptr(out), 0, None)
+        N.check(st, "rs_ingest_tiles_host", self._ctx)
+        return out
+
     def overlay_area_host(self, a: RoadSet, b: RoadSet, pair_a, pair_b):
         """(area of a[pair_a[k]] intersected with b[pair_b[k]] for every k, area of every polygon of ``a``):
         gpd.overlay(...).area and GeoSeries.area of determine_class.py:107-114 (rs_overlay_area_host)."""

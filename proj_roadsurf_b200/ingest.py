@@ -3,12 +3,13 @@
 The reference reads every tile with ``rasterio.open(tile).read()`` inside its pair loop (scripts/functions/fct_misc.py:76-77)
 and gets the tiles from a tile server that selects and reorders bands (``bidx=2&bidx=3&bidx=4&bidx=1``,
 config/config_stats.yaml:39) after tif2cog's 16 -> 8 bit rescale (scripts/preprocessing/tif2cog.py:260-270).  Here the
-host only parses the TIFF directory and inflates the segments (zlib, a thread per file); everything per pixel -- TIFF
-predictor 2, byte order, band-sequential -> interleaved, band selection, rescale -- is one kernel over the whole batch
-(rs_assemble_tiles_*).
+host only parses the TIFF directories; the compressed segments go to the device as they are in the files and are decoded
+there (rs_decode_segments: DEFLATE and TIFF LZW, a thread per segment), and everything per pixel -- TIFF predictor 2, byte
+order, band-sequential -> interleaved, band selection, rescale -- is one kernel over the whole batch (rs_assemble_tiles_*).
+``load_tiles(..., device_decode=False)`` keeps the earlier host inflate (zlib, a thread per file) as the comparison path.
 
-Supported: classic (non-Big) TIFF, little / big endian, strips or one internal tile row per image width, compression
-none (1) and deflate (8, 32946), predictor 1 / 2, PlanarConfiguration 1 / 2, unsigned 8 / 16 bit samples, 1-4 bands,
+Supported: classic TIFF and BigTIFF, little / big endian, strips or one internal tile row per image width, compression
+none (1), LZW (5, device path) and deflate (8, 32946), predictor 1 / 2, PlanarConfiguration 1 / 2, unsigned 8 / 16 bit samples, 1-4 bands,
 GeoTIFF ModelPixelScale + ModelTiepoint or ModelTransformation, GDAL_NODATA.  Anything else raises ``UnsupportedTiff``
 (fct_misc.open_tile then falls back to rasterio / PIL where installed).
 """
@@ -45,6 +46,7 @@ class TiffInfo:
     seg_width: int            # width of a stored segment row (image width for strips, TileWidth for internal tiles)
     transform: Tuple[float, float, float, float, float, float]
     nodata: Optional[float]
+    tiled: bool = False       # internal tiles (the last one may be padded below the image)
 
     @property
     def layout(self):
@@ -52,7 +54,7 @@ class TiffInfo:
 
 
 _TYPE = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: ("b", 1), 7: ("B", 1), 8: ("h", 2), 9: ("i", 4),
-         10: ("ii", 8), 11: ("f", 4), 12: ("d", 8), 16: ("Q", 8)}
+         10: ("ii", 8), 11: ("f", 4), 12: ("d", 8), 16: ("Q", 8), 17: ("q", 8), 18: ("Q", 8)}
 
 
 def parse_tiff(buf: bytes) -> TiffInfo:
@@ -65,18 +67,29 @@ def parse_tiff(buf: bytes) -> TiffInfo:
         e = ">"
     else:
         raise UnsupportedTiff("not a TIFF")
-    magic, ifd = struct.unpack(e + "HI", buf[2:8])
-    if magic != 42:
-        raise UnsupportedTiff("BigTIFF / unknown magic")
-    (n,) = struct.unpack(e + "H", buf[ifd:ifd + 2])
+    (magic,) = struct.unpack(e + "H", buf[2:4])
+    if magic == 42:                                         # classic: 4-byte offsets, 12-byte directory entries
+        (ifd,) = struct.unpack(e + "I", buf[4:8])
+        (n,) = struct.unpack(e + "H", buf[ifd:ifd + 2])
+        first, esz, head, inline, ofmt = ifd + 2, 12, "HHI", 4, "I"
+    elif magic == 43:                                       # BigTIFF: 8-byte offsets, 20-byte directory entries
+        osz, zero, ifd = struct.unpack(e + "HHQ", buf[4:16])
+        if osz != 8 or zero != 0:
+            raise UnsupportedTiff("BigTIFF with an offset size other than 8")
+        (n,) = struct.unpack(e + "Q", buf[ifd:ifd + 8])
+        first, esz, head, inline, ofmt = ifd + 8, 20, "HHQ", 8, "Q"
+    else:
+        raise UnsupportedTiff("unknown TIFF magic")
     tags = {}
     for i in range(n):
-        tag, typ, cnt, raw = struct.unpack(e + "HHI4s", buf[ifd + 2 + 12 * i: ifd + 14 + 12 * i])
+        ent = buf[first + esz * i: first + esz * (i + 1)]
+        tag, typ, cnt = struct.unpack(e + head, ent[:esz - inline])
+        raw = ent[esz - inline:]
         if typ not in _TYPE:
             continue
         fmt, size = _TYPE[typ]
         nbytes = size * cnt
-        data = raw[:nbytes] if nbytes <= 4 else buf[struct.unpack(e + "I", raw)[0]:][:nbytes]
+        data = raw[:nbytes] if nbytes <= inline else buf[struct.unpack(e + ofmt, raw)[0]:][:nbytes]
         if typ == 2:
             tags[tag] = data.split(b"\x00")[0].decode("latin-1")
         elif typ in (5, 10):
@@ -101,7 +114,7 @@ def parse_tiff(buf: bytes) -> TiffInfo:
     if not 1 <= C <= 4:
         raise UnsupportedTiff(f"{C} samples per pixel")
     comp = int(one(259, 1))
-    if comp not in (1, 8, 32946):
+    if comp not in (1, 5, 8, 32946):
         raise UnsupportedTiff(f"compression {comp}")
     pred = int(one(317, 1))
     if pred not in (1, 2):
@@ -136,7 +149,7 @@ def parse_tiff(buf: bytes) -> TiffInfo:
         except ValueError:
             nodata = None
     return TiffInfo(int(W), int(H), C, bits[0] // 8, planar, pred, comp, e == ">", tuple(int(o) for o in offs),
-                    tuple(int(c) for c in cnts), int(rps), int(sw), transform, nodata)
+                    tuple(int(c) for c in cnts), int(rps), int(sw), transform, nodata, 322 in tags)
 
 
 def read_raw(path_or_bytes) -> Tuple[np.ndarray, TiffInfo]:
@@ -156,6 +169,8 @@ def read_raw(path_or_bytes) -> Tuple[np.ndarray, TiffInfo]:
         for s in range(segs_per_plane):
             k = pl * segs_per_plane + s
             data = buf[info.seg_offsets[k]: info.seg_offsets[k] + info.seg_counts[k]]
+            if info.compression == 5:
+                raise UnsupportedTiff("LZW is decoded on the device (load_tiles(device_decode=True))")
             if info.compression != 1:
                 data = zlib.decompress(data)
             r0 = s * info.rows_per_seg
@@ -167,25 +182,64 @@ def read_raw(path_or_bytes) -> Tuple[np.ndarray, TiffInfo]:
     return (out[0].reshape(H, W * C * sb) if info.planar == 1 else out.reshape(C, H, W * sb)), info
 
 
+def segments(buf: bytes, info: TiffInfo):
+    """(compressed bytes, decoded size) of every segment of the first image, in sample-buffer order, or None when the segments do
+    not tile the sample buffer directly (internal tiles wider than the image: padded rows)."""
+    if info.tiled or info.seg_width != info.width:
+        return None
+    H, W, C, sb = info.height, info.width, info.channels, info.sample_bytes
+    spp = C if info.planar == 1 else 1
+    planes = 1 if info.planar == 1 else C
+    segs_per_plane = (H + info.rows_per_seg - 1) // info.rows_per_seg
+    if len(info.seg_offsets) < planes * segs_per_plane:
+        raise UnsupportedTiff("segment table shorter than the image")
+    out = []
+    for pl in range(planes):
+        for s_ in range(segs_per_plane):
+            k = pl * segs_per_plane + s_
+            nr = min(info.rows_per_seg, H - s_ * info.rows_per_seg)
+            out.append((buf[info.seg_offsets[k]: info.seg_offsets[k] + info.seg_counts[k]], nr * W * spp * sb))
+    return out
+
+
 def load_tiles(paths: Sequence, bidx: Optional[Sequence[int]] = None, rescale: Optional[dict] = None, engine=None,
-               threads: int = 8, ids: Optional[Sequence] = None) -> TileBatch:
+               threads: int = 8, ids: Optional[Sequence] = None, device_decode: bool = True) -> TileBatch:
     """Read equally shaped GeoTIFF tiles into one TileBatch (pixels (T, H, W, C_out) on the host, transforms, nodata).
     bidx: 1-based input bands of the output bands, the tile server's ``bidx=`` list (default: all, in order).
     rescale: {'smin': [...], 'smax': [...], 'f32': bool} per OUTPUT band -- the gdal.Translate scaleParams of
-    tif2cog.py:260-270 (dst = src * k + off, k = 255 / (smax - smin), off = -smin * k, clamped and rounded) -> uint8."""
+    tif2cog.py:260-270 (dst = src * k + off, k = 255 / (smax - smin), off = -smin * k, clamped and rounded) -> uint8.
+    device_decode: the compressed segments are uploaded as they are and decompressed on the GPU (rs_ingest_tiles_host);
+    False (or a layout whose segments are padded) inflates on the host, a thread per file."""
     from .engine import default_engine
     eng = engine or default_engine()
     paths = list(paths)
     if not paths:
         raise ValueError("no tiles")
-    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:         # zlib releases the GIL
-        got: List[Tuple[np.ndarray, TiffInfo]] = list(ex.map(read_raw, paths))
-    info0 = got[0][1]
-    for _, inf in got:
+
+    def read(p):
+        buf = p if isinstance(p, (bytes, bytearray)) else open(p, "rb").read()
+        return buf, parse_tiff(buf)
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        files = list(ex.map(read, paths))
+    info0 = files[0][1]
+    for _, inf in files:
         if inf.layout != info0.layout:
             raise ValueError("tiles of one batch must share shape, sample width and layout")
-    raw = np.stack([g[0] for g in got])
-    gt = np.array([g[1].transform for g in got], np.float64)
-    nodata = info0.nodata
-    pixels = eng.assemble_tiles_host(raw, info0, bidx, rescale)
-    return TileBatch(pixels, gt, info0.height, info0.width, pixels.shape[3], nodata, list(ids) if ids is not None else paths)
+    gt = np.array([inf.transform for _, inf in files], np.float64)
+    comps = {inf.compression for _, inf in files}
+    segs = [segments(buf, inf) for buf, inf in files] if (device_decode and len(comps) == 1) else None
+    if segs is not None and all(s_ is not None for s_ in segs):
+        flat = [x for s_ in segs for x in s_]
+        comp_off = np.zeros(len(flat) + 1, np.int64)
+        raw_off = np.zeros(len(flat) + 1, np.int64)
+        comp_off[1:] = np.cumsum([len(c) for c, _ in flat])
+        raw_off[1:] = np.cumsum([n for _, n in flat])
+        comp = np.frombuffer(b"".join(c for c, _ in flat), np.uint8)
+        pixels = eng.ingest_tiles_host(comp, comp_off, info0.compression, raw_off, len(files), info0, bidx, rescale)
+    else:
+        if 5 in comps:
+            raise UnsupportedTiff("LZW tiles with padded internal tiles are not supported")
+        with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:         # zlib releases the GIL
+            raw = np.stack(list(ex.map(lambda f: read_raw(f[0])[0], files)))
+        pixels = eng.assemble_tiles_host(raw, info0, bidx, rescale)
+    return TileBatch(pixels, gt, info0.height, info0.width, pixels.shape[3], info0.nodata, list(ids) if ids is not None else paths)

@@ -1,0 +1,112 @@
+"""The decoder cores of the device-side ingest (proj_roadsurf_b200/csrc/rs_codec_core.h) compiled for the HOST with g++ and held
+to zlib (every compression level and strategy: stored, fixed and dynamic Huffman blocks, long matches, window-length distances)
+and to libtiff-made LZW streams (PIL) -- the same source the GPU kernels compile, so the bit-level logic is checked without a
+GPU; tests/test_ingest.py checks the kernels themselves with -m gpu."""
+import ctypes
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    out_dir = os.path.join(HERE, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcodec_host.so")
+    src = os.path.join(HERE, "native", "codec_host.cpp")
+    hdr = os.path.join(ROOT, "proj_roadsurf_b200", "csrc", "rs_codec_core.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.dirname(hdr), "-o", so, src])
+    L = ctypes.CDLL(so)
+    for f in (L.host_inflate, L.host_lzw):
+        f.restype = ctypes.c_longlong
+        f.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong]
+    return L
+
+
+def _run(fn, comp: bytes, cap: int):
+    out = np.zeros(max(cap, 1), np.uint8)
+    got = fn(comp, len(comp), out.ctypes.data, cap)
+    return got, out[:max(got, 0)].tobytes()
+
+
+def _payloads():
+    rng = np.random.default_rng(5)
+    yield b""
+    yield b"a"
+    yield bytes(70000)                                                     # one long run: maximal matches, distance 1
+    yield rng.integers(0, 256, 50000, dtype=np.uint8).tobytes()            # incompressible: stored blocks at level 0 / 1
+    yield np.clip(rng.normal(110, 6, (256, 256, 3)), 0, 255).astype(np.uint8).tobytes()      # "asphalt" tile
+    yield (np.arange(200000) % 251).astype(np.uint8).tobytes()             # period 251: long-distance matches
+    yield rng.integers(0, 4, 300000, dtype=np.uint8).tobytes()             # tiny alphabet: short codes, 32 KiB window in use
+    img = rng.integers(0, 256, (64, 64, 4), dtype=np.uint8)
+    d = img.astype(np.int16)
+    d[:, 1:] -= img[:, :-1]
+    yield (d % 256).astype(np.uint8).tobytes()                             # predictor-2 residuals
+
+
+def test_inflate_matches_zlib(lib):
+    n = 0
+    for raw in _payloads():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strategy)
+                comp = c.compress(raw) + c.flush()
+                got, out = _run(lib.host_inflate, comp, len(raw))
+                assert got == len(raw) and out == raw, (len(raw), level, strategy)
+                n += 1
+    assert n == 8 * 16
+
+
+def test_inflate_rejects_bad_streams(lib):
+    raw = bytes(range(256)) * 40
+    comp = zlib.compress(raw)
+    assert _run(lib.host_inflate, comp, len(raw) - 1)[0] == -1             # output larger than the segment may hold
+    assert _run(lib.host_inflate, comp[: len(comp) // 2], len(raw))[0] == -1        # truncated
+    assert _run(lib.host_inflate, b"\x78\x9d" + comp[2:], len(raw))[0] == -1        # header check fails
+    bad = bytearray(comp)
+    bad[2] |= 0x06                                                         # block type 3
+    assert _run(lib.host_inflate, bytes(bad), len(raw))[0] == -1
+    assert _run(lib.host_inflate, b"", 10)[0] == -1
+
+
+def test_lzw_matches_libtiff(lib, tmp_path):
+    from tiff_util import lzw_encode
+    rng = np.random.default_rng(9)
+    for raw in _payloads():
+        if not raw:
+            continue
+        got, out = _run(lib.host_lzw, lzw_encode(raw), len(raw))
+        assert got == len(raw) and out == raw, len(raw)
+    Image = pytest.importorskip("PIL.Image")
+    from proj_roadsurf_b200 import ingest
+    for k, img in enumerate((rng.integers(0, 256, (300, 400, 3), dtype=np.uint8), np.full((90, 130), 77, np.uint8),
+                             rng.integers(0, 7, (513, 257), dtype=np.uint8))):
+        p = str(tmp_path / f"pil{k}.tif")
+        Image.fromarray(img).save(p, compression="tiff_lzw")               # libtiff's encoder
+        buf = open(p, "rb").read()
+        info = ingest.parse_tiff(buf)
+        assert info.compression == 5
+        dec = b""
+        for comp, n in ingest.segments(buf, info):
+            got, out = _run(lib.host_lzw, comp, n)
+            assert got == n
+            dec += out
+        assert dec == img.tobytes()
+    assert _run(lib.host_lzw, lzw_encode(bytes(1000)), 999)[0] == -1       # does not fit
+
+
+def test_inflate_checks_the_adler32_trailer(lib):
+    raw = np.random.default_rng(1).integers(0, 256, 20000, dtype=np.uint8).tobytes()
+    comp = bytearray(zlib.compress(raw, 0))                                # stored blocks: a flipped payload byte still "decodes"
+    comp[100] ^= 0x01
+    assert _run(lib.host_inflate, bytes(comp), len(raw))[0] == -1
+    comp[100] ^= 0x01
+    assert _run(lib.host_inflate, bytes(comp), len(raw))[0] == len(raw)
+    assert _run(lib.host_inflate, bytes(comp[:-1]), len(raw))[0] == -1     # trailer cut short

@@ -84,9 +84,74 @@ def test_unsupported_files_are_refused(tmp_path):
     p = str(tmp_path / "lzw.tif")
     Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(p, compression="tiff_lzw")
     with pytest.raises(ingest.UnsupportedTiff):
-        ingest.read_raw(p)
+        ingest.read_raw(p)                                          # LZW has no host decoder here: it is decoded on the device
+    assert ingest.parse_tiff(open(p, "rb").read()).compression == 5
+    p = str(tmp_path / "jpeg.tif")
+    Image.fromarray(np.zeros((16, 16, 3), np.uint8)).save(p, compression="jpeg")
+    with pytest.raises(ingest.UnsupportedTiff):
+        ingest.parse_tiff(open(p, "rb").read())
     with pytest.raises(ingest.UnsupportedTiff):
         ingest.parse_tiff(b"not a tiff at all")
+
+
+def test_bigtiff_directories_parse_like_classic_ones(tmp_path):
+    rng = np.random.default_rng(4)
+    img = _image(rng, 3, np.uint8)
+    for i, v in enumerate(VARIANTS[::3]):
+        pc, pb = str(tmp_path / f"c{i}.tif"), str(tmp_path / f"b{i}.tif")
+        write_tiff(pc, img, transform=T, nodata=0, **v)
+        write_tiff(pb, img, transform=T, nodata=0, bigtiff=True, **v)
+        assert open(pb, "rb").read()[2:4] in (b"+\x00", b"\x00+")
+        gc, ic = _decode(pc)
+        gb, ib = _decode(pb)
+        assert np.array_equal(gc, gb) and np.array_equal(gb, img)
+        assert ic.layout == ib.layout and ib.transform == T and ib.nodata == 0 and ic.seg_counts == ib.seg_counts
+
+
+@pytest.mark.gpu
+def test_device_decode_deflate_lzw_bigtiff(tmp_path):
+    """the compressed strips are decoded ON THE DEVICE (rs_ingest_tiles_host): deflate and LZW, predictor 1 / 2, chunky / planar,
+    both byte orders, classic and BigTIFF, files written here and by libtiff (PIL); equal to the host-inflate path and to the
+    images; a corrupt strip is an error, never garbage"""
+    from proj_roadsurf_b200._native import NativeError
+    rng = np.random.default_rng(17)
+    n_checked = 0
+    for comp, pred, planar, be, rps, big in itertools.product((8, 5), (1, 2), (1, 2), (False, True), (5, None), (False, True)):
+        if be and big:
+            continue
+        imgs, paths = [], []
+        for k in range(4):
+            img = _image(rng, 4, np.uint16 if (pred == 2 and planar == 2) else np.uint8, H=37, W=48)
+            p = str(tmp_path / f"d{n_checked}_{k}.tif")
+            write_tiff(p, img, compression=comp, predictor=pred, planar=planar, big_endian=be, rows_per_strip=rps, bigtiff=big,
+                       transform=T, nodata=0)
+            imgs.append(img); paths.append(p)
+        tb = ingest.load_tiles(paths, device_decode=True)
+        assert np.array_equal(tb.pixels, np.stack(imgs)), (comp, pred, planar, be, rps, big)
+        if comp == 8:
+            assert np.array_equal(ingest.load_tiles(paths, device_decode=False).pixels, tb.pixels)
+        n_checked += 1
+    assert n_checked == 48
+    Image = pytest.importorskip("PIL.Image")
+    rgb = np.clip(rng.normal(110, 6, (3, 256, 256, 3)), 0, 255).astype(np.uint8)            # three "asphalt" tiles
+    for comp in ("tiff_lzw", "tiff_adobe_deflate", "raw"):
+        paths = []
+        for k in range(3):
+            p = str(tmp_path / f"pil_{comp}_{k}.tif")
+            Image.fromarray(rgb[k]).save(p, compression=comp)
+            paths.append(p)
+        assert np.array_equal(ingest.load_tiles(paths).pixels, rgb), comp
+    # a damaged strip: RS_ERR_CODEC
+    buf = bytearray(open(paths[0], "rb").read())
+    p = str(tmp_path / "bad.tif")
+    write_tiff(p, rgb[0], compression=8, rows_per_strip=16)
+    buf = bytearray(open(p, "rb").read())
+    info = ingest.parse_tiff(bytes(buf))
+    buf[info.seg_offsets[3] + 10] ^= 0x55
+    open(p, "wb").write(bytes(buf))
+    with pytest.raises(NativeError) as ei:
+        ingest.load_tiles([p])
+    assert ei.value.status == -10
 
 
 @pytest.mark.gpu
