@@ -471,6 +471,17 @@ int rs_ingest_tiles_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_o
                          int32_t rescale, const double *k, const double *off, void *out, int32_t keep_on_device, void **device_out);
 
 /*
+ * rs_zonal_stats_host for uint8 tiles that are still COMPRESSED (the strips of GeoTIFF files as they are on disk): the compressed
+ * bytes are uploaded, decoded and assembled on the device (rs_decode_segments + rs_assemble_tiles) and the statistics computed
+ * from there -- the reference's rasterio.open(tile).read() + mask + statistics for a whole batch without the decoded tiles ever
+ * crossing the host link.  tiles->pixels is ignored; raw_off must tile n_tiles * H * W * channels bytes.
+ */
+int rs_zonal_stats_compressed_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                                   const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles,
+                                   int32_t n_pct, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec,
+                                   const int64_t *raw_off, int32_t planar, int32_t predictor, int32_t big_endian, double *stats);
+
+/*
  * Deterministic synthetic tiles (bench / tests only; the reference ships no imagery,
  * data/readme.md:20-21).  value = f(seed, tile_key[t], pixel, band), see DESIGN.md.
  * kind 0: iid uniform; 1: low-entropy "asphalt"; 2: class/score planes (channels == 2).

@@ -36,7 +36,7 @@ EXPORTS = (
     "rs_finalize_stats_host", "rs_vote_metrics_dev", "rs_vote_metrics_host", "rs_synth_tiles_dev",
     "rs_extract_pixels_host", "rs_group_hist_host", "rs_vote_table_host", "rs_confusion_metrics_host",
     "rs_pairs_bbox_host", "rs_rescale_u16_dev", "rs_rescale_u16_host", "rs_ks_hist_host",
-    "rs_zonal_stats_f32_host", "rs_pairs_bbox_grid_host", "rs_pairs_intersect_host", "rs_clip_rings_host", "rs_decode_segments_dev", "rs_decode_segments_host", "rs_ingest_tiles_host", "rs_comm_unique_id", "rs_comm_init", "rs_comm_destroy", "rs_comm_world", "rs_allreduce_accumulators_dev",
+    "rs_zonal_stats_f32_host", "rs_pairs_bbox_grid_host", "rs_pairs_intersect_host", "rs_clip_rings_host", "rs_decode_segments_dev", "rs_decode_segments_host", "rs_ingest_tiles_host", "rs_zonal_stats_compressed_host", "rs_comm_unique_id", "rs_comm_init", "rs_comm_destroy", "rs_comm_world", "rs_allreduce_accumulators_dev",
 )
 
 
@@ -145,6 +145,9 @@ def load():
     L.rs_decode_segments_dev.argtypes = [P, P, P, C.c_int32, C.c_int32, P, P, P]
     L.rs_decode_segments_host.argtypes = L.rs_decode_segments_dev.argtypes[:-1]
     L.rs_ingest_tiles_host.argtypes = [P, P, P, C.c_int32, C.c_int32, P] + [C.c_int32] * 9 + [P, C.c_int32, P, P, P, C.c_int32, P]
+    L.rs_zonal_stats_compressed_host.argtypes = [P, C.POINTER(RsRoads), C.POINTER(RsTiles), C.POINTER(RsPairs), C.POINTER(RsZonalParams),
+                                                 C.c_int32, C.c_int32, P, C.c_int32, P, P, C.c_int32, C.c_int32, P, C.c_int32, C.c_int32,
+                                                 C.c_int32, P]
     L.rs_comm_unique_id.argtypes = [P]
     L.rs_comm_init.argtypes = [P, P, C.c_int32, C.c_int32]
     L.rs_comm_destroy.argtypes = [P]

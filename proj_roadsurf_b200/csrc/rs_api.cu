@@ -1112,6 +1112,59 @@ int rs_ingest_tiles_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_o
     return finish(ctx);
 }
 
+int rs_zonal_stats_compressed_host(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,
+                                   const rs_zonal_params *prm, int32_t nodata_mode, int32_t ddof, const double *percentiles, int32_t n_pct,
+                                   const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec, const int64_t *raw_off,
+                                   int32_t planar, int32_t predictor, int32_t big_endian, double *stats)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!prm || !stats || prm->road_slot || n_pct < 0 || n_pct > 16 || n_segments < 0) return RS_ERR_INVALID_ARG;
+    if (prm->hist_mode != RS_HIST_BANDS || !tiles || !roads || !pairs) return RS_ERR_INVALID_ARG;
+    if (tiles->dtype != RS_U8 || !comp || !comp_off || !raw_off) return RS_ERR_INVALID_ARG;
+    rs_roads dr;
+    rs_tiles dt;
+    rs_pairs dp;
+    if ((rc = stage_inputs(ctx, roads, tiles, pairs, false, dr, dt, dp))) return rc;     // geometry + pairs + transforms, no pixels
+    const int R = roads->n_roads, C = tiles->channels;
+    if (R == 0) return RS_OK;
+    const size_t npx = (size_t)tiles->n_tiles * tiles->height * tiles->width, in_b = npx * C;
+    if ((size_t)raw_off[n_segments] != in_b) return RS_ERR_INVALID_ARG;
+    const size_t hb = sizeof(uint32_t) * 256 * (size_t)C * R, zb = sizeof(uint32_t) * (size_t)R;
+    const size_t sb = sizeof(double) * (size_t)(RS_NSTAT + n_pct) * C * R;
+    // stage[12..14]: compressed bytes + offsets (only these cross the host link); stage[7]: decoded samples; stage[8]: tiles
+    if ((rc = up(ctx, ctx->stage[12], comp, (size_t)comp_off[n_segments]))) return rc;
+    if ((rc = up(ctx, ctx->stage[13], comp_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
+    if ((rc = up(ctx, ctx->stage[14], raw_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[7], in_b))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[8], in_b))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[9], hb))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[11], sb))) return rc;
+    cudaStream_t st = ctx->host_stream;
+    if ((rc = launch_decode_segments(ctx, (const uint8_t *)ctx->stage[12].p, (const long long *)ctx->stage[13].p, n_segments, codec,
+                                     (uint8_t *)ctx->stage[7].p, (const long long *)ctx->stage[14].p, st)))
+        return rc;
+    if ((rc = launch_assemble(ctx, (const uint8_t *)ctx->stage[7].p, tiles->n_tiles, tiles->height, tiles->width, C, planar, predictor, 1,
+                              big_endian, C, nullptr, 0, nullptr, nullptr, ctx->stage[8].p, st)))
+        return rc;
+    dt.pixels = ctx->stage[8].p;
+    rs_zonal_params p = *prm;
+    const uint32_t *aux = (const uint32_t *)ctx->stage[10].p;
+    p.min_zero = nullptr;
+    if (nodata_mode == RS_NODATA_ZERO) {
+        if ((rc = ensure(ctx, ctx->stage[15], zb))) return rc;
+        aux = p.min_zero = (uint32_t *)ctx->stage[15].p;
+    }
+    if ((rc = launch_zonal(ctx, &dr, &dt, &dp, &p, (uint32_t *)ctx->stage[9].p, (uint32_t *)ctx->stage[10].p, nullptr, prm->window_mode, st)))
+        return rc;
+    if ((rc = launch_finalize(ctx, (const uint32_t *)ctx->stage[9].p, aux, R, C, nodata_mode, ddof, percentiles, n_pct,
+                              (double *)ctx->stage[11].p, st)))
+        return rc;
+    RS_CUDA_OK(ctx, cudaMemcpyAsync(stats, ctx->stage[11].p, sb, cudaMemcpyDeviceToHost, st));
+    return finish(ctx);
+}
+
 int rs_synth_tiles_dev(rs_ctx *ctx, void *pixels, const int64_t *tile_key, int32_t n_tiles, int32_t height, int32_t width,
                        int32_t channels, int32_t dtype, int32_t kind, uint64_t seed, void *stream)
 {

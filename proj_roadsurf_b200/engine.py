@@ -213,6 +213,32 @@ class Engine:
         N.check(st, "rs_zonal_stats_f32_host", self._ctx)
         return out
 
+    def zonal_stats_compressed_host(self, roads: RoadSet, gt: np.ndarray, height: int, width: int, channels: int, pairs: PairList,
+                                    comp: np.ndarray, comp_off, raw_off, codec: int = 8, planar: int = 1, predictor: int = 1,
+                                    nodata_mode: str = "none", ddof: int = 1, percentiles: Sequence[float] = ()) -> np.ndarray:
+        """Statistics straight from compressed uint8 tile segments (rs_zonal_stats_compressed_host): decode + assemble + fused
+        rasterize / histogram + statistics on the device, only the compressed bytes uploaded."""
+        comp = np.ascontiguousarray(comp, np.uint8)
+        co, ro = np.ascontiguousarray(comp_off, np.int64), np.ascontiguousarray(raw_off, np.int64)
+        gt = np.ascontiguousarray(gt, np.float64).reshape(-1, 6)
+        pct = np.ascontiguousarray(percentiles, np.float64)
+        R = roads.n_roads
+        stats = np.zeros((R, channels, N.RS_NSTAT + len(pct)), np.float64)
+        xy = np.ascontiguousarray(roads.xy, np.float64)
+        rof, rro = np.ascontiguousarray(roads.ring_off, np.int32), np.ascontiguousarray(roads.road_ring_off, np.int32)
+        bb = np.ascontiguousarray(roads.bbox, np.float64)
+        rpo, pt = np.ascontiguousarray(pairs.road_pair_off, np.int32), np.ascontiguousarray(pairs.pair_tile, np.int32)
+        rd = self._roads_desc(_np_ptr(xy), _np_ptr(rof), _np_ptr(rro), _np_ptr(bb), R, roads.n_rings, roads.n_verts)
+        td = N.RsTiles(None, _np_ptr(gt), gt.shape[0], height, width, channels, N.RS_U8)
+        pd_ = N.RsPairs(_np_ptr(rpo), _np_ptr(pt), pairs.n_pairs)
+        prm = self._params("bands", "crop", None, None)
+        st = self.lib.rs_zonal_stats_compressed_host(self._ctx, C.byref(rd), C.byref(td), C.byref(pd_), C.byref(prm),
+                                                     _NODATA_MODES[nodata_mode], int(ddof), _np_ptr(pct) if len(pct) else None, len(pct),
+                                                     _np_ptr(comp), _np_ptr(co), len(co) - 1, int(codec), _np_ptr(ro), int(planar),
+                                                     int(predictor), 0, _np_ptr(stats))
+        N.check(st, "rs_zonal_stats_compressed_host", self._ctx)
+        return stats
+
     def pin_host(self, array: np.ndarray) -> np.ndarray:
         """Page-lock a numpy buffer in place (rs_host_register) so that zonal_stats_host reads it without a copy; call
         unpin_host before the array is freed.  Returns the array."""
