@@ -36,7 +36,7 @@ constexpr int WBAND = 256;           // rows per band, at most
 constexpr int WMASKW = 8448;         // mask words per band (256 rows x 33 words; fewer rows for wider windows)
 constexpr int WQCAP = 160;           // entries of a warp's queue
 constexpr int WCHUNK = 128;          // vertices per chunk (bounds granularity = TMA transfer)
-constexpr int WGROUP = WT / WCHUNK;  // chunks per pipeline stage: one vertex per thread
+constexpr int WSUB = 64;             // vertices per TMA transfer (half a chunk): every warp runs its own two-stage pipeline
 constexpr int WRELCAP = 1024;        // chunks culled per sweep
 constexpr int WRINGCAP = 32;         // ring starts kept in shared memory
 constexpr int WMAXW = 2048;          // tile width limit (65 mask words per row)
@@ -149,13 +149,14 @@ __global__ void __launch_bounds__(256) wide_zero_rows_kernel(const int *__restri
 // shared memory of the CTA
 // ---------------------------------------------------------------------------------------------
 struct WideSmem {
-    alignas(16) uint32_t mask[WMASKW];
-    uint32_t rowinfo[WBAND];                         // first word | (last word + 1) << 8 of the row's inside mask, 0 = empty
+    alignas(16) uint32_t mask[WMASKW];               // all zero between bands: the pixel phase clears what it consumes
+    uint32_t rowinfo[WBAND];                         // edge phase: words toggled in the row (bit min(word, 31)); after the prefix:
+                                                     // first word | (last word + 1) << 8 of the row's inside mask; 0 = empty row
     uint32_t queue[WWARPS][WQCAP];
-    alignas(16) double2 verts[2][WGROUP][WCHUNK + 1];  // [stage][chunk of the group]: [0] = the vertex before the chunk
+    alignas(16) double2 verts[WWARPS][2][WSUB + 1];  // [warp][stage]: a half chunk, [0] = the vertex before it
     int rel[WRELCAP];
     int ring_start[WRINGCAP + 1];
-    alignas(8) uint64_t mbar[2];
+    alignas(8) uint64_t mbar[WWARPS][2];
     int s_pair, s_nrel, s_anyhb;
     uint32_t s_nz;
 };
@@ -222,13 +223,15 @@ __global__ void __launch_bounds__(WT, 1) zonal_wide_kernel(const WideArgs a)
     const uint32_t one = a.one;
 
     for (int i = tid; i < C * 8192; i += WT) hist[i] = 0;
-    if (tid == 0) {
-        mbar_init(&s.mbar[0], 1);
-        mbar_init(&s.mbar[1], 1);
-        s.s_nz = 0;
+    for (int i = tid; i < WMASKW; i += WT) s.mask[i] = 0;
+    for (int i = tid; i < WBAND; i += WT) s.rowinfo[i] = 0;
+    if (lane == 0) {
+        mbar_init(&s.mbar[warp][0], 1);
+        mbar_init(&s.mbar[warp][1], 1);
     }
+    if (tid == 0) s.s_nz = 0;
     __syncthreads();
-    uint32_t ph0 = 0, ph1 = 0;                       // mbarrier phases (uniform)
+    uint32_t ph0 = 0, ph1 = 0;                       // phases of this warp's two mbarriers (warp-uniform)
 
     for (;;) {
         if (tid == 0) s.s_pair = atomicAdd(a.work_counter, 1);
@@ -284,16 +287,158 @@ __global__ void __launch_bounds__(WT, 1) zonal_wide_kernel(const WideArgs a)
 
         for (int r0 = 0; r0 < g.h; r0 += rbal) {
             const int rc = min(rbal, g.h - r0);
-            __syncthreads();                                  // the previous band's pixel phase is done with the mask
-            for (int i = tid; i < rc * pitch; i += WT) s.mask[i] = 0;
-            for (int i = tid; i < rc; i += WT) s.rowinfo[i] = 0;
-            if (tid == 0) s.s_anyhb = 0;
             bool band_has_edges = false;
 
-            // ---------------- edge sweeps: 0 = crossings (toggles), 1 = horizontal-edge burns (after the prefix) ----------------
-            for (int pass = 0; pass < 2; pass++) {
+            // one edge of the road against this band: crossings toggle bits (pass 0), horizontal edges lying exactly on a scanline
+            // and running towards -x are burnt after the prefix (pass 1)
+            auto edge = [&](const double2 q1, const double2 q2, const int pass) {
+                const double x1 = __dadd_rn(g.inv0, __dmul_rn(q1.x, g.inv1));
+                const double y1 = __dadd_rn(g.inv3, __dmul_rn(q1.y, g.inv5));
+                const double x2 = __dadd_rn(g.inv0, __dmul_rn(q2.x, g.inv1));
+                const double y2 = __dadd_rn(g.inv3, __dmul_rn(q2.y, g.inv5));
+                if (y1 == y2) {
+                    const double fy = floor(y1);
+                    const bool hb = (x1 > x2) && (fy + 0.5 == y1) && fy >= (double)(r0 + g.yshift) && fy < (double)(r0 + g.yshift + rc);
+                    if (hb && pass == 0) s.s_anyhb = 1;
+                    if (hb && pass == 1) {
+                        const double hx1 = floor(__dadd_rn(x2, 0.5)), hx2 = floor(__dadd_rn(x1, 0.5));
+                        if (!(hx1 > (double)(g.wu - 1) || hx2 <= 0.0)) {
+                            const int xa = max((int)fmax(hx1, 0.0) - g.xshift, 0);
+                            const int xb = min((int)fmin(hx2 - 1.0, (double)(g.wu - 1)) - g.xshift, g.w - 1);
+                            const int row = (int)floor(y1) - g.yshift - r0;
+                            if (xa <= xb) {
+                                for (int kk = (lo + xa) >> 5; kk <= ((lo + xb) >> 5); kk++) {
+                                    const int b0 = max(lo + xa - 32 * kk, 0), b1 = min(lo + xb - 32 * kk, 31);
+                                    const uint32_t bits = (b1 >= 31 ? FULL : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
+                                    atomicOr(&s.mask[row * pitch + kk], bits);
+                                }
+                                s.rowinfo[row] = (uint32_t)pitch << 8;          // the whole row is rescanned
+                            }
+                        }
+                    }
+                } else if (pass == 0 && fmin(x1, x2) <= (double)(g.xshift + g.w) + 1.0) {
+                    const int ya = max(first_row_ge(fmin(y1, y2)) - g.yshift, r0);
+                    const int yb = min(last_row_lt(fmax(y1, y2)) - g.yshift, r0 + rc - 1);
+                    if (ya <= yb) {
+                        double dx1, dy1, dx2, dy2;
+                        if (y1 < y2) { dx1 = x1; dy1 = y1; dx2 = x2; dy2 = y2; }
+                        else         { dx1 = x2; dy1 = y2; dx2 = x1; dy2 = y1; }
+                        const double ea = __dsub_rn(dx2, dx1), eb = __dsub_rn(dy2, dy1), erb = __ddiv_rn(1.0, eb);
+                        for (int y = ya; y <= yb; y++) {
+                            // GDAL: intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1, then floor(intersect + 0.5);
+                            // reciprocal first, the correctly rounded division when the floor could differ
+                            const double dy = __dadd_rn(int2double_magic(y + g.yshift), 0.5);
+                            const double num = __dmul_rn(__dsub_rn(dy, dy1), ea);
+                            const double qf = __dmul_rn(num, erb);
+                            double v = __dadd_rn(__dadd_rn(qf, dx1), 0.5);
+                            double tt;
+                            int ti = rint_magic(fmin(fmax(v, -1.0e9), 1.0e9), tt);
+                            if (!(fabs(qf) < 1.0e9) || !(fabs(v) < 1.0e9) || fabs(__dsub_rn(v, tt)) < 1.0e-4) {
+                                v = __dadd_rn(__dadd_rn(__ddiv_rn(num, eb), dx1), 0.5);
+                                v = fmin(fmax(v, -1.0e9), 1.0e9);
+                                ti = rint_magic(v, tt);
+                            }
+                            const int fl = ti - (__dsub_rn(v, tt) < 0.0 ? 1 : 0) - g.xshift;
+                            if (fl < g.w) {
+                                const int bit = lo + max(fl, 0), word = bit >> 5;
+                                atomicXor(&s.mask[(y - r0) * pitch + word], 1u << (bit & 31));
+                                atomicOr(&s.rowinfo[y - r0], 1u << min(word, 31));
+                            }
+                        }
+                    }
+                }
+            };
+
+            // the edges of the chunks in s.rel: every warp takes chunks on its own, half a chunk (WSUB vertices + the one before)
+            // per TMA transfer through its private two-stage pipeline -- no block barrier inside the sweep
+            auto edge_sweep = [&](const int nrel, const int pass) {
+                const int ntask = 2 * nrel;
+                auto range = [&](int tsk, int &cs, int &ce) {
+                    cs = s.rel[tsk >> 1] * WCHUNK + (tsk & 1) * WSUB;
+                    ce = min(nv, cs + WSUB);
+                };
+                auto issue = [&](int tsk, int stg) {                 // lane 0
+                    int cs, ce;
+                    range(tsk, cs, ce);
+                    if (cs >= ce) return;
+                    const int from = cs > 0 ? cs - 1 : 0;
+                    const uint32_t bytes = (uint32_t)(ce - from) * 16u;
+                    mbar_arrive_expect_tx(&s.mbar[warp][stg], bytes);
+                    tma_bulk_g2s(&s.verts[warp][stg][from - cs + 1], a.xy + v0 + from, bytes, &s.mbar[warp][stg]);
+                };
+                int tsk = warp, stg = 0;
+                if (tsk < ntask && lane == 0) issue(tsk, 0);
+                for (; tsk < ntask; tsk += WWARPS, stg ^= 1) {
+                    if (tsk + WWARPS < ntask && lane == 0) issue(tsk + WWARPS, stg ^ 1);
+                    int cs, ce;
+                    range(tsk, cs, ce);
+                    if (cs < ce) {
+                        mbar_wait(&s.mbar[warp][stg], stg ? ph1 : ph0);
+                        if (stg) ph1 ^= 1u; else ph0 ^= 1u;
+                        for (int k = lane; cs + k < ce; k += 32) {
+                            const int i = cs + k;
+                            bool is_start;
+                            const int pr = ring_prev(i, is_start);
+                            edge(is_start ? __ldg(&a.xy[v0 + pr]) : s.verts[warp][stg][k], s.verts[warp][stg][k + 1], pass);
+                        }
+                    }
+                    __syncwarp();                                     // the stage is free for the transfer after next
+                }
+            };
+
+            for (int cs0 = 0; cs0 < nch; cs0 += WRELCAP) {
+                // ---------------- cull: chunks whose bounds reach a row of this band and are not right of the window ----------------
+                __syncthreads();                                      // s.rel / the previous sweep or band are done
+                if (tid == 0) { s.s_nrel = 0; if (cs0 == 0) s.s_anyhb = 0; }
+                __syncthreads();
+                for (int c = cs0 + tid; c < min(nch, cs0 + WRELCAP); c += WT) {
+                    const float4 b = __ldg(a.chunk_bounds + c_first + c);
+                    const double ya_ = __dadd_rn(g.inv3, __dmul_rn((double)b.x, g.inv5));
+                    const double yb_ = __dadd_rn(g.inv3, __dmul_rn((double)b.y, g.inv5));
+                    const double xa_ = __dadd_rn(g.inv0, __dmul_rn((double)b.z, g.inv1));
+                    const double xb_ = __dadd_rn(g.inv0, __dmul_rn((double)b.w, g.inv1));
+                    const double cy_lo = fmin(ya_, yb_) - 1.0 - (double)g.yshift, cy_hi = fmax(ya_, yb_) + 1.0 - (double)g.yshift;
+                    if (fmin(xa_, xb_) - 1.0 <= (double)(g.xshift + g.w) && cy_hi >= (double)r0 && cy_lo <= (double)(r0 + rc))
+                        s.rel[atomicAdd(&s.s_nrel, 1)] = c;
+                }
+                __syncthreads();
+                const int nrel = s.s_nrel;
+                if (nrel == 0) continue;
+                band_has_edges = true;
+                edge_sweep(nrel, 0);
+            }
+            if (!band_has_edges) continue;
+            __syncthreads();                                          // every toggle of the band is in
+
+            // ---------------- prefix: a warp per TOUCHED row, a lane per word ----------------
+            for (int row = warp; row < rc; row += WWARPS) {
+                const uint32_t touched = s.rowinfo[row];
+                if (!touched) continue;
+                uint32_t *mrow = s.mask + row * pitch;
+                uint32_t carry = 0;
+                int kfirst = 255, klast = -1;
+                for (int kb = 0; kb < pitch; kb += 32) {
+                    if (kb > 0 && !carry && !(touched >> 31)) break;  // nothing toggled beyond word 30 and no open span
+                    const int k = kb + lane;
+                    const uint32_t tg = k < pitch ? mrow[k] : 0u;
+                    const unsigned odd = __ballot_sync(FULL, __popc(tg) & 1);
+                    const uint32_t cin = carry ^ (uint32_t)(__popc(odd & ((1u << lane) - 1u)) & 1);
+                    uint32_t m = prefix_xor32(tg) ^ (cin ? FULL : 0u);
+                    const int hi_k = lo + g.w - 32 * k;                 // window columns end here
+                    if (hi_k < 32) m &= (hi_k <= 0 ? 0u : ((1u << hi_k) - 1u));
+                    if (k < pitch) mrow[k] = m;
+                    const unsigned nzw = __ballot_sync(FULL, m != 0u);
+                    if (nzw) {
+                        kfirst = min(kfirst, kb + __ffs(nzw) - 1);
+                        klast = max(klast, kb + 31 - __clz(nzw));
+                    }
+                    carry ^= (uint32_t)(__popc(odd) & 1);
+                }
+                if (lane == 0) s.rowinfo[row] = klast >= 0 ? ((uint32_t)kfirst | ((uint32_t)(klast + 1) << 8)) : 0u;
+            }
+            __syncthreads();
+            if (s.s_anyhb) {                                          // horizontal-edge burns: the same sweeps once more
                 for (int cs0 = 0; cs0 < nch; cs0 += WRELCAP) {
-                    // cull: chunks whose bounds reach a row of this band and are not right of the window
                     __syncthreads();
                     if (tid == 0) s.s_nrel = 0;
                     __syncthreads();
@@ -301,140 +446,14 @@ __global__ void __launch_bounds__(WT, 1) zonal_wide_kernel(const WideArgs a)
                         const float4 b = __ldg(a.chunk_bounds + c_first + c);
                         const double ya_ = __dadd_rn(g.inv3, __dmul_rn((double)b.x, g.inv5));
                         const double yb_ = __dadd_rn(g.inv3, __dmul_rn((double)b.y, g.inv5));
-                        const double xa_ = __dadd_rn(g.inv0, __dmul_rn((double)b.z, g.inv1));
-                        const double xb_ = __dadd_rn(g.inv0, __dmul_rn((double)b.w, g.inv1));
                         const double cy_lo = fmin(ya_, yb_) - 1.0 - (double)g.yshift, cy_hi = fmax(ya_, yb_) + 1.0 - (double)g.yshift;
-                        if (fmin(xa_, xb_) - 1.0 <= (double)(g.xshift + g.w) && cy_hi >= (double)r0 && cy_lo <= (double)(r0 + rc))
-                            s.rel[atomicAdd(&s.s_nrel, 1)] = c;
+                        if (cy_hi >= (double)r0 && cy_lo <= (double)(r0 + rc)) s.rel[atomicAdd(&s.s_nrel, 1)] = c;
                     }
                     __syncthreads();
-                    const int nrel = s.s_nrel, ngroups = (nrel + WGROUP - 1) / WGROUP;
-                    if (nrel == 0) continue;
-                    band_has_edges = true;
-                    // TMA pipeline: a group = up to WGROUP chunks, each with the vertex before it, into one stage
-                    auto issue = [&](int gi) {
-                        const int st = gi & 1;
-                        uint32_t bytes = 0;
-                        for (int j = 0; j < WGROUP && gi * WGROUP + j < nrel; j++) {
-                            const int c = s.rel[gi * WGROUP + j], cs = c * WCHUNK, ce = min(nv, cs + WCHUNK);
-                            bytes += (uint32_t)(ce - (cs > 0 ? cs - 1 : 0)) * 16u;
-                        }
-                        mbar_arrive_expect_tx(&s.mbar[st], bytes);
-                        for (int j = 0; j < WGROUP && gi * WGROUP + j < nrel; j++) {
-                            const int c = s.rel[gi * WGROUP + j], cs = c * WCHUNK, ce = min(nv, cs + WCHUNK);
-                            const int from = cs > 0 ? cs - 1 : 0;
-                            tma_bulk_g2s(&s.verts[st][j][from - cs + 1], a.xy + v0 + from, (uint32_t)(ce - from) * 16u, &s.mbar[st]);
-                        }
-                    };
-                    if (tid == 0) {
-                        issue(0);
-                        if (ngroups > 1) issue(1);
-                    }
-                    for (int gi = 0; gi < ngroups; gi++) {
-                        const int st = gi & 1;
-                        mbar_wait(&s.mbar[st], st ? ph1 : ph0);
-                        if (st) ph1 ^= 1u; else ph0 ^= 1u;
-                        const int j = tid / WCHUNK, k = tid % WCHUNK;
-                        if (gi * WGROUP + j < nrel) {
-                            const int c = s.rel[gi * WGROUP + j], cs = c * WCHUNK, i = cs + k;
-                            if (i < min(nv, cs + WCHUNK)) {
-                                const double2 q2 = s.verts[st][j][k + 1];
-                                bool is_start;
-                                const int pr = ring_prev(i, is_start);
-                                const double2 q1 = is_start ? __ldg(&a.xy[v0 + pr]) : s.verts[st][j][k];
-                                const double x1 = __dadd_rn(g.inv0, __dmul_rn(q1.x, g.inv1));
-                                const double y1 = __dadd_rn(g.inv3, __dmul_rn(q1.y, g.inv5));
-                                const double x2 = __dadd_rn(g.inv0, __dmul_rn(q2.x, g.inv1));
-                                const double y2 = __dadd_rn(g.inv3, __dmul_rn(q2.y, g.inv5));
-                                if (y1 == y2) {
-                                    // horizontal edge: burnt separately iff it lies exactly on a scanline of this band and runs
-                                    // towards -x
-                                    const double fy = floor(y1);
-                                    const bool hb = (x1 > x2) && (fy + 0.5 == y1) && fy >= (double)(r0 + g.yshift) &&
-                                                    fy < (double)(r0 + g.yshift + rc);
-                                    if (hb && pass == 0) s.s_anyhb = 1;
-                                    if (hb && pass == 1) {
-                                        const double hx1 = floor(__dadd_rn(x2, 0.5)), hx2 = floor(__dadd_rn(x1, 0.5));
-                                        if (!(hx1 > (double)(g.wu - 1) || hx2 <= 0.0)) {
-                                            const int xa = max((int)fmax(hx1, 0.0) - g.xshift, 0);
-                                            const int xb = min((int)fmin(hx2 - 1.0, (double)(g.wu - 1)) - g.xshift, g.w - 1);
-                                            const int row = (int)floor(y1) - g.yshift - r0;
-                                            if (xa <= xb) {
-                                                for (int kk = (lo + xa) >> 5; kk <= ((lo + xb) >> 5); kk++) {
-                                                    const int b0 = max(lo + xa - 32 * kk, 0), b1 = min(lo + xb - 32 * kk, 31);
-                                                    const uint32_t bits = (b1 >= 31 ? FULL : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
-                                                    atomicOr(&s.mask[row * pitch + kk], bits);
-                                                }
-                                                s.rowinfo[row] = (uint32_t)pitch << 8;          // the whole row is rescanned
-                                            }
-                                        }
-                                    }
-                                } else if (pass == 0 && fmin(x1, x2) <= (double)(g.xshift + g.w) + 1.0) {
-                                    const int ya = max(first_row_ge(fmin(y1, y2)) - g.yshift, r0);
-                                    const int yb = min(last_row_lt(fmax(y1, y2)) - g.yshift, r0 + rc - 1);
-                                    if (ya <= yb) {
-                                        double dx1, dy1, dx2, dy2;
-                                        if (y1 < y2) { dx1 = x1; dy1 = y1; dx2 = x2; dy2 = y2; }
-                                        else         { dx1 = x2; dy1 = y2; dx2 = x1; dy2 = y1; }
-                                        const double ea = __dsub_rn(dx2, dx1), eb = __dsub_rn(dy2, dy1), erb = __ddiv_rn(1.0, eb);
-                                        for (int y = ya; y <= yb; y++) {
-                                            // GDAL: intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1, then floor(intersect + 0.5);
-                                            // reciprocal first, the correctly rounded division when the floor could differ
-                                            const double dy = __dadd_rn(int2double_magic(y + g.yshift), 0.5);
-                                            const double num = __dmul_rn(__dsub_rn(dy, dy1), ea);
-                                            const double qf = __dmul_rn(num, erb);
-                                            double v = __dadd_rn(__dadd_rn(qf, dx1), 0.5);
-                                            double tt;
-                                            int ti = rint_magic(fmin(fmax(v, -1.0e9), 1.0e9), tt);
-                                            if (!(fabs(qf) < 1.0e9) || !(fabs(v) < 1.0e9) || fabs(__dsub_rn(v, tt)) < 1.0e-4) {
-                                                v = __dadd_rn(__dadd_rn(__ddiv_rn(num, eb), dx1), 0.5);
-                                                v = fmin(fmax(v, -1.0e9), 1.0e9);
-                                                ti = rint_magic(v, tt);
-                                            }
-                                            const int fl = ti - (__dsub_rn(v, tt) < 0.0 ? 1 : 0) - g.xshift;
-                                            if (fl < g.w) {
-                                                const int bit = lo + max(fl, 0);
-                                                atomicXor(&s.mask[(y - r0) * pitch + (bit >> 5)], 1u << (bit & 31));
-                                            }
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                        __syncthreads();                                  // everybody is done with stage st
-                        if (tid == 0 && gi + 2 < ngroups) issue(gi + 2);
-                    }
+                    edge_sweep(s.s_nrel, 1);
                 }
                 __syncthreads();
-                if (pass == 1 || !band_has_edges) break;
-
-                // ---------------- prefix: a warp per row, a lane per word ----------------
-                for (int row = warp; row < rc; row += WWARPS) {
-                    uint32_t *mrow = s.mask + row * pitch;
-                    uint32_t carry = 0;
-                    int kfirst = 255, klast = -1;
-                    for (int kb = 0; kb < pitch; kb += 32) {
-                        const int k = kb + lane;
-                        const uint32_t tg = k < pitch ? mrow[k] : 0u;
-                        const unsigned odd = __ballot_sync(FULL, __popc(tg) & 1);
-                        const uint32_t cin = carry ^ (uint32_t)(__popc(odd & ((1u << lane) - 1u)) & 1);
-                        uint32_t m = prefix_xor32(tg) ^ (cin ? FULL : 0u);
-                        const int hi_k = lo + g.w - 32 * k;                 // window columns end here
-                        if (hi_k < 32) m &= (hi_k <= 0 ? 0u : ((1u << hi_k) - 1u));
-                        if (k < pitch) mrow[k] = m;
-                        const unsigned nzw = __ballot_sync(FULL, m != 0u);
-                        if (nzw) {
-                            kfirst = min(kfirst, kb + __ffs(nzw) - 1);
-                            klast = max(klast, kb + 31 - __clz(nzw));
-                        }
-                        carry ^= (uint32_t)(__popc(odd) & 1);
-                    }
-                    if (lane == 0) s.rowinfo[row] = klast >= 0 ? ((uint32_t)kfirst | ((uint32_t)(klast + 1) << 8)) : 0u;
-                }
-                __syncthreads();
-                if (!s.s_anyhb) break;
             }
-            if (!band_has_edges) continue;
 
             // ---------------- pixels: every warp queues the 16-pixel groups of its rows and consumes them, a group per lane -------------
             uint32_t *q = s.queue[warp];
@@ -470,10 +489,13 @@ __global__ void __launch_bounds__(WT, 1) zonal_wide_kernel(const WideArgs a)
                 const uint32_t ri = s.rowinfo[row];
                 if (!ri) continue;
                 const int h0 = 2 * (int)(ri & 255u), h1 = 2 * (int)(ri >> 8);
-                const uint32_t *mrow = s.mask + row * pitch;
+                uint32_t *mrow = s.mask + row * pitch;
+                if (lane == 0) s.rowinfo[row] = 0;                    // consumed: back to the all-zero state
                 for (int hb = h0; hb < h1; hb += 32) {
                     const int h = hb + lane;
                     const uint32_t m16 = h < h1 ? (mrow[h >> 1] >> ((h & 1) * 16)) & 0xffffu : 0u;
+                    __syncwarp();
+                    if (h < h1 && (h & 1)) mrow[h >> 1] = 0;
                     const unsigned bal = __ballot_sync(FULL, m16 != 0u);
                     const int cnt = __popc(bal);
                     if (nq + cnt > WQCAP) {                             // drain the full rounds, keep the rest
