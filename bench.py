@@ -235,6 +235,14 @@ def rows_match(gpu_hist, gpu_nz, rows, oh, onz):
     return bool(np.array_equal(gh, oh) and np.array_equal(gz, onz))
 
 
+def u16_scale_range():
+    """(smin, smax) per band of the fused 16 -> 8 bit rescale for the synthetic uint16 tiles (uniform 0 .. 65535, 1 % zeros):
+    tif2cog.py:224-236 summarize_stats on the population statistics."""
+    mean, std = 0.99 * 32767.5, float(np.sqrt(0.99 * (65535.0 ** 2 / 3.0) - (0.99 * 32767.5) ** 2))
+    lo, hi = max(mean - 2.0 * std, 0.0), min(mean + 2.0 * std, 65535.0)          # identical for every band: the std over bands is 0
+    return [lo] * 4, [hi] * 4
+
+
 def spread(n, k):
     """k indices spread over range(n)"""
     return np.unique(np.linspace(0, n - 1, min(n, k)).astype(np.int64)) if n > 0 else np.zeros(0, np.int64)
@@ -370,9 +378,13 @@ def config_legs(args, eng, torch, dev, grid, sh, rr_gt_class, dr, dp, peak, traf
             roads16, pairs16, _ = sub_problem(sh.roads, sh.pairs, n16)
             dr16, dp16 = eng.upload_roads(roads16), eng.upload_pairs(pairs16)
         t = eng.synth_tiles_dev(grid.keys(tile_idx[:n16]), H, W, 4, dtype="u16", kind=0, gt=gt[:n16])
-        k, off = scale_params([150.0] * 4, [9000.0] * 4)
+        # scale ranges from the population, the way tif2cog.py:224-236 derives them (mean -+ 2 std of every band, then
+        # mean -+ std over the bands, clamped to [0, 65535]): the synthetic uint16 values are uniform, so the ranges are the
+        # whole 16 bits and the 8-bit outputs spread over all 256 bins
+        smin16, smax16 = u16_scale_range()
+        k, off = scale_params(smin16, smax16)
         for f32 in (False, True):
-            rs = (k, off, f32) if not f32 else scale_params([150.0] * 4, [9000.0] * 4, True) + (True,)
+            rs = (k, off, f32) if not f32 else scale_params(smin16, smax16, True) + (True,)
             out = eng.zonal_hist_dev(dr16, t, dp16, rescale=rs, check=False)
             ms = time_loop(torch, lambda: eng.zonal_hist_dev(dr16, t, dp16, rescale=rs, out=out, check=False), args.leg_steps, 3)
             eng.sync_status()

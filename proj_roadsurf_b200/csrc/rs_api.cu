@@ -158,7 +158,7 @@ int rs_ctx_destroy(rs_ctx *ctx)
     if (ctx->items.p) cudaFree(ctx->items.p);
     if (ctx->pgeom.p) cudaFree(ctx->pgeom.p);
     if (ctx->pair_zero.p) cudaFree(ctx->pair_zero.p);
-    for (rs::DevBuf *b : {&ctx->wide_cnt, &ctx->wide_off, &ctx->wide_bounds, &ctx->wide_pair_road, &ctx->wide_tmp})
+    for (rs::DevBuf *b : {&ctx->wide_cnt, &ctx->wide_off, &ctx->wide_bounds, &ctx->wide_flags, &ctx->wide_pair_road, &ctx->wide_tmp})
         if (b->p) cudaFree(b->p);
     if (ctx->lut_dev.p) cudaFree(ctx->lut_dev.p);
     if (ctx->lzw_scratch.p) cudaFree(ctx->lzw_scratch.p);

@@ -34,7 +34,7 @@ struct rs_ctx {
     rs::DevBuf pgeom;                     // grow-only per-pair geometry records of the zonal kernel
     rs::DevBuf pair_zero;                 // grow-only per-pair zero counts (min_zero of row-split pairs on tall tiles)
     rs::DevBuf pool, heads, ov_items;     // grow-only entry pool / per-item segment heads / overflow items of the two-kernel form
-    rs::DevBuf wide_cnt, wide_off, wide_bounds, wide_pair_road, wide_tmp;   // per-launch tables of the wide-window kernel (rs_wide.cu)
+    rs::DevBuf wide_cnt, wide_off, wide_bounds, wide_flags, wide_pair_road, wide_tmp;   // per-launch tables of the wide-window kernel (rs_wide.cu)
     cudaEvent_t ev_scratch = nullptr;     // recorded after every launch that uses the scratch above
     cudaStream_t scratch_stream = nullptr;
     bool scratch_used = false;
@@ -45,6 +45,9 @@ struct rs_ctx {
     double lut_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t lut_k[4] = {0, 0, 0, 0};
     long long lut_b[4] = {0, 0, 0, 0};
+    bool guard_valid = false, guard_ok = false;   // guarded float32 rescale (PxU16x4Guard): verified parameters
+    double guard_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float guard_k[4] = {0, 0, 0, 0}, guard_o[4] = {0, 0, 0, 0}, guard_g[4] = {0, 0, 0, 0};
     void *comm = nullptr;                 // ncclComm_t of rs_comm_init (rs_comm.cu)
     int comm_world = 0, comm_rank = 0;
 };

@@ -824,8 +824,8 @@ def test_wide_kernel_window_modes_and_slots(eng, monkeypatch):
 
 @pytest.mark.parametrize("f32", [False, True])
 def test_u16_rescale_integer_form_equals_floating_form(eng, f32, monkeypatch):
-    """PxU16x4Lut (thresholds + fixed-point guess, verified on all 65 536 inputs by the launcher) against the floating-point
-    policy (RS_ZONAL_LUT=0) and the oracle, for ordinary ranges, for ranges whose steps fall on exact .5 ties, and for a
+    """PxU16x4Lut (thresholds + fixed-point guess) and PxU16x4Guard (float32 with an undecided zone that falls back to binary64),
+    both verified on all 65 536 inputs by the launcher, against the floating-point policy (RS_ZONAL_LUT=0) and the oracle, for ordinary ranges, for ranges whose steps fall on exact .5 ties, and for a
     range narrower than 255 (scale >= 1: the integer form is refused and the floating one runs)."""
     from proj_roadsurf_b200.engine import scale_params
     g = synth.Grid(3, 3)
@@ -839,10 +839,13 @@ def test_u16_rescale_integer_form_equals_floating_form(eng, f32, monkeypatch):
                        ([0.0, 0.0, 0.0, 0.0], [510.0, 65535.0, 1020.0, 256.0]),          # k = 1/2, 1/257, 1/4: ties at x.5
                        ([1000.0, 10.0, 0.0, 100.0], [1100.0, 60000.0, 65535.0, 600.0])):   # 100-wide range: scale 2.55
         k, off = scale_params(smin, smax, f32)
-        monkeypatch.setenv("RS_ZONAL_LUT", "1")
+        monkeypatch.setenv("RS_ZONAL_LUT", "1")                # integer thresholds
         h1, z1 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
-        monkeypatch.setenv("RS_ZONAL_LUT", "0")
+        monkeypatch.setenv("RS_ZONAL_LUT", "0")                # plain floating point
         h0, z0 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
         assert np.array_equal(h1, h0) and np.array_equal(z1, z0), (smin, smax)
+        monkeypatch.delenv("RS_ZONAL_LUT")                     # the default: guarded float32 for the binary64 semantics
+        h2, z2 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
+        assert np.array_equal(h2, h0) and np.array_equal(z2, z0), (smin, smax)
         oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt, scale_k=k, scale_off=off, rescale_f32=f32)
         assert np.array_equal(h1.astype(np.uint64), oh) and np.array_equal(z1.astype(np.uint64), onz), (smin, smax)
