@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-legs", action="store_true", help="skip the full-size legs of the other BASELINE configurations (N = 1)")
     ap.add_argument("--leg-steps", type=int, default=5)
     ap.add_argument("--wide-grid", type=int, default=64, help="configs[4] leg: tiles per side of the 1024 px lattice (64 -> 4096 tiles)")
-    ap.add_argument("--wide-polys", type=int, default=1536)
+    ap.add_argument("--wide-polys", type=int, default=1024, help="configs[4] leg: polygons of the dense variant (the sparse one has a quarter)")
     ap.add_argument("--pageable-rows", type=int, default=96, help="tile rows of the pageable-caller e2e sample")
     ap.add_argument("--no-pageable", action="store_true")
     ap.add_argument("--compressed-rows", type=int, default=32, help="tile rows of the compressed-tiles e2e sample")
@@ -399,23 +399,28 @@ def config_legs(args, eng, torch, dev, grid, sh, rr_gt_class, dr, dp, peak, traf
         torch.cuda.empty_cache()
 
     # ---- configs[4]: 1024 px tiles, wide polygons with holes and 1 k - 10 k vertices (long edge lists) ----
+    # two densities of the same polygons: "dense" = the tiles are covered 1.25 times over (every pixel is read and histogrammed
+    # once per polygon above it, so the work is 1.25 x the tile bytes), "sparse" = a third of the surface, closer to a road network
     g5 = synth.Grid(args.wide_grid, args.wide_grid, size=1024)
-    wp = synth.wide_polygons(g5, args.wide_polys)
     t5 = eng.synth_tiles_dev(g5.keys(), 1024, 1024, 3, kind=0, gt=g5.transforms())
-    d5r, d5p = eng.upload_roads(wp.roads), eng.upload_pairs(wp.pairs)
-    o5 = eng.zonal_hist_dev(d5r, t5, d5p, check=False)
-    ms5 = time_loop(torch, lambda: eng.zonal_hist_dev(d5r, t5, d5p, out=o5, check=False), args.leg_steps, 2)
-    eng.sync_status()
-    smp = spread(wp.roads.n_roads, 6)
-    oh, onz = oracle_rows(eng, g5, wp.roads, wp.pairs, smp, t5, 0, g5.n_tiles, size=1024)
-    cov5 = float(o5[0][:, 0].sum().item()) / (g5.n_tiles * 1024.0 * 1024.0)
-    nv5 = np.diff(wp.roads.ring_off[wp.roads.road_ring_off])
-    legs["wide_polygons_1024px"] = leg_entry(ms5, g5.n_tiles * 1024 * 1024, 3, "wide_polygons_1024px",
-                                             rows_match(o5[0], o5[1], smp, oh, onz),
-                                             config="configs[4]: 10 cm 1024x1024 tiles, 100-300 px wide polygons with 1-8 holes",
-                                             tiles=g5.n_tiles, polygons=int(wp.roads.n_roads), pairs=int(wp.pairs.n_pairs),
-                                             covered_fraction=cov5, mean_vertices=float(nv5.mean()), max_vertices=int(nv5.max()))
-    del t5, o5
+    for name, n_poly in (("wide_polygons_1024px", args.wide_polys), ("wide_polygons_1024px_sparse", max(1, args.wide_polys // 4))):
+        wp = synth.wide_polygons(g5, n_poly)
+        d5r, d5p = eng.upload_roads(wp.roads), eng.upload_pairs(wp.pairs)
+        o5 = eng.zonal_hist_dev(d5r, t5, d5p, check=False)
+        ms5 = time_loop(torch, lambda: eng.zonal_hist_dev(d5r, t5, d5p, out=o5, check=False), args.leg_steps, 2)
+        eng.sync_status()
+        smp = spread(wp.roads.n_roads, 6)
+        oh, onz = oracle_rows(eng, g5, wp.roads, wp.pairs, smp, t5, 0, g5.n_tiles, size=1024)
+        cov5 = float(o5[0][:, 0].sum().item()) / (g5.n_tiles * 1024.0 * 1024.0)
+        nv5 = np.diff(wp.roads.ring_off[wp.roads.road_ring_off])
+        legs[name] = leg_entry(ms5, g5.n_tiles * 1024 * 1024, 3, name, rows_match(o5[0], o5[1], smp, oh, onz),
+                               config="configs[4]: 10 cm 1024x1024 tiles, 100-300 px wide polygons with 1-8 holes",
+                               kernel="zonal_wide_kernel (rs_wide.cu)", tiles=g5.n_tiles, polygons=int(wp.roads.n_roads),
+                               pairs=int(wp.pairs.n_pairs), covered_fraction=cov5,
+                               covered_Gpixel_s=cov5 * g5.n_tiles * 1024 * 1024 / (ms5 * 1e-3) / 1e9,
+                               mean_vertices=float(nv5.mean()), max_vertices=int(nv5.max()))
+        del o5, d5r, d5p
+    del t5
     torch.cuda.empty_cache()
     return legs
 

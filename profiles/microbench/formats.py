@@ -1,6 +1,6 @@
 """One tile format of the fused kernel at a chosen size, for ncu captures and quick comparisons; run on a B200:
     python profiles/microbench/formats.py --format u16lut --tiles 128 [--once]
-formats: u8x3, u8x4, class_score, u16f64, u16f32 (RS_ZONAL_LUT=0), u16lut (=1), u16guard (the default for the binary64 semantics)"""
+formats: u8x3, u8x4, class_score, u16f64, u16f32 (RS_ZONAL_LUT=0), u16lut (RS_ZONAL_LUT=1, the default for the binary64 semantics)"""
 import argparse
 import json
 import os
@@ -25,10 +25,8 @@ fmt = args.format
 ch, dtype, kind, kw, bpp = {"u8x3": (3, "u8", 0, {}, 3), "u8x4": (4, "u8", 0, {}, 4), "class_score": (2, "u8", 2, {"hist_mode": "class_score"}, 2),
                             "u16f64": (4, "u16", 0, {"rescale": scale_params([0.0] * 4, [65535.0] * 4) + (False,)}, 8),
                             "u16f32": (4, "u16", 0, {"rescale": scale_params([0.0] * 4, [65535.0] * 4, True) + (True,)}, 8),
-                            "u16lut": (4, "u16", 0, {"rescale": scale_params([0.0] * 4, [65535.0] * 4) + (False,)}, 8),
-                            "u16guard": (4, "u16", 0, {"rescale": scale_params([0.0] * 4, [65535.0] * 4) + (False,)}, 8)}[fmt]
-if fmt != "u16guard":
-    os.environ["RS_ZONAL_LUT"] = "1" if fmt == "u16lut" else "0"
+                            "u16lut": (4, "u16", 0, {"rescale": scale_params([0.0] * 4, [65535.0] * 4) + (False,)}, 8)}[fmt]
+os.environ["RS_ZONAL_LUT"] = "1" if fmt == "u16lut" else "0"
 t = eng.synth_tiles_dev(g.keys(), 256, 256, ch, dtype=dtype, kind=kind, gt=g.transforms())
 out = eng.zonal_hist_dev(dr, t, dp, **kw)
 if not args.once:

@@ -45,9 +45,6 @@ struct rs_ctx {
     double lut_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t lut_k[4] = {0, 0, 0, 0};
     long long lut_b[4] = {0, 0, 0, 0};
-    bool guard_valid = false, guard_ok = false;   // guarded float32 rescale (PxU16x4Guard): verified parameters
-    double guard_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float guard_k[4] = {0, 0, 0, 0}, guard_o[4] = {0, 0, 0, 0}, guard_g[4] = {0, 0, 0, 0};
     void *comm = nullptr;                 // ncclComm_t of rs_comm_init (rs_comm.cu)
     int comm_world = 0, comm_rank = 0;
 };

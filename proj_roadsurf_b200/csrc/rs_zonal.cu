@@ -40,6 +40,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "rs_internal.h"
 #include "rs_raster.cuh"
 
@@ -116,7 +118,6 @@ struct ZonalArgs {
     uint32_t lut_k[4];
     long long lut_b[4];
     const uint32_t *lut_lohi;
-    float gk[4], go[4], gg[4];   // PxU16x4Guard: float32 scale / offset and the width of the undecided zone around x.5
     int *work_counter;
     int *status;
     // two-kernel form
@@ -315,67 +316,21 @@ struct PxU16x4Rescale {
     }
 };
 
-// binary64 semantics at float32 cost: the value is first evaluated in float32; when clamp(f) + 0.5 is farther from an integer
-// than the float32 evaluation can be off (gg, a few 1e-4), its floor is the binary64 result; only the few values inside that zone
-// take the binary64 expression (the same guard idea as the crossing evaluation).  The launcher checks all 65 536 inputs of every
-// band on the host before selecting this policy.
-struct PxU16x4Guard {
-    static constexpr int C = 4, HC = 4, BPP = 8, NW = 16;
-    static constexpr bool MASK = false, EMIT = false, FLT = false, EXTRACT = false;
-    __device__ static __forceinline__ uint32_t scale(const ZonalArgs &a, uint32_t s, int c)
-    {
-        const float sf = __fsub_rn(__uint_as_float(0x4b000000u | s), 8388608.0f);          // exact for s < 2^23, no conversion unit
-        const float f = __fadd_rn(__fmul_rn(sf, a.gk[c]), a.go[c]);
-        const float t = __fadd_rn(f, 0.5f);
-        const float tc = fminf(fmaxf(t, 0.0f), 256.0f);
-        const float r = __fsub_rn(__fadd_rn(tc, 12582912.0f), 12582912.0f);                // rint(tc)
-        if (fabsf(__fsub_rn(tc, r)) < a.gg[c] && fabsf(__fsub_rn(tc, 128.0f)) < 127.25f) {      // undecided: tc within gg of 1 .. 255
-            double d = __dadd_rn(__dmul_rn((double)s, a.sk[c]), a.so[c]);
-            d = fmin(fmax(d, 0.0), 255.0);
-            return (uint32_t)(int)__dadd_rn(d, 0.5);
-        }
-        const float fc = fminf(fmaxf(f, 0.0f), 255.0f);
-        return __float_as_uint(__fadd_rn(fc, 12582912.0f)) & 0x1ffu;                       // rint(fc) == floor(fc + 0.5) away from x.5
-    }
-    template <int I>
-    __device__ static __forceinline__ void pixel(const ZonalArgs &a, const uint32_t (&r)[NW], uint32_t on, uint32_t hist, uint32_t one, uint32_t &nz)
-    {
-        uint32_t any = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const uint32_t o = scale(a, (r[(I * 8 + 2 * c) >> 2] >> (((I * 8 + 2 * c) & 3) * 8)) & 0xffffu, c);
-            red_inc1(hist + 4u * (c * 256u + o), on);
-            any |= o;
-        }
-        nz += (any == 0) ? on : 0u;
-    }
-    __device__ static __forceinline__ void pixel_slow(const ZonalArgs &a, size_t pix, uint32_t *hist, uint32_t &nz)
-    {
-        const uint16_t *p = (const uint16_t *)a.pixels + pix * 4;
-        uint32_t any = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const uint32_t o = scale(a, __ldg(p + c), c);
-            atomicAdd(&hist[c * 256 + o], 1u);
-            any |= o;
-        }
-        nz += (any == 0);
-    }
-};
-
 // the same rescale without floating point in the pixel loop: gdal.Translate's  byte(clamp(s k + off, 0, 255) + 0.5)  is a
 // non-decreasing step function of the 16-bit source value, so it is fixed by the 255 source values at which it steps.  The
 // launcher tabulates them per band with the exact arithmetic of PxU16x4Rescale (either precision), checks on ALL 65 536 inputs
 // that a 32.32 fixed-point guess is never more than one step off, and only then selects this policy: bit-identical by
 // construction, four integer instructions and one L1-resident table read per band byte instead of the FP64 / XU pipe.
+__shared__ uint32_t g_lut_s[4 * 256];        // PxU16x4Lut: the CTA's copy of the thresholds (static: in front of the team memory)
+
 struct PxU16x4Lut {
     static constexpr int C = 4, HC = 4, BPP = 8, NW = 16;
-    static constexpr bool MASK = false, EMIT = false, FLT = false, EXTRACT = false;
+    static constexpr bool MASK = false, EMIT = false, FLT = false, EXTRACT = false, LUT = true;
     __device__ static __forceinline__ uint32_t scale(const ZonalArgs &a, uint32_t s, int c)
     {
         const long long t = (long long)((unsigned long long)s * a.lut_k[c]) + a.lut_b[c];
         const int g = min(max((int)(t >> 32), 0), 255);
-        const uint32_t lh = __ldg(a.lut_lohi + c * 256 + g);
+        const uint32_t lh = g_lut_s[c * 256 + g];
         return (uint32_t)(g + (s > (lh >> 16) ? 1 : 0) - (s < (lh & 0xffffu) ? 1 : 0));
     }
     template <int I>
@@ -1111,6 +1066,10 @@ __global__ void __launch_bounds__(WARPS * 32, PX::EMIT ? EMIT_CTAS : CTAS_PER_SM
         return;
     }
     S &s = reinterpret_cast<S *>(smem_raw)[warp];
+    if constexpr (std::is_same<PX, PxU16x4Lut>::value) {
+        for (int i = threadIdx.x; i < 4 * 256; i += WARPS * 32) g_lut_s[i] = __ldg(a.lut_lohi + i);
+        __syncthreads();
+    }
     if (lane == 0) mbar_init(&s.mbar, 1);
     for (int i = lane; i < MASKW / 4; i += 32) reinterpret_cast<uint4 *>(s.mask)[i] = make_uint4(0, 0, 0, 0);
     for (int i = lane; i < RCMAX / 4; i += 32) reinterpret_cast<uint4 *>(s.rowmap)[i] = make_uint4(0, 0, 0, 0);
@@ -1466,51 +1425,6 @@ static inline int rescale_exact(unsigned s, double k, double off, bool f32)
     return (int)(f + 0.5);
 }
 
-// PxU16x4Guard on the host, operation for operation (IEEE float32 / float64, no contraction)
-static inline int rescale_guarded(unsigned s, double k, double off, float gk, float go, float gg)
-{
-    volatile float m = (float)s * gk;
-    volatile float f = m + go;
-    volatile float t = f + 0.5f;
-    float tc = t < 0.0f ? 0.0f : (t > 256.0f ? 256.0f : t);
-    volatile float tm = tc + 12582912.0f;
-    volatile float r = tm - 12582912.0f;
-    volatile float d1 = tc - r, d2 = tc - 128.0f;
-    if (fabsf(d1) < gg && fabsf(d2) < 127.25f) return rescale_exact(s, k, off, false);
-    float fc = f < 0.0f ? 0.0f : (f > 255.0f ? 255.0f : f);
-    volatile float q = fc + 12582912.0f;
-    float qf = q;
-    uint32_t bits;
-    memcpy(&bits, &qf, 4);
-    return (int)(bits & 0x1ffu);
-}
-
-// returns 1 when the guarded float32 form reproduces the binary64 rescale on all 65 536 inputs of all 4 bands (args filled)
-static int prepare_rescale_guard(rs_ctx *ctx, const rs_zonal_params *prm, ZonalArgs &a)
-{
-    bool same = ctx->guard_valid;
-    for (int c = 0; c < 4 && same; c++) same = ctx->guard_key[c] == prm->scale_k[c] && ctx->guard_key[4 + c] == prm->scale_off[c];
-    if (!same) {
-        bool ok = true;
-        for (int c = 0; c < 4 && ok; c++) {
-            const double k = prm->scale_k[c], off = prm->scale_off[c];
-            if (!(k == k) || !(off == off) || fabs(k) > 1.0e3 || fabs(off) > 1.0e7) { ok = false; break; }
-            ctx->guard_k[c] = (float)k;
-            ctx->guard_o[c] = (float)off;
-            ctx->guard_g[c] = (float)(4.0e-7 * (65535.0 * fabs(k) + fabs(off) + 256.0) + 1.0e-6);
-            if (!(ctx->guard_g[c] < 0.25f)) { ok = false; break; }
-            for (unsigned sv = 0; sv < 65536u && ok; sv++)
-                if (rescale_guarded(sv, k, off, ctx->guard_k[c], ctx->guard_o[c], ctx->guard_g[c]) != rescale_exact(sv, k, off, false)) ok = false;
-        }
-        for (int c = 0; c < 4; c++) { ctx->guard_key[c] = prm->scale_k[c]; ctx->guard_key[4 + c] = prm->scale_off[c]; }
-        ctx->guard_ok = ok;
-        ctx->guard_valid = true;
-    }
-    if (!ctx->guard_ok) return 0;
-    for (int c = 0; c < 4; c++) { a.gk[c] = ctx->guard_k[c]; a.go[c] = ctx->guard_o[c]; a.gg[c] = ctx->guard_g[c]; }
-    return 1;
-}
-
 // returns 1 when the integer form is exact for all 65 536 inputs of all 4 bands (tables uploaded, args filled), 0 otherwise
 static int prepare_rescale_lut(rs_ctx *ctx, const rs_zonal_params *prm, ZonalArgs &a, cudaStream_t st)
 {
@@ -1745,12 +1659,11 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     else if (masks) rc = launch_one<PxMask>(ctx, a, st);
     else if (prm->hist_mode == RS_HIST_CLASS_SCORE) rc = launch_one<PxClassScore>(ctx, a, st);
     else if (tiles->dtype == RS_U16) {
-        // RS_ZONAL_LUT: 0 = the plain floating-point policies, 1 = integer thresholds (PxU16x4Lut), default = for the binary64
-        // semantics the guarded float32 evaluation (PxU16x4Guard), for the float32 semantics the float32 policy itself
+        // the binary64 semantics go through the integer thresholds (PxU16x4Lut) when the launcher could verify them, the float32
+        // semantics through the float32 policy itself (already at the roofline); RS_ZONAL_LUT=0 / 1 forces plain / thresholds
         const char *env = getenv("RS_ZONAL_LUT");
-        const int mode = env ? atoi(env) : 2;
+        const int mode = env ? atoi(env) : (prm->rescale == 1 ? 1 : 0);
         if (mode == 1 && prepare_rescale_lut(ctx, prm, a, st)) rc = launch_one<PxU16x4Lut>(ctx, a, st);
-        else if (mode == 2 && prm->rescale == 1 && prepare_rescale_guard(ctx, prm, a)) rc = launch_one<PxU16x4Guard>(ctx, a, st);
         else rc = prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);
     }
     else

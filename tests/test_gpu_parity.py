@@ -824,8 +824,8 @@ def test_wide_kernel_window_modes_and_slots(eng, monkeypatch):
 
 @pytest.mark.parametrize("f32", [False, True])
 def test_u16_rescale_integer_form_equals_floating_form(eng, f32, monkeypatch):
-    """PxU16x4Lut (thresholds + fixed-point guess) and PxU16x4Guard (float32 with an undecided zone that falls back to binary64),
-    both verified on all 65 536 inputs by the launcher, against the floating-point policy (RS_ZONAL_LUT=0) and the oracle, for ordinary ranges, for ranges whose steps fall on exact .5 ties, and for a
+    """PxU16x4Lut (thresholds + fixed-point guess, verified on all 65 536 inputs by the launcher) against the floating-point
+    policy (RS_ZONAL_LUT=0) and the oracle, for ordinary ranges, for ranges whose steps fall on exact .5 ties, and for a
     range narrower than 255 (scale >= 1: the integer form is refused and the floating one runs)."""
     from proj_roadsurf_b200.engine import scale_params
     g = synth.Grid(3, 3)
@@ -844,7 +844,7 @@ def test_u16_rescale_integer_form_equals_floating_form(eng, f32, monkeypatch):
         monkeypatch.setenv("RS_ZONAL_LUT", "0")                # plain floating point
         h0, z0 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
         assert np.array_equal(h1, h0) and np.array_equal(z1, z0), (smin, smax)
-        monkeypatch.delenv("RS_ZONAL_LUT")                     # the default: guarded float32 for the binary64 semantics
+        monkeypatch.delenv("RS_ZONAL_LUT")                     # the default choice of the launcher
         h2, z2 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
         assert np.array_equal(h2, h0) and np.array_equal(z2, z0), (smin, smax)
         oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, gt, scale_k=k, scale_off=off, rescale_f32=f32)
