@@ -5,9 +5,9 @@
 // (scripts/functions/fct_misc.py:76-77; the tiles of config/config_stats.yaml:39 are deflate- or LZW-compressed COGs).
 //
 //   codec 8 / 32946  zlib-wrapped DEFLATE (RFC 1950 / 1951): stored, fixed and dynamic Huffman blocks; canonical codes are
-//                    decoded bit by bit from per-length counts (no per-thread look-up tables: a decoder's whole state is
-//                    ~1.3 KB of local memory, so hundreds of thousands of segments decode concurrently); matches copy from the
-//                    output itself (the 32 KiB window is the already written part of the segment)
+//                    decoded bit by bit from per-length counts; a decoder's tables are ~1 KiB and live in SHARED memory (column
+//                    t of the block's arrays belongs to thread t), 64 decoders per block; matches copy from the output itself
+//                    (the 32 KiB window is the already written part of the segment); the Adler-32 trailer is checked
 //   codec 5          TIFF LZW (MSB-first codes of 9 - 12 bits, ClearCode 256, EOI 257, the "early change" of libtiff); the
 //                    string table (4096 x 6 bytes per decoder) lives in a scratch buffer, decoders run grid-strided
 //   codec 1          none: a copy
@@ -37,8 +37,14 @@ struct CodecArgs {
     int *bad_segment;                 // index of (one of) the failing segments, -1 = none
 };
 
-__global__ void __launch_bounds__(64) decode_kernel(const CodecArgs a)
+constexpr int DEC_THREADS = 64;       // decoders per block: their DEFLATE tables fill 64 KiB of shared memory, three blocks per SM
+
+__global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const CodecArgs a)
 {
+    // column t of the two arrays is thread t's table space (rs_codec_core.h)
+    extern __shared__ __align__(16) unsigned char dec_smem[];
+    uint16_t *tab16 = reinterpret_cast<uint16_t *>(dec_smem);
+    uint8_t *tab8 = dec_smem + sizeof(uint16_t) * RS_INFLATE_U16 * DEC_THREADS;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     for (int s = tid; s < a.n_seg; s += nthr) {
         const uint8_t *src = a.comp + a.comp_off[s];
@@ -52,7 +58,7 @@ __global__ void __launch_bounds__(64) decode_kernel(const CodecArgs a)
         } else if (a.codec == 5)
             got = lzw_segment(src, n, dst, cap, a.lzw_tab + (size_t)tid * 4096, a.lzw_len + (size_t)tid * 4096);
         else
-            got = inflate_segment(src, n, dst, cap, true);
+            got = inflate_segment(src, n, dst, cap, true, tab16 + threadIdx.x, tab8 + threadIdx.x, DEC_THREADS);
         // libtiff pads nothing: a strip decodes to exactly rows * row_bytes (the last strip of an image to its remaining rows)
         if (got != cap) {
             atomicMin(a.status, (int)RS_ERR_CODEC);
@@ -69,17 +75,20 @@ int launch_decode_segments(rs_ctx *ctx, const uint8_t *comp, const long long *co
     if (n_seg <= 0) return RS_OK;
     if (codec != 1 && codec != 5 && codec != 8 && codec != 32946) return RS_ERR_UNSUPPORTED;
     CodecArgs a{comp, comp_off, raw, raw_off, n_seg, codec == 32946 ? 8 : codec, nullptr, nullptr, ctx->d_status, ctx->d_counters + 8};
-    int blocks = (n_seg + 63) / 64;
+    int blocks = (n_seg + DEC_THREADS - 1) / DEC_THREADS;
+    if (blocks > ctx->sm_count * 48) blocks = ctx->sm_count * 48;       // grid-stride over the segments
     if (codec == 5) {                                      // string tables: bound the number of concurrent decoders
         const int max_blocks = ctx->sm_count * 2;
         if (blocks > max_blocks) blocks = max_blocks;
-        int rc = ensure(ctx, ctx->lzw_scratch, (size_t)blocks * 64 * 4096 * (sizeof(uint32_t) + sizeof(uint16_t)));
+        int rc = ensure(ctx, ctx->lzw_scratch, (size_t)blocks * DEC_THREADS * 4096 * (sizeof(uint32_t) + sizeof(uint16_t)));
         if (rc) return rc;
         a.lzw_tab = (uint32_t *)ctx->lzw_scratch.p;
-        a.lzw_len = (uint16_t *)(a.lzw_tab + (size_t)blocks * 64 * 4096);
+        a.lzw_len = (uint16_t *)(a.lzw_tab + (size_t)blocks * DEC_THREADS * 4096);
     }
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0xff, sizeof(int), st));     // bad_segment = -1
-    decode_kernel<<<blocks, 64, 0, st>>>(a);
+    const size_t smem = (sizeof(uint16_t) * RS_INFLATE_U16 + RS_INFLATE_U8) * DEC_THREADS;
+    RS_CUDA_OK(ctx, cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    decode_kernel<<<blocks, DEC_THREADS, smem, st>>>(a);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
     return RS_OK;

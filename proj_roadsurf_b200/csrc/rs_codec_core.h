@@ -48,38 +48,47 @@ struct Bits {                         // LSB-first bit reader over [p, p + n)
     }
 };
 
+// A decoder's tables live where its caller puts them: element i of an array is at base[i * stride].  On the device the base is
+// a slot of the block's shared memory and the stride the block size (thread t owns column t: a table read is a shared-memory
+// access, not a trip through local memory to L2 / HBM -- with hundreds of thousands of resident decoders the tables would
+// not even fit L2); on the host (tests) stride is 1.
 struct Huff {                         // canonical code: symbols ordered by (length, value), count of codes per length
-    uint16_t count[16];
-    uint16_t symbol[288];
+    uint16_t *count;                  // [16]
+    uint16_t *symbol;                 // [288] (literal / length) or [30] (distance)
+    int stride;
 };
+enum { RS_INFLATE_U16 = 16 + 288 + 16 + 30 + 16, RS_INFLATE_U8 = 320 };     // table space of one decoder: uint16 + uint8 elements
 
 // lengths[0 .. n) -> canonical code; returns false for an over-subscribed set (an incomplete set is accepted, as zlib accepts
-// the single-code distance trees real encoders write)
-RS_HD bool huff_build(Huff &h, const uint8_t *len, int n)
+// the single-code distance trees real encoders write).  offs: 16 uint16 of scratch (same stride)
+RS_HD bool huff_build(Huff &h, const uint8_t *len, int lstride, int n, uint16_t *offs)
 {
-    for (int i = 0; i < 16; i++) h.count[i] = 0;
-    for (int i = 0; i < n; i++) h.count[len[i]]++;
+    const int st = h.stride;
+    for (int i = 0; i < 16; i++) h.count[i * st] = 0;
+    for (int i = 0; i < n; i++) h.count[len[i * lstride] * st]++;
     int left = 1;
     for (int l = 1; l < 16; l++) {
         left <<= 1;
-        left -= h.count[l];
+        left -= h.count[l * st];
         if (left < 0) return false;
     }
-    uint16_t offs[16];
-    offs[1] = 0;
-    for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + h.count[l];
-    for (int i = 0; i < n; i++)
-        if (len[i]) h.symbol[offs[len[i]]++] = (uint16_t)i;
+    offs[1 * st] = 0;
+    for (int l = 1; l < 15; l++) offs[(l + 1) * st] = offs[l * st] + h.count[l * st];
+    for (int i = 0; i < n; i++) {
+        const int l = len[i * lstride];
+        if (l) h.symbol[(offs[l * st]++) * st] = (uint16_t)i;
+    }
     return true;
 }
 
 RS_HD int huff_decode(Bits &b, const Huff &h)
 {
     int code = 0, first = 0, index = 0;
+    const int st = h.stride;
     for (int l = 1; l < 16; l++) {
         code |= (int)b.get(1);
-        const int count = h.count[l];
-        if (code - count < first) return h.symbol[index + (code - first)];
+        const int count = h.count[l * st];
+        if (code - count < first) return h.symbol[(index + (code - first)) * st];
         index += count;
         first += count;
         first <<= 1;
@@ -89,7 +98,9 @@ RS_HD int huff_decode(Bits &b, const Huff &h)
 }
 
 // returns bytes written, or -1 (corrupt / unsupported stream, or output larger than cap)
-RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, long long cap, bool zlib_wrapper)
+// tab16 / tab8: RS_INFLATE_U16 uint16 and RS_INFLATE_U8 uint8 elements of table space, element i at [i * stride]
+RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, long long cap, bool zlib_wrapper, uint16_t *tab16,
+                                uint8_t *lens, int stride)
 {
     Bits b{src, n, 0, 0u, 0, false};
     if (zlib_wrapper) {
@@ -98,8 +109,8 @@ RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, l
         if ((cmf & 15u) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) return -1;      // deflate, header check, no preset dictionary
     }
     long long out = 0;
-    Huff lit, dist;
-    uint8_t lens[320];
+    Huff lit{tab16, tab16 + 16 * stride, stride}, dist{tab16 + 304 * stride, tab16 + 320 * stride, stride};
+    uint16_t *offs = tab16 + 350 * stride;
     for (;;) {
         const uint32_t last = b.get(1), type = b.get(2);
         if (type == 0) {
@@ -113,40 +124,40 @@ RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, l
             b.pos += len;
         } else if (type == 1 || type == 2) {
             if (type == 1) {
-                for (int i = 0; i < 144; i++) lens[i] = 8;
-                for (int i = 144; i < 256; i++) lens[i] = 9;
-                for (int i = 256; i < 280; i++) lens[i] = 7;
-                for (int i = 280; i < 288; i++) lens[i] = 8;
-                huff_build(lit, lens, 288);
-                for (int i = 0; i < 30; i++) lens[i] = 5;
-                huff_build(dist, lens, 30);
+                for (int i = 0; i < 144; i++) lens[i * stride] = 8;
+                for (int i = 144; i < 256; i++) lens[i * stride] = 9;
+                for (int i = 256; i < 280; i++) lens[i * stride] = 7;
+                for (int i = 280; i < 288; i++) lens[i * stride] = 8;
+                huff_build(lit, lens, stride, 288, offs);
+                for (int i = 0; i < 30; i++) lens[i * stride] = 5;
+                huff_build(dist, lens, stride, 30, offs);
             } else {
                 const int nlen = (int)b.get(5) + 257, ndist = (int)b.get(5) + 1, ncode = (int)b.get(4) + 4;
                 if (nlen > 286 || ndist > 30) return -1;
-                for (int i = 0; i < 19; i++) lens[i] = 0;
-                for (int i = 0; i < ncode; i++) lens[CL_ORDER[i]] = (uint8_t)b.get(3);
-                if (!huff_build(lit, lens, 19)) return -1;          // the code-length code, kept in `lit` for a moment
+                for (int i = 0; i < 19; i++) lens[i * stride] = 0;
+                for (int i = 0; i < ncode; i++) lens[CL_ORDER[i] * stride] = (uint8_t)b.get(3);
+                if (!huff_build(lit, lens, stride, 19, offs)) return -1;          // the code-length code, kept in `lit` for a moment
                 int idx = 0;
                 while (idx < nlen + ndist) {
                     const int sym = huff_decode(b, lit);
                     if (sym < 0) return -1;
-                    if (sym < 16) lens[idx++] = (uint8_t)sym;
+                    if (sym < 16) lens[(idx++) * stride] = (uint8_t)sym;
                     else {
                         int rep, val = 0;
                         if (sym == 16) {
                             if (idx == 0) return -1;
-                            val = lens[idx - 1];
+                            val = lens[(idx - 1) * stride];
                             rep = 3 + (int)b.get(2);
                         } else if (sym == 17) rep = 3 + (int)b.get(3);
                         else rep = 11 + (int)b.get(7);
                         if (idx + rep > nlen + ndist) return -1;
-                        while (rep--) lens[idx++] = (uint8_t)val;
+                        while (rep--) lens[(idx++) * stride] = (uint8_t)val;
                     }
                 }
-                if (lens[256] == 0) return -1;                      // no end-of-block code
+                if (lens[256 * stride] == 0) return -1;             // no end-of-block code
                 // the distance lengths first: building the literal code overwrites nothing they need (separate arrays)
-                if (!huff_build(dist, lens + nlen, ndist)) return -1;
-                if (!huff_build(lit, lens, nlen)) return -1;
+                if (!huff_build(dist, lens + nlen * stride, stride, ndist, offs)) return -1;
+                if (!huff_build(lit, lens, stride, nlen, offs)) return -1;
             }
             for (;;) {
                 const int sym = huff_decode(b, lit);

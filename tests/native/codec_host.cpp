@@ -7,7 +7,9 @@
 
 extern "C" long long host_inflate(const uint8_t *src, long long n, uint8_t *dst, long long cap)
 {
-    return rs::codec::inflate_segment(src, n, dst, cap, true);
+    static thread_local uint16_t tab16[rs::codec::RS_INFLATE_U16];
+    static thread_local uint8_t lens[rs::codec::RS_INFLATE_U8];
+    return rs::codec::inflate_segment(src, n, dst, cap, true, tab16, lens, 1);
 }
 
 extern "C" long long host_lzw(const uint8_t *src, long long n, uint8_t *dst, long long cap)
