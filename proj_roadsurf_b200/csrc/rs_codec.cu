@@ -5,8 +5,8 @@
 // (scripts/functions/fct_misc.py:76-77; the tiles of config/config_stats.yaml:39 are deflate- or LZW-compressed COGs).
 //
 //   codec 8 / 32946  zlib-wrapped DEFLATE (RFC 1950 / 1951): stored, fixed and dynamic Huffman blocks; canonical codes are
-//                    decoded bit by bit from per-length counts; a decoder's tables are ~1 KiB and live in SHARED memory (column
-//                    t of the block's arrays belongs to thread t), 64 decoders per block; matches copy from the output itself
+//                    decoded bit by bit from per-length counts, which live in SHARED memory (column t of the block's array
+//                    belongs to thread t; symbol lists and code lengths in local memory); matches copy from the output itself
 //                    (the 32 KiB window is the already written part of the segment); the Adler-32 trailer is checked
 //   codec 5          TIFF LZW (MSB-first codes of 9 - 12 bits, ClearCode 256, EOI 257, the "early change" of libtiff); the
 //                    string table (4096 x 6 bytes per decoder) lives in a scratch buffer, decoders run grid-strided
@@ -37,14 +37,15 @@ struct CodecArgs {
     int *bad_segment;                 // index of (one of) the failing segments, -1 = none
 };
 
-constexpr int DEC_THREADS = 64;       // decoders per block: their DEFLATE tables fill 64 KiB of shared memory, three blocks per SM
+constexpr int DEC_THREADS = 128;      // decoders per block
 
 __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const CodecArgs a)
 {
-    // column t of the two arrays is thread t's table space (rs_codec_core.h)
-    extern __shared__ __align__(16) unsigned char dec_smem[];
-    uint16_t *tab16 = reinterpret_cast<uint16_t *>(dec_smem);
-    uint8_t *tab8 = dec_smem + sizeof(uint16_t) * RS_INFLATE_U16 * DEC_THREADS;
+    // the per-length counts of the two Huffman codes are read for every bit: column t of this array is thread t's (12 KiB per
+    // block); the symbol lists and code lengths are touched once per code and stay in the thread's local memory
+    __shared__ uint16_t hot[RS_INFLATE_HOT * DEC_THREADS];
+    uint16_t sym[RS_INFLATE_SYM];
+    uint8_t lens[RS_INFLATE_LEN];
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     for (int s = tid; s < a.n_seg; s += nthr) {
         const uint8_t *src = a.comp + a.comp_off[s];
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const CodecArgs a)
         } else if (a.codec == 5)
             got = lzw_segment(src, n, dst, cap, a.lzw_tab + (size_t)tid * 4096, a.lzw_len + (size_t)tid * 4096);
         else
-            got = inflate_segment(src, n, dst, cap, true, tab16 + threadIdx.x, tab8 + threadIdx.x, DEC_THREADS);
+            got = inflate_segment(src, n, dst, cap, true, hot + threadIdx.x, DEC_THREADS, sym, lens);
         // libtiff pads nothing: a strip decodes to exactly rows * row_bytes (the last strip of an image to its remaining rows)
         if (got != cap) {
             atomicMin(a.status, (int)RS_ERR_CODEC);
@@ -86,9 +87,7 @@ int launch_decode_segments(rs_ctx *ctx, const uint8_t *comp, const long long *co
         a.lzw_len = (uint16_t *)(a.lzw_tab + (size_t)blocks * DEC_THREADS * 4096);
     }
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0xff, sizeof(int), st));     // bad_segment = -1
-    const size_t smem = (sizeof(uint16_t) * RS_INFLATE_U16 + RS_INFLATE_U8) * DEC_THREADS;
-    RS_CUDA_OK(ctx, cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    decode_kernel<<<blocks, DEC_THREADS, smem, st>>>(a);
+    decode_kernel<<<blocks, DEC_THREADS, 0, st>>>(a);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
     return RS_OK;

@@ -48,24 +48,23 @@ struct Bits {                         // LSB-first bit reader over [p, p + n)
     }
 };
 
-// A decoder's tables live where its caller puts them: element i of an array is at base[i * stride].  On the device the base is
-// a slot of the block's shared memory and the stride the block size (thread t owns column t: a table read is a shared-memory
-// access, not a trip through local memory to L2 / HBM -- with hundreds of thousands of resident decoders the tables would
-// not even fit L2); on the host (tests) stride is 1.
+// A decoder's tables live where its caller puts them.  The per-length COUNTS are read for every bit of every code: element i is
+// at count[i * stride] -- on the device a column of the block's shared memory (stride = block size: thread t owns column t), on
+// the host (tests) stride 1.  The symbol lists and the code lengths are touched once per code: plain per-decoder arrays.
 struct Huff {                         // canonical code: symbols ordered by (length, value), count of codes per length
-    uint16_t *count;                  // [16]
+    uint16_t *count;                  // [16], strided
     uint16_t *symbol;                 // [288] (literal / length) or [30] (distance)
     int stride;
 };
-enum { RS_INFLATE_U16 = 16 + 288 + 16 + 30 + 16, RS_INFLATE_U8 = 320 };     // table space of one decoder: uint16 + uint8 elements
+enum { RS_INFLATE_HOT = 48, RS_INFLATE_SYM = 288 + 30, RS_INFLATE_LEN = 320 };   // strided uint16 / plain uint16 / plain uint8 per decoder
 
 // lengths[0 .. n) -> canonical code; returns false for an over-subscribed set (an incomplete set is accepted, as zlib accepts
 // the single-code distance trees real encoders write).  offs: 16 uint16 of scratch (same stride)
-RS_HD bool huff_build(Huff &h, const uint8_t *len, int lstride, int n, uint16_t *offs)
+RS_HD bool huff_build(Huff &h, const uint8_t *len, int n, uint16_t *offs)
 {
     const int st = h.stride;
     for (int i = 0; i < 16; i++) h.count[i * st] = 0;
-    for (int i = 0; i < n; i++) h.count[len[i * lstride] * st]++;
+    for (int i = 0; i < n; i++) h.count[len[i] * st]++;
     int left = 1;
     for (int l = 1; l < 16; l++) {
         left <<= 1;
@@ -75,8 +74,8 @@ RS_HD bool huff_build(Huff &h, const uint8_t *len, int lstride, int n, uint16_t 
     offs[1 * st] = 0;
     for (int l = 1; l < 15; l++) offs[(l + 1) * st] = offs[l * st] + h.count[l * st];
     for (int i = 0; i < n; i++) {
-        const int l = len[i * lstride];
-        if (l) h.symbol[(offs[l * st]++) * st] = (uint16_t)i;
+        const int l = len[i];
+        if (l) h.symbol[offs[l * st]++] = (uint16_t)i;
     }
     return true;
 }
@@ -88,7 +87,7 @@ RS_HD int huff_decode(Bits &b, const Huff &h)
     for (int l = 1; l < 16; l++) {
         code |= (int)b.get(1);
         const int count = h.count[l * st];
-        if (code - count < first) return h.symbol[(index + (code - first)) * st];
+        if (code - count < first) return h.symbol[index + (code - first)];
         index += count;
         first += count;
         first <<= 1;
@@ -98,9 +97,9 @@ RS_HD int huff_decode(Bits &b, const Huff &h)
 }
 
 // returns bytes written, or -1 (corrupt / unsupported stream, or output larger than cap)
-// tab16 / tab8: RS_INFLATE_U16 uint16 and RS_INFLATE_U8 uint8 elements of table space, element i at [i * stride]
-RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, long long cap, bool zlib_wrapper, uint16_t *tab16,
-                                uint8_t *lens, int stride)
+// hot: RS_INFLATE_HOT uint16 elements, element i at hot[i * stride]; sym: RS_INFLATE_SYM uint16; lens: RS_INFLATE_LEN uint8
+RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, long long cap, bool zlib_wrapper, uint16_t *hot,
+                                int stride, uint16_t *sym, uint8_t *lens)
 {
     Bits b{src, n, 0, 0u, 0, false};
     if (zlib_wrapper) {
@@ -109,8 +108,8 @@ RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, l
         if ((cmf & 15u) != 8u || ((cmf << 8) | flg) % 31u != 0u || (flg & 32u)) return -1;      // deflate, header check, no preset dictionary
     }
     long long out = 0;
-    Huff lit{tab16, tab16 + 16 * stride, stride}, dist{tab16 + 304 * stride, tab16 + 320 * stride, stride};
-    uint16_t *offs = tab16 + 350 * stride;
+    Huff lit{hot, sym, stride}, dist{hot + 16 * stride, sym + 288, stride};
+    uint16_t *offs = hot + 32 * stride;
     for (;;) {
         const uint32_t last = b.get(1), type = b.get(2);
         if (type == 0) {
@@ -124,50 +123,50 @@ RS_HD long long inflate_segment(const uint8_t *src, long long n, uint8_t *dst, l
             b.pos += len;
         } else if (type == 1 || type == 2) {
             if (type == 1) {
-                for (int i = 0; i < 144; i++) lens[i * stride] = 8;
-                for (int i = 144; i < 256; i++) lens[i * stride] = 9;
-                for (int i = 256; i < 280; i++) lens[i * stride] = 7;
-                for (int i = 280; i < 288; i++) lens[i * stride] = 8;
-                huff_build(lit, lens, stride, 288, offs);
-                for (int i = 0; i < 30; i++) lens[i * stride] = 5;
-                huff_build(dist, lens, stride, 30, offs);
+                for (int i = 0; i < 144; i++) lens[i] = 8;
+                for (int i = 144; i < 256; i++) lens[i] = 9;
+                for (int i = 256; i < 280; i++) lens[i] = 7;
+                for (int i = 280; i < 288; i++) lens[i] = 8;
+                huff_build(lit, lens, 288, offs);
+                for (int i = 0; i < 30; i++) lens[i] = 5;
+                huff_build(dist, lens, 30, offs);
             } else {
                 const int nlen = (int)b.get(5) + 257, ndist = (int)b.get(5) + 1, ncode = (int)b.get(4) + 4;
                 if (nlen > 286 || ndist > 30) return -1;
-                for (int i = 0; i < 19; i++) lens[i * stride] = 0;
-                for (int i = 0; i < ncode; i++) lens[CL_ORDER[i] * stride] = (uint8_t)b.get(3);
-                if (!huff_build(lit, lens, stride, 19, offs)) return -1;          // the code-length code, kept in `lit` for a moment
+                for (int i = 0; i < 19; i++) lens[i] = 0;
+                for (int i = 0; i < ncode; i++) lens[CL_ORDER[i]] = (uint8_t)b.get(3);
+                if (!huff_build(lit, lens, 19, offs)) return -1;          // the code-length code, kept in `lit` for a moment
                 int idx = 0;
                 while (idx < nlen + ndist) {
-                    const int sym = huff_decode(b, lit);
-                    if (sym < 0) return -1;
-                    if (sym < 16) lens[(idx++) * stride] = (uint8_t)sym;
+                    const int sy = huff_decode(b, lit);
+                    if (sy < 0) return -1;
+                    if (sy < 16) lens[idx++] = (uint8_t)sy;
                     else {
                         int rep, val = 0;
-                        if (sym == 16) {
+                        if (sy == 16) {
                             if (idx == 0) return -1;
-                            val = lens[(idx - 1) * stride];
+                            val = lens[idx - 1];
                             rep = 3 + (int)b.get(2);
-                        } else if (sym == 17) rep = 3 + (int)b.get(3);
+                        } else if (sy == 17) rep = 3 + (int)b.get(3);
                         else rep = 11 + (int)b.get(7);
                         if (idx + rep > nlen + ndist) return -1;
-                        while (rep--) lens[(idx++) * stride] = (uint8_t)val;
+                        while (rep--) lens[idx++] = (uint8_t)val;
                     }
                 }
-                if (lens[256 * stride] == 0) return -1;             // no end-of-block code
+                if (lens[256] == 0) return -1;                      // no end-of-block code
                 // the distance lengths first: building the literal code overwrites nothing they need (separate arrays)
-                if (!huff_build(dist, lens + nlen * stride, stride, ndist, offs)) return -1;
-                if (!huff_build(lit, lens, stride, nlen, offs)) return -1;
+                if (!huff_build(dist, lens + nlen, ndist, offs)) return -1;
+                if (!huff_build(lit, lens, nlen, offs)) return -1;
             }
             for (;;) {
-                const int sym = huff_decode(b, lit);
-                if (sym < 0 || b.over) return -1;
-                if (sym < 256) {
+                const int sy = huff_decode(b, lit);
+                if (sy < 0 || b.over) return -1;
+                if (sy < 256) {
                     if (out >= cap) return -1;
-                    dst[out++] = (uint8_t)sym;
-                } else if (sym == 256) break;
+                    dst[out++] = (uint8_t)sy;
+                } else if (sy == 256) break;
                 else {
-                    const int ls = sym - 257;
+                    const int ls = sy - 257;
                     if (ls >= 29) return -1;
                     const int len = LEN_BASE[ls] + (int)b.get(LEN_EXTRA[ls]);
                     const int ds = huff_decode(b, dist);

@@ -7,9 +7,9 @@
 
 extern "C" long long host_inflate(const uint8_t *src, long long n, uint8_t *dst, long long cap)
 {
-    static thread_local uint16_t tab16[rs::codec::RS_INFLATE_U16];
-    static thread_local uint8_t lens[rs::codec::RS_INFLATE_U8];
-    return rs::codec::inflate_segment(src, n, dst, cap, true, tab16, lens, 1);
+    uint16_t hot[rs::codec::RS_INFLATE_HOT], sym[rs::codec::RS_INFLATE_SYM];
+    uint8_t lens[rs::codec::RS_INFLATE_LEN];
+    return rs::codec::inflate_segment(src, n, dst, cap, true, hot, 1, sym, lens);
 }
 
 extern "C" long long host_lzw(const uint8_t *src, long long n, uint8_t *dst, long long cap)
