@@ -8,6 +8,7 @@
   band ratios, VgNIR-BI                       ->  fct_statistics.add_band_ratios         (:279-293)
   statistics per road type                    ->  fct_statistics.cover_stats_from_accumulators   (:296-316)
   Kolmogorov-Smirnov per road and band        ->  fct_statistics.ks_test_from_hists      (:436-461)
+  elevation statistics per road over a DEM    ->  fct_rasters.zonal_stats                (scripts/functions/fct_rasters.py:147-167)
 
 The reference ships no imagery (data/readme.md), so the script first writes synthetic 4-band tiles and ribbon roads.
 Needs a B200 (there is no CPU path).   python examples/statistical_analysis_b200.py --out /tmp/roadsurf_demo
@@ -27,7 +28,7 @@ if ROOT not in sys.path:
 
 from proj_roadsurf_b200 import ingest, synth, workflows                     # noqa: E402
 from proj_roadsurf_b200.engine import default_engine                         # noqa: E402
-from proj_roadsurf_b200.functions import fct_misc, fct_statistics as fs      # noqa: E402
+from proj_roadsurf_b200.functions import fct_misc, fct_rasters, fct_statistics as fs      # noqa: E402
 
 
 def write_synthetic_tiles(grid: synth.Grid, folder: str) -> list:
@@ -112,11 +113,29 @@ def main(argv=None) -> dict:
         ks.to_csv(os.path.join(tables, "ks_test.csv"), index=False)
         written_files.append(os.path.join(tables, "ks_test.csv"))
 
+    print("Calculating zonal stats over the DEM...")
+    # fct_rasters.py:147-167: a float32 elevation raster (2 m grid, nodata -9999) under the road polygons
+    X0, Y1 = grid.origin
+    dem_res = grid.span / 64.0
+    dh, dw = args.tiles_y * 64, args.tiles_x * 64
+    yy, xx = np.mgrid[0:dh, 0:dw]
+    rng = np.random.default_rng(11)
+    dem_array = (430.0 + 0.02 * xx + 0.05 * yy + rng.normal(0.0, 0.3, (dh, dw))).astype(np.float32)
+    dem_array[rng.random((dh, dw)) < 0.01] = -9999.0
+    affine = (dem_res, 0.0, X0, 0.0, -dem_res, Y1)
+    labels = [roads.rings(r) for r in range(roads.n_roads)]
+    zs_df = pd.DataFrame(fct_rasters.zonal_stats(labels, dem_array, affine=affine, stats=['min', 'max', 'mean', 'median', 'std'],
+                                                 nodata=-9999))
+    zs_roads = pd.concat([pd.DataFrame({"road_id": ids}), zs_df], axis=1)
+    zs_roads.to_csv(os.path.join(tables, "roads_dem_zs.csv"), index=False)
+    written_files.append(os.path.join(tables, "roads_dem_zs.csv"))
+
     print("The following files were written:")
     for f in written_files:
         print(f)
     return {"roads_stats": roads_stats, "roads_stats_filtered": roads_stats_filtered, "pixels_per_band": pixels_per_band,
-            "cover_stats": cover_stats_df, "ks": ks, "tiles": tiles, "roads": roads, "pairs": pairs, "road_type": road_type}
+            "cover_stats": cover_stats_df, "ks": ks, "tiles": tiles, "roads": roads, "pairs": pairs, "road_type": road_type,
+            "dem_stats": zs_roads, "dem": (dem_array, affine)}
 
 
 if __name__ == "__main__":
