@@ -383,17 +383,26 @@ def config_legs(args, eng, torch, dev, grid, sh, rr_gt_class, dr, dp, peak, traf
         # whole 16 bits and the 8-bit outputs spread over all 256 bins
         smin16, smax16 = u16_scale_range()
         k, off = scale_params(smin16, smax16)
-        for f32 in (False, True):
+        # float64 semantics twice: the launcher's own choice (it verifies on all 65 536 inputs per band that the float32 evaluation
+        # gives the same bytes for this range and then runs that policy), and the integer-threshold form it uses for ranges where
+        # the two precisions differ somewhere (RS_ZONAL_F32EQ=0)
+        for f32, forced in ((False, None), (False, "0"), (True, None)):
             rs = (k, off, f32) if not f32 else scale_params(smin16, smax16, True) + (True,)
+            if forced is not None:
+                os.environ["RS_ZONAL_F32EQ"] = forced
             out = eng.zonal_hist_dev(dr16, t, dp16, rescale=rs, check=False)
             ms = time_loop(torch, lambda: eng.zonal_hist_dev(dr16, t, dp16, rescale=rs, out=out, check=False), args.leg_steps, 3)
             eng.sync_status()
+            os.environ.pop("RS_ZONAL_F32EQ", None)
             smp = spread(roads16.n_roads, 64)
             oh, onz = oracle_rows(eng, grid, roads16, pairs16, smp, t, 0, n16, channels=4, dtype="u16", scale=rs)
-            name = "rescale_u16x4_" + ("f32" if f32 else "f64")
+            name = "rescale_u16x4_" + ("f32" if f32 else "f64") + ("_thresholds" if forced is not None else "")
+            how = ("float32 working precision" if f32 else
+                   "float64 working precision, " + ("integer-threshold form" if forced is not None else
+                                                    "evaluated in float32 after the launcher verified every input gives the same byte"))
             legs[name] = leg_entry(ms, n16 * H * W, 8, name, rows_match(out[0], out[1], smp, oh, onz),
-                                   config="configs[2]: RGB+NIR uint16 tiles, gdal.Translate -scale fused into the accumulation, "
-                                          + ("float32" if f32 else "float64") + " working precision", tiles=n16)
+                                   config="configs[2]: RGB+NIR uint16 tiles, gdal.Translate -scale fused into the accumulation, " + how,
+                                   tiles=n16)
             del out
         del t
         torch.cuda.empty_cache()

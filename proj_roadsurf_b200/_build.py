@@ -10,7 +10,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("ROADSURF_B200_LIB") or os.path.join(LIB_DIR, "libroadsurf_b200.so")   # env: an experiment build
-SOURCES = ["rs_zonal.cu", "rs_tables.cu", "rs_extract.cu", "rs_pairs.cu", "rs_api.cu", "rs_comm.cu", "rs_wide.cu", "rs_fstats.cu", "rs_codec.cu"]
+SOURCES = ["rs_zonal.cu", "rs_tables.cu", "rs_extract.cu", "rs_pairs.cu", "rs_api.cu", "rs_comm.cu", "rs_wide.cu", "rs_fstats.cu", "rs_codec.cu",
+           "rs_hostcopy.cu"]
 HEADERS = [os.path.join(CSRC, "rs_internal.h"), os.path.join(CSRC, "rs_raster.cuh"), os.path.join(ROOT, "include", "roadsurf_b200.h")]
 
 # -fmad=false: the rounding of every float64 operation of the rasterizer is part of the
@@ -46,6 +47,6 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += os.environ.get("RS_NVCC_EXTRA", "").split()
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
     subprocess.check_call(cmd)
     return LIB_PATH

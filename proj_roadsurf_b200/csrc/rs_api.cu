@@ -35,8 +35,7 @@ static int up(rs_ctx *ctx, DevBuf &b, const void *src, size_t bytes)
 {
     int rc = ensure(ctx, b, bytes);
     if (rc) return rc;
-    if (bytes) RS_CUDA_OK(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->host_stream));
-    return RS_OK;
+    return copy_h2d(ctx, b.p, src, bytes, ctx->host_stream);
 }
 
 static size_t elem_bytes(int dtype) { return dtype == RS_U16 ? 2 : 1; }
@@ -153,6 +152,7 @@ int rs_ctx_destroy(rs_ctx *ctx)
     if (!ctx) return RS_OK;
     cudaSetDevice(ctx->device);
     rs_comm_destroy(ctx);
+    copier_destroy(ctx);
     for (auto &b : ctx->stage)
         if (b.p) cudaFree(b.p);
     if (ctx->items.p) cudaFree(ctx->items.p);
@@ -375,8 +375,8 @@ int rs_zonal_stats_stream_host(rs_ctx *ctx, const rs_roads *roads, const rs_tile
         const int hi = lo + per < tiles->n_tiles ? lo + per : tiles->n_tiles, b = k & 1;
         void *buf = b ? ctx->stage[8].p : ctx->stage[7].p;
         if (k >= 2) RS_CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->ev_used[b], 0));          // the kernel of chunk k-2 is done with it
-        RS_CUDA_OK(ctx, cudaMemcpyAsync(buf, (const uint8_t *)tiles->pixels + (size_t)lo * tile_bytes, (size_t)(hi - lo) * tile_bytes,
-                                        cudaMemcpyHostToDevice, cs));
+        if ((rc = copy_h2d(ctx, buf, (const uint8_t *)tiles->pixels + (size_t)lo * tile_bytes, (size_t)(hi - lo) * tile_bytes, cs)))
+            return rc;
         RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
         RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[b], 0));
         rs_tiles chunk = dt;

@@ -15,6 +15,7 @@ struct DevBuf {
     void  *p = nullptr;
     size_t cap = 0;
 };
+struct HostCopier;                // page-locked slot ring + copy threads for pageable sources (rs_hostcopy.cu)
 
 }  // namespace rs
 
@@ -40,11 +41,12 @@ struct rs_ctx {
     bool scratch_used = false;
     rs::DevBuf lzw_scratch;               // LZW string tables of the resident decoders (rs_codec.cu)
     rs::DevBuf lut_dev;                   // 16 -> 8 bit rescale thresholds of the last scale parameters (rs_zonal.cu, PxU16x4Lut)
-    bool lut_valid = false, lut_ok = false;
+    bool lut_valid = false, lut_ok = false, lut_f32_same = false;
     int lut_f32 = 0;
     double lut_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t lut_k[4] = {0, 0, 0, 0};
     long long lut_b[4] = {0, 0, 0, 0};
+    rs::HostCopier *copier = nullptr;     // created by the first large copy out of pageable memory
     void *comm = nullptr;                 // ncclComm_t of rs_comm_init (rs_comm.cu)
     int comm_world = 0, comm_rank = 0;
 };
@@ -64,6 +66,10 @@ int ensure(rs_ctx *ctx, DevBuf &b, size_t bytes);
             return RS_ERR_CUDA;                                \
         }                                                      \
     } while (0)
+
+// host -> device copy queued on `st`; large pageable sources are staged by several host threads through page-locked slots
+int copy_h2d(rs_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);
+void copier_destroy(rs_ctx *ctx);
 
 // launches (defined in the .cu files)
 int launch_zonal(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles, const rs_pairs *pairs,

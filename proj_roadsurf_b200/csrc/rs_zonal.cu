@@ -1187,7 +1187,7 @@ constexpr int BIG_PAIRS = 4;    // an item of at least this many pairs (or a row
 // WRITE pass: big items go to items[big_base++], small ones to items[cap - 1 - small_base++].
 template <bool WRITE>
 __device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, int road, int p0, int p1, int4 *items, int big_base,
-                                          int small_base, int cap, int flag, bool tall, int &n_big)
+                                          int small_base, int cap, int flag, bool tall, int ppi, int &n_big)
 {
     int ni = 0;
     n_big = 0;
@@ -1197,8 +1197,8 @@ __device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, in
         n_big += big ? 1 : 0;
     };
     if (!tall) {            // no window can exceed ROWS_ITEM rows (tile height <= ROWS_ITEM): groups of PPI pairs, no geometry reads
-        for (int p = p0; p < p1; p += PPI) {
-            const int cnt = min(PPI, p1 - p);
+        for (int p = p0; p < p1; p += ppi) {
+            const int cnt = min(ppi, p1 - p);
             emit(p, cnt, -1, cnt >= BIG_PAIRS);
         }
         return ni;
@@ -1216,7 +1216,7 @@ __device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, in
             gp = p + 1;
             continue;
         }
-        if (gn == PPI || (gn > 0 && garea + area > AREA_MAX)) close();
+        if (gn == ppi || (gn > 0 && garea + area > AREA_MAX)) close();
         if (gn == 0) gp = p;
         gn++; garea += area;
     }
@@ -1227,13 +1227,13 @@ __device__ __forceinline__ int road_items(const PairGeom *__restrict__ pgeom, in
 __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__ road_pair_off, const PairGeom *__restrict__ pgeom,
                                                          int n_roads, const int *__restrict__ road_slot, uint32_t *hist, uint32_t *nzero,
                                                          uint32_t *minzero, int hc, int4 *items, int *n_items, int items_cap, int tall,
-                                                         int accumulate)
+                                                         int accumulate, int ppi)
 {
     const int road = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     int p0 = 0, p1 = 0, ni = 0, nb = 0;
     if (road < n_roads) {
         p0 = road_pair_off[road]; p1 = road_pair_off[road + 1];
-        ni = road_items<false>(pgeom, road, p0, p1, nullptr, 0, 0, items_cap, 0, tall != 0, nb);
+        ni = road_items<false>(pgeom, road, p0, p1, nullptr, 0, 0, items_cap, 0, tall != 0, ppi, nb);
     }
     // two warp scans (big, small), one atomicAdd per warp and list
     int ib = nb, is = ni - nb;
@@ -1250,7 +1250,7 @@ __global__ void __launch_bounds__(256) prep_items_kernel(const int *__restrict__
     bs = __shfl_sync(FULL, bs, 31) + is - (ni - nb);
     if (ni > 0) {
         int dummy;
-        road_items<true>(pgeom, road, p0, p1, items, bb, bs, items_cap, (ni > 1 || accumulate) ? ITEM_SPLIT : 0, tall != 0, dummy);
+        road_items<true>(pgeom, road, p0, p1, items, bb, bs, items_cap, (ni > 1 || accumulate) ? ITEM_SPLIT : 0, tall != 0, ppi, dummy);
     }
     if (hist && !accumulate) {
         unsigned m = __ballot_sync(FULL, road < n_roads && ni != 1);
@@ -1434,6 +1434,14 @@ static int prepare_rescale_lut(rs_ctx *ctx, const rs_zonal_params *prm, ZonalArg
     if (!same) {
         ctx->lut_valid = false;
         ctx->lut_ok = false;
+        // binary64 semantics: does the float32 evaluation give the same byte for EVERY 16-bit input of every band?  (True for
+        // ranges whose steps stay clear of the .5 ties by more than float32's rounding, e.g. 0 .. 65535.)  Then the float32
+        // policy -- the one form of this kernel that runs at the memory roofline -- computes the binary64 result.
+        bool fsame = !f32;
+        for (int c = 0; c < 4 && fsame; c++)
+            for (unsigned sv = 0; sv < 65536u && fsame; sv++)
+                fsame = rescale_exact(sv, prm->scale_k[c], prm->scale_off[c], true) == rescale_exact(sv, prm->scale_k[c], prm->scale_off[c], false);
+        ctx->lut_f32_same = fsame;
         static thread_local uint32_t lohi[4 * 256];
         bool ok = true;
         for (int c = 0; c < 4 && ok; c++) {
@@ -1643,11 +1651,21 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     }
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));      // work counter, big items, small items, pool cursor, ...
     if ((rc = launch_pair_geom(ctx, roads, tiles, pairs, window_mode, prm ? prm->border_px : 0, tile_lo, tile_hi, st))) return rc;
+    // pairs per item: PPI when the launch has plenty of items per team; a small launch (a shard of a strongly scaled job) gets
+    // shorter items, so that the tail of the dynamic queue -- teams idle while the last items finish -- stays a few per cent of it
+    int ppi = PPI;
+    {
+        const size_t teams = (size_t)ctx->sm_count * CTAS_PER_SM * WARPS;
+        const size_t want = (size_t)pairs->n_pairs / (teams * 16);
+        if (want < (size_t)PPI) ppi = want < 1 ? 1 : (int)want;
+        const char *env = getenv("RS_ZONAL_PPI");
+        if (env && atoi(env) >= 1 && atoi(env) <= PPI) ppi = atoi(env);
+    }
     prep_items_kernel<<<(roads->n_roads + 255) / 256, 256, 0, st>>>(pairs->road_pair_off, (const PairGeom *)ctx->pgeom.p, roads->n_roads,
                                                                     a.road_slot, (masks || f32 || ex) ? nullptr : hist, n_allzero, a.minzero, HC,
                                                                     (int4 *)ctx->items.p, ctx->d_counters + 1, (int)cap,
                                                                     !ex && tiles->height > ROWS_ITEM,
-                                                                    accumulate);
+                                                                    accumulate, ppi);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
 
@@ -1659,11 +1677,17 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     else if (masks) rc = launch_one<PxMask>(ctx, a, st);
     else if (prm->hist_mode == RS_HIST_CLASS_SCORE) rc = launch_one<PxClassScore>(ctx, a, st);
     else if (tiles->dtype == RS_U16) {
-        // the binary64 semantics go through the integer thresholds (PxU16x4Lut) when the launcher could verify them, the float32
-        // semantics through the float32 policy itself (already at the roofline); RS_ZONAL_LUT=0 / 1 forces plain / thresholds
+        // the float32 semantics go through the float32 policy itself (at the roofline); the binary64 semantics through the same
+        // policy when the launcher verified on all 65 536 inputs per band that both precisions give the same byte, else through
+        // the integer thresholds (PxU16x4Lut) when those verify, else through FP64.  RS_ZONAL_LUT=0 / 1 forces plain / verified
+        // forms, RS_ZONAL_F32EQ=0 skips the float32 evaluation.
         const char *env = getenv("RS_ZONAL_LUT");
         const int mode = env ? atoi(env) : (prm->rescale == 1 ? 1 : 0);
-        if (mode == 1 && prepare_rescale_lut(ctx, prm, a, st)) rc = launch_one<PxU16x4Lut>(ctx, a, st);
+        const int lut = mode == 1 ? prepare_rescale_lut(ctx, prm, a, st) : 0;
+        const char *feq = getenv("RS_ZONAL_F32EQ");           // 0: never take the verified float32 evaluation for binary64 semantics
+        if (mode == 1 && prm->rescale == 1 && ctx->lut_f32_same && !(feq && atoi(feq) == 0))
+            rc = launch_one<PxU16x4Rescale<true>>(ctx, a, st);
+        else if (lut) rc = launch_one<PxU16x4Lut>(ctx, a, st);
         else rc = prm->rescale == 1 ? launch_one<PxU16x4Rescale<false>>(ctx, a, st) : launch_one<PxU16x4Rescale<true>>(ctx, a, st);
     }
     else

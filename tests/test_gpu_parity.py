@@ -655,6 +655,56 @@ def test_streaming_from_host_equals_resident(eng):
     assert np.array_equal(ref[1].astype(np.uint64), oh)
 
 
+def test_pageable_sources_through_the_slot_ring(monkeypatch):
+    """rs_hostcopy.cu: copies of >= 8 MiB out of pageable memory go through page-locked slots filled by several host threads;
+    results equal the plain cudaMemcpyAsync path (RS_STAGE_COPY=0) for the whole-batch copy and for streamed chunks whose sizes
+    are not multiples of the slot size, with 1, 3 and the default number of copy threads"""
+    from proj_roadsurf_b200.engine import Engine
+    g = synth.Grid(16, 12)
+    rr = synth.ribbon_roads(g, 60, seed=83)
+    tiles = synth.host_tiles(g, 3)                         # 37.7 MB of ordinary numpy memory
+    tb = TileBatch.from_arrays(tiles, g.transforms())
+    monkeypatch.setenv("RS_STAGE_COPY", "0")
+    e0 = Engine(0)
+    ref = e0.zonal_stats_host(rr.roads, tb, rr.pairs, want_hist=True, mapped=False)
+    monkeypatch.delenv("RS_STAGE_COPY")
+    for threads in ("1", "3", None):
+        if threads is None:
+            monkeypatch.delenv("RS_STAGE_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("RS_STAGE_THREADS", threads)
+        e = Engine(0)                                      # the copy threads are created with the context's first staged copy
+        for per in (None, 100, 50, 192):
+            got = e.zonal_stats_host(rr.roads, tb, rr.pairs, want_hist=True, mapped=False, tiles_per_chunk=per)
+            assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]), (threads, per)
+            assert np.array_equal(got[0], ref[0], equal_nan=True), (threads, per)
+        del e
+    oh, _ = oracle_hist(rr.roads, rr.pairs, tiles, g.transforms(), threads=4)
+    assert np.array_equal(ref[1].astype(np.uint64), oh)
+
+
+def test_pairs_per_item_do_not_change_results(eng, monkeypatch):
+    """small launches get shorter work items (rs_zonal.cu, launch_impl: pairs per item from the number of pairs per team); the
+    rows of roads split over several items are accumulated with atomics -- same histograms, n_allzero and min_zero"""
+    g = synth.Grid(6, 6)
+    rr = synth.ribbon_roads(g, 50, seed=84)
+    tiles = synth.host_tiles(g, 3)
+    tiles[tiles < 40] = 0                                  # plenty of zeros: n_allzero and min_zero are exercised
+    tb = TileBatch.from_arrays(tiles, g.transforms())
+    res = {}
+    for ppi in ("8", "3", "1", None):
+        if ppi is None:
+            monkeypatch.delenv("RS_ZONAL_PPI", raising=False)
+        else:
+            monkeypatch.setenv("RS_ZONAL_PPI", ppi)
+        res[ppi] = eng.zonal_hist_host(rr.roads, tb, rr.pairs, want_min_zero=True)
+    for ppi in ("3", "1", None):
+        for a, b in zip(res[ppi], res["8"]):
+            assert np.array_equal(a, b), ppi
+    oh, onz = oracle_hist(rr.roads, rr.pairs, tiles, g.transforms())
+    assert np.array_equal(res["1"][0].astype(np.uint64), oh) and np.array_equal(res["1"][1].astype(np.uint64), onz)
+
+
 def test_mapped_host_tiles_equal_resident(eng):
     """rs_zonal_stats_mapped_host: the kernel reads page-locked host tiles in place; pageable memory is refused"""
     import torch
@@ -837,10 +887,15 @@ def test_u16_rescale_integer_form_equals_floating_form(eng, f32, monkeypatch):
     tb = TileBatch.from_arrays(tiles, gt)
     for smin, smax in (([150.0, 300.0, 300.0, 300.0], [9000.0, 6000.0, 6000.0, 6000.0]),
                        ([0.0, 0.0, 0.0, 0.0], [510.0, 65535.0, 1020.0, 256.0]),          # k = 1/2, 1/257, 1/4: ties at x.5
+                       ([0.0, 0.0, 0.0, 0.0], [65535.0, 65535.0, 65535.0, 65535.0]),       # both precisions agree on every input
                        ([1000.0, 10.0, 0.0, 100.0], [1100.0, 60000.0, 65535.0, 600.0])):   # 100-wide range: scale 2.55
         k, off = scale_params(smin, smax, f32)
         monkeypatch.setenv("RS_ZONAL_LUT", "1")                # integer thresholds
+        monkeypatch.setenv("RS_ZONAL_F32EQ", "0")
         h1, z1 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
+        monkeypatch.delenv("RS_ZONAL_F32EQ")                   # binary64 through the float32 evaluation where the launcher verified it
+        h3, z3 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
+        assert np.array_equal(h3, h1) and np.array_equal(z3, z1), (smin, smax)
         monkeypatch.setenv("RS_ZONAL_LUT", "0")                # plain floating point
         h0, z0 = eng.zonal_hist_host(rr.roads, tb, rr.pairs, rescale=(k, off, f32))
         assert np.array_equal(h1, h0) and np.array_equal(z1, z0), (smin, smax)
