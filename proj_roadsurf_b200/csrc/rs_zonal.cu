@@ -1652,11 +1652,13 @@ static int launch_impl(rs_ctx *ctx, const rs_roads *roads, const rs_tiles *tiles
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(int), st));      // work counter, big items, small items, pool cursor, ...
     if ((rc = launch_pair_geom(ctx, roads, tiles, pairs, window_mode, prm ? prm->border_px : 0, tile_lo, tile_hi, st))) return rc;
     // pairs per item: PPI when the launch has plenty of items per team; a small launch (a shard of a strongly scaled job) gets
-    // shorter items, so that the tail of the dynamic queue -- teams idle while the last items finish -- stays a few per cent of it
+    // shorter items, so that the tail of the dynamic queue -- teams idle while the last items finish -- stays a few per cent of it.
+    // About ten items per team: on an eighth of the benchmark shard (125 k pairs) 8 / 4 / 2 / 1 pairs per item take
+    // 1.52 / 1.33 / 1.39 / 1.47 ms (shorter items pay the per-item set-up and the atomic row merge more often).
     int ppi = PPI;
     {
         const size_t teams = (size_t)ctx->sm_count * CTAS_PER_SM * WARPS;
-        const size_t want = (size_t)pairs->n_pairs / (teams * 16);
+        const size_t want = (size_t)pairs->n_pairs / (teams * 10);
         if (want < (size_t)PPI) ppi = want < 1 ? 1 : (int)want;
         const char *env = getenv("RS_ZONAL_PPI");
         if (env && atoi(env) >= 1 && atoi(env) <= PPI) ppi = atoi(env);
