@@ -18,7 +18,7 @@ HEADERS = [os.path.join(CSRC, "rs_internal.h"), os.path.join(CSRC, "rs_raster.cu
 # specification (GDAL evaluates a*b+c with separate multiply and add on x86-64).
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-fmad=false",
+    "-Xcompiler", "-fPIC", "-shared", "-fmad=false", "-t", "0",
 ]
 
 

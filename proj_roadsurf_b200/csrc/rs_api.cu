@@ -1080,6 +1080,47 @@ int rs_assemble_tiles_host(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int
     return finish(ctx);
 }
 
+}  // extern "C" (helper below is internal)
+
+// Compressed segments -> decoded samples with the upload and the decoding overlapped: the compressed bytes cross the host link in
+// up to eight pieces on the copy stream, and the decoder of a piece is queued on the host stream behind the event of its copy
+// -- while it runs, the next piece is staged and copied.  d_comp / d_coff / d_roff: device buffers (offsets already uploaded).
+static int decode_overlapped(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec,
+                             uint8_t *d_comp, const long long *d_coff, uint8_t *d_raw, const long long *d_roff)
+{
+    int rc;
+    if (!ctx->copy_stream) {
+        RS_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            RS_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            RS_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_used[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t st = ctx->host_stream, cs = ctx->copy_stream;
+    // a piece is at least a full wave of decoders (a launch lasts as long as its slowest segment, however few it has) and at
+    // most an eighth of the call
+    const int per_piece = (n_segments + 7) / 8 > 65536 ? (n_segments + 7) / 8 : 65536;
+    // the copy stream starts behind whatever the host stream still does with these buffers (a previous call's decoder)
+    RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_used[0], st));
+    RS_CUDA_OK(ctx, cudaStreamWaitEvent(cs, ctx->ev_used[0], 0));
+    int a = 0, k = 0;
+    while (a < n_segments) {
+        const int b = n_segments - a <= per_piece + per_piece / 4 ? n_segments : a + per_piece;      // segments [a, b)
+        const int64_t lo = comp_off[a], hi = comp_off[b];
+        if ((rc = copy_h2d(ctx, d_comp + lo, comp + lo, (size_t)(hi - lo), cs))) return rc;
+        // two events in turn: a record waits (host side) until the decoder that waited on its previous use was queued -- it was,
+        // two pieces ago, in this same thread
+        RS_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copied[k & 1], cs));
+        RS_CUDA_OK(ctx, cudaStreamWaitEvent(st, ctx->ev_copied[k & 1], 0));
+        if ((rc = launch_decode_segments(ctx, d_comp, d_coff + a, b - a, codec, d_raw, d_roff + a, st))) return rc;
+        a = b;
+        k++;
+    }
+    return RS_OK;
+}
+
+extern "C" {
+
 int rs_ingest_tiles_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_off, int32_t n_segments, int32_t codec,
                          const int64_t *raw_off, int32_t n_tiles, int32_t height, int32_t width, int32_t c_in, int32_t planar,
                          int32_t predictor, int32_t sample_bytes, int32_t big_endian, int32_t c_out, const int32_t *bidx, int32_t rescale,
@@ -1095,14 +1136,14 @@ int rs_ingest_tiles_host(rs_ctx *ctx, const uint8_t *comp, const int64_t *comp_o
     const size_t in_b = npx * c_in * sample_bytes, out_b = npx * c_out * ((sample_bytes == 1 || rescale) ? 1 : 2);
     if ((size_t)raw_off[n_segments] != in_b) return RS_ERR_INVALID_ARG;           // the segments must tile the sample buffer exactly
     const size_t cb = (size_t)comp_off[n_segments];
-    if ((rc = up(ctx, ctx->stage[0], comp, cb))) return rc;                        // only the COMPRESSED bytes cross the host link
+    if ((rc = ensure(ctx, ctx->stage[0], cb))) return rc;                          // only the COMPRESSED bytes cross the host link
     if ((rc = up(ctx, ctx->stage[1], comp_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
     if ((rc = up(ctx, ctx->stage[2], raw_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
     if ((rc = ensure(ctx, ctx->stage[7], in_b))) return rc;
     if ((rc = ensure(ctx, ctx->stage[9], out_b))) return rc;
     cudaStream_t st = ctx->host_stream;
-    if ((rc = launch_decode_segments(ctx, (const uint8_t *)ctx->stage[0].p, (const long long *)ctx->stage[1].p, n_segments, codec,
-                                     (uint8_t *)ctx->stage[7].p, (const long long *)ctx->stage[2].p, st)))
+    if ((rc = decode_overlapped(ctx, comp, comp_off, n_segments, codec, (uint8_t *)ctx->stage[0].p, (const long long *)ctx->stage[1].p,
+                                (uint8_t *)ctx->stage[7].p, (const long long *)ctx->stage[2].p)))
         return rc;
     if ((rc = launch_assemble(ctx, (const uint8_t *)ctx->stage[7].p, n_tiles, height, width, c_in, planar, predictor, sample_bytes,
                               big_endian, c_out, bidx, rescale, k, off, ctx->stage[9].p, st)))
@@ -1133,7 +1174,7 @@ int rs_zonal_stats_compressed_host(rs_ctx *ctx, const rs_roads *roads, const rs_
     const size_t hb = sizeof(uint32_t) * 256 * (size_t)C * R, zb = sizeof(uint32_t) * (size_t)R;
     const size_t sb = sizeof(double) * (size_t)(RS_NSTAT + n_pct) * C * R;
     // stage[12..14]: compressed bytes + offsets (only these cross the host link); stage[7]: decoded samples; stage[8]: tiles
-    if ((rc = up(ctx, ctx->stage[12], comp, (size_t)comp_off[n_segments]))) return rc;
+    if ((rc = ensure(ctx, ctx->stage[12], (size_t)comp_off[n_segments]))) return rc;
     if ((rc = up(ctx, ctx->stage[13], comp_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
     if ((rc = up(ctx, ctx->stage[14], raw_off, sizeof(int64_t) * ((size_t)n_segments + 1)))) return rc;
     if ((rc = ensure(ctx, ctx->stage[7], in_b))) return rc;
@@ -1142,8 +1183,8 @@ int rs_zonal_stats_compressed_host(rs_ctx *ctx, const rs_roads *roads, const rs_
     if ((rc = ensure(ctx, ctx->stage[10], zb))) return rc;
     if ((rc = ensure(ctx, ctx->stage[11], sb))) return rc;
     cudaStream_t st = ctx->host_stream;
-    if ((rc = launch_decode_segments(ctx, (const uint8_t *)ctx->stage[12].p, (const long long *)ctx->stage[13].p, n_segments, codec,
-                                     (uint8_t *)ctx->stage[7].p, (const long long *)ctx->stage[14].p, st)))
+    if ((rc = decode_overlapped(ctx, comp, comp_off, n_segments, codec, (uint8_t *)ctx->stage[12].p, (const long long *)ctx->stage[13].p,
+                                (uint8_t *)ctx->stage[7].p, (const long long *)ctx->stage[14].p)))
         return rc;
     if ((rc = launch_assemble(ctx, (const uint8_t *)ctx->stage[7].p, tiles->n_tiles, tiles->height, tiles->width, C, planar, predictor, 1,
                               big_endian, C, nullptr, 0, nullptr, nullptr, ctx->stage[8].p, st)))

@@ -15,6 +15,7 @@
 // 256 x 256 tile stored in 8-row strips is 32 of them, a canton 67 M.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "rs_codec_core.h"
 #include "rs_internal.h"
@@ -68,6 +69,77 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const CodecArgs a)
     }
 }
 
+// DEFLATE, a warp per segment (rs_codec_core.h inflate_segment_warp): one decoder per warp with its first-level tables in shared
+// memory, the lanes sharing the input line, the table builds, the copies and the checksum
+constexpr int WDEC_WARPS = 8;
+
+__global__ void __launch_bounds__(WDEC_WARPS * 32, 4) inflate_warp_kernel(const CodecArgs a)
+{
+    __shared__ WTables tables[WDEC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * WDEC_WARPS + warp, nw = gridDim.x * WDEC_WARPS;
+    for (int s = wid; s < a.n_seg; s += nw) {
+        const long long c0 = a.comp_off[s], r0 = a.raw_off[s];
+        const long long n = a.comp_off[s + 1] - c0, cap = a.raw_off[s + 1] - r0;
+        const long long got = inflate_segment_warp(a.comp + c0, n, a.raw + r0, cap, true, tables[warp], lane);
+        if (got != cap && lane == 0) {
+            atomicMin(a.status, (int)RS_ERR_CODEC);
+            atomicMax(a.bad_segment, s);
+        }
+        __syncwarp();
+    }
+}
+
+// DEFLATE, a thread per segment with first-level tables in shared memory (rs_codec_core.h inflate_segment_lut): column t of the
+// block's array is thread t's tables; the threads of a warp take their segments in step
+#ifndef RS_TDEC_THREADS
+#define RS_TDEC_THREADS 64
+#endif
+constexpr int TDEC_THREADS = RS_TDEC_THREADS;
+
+__global__ void __launch_bounds__(TDEC_THREADS) inflate_lut_kernel(const CodecArgs a)
+{
+    extern __shared__ uint16_t tdec_tab[];          // [RS_T_SMEM][TDEC_THREADS]
+    uint16_t sym[RS_INFLATE_SYM];
+    uint8_t lens[RS_INFLATE_LEN];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    // the lanes of a warp take one segment each per round and step their decoders together: every loop below is warp-uniform
+    // (its condition is a vote), so the lanes meet again after each header, each symbol and each trailer
+    for (int s0 = tid - lane; s0 < a.n_seg; s0 += nthr) {
+        const int s = s0 + lane;
+        const bool valid = s < a.n_seg;
+        TInflate d;
+        d.state = TInflate::DONE;
+        long long cap = 0;
+        if (valid) {
+            const long long c0 = a.comp_off[s], r0 = a.raw_off[s];
+            cap = a.raw_off[s + 1] - r0;
+            d.begin(a.comp + c0, a.comp_off[s + 1] - c0, a.raw + r0, cap, true, tdec_tab + threadIdx.x, TDEC_THREADS, sym, lens);
+        }
+        for (;;) {
+            const bool hd = d.state == TInflate::HEADER;
+            if (__any_sync(0xffffffffu, hd)) {
+                if (hd) d.header();
+                __syncwarp();
+            }
+            bool more = false;
+            for (;;) {                              // symbols, until every lane's block ends (or one reaches its next header)
+                const bool act = d.state == TInflate::SYMBOLS;
+                if (!__any_sync(0xffffffffu, act)) break;
+                if (act) d.symbol();
+                if (__any_sync(0xffffffffu, d.state == TInflate::HEADER)) { more = true; break; }
+            }
+            if (!more && !__any_sync(0xffffffffu, d.state == TInflate::HEADER)) break;
+        }
+        if (d.state == TInflate::TRAILER) d.trailer();
+        __syncwarp();
+        if (valid && d.result() != cap) {
+            atomicMin(a.status, (int)RS_ERR_CODEC);
+            atomicMax(a.bad_segment, s);
+        }
+    }
+}
+
 }  // namespace
 
 int launch_decode_segments(rs_ctx *ctx, const uint8_t *comp, const long long *comp_off, int n_seg, int codec, uint8_t *raw,
@@ -87,6 +159,32 @@ int launch_decode_segments(rs_ctx *ctx, const uint8_t *comp, const long long *co
         a.lzw_len = (uint16_t *)(a.lzw_tab + (size_t)blocks * DEC_THREADS * 4096);
     }
     RS_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0xff, sizeof(int), st));     // bad_segment = -1
+    // DEFLATE: RS_INFLATE = lut (default: a thread per segment, first-level tables in shared memory) | warp (a warp per segment)
+    // | bits (a thread per segment, canonical walk bit by bit) -- three decoders held to each other and to zlib by the tests
+    const char *mode = getenv("RS_INFLATE");
+    const char *env = getenv("RS_INFLATE_WARP");              // older switch: 1 = warp, 0 = bits
+    const bool use_warp = (mode && mode[0] == 'w') || (!mode && env && atoi(env) != 0);
+    const bool use_bits = (mode && mode[0] == 'b') || (!mode && env && atoi(env) == 0);
+    if (a.codec == 8 && !use_warp && !use_bits) {
+        const size_t smem = sizeof(uint16_t) * RS_T_SMEM * TDEC_THREADS;
+        RS_CUDA_OK(ctx, cudaFuncSetAttribute(inflate_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        int tblocks = (n_seg + TDEC_THREADS - 1) / TDEC_THREADS;
+        if (tblocks > ctx->sm_count * per_sm) tblocks = ctx->sm_count * per_sm;        // one wave: threads stride over the segments
+        inflate_lut_kernel<<<tblocks, TDEC_THREADS, smem, st>>>(a);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+        return RS_OK;
+    }
+    if (a.codec == 8 && use_warp) {
+        int wblocks = (n_seg + WDEC_WARPS - 1) / WDEC_WARPS;
+        if (wblocks > ctx->sm_count * 16) wblocks = ctx->sm_count * 16;                // warps stride over the segments
+        inflate_warp_kernel<<<wblocks, WDEC_WARPS * 32, 0, st>>>(a);
+        ctx->launches++;
+        RS_CUDA_OK(ctx, cudaGetLastError());
+        return RS_OK;
+    }
     decode_kernel<<<blocks, DEC_THREADS, 0, st>>>(a);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());

@@ -23,8 +23,29 @@ __device__ __forceinline__ u64 warp_sum_u64(u64 v)
     return v;
 }
 
+// Warp-cooperative staging for the thread-per-row kernels below: the 128-byte block `blk` of the 32 table rows
+// [row0, row0 + 32) (row_u4 uint4 per row) goes to tile[row][0..7] with coalesced 128-byte reads (eight lanes per row); the
+// rows are 144 bytes apart in shared memory, so that every lane then reads ITS row with conflict-free 128-bit loads.
+typedef uint4 RowTile[32][9];
+__device__ __forceinline__ void stage_block(const uint4 *__restrict__ base, long long row0, long long n_rows, int row_u4, int blk,
+                                            RowTile &tile, int lane)
+{
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int idx = 32 * j + lane, r = idx >> 3, u = idx & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row0 + r < n_rows) v = __ldg(base + (size_t)(row0 + r) * row_u4 + 8 * blk + u);
+        tile[r][u] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// K3: one warp per (road, band); lane l owns bins [8l, 8l+8)
+// K3: one THREAD per (road, band).  The row's 256 bins are walked once for count / sum / sum of squares / min / max (every
+// bin value is a compile-time constant of the unrolled walk) with the running count kept per block of 32 bins; an order
+// statistic is then located in those eight block counts and resolved by re-reading one 128-byte block (an L1 / L2 hit).
+// The rows of a warp's 32 threads are 1 KiB apart: the warp stages them block by block through shared memory (stage_block).
+// A warp-per-row form with lane-distributed bins (round 1) needed ~8x the warp instructions: two 64-bit warp scans /
+// reductions per statistic for 1 KiB of input.
 // ---------------------------------------------------------------------------------------------
 struct FinalizeArgs {
     const uint32_t *hist;
@@ -34,121 +55,123 @@ struct FinalizeArgs {
     double *stats;
 };
 
-// value of the k-th (0-based) smallest element of the multiset described by the lane-distributed bins
-__device__ __forceinline__ int order_stat(const u64 c[8], u64 excl, u64 nl, u64 k, int lane)
+// value of the k-th (0-based) smallest element of the multiset described by the row's bins; blk[i] = elements in bins
+// [0, 32 (i + 1)), bin0 = the (nodata-adjusted) count of bin 0, k < blk[7]
+__device__ __forceinline__ int order_stat(const uint4 *__restrict__ hr, const u64 (&blk)[8], uint32_t bin0, u64 k)
 {
-    const bool owner = (k >= excl) && (k < excl + nl);
-    int v = 0;
-    if (owner) {
-        u64 run = excl;
+    int B = 0;
+    u64 run = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (k < run + c[j]) { v = 8 * lane + j; break; }
-            run += c[j];
-        }
+    for (int i = 0; i < 7; i++)
+        if (blk[i] <= k) { B = i + 1; run = blk[i]; }
+    const uint4 *p = hr + 8 * B;
+    int cnt = 0;                        // bins of the block whose inclusive running count is <= k
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint4 q = __ldg(p + i);
+        if (i == 0 && B == 0) q.x = bin0;
+        run += q.x; cnt += run <= k;
+        run += q.y; cnt += run <= k;
+        run += q.z; cnt += run <= k;
+        run += q.w; cnt += run <= k;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, owner);
-    return __shfl_sync(0xffffffffu, v, m ? __ffs(m) - 1 : 0);
+    return 32 * B + min(cnt, 31);
 }
 
-__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a)
+__global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a)
 {
-    // one warp per (road, band)
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int C = a.C, NS = RS_NSTAT + a.n_pct;
-    if (wid >= (long long)a.n_roads * C) return;
-    const int road = (int)(wid / C), b_only = (int)(wid - (long long)road * C);
-    const uint32_t *hr = a.hist + (size_t)road * C * 256;
-
+    __shared__ RowTile tiles[4];
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = a.C, NS = RS_NSTAT + a.n_pct, lane = threadIdx.x & 31;
+    const long long n_rows = (long long)a.n_roads * C;
+    const bool valid = row < n_rows;
+    const int road = (int)((valid ? row : n_rows - 1) / C);
+    const uint4 *hr = reinterpret_cast<const uint4 *>(a.hist) + (size_t)(valid ? row : n_rows - 1) * 64;
     const u64 allzero = a.nzero ? (u64)a.nzero[road] : 0ull;
+    RowTile &tile = tiles[threadIdx.x >> 5];
 
-    for (int b = b_only; b <= b_only; b++) {
-        const uint4 q0 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane);
-        const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + b * 256 + 8 * lane + 4);
-        u64 c[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        if (a.mode != RS_NODATA_RAW) {
-            if (lane == 0) {
-                // NONE: rows with every band 0 are dropped (allzero = their count).  ZERO: per (road, tile) call the zeros of a
-                // band are dropped and the band is padded with zeros up to the call's longest band; over the road's calls
-                // the band keeps zeros(band) - sum over calls of min over bands of zeros(call, band)  (allzero = that sum,
-                // rs_zonal_params::min_zero)
-                if (a.mode == RS_NODATA_NONE || a.mode == RS_NODATA_ZERO) c[0] = c[0] >= allzero ? c[0] - allzero : 0ull;
-                else c[0] = 0ull;                       // RS_NODATA_ZERO_MASKED
+    u64 n = 0, s1 = 0, s2 = 0, blk[8];
+    uint32_t occ[8], bin0 = 0;          // occ[B]: which bins of block B are non-empty
+#pragma unroll
+    for (int B = 0; B < 8; B++) {
+        uint4 q[8];
+        __syncwarp();
+        stage_block(reinterpret_cast<const uint4 *>(a.hist), row - lane, n_rows, 64, B, tile, lane);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = tile[lane][i];
+        if (B == 0) {
+            // NONE: rows with every band 0 are dropped (allzero = their count).  ZERO: per (road, tile) call the zeros of a
+            // band are dropped and the band is padded with zeros up to the call's longest band; over the road's calls
+            // the band keeps zeros(band) - sum over calls of min over bands of zeros(call, band)  (allzero = that sum,
+            // rs_zonal_params::min_zero)
+            if (a.mode == RS_NODATA_NONE || a.mode == RS_NODATA_ZERO) q[0].x = q[0].x >= allzero ? (uint32_t)(q[0].x - allzero) : 0u;
+            else if (a.mode != RS_NODATA_RAW) q[0].x = 0u;          // RS_NODATA_ZERO_MASKED
+            bin0 = q[0].x;
+        }
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t c[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const u64 v = (u64)(32 * B + 4 * i + j);
+                n += c[j];
+                s1 += v * c[j];
+                s2 += v * v * c[j];
+                o |= c[j] ? (1u << (4 * i + j)) : 0u;
             }
         }
-        u64 nl = 0, s1 = 0, s2 = 0;
-        int vmin = 256, vmax = -1;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const u64 v = (u64)(8 * lane + j);
-            nl += c[j];
-            s1 += v * c[j];
-            s2 += v * v * c[j];
-            if (c[j]) { vmin = min(vmin, (int)v); vmax = max(vmax, (int)v); }
-        }
-        // exclusive prefix of nl over lanes
-        u64 incl = nl;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const u64 excl = incl - nl;
-        const u64 n = __shfl_sync(0xffffffffu, incl, 31);
-        s1 = warp_sum_u64(s1);
-        s2 = warp_sum_u64(s2);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            vmin = min(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-            vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        }
-        double *out = a.stats + ((size_t)road * C + b) * NS;
-        const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        if (n == 0) {
-            if (lane == 0) {
-                out[RS_STAT_COUNT] = 0.0;
-                for (int i = 1; i < NS; i++) out[i] = nan;
-            }
-            continue;
-        }
-        const int med_lo = order_stat(c, excl, nl, (n - 1) >> 1, lane);
-        const int med_hi = order_stat(c, excl, nl, n >> 1, lane);
-        double pv[16];
-        for (int i = 0; i < a.n_pct; i++) {
-            // numpy.percentile, method 'linear': virtual index (n-1)*q/100, _lerp between neighbours
-            const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(a.pct[i], 100.0));
-            double fl = floor(vi);
-            if (fl < 0.0) fl = 0.0;
-            u64 k0 = (u64)fl;
-            if (k0 > n - 1) k0 = n - 1;
-            const u64 k1 = k0 + 1 > n - 1 ? n - 1 : k0 + 1;
-            const double t = __dsub_rn(vi, fl);
-            const double va = (double)order_stat(c, excl, nl, k0, lane), vb = (double)order_stat(c, excl, nl, k1, lane);
-            const double d = __dsub_rn(vb, va);
-            pv[i] = t >= 0.5 ? __dsub_rn(vb, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(va, __dmul_rn(d, t));
-        }
-        if (lane == 0) {
-            const double dn = (double)n;
-            const double mean = (double)s1 / dn;
-            double sd = nan;
-            if (n > (u64)a.ddof) {
-                const unsigned __int128 num = (unsigned __int128)n * s2 - (unsigned __int128)s1 * s1;
-                const double var = (double)num / (dn * (double)(n - (u64)a.ddof));
-                sd = sqrt(var);
-            }
-            out[RS_STAT_COUNT] = dn;
-            out[RS_STAT_MIN] = (double)vmin;
-            out[RS_STAT_MAX] = (double)vmax;
-            out[RS_STAT_SUM] = (double)s1;
-            out[RS_STAT_SUMSQ] = (double)s2;
-            out[RS_STAT_MEAN] = mean;
-            out[RS_STAT_STD] = sd;
-            out[RS_STAT_MEDIAN] = ((double)med_lo + (double)med_hi) * 0.5;
-            out[RS_STAT_MARGIN] = 2.0 * sd / sqrt(dn);        // Z = 2, fct_statistics.py:58-59
-            for (int i = 0; i < a.n_pct; i++) out[RS_NSTAT + i] = pv[i];
-        }
+        blk[B] = n;
+        occ[B] = o;
     }
+    if (!valid) return;
+    double *out = a.stats + (size_t)row * NS;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (n == 0) {
+        out[RS_STAT_COUNT] = 0.0;
+        for (int i = 1; i < NS; i++) out[i] = nan;
+        return;
+    }
+    int vmin = 256, vmax = -1;
+#pragma unroll
+    for (int B = 7; B >= 0; B--)
+        if (occ[B]) vmin = 32 * B + __ffs(occ[B]) - 1;
+#pragma unroll
+    for (int B = 0; B < 8; B++)
+        if (occ[B]) vmax = 32 * B + 31 - __clz(occ[B]);
+    const int med_lo = order_stat(hr, blk, bin0, (n - 1) >> 1);
+    const int med_hi = (n & 1ull) ? med_lo : order_stat(hr, blk, bin0, n >> 1);
+    for (int i = 0; i < a.n_pct; i++) {
+        // numpy.percentile, method 'linear': virtual index (n-1)*q/100, _lerp between neighbours
+        const double vi = __dmul_rn((double)(n - 1), __ddiv_rn(a.pct[i], 100.0));
+        double fl = floor(vi);
+        if (fl < 0.0) fl = 0.0;
+        u64 k0 = (u64)fl;
+        if (k0 > n - 1) k0 = n - 1;
+        const u64 k1 = k0 + 1 > n - 1 ? n - 1 : k0 + 1;
+        const double t = __dsub_rn(vi, fl);
+        const double va = (double)order_stat(hr, blk, bin0, k0), vb = (double)order_stat(hr, blk, bin0, k1);
+        const double d = __dsub_rn(vb, va);
+        out[RS_NSTAT + i] = t >= 0.5 ? __dsub_rn(vb, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(va, __dmul_rn(d, t));
+    }
+    const double dn = (double)n;
+    const double mean = (double)s1 / dn;
+    double sd = nan;
+    if (n > (u64)a.ddof) {
+        const unsigned __int128 num = (unsigned __int128)n * s2 - (unsigned __int128)s1 * s1;
+        const double var = (double)num / (dn * (double)(n - (u64)a.ddof));
+        sd = sqrt(var);
+    }
+    out[RS_STAT_COUNT] = dn;
+    out[RS_STAT_MIN] = (double)vmin;
+    out[RS_STAT_MAX] = (double)vmax;
+    out[RS_STAT_SUM] = (double)s1;
+    out[RS_STAT_SUMSQ] = (double)s2;
+    out[RS_STAT_MEAN] = mean;
+    out[RS_STAT_STD] = sd;
+    out[RS_STAT_MEDIAN] = ((double)med_lo + (double)med_hi) * 0.5;
+    out[RS_STAT_MARGIN] = 2.0 * sd / sqrt(dn);        // Z = 2, fct_statistics.py:58-59
 }
 
 int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero, int n_roads, int channels,
@@ -164,8 +187,8 @@ int launch_finalize(rs_ctx *ctx, const uint32_t *hist, const uint32_t *n_allzero
     a.n_pct = n_pct;
     for (int i = 0; i < n_pct; i++) a.pct[i] = pct_host[i];
     a.stats = stats;
-    const int threads = 256;
-    const unsigned blocks = (unsigned)(((size_t)n_roads * channels * 32 + threads - 1) / threads);
+    const int threads = 128;
+    const unsigned blocks = (unsigned)(((size_t)n_roads * channels + threads - 1) / threads);
     finalize_kernel<<<blocks, threads, 0, st>>>(a);
     ctx->launches++;
     RS_CUDA_OK(ctx, cudaGetLastError());
@@ -182,53 +205,42 @@ struct VoteArgs {
     const int8_t *gt;
     int n_roads, n_thr, rule;
     double min_area_frac;
-    int cut[RS_MAX_THR];
+    int cut[RS_MAX_THR];        // cut-offs sorted in DESCENDING order ...
+    int idx[RS_MAX_THR];        // ... and the position of each in the caller's list
     int8_t *cover;
     double *scores;
     u64 *confusion;     // [n_thr][2][4]
 };
 
-__global__ void __launch_bounds__(256) vote_kernel(const VoteArgs a)
+// One THREAD per road.  The score bins of the two detected classes are walked once from 255 down, keeping the suffix sums
+// (pixels and score-weighted pixels with score >= bin); the cut-offs are visited in descending order as the walk reaches
+// them, so a cut-off costs its decision and nothing else.  (Round 1: a warp per road and four 64-bit warp reductions per
+// cut-off, ~10x the warp instructions.)
+__global__ void __launch_bounds__(128) vote_kernel(const VoteArgs a)
 {
     __shared__ unsigned int conf[RS_MAX_THR * 8];
     for (int i = threadIdx.x; i < RS_MAX_THR * 8; i += blockDim.x) conf[i] = 0;
     __syncthreads();
-    const int road = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (road < a.n_roads) {
-        const uint32_t *hr = a.jh + (size_t)road * 768;
-        u64 c[3][8];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const uint4 q0 = *reinterpret_cast<const uint4 *>(hr + k * 256 + 8 * lane);
-            const uint4 q1 = *reinterpret_cast<const uint4 *>(hr + k * 256 + 8 * lane + 4);
-            c[k][0] = q0.x; c[k][1] = q0.y; c[k][2] = q0.z; c[k][3] = q0.w;
-            c[k][4] = q1.x; c[k][5] = q1.y; c[k][6] = q1.z; c[k][7] = q1.w;
-        }
+    __shared__ RowTile tiles[4][2];
+    const int road = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool valid = road < a.n_roads;
+    const uint4 *jh4 = reinterpret_cast<const uint4 *>(a.jh);
+    RowTile &t1 = tiles[threadIdx.x >> 5][0], &t2 = tiles[threadIdx.x >> 5][1];
+    {
         u64 ninside = 0;
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) ninside += c[k][j];
-        ninside = warp_sum_u64(ninside);
-
-        u64 my_n[2] = {0, 0}, my_s[2] = {0, 0};     // lane i keeps the sums of cut-off i
-        for (int i = 0; i < a.n_thr; i++) {
-            const int cut = a.cut[i];
-            u64 n1 = 0, n2 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int sc = 8 * lane + j;
-                if (sc >= cut) {
-                    n1 += c[1][j]; s1 += (u64)sc * c[1][j];
-                    n2 += c[2][j]; s2 += (u64)sc * c[2][j];
-                }
+        if (a.min_area_frac > 0.0 && valid) {        // pixels of the road in all three classes
+            const uint4 *h0 = jh4 + (size_t)road * 192;
+#pragma unroll 4
+            for (int i = 0; i < 192; i++) {
+                const uint4 q = __ldg(h0 + i);
+                ninside += (u64)q.x + q.y + q.z + q.w;
             }
-            n1 = warp_sum_u64(n1); n2 = warp_sum_u64(n2);
-            s1 = warp_sum_u64(s1); s2 = warp_sum_u64(s2);
-            if (lane == i) { my_n[0] = n1; my_n[1] = n2; my_s[0] = s1; my_s[1] = s2; }
         }
-        if (lane < a.n_thr) {
-            u64 na = my_n[0], nn = my_n[1], sa = my_s[0], sn = my_s[1];
+        const int g = (a.gt && valid) ? (int)a.gt[road] : -1;
+        u64 n1 = 0, n2 = 0, s1 = 0, s2 = 0;
+        int nx = 0;
+        auto decide = [&]() {                        // cut-off nx with the current suffix sums
+            u64 na = n1, nn = n2, sa = s1, sn = s2;
             if (a.min_area_frac > 0.0) {
                 const double den = (double)(ninside ? ninside : 1ull);
                 const double fa = rint(__dmul_rn(__ddiv_rn((double)na, den), 100.0)) / 100.0;   // np.round(x, 2)
@@ -248,16 +260,38 @@ __global__ void __launch_bounds__(256) vote_kernel(const VoteArgs a)
             if (left > right) cov = RS_COVER_ARTIFICIAL;
             else if (left < right) cov = RS_COVER_NATURAL;
             if (na + nn == 0) cov = RS_COVER_UNDETECTED;
-            const size_t o = (size_t)lane * a.n_roads + road;
-            if (a.cover) a.cover[o] = (int8_t)cov;
-            if (a.scores) {
+            const int t = a.idx[nx];
+            const size_t o = (size_t)t * a.n_roads + road;
+            if (a.cover && valid) a.cover[o] = (int8_t)cov;
+            if (a.scores && valid) {
                 a.scores[3 * o + 0] = ia;
                 a.scores[3 * o + 1] = in_;
                 a.scores[3 * o + 2] = fabs(ia - in_);
             }
-            const int g = a.gt ? (int)a.gt[road] : -1;
-            if (g == 0 || g == 1) atomicAdd(&conf[lane * 8 + g * 4 + cov], 1u);
+            if (g == 0 || g == 1) atomicAdd(&conf[t * 8 + g * 4 + cov], 1u);
+            nx++;
+        };
+        while (nx < a.n_thr && a.cut[nx] > 255) decide();           // nothing reaches these cut-offs
+#pragma unroll 1
+        for (int blk = 7; blk >= 0; blk--) {
+            __syncwarp();
+            stage_block(jh4, road - lane, a.n_roads, 192, 8 + blk, t1, lane);
+            stage_block(jh4, road - lane, a.n_roads, 192, 16 + blk, t2, lane);
+            __syncwarp();
+#pragma unroll 1
+            for (int u = 7; u >= 0; u--) {
+                const uint4 q1 = t1[lane][u], q2 = t2[lane][u];
+                const uint32_t c1[4] = {q1.x, q1.y, q1.z, q1.w}, c2[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                for (int j = 3; j >= 0; j--) {
+                    const int sc = 32 * blk + 4 * u + j;
+                    n1 += c1[j]; s1 += (u64)sc * c1[j];
+                    n2 += c2[j]; s2 += (u64)sc * c2[j];
+                    while (nx < a.n_thr && a.cut[nx] >= sc) decide();
+                }
+            }
         }
+        while (nx < a.n_thr) decide();                              // cut-offs below 0: everything counts
     }
     __syncthreads();
     for (int i = threadIdx.x; i < a.n_thr * 8; i += blockDim.x)
@@ -316,10 +350,14 @@ int launch_vote(rs_ctx *ctx, const uint32_t *joint_hist, const int8_t *gt_class,
         VoteArgs a{};
         a.jh = joint_hist; a.gt = gt_class; a.n_roads = n_roads; a.n_thr = n_thr; a.rule = rule;
         a.min_area_frac = min_area_frac;
-        for (int i = 0; i < n_thr; i++) a.cut[i] = cutoffs_host[i];
+        for (int i = 0; i < n_thr; i++) {            // insertion sort, descending, stable
+            int k = i;
+            while (k > 0 && a.cut[k - 1] < cutoffs_host[i]) { a.cut[k] = a.cut[k - 1]; a.idx[k] = a.idx[k - 1]; k--; }
+            a.cut[k] = cutoffs_host[i]; a.idx[k] = i;
+        }
         a.cover = cover; a.scores = scores; a.confusion = (u64 *)confusion;
-        const int threads = 256;
-        const unsigned blocks = (unsigned)(((size_t)n_roads * 32 + threads - 1) / threads);
+        const int threads = 128;
+        const unsigned blocks = (unsigned)(((size_t)n_roads + threads - 1) / threads);
         vote_kernel<<<blocks, threads, 0, st>>>(a);
         ctx->launches++;
         RS_CUDA_OK(ctx, cudaGetLastError());

@@ -30,6 +30,17 @@ static long long run(int kind, const uint8_t *src, long long n, long long cap)
         uint16_t hot[rs::codec::RS_INFLATE_HOT], sym[rs::codec::RS_INFLATE_SYM];
         uint8_t lens[rs::codec::RS_INFLATE_LEN];
         got = rs::codec::inflate_segment(in, n, out, cap, true, hot, 1, sym, lens);
+        // the warp-per-segment decoder (one lane here) must agree on intact streams and stay inside its buffers on damaged ones
+        uint8_t *out2 = (uint8_t *)malloc(cap > 0 ? cap : 1);
+        rs::codec::WTables *t = (rs::codec::WTables *)malloc(sizeof(rs::codec::WTables));
+        const long long got2 = rs::codec::inflate_segment_warp(in, n, out2, cap, true, *t, 0);
+        if (got2 < -1 || got2 > cap || (got >= 0) != (got2 >= 0) || (got >= 0 && (got2 != got || memcmp(out, out2, got) != 0))) got = -2;
+        free(t);
+        // and the table-driven thread-per-segment decoder
+        uint16_t tab[rs::codec::RS_T_SMEM];
+        const long long got3 = rs::codec::inflate_segment_lut(in, n, out2, cap, true, tab, 1, sym, lens);
+        if (got3 < -1 || got3 > cap || (got >= 0) != (got3 >= 0) || (got >= 0 && (got3 != got || memcmp(out, out2, got) != 0))) got = -2;
+        free(out2);
     } else {
         uint32_t *tab = (uint32_t *)malloc(4096 * sizeof(uint32_t));
         uint16_t *len = (uint16_t *)malloc(4096 * sizeof(uint16_t));

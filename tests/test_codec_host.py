@@ -24,7 +24,7 @@ def lib():
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.dirname(hdr), "-o", so, src])
     L = ctypes.CDLL(so)
-    for f in (L.host_inflate, L.host_lzw):
+    for f in (L.host_inflate, L.host_inflate_warp, L.host_inflate_lut, L.host_lzw):
         f.restype = ctypes.c_longlong
         f.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong]
     return L
@@ -51,29 +51,36 @@ def _payloads():
     yield (d % 256).astype(np.uint8).tobytes()                             # predictor-2 residuals
 
 
-def test_inflate_matches_zlib(lib):
+INFLATERS = ("host_inflate", "host_inflate_warp", "host_inflate_lut")      # bit by bit / a warp per segment (one lane here) / tables
+
+
+@pytest.mark.parametrize("which", INFLATERS)
+def test_inflate_matches_zlib(lib, which):
+    inflate = getattr(lib, which)
     n = 0
     for raw in _payloads():
         for level in (0, 1, 6, 9):
             for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
                 c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strategy)
                 comp = c.compress(raw) + c.flush()
-                got, out = _run(lib.host_inflate, comp, len(raw))
+                got, out = _run(inflate, comp, len(raw))
                 assert got == len(raw) and out == raw, (len(raw), level, strategy)
                 n += 1
     assert n == 8 * 16
 
 
-def test_inflate_rejects_bad_streams(lib):
+@pytest.mark.parametrize("which", INFLATERS)
+def test_inflate_rejects_bad_streams(lib, which):
+    inflate = getattr(lib, which)
     raw = bytes(range(256)) * 40
     comp = zlib.compress(raw)
-    assert _run(lib.host_inflate, comp, len(raw) - 1)[0] == -1             # output larger than the segment may hold
-    assert _run(lib.host_inflate, comp[: len(comp) // 2], len(raw))[0] == -1        # truncated
-    assert _run(lib.host_inflate, b"\x78\x9d" + comp[2:], len(raw))[0] == -1        # header check fails
+    assert _run(inflate, comp, len(raw) - 1)[0] == -1             # output larger than the segment may hold
+    assert _run(inflate, comp[: len(comp) // 2], len(raw))[0] == -1        # truncated
+    assert _run(inflate, b"\x78\x9d" + comp[2:], len(raw))[0] == -1        # header check fails
     bad = bytearray(comp)
     bad[2] |= 0x06                                                         # block type 3
-    assert _run(lib.host_inflate, bytes(bad), len(raw))[0] == -1
-    assert _run(lib.host_inflate, b"", 10)[0] == -1
+    assert _run(inflate, bytes(bad), len(raw))[0] == -1
+    assert _run(inflate, b"", 10)[0] == -1
 
 
 def test_lzw_matches_libtiff(lib, tmp_path):
@@ -102,14 +109,16 @@ def test_lzw_matches_libtiff(lib, tmp_path):
     assert _run(lib.host_lzw, lzw_encode(bytes(1000)), 999)[0] == -1       # does not fit
 
 
-def test_inflate_checks_the_adler32_trailer(lib):
+@pytest.mark.parametrize("which", INFLATERS)
+def test_inflate_checks_the_adler32_trailer(lib, which):
+    inflate = getattr(lib, which)
     raw = np.random.default_rng(1).integers(0, 256, 20000, dtype=np.uint8).tobytes()
     comp = bytearray(zlib.compress(raw, 0))                                # stored blocks: a flipped payload byte still "decodes"
     comp[100] ^= 0x01
-    assert _run(lib.host_inflate, bytes(comp), len(raw))[0] == -1
+    assert _run(inflate, bytes(comp), len(raw))[0] == -1
     comp[100] ^= 0x01
-    assert _run(lib.host_inflate, bytes(comp), len(raw))[0] == len(raw)
-    assert _run(lib.host_inflate, bytes(comp[:-1]), len(raw))[0] == -1     # trailer cut short
+    assert _run(inflate, bytes(comp), len(raw))[0] == len(raw)
+    assert _run(inflate, bytes(comp[:-1]), len(raw))[0] == -1     # trailer cut short
 
 
 def test_corrupt_streams_never_leave_their_buffers(tmp_path):

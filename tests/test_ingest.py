@@ -177,3 +177,48 @@ def test_load_tiles_on_the_gpu(tmp_path, C, dtype):
                     got = ingest.load_tiles(paths, bidx=bidx, rescale={"smin": smin, "smax": smax, "f32": f32}).pixels
                     exp = oraster.rescale_u16_to_u8(np.stack(imgs)[..., [1, 2, 3, 0]], smin, smax, f32)
                     assert got.dtype == np.uint8 and np.array_equal(got, exp), (v, f32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["lut", "warp", "bits"])
+def test_device_inflate_matches_zlib(mode, monkeypatch):
+    """rs_decode_segments_host on zlib streams of every compression level and strategy (stored, fixed and dynamic blocks, maximal
+    matches at distance 1, window-length distances, tiny alphabets, segments far larger than a strip) in ONE batch: byte for
+    byte what zlib gives -- the three decoders (tables, a thread per segment; a warp per segment; bit by bit); damaged
+    streams are reported (RS_ERR_CODEC), the others of the batch untouched by them"""
+    import zlib
+    from test_codec_host import _payloads
+    from proj_roadsurf_b200._native import NativeError
+    from proj_roadsurf_b200.engine import Engine
+    monkeypatch.setenv("RS_INFLATE", mode)
+    raws, comps = [], []
+    for raw in _payloads():
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                c = zlib.compressobj(level, zlib.DEFLATED, 15, 9, strategy)
+                comps.append(c.compress(raw) + c.flush())
+                raws.append(raw)
+    rng = np.random.default_rng(23)
+    for k in range(300):                                                   # many small strips of varied content and alignment
+        n = int(rng.integers(1, 7000))
+        kind = k % 3
+        raw = (rng.integers(0, 256, n, dtype=np.uint8) if kind == 0 else np.clip(rng.normal(110, 6, n), 0, 255).astype(np.uint8)
+               if kind == 1 else (np.arange(n) // int(rng.integers(1, 40)) % 7).astype(np.uint8)).tobytes()
+        comps.append(zlib.compress(raw, int(rng.integers(0, 10))))
+        raws.append(raw)
+    comp = np.frombuffer(b"".join(comps), np.uint8)
+    comp_off = np.concatenate([[0], np.cumsum([len(c) for c in comps])]).astype(np.int64)
+    raw_off = np.concatenate([[0], np.cumsum([len(r) for r in raws])]).astype(np.int64)
+    eng = Engine(0)
+    out = eng.decode_segments_host(comp, comp_off, 8, raw_off)
+    want = np.frombuffer(b"".join(raws), np.uint8)
+    for i in range(len(raws)):
+        assert np.array_equal(out[raw_off[i]:raw_off[i + 1]], want[raw_off[i]:raw_off[i + 1]]), (i, len(raws[i]))
+    # one damaged stream in the batch
+    bad = comp.copy()
+    victim = len(comps) - 7
+    bad[comp_off[victim] + len(comps[victim]) // 2] ^= 0x10
+    with pytest.raises(NativeError) as ei:
+        eng.decode_segments_host(bad, comp_off, 8, raw_off)
+    assert ei.value.status == -10
+    eng.close()
