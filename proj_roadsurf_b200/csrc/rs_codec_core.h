@@ -792,23 +792,30 @@ struct TInflate {
         uint8_t *dp = dst + out;
         const uint8_t *sp = dp - d;
         out += len;
-        int i = 0;
-        if (d >= len) {
-            // source and destination do not overlap: four loads, then four stores (a byte loop would wait for every store to
-            // come back through memory before the next load)
-            for (; i + 4 <= len; i += 4) {
-                const uint8_t v0 = sp[i], v1 = sp[i + 1], v2 = sp[i + 2], v3 = sp[i + 3];
-                dp[i] = v0; dp[i + 1] = v1; dp[i + 2] = v2; dp[i + 3] = v3;
-                s1 += v0; s2 += s1; s1 += v1; s2 += s1; s1 += v2; s2 += s1; s1 += v3; s2 += s1;
+        // Every byte a match reads was stored a moment ago and comes back through the memory system: the copy is arranged so
+        // that a match costs one such round trip per 8 bytes (8 independent loads, then 8 stores), not one per byte.
+        if (d >= 8 || d >= len) {                     // an 8-byte piece never reads what it writes
+            for (int i = 0; i < len; i += 8) {
+                const int m = len - i < 8 ? len - i : 8;
+                uint8_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = k < m ? sp[i + k] : (uint8_t)0;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (k < m) { dp[i + k] = v[k]; s1 += v[k]; s2 += s1; }
             }
-        } else if (d == 1) {                                     // a run of one byte
-            const uint8_t v = sp[0];
-            for (; i < len; i++) { dp[i] = v; s1 += v; s2 += s1; }
-        }
-        for (; i < len; i++) {
-            const uint8_t v = sp[i];
-            dp[i] = v;
-            s1 += v; s2 += s1;
+        } else {                                      // a pattern of d < 8 bytes repeated: read once, kept in a register
+            unsigned long long pat = 0;
+#pragma unroll
+            for (int k = 0; k < 7; k++)
+                if (k < d) pat |= (unsigned long long)sp[k] << (8 * k);
+            int j = 0;
+            for (int i = 0; i < len; i++) {
+                const uint8_t v = (uint8_t)(pat >> (8 * j));
+                dp[i] = v;
+                s1 += v; s2 += s1;
+                j = j + 1 == (int)d ? 0 : j + 1;
+            }
         }
     }
 
