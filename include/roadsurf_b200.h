@@ -447,7 +447,8 @@ int rs_assemble_tiles_host(rs_ctx *ctx, const uint8_t *raw, int32_t n_tiles, int
 
 /*
  * Tile ingest, decompression on the device: the compressed segments (strips / internal tiles) of a batch of TIFFs, concatenated
- * in comp[comp_off[s] .. comp_off[s + 1]), are decoded one thread per segment into raw[raw_off[s] .. raw_off[s + 1]); a segment
+ * in comp[comp_off[s] .. comp_off[s + 1]), are decoded one decoder per segment (DEFLATE: table-driven, the 32 decoders of a warp
+ * stepped together; RS_INFLATE = lut | warp | bits selects the decoder) into raw[raw_off[s] .. raw_off[s + 1]); a segment
  * must decode to exactly that many bytes (libtiff: rows * row bytes), otherwise RS_ERR_CODEC (latched for _dev, returned by
  * _host).  codec = the TIFF Compression tag: 1 none, 5 LZW (MSB-first, early change), 8 / 32946 zlib-wrapped DEFLATE.  The
  * compressed bytes are what crosses the host link; `raw` then feeds rs_assemble_tiles_* (predictor, byte order, bands, rescale).

@@ -4,7 +4,7 @@ The reference reads every tile with ``rasterio.open(tile).read()`` inside its pa
 and gets the tiles from a tile server that selects and reorders bands (``bidx=2&bidx=3&bidx=4&bidx=1``,
 config/config_stats.yaml:39) after tif2cog's 16 -> 8 bit rescale (scripts/preprocessing/tif2cog.py:260-270).  Here the
 host only parses the TIFF directories; the compressed segments go to the device as they are in the files and are decoded
-there (rs_decode_segments: DEFLATE and TIFF LZW, a thread per segment), and everything per pixel -- TIFF predictor 2, byte
+there (rs_decode_segments: DEFLATE through table-driven decoders stepped warp-wide, TIFF LZW a thread per segment), and everything per pixel -- TIFF predictor 2, byte
 order, band-sequential -> interleaved, band selection, rescale -- is one kernel over the whole batch (rs_assemble_tiles_*).
 ``load_tiles(..., device_decode=False)`` keeps the earlier host inflate (zlib, a thread per file) as the comparison path.
 
