@@ -374,6 +374,24 @@ def test_finalize_stats_nodata_conventions(eng, mode, omode):
 # vote + confusion + F1
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("rule", ["count", "score"])
+def test_vote_cutoffs_in_any_order(eng, rule):
+    """vote_kernel visits the cut-offs in descending order while it walks the score bins down: unsorted, repeated and
+    out-of-range cut-offs (above 255: nothing counts; 0 and below: everything counts) land in the caller's positions"""
+    g = synth.Grid(6, 6)
+    rr = synth.ribbon_roads(g, 150, seed=43)             # more roads than a block of the kernel: a partial last block
+    tiles = synth.host_tiles(g, 2, "class_score")
+    jh, _ = eng.zonal_hist_host(rr.roads, TileBatch.from_arrays(tiles, g.transforms()), rr.pairs, hist_mode="class_score")
+    cuts = np.array([128, 3, 255, 0, 300, 128, -5, 254, 17, 256, 1], np.int32)
+    cover, scores, conf, _ = eng.vote_metrics_host(jh, rr.gt_class, cuts, rule=rule, min_area_frac=0.05)
+    for i, c in enumerate(cuts):
+        ocov, ia, inn, _ = ovote.raster_vote(jh, int(c), rule, 0.05)
+        assert np.array_equal(cover[i], ocov.astype(np.int8)), (i, c)
+        assert np.array_equal(conf[i], ovote.confusion(ocov, rr.gt_class)), (i, c)
+        np.testing.assert_allclose(scores[i, :, 0], ia, rtol=1e-12)
+        np.testing.assert_allclose(scores[i, :, 1], inn, rtol=1e-12)
+
+
+@pytest.mark.parametrize("rule", ["count", "score"])
 @pytest.mark.parametrize("min_area_frac", [0.0, 0.05])
 def test_vote_metrics_sweep(eng, rule, min_area_frac):
     g = synth.Grid(8, 8)
