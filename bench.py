@@ -548,7 +548,15 @@ def run_b200(args):
     eng.sync_status()
     ms = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
     kms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        # every rank's own figures next to the maxima: kernel ms, step ms, pairs and road pixels of its shard
+        mine = torch.tensor([float(kms.item()), float(ms.item()) / args.steps, float(sh.pairs.n_pairs), float(hist[:sh.n_own, 0].sum().item())],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"kernel_ms": [round(float(t[0]), 4) for t in allr], "step_ms": [round(float(t[1]), 4) for t in allr],
+                    "pairs": [int(t[2]) for t in allr], "own_road_pixels": [int(t[3]) for t in allr]}
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
     ms_total, kernel_ms = float(ms.item()), float(kms.item())
@@ -790,6 +798,8 @@ def run_b200(args):
         }
         if legs is not None:
             line["configs"] = legs
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         print(json.dumps(line))
     eng.close()
     if world > 1:
