@@ -540,6 +540,9 @@ RS_HD inline long long inflate_segment_warp(const uint8_t *src, long long n, uin
 #ifndef RS_T_DISTBITS
 #define RS_T_DISTBITS 5
 #endif
+#ifndef RS_T_INLINE_SUM_MAX
+#define RS_T_INLINE_SUM_MAX (1ll << 28)   // longest segment whose Adler-32 sums stay unreduced in 64 bits (tests lower it)
+#endif
 enum { RS_T_SMEM = (1 << RS_T_LITBITS) + (1 << RS_T_DISTBITS) + 64 };    // strided uint16 elements per decoder
 
 struct TBits {                        // LSB-first bit reader over [src, src + n), fed by aligned 32-bit words, one word ahead
@@ -683,7 +686,7 @@ struct TInflate {
         b.base = src - ((uintptr_t)src & 3u);
         b.n = n;
         dst = dst_; cap = cap_; out = 0; last = 0; zlib = zlib_wrapper; lens = lens_;
-        s1 = 1; s2 = 0; inline_sum = cap_ <= (1ll << 28);
+        s1 = 1; s2 = 0; inline_sum = cap_ <= RS_T_INLINE_SUM_MAX;
         lit = TCode{tab, tab + ((1 << RS_T_LITBITS) + (1 << RS_T_DISTBITS)) * stride, sym, RS_T_LITBITS, stride};
         dist = TCode{tab + (1 << RS_T_LITBITS) * stride, lit.count + 16 * stride, sym + 288, RS_T_DISTBITS, stride};
         tmp = lit.count + 32 * stride;

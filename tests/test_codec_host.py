@@ -30,6 +30,27 @@ def lib():
     return L
 
 
+def test_long_segments_sum_their_output_again(tmp_path):
+    """segments longer than RS_T_INLINE_SUM_MAX bytes (2^28 in the product) leave the unreduced inline Adler-32 sums and sum
+    their output again in the trailer: the same source built with the limit at 1 000 bytes"""
+    so = str(tmp_path / "libcodec_small.so")
+    src = os.path.join(HERE, "native", "codec_host.cpp")
+    hdr = os.path.join(ROOT, "proj_roadsurf_b200", "csrc", "rs_codec_core.h")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DRS_T_INLINE_SUM_MAX=1000", "-I", os.path.dirname(hdr),
+                           "-o", so, src])
+    L = ctypes.CDLL(so)
+    L.host_inflate_lut.restype = ctypes.c_longlong
+    L.host_inflate_lut.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong]
+    rng = np.random.default_rng(3)
+    for n in (10, 999, 1000, 1001, 70000):
+        raw = np.clip(rng.normal(110, 6, n), 0, 255).astype(np.uint8).tobytes()
+        comp = bytearray(zlib.compress(raw, 6))
+        got, out = _run(L.host_inflate_lut, bytes(comp), n)
+        assert got == n and out == raw, n
+        comp[-1] ^= 0x01                                                   # a wrong checksum is still caught
+        assert _run(L.host_inflate_lut, bytes(comp), n)[0] == -1, n
+
+
 def _run(fn, comp: bytes, cap: int):
     out = np.zeros(max(cap, 1), np.uint8)
     got = fn(comp, len(comp), out.ctypes.data, cap)
