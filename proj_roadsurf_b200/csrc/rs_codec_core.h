@@ -661,6 +661,19 @@ RS_HD inline int t_decode(TBits &b, const TCode &h)           // needs >= 15 bit
     return -1;
 }
 
+// bytes [i, min(i + N, len)) of a match: N independent loads, then the stores and the Adler-32 sums in order
+template <int N>
+RS_HD inline void t_piece(const uint8_t *sp, uint8_t *dp, int i, int len, unsigned long long &s1, unsigned long long &s2)
+{
+    const int m = len - i < N ? len - i : N;
+    uint8_t v[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] = k < m ? sp[i + k] : (uint8_t)0;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        if (k < m) { dp[i + k] = v[k]; s1 += v[k]; s2 += s1; }
+}
+
 // The decoder as a state machine, so that the 32 decoders of a warp can be STEPPED TOGETHER (rs_codec.cu): written as one
 // function with its loops inside, the lanes of a warp part at the first data-dependent branch and, with the early exits of a
 // decoder, never meet again before the function returns -- one active lane per instruction, measured.  Stepped from a
@@ -796,21 +809,17 @@ struct TInflate {
         const uint8_t *sp = dp - d;
         out += len;
         // Every byte a match reads was stored a moment ago and comes back through the memory system: the copy is arranged so
-        // that a match costs one such round trip per 8 bytes (8 independent loads, then 8 stores), not one per byte.
-        if (d >= 8 || d >= len) {                     // an 8-byte piece never reads what it writes
-            for (int i = 0; i < len; i += 8) {
-                const int m = len - i < 8 ? len - i : 8;
-                uint8_t v[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = k < m ? sp[i + k] : (uint8_t)0;
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if (k < m) { dp[i + k] = v[k]; s1 += v[k]; s2 += s1; }
-            }
-        } else {                                      // a pattern of d < 8 bytes repeated: read once, kept in a register
+        // that a match costs one such round trip per piece of 4 or 8 bytes (independent loads, then the stores), not one per
+        // byte.
+        if (d >= 8 || d >= len) {                     // no piece reads what it writes: 4 bytes, then 8 at a time
+            t_piece<4>(sp, dp, 0, len, s1, s2);       // most matches of a fast encoder are 3 or 4 bytes long
+            for (int i = 4; i < len; i += 8) t_piece<8>(sp, dp, i, len, s1, s2);
+        } else if (d >= 4) {
+            for (int i = 0; i < len; i += 4) t_piece<4>(sp, dp, i, len, s1, s2);
+        } else {                                      // a pattern of d < 4 bytes repeated: read once, kept in a register
             unsigned long long pat = 0;
 #pragma unroll
-            for (int k = 0; k < 7; k++)
+            for (int k = 0; k < 3; k++)
                 if (k < d) pat |= (unsigned long long)sp[k] << (8 * k);
             int j = 0;
             for (int i = 0; i < len; i++) {
