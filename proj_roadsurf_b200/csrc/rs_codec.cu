@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(WDEC_WARPS * 32, 4) inflate_warp_kernel(const 
 
 // DEFLATE, a thread per segment with first-level tables in shared memory (rs_codec_core.h inflate_segment_lut): column t of the
 // block's array is thread t's tables; the threads of a warp take their segments in step
+#ifndef RS_T_MATCH_BATCH
+#define RS_T_MATCH_BATCH 16          // lanes with a waiting match that start a round of copies
+#endif
 #ifndef RS_TDEC_THREADS
 #define RS_TDEC_THREADS 64
 #endif
@@ -124,10 +127,23 @@ __global__ void __launch_bounds__(TDEC_THREADS) inflate_lut_kernel(const CodecAr
             }
             bool more = false;
             for (;;) {                              // symbols, until every lane's block ends (or one reaches its next header)
-                const bool act = d.state == TInflate::SYMBOLS;
-                if (!__any_sync(0xffffffffu, act)) break;
-                if (act) d.symbol();
-                if (__any_sync(0xffffffffu, d.state == TInflate::HEADER)) { more = true; break; }
+                // A decoded match is not copied at once: its lane waits (state MATCH) until half of the warp's decoders hold
+                // one or no lane can decode on -- then the waiting copies run together.  Every step used to pay the match
+                // path (a fifth of the symbols of a fast encoder's stream are matches, so some lane always had one) at a
+                // quarter of the lanes and one trip through memory.
+                const unsigned am = __ballot_sync(0xffffffffu, d.state == TInflate::SYMBOLS);
+                const unsigned mm = __ballot_sync(0xffffffffu, d.state == TInflate::MATCH);
+                if (!am && !mm) break;
+                if (__popc(mm) >= RS_T_MATCH_BATCH || !am) {
+                    if (d.state == TInflate::MATCH) d.copy_match();
+                    continue;
+                }
+                if (d.state == TInflate::SYMBOLS) d.symbol();
+                if (__any_sync(0xffffffffu, d.state == TInflate::HEADER)) {
+                    if (d.state == TInflate::MATCH) d.copy_match();     // (MATCH lanes are in SYMBOLS again before the headers)
+                    more = true;
+                    break;
+                }
             }
             if (!more && !__any_sync(0xffffffffu, d.state == TInflate::HEADER)) break;
         }

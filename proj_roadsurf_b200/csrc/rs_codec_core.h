@@ -678,9 +678,9 @@ RS_HD inline void t_piece(const uint8_t *sp, uint8_t *dp, int i, int len, unsign
 // function with its loops inside, the lanes of a warp part at the first data-dependent branch and, with the early exits of a
 // decoder, never meet again before the function returns -- one active lane per instruction, measured.  Stepped from a
 // warp-uniform loop (a vote per step) they reconverge after every symbol.
-//   begin -> { header -> symbol* }* -> trailer;   state: what the decoder needs next
+//   begin -> { header -> { symbol [-> copy_match] }* }* -> trailer;   state: what the decoder needs next
 struct TInflate {
-    enum { HEADER = 0, SYMBOLS = 1, TRAILER = 2, DONE = 3, FAIL = 4 };
+    enum { HEADER = 0, SYMBOLS = 1, TRAILER = 2, DONE = 3, FAIL = 4, MATCH = 5 };     // MATCH: a decoded match waits to be copied
     TBits b;
     TCode lit, dist;
     uint16_t *tmp;
@@ -689,6 +689,8 @@ struct TInflate {
     long long cap, out;
     unsigned long long s1, s2;        // Adler-32 sums of the output so far, not reduced (inline: segments up to 2^28 bytes)
     int state, last;
+    int mlen;                         // MATCH: length and distance of the waiting match
+    long long mdist;
     bool zlib, inline_sum;
 
     // tab: RS_T_SMEM strided uint16; sym: RS_INFLATE_SYM uint16; lens_: RS_INFLATE_LEN uint8
@@ -781,7 +783,7 @@ struct TInflate {
         state = SYMBOLS;
     }
 
-    // one literal, match or end-of-block code
+    // one literal, match (decoded and checked, not yet copied: state MATCH) or end-of-block code
     RS_HD inline void symbol()
     {
         b.refill();
@@ -805,6 +807,18 @@ struct TInflate {
         if (ds < 0 || ds >= 30) { state = FAIL; return; }
         const long long d = DIST_BASE[ds] + (long long)b.get(DIST_EXTRA[ds]);
         if (d > out || out + len > cap || b.over()) { state = FAIL; return; }
+        mlen = len;
+        mdist = d;
+        state = MATCH;
+    }
+
+    // the copy of the match decoded by symbol().  Apart from the stepping kernel's reasons (the copies of a warp's decoders run
+    // together, at most one trip through memory for all of them), a decoder is simply symbol(); copy_match() in turn.
+    RS_HD inline void copy_match()
+    {
+        const int len = mlen;
+        const long long d = mdist;
+        state = SYMBOLS;
         uint8_t *dp = dst + out;
         const uint8_t *sp = dp - d;
         out += len;
@@ -864,8 +878,9 @@ RS_HD inline long long inflate_segment_lut(const uint8_t *src, long long n, uint
 {
     TInflate d;
     d.begin(src, n, dst, cap, zlib_wrapper, tab, stride, sym, lens);
-    while (d.state == TInflate::HEADER || d.state == TInflate::SYMBOLS) {
+    while (d.state == TInflate::HEADER || d.state == TInflate::SYMBOLS || d.state == TInflate::MATCH) {
         if (d.state == TInflate::HEADER) d.header();
+        else if (d.state == TInflate::MATCH) d.copy_match();
         else d.symbol();
     }
     if (d.state == TInflate::TRAILER) d.trailer();
