@@ -52,6 +52,9 @@ def parse():
                     "(N = 8 is the canton configuration); strong: that much IN TOTAL, sharded over the GPUs (efficiency = T1 / (N TN))")
     ap.add_argument("--balance", default="pairs", choices=["tiles", "pairs"], help="shard cuts: equal tile counts, or tile ranges "
                     "holding equal numbers of (road, tile) pairs")
+    ap.add_argument("--shard-shift", type=int, default=0, help="rank r works on shard (r + shift) mod N: tells a slow shard from a slow GPU")
+    ap.add_argument("--plan-world", type=int, default=0, help="N = 1 only: plan the shards of a PLAN_WORLD-GPU weak-scaling run and time shard "
+                    "--shard-shift alone on this GPU (boundary rows stay partial: no merge, no oracle check)")
     ap.add_argument("--no-legs", action="store_true", help="skip the full-size legs of the other BASELINE configurations (N = 1)")
     ap.add_argument("--leg-steps", type=int, default=5)
     ap.add_argument("--wide-grid", type=int, default=64, help="configs[4] leg: tiles per side of the 1024 px lattice (64 -> 4096 tiles)")
@@ -495,8 +498,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    grid, rr = build_inputs(args, world, rank, dist if world > 1 else None, dev)
-    sh = plan_shards(rr.roads, rr.pairs, grid.n_tiles, world, only_rank=rank, balance=args.balance)[rank]
+    pw = args.plan_world if (world == 1 and args.plan_world > 1) else world
+    grid, rr = build_inputs(args, pw, rank, dist if world > 1 else None, dev)
+    shard = (rank + args.shard_shift) % pw
+    sh = plan_shards(rr.roads, rr.pairs, grid.n_tiles, pw, only_rank=shard, balance=args.balance)[shard]
     n_tiles = sh.tile_hi - sh.tile_lo
     tile_idx = np.arange(sh.tile_lo, sh.tile_hi)
     gt = grid.transforms(tile_idx)
@@ -506,7 +511,7 @@ def run_b200(args):
     kind = {"uniform": 0, "asphalt": 1}[args.kind]
     dt_ = eng.synth_tiles_dev(grid.keys(tile_idx), H, W, C, kind=kind, gt=gt)
     dr, dp = eng.upload_roads(sh.roads), eng.upload_pairs(sh.pairs)
-    slot = torch.from_numpy(sh.slot).to(dev) if world > 1 else None
+    slot = torch.from_numpy(sh.slot).to(dev) if pw > 1 else None
     hist = torch.zeros((sh.n_rows, C, 256), dtype=torch.int32, device=dev)
     nz = torch.zeros((sh.n_rows,), dtype=torch.int32, device=dev)
     stats = torch.empty((sh.n_rows, C, 9), dtype=torch.float64, device=dev)
@@ -555,7 +560,7 @@ def run_b200(args):
                             dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = {"kernel_ms": [round(float(t[0]), 4) for t in allr], "step_ms": [round(float(t[1]), 4) for t in allr],
+        per_rank = {"shard": [(r + args.shard_shift) % world for r in range(world)], "kernel_ms": [round(float(t[0]), 4) for t in allr], "step_ms": [round(float(t[1]), 4) for t in allr],
                     "pairs": [int(t[2]) for t in allr], "own_road_pixels": [int(t[3]) for t in allr]}
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
