@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--shard-shift", type=int, default=0, help="rank r works on shard (r + shift) mod N: tells a slow shard from a slow GPU")
     ap.add_argument("--plan-world", type=int, default=0, help="N = 1 only: plan the shards of a PLAN_WORLD-GPU weak-scaling run and time shard "
                     "--shard-shift alone on this GPU (boundary rows stay partial: no merge, no oracle check)")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: the statistics of a rank's own rows run under the all-reduce of the "
+                    "boundary rows on a second stream (measured at N = 2: no gain, 9.46 vs 9.45 ms per step -- off by default)")
     ap.add_argument("--no-legs", action="store_true", help="skip the full-size legs of the other BASELINE configurations (N = 1)")
     ap.add_argument("--leg-steps", type=int, default=5)
     ap.add_argument("--wide-grid", type=int, default=64, help="configs[4] leg: tiles per side of the 1024 px lattice (64 -> 4096 tiles)")
@@ -517,6 +519,10 @@ def run_b200(args):
     stats = torch.empty((sh.n_rows, C, 9), dtype=torch.float64, device=dev)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
+    overlap = world > 1 and args.overlap and sh.n_boundary > 0 and sh.n_own > 0
+    side = torch.cuda.Stream(device=dev) if overlap else None
+    ev_k = torch.cuda.Event() if overlap else None
+
     def step(i=None):
         if world > 1:                       # boundary rows of roads this rank does not hold must be zero before the sum
             hist[sh.n_own:].zero_()
@@ -526,6 +532,18 @@ def run_b200(args):
         eng.zonal_hist_dev(dr, dt_, dp, road_slot=slot, out=(hist, nz), check=False)
         if i is not None:
             ev[i][1].record()
+        if overlap:
+            # the rows of this rank's own roads are final when the kernel ends: their statistics run while the boundary rows
+            # are summed over the ranks on a second stream; the statistics of the boundary rows follow the sum
+            main = torch.cuda.current_stream()
+            ev_k.record(main)
+            side.wait_event(ev_k)
+            with torch.cuda.stream(side):
+                merge_boundary(hist, nz, sh.n_own, engine=eng)
+            eng.finalize_stats_dev(hist[:sh.n_own], nz[:sh.n_own], nodata_mode="none", ddof=1, out=stats[:sh.n_own], check=False)
+            main.wait_stream(side)
+            eng.finalize_stats_dev(hist[sh.n_own:], nz[sh.n_own:], nodata_mode="none", ddof=1, out=stats[sh.n_own:], check=False)
+            return
         merge_boundary(hist, nz, sh.n_own, engine=eng)
         eng.finalize_stats_dev(hist, nz, nodata_mode="none", ddof=1, out=stats, check=False)
 
