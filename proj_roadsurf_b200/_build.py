@@ -12,7 +12,8 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("ROADSURF_B200_LIB") or os.path.join(LIB_DIR, "libroadsurf_b200.so")   # env: an experiment build
 SOURCES = ["rs_zonal.cu", "rs_tables.cu", "rs_extract.cu", "rs_pairs.cu", "rs_api.cu", "rs_comm.cu", "rs_wide.cu", "rs_fstats.cu", "rs_codec.cu",
            "rs_hostcopy.cu"]
-HEADERS = [os.path.join(CSRC, "rs_internal.h"), os.path.join(CSRC, "rs_raster.cuh"), os.path.join(ROOT, "include", "roadsurf_b200.h")]
+HEADERS = [os.path.join(CSRC, "rs_internal.h"), os.path.join(CSRC, "rs_raster.cuh"), os.path.join(CSRC, "rs_codec_core.h"),
+           os.path.join(ROOT, "include", "roadsurf_b200.h")]
 
 # -fmad=false: the rounding of every float64 operation of the rasterizer is part of the
 # specification (GDAL evaluates a*b+c with separate multiply and add on x86-64).
