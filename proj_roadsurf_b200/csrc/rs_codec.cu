@@ -1,13 +1,16 @@
 // Tile ingest, decompression on the device: the compressed strips / internal tiles of a batch of GeoTIFFs cross
-// the host link as they are in the files and are decoded here, one thread per segment, straight into the sample buffer
+// the host link as they are in the files and are decoded here, one decoder per segment, straight into the sample buffer
 // rs_assemble_tiles_* reads (predictor, byte order, band selection and the 16 -> 8 bit rescale follow in assemble_kernel).
 // This is what rasterio.open(tile).read() does through libtiff inside the reference's pair loop
-// (scripts/functions/fct_misc.py:76-77; the tiles of config/config_stats.yaml:39 are deflate- or LZW-compressed COGs).
+// (scripts/functions/fct_misc.py:76-77; the tiles of config/config_stats.yaml:39 come from a tile server over COGs).
 //
-//   codec 8 / 32946  zlib-wrapped DEFLATE (RFC 1950 / 1951): stored, fixed and dynamic Huffman blocks; canonical codes are
-//                    decoded bit by bit from per-length counts, which live in SHARED memory (column t of the block's array
-//                    belongs to thread t; symbol lists and code lengths in local memory); matches copy from the output itself
-//                    (the 32 KiB window is the already written part of the segment); the Adler-32 trailer is checked
+//   codec 8 / 32946  zlib-wrapped DEFLATE (RFC 1950 / 1951): stored, fixed and dynamic Huffman blocks; matches copy from the
+//                    output itself (the 32 KiB window is the already written part of the segment); the Adler-32 trailer is
+//                    checked.  Three decoders (RS_INFLATE, rs_codec_core.h):
+//                      lut   inflate_lut_kernel (default): a thread per segment, first-level code tables as shared-memory
+//                            columns, the 32 decoders of a warp stepped together as state machines
+//                      warp  inflate_warp_kernel: a warp per segment, one decoder's state uniform over the lanes
+//                      bits  decode_kernel: a thread per segment, every code walked bit by bit through the per-length counts
 //   codec 5          TIFF LZW (MSB-first codes of 9 - 12 bits, ClearCode 256, EOI 257, the "early change" of libtiff); the
 //                    string table (4096 x 6 bytes per decoder) lives in a scratch buffer, decoders run grid-strided
 //   codec 1          none: a copy
