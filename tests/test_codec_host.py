@@ -179,3 +179,33 @@ def test_corrupt_streams_never_leave_their_buffers(tmp_path):
     intact, mutated, accepted = map(int, res.stdout.split())
     assert intact == n_streams and mutated == n_streams * rounds
     assert accepted < mutated                                             # most corruptions are noticed (not all can be: LZW has no checksum)
+
+
+def test_inflate_random_streams_property(lib):
+    """hypothesis: byte strings of mixed structure (runs, repeated phrases, noise, tiny alphabets) at a random level, strategy and
+    memLevel -- which moves the block boundaries and the code lengths -- decode to themselves through all three decoders, and a
+    capacity one byte short is refused"""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    piece = st.one_of(
+        st.binary(min_size=0, max_size=300),                                                  # noise
+        st.builds(lambda b, n: bytes([b]) * n, st.integers(0, 255), st.integers(1, 2000)),    # runs: distance-1 matches
+        st.builds(lambda w, n: w * n, st.binary(min_size=1, max_size=40), st.integers(1, 60)),    # phrases: short distances
+        st.builds(lambda n, k, seed: bytes(np.random.default_rng(seed).integers(0, k, n, dtype=np.uint8)),
+                  st.integers(1, 3000), st.integers(1, 6), st.integers(0, 2 ** 31)))          # tiny alphabets: short codes
+
+    @hyp.settings(max_examples=120, deadline=None)
+    @hyp.given(st.lists(piece, min_size=0, max_size=12), st.integers(0, 9),
+               st.sampled_from([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED]), st.integers(1, 9))
+    def check(pieces, level, strategy, mem):
+        raw = b"".join(pieces)
+        c = zlib.compressobj(level, zlib.DEFLATED, 15, mem, strategy)
+        comp = c.compress(raw) + c.flush()
+        for which in INFLATERS:
+            got, out = _run(getattr(lib, which), comp, len(raw))
+            assert got == len(raw) and out == raw, (which, len(raw), level, strategy, mem)
+            if raw:
+                assert _run(getattr(lib, which), comp, len(raw) - 1)[0] == -1, which
+
+    check()
